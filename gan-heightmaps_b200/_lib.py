@@ -1,0 +1,92 @@
+"""ctypes binding of libhmgan.so (include/hmgan.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, the
+product path raises.  Build with ``python __graft_entry__.py build`` or
+``make -C gan-heightmaps_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhmgan.so")
+
+F32, F16 = 0, 1
+ACT = {"linear": 0, "leaky_rectify": 1, "rectify": 2, "sigmoid": 3, "tanh": 4}
+UP_NONE, UP_NEAREST2, UP_BILINEAR2 = 0, 1, 2
+
+
+class HmError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("dtype", "B", "H", "W", "C1", "C2", "up", "kh", "kw", "stride", "pad", "transposed",
+                 "Ho", "Wo", "Cout", "oH", "oW", "os", "ou", "ov", "split", "act")] + \
+               [("slope", C.c_float), ("accumulate", C.c_int32)]
+
+
+class TcConvPlan(C.Structure):
+    _fields_ = [("opaque", C.c_uint8 * 2048)]
+
+
+_P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+_PROTOS = {
+    "hm_version": ([], C.c_int),
+    "hm_last_error_string": ([], C.c_char_p),
+    "hm_device_supported": ([], C.c_int),
+    "hm_conv_gather": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "hm_conv_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
+    "hm_pack_conv_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_unpack_conv_wgrad": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_bn_stats": ([_P, _I, _LL, _I, _P, _P], C.c_int),
+    "hm_bn_finalize": ([_P, _LL, _I, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P], C.c_int),
+    "hm_bn_apply_act": ([_P, _P, _I, _LL, _I, _P, _P, _I, _F, _P], C.c_int),
+    "hm_bn_bwd_reduce": ([_P, _P, _P, _I, _LL, _I, _P, _P, _I, _F, _P, _P], C.c_int),
+    "hm_bn_bwd_apply": ([_P, _P, _P, _P, _I, _LL, _I, _P, _P, _P, _I, _F, _P, _P, _P, _P], C.c_int),
+    "hm_act_bwd": ([_P, _P, _P, _I, _LL, _I, _F, _I, _P], C.c_int),
+    "hm_col_sum": ([_P, _I, _LL, _I, _P, _P], C.c_int),
+    "hm_maxpool2_fwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_maxpool2_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P], C.c_int),
+    "hm_upsample2_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_upsample2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_nhwc_to_nchw": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_cast": ([_P, _I, _P, _I, _LL, _P], C.c_int),
+    "hm_adv_loss": ([_P, _P, _I, _LL, _I, _I, _F, _I, _I, _F, _F, _I, _P, _P], C.c_int),
+    "hm_recon_loss": ([_P, _P, _P, _I, _LL, _I, _F, _F, _I, _P, _P], C.c_int),
+    "hm_rmsprop": ([_P, _P, _P, _LL, _P, _F, _F, _F, _P], C.c_int),
+    "hm_adam": ([_P, _P, _P, _P, _LL, _P, _F, _F, _F, _I, _F, _P], C.c_int),
+}
+
+_lib = None
+
+
+def load():
+    """Load libhmgan.so and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HmError("libhmgan.so is not built (%s missing); run `python __graft_entry__.py build`. "
+                      "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (args, res) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise HmError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise HmError("%s failed (%d): %s" % (name, rc, lib.hm_last_error_string().decode()))

@@ -1,0 +1,669 @@
+// HBM-bound kernels of the training step: BatchNorm statistics/apply/backward,
+// pooling, resampling adjoints, activation backward, losses, optimisers, layout.
+// All are coalesced over the innermost (channel) dimension of NHWC tensors, use
+// warp-shuffle reductions, and run grid-stride with grids sized from the SM count.
+#include <stdarg.h>
+
+#include "hm_common.cuh"
+
+namespace hm {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline unsigned ew_grid(long long n, int threads = 256, int per_sm = 8) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)num_sms() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// ---------------------------------------------------------------------------
+// Column reductions over x[M,C]: each block owns a slab of rows; thread t handles
+// channel (t % CT) ... and row lane (t / CT); partial sums go to double atomics.
+// ---------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+
+template <typename T, int MODE>  // MODE 0: sum,sumsq of x ; 1: sum only (col_sum)
+__global__ void __launch_bounds__(RED_THREADS) col_reduce_kernel(const T* __restrict__ x, long long M, int C,
+                                                                double* sums, float* fsum) {
+  __shared__ float sh0[RED_THREADS], sh1[RED_THREADS];
+  const int ct = C < RED_THREADS ? C : RED_THREADS;  // channels covered per pass
+  const int lanes = RED_THREADS / ct;                 // row lanes
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  for (int c0 = 0; c0 < C; c0 += ct) {
+    int c = c0 + tc;
+    float s0 = 0.f, s1 = 0.f;
+    if (active && c < C) {
+      for (long long m = (long long)blockIdx.x * lanes + tr; m < M; m += (long long)gridDim.x * lanes) {
+        float v = ldf(x + (size_t)m * C + c);
+        s0 += v;
+        if (MODE == 0) s1 += v * v;
+      }
+    }
+    sh0[threadIdx.x] = s0;
+    sh1[threadIdx.x] = s1;
+    __syncthreads();
+    if (tr == 0 && c < C) {
+      for (int l = 1; l < lanes; l++) {
+        s0 += sh0[l * ct + tc];
+        s1 += sh1[l * ct + tc];
+      }
+      if (MODE == 0) {
+        atomicAdd(sums + c, (double)s0);
+        atomicAdd(sums + C + c, (double)s1);
+      } else {
+        atomicAdd(fsum + c, s0);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_inv_std, float eps, float alpha,
+                                   int update_running, float* mean, float* inv_std, float* scale,
+                                   float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m, s;
+  if (sums) {
+    double mu = sums[c] / (double)M;
+    double var = sums[C + c] / (double)M - mu * mu;
+    if (var < 0) var = 0;
+    m = (float)mu;
+    s = (float)(1.0 / sqrt(var + (double)eps));
+    if (update_running) {
+      running_mean[c] = (1.f - alpha) * running_mean[c] + alpha * m;
+      running_inv_std[c] = (1.f - alpha) * running_inv_std[c] + alpha * s;
+    }
+  } else {
+    m = running_mean[c];
+    s = running_inv_std[c];
+  }
+  if (mean) mean[c] = m;
+  if (inv_std) inv_std[c] = s;
+  float sc = gamma[c] * s;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+}
+
+template <typename T>
+__global__ void bn_apply_act_kernel(const T* __restrict__ x, T* __restrict__ a, long long n, int C,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    int act, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float v = ldf(x + i) * scale[c] + shift[c];
+    stf(a + i, act_fwd(v, act, slope));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+    bn_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x, long long M,
+                         int C, const float* __restrict__ mean, const float* __restrict__ inv_std, int act,
+                         float slope, double* red) {
+  __shared__ float sh0[RED_THREADS], sh1[RED_THREADS];
+  const int ct = C < RED_THREADS ? C : RED_THREADS;
+  const int lanes = RED_THREADS / ct;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  for (int c0 = 0; c0 < C; c0 += ct) {
+    int c = c0 + tc;
+    float s0 = 0.f, s1 = 0.f;
+    if (active && c < C) {
+      float mu = mean[c], is = inv_std[c];
+      for (long long m = (long long)blockIdx.x * lanes + tr; m < M; m += (long long)gridDim.x * lanes) {
+        size_t i = (size_t)m * C + c;
+        float g = ldf(da + i) * act_grad_from_out(ldf(a + i), act, slope);
+        float xh = (ldf(x + i) - mu) * is;
+        s0 += g;
+        s1 += g * xh;
+      }
+    }
+    sh0[threadIdx.x] = s0;
+    sh1[threadIdx.x] = s1;
+    __syncthreads();
+    if (tr == 0 && c < C) {
+      for (int l = 1; l < lanes; l++) {
+        s0 += sh0[l * ct + tc];
+        s1 += sh1[l * ct + tc];
+      }
+      atomicAdd(red + c, (double)s0);
+      atomicAdd(red + C + c, (double)s1);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x,
+                                    T* __restrict__ dx, long long M, int C, const float* __restrict__ mean,
+                                    const float* __restrict__ inv_std, const float* __restrict__ gamma, int act,
+                                    float slope, const double* __restrict__ red, float* dgamma, float* dbeta) {
+  const long long n = M * C;
+  const float invM = 1.f / (float)M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float r0 = (float)red[c], r1 = (float)red[C + c];
+    float is = inv_std[c];
+    float g = ldf(da + i) * act_grad_from_out(ldf(a + i), act, slope);
+    float xh = (ldf(x + i) - mean[c]) * is;
+    stf(dx + i, gamma[c] * is * (g - r0 * invM - xh * r1 * invM));
+    if (i < C) {
+      if (dgamma) dgamma[c] = r1;
+      if (dbeta) dbeta[c] = r0;
+    }
+  }
+}
+
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* dx, long long n, int act,
+                               float slope, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = ldf(dy + i) * act_grad_from_out(ldf(y + i), act, slope);
+    if (accumulate) v += ldf(dx + i);
+    stf(dx + i, v);
+  }
+}
+
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ p, uint8_t* __restrict__ idx, int B,
+                                    int H, int W, int C) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long long n = (long long)B * Hp * Wp * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int px = (int)(t % Wp);
+    t /= Wp;
+    int py = (int)(t % Hp);
+    int b = (int)(t / Hp);
+    const T* base = x + (((size_t)b * H + 2 * py) * W + 2 * px) * C + c;
+    float v0 = ldf(base), v1 = ldf(base + C), v2 = ldf(base + (size_t)W * C), v3 = ldf(base + (size_t)W * C + C);
+    float m = v0;
+    int k = 0;
+    if (v1 > m) { m = v1; k = 1; }
+    if (v2 > m) { m = v2; k = 2; }
+    if (v3 > m) { m = v3; k = 3; }
+    stf(p + i, m);
+    idx[i] = (uint8_t)k;
+  }
+}
+
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ dp, const T* __restrict__ p,
+                                    const uint8_t* __restrict__ idx, T* __restrict__ dx, int B, int H, int W,
+                                    int C, int act, float slope) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long long n = (long long)B * Hp * Wp * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int px = (int)(t % Wp);
+    t /= Wp;
+    int py = (int)(t % Hp);
+    int b = (int)(t / Hp);
+    float g = ldf(dp + i) * act_grad_from_out(ldf(p + i), act, slope);
+    int k = idx[i];
+    T* base = dx + (((size_t)b * H + 2 * py) * W + 2 * px) * C + c;
+    stf(base, k == 0 ? g : 0.f);
+    stf(base + C, k == 1 ? g : 0.f);
+    stf(base + (size_t)W * C, k == 2 ? g : 0.f);
+    stf(base + (size_t)W * C + C, k == 3 ? g : 0.f);
+  }
+}
+
+// dx[b,y,x,c] (+)= sum over the up-res sites that read x[b,y,x,c]
+template <typename T>
+__global__ void upsample2_bwd_kernel(const T* __restrict__ dy, T* dx, int B, int H, int W, int C, int mode,
+                                     int accumulate) {
+  const long long n = (long long)B * H * W * C;
+  const int H2 = 2 * H, W2 = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int x = (int)(t % W);
+    t /= W;
+    int y = (int)(t % H);
+    int b = (int)(t / H);
+    const T* img = dy + (size_t)b * H2 * W2 * C + c;
+    float acc = 0.f;
+    if (mode == HM_UP_NEAREST2) {
+      for (int a = 0; a < 2; a++)
+        for (int e = 0; e < 2; e++) acc += ldf(img + ((size_t)(2 * y + a) * W2 + (2 * x + e)) * C);
+    } else {
+      // 1-D adjoint weights: up[2m] <- x[m] (1); up[2m+1] <- x[m] (.5), x[min(m+1,n-1)] (.5)
+      // so x[m] receives: up[2m]*1 + up[2m+1]*.5 + up[2m-1]*.5 (m>0) + up[2n-1]*.5 extra when m==n-1
+      int ys[3], xs[3];
+      float wy[3], wx[3];
+      int ny = 0, nx = 0;
+      ys[ny] = 2 * y; wy[ny++] = 1.f;
+      ys[ny] = 2 * y + 1; wy[ny++] = (y == H - 1) ? 1.f : .5f;
+      if (y > 0) { ys[ny] = 2 * y - 1; wy[ny++] = .5f; }
+      xs[nx] = 2 * x; wx[nx++] = 1.f;
+      xs[nx] = 2 * x + 1; wx[nx++] = (x == W - 1) ? 1.f : .5f;
+      if (x > 0) { xs[nx] = 2 * x - 1; wx[nx++] = .5f; }
+      for (int a = 0; a < ny; a++)
+        for (int e = 0; e < nx; e++) acc += wy[a] * wx[e] * ldf(img + ((size_t)ys[a] * W2 + xs[e]) * C);
+    }
+    if (accumulate) acc += ldf(dx + i);
+    stf(dx + i, acc);
+  }
+}
+
+template <typename T>
+__global__ void upsample2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
+                                     int mode) {
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long n = (long long)B * H2 * W2 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int ox = (int)(t % W2);
+    t /= W2;
+    int oy = (int)(t % H2);
+    int b = (int)(t / H2);
+    const T* img = x + (size_t)b * H * W * C + c;
+    int y0 = oy >> 1, x0 = ox >> 1;
+    float v;
+    if (mode == HM_UP_NEAREST2) {
+      v = ldf(img + ((size_t)y0 * W + x0) * C);
+    } else {
+      int y1 = (oy & 1) ? min(y0 + 1, H - 1) : y0;
+      int x1 = (ox & 1) ? min(x0 + 1, W - 1) : x0;
+      v = 0.25f * ((ldf(img + ((size_t)y0 * W + x0) * C) + ldf(img + ((size_t)y0 * W + x1) * C)) +
+                   (ldf(img + ((size_t)y1 * W + x0) * C) + ldf(img + ((size_t)y1 * W + x1) * C)));
+    }
+    stf(y + i, v);
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int H,
+                                    int W) {
+  const long long n = (long long)B * C * H * W;
+  const long long hw = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {  // i indexes dst (NHWC)
+    int c = (int)(i % C);
+    long long t = i / C;
+    long long p = t % hw;
+    long long b = t / hw;
+    stf(dst + i, src[(b * C + c) * hw + p]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int C, int H,
+                                    int W) {
+  const long long n = (long long)B * C * H * W;
+  const long long hw = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {  // i indexes dst (NCHW)
+    long long p = i % hw;
+    long long t = i / hw;
+    int c = (int)(t % C);
+    long long b = t / C;
+    dst[i] = ldf(src + (b * hw + p) * C + c);
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    stf(d + i, ldf(s + i));
+}
+
+// ---- losses ---------------------------------------------------------------
+template <typename T>
+__global__ void adv_loss_kernel(const T* __restrict__ h, T* dh, long long R, int G, int out_act, float target,
+                                int lsgan, int relu_head, float weight, float gscale, int accumulate,
+                                float* loss) {
+  float local = 0.f;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R;
+       r += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < G; g++) s += ldf(h + r * G + g);
+    float out = act_fwd(s / (float)G, out_act, 0.f);
+    float l, dl;
+    if (lsgan) {
+      float e = out - target;
+      l = e * e;
+      dl = 2.f * e;
+    } else {  // binary_crossentropy(out, target)
+      l = -(target * logf(out) + (1.f - target) * logf(1.f - out));
+      dl = -(target / out) + (1.f - target) / (1.f - out);
+    }
+    local += l;
+    if (dh) {
+      dl *= act_grad_from_out(out, out_act, 0.f);
+      float gbase = gscale * weight * dl / ((float)R * (float)G);
+      for (int g = 0; g < G; g++) {
+        float v = gbase;
+        if (relu_head && !(ldf(h + r * G + g) > 0.f)) v = 0.f;
+        if (accumulate) v += ldf(dh + r * G + g);
+        stf(dh + r * G + g, v);
+      }
+    }
+  }
+  local = warp_sum(local);
+  __shared__ float sh[32];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = local;
+  __syncthreads();
+  if (w == 0) {
+    float v = l < (blockDim.x >> 5) ? sh[l] : 0.f;
+    v = warp_sum(v);
+    if (l == 0) atomicAdd(loss, weight * v / (float)R);
+  }
+}
+
+template <typename T>
+__global__ void recon_loss_kernel(const T* __restrict__ p, const T* __restrict__ y, T* dp, long long n, int l2,
+                                  float weight, float gscale, int accumulate, float* loss) {
+  float local = 0.f;
+  const float gn = gscale * weight / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float e = ldf(p + i) - ldf(y + i);
+    float g;
+    if (l2) {
+      local += e * e;
+      g = 2.f * e * gn;
+    } else {
+      local += fabsf(e);
+      g = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * gn;
+    }
+    if (dp) {
+      if (accumulate) g += ldf(dp + i);
+      stf(dp + i, g);
+    }
+  }
+  local = warp_sum(local);
+  __shared__ float sh[32];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = local;
+  __syncthreads();
+  if (w == 0) {
+    float v = l < (blockDim.x >> 5) ? sh[l] : 0.f;
+    v = warp_sum(v);
+    if (l == 0) atomicAdd(loss, weight * v / (float)n);
+  }
+}
+
+// ---- optimisers -----------------------------------------------------------
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ acc,
+                               long long n, const float* __restrict__ lr_p, float rho, float eps, float gscale) {
+  const float lr = *lr_p;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float a = rho * acc[i] + (1.f - rho) * gi * gi;
+    acc[i] = a;
+    p[i] = p[i] - lr * gi / sqrtf(a + eps);
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const float* __restrict__ lr_p, float b1, float b2,
+                            float eps, float corr, float gscale) {
+  const float a_t = *lr_p * corr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - a_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+}  // namespace hm
+
+using namespace hm;
+
+#define DISPATCH_T(dtype, ...)                 \
+  if ((dtype) == HM_F32) {                     \
+    using T = float;                           \
+    __VA_ARGS__;                               \
+  } else {                                     \
+    using T = __half;                          \
+    __VA_ARGS__;                               \
+  }
+
+#define CHECK_DTYPE(dtype, who) \
+  HM_CHECK_ARG((dtype) == HM_F32 || (dtype) == HM_F16, "%s: bad dtype %d", who, (int)(dtype))
+
+extern "C" int hm_version(void) { return 100; }
+extern "C" const char* hm_last_error_string(void) { return g_err; }
+extern "C" int hm_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int hm_bn_stats(const void* x, int dtype, long long M, int C, double* sums, void* stream) {
+  CHECK_DTYPE(dtype, "hm_bn_stats");
+  HM_CHECK_ARG(x && sums && M > 0 && C > 0, "hm_bn_stats: bad argument");
+  int lanes = RED_THREADS / (C < RED_THREADS ? C : RED_THREADS);
+  unsigned grid = ew_grid((M + lanes - 1) / lanes, 1, 4);
+  DISPATCH_T(dtype, (col_reduce_kernel<T, 0><<<grid, RED_THREADS, 0, (cudaStream_t)stream>>>((const T*)x, M, C,
+                                                                                             sums, nullptr)));
+  HM_CHECK_LAUNCH("hm_bn_stats");
+  return HM_OK;
+}
+
+extern "C" int hm_col_sum(const void* dy, int dtype, long long M, int C, float* db, void* stream) {
+  CHECK_DTYPE(dtype, "hm_col_sum");
+  HM_CHECK_ARG(dy && db && M > 0 && C > 0, "hm_col_sum: bad argument");
+  int lanes = RED_THREADS / (C < RED_THREADS ? C : RED_THREADS);
+  unsigned grid = ew_grid((M + lanes - 1) / lanes, 1, 4);
+  DISPATCH_T(dtype, (col_reduce_kernel<T, 1><<<grid, RED_THREADS, 0, (cudaStream_t)stream>>>((const T*)dy, M, C,
+                                                                                             nullptr, db)));
+  HM_CHECK_LAUNCH("hm_col_sum");
+  return HM_OK;
+}
+
+extern "C" int hm_bn_finalize(const double* sums, long long M, int C, const float* gamma, const float* beta,
+                              float* running_mean, float* running_inv_std, float eps, float alpha,
+                              int update_running, float* mean, float* inv_std, float* scale, float* shift,
+                              void* stream) {
+  HM_CHECK_ARG(gamma && beta && scale && shift && C > 0, "hm_bn_finalize: bad argument");
+  HM_CHECK_ARG(sums || (running_mean && running_inv_std), "hm_bn_finalize: no statistics given");
+  HM_CHECK_ARG(!update_running || (running_mean && running_inv_std), "hm_bn_finalize: no running buffers");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sums, M, C, gamma, beta, running_mean, running_inv_std, eps, alpha, update_running, mean, inv_std, scale,
+      shift);
+  HM_CHECK_LAUNCH("hm_bn_finalize");
+  return HM_OK;
+}
+
+extern "C" int hm_bn_apply_act(const void* x, void* a, int dtype, long long M, int C, const float* scale,
+                               const float* shift, int act, float slope, void* stream) {
+  CHECK_DTYPE(dtype, "hm_bn_apply_act");
+  HM_CHECK_ARG(x && a && scale && shift && M > 0 && C > 0, "hm_bn_apply_act: bad argument");
+  long long n = M * C;
+  DISPATCH_T(dtype, (bn_apply_act_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (T*)a, n, C, scale, shift, act, slope)));
+  HM_CHECK_LAUNCH("hm_bn_apply_act");
+  return HM_OK;
+}
+
+extern "C" int hm_bn_bwd_reduce(const void* da, const void* a, const void* x, int dtype, long long M, int C,
+                                const float* mean, const float* inv_std, int act, float slope, double* red,
+                                void* stream) {
+  CHECK_DTYPE(dtype, "hm_bn_bwd_reduce");
+  HM_CHECK_ARG(da && a && x && mean && inv_std && red && M > 0 && C > 0, "hm_bn_bwd_reduce: bad argument");
+  int lanes = RED_THREADS / (C < RED_THREADS ? C : RED_THREADS);
+  unsigned grid = ew_grid((M + lanes - 1) / lanes, 1, 4);
+  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<grid, RED_THREADS, 0, (cudaStream_t)stream>>>(
+                        (const T*)da, (const T*)a, (const T*)x, M, C, mean, inv_std, act, slope, red)));
+  HM_CHECK_LAUNCH("hm_bn_bwd_reduce");
+  return HM_OK;
+}
+
+extern "C" int hm_bn_bwd_apply(const void* da, const void* a, const void* x, void* dx, int dtype, long long M,
+                               int C, const float* mean, const float* inv_std, const float* gamma, int act,
+                               float slope, const double* red, float* dgamma, float* dbeta, void* stream) {
+  CHECK_DTYPE(dtype, "hm_bn_bwd_apply");
+  HM_CHECK_ARG(da && a && x && dx && mean && inv_std && gamma && red && M > 0 && C > 0,
+               "hm_bn_bwd_apply: bad argument");
+  long long n = M * C;
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope,
+                        red, dgamma, dbeta)));
+  HM_CHECK_LAUNCH("hm_bn_bwd_apply");
+  return HM_OK;
+}
+
+extern "C" int hm_act_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, int act, float slope,
+                          int accumulate, void* stream) {
+  CHECK_DTYPE(dtype, "hm_act_bwd");
+  HM_CHECK_ARG(dy && y && dx && n > 0, "hm_act_bwd: bad argument");
+  DISPATCH_T(dtype, (act_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dy, (const T*)y, (T*)dx, n, act, slope, accumulate)));
+  HM_CHECK_LAUNCH("hm_act_bwd");
+  return HM_OK;
+}
+
+extern "C" int hm_maxpool2_fwd(const void* x, void* p, uint8_t* idx, int dtype, int B, int H, int W, int C,
+                               void* stream) {
+  CHECK_DTYPE(dtype, "hm_maxpool2_fwd");
+  HM_CHECK_ARG(x && p && idx && B > 0 && H >= 2 && W >= 2 && C > 0, "hm_maxpool2_fwd: bad argument");
+  long long n = (long long)B * (H / 2) * (W / 2) * C;
+  DISPATCH_T(dtype, (maxpool2_fwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)p,
+                                                                                          idx, B, H, W, C)));
+  HM_CHECK_LAUNCH("hm_maxpool2_fwd");
+  return HM_OK;
+}
+
+extern "C" int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx, void* dx, int dtype, int B,
+                               int H, int W, int C, int act, float slope, void* stream) {
+  CHECK_DTYPE(dtype, "hm_maxpool2_bwd");
+  HM_CHECK_ARG(dp && p && idx && dx && B > 0 && H >= 2 && W >= 2 && C > 0, "hm_maxpool2_bwd: bad argument");
+  HM_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "hm_maxpool2_bwd: odd spatial size");
+  long long n = (long long)B * (H / 2) * (W / 2) * C;
+  DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope)));
+  HM_CHECK_LAUNCH("hm_maxpool2_bwd");
+  return HM_OK;
+}
+
+extern "C" int hm_upsample2_bwd(const void* dy, void* dx, int dtype, int B, int H, int W, int C, int mode,
+                                int accumulate, void* stream) {
+  CHECK_DTYPE(dtype, "hm_upsample2_bwd");
+  HM_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C > 0, "hm_upsample2_bwd: bad argument");
+  HM_CHECK_ARG(mode == HM_UP_NEAREST2 || mode == HM_UP_BILINEAR2, "hm_upsample2_bwd: bad mode %d", mode);
+  long long n = (long long)B * H * W * C;
+  DISPATCH_T(dtype, (upsample2_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dy, (T*)dx, B, H, W, C, mode, accumulate)));
+  HM_CHECK_LAUNCH("hm_upsample2_bwd");
+  return HM_OK;
+}
+
+extern "C" int hm_upsample2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, int mode,
+                                void* stream) {
+  CHECK_DTYPE(dtype, "hm_upsample2_fwd");
+  HM_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0, "hm_upsample2_fwd: bad argument");
+  HM_CHECK_ARG(mode == HM_UP_NEAREST2 || mode == HM_UP_BILINEAR2, "hm_upsample2_fwd: bad mode %d", mode);
+  long long n = (long long)B * H * W * C * 4;
+  DISPATCH_T(dtype, (upsample2_fwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, B,
+                                                                                           H, W, C, mode)));
+  HM_CHECK_LAUNCH("hm_upsample2_fwd");
+  return HM_OK;
+}
+
+extern "C" int hm_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W,
+                               void* stream) {
+  CHECK_DTYPE(dtype, "hm_nchw_to_nhwc");
+  HM_CHECK_ARG(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "hm_nchw_to_nhwc: bad argument");
+  long long n = (long long)B * C * H * W;
+  DISPATCH_T(dtype, (nchw_to_nhwc_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, B, C, H,
+                                                                                          W)));
+  HM_CHECK_LAUNCH("hm_nchw_to_nhwc");
+  return HM_OK;
+}
+
+extern "C" int hm_nhwc_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, int W,
+                               void* stream) {
+  CHECK_DTYPE(dtype, "hm_nhwc_to_nchw");
+  HM_CHECK_ARG(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "hm_nhwc_to_nchw: bad argument");
+  long long n = (long long)B * C * H * W;
+  DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, B,
+                                                                                          C, H, W)));
+  HM_CHECK_LAUNCH("hm_nhwc_to_nchw");
+  return HM_OK;
+}
+
+extern "C" int hm_cast(const void* src, int sd, void* dst, int dd, long long n, void* stream) {
+  CHECK_DTYPE(sd, "hm_cast");
+  CHECK_DTYPE(dd, "hm_cast");
+  HM_CHECK_ARG(src && dst && n > 0, "hm_cast: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned g = ew_grid(n);
+  if (sd == HM_F32 && dd == HM_F16) cast_kernel<float, __half><<<g, 256, 0, st>>>((const float*)src, (__half*)dst, n);
+  else if (sd == HM_F16 && dd == HM_F32) cast_kernel<__half, float><<<g, 256, 0, st>>>((const __half*)src, (float*)dst, n);
+  else if (sd == HM_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else cast_kernel<__half, __half><<<g, 256, 0, st>>>((const __half*)src, (__half*)dst, n);
+  HM_CHECK_LAUNCH("hm_cast");
+  return HM_OK;
+}
+
+extern "C" int hm_adv_loss(const void* h, void* dh, int dtype, long long R, int G, int out_act, float target,
+                           int lsgan, int relu_head, float weight, float gscale, int accumulate, float* loss,
+                           void* stream) {
+  CHECK_DTYPE(dtype, "hm_adv_loss");
+  HM_CHECK_ARG(h && loss && R > 0 && G > 0, "hm_adv_loss: bad argument");
+  DISPATCH_T(dtype, (adv_loss_kernel<T><<<ew_grid(R, 256, 2), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)h, (T*)dh, R, G, out_act, target, lsgan, relu_head, weight, gscale, accumulate,
+                        loss)));
+  HM_CHECK_LAUNCH("hm_adv_loss");
+  return HM_OK;
+}
+
+extern "C" int hm_recon_loss(const void* p, const void* y, void* dp, int dtype, long long n, int l2,
+                             float weight, float gscale, int accumulate, float* loss, void* stream) {
+  CHECK_DTYPE(dtype, "hm_recon_loss");
+  HM_CHECK_ARG(p && y && loss && n > 0, "hm_recon_loss: bad argument");
+  DISPATCH_T(dtype, (recon_loss_kernel<T><<<ew_grid(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)p, (const T*)y, (T*)dp, n, l2, weight, gscale, accumulate, loss)));
+  HM_CHECK_LAUNCH("hm_recon_loss");
+  return HM_OK;
+}
+
+extern "C" int hm_rmsprop(float* p, const float* g, float* acc, long long n, const float* lr, float rho,
+                          float eps, float gscale, void* stream) {
+  HM_CHECK_ARG(p && g && acc && lr && n > 0, "hm_rmsprop: bad argument");
+  rmsprop_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, acc, n, lr, rho, eps, gscale);
+  HM_CHECK_LAUNCH("hm_rmsprop");
+  return HM_OK;
+}
+
+extern "C" int hm_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr, float b1,
+                       float b2, float eps, int t, float gscale, void* stream) {
+  HM_CHECK_ARG(p && g && m && v && lr && n > 0 && t > 0, "hm_adam: bad argument");
+  float corr = sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
+  adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, corr, gscale);
+  HM_CHECK_LAUNCH("hm_adam");
+  return HM_OK;
+}

@@ -1,0 +1,75 @@
+// Shared helpers for the hmgan kernel library (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hmgan.h"
+
+namespace hm {
+
+void set_error(const char* fmt, ...);
+
+#define HM_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      hm::set_error(__VA_ARGS__);          \
+      return HM_ERR_BAD_ARG;               \
+    }                                      \
+  } while (0)
+
+#define HM_CHECK_LAUNCH(name)                                                  \
+  do {                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) {                                                  \
+      hm::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+      return HM_ERR_CUDA;                                                      \
+    }                                                                          \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  switch (act) {
+    case HM_ACT_LRELU: return v >= 0.f ? v : v * slope;
+    case HM_ACT_RELU: return v > 0.f ? v : 0.f;
+    case HM_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case HM_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+// derivative expressed through the OUTPUT value y = act(x)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
+  switch (act) {
+    case HM_ACT_LRELU: return y >= 0.f ? 1.f : slope;
+    case HM_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case HM_ACT_SIGMOID: return y * (1.f - y);
+    case HM_ACT_TANH: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace hm

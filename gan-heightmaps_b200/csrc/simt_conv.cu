@@ -1,0 +1,383 @@
+// Gather-GEMM convolutions on CUDA cores (any shape, fp32 accumulate).
+//
+// This is the parity-mode arithmetic (fp32 tensors) and the fast-mode fallback for
+// the layers that are not tensor-core shaped (Cin=1, Cout in {1,3}, 2x2 kernels).
+// Restates theano CorrMM / CorrMM_gradInputs / CorrMM_gradWeights as reached from
+// lasagne Conv2DLayer / Deconv2DLayer / DenseLayer (reference architectures/dcgan.py:16,
+// 22,32,42,50; architectures/p2p.py:20-24).
+#include "hm_common.cuh"
+
+namespace hm {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+struct Site {
+  int n, oy, ox;
+};
+
+// Value of the virtual (upsampled, concatenated) source at logical site/tap/channel.
+template <typename T>
+__device__ __forceinline__ float gather(const HmConvDesc& d, const T* __restrict__ x1,
+                                        const T* __restrict__ x2, const Site& s, int k, int Ct) {
+  int tap = k / Ct;
+  int ci = k - tap * Ct;
+  int r = tap / d.kw;
+  int c = tap - r * d.kw;
+  int iy, ix;
+  if (!d.transposed) {
+    iy = s.oy * d.stride - d.pad + r;
+    ix = s.ox * d.stride - d.pad + c;
+  } else {
+    int ty = s.oy + d.pad - r, tx = s.ox + d.pad - c;
+    if (ty < 0 || tx < 0) return 0.f;
+    if (d.stride > 1) {
+      if ((ty % d.stride) || (tx % d.stride)) return 0.f;
+      ty /= d.stride;
+      tx /= d.stride;
+    }
+    iy = ty;
+    ix = tx;
+  }
+  const int sh = d.up ? 1 : 0;
+  if (iy < 0 || ix < 0 || iy >= (d.H << sh) || ix >= (d.W << sh)) return 0.f;
+  const T* src;
+  int C;
+  if (ci < d.C1) {
+    src = x1;
+    C = d.C1;
+  } else {
+    src = x2;
+    C = d.C2;
+    ci -= d.C1;
+  }
+  const size_t img = (size_t)s.n * d.H;
+  if (d.up != HM_UP_BILINEAR2) {
+    int py = iy >> sh, px = ix >> sh;
+    return ldf(src + ((img + py) * d.W + px) * C + ci);
+  }
+  // theano bilinear_upsampling, ratio 2: y[2m]=x[m], y[2m+1]=(x[m]+x[min(m+1,n-1)])/2
+  int y0 = iy >> 1, x0 = ix >> 1;
+  int y1 = (iy & 1) ? min(y0 + 1, d.H - 1) : y0;
+  int x1i = (ix & 1) ? min(x0 + 1, d.W - 1) : x0;
+  float a = ldf(src + ((img + y0) * d.W + x0) * C + ci);
+  float b = ldf(src + ((img + y0) * d.W + x1i) * C + ci);
+  float e = ldf(src + ((img + y1) * d.W + x0) * C + ci);
+  float f = ldf(src + ((img + y1) * d.W + x1i) * C + ci);
+  return 0.25f * ((a + b) + (e + f));
+}
+
+__device__ __forceinline__ Site decode_site(const HmConvDesc& d, long long m) {
+  Site s;
+  int hw = d.Ho * d.Wo;
+  s.n = (int)(m / hw);
+  int rem = (int)(m - (long long)s.n * hw);
+  s.oy = rem / d.Wo;
+  s.ox = rem - s.oy * d.Wo;
+  return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) conv_gather_kernel(HmConvDesc d, const T* __restrict__ x1,
+                                                         const T* __restrict__ x2,
+                                                         const T* __restrict__ w,
+                                                         const float* __restrict__ bias, T* y, T* y2) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int Ct = d.C1 + d.C2;
+  const int K = d.kh * d.kw * Ct;
+  const long long M = (long long)d.B * d.Ho * d.Wo;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A-load role: row a_m, 4 consecutive k
+  const int a_m = tid >> 2, a_k = (tid & 3) * 4;
+  const long long am = m0 + a_m;
+  const bool a_ok = am < M;
+  Site as = decode_site(d, a_ok ? am : 0);
+  // B-load role: k row b_k, 4 consecutive co
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int k = k0 + a_k + j;
+      As[a_k + j][a_m] = (a_ok && k < K) ? gather<T>(d, x1, x2, as, k, Ct) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int k = k0 + b_k, co = n0 + b_n + j;
+      Bs[b_k][b_n + j] = (k < K && co < d.Cout) ? ldf(w + (size_t)k * d.Cout + co) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    Site s = decode_site(d, m);
+    size_t pix = ((size_t)s.n * d.oH + (s.oy * d.os + d.ou)) * d.oW + (s.ox * d.os + d.ov);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int co = n0 + tx * 4 + j;
+      if (co >= d.Cout) continue;
+      float v = acc[i][j] + (bias ? bias[co] : 0.f);
+      v = act_fwd(v, d.act, d.slope);
+      T* dst;
+      int accum;
+      if (co < d.split) {
+        dst = y + pix * d.split + co;
+        accum = d.accumulate & 1;
+      } else {
+        dst = y2 + pix * (d.Cout - d.split) + (co - d.split);
+        accum = d.accumulate & 2;
+      }
+      if (co < d.split ? (y == nullptr) : (y2 == nullptr)) continue;
+      if (accum) v += ldf(dst);
+      stf(dst, v);
+    }
+  }
+}
+
+// dWp[k][co] += sum_sites gather(site,k) * dy[site][co]
+template <typename T>
+__global__ void __launch_bounds__(NT) conv_wgrad_kernel(HmConvDesc d, const T* __restrict__ x1,
+                                                        const T* __restrict__ x2,
+                                                        const T* __restrict__ dy, float* dw,
+                                                        long long sites_per_z) {
+  __shared__ float As[BK][BM + 4];  // [site][k]
+  __shared__ float Bs[BK][BN + 4];  // [site][co]
+  const int tid = threadIdx.x;
+  const int Ct = d.C1 + d.C2;
+  const int K = d.kh * d.kw * Ct;
+  const long long M = (long long)d.B * d.Ho * d.Wo;
+  const int k0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const long long s_begin = (long long)blockIdx.z * sites_per_z;
+  const long long s_end = min(M, s_begin + sites_per_z);
+
+  const int l_s = tid >> 4, l_c = (tid & 15) * 4;  // both tiles: site row, 4 consecutive cols
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (long long s0 = s_begin; s0 < s_end; s0 += BK) {
+    long long m = s0 + l_s;
+    bool ok = m < s_end;
+    Site st = decode_site(d, ok ? m : 0);
+    size_t pix = ((size_t)st.n * d.oH + (st.oy * d.os + d.ou)) * d.oW + (st.ox * d.os + d.ov);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int k = k0 + l_c + j;
+      As[l_s][l_c + j] = (ok && k < K) ? gather<T>(d, x1, x2, st, k, Ct) : 0.f;
+      int co = n0 + l_c + j;
+      Bs[l_s][l_c + j] = (ok && co < d.Cout) ? ldf(dy + pix * d.Cout + co) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int co = n0 + tx * 4 + j;
+      if (co < d.Cout) atomicAdd(dw + (size_t)k * d.Cout + co, acc[i][j]);
+    }
+  }
+}
+
+// ---- weight packing --------------------------------------------------------
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int mode, int cout,
+                                   int cin, int kh, int kw, int u, int v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float val;
+  if (mode == 0) {  // Wp[(r*kw+s)*cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]
+    int co = (int)(i % cout);
+    long long k = i / cout;
+    int ci = (int)(k % cin);
+    int tap = (int)(k / cin);
+    int r = tap / kw, s = tap % kw;
+    val = w[(((size_t)co * cin + ci) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)];
+  } else if (mode == 1) {  // Wp[(r*kw+s)*cout+co][ci] = W[co][ci][kh-1-r][kw-1-s]
+    int ci = (int)(i % cin);
+    long long k = i / cin;
+    int co = (int)(k % cout);
+    int tap = (int)(k / cout);
+    int r = tap / kw, s = tap % kw;
+    val = w[(((size_t)co * cin + ci) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)];
+  } else if (mode == 2) {  // deconv W (cin,cout,kh,kw), one phase: Wp[ci][co] = W[ci][co][kh-1-u][kw-1-v]
+    int co = (int)(i % cout);
+    int ci = (int)(i / cout);
+    val = w[(((size_t)ci * cout + co) * kh + (kh - 1 - u)) * kw + (kw - 1 - v)];
+  } else if (mode == 3) {  // deconv W: Wp[(u*kw+v)*cout+co][ci] = W[ci][co][kh-1-u][kw-1-v]
+    int ci = (int)(i % cin);
+    long long k = i / cin;
+    int co = (int)(k % cout);
+    int tap = (int)(k / cout);
+    int uu = tap / kw, vv = tap % kw;
+    val = w[(((size_t)ci * cout + co) * kh + (kh - 1 - uu)) * kw + (kw - 1 - vv)];
+  } else {
+    val = w[i];
+  }
+  stf(wp + i, val);
+}
+
+// packed fp32 gradient -> master layout gradient
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int mode,
+                                    int cout, int cin, int kh, int kw, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mode == 0) {  // i indexes master W[co][ci][a][b]
+    int b = (int)(i % kw);
+    long long t = i / kw;
+    int a = (int)(t % kh);
+    t /= kh;
+    int ci = (int)(t % cin);
+    int co = (int)(t / cin);
+    int r = kh - 1 - a, s = kw - 1 - b;
+    dw[i] = dwp[((size_t)(r * kw + s) * cin + ci) * cout + co];
+  } else if (mode == 2) {  // master deconv W[ci][co][a][b]; packed as kh*kw phase blocks [tap][ci][co]
+    int b = (int)(i % kw);
+    long long t = i / kw;
+    int a = (int)(t % kh);
+    t /= kh;
+    int co = (int)(t % cout);
+    int ci = (int)(t / cout);
+    int u = kh - 1 - a, v = kw - 1 - b;
+    dw[i] = dwp[((size_t)(u * kw + v) * cin + ci) * cout + co];
+  } else {
+    dw[i] = dwp[i];
+  }
+}
+
+}  // namespace hm
+
+using namespace hm;
+
+static int check_desc(const HmConvDesc* d, const char* who) {
+  HM_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
+  HM_CHECK_ARG(d->dtype == HM_F32 || d->dtype == HM_F16, "%s: bad dtype %d", who, d->dtype);
+  HM_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->C1 > 0 && d->C2 >= 0, "%s: bad source shape", who);
+  HM_CHECK_ARG(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad >= 0, "%s: bad kernel geometry", who);
+  HM_CHECK_ARG(d->Ho > 0 && d->Wo > 0 && d->Cout > 0, "%s: bad output grid", who);
+  HM_CHECK_ARG(d->os >= 1 && d->ou >= 0 && d->ov >= 0 && (d->Ho - 1) * d->os + d->ou < d->oH &&
+                   (d->Wo - 1) * d->os + d->ov < d->oW,
+               "%s: output scatter exceeds the physical tensor", who);
+  HM_CHECK_ARG(d->split > 0 && d->split <= d->Cout, "%s: bad channel split", who);
+  HM_CHECK_ARG(!(d->transposed && d->up), "%s: virtual upsampling only on the forward gather", who);
+  return HM_OK;
+}
+
+extern "C" int hm_conv_gather(const HmConvDesc* d, const void* x1, const void* x2, const void* w,
+                              const float* bias, void* y, void* y2, void* stream) {
+  int rc = check_desc(d, "hm_conv_gather");
+  if (rc) return rc;
+  HM_CHECK_ARG(x1 && w && (y || y2), "hm_conv_gather: null tensor");
+  HM_CHECK_ARG(d->C2 == 0 || x2, "hm_conv_gather: C2>0 but x2 is null");
+  long long M = (long long)d->B * d->Ho * d->Wo;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d->Cout + BN - 1) / BN));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == HM_F32)
+    conv_gather_kernel<float><<<grid, NT, 0, st>>>(*d, (const float*)x1, (const float*)x2,
+                                                   (const float*)w, bias, (float*)y, (float*)y2);
+  else
+    conv_gather_kernel<__half><<<grid, NT, 0, st>>>(*d, (const __half*)x1, (const __half*)x2,
+                                                    (const __half*)w, bias, (__half*)y, (__half*)y2);
+  HM_CHECK_LAUNCH("hm_conv_gather");
+  return HM_OK;
+}
+
+extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy,
+                             float* dw, void* stream) {
+  int rc = check_desc(d, "hm_conv_wgrad");
+  if (rc) return rc;
+  HM_CHECK_ARG(x1 && dy && dw, "hm_conv_wgrad: null tensor");
+  HM_CHECK_ARG(d->C2 == 0 || x2, "hm_conv_wgrad: C2>0 but x2 is null");
+  HM_CHECK_ARG(!d->transposed, "hm_conv_wgrad: descriptor must be a forward gather");
+  int K = d->kh * d->kw * (d->C1 + d->C2);
+  long long M = (long long)d->B * d->Ho * d->Wo;
+  unsigned gx = (K + BM - 1) / BM, gy = (d->Cout + BN - 1) / BN;
+  long long want = (4LL * num_sms() + gx * gy - 1) / (gx * gy);
+  long long maxz = (M + 4 * BK - 1) / (4 * BK);
+  long long gz = want < 1 ? 1 : (want > maxz ? maxz : want);
+  if (gz > 65535) gz = 65535;
+  long long per = (M + gz - 1) / gz;
+  per = (per + BK - 1) / BK * BK;
+  gz = (M + per - 1) / per;
+  dim3 grid(gx, gy, (unsigned)gz);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype == HM_F32)
+    conv_wgrad_kernel<float><<<grid, NT, 0, st>>>(*d, (const float*)x1, (const float*)x2,
+                                                  (const float*)dy, dw, per);
+  else
+    conv_wgrad_kernel<__half><<<grid, NT, 0, st>>>(*d, (const __half*)x1, (const __half*)x2,
+                                                   (const __half*)dy, dw, per);
+  HM_CHECK_LAUNCH("hm_conv_wgrad");
+  return HM_OK;
+}
+
+extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
+                                   int u, int v, int dst_dtype, void* stream) {
+  HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
+  HM_CHECK_ARG(mode >= 0 && mode <= 4, "hm_pack_conv_weight: bad mode %d", mode);
+  long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_dtype == HM_F32)
+    pack_weight_kernel<float><<<blocks, 256, 0, st>>>(w, (float*)wp, mode, cout, cin, kh, kw, u, v, n);
+  else
+    pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w, (__half*)wp, mode, cout, cin, kh, kw, u, v, n);
+  HM_CHECK_LAUNCH("hm_pack_conv_weight");
+  return HM_OK;
+}
+
+extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int cout, int cin, int kh,
+                                    int kw, void* stream) {
+  HM_CHECK_ARG(dwp && dw, "hm_unpack_conv_wgrad: null pointer");
+  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4, "hm_unpack_conv_wgrad: bad mode %d", mode);
+  long long n = (long long)cout * cin * kh * kw;
+  unpack_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dwp, dw, mode, cout,
+                                                                                     cin, kh, kw, n);
+  HM_CHECK_LAUNCH("hm_unpack_conv_wgrad");
+  return HM_OK;
+}

@@ -1,0 +1,197 @@
+/* hmgan.h — C ABI of the B200 (sm_100a) kernel library behind the gan-heightmaps
+ * training step.
+ *
+ * What this boundary replaces.  The reference has no native code: every number
+ * on its hot path is produced by a compiled Theano function,
+ * train_fn(Z,X,Y) (reference pix2pix.py:142), built from Lasagne layer objects
+ * (architectures/dcgan.py:14-58, architectures/p2p.py:20-27,126-292,
+ * architectures/layers.py:13-26) and Lasagne update rules (pix2pix.py:131-141).
+ * A Theano/Lasagne maintainer would bind these entry points as the `perform`
+ * bodies of the ops those layers lower to; each function
+ * below names the Lasagne/Theano op it stands in for.
+ *
+ * Conventions (all functions):
+ *   - every pointer is a BORROWED DEVICE pointer (the host side, PyTorch's caching
+ *     allocator, owns the memory); the library never allocates or frees;
+ *   - activations are NHWC, dtype HM_F32 (parity mode) or HM_F16 (fast mode);
+ *     statistics, losses, master parameters, gradients and optimiser state are
+ *     always float32 (double where stated);
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*), no
+ *     internal synchronisation, so a whole step can be captured in a CUDA graph;
+ *   - return value: 0 on success, a negative HmStatus on error; nothing throws
+ *     across the ABI; hm_last_error_string() describes the last error of the
+ *     calling thread.
+ */
+#ifndef HMGAN_H_
+#define HMGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum HmStatus {
+  HM_OK = 0,
+  HM_ERR_BAD_ARG = -1,
+  HM_ERR_UNSUPPORTED = -2,
+  HM_ERR_CUDA = -3,
+  HM_ERR_ALIGN = -4
+} HmStatus;
+
+typedef enum HmDType { HM_F32 = 0, HM_F16 = 1 } HmDType;
+
+typedef enum HmAct {
+  HM_ACT_LINEAR = 0,  /* lasagne.nonlinearities.linear                       */
+  HM_ACT_LRELU = 1,   /* LeakyRectify(slope): dcgan.py:24,45 (0.2); p2p 0.01 */
+  HM_ACT_RELU = 2,    /* rectify (Conv2DLayer default, dcgan.py:50)          */
+  HM_ACT_SIGMOID = 3, /* dcgan.py:32                                         */
+  HM_ACT_TANH = 4     /* p2p.py:275                                          */
+} HmAct;
+
+typedef enum HmUp {
+  HM_UP_NONE = 0,
+  HM_UP_NEAREST2 = 1, /* lasagne Upscale2DLayer(2), dcgan.py:31                      */
+  HM_UP_BILINEAR2 = 2 /* theano bilinear_upsampling(ratio=2), layers.py:21-26        */
+} HmUp;
+
+/* One gather-GEMM convolution problem.  The same descriptor drives forward,
+ * input-gradient and weight-gradient kernels.
+ *
+ * Forward (transposed=0):  for every logical output site (n,oy,ox), oy<Ho, ox<Wo
+ *   acc[co] = sum_{r<kh,s<kw,ci<C1+C2} src(n, oy*stride-pad+r, ox*stride-pad+s, ci) * w[(r*kw+s)*(C1+C2)+ci][co]
+ * where src is the channel-concatenation of x1 (C1 ch) and x2 (C2 ch, may be 0)
+ * seen through the virtual upsampling `up` (physical tensors are [B,H,W,C*];
+ * the virtual grid is [B,H<<(up!=0),W<<(up!=0)]); out-of-range taps read 0.
+ * The result is written to y[n, oy*os+ou, ox*os+ov, co] of a physical
+ * [B,oH,oW,Cout] tensor after  +bias, activation.
+ *
+ * Input gradient (transposed=1): the logical grid (Ho,Wo) is the grid of the
+ * tensor receiving the gradient, src is the upstream gradient [B,H,W,C1]:
+ *   acc[co] = sum_{r,s,ci} src(n,(oy+pad-r)/stride,(ox+pad-s)/stride,ci) * w[...]   (only where divisible)
+ * and channels [0,split) of the result go to y, channels [split,Cout) to y2.
+ *
+ * Weights are "packed" by hm_pack_conv_weight so that all kernels do plain
+ * correlation (Lasagne's filter flip is applied at pack time).
+ */
+typedef struct HmConvDesc {
+  int32_t dtype;               /* HmDType of x1,x2,y,y2 and packed weights              */
+  int32_t B, H, W, C1, C2;     /* physical source tensors                               */
+  int32_t up;                  /* HmUp, forward gather only                             */
+  int32_t kh, kw, stride, pad;
+  int32_t transposed;          /* 0 forward gather, 1 input-gradient gather             */
+  int32_t Ho, Wo, Cout;        /* logical output grid and GEMM N                        */
+  int32_t oH, oW, os, ou, ov;  /* physical output tensor and scatter                    */
+  int32_t split;               /* channels written to y (rest to y2); ==Cout if no y2   */
+  int32_t act;                 /* HmAct epilogue                                        */
+  float slope;                 /* LeakyRectify leakiness                                */
+  int32_t accumulate;          /* bit0: y += result, bit1: y2 += result                 */
+} HmConvDesc;
+
+/* ---- library -------------------------------------------------------------- */
+int hm_version(void);
+const char* hm_last_error_string(void);
+/* 1 if the tcgen05/TMA path can run on the current device (cc 10.x), else 0. */
+int hm_device_supported(void);
+
+/* ---- gather-GEMM convolutions (SIMT, any shape; fp32 accumulate) ----------
+ * Stand in for theano CorrMM / CorrMM_gradInputs / CorrMM_gradWeights as used by
+ * lasagne Conv2DLayer / Deconv2DLayer / DenseLayer (dcgan.py:16,22,32,42,50;
+ * p2p.py:20-24). */
+int hm_conv_gather(const HmConvDesc* d, const void* x1, const void* x2, const void* w_packed,
+                   const float* bias, void* y, void* y2, void* stream);
+/* dWp[(r*kw+s)*(C1+C2)+ci][co] (+)= sum_sites src(...) * dy[n,oy,ox,co]; fp32 output,
+ * atomically accumulated into `dw_packed` (caller zeroes it).  `dy` is a dense
+ * [B,Ho,Wo,Cout] tensor unless os>1 (then read through the same scatter as y). */
+int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy,
+                  float* dw_packed, void* stream);
+
+/* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
+ *  mode 0: Conv2DLayer W (Cout,Cin,kh,kw)      -> Wp[(r*kw+s)*Cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]   (forward)
+ *  mode 1: Conv2DLayer W                       -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][kh-1-r][kw-1-s]  (input gradient)
+ *  mode 2: Deconv2DLayer W (Cin,Cout,kh,kw), tap (u,v) -> Wp[ci][co] = W[ci][co][kh-1-u][kw-1-v]        (forward, one output phase)
+ *  mode 3: Deconv2DLayer W                     -> Wp[(u*kw+v)*Cout+co][ci] = W[ci][co][kh-1-u][kw-1-v]  (input gradient = strided conv)
+ *  mode 4: DenseLayer W (in,out)               -> Wp = W (dtype cast only)
+ * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the
+ * inverse index map of mode 0 / 2(all taps) / 4 to a packed fp32 gradient and
+ * (over)writes the master-layout gradient. */
+int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
+                        int u, int v, int dst_dtype, void* stream);
+int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int cout, int cin, int kh, int kw,
+                         void* stream);
+
+/* ---- BatchNormLayer (dcgan.py:17,23; p2p.py:146-268) ----------------------- */
+/* sums[0..C) = sum x, sums[C..2C) = sum x^2 over the M rows of x[M,C]; double, caller zeroes. */
+int hm_bn_stats(const void* x, int dtype, long long M, int C, double* sums, void* stream);
+/* From the sums: mean, inv_std = 1/sqrt(var+eps) (biased var), scale = gamma*inv_std,
+ * shift = beta - mean*scale; if update_running: running <- (1-alpha)*running + alpha*batch
+ * for BOTH mean and inv_std (Lasagne averages inv_std).  If sums==NULL (deterministic):
+ * scale/shift come from the running statistics. */
+int hm_bn_finalize(const double* sums, long long M, int C, const float* gamma, const float* beta,
+                   float* running_mean, float* running_inv_std, float eps, float alpha,
+                   int update_running, float* mean, float* inv_std, float* scale, float* shift,
+                   void* stream);
+/* a = act(x*scale[c]+shift[c]) */
+int hm_bn_apply_act(const void* x, void* a, int dtype, long long M, int C, const float* scale,
+                    const float* shift, int act, float slope, void* stream);
+/* Backward, pass 1: with dyh = da * act'(a):  red[0..C) += sum dyh, red[C..2C) += sum dyh*xhat,
+ * xhat = (x-mean)*inv_std.  double, caller zeroes. */
+int hm_bn_bwd_reduce(const void* da, const void* a, const void* x, int dtype, long long M, int C,
+                     const float* mean, const float* inv_std, int act, float slope, double* red,
+                     void* stream);
+/* Backward, pass 2: dx = gamma*inv_std*(dyh - red0/M - xhat*red1/M); also dgamma=red1, dbeta=red0. */
+int hm_bn_bwd_apply(const void* da, const void* a, const void* x, void* dx, int dtype, long long M,
+                    int C, const float* mean, const float* inv_std, const float* gamma, int act,
+                    float slope, const double* red, float* dgamma, float* dbeta, void* stream);
+
+/* ---- elementwise / pooling / resampling ----------------------------------- */
+/* dx = dy * act'(y)   (NonlinearityLayer backward expressed through the OUTPUT y) */
+int hm_act_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, int act, float slope,
+               int accumulate, void* stream);
+/* db[c] (+)= sum_rows dy[M,C]  (conv / dense bias gradient) */
+int hm_col_sum(const void* dy, int dtype, long long M, int C, float* db, void* stream);
+/* MaxPool2DLayer(2) (dcgan.py:47): p = max over 2x2, idx = argmax (0..3, first max wins) */
+int hm_maxpool2_fwd(const void* x, void* p, uint8_t* idx, int dtype, int B, int H, int W, int C,
+                    void* stream);
+/* dx[.. 2x2 ..] = (k==idx) ? dp * act'(p) : 0   — unpool fused with the backward of the
+ * (monotonic) activation that preceded the pool. */
+int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx, void* dx, int dtype, int B,
+                    int H, int W, int C, int act, float slope, void* stream);
+/* Adjoint of the virtual upsampling: dx[B,H,W,C] (+)= U^T dy[B,2H,2W,C]; mode = HmUp. */
+int hm_upsample2_bwd(const void* dy, void* dx, int dtype, int B, int H, int W, int C, int mode,
+                     int accumulate, void* stream);
+/* Materialised upsampling (fast path feeding the tensor-core conv): y[B,2H,2W,C] = U x. */
+int hm_upsample2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int C, int mode,
+                     void* stream);
+/* Boundary layout changes: NCHW float32 (the reference's numpy convention) <-> NHWC dtype. */
+int hm_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W, void* stream);
+int hm_nhwc_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, int W, void* stream);
+int hm_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, void* stream);
+
+/* ---- losses (pix2pix.py:102-121) ------------------------------------------ */
+/* Adversarial loss on a discriminator head h[R, G] (R rows of G values; the DCGAN head
+ * average-pools G=rf*rf post-ReLU values per sample, dcgan.py:50-56; PatchGAN has G=1):
+ *   out_r = out_act(mean_g h[r,g])  (out_act: HM_ACT_LINEAR or HM_ACT_SIGMOID);  lsgan: l_r=(out_r-target)^2 ; else BCE(out_r,target)
+ *   loss[0] += weight * mean_r l_r ;  dh[r,g] (+)= gscale * weight * dl_r/dout_r /(R*G) * (relu_head ? h>0 : 1)
+ * dh may be NULL (loss only). */
+int hm_adv_loss(const void* h, void* dh, int dtype, long long R, int G, int out_act, float target,
+                int lsgan, int relu_head, float weight, float gscale, int accumulate, float* loss,
+                void* stream);
+/* Reconstruction loss: l1: mean|p-y| , l2: mean (p-y)^2 ; dp (+)= gscale*weight*dl/dp. */
+int hm_recon_loss(const void* p, const void* y, void* dp, int dtype, long long n, int l2,
+                  float weight, float gscale, int accumulate, float* loss, void* stream);
+
+/* ---- optimisers (lasagne.updates, experiments.py:116-117) ------------------ */
+/* rmsprop: acc = rho*acc + (1-rho)*g^2 ; p -= lr*g/sqrt(acc+eps)   (eps inside the sqrt).
+ * g is multiplied by gscale first (1/world_size after a sum all-reduce, 1/loss_scale). */
+int hm_rmsprop(float* p, const float* g, float* acc, long long n, const float* lr, float rho,
+               float eps, float gscale, void* stream);
+/* adam (lasagne 0.2.dev1): t is the NEW step count. */
+int hm_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr, float b1,
+            float b2, float eps, int t, float gscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMGAN_H_ */
