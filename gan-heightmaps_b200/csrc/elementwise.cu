@@ -325,6 +325,24 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
   }
 }
 
+// ReshapeLayer((-1,C,H,W)) of a flat NCHW-ordered feature vector <-> NHWC buffer (same dtype).
+template <typename T>
+__global__ void permute_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int H, int W,
+                               int inverse) {
+  const long long n = (long long)B * C * H * W;
+  const long long hw = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {  // i indexes the NHWC side
+    int c = (int)(i % C);
+    long long t = i / C;
+    long long p = t % hw;
+    long long b = t / hw;
+    long long j = (b * C + c) * hw + p;           // NCHW side
+    if (inverse) dst[j] = src[i];
+    else dst[i] = src[j];
+  }
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -612,6 +630,17 @@ extern "C" int hm_nhwc_to_nchw(const void* src, float* dst, int dtype, int B, in
   DISPATCH_T(dtype, (nhwc_to_nchw_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)src, dst, B,
                                                                                           C, H, W)));
   HM_CHECK_LAUNCH("hm_nhwc_to_nchw");
+  return HM_OK;
+}
+
+extern "C" int hm_permute(const void* src, void* dst, int dtype, int B, int C, int H, int W, int inverse,
+                          void* stream) {
+  CHECK_DTYPE(dtype, "hm_permute");
+  HM_CHECK_ARG(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "hm_permute: bad argument");
+  long long n = (long long)B * C * H * W;
+  DISPATCH_T(dtype, (permute_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, B, C,
+                                                                                     H, W, inverse)));
+  HM_CHECK_LAUNCH("hm_permute");
   return HM_OK;
 }
 

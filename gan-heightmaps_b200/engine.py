@@ -1,0 +1,672 @@
+"""Lowering of Lasagne-style layer graphs to programs of sm_100a kernel launches.
+
+The reference hands its layer graphs to Theano (``lasagne.layers.get_output`` +
+``theano.function``, reference pix2pix.py:91-101,142-147), which compiles them to
+CorrMM / cuDNN calls.  Here ``Net`` plays that role: it walks a
+``lasagne_compat`` graph once, emits a list of ops over NHWC device buffers, and
+runs them forwards and backwards by calling the C-ABI kernel library
+(include/hmgan.h) through ``_lib.call``.  PyTorch only owns the device memory and
+the stream; every arithmetic operation on the path is one of our kernels.
+
+Graph canonicalisation (all exact, elementwise ops commute with concatenation):
+  * NonlinearityLayer(ConcatLayer([a, b]))  ->  concat(act(a), act(b)); the U-Net
+    skip tensor act(BN(conv_k)) is then shared with the encoder's own activation
+    (reference architectures/p2p.py:146-147 and :213-214 use the same slope);
+  * BatchNormLayer + NonlinearityLayer      ->  one normalise+activate pass;
+  * Conv/Dense/Deconv + NonlinearityLayer   ->  activation in the conv epilogue;
+  * Upscale2DLayer / BilinearUpsample2DLayer / ConcatLayer are never materialised
+    in parity mode: the consumer convolution gathers through them;
+  * Pool2D(average, full extent) + Reshape(-1,1) + Nonlinearity (the DCGAN
+    discriminator head, reference architectures/dcgan.py:50-56) is evaluated
+    inside the adversarial-loss kernel.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+import _lib
+import lasagne_compat as L
+from architectures.layers import BilinearUpsample2DLayer
+
+ACT = _lib.ACT
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Runtime(object):
+    """Device, compute dtype and stream shared by the networks of one model."""
+
+    def __init__(self, device="cuda", precision="parity", loss_scale=None):
+        self.device = torch.device(device)
+        if precision not in ("parity", "fast"):
+            raise ValueError("precision must be 'parity' (fp32) or 'fast' (fp16 storage, fp32 accumulate)")
+        self.precision = precision
+        self.cd = _lib.F32 if precision == "parity" else _lib.F16
+        self.tdtype = torch.float32 if precision == "parity" else torch.float16
+        if loss_scale is None:
+            loss_scale = 1.0 if precision == "parity" else 1024.0
+        self.loss_scale = float(loss_scale)
+        self.launches = 0
+        _lib.load()
+
+    @property
+    def stream(self):
+        if self.device.type == "cuda":
+            return torch.cuda.current_stream(self.device).cuda_stream
+        return None
+
+    def call(self, name, *args):
+        self.launches += 1
+        _lib.call(name, *args, self.stream)
+
+    def empty(self, shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.tdtype, device=self.device)
+
+    def zeros(self, shape, dtype=None):
+        return torch.zeros(shape, dtype=dtype or self.tdtype, device=self.device)
+
+
+class Val(object):
+    """A tensor of the lowered program.  kind: 'input' | 'buf' | 'up' | 'cat'.
+    shape is per-sample (H, W, C)."""
+
+    def __init__(self, vid, kind, shape, srcs=(), up=0):
+        self.vid, self.kind, self.shape, self.srcs, self.up = vid, kind, tuple(shape), tuple(srcs), up
+        self.buf = None
+        self.grad = None
+        self.consumers = 0
+        self.grad_is_preact = False      # consumer hands back d/d(pre-activation)
+        self.want_grad = kind == "buf"
+        self.gw = False                  # gradient written during the current backward pass
+
+    def b(self, lo, hi):
+        return self.buf[lo:hi]
+
+    def g(self, lo, hi):
+        return self.grad[lo:hi]
+
+    def take_acc(self):
+        acc = 1 if self.gw else 0
+        self.gw = True
+        return acc
+
+
+def _resolve_src(v):
+    """conv source -> (x1, x2, up_mode) with x1/x2 physical values."""
+    up = 0
+    if v.kind == "up":
+        up = v.up
+        v = v.srcs[0]
+    if v.kind == "cat":
+        a, b = v.srcs
+        if a.kind not in ("buf", "input") or b.kind not in ("buf", "input"):
+            raise NotImplementedError("nested virtual tensors")
+        return a, b, up
+    if v.kind not in ("buf", "input"):
+        raise NotImplementedError("nested virtual tensors")
+    return v, None, up
+
+
+# --------------------------------------------------------------------------- #
+# ops
+# --------------------------------------------------------------------------- #
+class ConvOp(object):
+    """Conv2DLayer / DenseLayer / TransposedConv2DLayer with its bias and epilogue
+    activation.  kind in {'conv', 'dense', 'deconv'}."""
+
+    def __init__(self, net, kind, layer, src, out, act):
+        self.net, self.kind, self.layer, self.out, self.act = net, kind, layer, out, act
+        self.x1, self.x2, self.up = _resolve_src(src)
+        self.src = src
+        self.W, self.bias = layer.params
+        self.C1 = self.x1.shape[2]
+        self.C2 = self.x2.shape[2] if self.x2 is not None else 0
+        self.Cin = self.C1 + self.C2
+        self.Cout = out.shape[2]
+        if kind == "dense":
+            self.kh = self.kw = 1
+            self.stride, self.pad = 1, 0
+        else:
+            self.kh, self.kw = layer.filter_size
+            if layer.stride[0] != layer.stride[1]:
+                raise NotImplementedError("anisotropic stride")
+            self.stride = layer.stride[0]
+            self.pad = layer.pad[0] if kind == "conv" else 0
+            if kind == "conv" and layer.pad[0] != layer.pad[1]:
+                raise NotImplementedError("anisotropic padding")
+        sh = 1 if self.up else 0
+        self.Hv, self.Wv = self.x1.shape[0] << sh, self.x1.shape[1] << sh     # virtual source grid
+        if kind == "deconv":
+            if self.up:
+                raise NotImplementedError("upsampling into a transposed convolution")
+            if not (self.stride == self.kh == self.kw or (self.Hv == 1 and self.Wv == 1)):
+                raise NotImplementedError("overlapping transposed convolution (stride < kernel on a >1x1 input)")
+        self.K = self.kh * self.kw * self.Cin
+        self.wp_f = self.wp_d = self.dwp = self.gup = None
+
+    # -- buffers ------------------------------------------------------------ #
+    def alloc(self, rt, B):
+        n = self.K * self.Cout
+        if self.wp_f is None:
+            self.wp_f = rt.empty((n,))
+            self.wp_d = rt.empty((n,)) if self.kind != "dense" else None
+            self.dwp = rt.empty((n,), torch.float32)
+        if self.up and self.src.srcs[0].kind != "input":
+            self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
+
+    def pack(self, rt):
+        """master (Lasagne layout, fp32) -> packed [K][Cout] copies in the compute dtype."""
+        w = self.net.pview(self.W)
+        if self.kind == "dense":
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 4, self.Cout, self.Cin, 1, 1, 0, 0, rt.cd)
+        elif self.kind == "conv":
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
+                    0, 0, rt.cd)
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 1, self.Cout, self.Cin, self.kh, self.kw,
+                    0, 0, rt.cd)
+        else:
+            per = self.Cin * self.Cout
+            for u in range(self.kh):
+                for v in range(self.kw):
+                    t = u * self.kw + v
+                    rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f[t * per:]), 2, self.Cout, self.Cin,
+                            self.kh, self.kw, u, v, rt.cd)
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 3, self.Cout, self.Cin, self.kh, self.kw,
+                    0, 0, rt.cd)
+
+    # -- descriptors -------------------------------------------------------- #
+    def _fwd_desc(self, rt, n, tap=None):
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W, d.C1, d.C2 = n, self.x1.shape[0], self.x1.shape[1], self.C1, self.C2
+        d.up = self.up
+        d.transposed = 0
+        d.Cout = self.Cout
+        d.split = self.Cout
+        d.act = ACT[self.act.name]
+        d.slope = self.act.slope
+        d.accumulate = 0
+        oH, oW = self.out.shape[0], self.out.shape[1]
+        d.oH, d.oW = oH, oW
+        if self.kind == "deconv":
+            u, v = tap
+            d.kh = d.kw = 1
+            d.stride, d.pad = 1, 0
+            d.Ho, d.Wo = self.Hv, self.Wv
+            d.os, d.ou, d.ov = self.stride, u, v
+        else:
+            d.kh, d.kw, d.stride, d.pad = self.kh, self.kw, self.stride, self.pad
+            d.Ho, d.Wo = oH, oW
+            d.os, d.ou, d.ov = 1, 0, 0
+        return d
+
+    def _dgrad_desc(self, rt, n, acc):
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W = n, self.out.shape[0], self.out.shape[1]
+        d.C1, d.C2, d.up = self.Cout, 0, 0
+        d.kh, d.kw, d.stride = self.kh, self.kw, self.stride
+        d.Ho, d.Wo, d.Cout = self.Hv, self.Wv, self.Cin
+        d.oH, d.oW, d.os, d.ou, d.ov = self.Hv, self.Wv, 1, 0, 0
+        d.split = self.C1
+        d.act, d.slope = 0, 0.0
+        d.accumulate = acc
+        if self.kind == "deconv":
+            d.transposed, d.pad = 0, 0          # input gradient of a transposed conv = strided conv of dy
+        else:
+            d.transposed, d.pad = 1, self.pad
+        return d
+
+    # -- execution ---------------------------------------------------------- #
+    def fwd(self, rt, lo, hi, det):
+        n = hi - lo
+        x1 = _ptr(self.x1.b(lo, hi))
+        x2 = _ptr(self.x2.b(lo, hi)) if self.x2 is not None else None
+        bias = _ptr(self.net.pview(self.bias))
+        y = _ptr(self.out.b(lo, hi))
+        if self.kind == "deconv":
+            per = self.Cin * self.Cout
+            for u in range(self.kh):
+                for v in range(self.kw):
+                    d = self._fwd_desc(rt, n, (u, v))
+                    rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f[(u * self.kw + v) * per:]),
+                            bias, y, None)
+        else:
+            d = self._fwd_desc(rt, n)
+            rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f), bias, y, None)
+
+    def bwd(self, rt, lo, hi, wgrad, input_grad):
+        n = hi - lo
+        g = self.out.g(lo, hi)
+        if self.act.name != "linear" and not self.out.grad_is_preact:
+            rt.call("hm_act_bwd", _ptr(g), _ptr(self.out.b(lo, hi)), _ptr(g), rt.cd, g.numel(),
+                    ACT[self.act.name], self.act.slope, 0)
+        x1 = _ptr(self.x1.b(lo, hi))
+        x2 = _ptr(self.x2.b(lo, hi)) if self.x2 is not None else None
+        if wgrad:
+            self.dwp.zero_()
+            if self.kind == "deconv":
+                per = self.Cin * self.Cout
+                for u in range(self.kh):
+                    for v in range(self.kw):
+                        d = self._fwd_desc(rt, n, (u, v))
+                        rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
+                                _ptr(self.dwp[(u * self.kw + v) * per:]))
+                mode = 2
+            else:
+                d = self._fwd_desc(rt, n)
+                rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g), _ptr(self.dwp))
+                mode = 4 if self.kind == "dense" else 0
+            rt.call("hm_unpack_conv_wgrad", _ptr(self.dwp), _ptr(self.net.gview(self.W)), mode, self.Cout,
+                    self.Cin, self.kh, self.kw)
+            M = n * self.out.shape[0] * self.out.shape[1]
+            db = self.net.gview(self.bias)
+            db.zero_()
+            rt.call("hm_col_sum", _ptr(g), rt.cd, M, self.Cout, _ptr(db))
+        # input gradient
+        t1 = self.x1.want_grad or (input_grad and self.x1.kind == "input" and self.x1.grad is not None)
+        t2 = self.x2 is not None and (self.x2.want_grad or (input_grad and self.x2.kind == "input"
+                                                             and self.x2.grad is not None))
+        if not (t1 or t2):
+            return
+        if self.kind == "dense":
+            raise NotImplementedError("input gradient of a DenseLayer (only ever fed by the latent input)")
+        if self.up:
+            # gradient on the virtual (2x) grid, then the adjoint of the resampling
+            d = self._dgrad_desc(rt, n, 0)
+            gu = self.gup[lo:hi]
+            flat = gu.view(-1)
+            n1 = n * self.Hv * self.Wv * self.C1
+            y1 = flat[:n1] if t1 else None
+            y2 = flat[n1:] if t2 else None
+            rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, _ptr(y1), _ptr(y2))
+            for (x, y, c) in ((self.x1, y1, self.C1), (self.x2, y2, self.C2)):
+                if y is None:
+                    continue
+                rt.call("hm_upsample2_bwd", _ptr(y), _ptr(x.g(lo, hi)), rt.cd, n, x.shape[0], x.shape[1], c,
+                        self.up, x.take_acc())
+        else:
+            acc = (self.x1.take_acc() if t1 else 0) | ((self.x2.take_acc() << 1) if t2 else 0)
+            d = self._dgrad_desc(rt, n, acc)
+            y1 = _ptr(self.x1.g(lo, hi)) if t1 else None
+            y2 = _ptr(self.x2.g(lo, hi)) if t2 else None
+            rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, y1, y2)
+
+
+class BNActOp(object):
+    """BatchNormLayer (+ the NonlinearityLayer that follows it)."""
+
+    def __init__(self, net, layer, x, out, act):
+        self.net, self.layer, self.x, self.out, self.act = net, layer, x, out, act
+        self.beta, self.gamma, self.mean, self.inv_std = layer.params
+        self.Cn = x.shape[2]
+        self.st = None
+
+    def alloc(self, rt, B):
+        if self.st is None:
+            self.sums = rt.zeros((2 * self.Cn,), torch.float64)
+            self.red = rt.zeros((2 * self.Cn,), torch.float64)
+            self.st = rt.zeros((4, self.Cn), torch.float32)     # batch mean, inv_std, scale, shift
+
+    def pack(self, rt):
+        pass
+
+    def fwd(self, rt, lo, hi, det):
+        n = hi - lo
+        M = n * self.x.shape[0] * self.x.shape[1]
+        net = self.net
+        bm, bi, sc, sf = (self.st[i] for i in range(4))
+        rm, ri = net.sview(self.mean), net.sview(self.inv_std)
+        if det:
+            sums = None
+        else:
+            self.sums.zero_()
+            rt.call("hm_bn_stats", _ptr(self.x.b(lo, hi)), rt.cd, M, self.Cn, _ptr(self.sums))
+            sums = _ptr(self.sums)
+        rt.call("hm_bn_finalize", sums, M, self.Cn, _ptr(net.pview(self.gamma)), _ptr(net.pview(self.beta)),
+                _ptr(rm), _ptr(ri), self.layer.epsilon, self.layer.alpha, 0 if det else 1,
+                _ptr(bm), _ptr(bi), _ptr(sc), _ptr(sf))
+        rt.call("hm_bn_apply_act", _ptr(self.x.b(lo, hi)), _ptr(self.out.b(lo, hi)), rt.cd, M, self.Cn,
+                _ptr(sc), _ptr(sf), ACT[self.act.name], self.act.slope)
+
+    def bwd(self, rt, lo, hi, wgrad, input_grad):
+        n = hi - lo
+        M = n * self.x.shape[0] * self.x.shape[1]
+        net = self.net
+        bm, bi = self.st[0], self.st[1]
+        da, a, x = self.out.g(lo, hi), self.out.b(lo, hi), self.x.b(lo, hi)
+        self.red.zero_()
+        rt.call("hm_bn_bwd_reduce", _ptr(da), _ptr(a), _ptr(x), rt.cd, M, self.Cn, _ptr(bm), _ptr(bi),
+                ACT[self.act.name], self.act.slope, _ptr(self.red))
+        assert self.x.consumers == 1
+        self.x.gw = True
+        rt.call("hm_bn_bwd_apply", _ptr(da), _ptr(a), _ptr(x), _ptr(self.x.g(lo, hi)), rt.cd, M, self.Cn,
+                _ptr(bm), _ptr(bi), _ptr(net.pview(self.gamma)), ACT[self.act.name], self.act.slope,
+                _ptr(self.red), _ptr(net.gview(self.gamma)) if wgrad else None,
+                _ptr(net.gview(self.beta)) if wgrad else None)
+
+
+class PoolOp(object):
+    """MaxPool2DLayer(2).  Its backward is fused with the backward of the monotonic
+    activation that the producing convolution applied in its epilogue."""
+
+    def __init__(self, net, x, out, act):
+        self.net, self.x, self.out, self.act = net, x, out, act
+        self.idx = None
+
+    def alloc(self, rt, B):
+        H, W, Cn = self.out.shape
+        self.idx = torch.empty((B, H, W, Cn), dtype=torch.uint8, device=rt.device)
+
+    def pack(self, rt):
+        pass
+
+    def fwd(self, rt, lo, hi, det):
+        H, W, Cn = self.x.shape
+        rt.call("hm_maxpool2_fwd", _ptr(self.x.b(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
+                rt.cd, hi - lo, H, W, Cn)
+
+    def bwd(self, rt, lo, hi, wgrad, input_grad):
+        H, W, Cn = self.x.shape
+        assert self.x.consumers == 1
+        self.x.gw = True
+        rt.call("hm_maxpool2_bwd", _ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
+                _ptr(self.x.g(lo, hi)), rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope)
+
+
+class PermuteOp(object):
+    """ReshapeLayer((-1, C, H, W)) of a flat feature vector: NCHW order -> NHWC buffer."""
+
+    def __init__(self, net, x, out):
+        self.net, self.x, self.out = net, x, out
+
+    def alloc(self, rt, B):
+        pass
+
+    def pack(self, rt):
+        pass
+
+    def fwd(self, rt, lo, hi, det):
+        H, W, Cn = self.out.shape
+        rt.call("hm_permute", _ptr(self.x.b(lo, hi)), _ptr(self.out.b(lo, hi)), rt.cd, hi - lo, Cn, H, W, 0)
+
+    def bwd(self, rt, lo, hi, wgrad, input_grad):
+        H, W, Cn = self.out.shape
+        assert self.x.consumers == 1
+        self.x.gw = True
+        rt.call("hm_permute", _ptr(self.out.g(lo, hi)), _ptr(self.x.g(lo, hi)), rt.cd, hi - lo, Cn, H, W, 1)
+
+
+# --------------------------------------------------------------------------- #
+# network
+# --------------------------------------------------------------------------- #
+class Net(object):
+    """One lowered network: parameters (flat fp32 master copies in Lasagne's
+    get_all_params order), program, buffers."""
+
+    def __init__(self, rt, out_layer, input_layers=None, name="net", rng=None):
+        self.rt, self.name = rt, name
+        self.layers = L.get_all_layers(out_layer)
+        if input_layers is None:
+            input_layers = [l for l in self.layers if isinstance(l, L.InputLayer)]
+        self.input_layers = list(input_layers)
+        self.vals, self.ops, self._memo = [], [], {}
+        self.inputs = []
+        for il in self.input_layers:
+            s = il.shape
+            shape = (1, 1, s[1]) if len(s) == 2 else (s[2], s[3], s[1])
+            v = self._new("input", shape)
+            self._memo[(id(il), "linear", 0.0)] = v
+            self.inputs.append(v)
+        self.head = None
+        body = self._strip_head(out_layer)
+        self.out = self._lower(body, None)
+        if self.out.kind != "buf":
+            raise NotImplementedError("network output must be a materialised tensor")
+        if self.head is not None and self.head["relu_head"]:
+            self.out.grad_is_preact = True
+        # pooled activations hand back pre-activation gradients
+        for op in self.ops:
+            if isinstance(op, PoolOp) and op.x.consumers == 1 and op.act.name != "linear":
+                op.x.grad_is_preact = True
+        # parameters
+        self.params = L.get_all_params(out_layer)
+        self._loc = {}
+        nt = ns = 0
+        for p in self.params:
+            if p.trainable:
+                self._loc[id(p)] = ("p", nt)
+                nt += p.size
+            else:
+                self._loc[id(p)] = ("s", ns)
+                ns += p.size
+        self.n_trainable, self.n_stats = nt, ns
+        self.pflat = rt.zeros((max(nt, 1),), torch.float32)
+        self.gflat = rt.zeros((max(nt, 1),), torch.float32)
+        self.sflat = rt.zeros((max(ns, 1),), torch.float32)
+        self.opt_state = {}
+        self.B = 0
+        if rng is not None:
+            self.set_all_param_values([L.init_param(rng, p) for p in self.params])
+
+    # -- lowering ----------------------------------------------------------- #
+    def _new(self, kind, shape, srcs=(), up=0):
+        v = Val(len(self.vals), kind, shape, srcs, up)
+        self.vals.append(v)
+        for s in srcs:
+            s.consumers += 1
+        return v
+
+    def _strip_head(self, out_layer):
+        """Detect NonlinearityLayer(ReshapeLayer(Pool2DLayer(avg, full extent)(conv)), f)."""
+        l = out_layer
+        if isinstance(l, L.NonlinearityLayer) and isinstance(l.input_layer, L.ReshapeLayer) and \
+                isinstance(l.input_layer.input_layer, L.Pool2DLayer) and \
+                l.input_layer.input_layer.mode.startswith("average"):
+            pool = l.input_layer.input_layer
+            conv = pool.input_layer
+            s = conv.output_shape
+            if pool.pool_size != (s[2], s[3]) or s[1] != 1 or l.input_layer.shape != (-1, 1):
+                raise NotImplementedError(
+                    "discriminator head: the average pool (size %r, derived from nch) must cover the %dx%d "
+                    "feature map, i.e. nch == in_shp (reference architectures/dcgan.py:51-52)"
+                    % (pool.pool_size, s[2], s[3]))
+            f = L.as_nonlinearity(l.nonlinearity)
+            if f.name not in ("linear", "sigmoid"):
+                raise NotImplementedError("head nonlinearity %r" % f)
+            cf = getattr(conv, "nonlinearity", L.linear)
+            if cf.name not in ("linear", "rectify"):
+                raise NotImplementedError("head convolution nonlinearity %r" % cf)
+            self.head = dict(G=s[2] * s[3], out_act=f.name, relu_head=cf.name == "rectify")
+            return conv
+        return out_layer
+
+    @staticmethod
+    def _compose(inner, outer):
+        if outer is None or outer.name == "linear":
+            return inner
+        if inner.name == "linear":
+            return outer
+        raise NotImplementedError("two stacked nonlinearities %r, %r" % (inner, outer))
+
+    def _lower(self, layer, act):
+        a = act or L.linear
+        key = (id(layer), a.name, a.slope)
+        if key in self._memo:
+            return self._memo[key]
+        v = self._lower_uncached(layer, a)
+        self._memo[key] = v
+        return v
+
+    def _lower_uncached(self, layer, act):
+        if isinstance(layer, L.InputLayer):
+            if act.name != "linear":
+                raise NotImplementedError("nonlinearity applied directly to a network input")
+            raise ValueError("input layer %r was not declared" % layer)
+        if isinstance(layer, L.NonlinearityLayer):
+            return self._lower(layer.input_layer, self._compose(layer.nonlinearity, act))
+        if isinstance(layer, L.DropoutLayer):
+            if layer.p > 0:
+                raise NotImplementedError("dropout is disabled in every experiment of the reference "
+                                          "(SURVEY.md appendix A); p>0 is not implemented")
+            return self._lower(layer.input_layer, act)
+        if isinstance(layer, L.ConcatLayer):
+            srcs = [self._lower(i, act) for i in layer.input_layers]
+            if len(srcs) != 2:
+                raise NotImplementedError("concatenation of %d tensors" % len(srcs))
+            s = layer.output_shape
+            return self._new("cat", (s[2], s[3], s[1]), srcs)
+        if isinstance(layer, (L.Upscale2DLayer, BilinearUpsample2DLayer)):
+            if act.name != "linear":
+                raise NotImplementedError("nonlinearity after an upsampling layer")
+            src = self._lower(layer.input_layer, None)
+            s = layer.output_shape
+            mode = _lib.UP_NEAREST2 if isinstance(layer, L.Upscale2DLayer) else _lib.UP_BILINEAR2
+            return self._new("up", (s[2], s[3], s[1]), [src], up=mode)
+        if isinstance(layer, L.BatchNormLayer):
+            x = self._lower(layer.input_layer, None)
+            if x.kind != "buf":
+                raise NotImplementedError("BatchNorm of a virtual tensor")
+            out = self._new("buf", x.shape, [x])
+            self.ops.append(BNActOp(self, layer, x, out, act))
+            return out
+        if isinstance(layer, L.ReshapeLayer):
+            if act.name != "linear":
+                raise NotImplementedError("nonlinearity after a reshape")
+            x = self._lower(layer.input_layer, None)
+            shp = layer.shape
+            if len(shp) != 4 or x.shape[:2] != (1, 1) or shp[1] * shp[2] * shp[3] != x.shape[2]:
+                raise NotImplementedError("reshape %r" % (shp,))
+            out = self._new("buf", (shp[2], shp[3], shp[1]), [x])
+            self.ops.append(PermuteOp(self, x, out))
+            return out
+        if isinstance(layer, L.Pool2DLayer):
+            if layer.mode != "max" or layer.pool_size != (2, 2):
+                raise NotImplementedError("pooling mode %r size %r (every experiment uses 2x2 max pooling)"
+                                          % (layer.mode, layer.pool_size))
+            if act.name != "linear":
+                raise NotImplementedError("nonlinearity after a pooling layer")
+            x = self._lower(layer.input_layer, None)
+            if x.kind != "buf":
+                raise NotImplementedError("pooling of a virtual tensor")
+            s = layer.output_shape
+            out = self._new("buf", (s[2], s[3], s[1]), [x])
+            # which activation produced x (for the fused backward)?
+            prod = [o for o in self.ops if getattr(o, "out", None) is x]
+            pact = prod[0].act if prod and isinstance(prod[0], ConvOp) else L.linear
+            if pact.name not in ("linear", "leaky_rectify", "rectify"):
+                pact = L.linear
+            self.ops.append(PoolOp(self, x, out, pact))
+            return out
+        if isinstance(layer, (L.Conv2DLayer, L.TransposedConv2DLayer, L.DenseLayer)):
+            src = self._lower(layer.input_layer, None)
+            s = layer.output_shape
+            if isinstance(layer, L.DenseLayer):
+                kind, shape = "dense", (1, 1, s[1])
+                if src.shape[:2] != (1, 1):
+                    raise NotImplementedError("DenseLayer on a spatial tensor")
+            else:
+                kind = "conv" if isinstance(layer, L.Conv2DLayer) else "deconv"
+                shape = (s[2], s[3], s[1])
+            out = self._new("buf", shape, [src])
+            self.ops.append(ConvOp(self, kind, layer, src, out, self._compose(layer.nonlinearity, act)))
+            return out
+        raise NotImplementedError("layer %r is not on the hot path" % layer)
+
+    # -- parameters --------------------------------------------------------- #
+    def _view(self, flat, p):
+        _, off = self._loc[id(p)]
+        return flat[off:off + p.size]
+
+    def pview(self, p):
+        return self._view(self.pflat if p.trainable else self.sflat, p)
+
+    def sview(self, p):
+        return self._view(self.sflat, p)
+
+    def gview(self, p):
+        return self._view(self.gflat, p)
+
+    def get_all_param_values(self):
+        return [self.pview(p).detach().cpu().numpy().reshape(p.shape).copy() for p in self.params]
+
+    def set_all_param_values(self, values):
+        if len(values) != len(self.params):
+            raise ValueError("mismatch: got %d values to set %d parameters" % (len(values), len(self.params)))
+        for p, v in zip(self.params, values):
+            v = np.asarray(v, dtype=np.float32)
+            if v.shape != p.shape:
+                raise ValueError("mismatch: parameter has shape %r but value to set has shape %r"
+                                 % (p.shape, v.shape))
+            self.pview(p).copy_(torch.from_numpy(np.ascontiguousarray(v).reshape(-1)))
+        self._packed = False
+
+    def get_grads(self):
+        return [self.gview(p).detach().cpu().numpy().reshape(p.shape).copy() for p in self.params if p.trainable]
+
+    # -- buffers / execution ------------------------------------------------ #
+    def ensure(self, B, input_grads=()):
+        rt = self.rt
+        if B > self.B:
+            for v in self.vals:
+                if v.kind == "buf":
+                    v.buf = rt.empty((B,) + v.shape)
+                    v.grad = rt.empty((B,) + v.shape)
+                elif v.kind == "input":
+                    v.buf = rt.empty((B,) + v.shape)
+            for op in self.ops:
+                op.alloc(rt, B)
+            self.B = B
+            self._packed = False
+        for i in input_grads:
+            v = self.inputs[i]
+            if v.grad is None or v.grad.shape[0] < self.B:
+                v.grad = rt.empty((self.B,) + v.shape)
+
+    def pack(self):
+        for op in self.ops:
+            op.pack(self.rt)
+        self._packed = True
+
+    def forward(self, B, lo=0, hi=None, deterministic=False):
+        """Inputs must already be in self.inputs[i].buf[lo:hi]."""
+        hi = B if hi is None else hi
+        if not self._packed:
+            self.pack()
+        for op in self.ops:
+            op.fwd(self.rt, lo, hi, deterministic)
+        return self.out.buf[lo:hi]
+
+    def backward(self, lo, hi, wgrad=True, input_grad=False):
+        """self.out.grad[lo:hi] must hold d loss / d out."""
+        for v in self.vals:
+            v.gw = False
+        self.out.gw = True
+        for op in reversed(self.ops):
+            op.bwd(self.rt, lo, hi, wgrad, input_grad)
+
+    def apply_update(self, opt, lr_dev, gscale, hyper):
+        """lasagne.updates.rmsprop / adam over the whole flat parameter vector."""
+        rt, n = self.rt, self.n_trainable
+        if n == 0:
+            return
+        if opt == "rmsprop":
+            if "acc" not in self.opt_state:
+                self.opt_state["acc"] = rt.zeros((n,), torch.float32)
+            rt.call("hm_rmsprop", _ptr(self.pflat), _ptr(self.gflat), _ptr(self.opt_state["acc"]), n,
+                    _ptr(lr_dev), hyper.get("rho", 0.9), hyper.get("epsilon", 1e-6), gscale)
+        elif opt == "adam":
+            if "m" not in self.opt_state:
+                self.opt_state["m"] = rt.zeros((n,), torch.float32)
+                self.opt_state["v"] = rt.zeros((n,), torch.float32)
+                self.opt_state["t"] = 0
+            self.opt_state["t"] += 1
+            rt.call("hm_adam", _ptr(self.pflat), _ptr(self.gflat), _ptr(self.opt_state["m"]),
+                    _ptr(self.opt_state["v"]), n, _ptr(lr_dev), hyper.get("beta1", 0.9),
+                    hyper.get("beta2", 0.999), hyper.get("epsilon", 1e-8), self.opt_state["t"], gscale)
+        else:
+            raise NotImplementedError("optimiser %r" % opt)
+        self._packed = False

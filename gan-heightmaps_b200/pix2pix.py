@@ -1,0 +1,429 @@
+"""Two-stage DCGAN / pix2pix trainer with the reference's object surface
+(reference pix2pix.py:19-425), executing on B200 through the hmgan kernel library.
+
+What Theano compiled from the symbolic graph (pix2pix.py:87-147) is written out
+here as an explicit step: four lowered networks (engine.Net), the five losses,
+gradients of four losses with respect to four disjoint parameter sets evaluated
+at the OLD parameters, and one simultaneous update.  The six callables keep
+their names and their numpy NCHW float32 calling convention:
+
+    train_fn(Z, X, Y) -> [dcgan_gen, dcgan_disc, p2p_gen, p2p_recon, p2p_disc]
+    loss_fn(Z, X, Y)  -> same, without parameter updates (BatchNorm running
+                         averages still move: the graph is non-deterministic,
+                         pix2pix.py:92,99)
+    gen_fn / gen_fn_det (X) -> P(X);   z_fn / z_fn_det (Z) -> G(z)
+
+Differences from the reference, all additive:
+  * discriminators see real and fake samples as one 2B batch (they have no
+    BatchNorm in any experiment), which is arithmetically the same as two
+    applications with shared weights;
+  * gen_fn_p2p=None builds a DCGAN-only model (the 64-px gate of BASELINE.json);
+  * keyword-only extras: device, precision ('parity' fp32 | 'fast' fp16), seed,
+    process_group (data-parallel gradient all-reduce over NCCL).
+"""
+import gzip
+import os
+import pickle
+from time import time
+
+import numpy as np
+import torch
+
+import _lib
+import engine
+import lasagne_compat as L
+from lasagne_compat import adam, floatX, shared
+from util import convert_to_rgb, plot_grid, imsave
+
+_ptr = engine._ptr
+
+
+class Pix2Pix(object):
+    def _print_network(self, l_out):
+        for layer in L.get_all_layers(l_out):
+            print(layer, layer.output_shape, "" if not hasattr(layer, 'nonlinearity') else layer.nonlinearity)
+        print("# learnable params:", L.count_params(l_out, trainable=True))
+
+    def __init__(self,
+                 gen_fn_dcgan, disc_fn_dcgan,
+                 gen_params_dcgan, disc_params_dcgan,
+                 gen_fn_p2p, disc_fn_p2p,
+                 gen_params_p2p, disc_params_p2p,
+                 in_shp, latent_dim, is_a_grayscale, is_b_grayscale,
+                 alpha=100, opt=adam, opt_args=None,
+                 train_mode='both', reconstruction='l1', sampler=np.random.rand, lsgan=False, verbose=True,
+                 device="cuda", precision=None, seed=None, process_group=None, loss_scale=None):
+        assert train_mode in ['dcgan', 'p2p', 'both']
+        assert reconstruction in ['l1', 'l2']
+        if opt_args is None:
+            opt_args = {'learning_rate': shared(floatX(1e-3))}
+        self.is_a_grayscale = is_a_grayscale
+        self.is_b_grayscale = is_b_grayscale
+        self.latent_dim = latent_dim
+        self.sampler = sampler
+        self.in_shp = in_shp
+        self.verbose = verbose
+        self.train_mode = train_mode
+        self.alpha = float(alpha)
+        self.reconstruction = reconstruction
+        self.lsgan = lsgan
+        if precision is None:
+            precision = os.environ.get("HMGAN_PRECISION", "parity")
+        self.rt = rt = engine.Runtime(device, precision, loss_scale)
+        self.pg = process_group
+        # the reference draws its Glorot weights from the global, unseeded np.random
+        rng = np.random.RandomState(seed) if seed is not None else np.random.mtrand._rand
+        self.have_dcgan = gen_fn_dcgan is not None
+        self.have_p2p = gen_fn_p2p is not None
+        dcgan_gen = dcgan_disc = p2p_gen = p2p_disc = None
+        if self.have_dcgan:
+            dcgan_gen = gen_fn_dcgan(latent_dim, is_a_grayscale, **gen_params_dcgan)
+            dcgan_disc = disc_fn_dcgan(in_shp, is_a_grayscale, **disc_params_dcgan)
+        if self.have_p2p:
+            p2p_gen = gen_fn_p2p(in_shp, is_a_grayscale, is_b_grayscale, **gen_params_p2p)
+            p2p_disc = disc_fn_p2p(in_shp, is_a_grayscale, is_b_grayscale, **disc_params_p2p)
+        if verbose:
+            for tag, net in (("dcgan gen:", dcgan_gen), ("dcgan disc:", dcgan_disc), ("p2p gen:", p2p_gen),
+                             ("p2p disc:", p2p_disc["out"] if p2p_disc else None)):
+                if net is not None:
+                    print(tag)
+                    self._print_network(net)
+        self.dcgan = {'gen': dcgan_gen, 'disc': dcgan_disc}
+        self.p2p = {'gen': p2p_gen, 'disc': p2p_disc["out"] if p2p_disc else None}
+        self.G = self.D = self.P = self.Dp = None
+        if self.have_dcgan:
+            self.G = engine.Net(rt, dcgan_gen, name="dcgan_gen", rng=rng)
+            self.D = engine.Net(rt, dcgan_disc, name="dcgan_disc", rng=rng)
+        if self.have_p2p:
+            self.P = engine.Net(rt, p2p_gen, name="p2p_gen", rng=rng)
+            self.Dp = engine.Net(rt, p2p_disc["out"], input_layers=p2p_disc["inputs"], name="p2p_disc", rng=rng)
+        self.nets = {'dcgan': {'gen': self.G, 'disc': self.D}, 'p2p': {'gen': self.P, 'disc': self.Dp}}
+        # optimiser
+        if not isinstance(opt, L._Optimiser):
+            raise TypeError("opt must be lasagne_compat.rmsprop or lasagne_compat.adam")
+        self.opt = opt.name
+        hyper = dict(opt.defaults)
+        hyper.update({k: v for k, v in opt_args.items() if k != 'learning_rate'})
+        self.opt_hyper = hyper
+        lr = opt_args.get('learning_rate', opt.defaults['learning_rate'])
+        if not hasattr(lr, 'get_value'):
+            lr = shared(floatX(lr))
+        self.lr = lr
+        self._lr_dev = rt.zeros((1,), torch.float32)
+        self._lr_host = None
+        self.losses = rt.zeros((5,), torch.float32)
+        self.train_keys = ['dcgan_gen', 'dcgan_disc', 'p2p_gen', 'p2p_recon', 'p2p_disc']
+        self._stage = {}
+        self.train_fn = lambda Z, X, Y: self._step_host(Z, X, Y, True)
+        self.loss_fn = lambda Z, X, Y: self._step_host(Z, X, Y, False)
+        self.gen_fn = lambda X: self._gen_p2p(X, False)
+        self.gen_fn_det = lambda X: self._gen_p2p(X, True)
+        self.z_fn = lambda Z: self._gen_dcgan(Z, False)
+        self.z_fn_det = lambda Z: self._gen_dcgan(Z, True)
+
+    # ------------------------------------------------------------------ #
+    # host <-> device staging
+    # ------------------------------------------------------------------ #
+    def _to_dev(self, name, a):
+        """numpy float32 -> device float32 staging buffer (reused across steps)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        t = self._stage.get(name)
+        if t is None or t.shape != a.shape:
+            t = self.rt.empty(a.shape, torch.float32)
+            self._stage[name] = t
+        t.copy_(torch.from_numpy(a), non_blocking=False)
+        return t
+
+    def _load_nchw(self, src_f32, dst, B, Cn, H, W):
+        """NCHW float32 device tensor -> NHWC compute-dtype buffer dst[:B]."""
+        self.rt.call("hm_nchw_to_nhwc", _ptr(src_f32), _ptr(dst), self.rt.cd, B, Cn, H, W)
+
+    def _store_nchw(self, src, B, Cn, H, W):
+        out = self.rt.empty((B, Cn, H, W), torch.float32)
+        self.rt.call("hm_nhwc_to_nchw", _ptr(src), _ptr(out), self.rt.cd, B, Cn, H, W)
+        return out
+
+    def _copy(self, src, dst):
+        self.rt.call("hm_cast", _ptr(src), self.rt.cd, _ptr(dst), self.rt.cd, src.numel())
+
+    def _sync_lr(self):
+        v = float(self.lr.get_value())
+        if v != self._lr_host:
+            self._lr_dev.fill_(v)
+            self._lr_host = v
+
+    # ------------------------------------------------------------------ #
+    # the step (reference pix2pix.py:87-147)
+    # ------------------------------------------------------------------ #
+    def _adv(self, net, h, dh, target, slot, gscale):
+        """adv_loss(out, target).mean() of pix2pix.py:102-110 on a (half) batch of
+        discriminator outputs; optionally its gradient."""
+        head = net.head or dict(G=1, out_act="linear", relu_head=False)
+        R = h.numel() // head["G"]
+        self.rt.call("hm_adv_loss", _ptr(h), _ptr(dh), self.rt.cd, R, head["G"], _lib.ACT[head["out_act"]],
+                     float(target), 1 if self.lsgan else 0, 1 if head["relu_head"] else 0, 1.0, gscale, 0,
+                     _ptr(self.losses[slot:]))
+
+    def step_device(self, Zd, Xd, Yd, train=True):
+        """One train_fn / loss_fn evaluation on float32 NCHW DEVICE tensors; the five
+        losses stay on the device in self.losses (no host synchronisation)."""
+        rt = self.rt
+        B = int(Xd.shape[0])
+        S = self.in_shp
+        ls = rt.loss_scale
+        self.losses.zero_()
+        upd = []
+        if self.have_dcgan:
+            G, D = self.G, self.D
+            do = train and self.train_mode in ('both', 'dcgan')
+            G.ensure(B)
+            D.ensure(2 * B, input_grads=(0,))
+            ca = 1 if self.is_a_grayscale else 3
+            rt.call("hm_cast", _ptr(Zd), _lib.F32, _ptr(G.inputs[0].buf), rt.cd, Zd.numel())
+            self._load_nchw(Xd, D.inputs[0].buf, B, ca, S, S)
+            gz = G.forward(B)                                               # G(z)            :92
+            self._copy(gz, D.inputs[0].buf[B:2 * B])
+            h = D.forward(2 * B)                                            # D(x), D(G(z))   :94-95
+            dh = D.out.grad if do else None
+            self._adv(D, h[:B], dh[:B] if do else None, 1., 1, ls)          # disc_loss_dcgan :108
+            self._adv(D, h[B:], dh[B:2 * B] if do else None, 0., 1, ls)
+            if do:
+                D.backward(0, 2 * B, wgrad=True, input_grad=False)
+            self._adv(D, h[B:], dh[B:2 * B] if do else None, 1., 0, ls)     # gen_loss_dcgan  :107
+            if do:
+                D.backward(B, 2 * B, wgrad=False, input_grad=True)
+                self._copy(D.inputs[0].grad[B:2 * B], G.out.grad[:B])
+                G.backward(0, B, wgrad=True)
+                upd += [G, D]
+        if self.have_p2p:
+            P, Dp = self.P, self.Dp
+            do = train and self.train_mode in ('both', 'p2p')
+            P.ensure(B)
+            Dp.ensure(2 * B, input_grads=(1,))
+            ca = 1 if self.is_a_grayscale else 3
+            cb = 1 if self.is_b_grayscale else 3
+            self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S)
+            a_in, b_in = Dp.inputs
+            self._load_nchw(Xd, a_in.buf, B, ca, S, S)
+            self._copy(a_in.buf[:B], a_in.buf[B:2 * B])
+            self._load_nchw(Yd, b_in.buf, B, cb, S, S)
+            px = P.forward(B)                                               # P(X)            :99
+            self._copy(px, b_in.buf[B:2 * B])
+            h = Dp.forward(2 * B)                                           # Dp(X,Y), Dp(X,P(X)) :98,101
+            dh = Dp.out.grad if do else None
+            self._adv(Dp, h[:B], dh[:B] if do else None, 1., 4, ls)         # disc_loss_p2p   :121
+            self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 0., 4, ls)
+            if do:
+                Dp.backward(0, 2 * B, wgrad=True, input_grad=False)
+            self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 1., 2, ls)   # gen_loss_p2p :110
+            dpx = None
+            if do:
+                Dp.backward(B, 2 * B, wgrad=False, input_grad=True)
+                dpx = b_in.grad[B:2 * B]
+            # recon_loss :112-115 ; gradient weight alpha (gen_total_loss_p2p :117)
+            rt.call("hm_recon_loss", _ptr(px), _ptr(b_in.buf[:B]), _ptr(dpx), rt.cd, px.numel(),
+                    1 if self.reconstruction == 'l2' else 0, 1.0, ls * self.alpha, 1, _ptr(self.losses[3:]))
+            if do:
+                self._copy(dpx, P.out.grad[:B])
+                P.backward(0, B, wgrad=True)
+                upd += [P, Dp]
+        if upd:
+            self._sync_lr()
+            world = 1
+            if self.pg is not None:
+                import torch.distributed as dist
+                world = dist.get_world_size(self.pg)
+                for net in upd:                                  # data-parallel: sum of per-rank mean gradients
+                    dist.all_reduce(net.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+            for net in upd:
+                net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
+        return self.losses
+
+    def _step_host(self, Z, X, Y, train):
+        Zd = self._to_dev("Z", Z)
+        Xd = self._to_dev("X", X)
+        Yd = self._to_dev("Y", Y)
+        losses = self.step_device(Zd, Xd, Yd, train).cpu().numpy()
+        return [np.float32(v) for v in losses]
+
+    def _gen_dcgan(self, Z, det):
+        if not self.have_dcgan:
+            raise RuntimeError("this model was built without a DCGAN")
+        Zd = self._to_dev("Z", Z)
+        B = Zd.shape[0]
+        G = self.G
+        G.ensure(B)
+        self.rt.call("hm_cast", _ptr(Zd), _lib.F32, _ptr(G.inputs[0].buf), self.rt.cd, Zd.numel())
+        out = G.forward(B, deterministic=det)
+        H, W, Cn = G.out.shape
+        return self._store_nchw(out, B, Cn, H, W).cpu().numpy()
+
+    def _gen_p2p(self, X, det):
+        if not self.have_p2p:
+            raise RuntimeError("this model was built without a pix2pix stage")
+        Xd = self._to_dev("X", X)
+        B, ca, S, _ = Xd.shape
+        P = self.P
+        P.ensure(B)
+        self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S)
+        out = P.forward(B, deterministic=det)
+        H, W, Cn = P.out.shape
+        return self._store_nchw(out, B, Cn, H, W).cpu().numpy()
+
+    # ------------------------------------------------------------------ #
+    # checkpoints (reference pix2pix.py:158-186): gzip-pickle of
+    # get_all_param_values lists
+    # ------------------------------------------------------------------ #
+    def save_model(self, filename):
+        def vals(net):
+            return net.get_all_param_values() if net is not None else []
+        with gzip.open(filename, "wb") as g:
+            pickle.dump({'dcgan': {'gen': vals(self.G), 'disc': vals(self.D)},
+                         'p2p': {'gen': vals(self.P), 'disc': vals(self.Dp)}}, g, pickle.HIGHEST_PROTOCOL)
+
+    def load_model(self, filename, mode='both'):
+        assert mode in ['both', 'dcgan', 'p2p']
+        with gzip.open(filename) as g:
+            dd = pickle.load(g, encoding='latin1')      # reference checkpoints are Python-2 pickles
+        if mode in ('both', 'dcgan'):
+            self.G.set_all_param_values(dd['dcgan']['gen'])
+            self.D.set_all_param_values(dd['dcgan']['disc'])
+        if mode in ('both', 'p2p'):
+            self.P.set_all_param_values(dd['p2p']['gen'])
+            self.Dp.set_all_param_values(dd['p2p']['disc'])
+
+    # ------------------------------------------------------------------ #
+    # training loop (reference pix2pix.py:187-275)
+    # ------------------------------------------------------------------ #
+    def train(self, it_train, it_val, batch_size, num_epochs, out_dir, model_dir=None, save_every=10,
+              resume=False, quick_run=False):
+        def _loop(fn, itr):
+            rec = [[] for _ in range(len(self.train_keys))]
+            for b in range(itr.N // batch_size):
+                X_batch, Y_batch = it_train.next()      # sic: the reference reads it_train here too (:204)
+                Z_batch = floatX(self.sampler(X_batch.shape[0], self.latent_dim))
+                results = fn(Z_batch, X_batch, Y_batch)
+                for i in range(len(results)):
+                    rec[i].append(results[i])
+                if quick_run:
+                    break
+            return tuple([np.mean(elem) for elem in rec])
+        header = ["epoch"] + ["train_%s" % k for k in self.train_keys] + ["valid_%s" % k for k in self.train_keys]
+        header += ["lr", "time", "mode"]
+        if not os.path.exists(out_dir):
+            os.makedirs(out_dir)
+        if model_dir is not None and not os.path.exists(model_dir):
+            os.makedirs(model_dir)
+        f = open("%s/results.txt" % out_dir, "w" if not resume else "a")
+        if not resume:
+            f.write(",".join(header) + "\n")
+            f.flush()
+            print(",".join(header))
+        else:
+            if self.verbose:
+                print("loading weights from: %s" % resume)
+            self.load_model(resume)
+        for e in range(num_epochs):
+            out_str = [str(e + 1)]
+            t0 = time()
+            out_str += [str(r) for r in _loop(self.train_fn, it_train)]
+            out_str += [str(r) for r in _loop(self.loss_fn, it_val)]
+            out_str.append(str(self.lr.get_value()))
+            out_str.append(str(time() - t0))
+            out_str.append(self.train_mode)
+            out_str = ",".join(out_str)
+            print(out_str)
+            f.write("%s\n" % out_str)
+            f.flush()
+            if self.train_mode in ['both', 'p2p'] and self.have_p2p:
+                plot_grid("%s/out_%i.png" % (out_dir, e + 1), it_val, self.gen_fn,
+                          is_a_grayscale=self.is_a_grayscale, is_b_grayscale=self.is_b_grayscale)
+                self.generate_atob(it_train, 1, "%s/dump_train" % out_dir, deterministic=False)
+                self.generate_atob(it_val, 1, "%s/dump_valid" % out_dir, deterministic=False)
+            if self.train_mode in ['both', 'dcgan'] and self.have_dcgan:
+                self.generate_gz(num_examples=20, batch_size=batch_size, out_dir="%s/dump_a" % out_dir,
+                                 deterministic=False)
+            if model_dir is not None and (e + 1) % save_every == 0:
+                self.save_model("%s/%i.model" % (model_dir, e + 1))
+        f.close()
+
+    # ------------------------------------------------------------------ #
+    # sampling (reference pix2pix.py:276-425)
+    # ------------------------------------------------------------------ #
+    def generate_atob(self, itr, num_batches, out_dir, dont_predict=False, deterministic=True):
+        fn = self.gen_fn if not deterministic else self.gen_fn_det
+        if not os.path.exists(out_dir):
+            os.makedirs(out_dir)
+        ctr = 0
+        for n in range(num_batches):
+            this_x, this_y = itr.next()
+            pred_y = this_y if dont_predict else fn(this_x)
+            for i in range(pred_y.shape[0]):
+                imsave("%s/%i.a.png" % (out_dir, ctr), convert_to_rgb(this_x[i], is_grayscale=self.is_a_grayscale))
+                imsave("%s/%i.b.png" % (out_dir, ctr), convert_to_rgb(pred_y[i], is_grayscale=self.is_b_grayscale))
+                ctr += 1
+
+    def generate_gz(self, num_examples, batch_size, out_dir, deterministic=True):
+        if not os.path.exists(out_dir):
+            os.makedirs(out_dir)
+        fn = self.z_fn if not deterministic else self.z_fn_det
+        z = floatX(self.sampler(num_examples, self.latent_dim))
+        ctr = 0
+        for b in range(num_examples // batch_size):
+            out = fn(z[b * batch_size:(b + 1) * batch_size])
+            for i in range(out.shape[0]):
+                imsave("%s/%i.png" % (out_dir, ctr), convert_to_rgb(out[i], is_grayscale=self.is_a_grayscale))
+                ctr += 1
+
+    def generate_interpolation(self, out_name, zsample1=None, zsample2=None, deterministic=True, mode='row',
+                               figsize=(10, 10), cmap='gray'):
+        assert mode in ['row', 'matrix']
+        fn = self.z_fn if not deterministic else self.z_fn_det
+        if zsample1 is None:
+            zsample1 = floatX(self.sampler(1, self.latent_dim)[0])
+        if zsample2 is None:
+            zsample2 = floatX(self.sampler(1, self.latent_dim)[0])
+        coefs = [0.0, 0.1, 0.3, 0.6, 0.9, 1.0] if mode == 'row' else list(np.linspace(0, 1, 25))
+        rows, cols = (1, 6) if mode == 'row' else (5, 5)
+        S = self.in_shp
+        canvas = np.zeros((rows * S, cols * S, 3), np.float32)
+        for k, a in enumerate(coefs):
+            tmp = fn(floatX((1 - a) * zsample1[np.newaxis] + a * zsample2[np.newaxis]))
+            y, x = divmod(k, cols)
+            canvas[y * S:(y + 1) * S, x * S:(x + 1) * S] = convert_to_rgb(tmp[0], is_grayscale=self.is_a_grayscale)
+        imsave(out_name, canvas)
+
+    def generate_interpolation_clip(self, num_samples, batch_size, out_dir, deterministic=True, min_max_norm=False,
+                                    concat=False):
+        if not os.path.exists(out_dir):
+            os.makedirs(out_dir)
+        fn = self.z_fn if not deterministic else self.z_fn_det
+        fn_atob = self.gen_fn if not deterministic else self.gen_fn_det
+        zs = floatX(self.sampler(num_samples, self.latent_dim))
+        coefs = np.linspace(0, 1, 25).astype(zs.dtype)
+        all_tps = []
+        for i in range(zs.shape[0] - 1):
+            for a in coefs:
+                all_tps.append((1 - a) * zs[i] + a * zs[i + 1])
+        all_tps = np.asarray(all_tps, dtype=zs.dtype)
+        ctr = 0
+        S = self.in_shp
+        for b in range(all_tps.shape[0] // batch_size):
+            z_out = fn(all_tps[b * batch_size:(b + 1) * batch_size])
+            p2p_out = fn_atob(z_out)
+            for i in range(z_out.shape[0]):
+                a_img, b_img = z_out[i], p2p_out[i]
+                if min_max_norm:
+                    a_img = (a_img - np.min(a_img)) / (np.max(a_img) - np.min(a_img))
+                a_img = convert_to_rgb(a_img, is_grayscale=self.is_a_grayscale)
+                b_img = convert_to_rgb(b_img, is_grayscale=self.is_b_grayscale)
+                d = '%04d' % ctr
+                if concat:
+                    full = np.zeros((S, S * 2, 3), dtype=zs.dtype)
+                    full[:, :S] = a_img
+                    full[:, S:] = b_img
+                    imsave("%s/concat_%s.png" % (out_dir, d), full)
+                else:
+                    imsave("%s/a_%s.png" % (out_dir, d), a_img)
+                    imsave("%s/b_%s.png" % (out_dir, d), b_img)
+                ctr += 1

@@ -1,0 +1,417 @@
+"""TEST INFRASTRUCTURE: a CPU emulation of the libhmgan C ABI (include/hmgan.h).
+
+Two uses, both in tests only:
+  * `-m "not gpu"` tests monkeypatch ``_lib.call`` with ``call`` below so that the
+    HOST logic (graph lowering, backward ordering, gradient accumulation, the
+    two-pass discriminator backward, optimiser plumbing) can be checked against
+    the oracle without a GPU;
+  * `-m gpu` kernel tests run each real kernel and this emulation on the same
+    seeded inputs and compare.
+Every function takes exactly the ctypes arguments of its C counterpart (raw
+addresses, sizes) and reads/writes the memory behind them through numpy views.
+It is never importable from the product package.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+F32, F16 = 0, 1
+_NP = {F32: np.float32, F16: np.float16}
+
+
+def _a(ptr, n, dtype):
+    """numpy view of n elements at address ptr."""
+    if ptr is None or ptr == 0:
+        return None
+    ptr = int(ptr) if not isinstance(ptr, int) else ptr
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+def _act(v, act, slope):
+    if act == 1:
+        return torch.where(v >= 0, v, v * slope)
+    if act == 2:
+        return torch.relu(v)
+    if act == 3:
+        return torch.sigmoid(v)
+    if act == 4:
+        return torch.tanh(v)
+    return v
+
+
+def _act_grad_from_out(y, act, slope):
+    if act == 1:
+        return torch.where(y >= 0, torch.ones_like(y), torch.full_like(y, slope))
+    if act == 2:
+        return (y > 0).to(y.dtype)
+    if act == 3:
+        return y * (1 - y)
+    if act == 4:
+        return 1 - y * y
+    return torch.ones_like(y)
+
+
+def _t(arr):
+    return torch.from_numpy(arr.astype(np.float32))
+
+
+def _bilinear2(x):      # x: [B,C,H,W]
+    def up(a, axis):
+        n = a.shape[axis]
+        idx = torch.clamp(torch.arange(n) + 1, max=n - 1)
+        nxt = a.index_select(axis, idx)
+        st = torch.stack([a, 0.5 * (a + nxt)], dim=axis + 1)
+        shp = list(a.shape)
+        shp[axis] = 2 * n
+        return st.reshape(shp)
+    return up(up(x, 2), 3)
+
+
+def _virtual_src(d, x1, x2):
+    """[B,Ct,Hv,Wv] float32 virtual source of a forward gather."""
+    B, H, W, C1, C2 = d.B, d.H, d.W, d.C1, d.C2
+    np_dt = _NP[d.dtype]
+    a = _t(_a(x1, B * H * W * C1, np_dt)).reshape(B, H, W, C1)
+    if C2:
+        b = _t(_a(x2, B * H * W * C2, np_dt)).reshape(B, H, W, C2)
+        a = torch.cat([a, b], 3)
+    a = a.permute(0, 3, 1, 2).contiguous()
+    if d.up == 1:
+        a = a.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    elif d.up == 2:
+        a = _bilinear2(a)
+    return a
+
+
+def hm_conv_gather(dp, x1, x2, w, bias, y, y2, stream=None):
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    np_dt = _NP[d.dtype]
+    Ct = d.C1 + d.C2
+    K = d.kh * d.kw * Ct
+    wk = _t(_a(w, K * d.Cout, np_dt)).reshape(d.kh, d.kw, Ct, d.Cout)
+    src = _virtual_src(d, x1, x2)
+    if not d.transposed:
+        out = F.conv2d(src, wk.permute(3, 2, 0, 1).contiguous(), stride=d.stride, padding=d.pad)
+    else:
+        nat_h = (src.shape[2] - 1) * d.stride - 2 * d.pad + d.kh
+        nat_w = (src.shape[3] - 1) * d.stride - 2 * d.pad + d.kw
+        out = F.conv_transpose2d(src, wk.permute(2, 3, 0, 1).contiguous(), stride=d.stride, padding=d.pad,
+                                 output_padding=(max(d.Ho - nat_h, 0), max(d.Wo - nat_w, 0)))
+        out = out[:, :, :d.Ho, :d.Wo]
+    assert out.shape[2:] == (d.Ho, d.Wo), (out.shape, d.Ho, d.Wo)
+    if bias:
+        out = out + _t(_a(bias, d.Cout, np.float32)).view(1, -1, 1, 1)
+    out = _act(out, d.act, d.slope).permute(0, 2, 3, 1)      # [B,Ho,Wo,Cout]
+    ys = slice(d.ou, d.ou + (d.Ho - 1) * d.os + 1, d.os)
+    xs = slice(d.ov, d.ov + (d.Wo - 1) * d.os + 1, d.os)
+    for ptr, lo, hi, bit in ((y, 0, d.split, 1), (y2, d.split, d.Cout, 2)):
+        if not ptr or hi <= lo:
+            continue
+        dst = _a(ptr, d.B * d.oH * d.oW * (hi - lo), np_dt).reshape(d.B, d.oH, d.oW, hi - lo)
+        v = out[..., lo:hi]
+        if d.accumulate & bit:
+            v = v + _t(dst[:, ys, xs, :])
+        dst[:, ys, xs, :] = v.numpy().astype(np_dt)
+    return 0
+
+
+def hm_conv_wgrad(dp, x1, x2, dy, dw, stream=None):
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    np_dt = _NP[d.dtype]
+    Ct = d.C1 + d.C2
+    src = _virtual_src(d, x1, x2)
+    cols = F.unfold(src, (d.kh, d.kw), padding=d.pad, stride=d.stride)          # [B, Ct*kh*kw, L]
+    L = cols.shape[2]
+    assert L == d.Ho * d.Wo, (L, d.Ho, d.Wo)
+    cols = cols.reshape(d.B, Ct, d.kh * d.kw, L).permute(0, 2, 1, 3).reshape(d.B, d.kh * d.kw * Ct, L)
+    g = _t(_a(dy, d.B * d.oH * d.oW * d.Cout, np_dt)).reshape(d.B, d.oH, d.oW, d.Cout)
+    ys = slice(d.ou, d.ou + (d.Ho - 1) * d.os + 1, d.os)
+    xs = slice(d.ov, d.ov + (d.Wo - 1) * d.os + 1, d.os)
+    g = g[:, ys, xs, :].reshape(d.B, L, d.Cout)
+    out = _a(dw, d.kh * d.kw * Ct * d.Cout, np.float32)
+    out += torch.einsum("bkl,blc->kc", cols.double(), g.double()).float().numpy().reshape(-1)
+    return 0
+
+
+def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=None):
+    n = cout * cin * kh * kw
+    W = _a(w, n, np.float32)
+    if mode == 0:
+        src = W.reshape(cout, cin, kh, kw)[:, :, ::-1, ::-1]
+        out = src.transpose(2, 3, 1, 0)                      # [r][s][ci][co]
+    elif mode == 1:
+        src = W.reshape(cout, cin, kh, kw)[:, :, ::-1, ::-1]
+        out = src.transpose(2, 3, 0, 1)                      # [r][s][co][ci]
+    elif mode == 2:
+        src = W.reshape(cin, cout, kh, kw)
+        out = src[:, :, kh - 1 - u, kw - 1 - v]              # [ci][co]
+    elif mode == 3:
+        src = W.reshape(cin, cout, kh, kw)[:, :, ::-1, ::-1]
+        out = src.transpose(2, 3, 1, 0)                      # [u][v][co][ci]
+    else:
+        out = W
+    out = np.ascontiguousarray(out).reshape(-1)
+    _a(wp, out.size, _NP[dst_dtype])[:] = out.astype(_NP[dst_dtype])
+    return 0
+
+
+def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
+    n = cout * cin * kh * kw
+    src = _a(dwp, n, np.float32)
+    dst = _a(dw, n, np.float32)
+    if mode == 0:
+        g = src.reshape(kh, kw, cin, cout).transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]
+    elif mode == 2:
+        g = src.reshape(kh, kw, cin, cout).transpose(2, 3, 0, 1)[:, :, ::-1, ::-1]
+    else:
+        g = src
+    dst[:] = np.ascontiguousarray(g).reshape(-1)
+    return 0
+
+
+def hm_bn_stats(x, dtype, M, Cn, sums, stream=None):
+    v = _a(x, M * Cn, _NP[dtype]).astype(np.float64).reshape(M, Cn)
+    s = _a(sums, 2 * Cn, np.float64)
+    s[:Cn] += v.sum(0)
+    s[Cn:] += (v * v).sum(0)
+    return 0
+
+
+def hm_col_sum(dy, dtype, M, Cn, db, stream=None):
+    v = _a(dy, M * Cn, _NP[dtype]).astype(np.float64).reshape(M, Cn)
+    _a(db, Cn, np.float32)[:] += v.sum(0).astype(np.float32)
+    return 0
+
+
+def hm_bn_finalize(sums, M, Cn, gamma, beta, rmean, rinv, eps, alpha, update_running, mean, inv_std, scale,
+                   shift, stream=None):
+    g = _a(gamma, Cn, np.float32)
+    b = _a(beta, Cn, np.float32)
+    if sums:
+        s = _a(sums, 2 * Cn, np.float64)
+        mu = s[:Cn] / M
+        var = np.maximum(s[Cn:] / M - mu * mu, 0)
+        m = mu.astype(np.float32)
+        i = (1.0 / np.sqrt(var + np.float64(np.float32(eps)))).astype(np.float32)
+        if update_running:
+            rm, ri = _a(rmean, Cn, np.float32), _a(rinv, Cn, np.float32)
+            a = np.float32(alpha)
+            rm[:] = (np.float32(1) - a) * rm + a * m
+            ri[:] = (np.float32(1) - a) * ri + a * i
+    else:
+        m = _a(rmean, Cn, np.float32).copy()
+        i = _a(rinv, Cn, np.float32).copy()
+    if mean:
+        _a(mean, Cn, np.float32)[:] = m
+    if inv_std:
+        _a(inv_std, Cn, np.float32)[:] = i
+    sc = g * i
+    _a(scale, Cn, np.float32)[:] = sc
+    _a(shift, Cn, np.float32)[:] = b - m * sc
+    return 0
+
+
+def hm_bn_apply_act(x, a, dtype, M, Cn, scale, shift, act, slope, stream=None):
+    v = _t(_a(x, M * Cn, _NP[dtype])).reshape(M, Cn)
+    sc = _t(_a(scale, Cn, np.float32))
+    sf = _t(_a(shift, Cn, np.float32))
+    out = _act(v * sc + sf, act, slope)
+    _a(a, M * Cn, _NP[dtype])[:] = out.numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_bn_bwd_reduce(da, a, x, dtype, M, Cn, mean, inv_std, act, slope, red, stream=None):
+    g = _t(_a(da, M * Cn, _NP[dtype])).reshape(M, Cn)
+    av = _t(_a(a, M * Cn, _NP[dtype])).reshape(M, Cn)
+    xv = _t(_a(x, M * Cn, _NP[dtype])).reshape(M, Cn)
+    g = g * _act_grad_from_out(av, act, slope)
+    xh = (xv - _t(_a(mean, Cn, np.float32))) * _t(_a(inv_std, Cn, np.float32))
+    r = _a(red, 2 * Cn, np.float64)
+    r[:Cn] += g.double().sum(0).numpy()
+    r[Cn:] += (g * xh).double().sum(0).numpy()
+    return 0
+
+
+def hm_bn_bwd_apply(da, a, x, dx, dtype, M, Cn, mean, inv_std, gamma, act, slope, red, dgamma, dbeta,
+                    stream=None):
+    g = _t(_a(da, M * Cn, _NP[dtype])).reshape(M, Cn)
+    av = _t(_a(a, M * Cn, _NP[dtype])).reshape(M, Cn)
+    xv = _t(_a(x, M * Cn, _NP[dtype])).reshape(M, Cn)
+    g = g * _act_grad_from_out(av, act, slope)
+    is_ = _t(_a(inv_std, Cn, np.float32))
+    xh = (xv - _t(_a(mean, Cn, np.float32))) * is_
+    r = _a(red, 2 * Cn, np.float64)
+    r0 = torch.from_numpy(r[:Cn].astype(np.float32))
+    r1 = torch.from_numpy(r[Cn:].astype(np.float32))
+    out = _t(_a(gamma, Cn, np.float32)) * is_ * (g - r0 / M - xh * r1 / M)
+    _a(dx, M * Cn, _NP[dtype])[:] = out.numpy().reshape(-1).astype(_NP[dtype])
+    if dgamma:
+        _a(dgamma, Cn, np.float32)[:] = r1.numpy()
+    if dbeta:
+        _a(dbeta, Cn, np.float32)[:] = r0.numpy()
+    return 0
+
+
+def hm_act_bwd(dy, y, dx, dtype, n, act, slope, accumulate, stream=None):
+    g = _t(_a(dy, n, _NP[dtype]))
+    yv = _t(_a(y, n, _NP[dtype]))
+    out = g * _act_grad_from_out(yv, act, slope)
+    dst = _a(dx, n, _NP[dtype])
+    if accumulate:
+        out = out + _t(dst)
+    dst[:] = out.numpy().astype(_NP[dtype])
+    return 0
+
+
+def hm_maxpool2_fwd(x, p, idx, dtype, B, H, W, Cn, stream=None):
+    v = _t(_a(x, B * H * W * Cn, _NP[dtype])).reshape(B, H, W, Cn)
+    Hp, Wp = H // 2, W // 2
+    v = v[:, :Hp * 2, :Wp * 2]
+    win = torch.stack([v[:, 0::2, 0::2], v[:, 0::2, 1::2], v[:, 1::2, 0::2], v[:, 1::2, 1::2]], 0)
+    m, k = win.max(0)           # torch returns the first maximal index on CPU
+    # enforce "first max wins"
+    first = torch.zeros_like(k)
+    found = torch.zeros_like(k, dtype=torch.bool)
+    for j in range(4):
+        hit = (win[j] == m) & ~found
+        first[hit] = j
+        found |= hit
+    _a(p, B * Hp * Wp * Cn, _NP[dtype])[:] = m.numpy().reshape(-1).astype(_NP[dtype])
+    _a(idx, B * Hp * Wp * Cn, np.uint8)[:] = first.numpy().reshape(-1).astype(np.uint8)
+    return 0
+
+
+def hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, stream=None):
+    Hp, Wp = H // 2, W // 2
+    n = B * Hp * Wp * Cn
+    g = _t(_a(dp, n, _NP[dtype])).reshape(B, Hp, Wp, Cn)
+    pv = _t(_a(p, n, _NP[dtype])).reshape(B, Hp, Wp, Cn)
+    k = torch.from_numpy(_a(idx, n, np.uint8).astype(np.int64)).reshape(B, Hp, Wp, Cn)
+    g = g * _act_grad_from_out(pv, act, slope)
+    out = torch.zeros(B, H, W, Cn)
+    for j, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        out[:, a::2, b::2] = torch.where(k == j, g, torch.zeros_like(g))
+    _a(dx, B * H * W * Cn, _NP[dtype])[:] = out.numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_upsample2_fwd(x, y, dtype, B, H, W, Cn, mode, stream=None):
+    v = _t(_a(x, B * H * W * Cn, _NP[dtype])).reshape(B, H, W, Cn).permute(0, 3, 1, 2)
+    out = v.repeat_interleave(2, 2).repeat_interleave(2, 3) if mode == 1 else _bilinear2(v)
+    _a(y, B * 4 * H * W * Cn, _NP[dtype])[:] = out.permute(0, 2, 3, 1).numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_upsample2_bwd(dy, dx, dtype, B, H, W, Cn, mode, accumulate, stream=None):
+    g = _t(_a(dy, B * 4 * H * W * Cn, _NP[dtype])).reshape(B, 2 * H, 2 * W, Cn).permute(0, 3, 1, 2)
+    x = torch.zeros(B, Cn, H, W, requires_grad=True)
+    up = x.repeat_interleave(2, 2).repeat_interleave(2, 3) if mode == 1 else _bilinear2(x)
+    (gx,) = torch.autograd.grad(up, x, g.contiguous())
+    out = gx.permute(0, 2, 3, 1)
+    dst = _a(dx, B * H * W * Cn, _NP[dtype])
+    if accumulate:
+        out = out + _t(dst).reshape(out.shape)
+    dst[:] = out.numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_nchw_to_nhwc(src, dst, dtype, B, Cn, H, W, stream=None):
+    v = _a(src, B * Cn * H * W, np.float32).reshape(B, Cn, H, W).transpose(0, 2, 3, 1)
+    _a(dst, B * Cn * H * W, _NP[dtype])[:] = np.ascontiguousarray(v).reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_nhwc_to_nchw(src, dst, dtype, B, Cn, H, W, stream=None):
+    v = _a(src, B * Cn * H * W, _NP[dtype]).reshape(B, H, W, Cn).transpose(0, 3, 1, 2)
+    _a(dst, B * Cn * H * W, np.float32)[:] = np.ascontiguousarray(v).reshape(-1).astype(np.float32)
+    return 0
+
+
+def hm_permute(src, dst, dtype, B, Cn, H, W, inverse, stream=None):
+    n = B * Cn * H * W
+    s, d = _a(src, n, _NP[dtype]), _a(dst, n, _NP[dtype])
+    if inverse:
+        d[:] = np.ascontiguousarray(s.reshape(B, H, W, Cn).transpose(0, 3, 1, 2)).reshape(-1)
+    else:
+        d[:] = np.ascontiguousarray(s.reshape(B, Cn, H, W).transpose(0, 2, 3, 1)).reshape(-1)
+    return 0
+
+
+def hm_cast(src, sd, dst, dd, n, stream=None):
+    _a(dst, n, _NP[dd])[:] = _a(src, n, _NP[sd]).astype(_NP[dd])
+    return 0
+
+
+def hm_adv_loss(h, dh, dtype, R, G, out_act, target, lsgan, relu_head, weight, gscale, accumulate, loss,
+                stream=None):
+    hv = _t(_a(h, R * G, _NP[dtype])).reshape(R, G)
+    out = _act(hv.mean(1), out_act, 0.0)
+    if lsgan:
+        l = (out - target) ** 2
+        dl = 2 * (out - target)
+    else:
+        l = -(target * torch.log(out) + (1 - target) * torch.log(1 - out))
+        dl = -(target / out) + (1 - target) / (1 - out)
+    _a(loss, 1, np.float32)[0] += np.float32(weight * float(l.mean()))
+    if dh:
+        dl = dl * _act_grad_from_out(out, out_act, 0.0)
+        g = (gscale * weight * dl / (R * G)).view(R, 1).expand(R, G).clone()
+        if relu_head:
+            g = torch.where(hv > 0, g, torch.zeros_like(g))
+        dst = _a(dh, R * G, _NP[dtype])
+        if accumulate:
+            g = g + _t(dst).reshape(R, G)
+        dst[:] = g.numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_recon_loss(p, y, dp, dtype, n, l2, weight, gscale, accumulate, loss, stream=None):
+    e = _t(_a(p, n, _NP[dtype])) - _t(_a(y, n, _NP[dtype]))
+    if l2:
+        l, g = (e * e).mean(), 2 * e
+    else:
+        l, g = e.abs().mean(), torch.sign(e)
+    _a(loss, 1, np.float32)[0] += np.float32(weight * float(l))
+    if dp:
+        g = g * (gscale * weight / n)
+        dst = _a(dp, n, _NP[dtype])
+        if accumulate:
+            g = g + _t(dst)
+        dst[:] = g.numpy().astype(_NP[dtype])
+    return 0
+
+
+def hm_rmsprop(p, g, acc, n, lr, rho, eps, gscale, stream=None):
+    P, Gd, A = _a(p, n, np.float32), _a(g, n, np.float32), _a(acc, n, np.float32)
+    lrv = _a(lr, 1, np.float32)[0]
+    gi = Gd * np.float32(gscale)
+    a = np.float32(rho) * A + (np.float32(1) - np.float32(rho)) * gi * gi
+    A[:] = a
+    P[:] = P - lrv * gi / np.sqrt(a + np.float32(eps))
+    return 0
+
+
+def hm_adam(p, g, m, v, n, lr, b1, b2, eps, t, gscale, stream=None):
+    P, Gd, Mv, Vv = (_a(q, n, np.float32) for q in (p, g, m, v))
+    lrv = _a(lr, 1, np.float32)[0]
+    corr = np.float32(np.sqrt(1 - b2 ** t) / (1 - b1 ** t))
+    gi = Gd * np.float32(gscale)
+    mi = np.float32(b1) * Mv + np.float32(1 - b1) * gi
+    vi = np.float32(b2) * Vv + np.float32(1 - b2) * gi * gi
+    Mv[:] = mi
+    Vv[:] = vi
+    P[:] = P - lrv * corr * mi / (np.sqrt(vi) + np.float32(eps))
+    return 0
+
+
+_FUNCS = {k: v for k, v in globals().items() if k.startswith("hm_")}
+
+
+def call(name, *args):
+    rc = _FUNCS[name](*args)
+    if rc != 0:
+        raise RuntimeError("%s failed in the emulation (%d)" % (name, rc))
