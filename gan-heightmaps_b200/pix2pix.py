@@ -126,12 +126,15 @@ class Pix2Pix(object):
     # ------------------------------------------------------------------ #
     def _to_dev(self, name, a):
         """numpy float32 -> device float32 staging buffer (reused across steps)."""
-        a = np.ascontiguousarray(a, dtype=np.float32)
+        if isinstance(a, torch.Tensor):           # e.g. a pinned host tensor: copied as it is
+            src = a if a.dtype == torch.float32 else a.float()
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
         t = self._stage.get(name)
-        if t is None or t.shape != a.shape:
-            t = self.rt.empty(a.shape, torch.float32)
+        if t is None or t.shape != src.shape:
+            t = self.rt.empty(tuple(src.shape), torch.float32)
             self._stage[name] = t
-        t.copy_(torch.from_numpy(a), non_blocking=False)
+        t.copy_(src, non_blocking=True)
         return t
 
     def _load_nchw(self, src_f32, dst, B, Cn, H, W):

@@ -32,7 +32,7 @@ def _nl(name):
     return {"linear": L.linear, "tanh": L.tanh, "sigmoid": L.sigmoid}[name]
 
 
-def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with_p2p=True, seed=2):
+def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with_p2p=True, seed=2, device="cpu"):
     """The same seeded weights in the oracle and in the product model."""
     which = ('G', 'D', 'P', 'Dp') if with_p2p else ('G', 'D')
     nets = S.build_nets(cfg, seed=seed, which=which)
@@ -50,7 +50,7 @@ def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with
     m = Pix2Pix(in_shp=cfg['in_shp'], latent_dim=cfg['latent_dim'], is_a_grayscale=True, is_b_grayscale=False,
                 lsgan=True, opt=L.rmsprop if opt == "rmsprop" else L.adam,
                 opt_args={'learning_rate': L.shared(L.floatX(lr))}, train_mode=train_mode, verbose=False,
-                device="cpu", precision=precision, seed=0, **kw)
+                device=device, precision=precision, seed=0, **kw)
     for k, net in (('G', m.G), ('D', m.D), ('P', m.P), ('Dp', m.Dp)):
         if net is not None:
             net.set_all_param_values(om.get_all_param_values(k))

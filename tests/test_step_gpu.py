@@ -1,0 +1,95 @@
+"""Step-level parity on the GPU: the product path (Pix2Pix.train_fn & co. ->
+engine -> libhmgan kernels) against the oracle on the same seeded weights and
+inputs.  float32 'parity' mode: 1e-3 relative (BASELINE.json north_star);
+fp16 'fast' mode: tolerances stated per test."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import step as S
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gan-heightmaps_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+from test_engine_cpu import TINY, build_pair, _check_grads, _check_params   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gate64_dcgan_step_parity():
+    """BASELINE.json configs[0]."""
+    cfg = S.experiment_kwargs('gate64')
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda")
+    for it in range(3):
+        Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=10 + it)
+        lo = om.train_fn(Z, X, Y)
+        lm = m.train_fn(Z, X, Y)
+        np.testing.assert_allclose(lm[:2], lo[:2], rtol=1e-3, atol=1e-6)
+        if it == 0:
+            _check_grads(om, m, ('G', 'D'), 1e-3)
+    _check_params(om, m, rtol=2e-3, atol=2e-4)
+    Z = np.random.RandomState(5).rand(4, cfg['latent_dim']).astype(np.float32)
+    np.testing.assert_allclose(m.z_fn_det(Z), om.z_fn_det(Z), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(m.z_fn(Z), om.z_fn(Z), rtol=1e-3, atol=1e-5)
+    assert m.rt.launches > 0
+
+
+@pytest.mark.parametrize("bilinear", [True, False])
+def test_joint_512_step_parity(bilinear):
+    """test1_nobn_bilin_both topology (all four networks, 512x512) at reduced width."""
+    cfg = dict(TINY)
+    cfg['P'] = dict(TINY['P'], bilinear_upsample=bilinear)
+    om, m = build_pair(cfg, 'both', device="cuda")
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=3)
+    lo = om.train_fn(Z, X, Y)
+    lm = m.train_fn(Z, X, Y)
+    np.testing.assert_allclose(lm, lo, rtol=1e-3, atol=1e-6)
+    _check_grads(om, m, ('G', 'D', 'P', 'Dp'), 1e-3, {'G': 5e-2})   # see tests/test_engine_cpu.py on G
+    np.testing.assert_allclose(m.gen_fn_det(X[:1]), om.gen_fn_det(X[:1]), rtol=2e-3, atol=2e-4)
+
+
+def test_full_width_dcgan_forward_and_losses_parity():
+    """BASELINE configs[1] architecture (full widths, 512x512, z=1000) at batch 2: G(z) and the two DCGAN
+    losses against the oracle; range properties of the outputs."""
+    cfg = S.experiment_kwargs('test1_nobn_bilin_both')
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda")
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=1)
+    lo = om.loss_fn(Z, X, Y)
+    lm = m.loss_fn(Z, X, Y)
+    np.testing.assert_allclose(lm[:2], lo[:2], rtol=1e-3, atol=1e-6)
+    gz = m.z_fn_det(Z)
+    assert gz.shape == (2, 1, 512, 512) and gz.min() > 0 and gz.max() < 1
+    np.testing.assert_allclose(gz, om.z_fn_det(Z), rtol=1e-3, atol=1e-5)
+
+
+def test_fast_mode_tracks_parity_mode():
+    """fp16 storage / fp32 accumulate against the float32 oracle on the 64-px gate: losses within 1e-2
+    relative over three steps, G(z) within 1e-2 absolute (values in (0,1))."""
+    cfg = S.experiment_kwargs('gate64')
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast")
+    for it in range(3):
+        Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=10 + it)
+        lo = om.train_fn(Z, X, Y)
+        lm = m.train_fn(Z, X, Y)
+        assert np.all(np.isfinite(lm))
+        np.testing.assert_allclose(lm[:2], lo[:2], rtol=1e-2, atol=1e-4)
+    Z = np.random.RandomState(5).rand(4, cfg['latent_dim']).astype(np.float32)
+    np.testing.assert_allclose(m.z_fn_det(Z), om.z_fn_det(Z), atol=1e-2)
+
+
+def test_p2p_mode_leaves_dcgan_untouched_and_device_api_matches_host_api():
+    cfg = dict(TINY)
+    om, m = build_pair(cfg, 'p2p', device="cuda")
+    before = [a.copy() for a in m.D.get_all_param_values()]
+    Z, X, Y = S.synthetic_batch(1, cfg['latent_dim'], 512, seed=4)
+    lm = m.loss_fn(Z, X, Y)
+    dev = m.step_device(torch.from_numpy(Z).cuda(), torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda(),
+                        train=False).cpu().numpy()
+    np.testing.assert_allclose(dev[2:], np.asarray(lm)[2:], rtol=1e-5)     # G's BN statistics moved in between
+    m.train_fn(Z, X, Y)
+    for a, b in zip(m.D.get_all_param_values(), before):
+        np.testing.assert_array_equal(a, b)
