@@ -256,6 +256,20 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     int tap = (int)(k / cout);
     int uu = tap / kw, vv = tap % kw;
     val = w[(((size_t)ci * cout + co) * kh + (kh - 1 - uu)) * kw + (kw - 1 - vv)];
+  } else if (mode == 5) {  // tcgen05 forward pack, K-major: Wt[(r*kw+s)][co][ci] = W[co][ci][kh-1-r][kw-1-s]
+    int ci = (int)(i % cin);
+    long long k = i / cin;
+    int co = (int)(k % cout);
+    int tap = (int)(k / cout);
+    int r = tap / kw, s = tap % kw;
+    val = w[(((size_t)co * cin + ci) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)];
+  } else if (mode == 6) {  // tcgen05 input-gradient pack (a forward correlation of dy): Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
+    int co = (int)(i % cout);
+    long long k = i / cout;
+    int ci = (int)(k % cin);
+    int tap = (int)(k / cin);
+    int r = tap / kw, s = tap % kw;
+    val = w[(((size_t)co * cin + ci) * kh + r) * kw + s];
   } else {
     val = w[i];
   }
@@ -359,7 +373,7 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG(mode >= 0 && mode <= 4, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode >= 0 && mode <= 6, "hm_pack_conv_weight: bad mode %d", mode);
   long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;

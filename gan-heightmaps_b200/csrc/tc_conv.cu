@@ -1,0 +1,443 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (fast mode: fp16 operands, fp32 accumulate in TMEM).
+//
+// Stands in for the cuDNN/CorrMM convolution that Theano dispatches for lasagne Conv2DLayer
+// (reference architectures/dcgan.py:22,42; architectures/p2p.py:20-21,208-209) and, with the
+// rotated weight pack, for its input gradient (CorrMM_gradInputs).
+//
+// GEMM view:  D[M = 128 output pixels][N = Cout tile] += A[M][K] * B[N][K],  K = taps x Cin.
+//   * A is never materialised (no im2col buffer): for every filter tap (r,s) and every 64-channel
+//     slice, ONE tiled TMA load of the box {64 ch, bw, bh, bn} (bw*bh*bn = 128 pixels) at the
+//     tap-shifted coordinate lands the 128x64 operand tile in shared memory in the 128B-swizzled
+//     K-major layout tcgen05 reads; rows that fall into the zero padding are zero-filled by the
+//     TMA unit itself (out-of-bounds box elements, negative coordinates included).
+//   * B is the per-tap weight slice [Cout tile][64 ch] of the pack [tap][Cout][Cin] (K-major).
+//   * One elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128, N<=256, K=16 x4 per
+//     stage); tcgen05.commit releases the shared-memory stage and, at the end of a tile, publishes
+//     the TMEM accumulator to the four epilogue warps.  Two accumulators (2 x N columns) let the
+//     epilogue of tile i overlap the MMAs of tile i+1.  CTAs are persistent over the tile list.
+//   * Epilogue: tcgen05.ld 32 lanes x 32 columns -> bias, activation -> fp16 -> 16-byte stores
+//     into the NHWC output.
+#include <cuda.h>
+
+#include "hm_common.cuh"
+
+namespace hm {
+
+constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int TILE_M = 128;
+constexpr int KCH = 64;                      // channels per pipeline stage = one 128-byte swizzle row
+constexpr int A_BYTES = TILE_M * KCH * 2;    // 16 KB
+
+struct TcParams {
+  int B, Ho, Wo;           // output grid
+  int Cin, C1, Cout;       // K per tap (C1 from source 1, Cin-C1 from source 2), total N
+  int kh, kw, pad;
+  int bw, bh, bn;          // pixel box of one M tile
+  int tiles_x, tiles_y, tiles_n, n_mtiles;
+  int ntile, n_ntiles;     // N tile (<=256, multiple of 16)
+  int stages;
+  int act;
+  float slope;
+  const float* bias;       // [Cout] or null
+  __half* y;               // [B,Ho,Wo,Cout]
+};
+
+// ---- PTX wrappers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address      bits [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: A,B = F16 (K-major), D = F32, M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = A_BYTES + p.ntile * 128;
+  const uint32_t ctrl = base + p.stages * stage_bytes;        // 1024-aligned
+  // control block: full[stages] | empty[stages] | tfull[2] | tempty[2] | tmem base address
+  auto full_bar = [&](int s) { return ctrl + 8u * s; };
+  auto empty_bar = [&](int s) { return ctrl + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return ctrl + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return ctrl + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = ctrl + 8u * (2 * p.stages + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tmem_cols = p.ntile <= 64 ? 128 : (p.ntile <= 128 ? 256 : 512);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+
+  const int total_tiles = p.n_mtiles * p.n_ntiles;
+  const int ksteps_per_tap = p.Cin / KCH;
+  const int taps = p.kh * p.kw;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tn = mt / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = tn * p.bn;
+        for (int tap = 0; tap < taps; tap++) {
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          for (int cc = 0; cc < ksteps_per_tap; cc++) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = base + stage * stage_bytes;
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            const int c = cc * KCH;
+            if (c < p.C1)
+              tma_load_4d(&tmA, sa, full_bar(stage), c, ox0 - p.pad + s, oy0 - p.pad + r, n0);
+            else
+              tma_load_4d(&tmA2, sa, full_bar(stage), c - p.C1, ox0 - p.pad + s, oy0 - p.pad + r, n0);
+            tma_load_3d(&tmB, sa + A_BYTES, full_bar(stage), c, nt * p.ntile, tap);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.ntile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.ntile;
+        const int ksteps = taps * ksteps_per_tap;
+        for (int ks = 0; ks < ksteps; ks++) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes;
+          const uint64_t ad = umma_desc_k_sw128(sa);
+          const uint64_t bd = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < KCH / 16; k++)                  // +32 B per K=16 slice inside the swizzle atom
+            tc_mma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0);
+          tc_commit(empty_bar(stage));                        // frees the stage when these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(tfull_bar(acc));                            // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int px_per_img = p.bw * p.bh;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int tn = mt / (p.tiles_x * p.tiles_y);
+      const int in = row / px_per_img;
+      const int rem = row - in * px_per_img;
+      const int iy = rem / p.bw, ix = rem - iy * p.bw;
+      const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
+      const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
+      const int acc = it & 1;
+      mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.ntile;
+      __half* dst = p.y + ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout + nt * p.ntile;
+      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+        uint32_t v[32];
+        if (p.ntile - c0 >= 32) {
+          tmem_ld32(taddr + c0, v);
+        } else {
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int j = 16; j < 32; j++) v[j] = 0;
+        }
+        tmem_ld_wait();
+        const int ncols = min(32, p.ntile - c0);
+        if (valid) {
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+            if (p.bias) {
+              const int co = nt * p.ntile + c0 + j;
+              a += __ldg(p.bias + min(co, p.Cout - 1));
+              b += __ldg(p.bias + min(co + 1, p.Cout - 1));
+            }
+            a = act_fwd(a, p.act, p.slope);
+            b = act_fwd(b, p.act, p.slope);
+            __half2 h = __floats2half2_rn(a, b);
+            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (j * 8 < ncols) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static inline int pow2_floor(int v) {
+  int r = 1;
+  while (r * 2 <= v) r *= 2;
+  return r;
+}
+
+// NHWC fp16 activation tensor [B,H,W,C], box {64, bw, bh, bn}
+static int encode_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// weight pack [taps][Cout][Cin] fp16, box {64, ntile, 1}
+static int encode_wgt(CUtensorMap* tm, const void* ptr, int taps, int Cout, int Cin, int ntile) {
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+  cuuint32_t box[3] = {(cuuint32_t)KCH, (cuuint32_t)ntile, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int pick_ntile(int Cout) {
+  if (Cout <= 256) return Cout;
+  for (int n = 256; n >= 16; n -= 16)
+    if (Cout % n == 0) return n;
+  return 0;
+}
+
+}  // namespace hm
+
+using namespace hm;
+
+extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
+  if (!d) return 0;
+  if (d->dtype != HM_F16 || d->transposed || d->up || d->stride != 1) return 0;
+  if (d->os != 1 || d->ou || d->ov || d->split != d->Cout || d->accumulate) return 0;
+  if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
+  if (d->Cout % 16 || d->Cout < 16 || pick_ntile(d->Cout) == 0) return 0;
+  if (d->Ho != d->H + 2 * d->pad - d->kh + 1 || d->Wo != d->W + 2 * d->pad - d->kw + 1) return 0;
+  if (d->oH != d->Ho || d->oW != d->Wo) return 0;
+  return 1;
+}
+
+// y[B,Ho,Wo,Cout] = act( corr(x1|x2, w_tc) + bias );  w_tc is the pack [kh*kw][Cout][C1+C2] (fp16, K-major).
+extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+                          void* y, void* stream) {
+  HM_CHECK_ARG(d && x1 && w_tc && y, "hm_tc_conv: null argument");
+  if (!hm_tc_conv_supported(d)) {
+    set_error("hm_tc_conv: shape not supported by the tcgen05 path (need fp16, stride 1, C%%64==0, Cout%%16==0)");
+    return HM_ERR_UNSUPPORTED;
+  }
+  HM_CHECK_ARG(d->C2 == 0 || x2, "hm_tc_conv: C2>0 but x2 is null");
+  if (!encode_fn()) {
+    set_error("hm_tc_conv: cuTensorMapEncodeTiled is not available from this driver");
+    return HM_ERR_CUDA;
+  }
+  if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc | (uintptr_t)y) & 15) {
+    set_error("hm_tc_conv: pointers must be 16-byte aligned");
+    return HM_ERR_ALIGN;
+  }
+  TcParams p;
+  p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = d->Cout;
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
+  p.bw = pow2_floor(d->Wo < TILE_M ? d->Wo : TILE_M);
+  p.bh = pow2_floor(d->Ho < TILE_M / p.bw ? d->Ho : TILE_M / p.bw);
+  p.bn = TILE_M / (p.bw * p.bh);
+  p.tiles_x = (d->Wo + p.bw - 1) / p.bw;
+  p.tiles_y = (d->Ho + p.bh - 1) / p.bh;
+  p.tiles_n = (d->B + p.bn - 1) / p.bn;
+  p.n_mtiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.ntile = pick_ntile(d->Cout);
+  p.n_ntiles = d->Cout / p.ntile;
+  const int stage_bytes = A_BYTES + p.ntile * 128;
+  int stages = (227 * 1024 - 4096) / stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y;
+
+  CUtensorMap tmA, tmA2, tmB;
+  int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn);
+  if (!rc) rc = d->C2 ? encode_act(&tmA2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn) : 0;
+  if (!d->C2) tmA2 = tmA;
+  if (!rc) rc = encode_wgt(&tmB, w_tc, d->kh * d->kw, d->Cout, p.Cin, p.ntile);
+  if (rc) {
+    set_error("hm_tc_conv: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
+    return HM_ERR_CUDA;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 2048 /*control block*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("hm_tc_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+      return HM_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  int grid = p.n_mtiles * p.n_ntiles;
+  if (grid > num_sms()) grid = num_sms();
+  tc_conv_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmA2, tmB, p);
+  HM_CHECK_LAUNCH("hm_tc_conv");
+  return HM_OK;
+}

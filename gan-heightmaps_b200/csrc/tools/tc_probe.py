@@ -1,0 +1,84 @@
+"""Diagnostic probe (GPU): tcgen05 conv vs the SIMT gather conv on the same fp16 inputs.  Prints one line per
+case with error statistics; used while bringing the tensor-core path up (the asserting version is
+tests/test_tc_gpu.py)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gan-heightmaps_b200"))
+import _lib  # noqa: E402
+
+CASES = [
+    # name, B, H, W, C1, C2, Cout, k, pad, act
+    ("1x1_64_64_w16", 2, 16, 16, 64, 0, 64, 1, 0, 0),
+    ("3x3_64_64_w16", 2, 16, 16, 64, 0, 64, 3, 1, 0),
+    ("5x5_64_64_w16", 2, 16, 16, 64, 0, 64, 5, 2, 1),
+    ("5x5_128_64_4x4_b4", 4, 4, 4, 128, 0, 64, 5, 2, 1),
+    ("5x5_64_128_w128", 1, 32, 128, 64, 0, 128, 5, 2, 1),
+    ("3x3_64_64_w256", 1, 8, 256, 64, 0, 64, 3, 1, 0),
+    ("5x5_128_256_w32", 2, 32, 32, 128, 0, 256, 5, 2, 2),
+    ("3x3_cat128+64_512_w16", 1, 16, 16, 128, 64, 512, 3, 1, 0),
+    ("2x2valid_512_512", 4, 2, 2, 512, 0, 512, 2, 0, 0),
+    ("3x3_64_48_w12_ragged", 3, 10, 12, 64, 0, 48, 3, 1, 3),
+    ("5x5_256_256_8x8_b3", 3, 8, 8, 256, 0, 256, 5, 2, 1),
+]
+
+
+def desc(**kw):
+    d = _lib.ConvDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+def run_case(name, B, H, W, C1, C2, Cout, k, pad, act, verbose=True):
+    torch.manual_seed(abs(hash(name)) % 1000)
+    Ct = C1 + C2
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x1 = (torch.randn(B, H, W, C1, device="cuda")).half()
+    x2 = (torch.randn(B, H, W, C2, device="cuda")).half() if C2 else None
+    Wm = torch.randn(Cout, Ct, k, k, device="cuda") / np.sqrt(k * k * Ct)
+    bias = torch.randn(Cout, device="cuda")
+    wp = torch.empty(k * k * Ct * Cout, device="cuda", dtype=torch.float16)
+    wt = torch.empty_like(wp)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wp.data_ptr(), 0, Cout, Ct, k, k, 0, 0, 1, None)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wt.data_ptr(), 5, Cout, Ct, k, k, 0, 0, 1, None)
+    d = desc(dtype=1, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=Ho, Wo=Wo,
+             Cout=Cout, oH=Ho, oW=Wo, os=1, ou=0, ov=0, split=Cout, act=act, slope=0.2, accumulate=0)
+    y_ref = torch.zeros(B, Ho, Wo, Cout, device="cuda", dtype=torch.float16)
+    y_tc = torch.full((B, Ho, Wo, Cout), 7.0, device="cuda", dtype=torch.float16)
+    p2 = x2.data_ptr() if C2 else None
+    _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None,
+              None)
+    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None)
+    torch.cuda.synchronize()
+    a, b = y_tc.float(), y_ref.float()
+    err = (a - b).abs()
+    scale = float(b.abs().max())
+    line = "%-28s max_err %.4g  scale %.4g  rel %.3g  frac_bad %.4f  untouched %.4f" % (
+        name, float(err.max()), scale, float(err.max()) / scale, float((err > 2e-2 * scale).float().mean()),
+        float((a == 7.0).float().mean()))
+    if verbose and float(err.max()) > 5e-3 * scale:
+        bad = (err > 2e-2 * scale)
+        line += "\n    bad by channel%%64 chunk(8): %s" % [round(float(bad[..., c::8].float().mean()), 3) for c in range(8)]
+        line += "\n    bad by x%%8: %s" % [round(float(bad[:, :, xx::8].float().mean()), 3) for xx in range(min(8, Wo))]
+        line += "\n    bad by y: %s" % [round(float(bad[:, yy].float().mean()), 3) for yy in range(min(Ho, 8))]
+        line += "\n    bad by n: %s" % [round(float(bad[nn].float().mean()), 3) for nn in range(B)]
+    return float(err.max()) / scale, line
+
+
+if __name__ == "__main__":
+    sel = sys.argv[1:] or None
+    for c in CASES:
+        if sel and c[0] not in sel:
+            continue
+        try:
+            rel, line = run_case(*c)
+            print(line, flush=True)
+        except Exception as e:     # keep going: one line per case
+            print("%-28s EXC %s" % (c[0], e), flush=True)
+            break

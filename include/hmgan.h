@@ -107,12 +107,26 @@ int hm_conv_gather(const HmConvDesc* d, const void* x1, const void* x2, const vo
 int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy,
                   float* dw_packed, void* stream);
 
+/* ---- tcgen05 / TMA implicit-GEMM convolution (fast mode) -------------------
+ * The tensor-core implementation of the same contract as hm_conv_gather for the GEMM-shaped layers:
+ * fp16 NHWC activations, stride 1, no virtual upsampling, C1 and C2 multiples of 64, Cout a multiple of 16,
+ * dense output.  `w_tc` is the K-major pack [kh*kw][Cout][C1+C2] (hm_pack_conv_weight modes 5/6).
+ * hm_tc_conv_supported() returns 1 when a descriptor qualifies; hm_tc_conv() returns HM_ERR_UNSUPPORTED
+ * otherwise (the caller then uses hm_conv_gather). */
+int hm_tc_conv_supported(const HmConvDesc* d);
+int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+               void* y, void* stream);
+
 /* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
  *  mode 0: Conv2DLayer W (Cout,Cin,kh,kw)      -> Wp[(r*kw+s)*Cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]   (forward)
  *  mode 1: Conv2DLayer W                       -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][kh-1-r][kw-1-s]  (input gradient)
  *  mode 2: Deconv2DLayer W (Cin,Cout,kh,kw), tap (u,v) -> Wp[ci][co] = W[ci][co][kh-1-u][kw-1-v]        (forward, one output phase)
  *  mode 3: Deconv2DLayer W                     -> Wp[(u*kw+v)*Cout+co][ci] = W[ci][co][kh-1-u][kw-1-v]  (input gradient = strided conv)
  *  mode 4: DenseLayer W (in,out)               -> Wp = W (dtype cast only)
+ *  mode 5: Conv2DLayer W, tcgen05 forward pack (K-major)  -> Wt[(r*kw+s)][co][ci] = W[co][ci][kh-1-r][kw-1-s]
+ *  mode 6: Conv2DLayer W, tcgen05 input-gradient pack     -> Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
+ *          (the input gradient of a stride-1 'same' convolution is the forward correlation of dy with this
+ *           pack and pad' = k-1-pad)
  * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the
  * inverse index map of mode 0 / 2(all taps) / 4 to a packed fp32 gradient and
  * (over)writes the master-layout gradient. */
