@@ -1,0 +1,18 @@
+"""tcgen05/TMA implicit-GEMM convolution (fast mode) against the SIMT gather convolution on identical fp16
+inputs and weights, through the C ABI.  Both accumulate in fp32 and round the result to fp16 once, so the
+tolerance is 3e-3 of the output scale (one fp16 ulp at the top of the range plus summation-order noise)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import tc_probe   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", tc_probe.CASES, ids=[c[0] for c in tc_probe.CASES])
+def test_tc_conv_matches_simt(case):
+    rel, line = tc_probe.run_case(*case)
+    assert rel <= 3e-3, line
