@@ -38,7 +38,8 @@ _PROTOS = {
     "hm_device_supported": ([], C.c_int),
     "hm_conv_gather": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "hm_conv_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
-    "hm_tc_conv": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P], C.c_int),
+    "hm_tc_conv": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "hm_tc_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
     "hm_pack_conv_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_unpack_conv_wgrad": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_bn_stats": ([_P, _I, _LL, _I, _P, _P], C.c_int),
@@ -78,14 +79,15 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    lib.hm_tc_conv_supported.argtypes = [C.POINTER(ConvDesc)]
-    lib.hm_tc_conv_supported.restype = C.c_int
+    for name in ("hm_tc_conv_supported", "hm_tc_wgrad_supported"):
+        getattr(lib, name).argtypes = [C.POINTER(ConvDesc)]
+        getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
 
 
 def exported_symbols():
-    return sorted(list(_PROTOS) + ["hm_tc_conv_supported"])
+    return sorted(list(_PROTOS) + ["hm_tc_conv_supported", "hm_tc_wgrad_supported"])
 
 
 def call(name, *args):

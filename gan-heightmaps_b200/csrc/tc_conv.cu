@@ -39,7 +39,9 @@ struct TcParams {
   int act;
   float slope;
   const float* bias;       // [Cout] or null
-  __half* y;               // [B,Ho,Wo,Cout]
+  __half* y;               // [B,Ho,Wo,split]       channels [0,split)
+  __half* y2;              // [B,Ho,Wo,Cout-split]  channels [split,Cout)   (concat sources of an input gradient)
+  int split, accumulate;   // accumulate bit0: y += , bit1: y2 +=
 };
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -265,7 +267,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.ntile;
-      __half* dst = p.y + ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout + nt * p.ntile;
+      const int col0 = nt * p.ntile;
+      const size_t pix = (size_t)((size_t)n * p.Ho + oy) * p.Wo + ox;
+      const bool second = col0 >= p.split;
+      __half* dst = second ? p.y2 + pix * (p.Cout - p.split) + (col0 - p.split) : p.y + pix * p.split + col0;
+      const bool accum = (p.accumulate & (second ? 2 : 1)) != 0;
+      const bool store = valid && (second ? p.y2 != nullptr : p.y != nullptr);
       for (int c0 = 0; c0 < p.ntile; c0 += 32) {
         uint32_t v[32];
         if (p.ntile - c0 >= 32) {
@@ -277,8 +284,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         tmem_ld_wait();
         const int ncols = min(32, p.ntile - c0);
-        if (valid) {
+        if (store) {
           uint32_t packed[16];
+          uint4 prev[4];
+          if (accum) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (j * 8 < ncols) prev[j] = reinterpret_cast<const uint4*>(dst + c0)[j];
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
@@ -289,6 +302,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
             a = act_fwd(a, p.act, p.slope);
             b = act_fwd(b, p.act, p.slope);
+            if (accum) {
+              const uint32_t pv = reinterpret_cast<const uint32_t*>(prev)[j >> 1];
+              const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pv));
+              a += pf.x;
+              b += pf.y;
+            }
             __half2 h = __floats2half2_rn(a, b);
             packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
           }
@@ -358,10 +377,9 @@ static int encode_wgt(CUtensorMap* tm, const void* ptr, int taps, int Cout, int 
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-static int pick_ntile(int Cout) {
-  if (Cout <= 256) return Cout;
+static int pick_ntile(int Cout, int split) {
   for (int n = 256; n >= 16; n -= 16)
-    if (Cout % n == 0) return n;
+    if (Cout % n == 0 && split % n == 0) return n;
   return 0;
 }
 
@@ -372,9 +390,9 @@ using namespace hm;
 extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   if (!d) return 0;
   if (d->dtype != HM_F16 || d->transposed || d->up || d->stride != 1) return 0;
-  if (d->os != 1 || d->ou || d->ov || d->split != d->Cout || d->accumulate) return 0;
+  if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
   if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
-  if (d->Cout % 16 || d->Cout < 16 || pick_ntile(d->Cout) == 0) return 0;
+  if (d->Cout % 16 || d->Cout < 16 || pick_ntile(d->Cout, d->split) == 0) return 0;
   if (d->Ho != d->H + 2 * d->pad - d->kh + 1 || d->Wo != d->W + 2 * d->pad - d->kw + 1) return 0;
   if (d->oH != d->Ho || d->oW != d->Wo) return 0;
   return 1;
@@ -382,8 +400,8 @@ extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
 
 // y[B,Ho,Wo,Cout] = act( corr(x1|x2, w_tc) + bias );  w_tc is the pack [kh*kw][Cout][C1+C2] (fp16, K-major).
 extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
-                          void* y, void* stream) {
-  HM_CHECK_ARG(d && x1 && w_tc && y, "hm_tc_conv: null argument");
+                          void* y, void* y2, void* stream) {
+  HM_CHECK_ARG(d && x1 && w_tc && (y || y2), "hm_tc_conv: null argument");
   if (!hm_tc_conv_supported(d)) {
     set_error("hm_tc_conv: shape not supported by the tcgen05 path (need fp16, stride 1, C%%64==0, Cout%%16==0)");
     return HM_ERR_UNSUPPORTED;
@@ -393,7 +411,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     set_error("hm_tc_conv: cuTensorMapEncodeTiled is not available from this driver");
     return HM_ERR_CUDA;
   }
-  if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc | (uintptr_t)y) & 15) {
+  if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc | (uintptr_t)y | (uintptr_t)y2) & 15) {
     set_error("hm_tc_conv: pointers must be 16-byte aligned");
     return HM_ERR_ALIGN;
   }
@@ -408,13 +426,14 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.tiles_y = (d->Ho + p.bh - 1) / p.bh;
   p.tiles_n = (d->B + p.bn - 1) / p.bn;
   p.n_mtiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.ntile = pick_ntile(d->Cout);
+  p.ntile = pick_ntile(d->Cout, d->split);
   p.n_ntiles = d->Cout / p.ntile;
   const int stage_bytes = A_BYTES + p.ntile * 128;
   int stages = (227 * 1024 - 4096) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
-  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y;
+  p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y; p.y2 = (__half*)y2;
+  p.split = d->split; p.accumulate = d->accumulate;
 
   CUtensorMap tmA, tmA2, tmB;
   int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn);

@@ -115,7 +115,12 @@ int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const voi
  * otherwise (the caller then uses hm_conv_gather). */
 int hm_tc_conv_supported(const HmConvDesc* d);
 int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
-               void* y, void* stream);
+               void* y, void* y2, void* stream);
+/* Weight gradient on the tensor cores, same contract as hm_conv_wgrad (fp32 [kh*kw*(C1+C2)][Cout], atomically
+ * accumulated, caller zeroes): fp16, stride 1, no virtual upsampling, C1, C2 and Cout multiples of 64, dense dy. */
+int hm_tc_wgrad_supported(const HmConvDesc* d);
+int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw_packed,
+                void* stream);
 
 /* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
  *  mode 0: Conv2DLayer W (Cout,Cin,kh,kw)      -> Wp[(r*kw+s)*Cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]   (forward)

@@ -16,3 +16,9 @@ pytestmark = pytest.mark.gpu
 def test_tc_conv_matches_simt(case):
     rel, line = tc_probe.run_case(*case)
     assert rel <= 3e-3, line
+
+
+@pytest.mark.parametrize("case", tc_probe.WGRAD_CASES, ids=[c[0] for c in tc_probe.WGRAD_CASES])
+def test_tc_wgrad_matches_simt(case):
+    rel, line = tc_probe.run_wgrad_case(*case)
+    assert rel <= 3e-3, line

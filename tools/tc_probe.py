@@ -54,7 +54,7 @@ def run_case(name, B, H, W, C1, C2, Cout, k, pad, act, verbose=True):
     p2 = x2.data_ptr() if C2 else None
     _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None,
               None)
-    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None)
+    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
     torch.cuda.synchronize()
     a, b = y_tc.float(), y_ref.float()
     err = (a - b).abs()
@@ -71,7 +71,82 @@ def run_case(name, B, H, W, C1, C2, Cout, k, pad, act, verbose=True):
     return float(err.max()) / scale, line
 
 
+WGRAD_CASES = [c for c in CASES if c[6] % 64 == 0 and c[6] <= 256]
+
+
+def run_wgrad_case(name, B, H, W, C1, C2, Cout, k, pad, act):
+    torch.manual_seed(abs(hash(name)) % 1000 + 5)
+    Ct = C1 + C2
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x1 = (torch.randn(B, H, W, C1, device="cuda")).half()
+    x2 = (torch.randn(B, H, W, C2, device="cuda")).half() if C2 else None
+    dy = (torch.randn(B, Ho, Wo, Cout, device="cuda")).half()
+    d = desc(dtype=1, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=Ho, Wo=Wo,
+             Cout=Cout, oH=Ho, oW=Wo, os=1, ou=0, ov=0, split=Cout, act=0, slope=0.0, accumulate=0)
+    ref = torch.zeros(k * k * Ct, Cout, device="cuda")
+    out = torch.zeros(k * k * Ct, Cout, device="cuda")
+    p2 = x2.data_ptr() if C2 else None
+    _lib.call("hm_conv_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), ref.data_ptr(), None)
+    _lib.call("hm_tc_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), out.data_ptr(), None)
+    torch.cuda.synchronize()
+    err = (out - ref).abs()
+    scale = float(ref.abs().max())
+    line = "wgrad %-28s max_err %.4g  scale %.4g  rel %.3g  frac_bad %.4f  zero_frac %.4f" % (
+        name, float(err.max()), scale, float(err.max()) / scale, float((err > 2e-2 * scale).float().mean()),
+        float((out == 0).float().mean()))
+    if float(err.max()) > 5e-3 * scale:
+        bad = (err > 2e-2 * scale).view(k * k, Ct, Cout)
+        line += "\n    bad by tap: %s" % [round(float(bad[t].float().mean()), 2) for t in range(k * k)]
+        line += "\n    bad by ci%%64 (8 bins): %s" % [round(float(bad[:, c::8].float().mean()), 2) for c in range(8)]
+        line += "\n    bad by co (8 bins): %s" % [round(float(bad[:, :, c::8].float().mean()), 2) for c in range(8)]
+        line += "\n    ratio out/ref median: %.4g" % float((out / (ref + 1e-20)).median())
+    return float(err.max()) / scale, line
+
+
+def perf():
+    """Device time of the tensor-core kernels at the hottest DCGAN layer shapes (CUDA events, 5 launches)."""
+    shapes = [("D2 64->128 @256^2 x64", 64, 256, 256, 64, 128, 5, 2),
+              ("D3 128->128 @128^2 x64", 64, 128, 128, 128, 128, 5, 2),
+              ("G7 64->64 @256^2 x32", 32, 256, 256, 64, 64, 5, 2),
+              ("D5 128->256 @32^2 x64", 64, 32, 32, 128, 256, 5, 2),
+              ("D7 256->256 @8^2 x64", 64, 8, 8, 256, 256, 5, 2)]
+    for (name, B, H, W, Ci, Co, k, pad) in shapes:
+        x = torch.randn(B, H, W, Ci, device="cuda").half()
+        dy = torch.randn(B, H, W, Co, device="cuda").half()
+        wt = (torch.randn(k * k * Co * Ci, device="cuda") * 0.02).half()
+        y = torch.empty(B, H, W, Co, device="cuda", dtype=torch.float16)
+        dw = torch.zeros(k * k * Ci, Co, device="cuda")
+        d = desc(dtype=1, B=B, H=H, W=W, C1=Ci, C2=0, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=H, Wo=W,
+                 Cout=Co, oH=H, oW=W, os=1, ou=0, ov=0, split=Co, act=1, slope=0.2, accumulate=0)
+        flop = 2.0 * B * H * W * k * k * Ci * Co
+        for what, fn in (("fwd  ", lambda: _lib.call("hm_tc_conv", C.byref(d), x.data_ptr(), None, wt.data_ptr(), None,
+                                                      y.data_ptr(), None, None)),
+                         ("wgrad", lambda: _lib.call("hm_tc_wgrad", C.byref(d), x.data_ptr(), None, dy.data_ptr(),
+                                                      dw.data_ptr(), None))):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print("perf %-26s %s %8.3f ms  %7.1f TFLOP/s" % (name, what, ms, flop / ms / 1e9), flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["perf"]:
+        perf()
+        sys.exit(0)
+    if sys.argv[1:] == ["wgrad"]:
+        for c in WGRAD_CASES:
+            try:
+                print(run_wgrad_case(*c)[1], flush=True)
+            except Exception as e:
+                print("wgrad %-28s EXC %s" % (c[0], e), flush=True)
+                break
+        sys.exit(0)
     sel = sys.argv[1:] or None
     for c in CASES:
         if sel and c[0] not in sel:
