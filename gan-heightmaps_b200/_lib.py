@@ -96,3 +96,8 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise HmError("%s failed (%d): %s" % (name, rc, lib.hm_last_error_string().decode()))
+
+
+def query(name, *args):
+    """Call an entry point that answers a question (returns a plain int, no error convention)."""
+    return int(getattr(load(), name)(*args))

@@ -146,6 +146,15 @@ class ConvOp(object):
                 raise NotImplementedError("overlapping transposed convolution (stride < kernel on a >1x1 input)")
         self.K = self.kh * self.kw * self.Cin
         self.wp_f = self.wp_d = self.dwp = self.gup = None
+        # tensor-core (tcgen05/TMA) eligibility, fast mode only; everything else runs the SIMT gather kernels
+        self.tc_fwd = self.tc_dg = self.tc_wg = False
+        self.wt_f = self.wt_d = self.x1u = self.x2u = None
+        rt = net.rt
+        if rt.precision == "fast" and kind == "conv" and self.stride == 1:
+            self.tc_fwd = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_fwd_desc(rt, 1))))
+            self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
+            self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
+        self.path = "tcgen05" if self.tc_fwd else "simt"
 
     # -- buffers ------------------------------------------------------------ #
     def alloc(self, rt, B):
@@ -156,6 +165,15 @@ class ConvOp(object):
             self.dwp = rt.empty((n,), torch.float32)
         if self.up and self.src.srcs[0].kind != "input":
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
+        n = self.K * self.Cout
+        if self.tc_fwd and self.wt_f is None:
+            self.wt_f = rt.empty((n,))
+        if self.tc_dg and self.wt_d is None:
+            self.wt_d = rt.empty((n,))
+        if self.up and (self.tc_fwd or self.tc_wg):
+            # the tensor-core kernels read dense NHWC tiles through TMA: materialise the 2x resampling once
+            self.x1u = rt.empty((B, self.Hv, self.Wv, self.C1))
+            self.x2u = rt.empty((B, self.Hv, self.Wv, self.C2)) if self.x2 is not None else None
 
     def pack(self, rt):
         """master (Lasagne layout, fp32) -> packed [K][Cout] copies in the compute dtype."""
@@ -163,10 +181,18 @@ class ConvOp(object):
         if self.kind == "dense":
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 4, self.Cout, self.Cin, 1, 1, 0, 0, rt.cd)
         elif self.kind == "conv":
-            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
-                    0, 0, rt.cd)
-            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 1, self.Cout, self.Cin, self.kh, self.kw,
-                    0, 0, rt.cd)
+            if not self.tc_fwd:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
+                        0, 0, rt.cd)
+            else:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 5, self.Cout, self.Cin, self.kh, self.kw,
+                        0, 0, rt.cd)
+            if not self.tc_dg:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 1, self.Cout, self.Cin, self.kh, self.kw,
+                        0, 0, rt.cd)
+            else:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 6, self.Cout, self.Cin, self.kh, self.kw,
+                        0, 0, rt.cd)
         else:
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -203,6 +229,33 @@ class ConvOp(object):
             d.os, d.ou, d.ov = 1, 0, 0
         return d
 
+    def _tc_fwd_desc(self, rt, n):
+        """Forward descriptor over the MATERIALISED (already upsampled) source, for the tensor-core kernels."""
+        d = self._fwd_desc(rt, n)
+        d.H, d.W, d.up = self.Hv, self.Wv, 0
+        return d
+
+    def _tc_dgrad_desc(self, rt, n, acc):
+        """Input gradient of a stride-1 convolution as a forward correlation of dy with the pack of mode 6."""
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W = n, self.out.shape[0], self.out.shape[1]
+        d.C1, d.C2, d.up = self.Cout, 0, 0
+        d.kh, d.kw, d.stride, d.pad = self.kh, self.kw, 1, self.kh - 1 - self.pad
+        d.transposed = 0
+        d.Ho, d.Wo, d.Cout = self.Hv, self.Wv, self.Cin
+        d.oH, d.oW, d.os, d.ou, d.ov = self.Hv, self.Wv, 1, 0, 0
+        d.split = self.C1
+        d.act, d.slope = 0, 0.0
+        d.accumulate = acc
+        return d
+
+    def _srcs(self, rt, lo, hi, materialised):
+        """Device pointers of the two sources for rows [lo,hi): the tensors themselves, or their 2x copies."""
+        if materialised and self.up:
+            return _ptr(self.x1u[lo:hi]), (_ptr(self.x2u[lo:hi]) if self.x2 is not None else None)
+        return _ptr(self.x1.b(lo, hi)), (_ptr(self.x2.b(lo, hi)) if self.x2 is not None else None)
+
     def _dgrad_desc(self, rt, n, acc):
         d = _lib.ConvDesc()
         d.dtype = rt.cd
@@ -234,6 +287,15 @@ class ConvOp(object):
                     d = self._fwd_desc(rt, n, (u, v))
                     rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f[(u * self.kw + v) * per:]),
                             bias, y, None)
+        elif self.tc_fwd:
+            if self.up:
+                for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
+                    if x is not None:
+                        rt.call("hm_upsample2_fwd", _ptr(x.b(lo, hi)), _ptr(xu[lo:hi]), rt.cd, n, x.shape[0],
+                                x.shape[1], c, self.up)
+            u1, u2 = self._srcs(rt, lo, hi, True)
+            d = self._tc_fwd_desc(rt, n)
+            rt.call("hm_tc_conv", C.byref(d), u1, u2, _ptr(self.wt_f), bias, y, None)
         else:
             d = self._fwd_desc(rt, n)
             rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f), bias, y, None)
@@ -256,6 +318,16 @@ class ConvOp(object):
                         rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
                                 _ptr(self.dwp[(u * self.kw + v) * per:]))
                 mode = 2
+            elif self.tc_wg and (not self.up or self.x1u is not None):
+                if self.up and not self.tc_fwd:        # forward ran on the gather kernel: materialise now
+                    for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
+                        if x is not None:
+                            rt.call("hm_upsample2_fwd", _ptr(x.b(lo, hi)), _ptr(xu[lo:hi]), rt.cd, n, x.shape[0],
+                                    x.shape[1], c, self.up)
+                u1, u2 = self._srcs(rt, lo, hi, True)
+                d = self._tc_fwd_desc(rt, n)
+                rt.call("hm_tc_wgrad", C.byref(d), u1, u2, _ptr(g), _ptr(self.dwp))
+                mode = 0
             else:
                 d = self._fwd_desc(rt, n)
                 rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g), _ptr(self.dwp))
@@ -276,13 +348,17 @@ class ConvOp(object):
             raise NotImplementedError("input gradient of a DenseLayer (only ever fed by the latent input)")
         if self.up:
             # gradient on the virtual (2x) grid, then the adjoint of the resampling
-            d = self._dgrad_desc(rt, n, 0)
             gu = self.gup[lo:hi]
             flat = gu.view(-1)
             n1 = n * self.Hv * self.Wv * self.C1
             y1 = flat[:n1] if t1 else None
             y2 = flat[n1:] if t2 else None
-            rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, _ptr(y1), _ptr(y2))
+            if self.tc_dg:
+                d = self._tc_dgrad_desc(rt, n, 0)
+                rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, _ptr(y1), _ptr(y2))
+            else:
+                d = self._dgrad_desc(rt, n, 0)
+                rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, _ptr(y1), _ptr(y2))
             for (x, y, c) in ((self.x1, y1, self.C1), (self.x2, y2, self.C2)):
                 if y is None:
                     continue
@@ -290,10 +366,14 @@ class ConvOp(object):
                         self.up, x.take_acc())
         else:
             acc = (self.x1.take_acc() if t1 else 0) | ((self.x2.take_acc() << 1) if t2 else 0)
-            d = self._dgrad_desc(rt, n, acc)
             y1 = _ptr(self.x1.g(lo, hi)) if t1 else None
             y2 = _ptr(self.x2.g(lo, hi)) if t2 else None
-            rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, y1, y2)
+            if self.tc_dg:
+                d = self._tc_dgrad_desc(rt, n, acc)
+                rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, y1, y2)
+            else:
+                d = self._dgrad_desc(rt, n, acc)
+                rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, y1, y2)
 
 
 class BNActOp(object):
@@ -449,6 +529,7 @@ class Net(object):
         self.sflat = rt.zeros((max(ns, 1),), torch.float32)
         self.opt_state = {}
         self.B = 0
+        self._packed = False
         if rng is not None:
             self.set_all_param_values([L.init_param(rng, p) for p in self.params])
 

@@ -152,6 +152,11 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
     elif mode == 3:
         src = W.reshape(cin, cout, kh, kw)[:, :, ::-1, ::-1]
         out = src.transpose(2, 3, 1, 0)                      # [u][v][co][ci]
+    elif mode == 5:
+        src = W.reshape(cout, cin, kh, kw)[:, :, ::-1, ::-1]
+        out = src.transpose(2, 3, 0, 1)                      # [r][s][co][ci]
+    elif mode == 6:
+        out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 1, 0)   # [r][s][ci][co]
     else:
         out = W
     out = np.ascontiguousarray(out).reshape(-1)
@@ -408,7 +413,39 @@ def hm_adam(p, g, m, v, n, lr, b1, b2, eps, t, gscale, stream=None):
     return 0
 
 
+def _tc_ok(d, wgrad):
+    ok = d.dtype == F16 and not d.transposed and not d.up and d.stride == 1 and d.os == 1 and not d.ou and not d.ov
+    ok = ok and d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0
+    ok = ok and d.Ho == d.H + 2 * d.pad - d.kh + 1 and d.Wo == d.W + 2 * d.pad - d.kw + 1
+    ok = ok and d.oH == d.Ho and d.oW == d.Wo
+    if wgrad:
+        return ok and d.Cout % 64 == 0 and 0 < d.Cout <= 256
+    ntile = [n for n in range(256, 15, -16) if d.Cout % n == 0 and d.split % n == 0]
+    return ok and d.Cout % 16 == 0 and d.Cout >= 16 and 0 < d.split <= d.Cout and bool(ntile)
+
+
+def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
+    """Same contract as hm_conv_gather, weights in the K-major pack [tap][Cout][Cin]."""
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    assert _tc_ok(d, False)
+    Ct = d.C1 + d.C2
+    wt = _a(w_tc, d.kh * d.kw * Ct * d.Cout, np.float16).reshape(d.kh * d.kw, d.Cout, Ct)
+    wk = np.ascontiguousarray(wt.transpose(0, 2, 1))           # [tap][ci][co] = the gather kernel's pack
+    return hm_conv_gather(dp, x1, x2, wk.ctypes.data, bias, y, y2)
+
+
+def hm_tc_wgrad(dp, x1, x2, dy, dw, stream=None):
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    assert _tc_ok(d, True)
+    return hm_conv_wgrad(dp, x1, x2, dy, dw)
+
+
 _FUNCS = {k: v for k, v in globals().items() if k.startswith("hm_")}
+
+
+def query(name, dp):
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    return int(_tc_ok(d, name == "hm_tc_wgrad_supported"))
 
 
 def call(name, *args):

@@ -25,6 +25,7 @@ from pix2pix import Pix2Pix     # noqa: E402
 @pytest.fixture
 def cpu_backend(monkeypatch):
     monkeypatch.setattr(_lib, "call", fake_hmgan.call)
+    monkeypatch.setattr(_lib, "query", fake_hmgan.query)
     monkeypatch.setattr(_lib, "load", lambda: None)
 
 
@@ -182,3 +183,27 @@ def test_unsupported_configurations_fail_loudly(cpu_backend):
                 {'nch': 128, 'div': [8, 4, 2, 1], 'nonlinearity': L.linear},    # nch != in_shp: head malformed
                 None, None, {}, {}, in_shp=64, latent_dim=8, is_a_grayscale=True, is_b_grayscale=False,
                 verbose=False, device="cpu", seed=0)
+
+
+def test_fast_mode_lowering_uses_tensor_core_kernels_where_eligible(cpu_backend, monkeypatch):
+    """Host logic of the fp16 path: 64-channel-multiple stride-1 convolutions are routed to hm_tc_conv /
+    hm_tc_wgrad (forward, input gradient, weight gradient), the rest to the gather kernels; the step still
+    tracks the float32 oracle (fp16 storage: 2e-2 on the losses)."""
+    calls = {}
+    real = fake_hmgan.call
+
+    def counting(name, *a):
+        calls[name] = calls.get(name, 0) + 1
+        return real(name, *a)
+    monkeypatch.setattr(_lib, "call", counting)
+    cfg = dict(in_shp=64, latent_dim=32,
+               G=dict(nch=256, num_repeats=0, div=[2, 2, 4, 4]),                 # 128,128,64,64 channels
+               D=dict(nch=64, num_repeats=0, bn=False, nonlinearity='linear', div=[1, 1, 1, 1]))
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, precision="fast")
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 64, seed=1)
+    lo = om.train_fn(Z, X, Y)
+    lm = m.train_fn(Z, X, Y)
+    np.testing.assert_allclose(lm[:2], lo[:2], rtol=2e-2, atol=1e-4)
+    assert calls.get("hm_tc_conv", 0) >= 10 and calls.get("hm_tc_wgrad", 0) >= 6, calls
+    paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
+    assert "tcgen05" in paths and "simt" in paths
