@@ -61,6 +61,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// thin_conv.cu: HBM/L1-bound specialisations behind hm_conv_gather / hm_conv_wgrad; return false if the
+// descriptor does not qualify (the caller then runs the generic tiled kernel).
+bool thin_in_conv_launch(const HmConvDesc* d, const void* x1, const void* x2, const void* w, const float* bias,
+                         void* y, void* y2, cudaStream_t st);
+bool thin_wgrad_launch(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw,
+                       cudaStream_t st);
+
 inline int num_sms() {
   static int n = 0;
   if (!n) {

@@ -270,6 +270,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     int tap = (int)(k / cin);
     int r = tap / kw, s = tap % kw;
     val = w[(((size_t)co * cin + ci) * kh + r) * kw + s];
+  } else if (mode == 7) {  // input gradient of a stride-1 conv as a FORWARD gather of dy (pad' = k-1-pad):
+                           // Wp[(r*kw+s)*cout+co][ci] = W[co][ci][r][s]
+    int ci = (int)(i % cin);
+    long long k = i / cin;
+    int co = (int)(k % cout);
+    int tap = (int)(k / cout);
+    int r = tap / kw, s = tap % kw;
+    val = w[(((size_t)co * cin + ci) * kh + r) * kw + s];
   } else {
     val = w[i];
   }
@@ -331,6 +339,10 @@ extern "C" int hm_conv_gather(const HmConvDesc* d, const void* x1, const void* x
   long long M = (long long)d->B * d->Ho * d->Wo;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d->Cout + BN - 1) / BN));
   cudaStream_t st = (cudaStream_t)stream;
+  if (thin_in_conv_launch(d, x1, x2, w, bias, y, y2, st)) {
+    HM_CHECK_LAUNCH("hm_conv_gather(thin input)");
+    return HM_OK;
+  }
   if (d->dtype == HM_F32)
     conv_gather_kernel<float><<<grid, NT, 0, st>>>(*d, (const float*)x1, (const float*)x2,
                                                    (const float*)w, bias, (float*)y, (float*)y2);
@@ -348,6 +360,10 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
   HM_CHECK_ARG(x1 && dy && dw, "hm_conv_wgrad: null tensor");
   HM_CHECK_ARG(d->C2 == 0 || x2, "hm_conv_wgrad: C2>0 but x2 is null");
   HM_CHECK_ARG(!d->transposed, "hm_conv_wgrad: descriptor must be a forward gather");
+  if (thin_wgrad_launch(d, x1, x2, dy, dw, (cudaStream_t)stream)) {
+    HM_CHECK_LAUNCH("hm_conv_wgrad(thin)");
+    return HM_OK;
+  }
   int K = d->kh * d->kw * (d->C1 + d->C2);
   long long M = (long long)d->B * d->Ho * d->Wo;
   unsigned gx = (K + BM - 1) / BM, gy = (d->Cout + BN - 1) / BN;
@@ -373,7 +389,7 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG(mode >= 0 && mode <= 6, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode >= 0 && mode <= 7, "hm_pack_conv_weight: bad mode %d", mode);
   long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;

@@ -42,6 +42,7 @@ struct TcParams {
   __half* y;               // [B,Ho,Wo,split]       channels [0,split)
   __half* y2;              // [B,Ho,Wo,Cout-split]  channels [split,Cout)   (concat sources of an input gradient)
   int split, accumulate;   // accumulate bit0: y += , bit1: y2 +=
+  int vec_store;           // 1: 16-byte stores (Cout, split multiples of 8); 0: scalar stores of the real columns
 };
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -288,9 +289,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           uint32_t packed[16];
           uint4 prev[4];
           if (accum) {
+            if (p.vec_store) {
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (j * 8 < ncols) prev[j] = reinterpret_cast<const uint4*>(dst + c0)[j];
+              for (int j = 0; j < 4; j++)
+                if (j * 8 < ncols) prev[j] = reinterpret_cast<const uint4*>(dst + c0)[j];
+            } else {
+              __half* ph = reinterpret_cast<__half*>(prev);
+#pragma unroll
+              for (int j = 0; j < 32; j++) ph[j] = (col0 + c0 + j < p.Cout) ? dst[c0 + j] : __float2half(0.f);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -311,10 +318,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             __half2 h = __floats2half2_rn(a, b);
             packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
           }
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          if (p.vec_store) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (j * 8 < ncols) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < 4; j++)
+              if (j * 8 < ncols)
+                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          } else {  // thin outputs (Cout < 16 or not a multiple of 8): the N tile is zero-padded by TMA, store the real columns
+            const __half* ph = reinterpret_cast<const __half*>(packed);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (col0 + c0 + j < p.Cout) dst[c0 + j] = ph[j];
+          }
         }
       }
       tc_fence_before();
@@ -378,6 +393,11 @@ static int encode_wgt(CUtensorMap* tm, const void* ptr, int taps, int Cout, int 
 }
 
 static int pick_ntile(int Cout, int split) {
+  if (Cout % 16 || split % 16) {
+    // thin output: one zero-padded N tile (weight rows beyond Cout are TMA out-of-bounds = 0)
+    if (split != Cout || Cout > 256) return 0;
+    return (Cout + 15) / 16 * 16;
+  }
   for (int n = 256; n >= 16; n -= 16)
     if (Cout % n == 0 && split % n == 0) return n;
   return 0;
@@ -392,7 +412,7 @@ extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   if (d->dtype != HM_F16 || d->transposed || d->up || d->stride != 1) return 0;
   if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
   if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
-  if (d->Cout % 16 || d->Cout < 16 || pick_ntile(d->Cout, d->split) == 0) return 0;
+  if (d->Cout < 1 || pick_ntile(d->Cout, d->split) == 0) return 0;
   if (d->Ho != d->H + 2 * d->pad - d->kh + 1 || d->Wo != d->W + 2 * d->pad - d->kw + 1) return 0;
   if (d->oH != d->Ho || d->oW != d->Wo) return 0;
   return 1;
@@ -411,7 +431,8 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     set_error("hm_tc_conv: cuTensorMapEncodeTiled is not available from this driver");
     return HM_ERR_CUDA;
   }
-  if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc | (uintptr_t)y | (uintptr_t)y2) & 15) {
+  if ((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc) & 15) ||
+      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15))) {
     set_error("hm_tc_conv: pointers must be 16-byte aligned");
     return HM_ERR_ALIGN;
   }
@@ -427,7 +448,8 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.tiles_n = (d->B + p.bn - 1) / p.bn;
   p.n_mtiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.ntile = pick_ntile(d->Cout, d->split);
-  p.n_ntiles = d->Cout / p.ntile;
+  p.n_ntiles = (d->Cout + p.ntile - 1) / p.ntile;
+  p.vec_store = (d->Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
   const int stage_bytes = A_BYTES + p.ntile * 128;
   int stages = (227 * 1024 - 4096) / stage_bytes;
   if (stages > 8) stages = 8;

@@ -1,0 +1,277 @@
+// "Thin" convolutions: layers whose GEMM view has a degenerate K or N and are therefore HBM/L1-bound, not
+// tensor-core work: the first discriminator layer (1 -> 64 channels, reference
+// architectures/dcgan.py:42 with Cin=1; p2p.py:145,285 likewise) and the last generator layer (64 -> 1,
+// dcgan.py:32).  They are specialisations behind the hm_conv_gather / hm_conv_wgrad entry points (same
+// contract, same packed layouts); the generic tiled kernels in simt_conv.cu remain the fallback.
+//   * thin_in_conv:    Cin_total <= 4.  One thread = one output pixel x 8 output channels; the <=100 taps*Cin
+//                      inputs come through L1 (neighbouring pixels share them), the weights from shared memory,
+//                      the result leaves as one 16-byte store (coalesced 128 B per pixel for Cout = 64).
+//   * thin_in_wgrad:   Cin_total <= 4.  dWp[(tap,ci)][co] = sum_pix x[pix+tap][ci] * dy[pix][co]; one thread =
+//                      (tap, 8 output channels), a block streams a slab of pixels, fp32 register accumulators,
+//                      one atomic per (block, weight).
+//   * thin_out_wgrad:  Cout <= 4.   dWp[(tap,ci)][co] = sum_pix x[pix+tap][ci] * dy[pix][co]; one thread =
+//                      (tap, 8 input channels): one 16-byte load of x per pixel, dy broadcast.
+#include "hm_common.cuh"
+
+namespace hm {
+
+__device__ __forceinline__ void load8(const __half* p, float* v) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(__half* p, const float* v) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+constexpr int THIN_MAXK = 100;   // taps * Cin handled by the thin-input kernels (5x5x4)
+
+// ---- forward, Cin_total <= 4 ------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) thin_in_conv_kernel(HmConvDesc d, const T* __restrict__ x1,
+                                                           const T* __restrict__ x2, const T* __restrict__ w,
+                                                           const float* __restrict__ bias, T* __restrict__ y) {
+  extern __shared__ float ws[];                  // [K][Cout]
+  const int Ct = d.C1 + d.C2, K = d.kh * d.kw * Ct;
+  for (int i = threadIdx.x; i < K * d.Cout; i += blockDim.x) ws[i] = ldf(w + i);
+  __syncthreads();
+  const int groups = d.Cout >> 3;
+  const long long total = (long long)d.B * d.Ho * d.Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long pix = i / groups;
+    const int ox = (int)(pix % d.Wo);
+    long long t2 = pix / d.Wo;
+    const int oy = (int)(t2 % d.Ho);
+    const int n = (int)(t2 / d.Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = bias ? bias[g * 8 + j] : 0.f;
+    for (int r = 0; r < d.kh; r++) {
+      const int iy = oy * d.stride - d.pad + r;
+      if (iy < 0 || iy >= d.H) continue;
+      for (int s = 0; s < d.kw; s++) {
+        const int ix = ox * d.stride - d.pad + s;
+        if (ix < 0 || ix >= d.W) continue;
+        const size_t src = ((size_t)n * d.H + iy) * d.W + ix;
+        for (int ci = 0; ci < Ct; ci++) {
+          const float xv = ci < d.C1 ? ldf(x1 + src * d.C1 + ci) : ldf(x2 + src * d.C2 + (ci - d.C1));
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((r * d.kw + s) * Ct + ci) * d.Cout + g * 8);
+          const float4 wa = wr[0], wb = wr[1];
+          acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]);
+          acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
+          acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]);
+          acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = act_fwd(acc[j], d.act, d.slope);
+    store8(y + (size_t)pix * d.Cout + g * 8, acc);
+  }
+}
+
+// ---- weight gradient, Cin_total <= 4 ------------------------------------------------------------------------
+// thread = (tap, co8); block streams pixels [p0, p1)
+template <typename T>
+__global__ void __launch_bounds__(256) thin_in_wgrad_kernel(HmConvDesc d, const T* __restrict__ x1,
+                                                            const T* __restrict__ x2, const T* __restrict__ dy,
+                                                            float* dw, long long per_block) {
+  const int Ct = d.C1 + d.C2, taps = d.kh * d.kw, groups = d.Cout >> 3;
+  const int units = taps * groups;
+  const int lanes = blockDim.x / units;            // pixel lanes per block (>= 1 by launch)
+  const int u = threadIdx.x % units, pl = threadIdx.x / units;
+  const long long M = (long long)d.B * d.Ho * d.Wo;
+  const long long p0 = (long long)blockIdx.x * per_block, p1 = min(M, p0 + per_block);
+  if (pl >= lanes) return;
+  const int tap = u / groups, g = u - tap * groups;
+  const int r = tap / d.kw, s = tap - r * d.kw;
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[c][j] = 0.f;
+  for (long long pix = p0 + pl; pix < p1; pix += lanes) {
+    const int ox = (int)(pix % d.Wo);
+    long long t2 = pix / d.Wo;
+    const int oy = (int)(t2 % d.Ho);
+    const int n = (int)(t2 / d.Ho);
+    const int iy = oy * d.stride - d.pad + r, ix = ox * d.stride - d.pad + s;
+    if (iy < 0 || iy >= d.H || ix < 0 || ix >= d.W) continue;
+    float g8[8];
+    load8(dy + (size_t)pix * d.Cout + g * 8, g8);
+    const size_t src = ((size_t)n * d.H + iy) * d.W + ix;
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++) {
+      if (ci < Ct) {
+        const float xv = ci < d.C1 ? ldf(x1 + src * d.C1 + ci) : ldf(x2 + src * d.C2 + (ci - d.C1));
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[ci][j] = fmaf(xv, g8[j], acc[ci][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < 4; ci++)
+    if (ci < Ct) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) atomicAdd(dw + (size_t)(tap * Ct + ci) * d.Cout + g * 8 + j, acc[ci][j]);
+    }
+}
+
+// ---- weight gradient, Cout <= 4 -------------------------------------------------------------------------------
+// thread = (tap, ci8); x may be read through the virtual nearest/bilinear 2x upsampling.
+template <typename T>
+__device__ __forceinline__ void gather8(const HmConvDesc& d, const T* __restrict__ src, int C, int n, int iy, int ix,
+                                        int c0, float* v) {
+  const size_t img = (size_t)n * d.H;
+  if (d.up != HM_UP_BILINEAR2) {
+    const int sh = d.up ? 1 : 0;
+    load8(src + ((img + (iy >> sh)) * d.W + (ix >> sh)) * C + c0, v);
+    return;
+  }
+  const int y0 = iy >> 1, x0 = ix >> 1;
+  const int y1 = (iy & 1) ? min(y0 + 1, d.H - 1) : y0;
+  const int x1 = (ix & 1) ? min(x0 + 1, d.W - 1) : x0;
+  float a[8], b[8], e[8], f[8];
+  load8(src + ((img + y0) * d.W + x0) * C + c0, a);
+  load8(src + ((img + y0) * d.W + x1) * C + c0, b);
+  load8(src + ((img + y1) * d.W + x0) * C + c0, e);
+  load8(src + ((img + y1) * d.W + x1) * C + c0, f);
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = 0.25f * ((a[j] + b[j]) + (e[j] + f[j]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) thin_out_wgrad_kernel(HmConvDesc d, const T* __restrict__ x1,
+                                                             const T* __restrict__ x2, const T* __restrict__ dy,
+                                                             float* dw, long long per_block) {
+  const int Ct = d.C1 + d.C2, taps = d.kh * d.kw, cg = Ct >> 3;
+  const int units = taps * cg;
+  const long long M = (long long)d.B * d.Ho * d.Wo;
+  const long long p0 = (long long)blockIdx.x * per_block, p1 = min(M, p0 + per_block);
+  const int sh = d.up ? 1 : 0;
+  const int Hv = d.H << sh, Wv = d.W << sh;
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    const int tap = u / cg, c0 = (u - tap * cg) * 8;
+    const int r = tap / d.kw, s = tap - r * d.kw;
+    const T* src = c0 < d.C1 ? x1 : x2;
+    const int C = c0 < d.C1 ? d.C1 : d.C2;
+    const int cc = c0 < d.C1 ? c0 : c0 - d.C1;
+    float acc[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[c][j] = 0.f;
+    int ox = (int)(p0 % d.Wo);
+    long long t2 = p0 / d.Wo;
+    int oy = (int)(t2 % d.Ho);
+    int n = (int)(t2 / d.Ho);
+    for (long long pix = p0; pix < p1; pix++) {
+      const int iy = oy * d.stride - d.pad + r, ix = ox * d.stride - d.pad + s;
+      if (iy >= 0 && iy < Hv && ix >= 0 && ix < Wv) {
+        float xv[8];
+        gather8<T>(d, src, C, n, iy, ix, cc, xv);
+        const size_t op = ((size_t)n * d.oH + (oy * d.os + d.ou)) * d.oW + (ox * d.os + d.ov);
+#pragma unroll
+        for (int co = 0; co < 4; co++)
+          if (co < d.Cout) {
+            const float g = ldf(dy + op * d.Cout + co);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[co][j] = fmaf(xv[j], g, acc[co][j]);
+          }
+      }
+      if (++ox == d.Wo) {
+        ox = 0;
+        if (++oy == d.Ho) {
+          oy = 0;
+          ++n;
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < 4; co++)
+      if (co < d.Cout) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) atomicAdd(dw + (size_t)(tap * Ct + c0 + j) * d.Cout + co, acc[co][j]);
+      }
+  }
+}
+
+// ---- dispatch helpers called from simt_conv.cu ----------------------------------------------------------------
+bool thin_in_conv_launch(const HmConvDesc* d, const void* x1, const void* x2, const void* w, const float* bias,
+                         void* y, void* y2, cudaStream_t st) {
+  const int Ct = d->C1 + d->C2;
+  if (Ct > 4 || d->transposed || d->up || d->Cout % 8 || d->os != 1 || d->split != d->Cout || d->accumulate ||
+      y2 != nullptr || y == nullptr || d->kh * d->kw * Ct > THIN_MAXK || d->kh * d->kw * Ct * d->Cout * 4 > 48 * 1024)
+    return false;
+  if (((uintptr_t)y & 15) != 0) return false;
+  const long long total = (long long)d->B * d->Ho * d->Wo * (d->Cout / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)d->kh * d->kw * Ct * d->Cout * sizeof(float);
+  if (d->dtype == HM_F32)
+    thin_in_conv_kernel<float><<<(unsigned)blocks, 256, smem, st>>>(*d, (const float*)x1, (const float*)x2,
+                                                                    (const float*)w, bias, (float*)y);
+  else
+    thin_in_conv_kernel<__half><<<(unsigned)blocks, 256, smem, st>>>(*d, (const __half*)x1, (const __half*)x2,
+                                                                     (const __half*)w, bias, (__half*)y);
+  return true;
+}
+
+bool thin_wgrad_launch(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw,
+                       cudaStream_t st) {
+  const int Ct = d->C1 + d->C2;
+  const long long M = (long long)d->B * d->Ho * d->Wo;
+  if (d->transposed) return false;
+  if (Ct <= 4 && !d->up && d->os == 1 && d->Cout % 8 == 0 && d->kh * d->kw * (d->Cout / 8) <= 256 &&
+      ((uintptr_t)dy & 15) == 0) {
+    const int units = d->kh * d->kw * (d->Cout / 8);
+    const int lanes = 256 / units;
+    long long blocks = (long long)num_sms() * 4;
+    long long per = (M + blocks - 1) / blocks;
+    if (per < lanes) per = lanes;
+    blocks = (M + per - 1) / per;
+    if (d->dtype == HM_F32)
+      thin_in_wgrad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(*d, (const float*)x1, (const float*)x2,
+                                                                    (const float*)dy, dw, per);
+    else
+      thin_in_wgrad_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(*d, (const __half*)x1, (const __half*)x2,
+                                                                     (const __half*)dy, dw, per);
+    return true;
+  }
+  if (d->Cout <= 4 && d->C1 % 8 == 0 && d->C2 % 8 == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)x2 & 15) == 0) {
+    long long blocks = (long long)num_sms() * 4;
+    long long per = (M + blocks - 1) / blocks;
+    if (per < 64) per = 64;
+    blocks = (M + per - 1) / per;
+    if (d->dtype == HM_F32)
+      thin_out_wgrad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(*d, (const float*)x1, (const float*)x2,
+                                                                     (const float*)dy, dw, per);
+    else
+      thin_out_wgrad_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(*d, (const __half*)x1, (const __half*)x2,
+                                                                      (const __half*)dy, dw, per);
+    return true;
+  }
+  return false;
+}
+
+}  // namespace hm

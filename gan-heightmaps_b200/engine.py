@@ -155,6 +155,9 @@ class ConvOp(object):
             self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
         self.path = "tcgen05" if self.tc_fwd else "simt"
+        # input gradient of a thin-output stride-1 convolution (dy has <= 4 channels): forward-form gather of dy,
+        # which the library serves with its thin-input kernel
+        self.fw_dg = kind == "conv" and self.stride == 1 and self.Cout <= 4 and not self.tc_dg
 
     # -- buffers ------------------------------------------------------------ #
     def alloc(self, rt, B):
@@ -188,8 +191,8 @@ class ConvOp(object):
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 5, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
             if not self.tc_dg:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 1, self.Cout, self.Cin, self.kh, self.kw,
-                        0, 0, rt.cd)
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 7 if self.fw_dg else 1, self.Cout, self.Cin,
+                        self.kh, self.kw, 0, 0, rt.cd)
             else:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 6, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
@@ -357,7 +360,7 @@ class ConvOp(object):
                 d = self._tc_dgrad_desc(rt, n, 0)
                 rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, _ptr(y1), _ptr(y2))
             else:
-                d = self._dgrad_desc(rt, n, 0)
+                d = self._tc_dgrad_desc(rt, n, 0) if self.fw_dg else self._dgrad_desc(rt, n, 0)
                 rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, _ptr(y1), _ptr(y2))
             for (x, y, c) in ((self.x1, y1, self.C1), (self.x2, y2, self.C2)):
                 if y is None:
@@ -372,7 +375,7 @@ class ConvOp(object):
                 d = self._tc_dgrad_desc(rt, n, acc)
                 rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, y1, y2)
             else:
-                d = self._dgrad_desc(rt, n, acc)
+                d = self._tc_dgrad_desc(rt, n, acc) if self.fw_dg else self._dgrad_desc(rt, n, acc)
                 rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, y1, y2)
 
 

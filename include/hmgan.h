@@ -132,6 +132,8 @@ int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void*
  *  mode 6: Conv2DLayer W, tcgen05 input-gradient pack     -> Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
  *          (the input gradient of a stride-1 'same' convolution is the forward correlation of dy with this
  *           pack and pad' = k-1-pad)
+ *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
+ *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)
  * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the
  * inverse index map of mode 0 / 2(all taps) / 4 to a packed fp32 gradient and
  * (over)writes the master-layout gradient. */

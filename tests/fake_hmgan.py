@@ -155,6 +155,8 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
     elif mode == 5:
         src = W.reshape(cout, cin, kh, kw)[:, :, ::-1, ::-1]
         out = src.transpose(2, 3, 0, 1)                      # [r][s][co][ci]
+    elif mode == 7:
+        out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 1, 0)   # [r][s][ci][co]
     else:
@@ -420,8 +422,10 @@ def _tc_ok(d, wgrad):
     ok = ok and d.oH == d.Ho and d.oW == d.Wo
     if wgrad:
         return ok and d.Cout % 64 == 0 and 0 < d.Cout <= 256
+    if d.Cout % 16 or d.split % 16:
+        return ok and d.split == d.Cout and 0 < d.Cout <= 256
     ntile = [n for n in range(256, 15, -16) if d.Cout % n == 0 and d.split % n == 0]
-    return ok and d.Cout % 16 == 0 and d.Cout >= 16 and 0 < d.split <= d.Cout and bool(ntile)
+    return ok and 0 < d.split <= d.Cout and bool(ntile)
 
 
 def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):

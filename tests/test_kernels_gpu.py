@@ -74,6 +74,14 @@ FWD_CASES = {
                                       ov=0, Cout=3, split=3, act=4),
     "dense": dict(B=4, H=1, W=1, C1=100, kh=1, kw=1, pad=0, Ho=1, Wo=1, oH=1, oW=1, Cout=128, split=128),
     "wide": dict(B=1, H=20, W=20, C1=64, kh=5, kw=5, pad=2, Ho=20, Wo=20, oH=20, oW=20, Cout=96, split=96, act=2),
+    "thin_in_5x5_1_64": dict(B=2, H=24, W=20, C1=1, kh=5, kw=5, pad=2, Ho=24, Wo=20, oH=24, oW=20, Cout=64, split=64,
+                             act=1, slope=0.2),
+    "thin_in_3x3_s2_1+3_32": dict(B=2, H=16, W=16, C1=1, C2=3, kh=3, kw=3, stride=2, pad=1, Ho=8, Wo=8, oH=8, oW=8,
+                                  Cout=32, split=32, act=1, slope=0.01),
+    "thin_out_5x5_64_1": dict(B=2, H=16, W=16, C1=64, kh=5, kw=5, pad=2, Ho=16, Wo=16, oH=16, oW=16, Cout=1, split=1,
+                              act=3),
+    "thin_out_2x2_deconv_phase_128_3": dict(B=2, H=8, W=8, C1=64, C2=64, kh=1, kw=1, pad=0, Ho=8, Wo=8, oH=16, oW=16,
+                                            os=2, ou=0, ov=1, Cout=3, split=3, act=4),
     "dgrad_5x5": dict(H=12, W=10, C1=7, kh=5, kw=5, pad=2, transposed=1, Ho=12, Wo=10, oH=12, oW=10, Cout=5,
                       split=5),
     "dgrad_3x3_s2_split_acc": dict(H=8, W=8, C1=9, kh=3, kw=3, stride=2, pad=1, transposed=1, Ho=16, Wo=16, oH=16,
