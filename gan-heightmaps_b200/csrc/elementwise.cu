@@ -350,6 +350,356 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, long lon
     stf(d + i, ldf(s + i));
 }
 
+
+// ===========================================================================
+// 8-wide (16-byte) variants for channel counts that are multiples of 8: every
+// thread owns 8 consecutive channels of one pixel, so a warp moves 512 B per
+// access and the per-element index arithmetic is paid once per 8 elements.
+// ===========================================================================
+template <typename T, int MODE>  // MODE 0: sum,sumsq ; 1: sum only
+__global__ void __launch_bounds__(256) col_reduce_v8_kernel(const T* __restrict__ x, long long M, int C,
+                                                            double* sums, float* fsum) {
+  __shared__ float sh0[256 * 8], sh1[MODE == 0 ? 256 * 8 : 8];
+  const int cg = C >> 3;                       // channel groups
+  const int ct = cg < 256 ? cg : 256;          // groups covered per pass
+  const int lanes = 256 / ct;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  for (int g0 = 0; g0 < cg; g0 += ct) {
+    const int g = g0 + tc;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
+    if (active && g < cg) {
+      for (long long m = (long long)blockIdx.x * lanes + tr; m < M; m += (long long)gridDim.x * lanes) {
+        float v[8];
+        load8(x + (size_t)m * C + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += v[j];
+          if (MODE == 0) s1[j] += v[j] * v[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sh0[threadIdx.x * 8 + j] = s0[j];
+      if (MODE == 0) sh1[threadIdx.x * 8 + j] = s1[j];
+    }
+    __syncthreads();
+    if (tr == 0 && g < cg) {
+      for (int l = 1; l < lanes; l++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += sh0[(l * ct + tc) * 8 + j];
+          if (MODE == 0) s1[j] += sh1[(l * ct + tc) * 8 + j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (MODE == 0) {
+          atomicAdd(sums + g * 8 + j, (double)s0[j]);
+          atomicAdd(sums + C + g * 8 + j, (double)s1[j]);
+        } else {
+          atomicAdd(fsum + g * 8 + j, s0[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void bn_apply_act_v8_kernel(const T* __restrict__ x, T* __restrict__ a, long long n8, int C,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                       float slope) {
+  const int cg = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cg) * 8;
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = act_fwd(v[j] * scale[c0 + j] + shift[c0 + j], act, slope);
+    store8(a + i * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    bn_bwd_reduce_v8_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x, long long M,
+                            int C, const float* __restrict__ mean, const float* __restrict__ inv_std, int act,
+                            float slope, double* red) {
+  __shared__ float sh0[256 * 8], sh1[256 * 8];
+  const int cg = C >> 3;
+  const int ct = cg < 256 ? cg : 256;
+  const int lanes = 256 / ct;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  for (int g0 = 0; g0 < cg; g0 += ct) {
+    const int g = g0 + tc;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
+    if (active && g < cg) {
+      float mu[8], is[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        mu[j] = mean[g * 8 + j];
+        is[j] = inv_std[g * 8 + j];
+      }
+      for (long long m = (long long)blockIdx.x * lanes + tr; m < M; m += (long long)gridDim.x * lanes) {
+        const size_t o = (size_t)m * C + g * 8;
+        float gv[8], av[8], xv[8];
+        load8(da + o, gv);
+        load8(a + o, av);
+        load8(x + o, xv);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gg = gv[j] * act_grad_from_out(av[j], act, slope);
+          s0[j] += gg;
+          s1[j] += gg * (xv[j] - mu[j]) * is[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sh0[threadIdx.x * 8 + j] = s0[j];
+      sh1[threadIdx.x * 8 + j] = s1[j];
+    }
+    __syncthreads();
+    if (tr == 0 && g < cg) {
+      for (int l = 1; l < lanes; l++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += sh0[(l * ct + tc) * 8 + j];
+          s1[j] += sh1[(l * ct + tc) * 8 + j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        atomicAdd(red + g * 8 + j, (double)s0[j]);
+        atomicAdd(red + C + g * 8 + j, (double)s1[j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_v8_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x,
+                                       T* __restrict__ dx, long long M, int C, const float* __restrict__ mean,
+                                       const float* __restrict__ inv_std, const float* __restrict__ gamma, int act,
+                                       float slope, const double* __restrict__ red, float* dgamma, float* dbeta) {
+  const int cg = C >> 3;
+  const long long n8 = M * cg;
+  const float invM = 1.f / (float)M;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cg) * 8;
+    float gv[8], av[8], xv[8], o[8];
+    load8(da + i * 8, gv);
+    load8(a + i * 8, av);
+    load8(x + i * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = c0 + j;
+      const float r0 = (float)red[c], r1 = (float)red[C + c], is = inv_std[c];
+      const float gg = gv[j] * act_grad_from_out(av[j], act, slope);
+      const float xh = (xv[j] - mean[c]) * is;
+      o[j] = gamma[c] * is * (gg - r0 * invM - xh * r1 * invM);
+      if (i < cg) {
+        if (dgamma) dgamma[c] = r1;
+        if (dbeta) dbeta[c] = r0;
+      }
+    }
+    store8(dx + i * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void act_bwd_v8_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* dx, long long n8, int act,
+                                  float slope, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float g[8], yv[8], o[8];
+    load8(dy + i * 8, g);
+    load8(y + i * 8, yv);
+    if (accumulate) load8(dx + i * 8, o);
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j] = g[j] * act_grad_from_out(yv[j], act, slope) + (accumulate ? o[j] : 0.f);
+    store8(dx + i * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void maxpool2_fwd_v8_kernel(const T* __restrict__ x, T* __restrict__ p, uint8_t* __restrict__ idx, int B,
+                                       int H, int W, int C) {
+  const int Hp = H >> 1, Wp = W >> 1, cg = C >> 3;
+  const long long n8 = (long long)B * Hp * Wp * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long t = i / cg;
+    const int px = (int)(t % Wp);
+    t /= Wp;
+    const int py = (int)(t % Hp);
+    const int b = (int)(t / Hp);
+    const T* base = x + (((size_t)b * H + 2 * py) * W + 2 * px) * C + g * 8;
+    float v0[8], v1[8], v2[8], v3[8], m[8];
+    load8(base, v0);
+    load8(base + C, v1);
+    load8(base + (size_t)W * C, v2);
+    load8(base + (size_t)W * C + C, v3);
+    uint32_t klo = 0, khi = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float mm = v0[j];
+      uint32_t k = 0;
+      if (v1[j] > mm) { mm = v1[j]; k = 1; }
+      if (v2[j] > mm) { mm = v2[j]; k = 2; }
+      if (v3[j] > mm) { mm = v3[j]; k = 3; }
+      m[j] = mm;
+      if (j < 4) klo |= k << (8 * j); else khi |= k << (8 * (j - 4));
+    }
+    store8(p + i * 8, m);
+    *reinterpret_cast<uint2*>(idx + i * 8) = make_uint2(klo, khi);
+  }
+}
+
+template <typename T>
+__global__ void maxpool2_bwd_v8_kernel(const T* __restrict__ dp, const T* __restrict__ p,
+                                       const uint8_t* __restrict__ idx, T* __restrict__ dx, int B, int H, int W, int C,
+                                       int act, float slope) {
+  const int Hp = H >> 1, Wp = W >> 1, cg = C >> 3;
+  const long long n8 = (long long)B * Hp * Wp * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long t = i / cg;
+    const int px = (int)(t % Wp);
+    t /= Wp;
+    const int py = (int)(t % Hp);
+    const int b = (int)(t / Hp);
+    float gv[8], pv[8];
+    load8(dp + i * 8, gv);
+    load8(p + i * 8, pv);
+    const uint2 kk = *reinterpret_cast<const uint2*>(idx + i * 8);
+    float o0[8], o1[8], o2[8], o3[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float gg = gv[j] * act_grad_from_out(pv[j], act, slope);
+      const uint32_t k = ((j < 4 ? kk.x : kk.y) >> (8 * (j & 3))) & 0xff;
+      o0[j] = k == 0 ? gg : 0.f;
+      o1[j] = k == 1 ? gg : 0.f;
+      o2[j] = k == 2 ? gg : 0.f;
+      o3[j] = k == 3 ? gg : 0.f;
+    }
+    T* base = dx + (((size_t)b * H + 2 * py) * W + 2 * px) * C + g * 8;
+    store8(base, o0);
+    store8(base + C, o1);
+    store8(base + (size_t)W * C, o2);
+    store8(base + (size_t)W * C + C, o3);
+  }
+}
+
+template <typename T>
+__global__ void upsample2_fwd_v8_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
+                                        int mode) {
+  const int H2 = 2 * H, W2 = 2 * W, cg = C >> 3;
+  const long long n8 = (long long)B * H2 * W2 * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long t = i / cg;
+    const int ox = (int)(t % W2);
+    t /= W2;
+    const int oy = (int)(t % H2);
+    const int b = (int)(t / H2);
+    const T* img = x + (size_t)b * H * W * C + g * 8;
+    const int y0 = oy >> 1, x0 = ox >> 1;
+    float v[8];
+    if (mode == HM_UP_NEAREST2) {
+      load8(img + ((size_t)y0 * W + x0) * C, v);
+    } else {
+      const int y1 = (oy & 1) ? min(y0 + 1, H - 1) : y0;
+      const int x1 = (ox & 1) ? min(x0 + 1, W - 1) : x0;
+      float a[8], bb[8], e[8], f[8];
+      load8(img + ((size_t)y0 * W + x0) * C, a);
+      load8(img + ((size_t)y0 * W + x1) * C, bb);
+      load8(img + ((size_t)y1 * W + x0) * C, e);
+      load8(img + ((size_t)y1 * W + x1) * C, f);
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = 0.25f * ((a[j] + bb[j]) + (e[j] + f[j]));
+    }
+    store8(y + i * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void upsample2_bwd_v8_kernel(const T* __restrict__ dy, T* dx, int B, int H, int W, int C, int mode,
+                                        int accumulate) {
+  const int cg = C >> 3;
+  const long long n8 = (long long)B * H * W * cg;
+  const int H2 = 2 * H, W2 = 2 * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long t = i / cg;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    const T* img = dy + (size_t)b * H2 * W2 * C + g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    if (mode == HM_UP_NEAREST2) {
+      for (int a = 0; a < 2; a++)
+        for (int e = 0; e < 2; e++) {
+          float v[8];
+          load8(img + ((size_t)(2 * y + a) * W2 + (2 * x + e)) * C, v);
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[j] += v[j];
+        }
+    } else {
+      int ys[3], xs[3];
+      float wy[3], wx[3];
+      int ny = 0, nx = 0;
+      ys[ny] = 2 * y; wy[ny++] = 1.f;
+      ys[ny] = 2 * y + 1; wy[ny++] = (y == H - 1) ? 1.f : .5f;
+      if (y > 0) { ys[ny] = 2 * y - 1; wy[ny++] = .5f; }
+      xs[nx] = 2 * x; wx[nx++] = 1.f;
+      xs[nx] = 2 * x + 1; wx[nx++] = (x == W - 1) ? 1.f : .5f;
+      if (x > 0) { xs[nx] = 2 * x - 1; wx[nx++] = .5f; }
+      for (int a = 0; a < ny; a++)
+        for (int e = 0; e < nx; e++) {
+          float v[8];
+          load8(img + ((size_t)ys[a] * W2 + xs[e]) * C, v);
+          const float wgt = wy[a] * wx[e];
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[j] += wgt * v[j];
+        }
+    }
+    if (accumulate) {
+      float o[8];
+      load8(dx + i * 8, o);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += o[j];
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+template <typename T>
+__global__ void copy_v8_kernel(const T* __restrict__ s, T* __restrict__ d, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x)
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(T) / 2); q++)     // 8 elements = 1 (fp16) or 2 (fp32) 16-byte words
+      reinterpret_cast<uint4*>(d)[i * (sizeof(T) / 2) + q] = reinterpret_cast<const uint4*>(s)[i * (sizeof(T) / 2) + q];
+}
+
+static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
 // ---- losses ---------------------------------------------------------------
 template <typename T>
 __global__ void adv_loss_kernel(const T* __restrict__ h, T* dh, long long R, int G, int out_act, float target,
@@ -483,6 +833,14 @@ extern "C" int hm_device_supported(void) {
 extern "C" int hm_bn_stats(const void* x, int dtype, long long M, int C, double* sums, void* stream) {
   CHECK_DTYPE(dtype, "hm_bn_stats");
   HM_CHECK_ARG(x && sums && M > 0 && C > 0, "hm_bn_stats: bad argument");
+  if (C % 8 == 0 && al16(x)) {
+    int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
+    unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
+    DISPATCH_T(dtype, (col_reduce_v8_kernel<T, 0><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums,
+                                                                                       nullptr)));
+    HM_CHECK_LAUNCH("hm_bn_stats");
+    return HM_OK;
+  }
   int lanes = RED_THREADS / (C < RED_THREADS ? C : RED_THREADS);
   unsigned grid = ew_grid((M + lanes - 1) / lanes, 1, 4);
   DISPATCH_T(dtype, (col_reduce_kernel<T, 0><<<grid, RED_THREADS, 0, (cudaStream_t)stream>>>((const T*)x, M, C,
@@ -494,6 +852,14 @@ extern "C" int hm_bn_stats(const void* x, int dtype, long long M, int C, double*
 extern "C" int hm_col_sum(const void* dy, int dtype, long long M, int C, float* db, void* stream) {
   CHECK_DTYPE(dtype, "hm_col_sum");
   HM_CHECK_ARG(dy && db && M > 0 && C > 0, "hm_col_sum: bad argument");
+  if (C % 8 == 0 && al16(dy)) {
+    int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
+    unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
+    DISPATCH_T(dtype, (col_reduce_v8_kernel<T, 1><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)dy, M, C, nullptr,
+                                                                                       db)));
+    HM_CHECK_LAUNCH("hm_col_sum");
+    return HM_OK;
+  }
   int lanes = RED_THREADS / (C < RED_THREADS ? C : RED_THREADS);
   unsigned grid = ew_grid((M + lanes - 1) / lanes, 1, 4);
   DISPATCH_T(dtype, (col_reduce_kernel<T, 1><<<grid, RED_THREADS, 0, (cudaStream_t)stream>>>((const T*)dy, M, C,
@@ -521,6 +887,12 @@ extern "C" int hm_bn_apply_act(const void* x, void* a, int dtype, long long M, i
   CHECK_DTYPE(dtype, "hm_bn_apply_act");
   HM_CHECK_ARG(x && a && scale && shift && M > 0 && C > 0, "hm_bn_apply_act: bad argument");
   long long n = M * C;
+  if (C % 8 == 0 && al16(x) && al16(a)) {
+    DISPATCH_T(dtype, (bn_apply_act_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                          (const T*)x, (T*)a, n / 8, C, scale, shift, act, slope)));
+    HM_CHECK_LAUNCH("hm_bn_apply_act");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (bn_apply_act_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)x, (T*)a, n, C, scale, shift, act, slope)));
   HM_CHECK_LAUNCH("hm_bn_apply_act");
@@ -532,6 +904,14 @@ extern "C" int hm_bn_bwd_reduce(const void* da, const void* a, const void* x, in
                                 void* stream) {
   CHECK_DTYPE(dtype, "hm_bn_bwd_reduce");
   HM_CHECK_ARG(da && a && x && mean && inv_std && red && M > 0 && C > 0, "hm_bn_bwd_reduce: bad argument");
+  if (C % 8 == 0 && al16(da) && al16(a) && al16(x)) {
+    int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
+    unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
+    DISPATCH_T(dtype, (bn_bwd_reduce_v8_kernel<T><<<g8, 256, 0, (cudaStream_t)stream>>>(
+                          (const T*)da, (const T*)a, (const T*)x, M, C, mean, inv_std, act, slope, red)));
+    HM_CHECK_LAUNCH("hm_bn_bwd_reduce");
+    return HM_OK;
+  }
   int lanes = RED_THREADS / (C < RED_THREADS ? C : RED_THREADS);
   unsigned grid = ew_grid((M + lanes - 1) / lanes, 1, 4);
   DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<grid, RED_THREADS, 0, (cudaStream_t)stream>>>(
@@ -547,6 +927,13 @@ extern "C" int hm_bn_bwd_apply(const void* da, const void* a, const void* x, voi
   HM_CHECK_ARG(da && a && x && dx && mean && inv_std && gamma && red && M > 0 && C > 0,
                "hm_bn_bwd_apply: bad argument");
   long long n = M * C;
+  if (C % 8 == 0 && al16(da) && al16(a) && al16(x) && al16(dx)) {
+    DISPATCH_T(dtype, (bn_bwd_apply_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                          (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope, red,
+                          dgamma, dbeta)));
+    HM_CHECK_LAUNCH("hm_bn_bwd_apply");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope,
                         red, dgamma, dbeta)));
@@ -558,6 +945,12 @@ extern "C" int hm_act_bwd(const void* dy, const void* y, void* dx, int dtype, lo
                           int accumulate, void* stream) {
   CHECK_DTYPE(dtype, "hm_act_bwd");
   HM_CHECK_ARG(dy && y && dx && n > 0, "hm_act_bwd: bad argument");
+  if (n % 8 == 0 && al16(dy) && al16(y) && al16(dx)) {
+    DISPATCH_T(dtype, (act_bwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                          (const T*)dy, (const T*)y, (T*)dx, n / 8, act, slope, accumulate)));
+    HM_CHECK_LAUNCH("hm_act_bwd");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (act_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)dy, (const T*)y, (T*)dx, n, act, slope, accumulate)));
   HM_CHECK_LAUNCH("hm_act_bwd");
@@ -569,6 +962,12 @@ extern "C" int hm_maxpool2_fwd(const void* x, void* p, uint8_t* idx, int dtype, 
   CHECK_DTYPE(dtype, "hm_maxpool2_fwd");
   HM_CHECK_ARG(x && p && idx && B > 0 && H >= 2 && W >= 2 && C > 0, "hm_maxpool2_fwd: bad argument");
   long long n = (long long)B * (H / 2) * (W / 2) * C;
+  if (C % 8 == 0 && al16(x) && al16(p) && (((uintptr_t)idx) & 7) == 0) {
+    DISPATCH_T(dtype, (maxpool2_fwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)p,
+                                                                                                   idx, B, H, W, C)));
+    HM_CHECK_LAUNCH("hm_maxpool2_fwd");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (maxpool2_fwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)p,
                                                                                           idx, B, H, W, C)));
   HM_CHECK_LAUNCH("hm_maxpool2_fwd");
@@ -581,6 +980,12 @@ extern "C" int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx
   HM_CHECK_ARG(dp && p && idx && dx && B > 0 && H >= 2 && W >= 2 && C > 0, "hm_maxpool2_bwd: bad argument");
   HM_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "hm_maxpool2_bwd: odd spatial size");
   long long n = (long long)B * (H / 2) * (W / 2) * C;
+  if (C % 8 == 0 && al16(dp) && al16(p) && al16(dx) && (((uintptr_t)idx) & 7) == 0) {
+    DISPATCH_T(dtype, (maxpool2_bwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                          (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope)));
+    HM_CHECK_LAUNCH("hm_maxpool2_bwd");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope)));
   HM_CHECK_LAUNCH("hm_maxpool2_bwd");
@@ -593,6 +998,12 @@ extern "C" int hm_upsample2_bwd(const void* dy, void* dx, int dtype, int B, int 
   HM_CHECK_ARG(dy && dx && B > 0 && H > 0 && W > 0 && C > 0, "hm_upsample2_bwd: bad argument");
   HM_CHECK_ARG(mode == HM_UP_NEAREST2 || mode == HM_UP_BILINEAR2, "hm_upsample2_bwd: bad mode %d", mode);
   long long n = (long long)B * H * W * C;
+  if (C % 8 == 0 && al16(dy) && al16(dx)) {
+    DISPATCH_T(dtype, (upsample2_bwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                          (const T*)dy, (T*)dx, B, H, W, C, mode, accumulate)));
+    HM_CHECK_LAUNCH("hm_upsample2_bwd");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (upsample2_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)dy, (T*)dx, B, H, W, C, mode, accumulate)));
   HM_CHECK_LAUNCH("hm_upsample2_bwd");
@@ -605,6 +1016,12 @@ extern "C" int hm_upsample2_fwd(const void* x, void* y, int dtype, int B, int H,
   HM_CHECK_ARG(x && y && B > 0 && H > 0 && W > 0 && C > 0, "hm_upsample2_fwd: bad argument");
   HM_CHECK_ARG(mode == HM_UP_NEAREST2 || mode == HM_UP_BILINEAR2, "hm_upsample2_fwd: bad mode %d", mode);
   long long n = (long long)B * H * W * C * 4;
+  if (C % 8 == 0 && al16(x) && al16(y)) {
+    DISPATCH_T(dtype, (upsample2_fwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y,
+                                                                                                    B, H, W, C, mode)));
+    HM_CHECK_LAUNCH("hm_upsample2_fwd");
+    return HM_OK;
+  }
   DISPATCH_T(dtype, (upsample2_fwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, B,
                                                                                            H, W, C, mode)));
   HM_CHECK_LAUNCH("hm_upsample2_fwd");
@@ -650,6 +1067,12 @@ extern "C" int hm_cast(const void* src, int sd, void* dst, int dd, long long n, 
   HM_CHECK_ARG(src && dst && n > 0, "hm_cast: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned g = ew_grid(n);
+  if (sd == dd && n % 8 == 0 && al16(src) && al16(dst)) {
+    if (sd == HM_F32) copy_v8_kernel<float><<<ew_grid(n / 8), 256, 0, st>>>((const float*)src, (float*)dst, n / 8);
+    else copy_v8_kernel<__half><<<ew_grid(n / 8), 256, 0, st>>>((const __half*)src, (__half*)dst, n / 8);
+    HM_CHECK_LAUNCH("hm_cast");
+    return HM_OK;
+  }
   if (sd == HM_F32 && dd == HM_F16) cast_kernel<float, __half><<<g, 256, 0, st>>>((const float*)src, (__half*)dst, n);
   else if (sd == HM_F16 && dd == HM_F32) cast_kernel<__half, float><<<g, 256, 0, st>>>((const __half*)src, (float*)dst, n);
   else if (sd == HM_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);

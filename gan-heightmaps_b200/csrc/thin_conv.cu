@@ -15,32 +15,6 @@
 
 namespace hm {
 
-__device__ __forceinline__ void load8(const __half* p, float* v) {
-  uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    float2 f = __half22float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void load8(const float* p, float* v) {
-  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void store8(__half* p, const float* v) {
-  uint4 u;
-  __half2* h = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-__device__ __forceinline__ void store8(float* p, const float* v) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-
 constexpr int THIN_MAXK = 100;   // taps * Cin handled by the thin-input kernels (5x5x4)
 
 // ---- forward, Cin_total <= 4 ------------------------------------------------------------------------------
@@ -136,6 +110,121 @@ __global__ void __launch_bounds__(256) thin_in_wgrad_kernel(HmConvDesc d, const 
     }
 }
 
+
+// ---- forward, Cin = 1, stride 1, 4 consecutive output pixels x 8 channels per thread ---------------------------
+// Fully unrolled over the KHxKW taps; per filter row the thread loads KW+3 neighbouring inputs once and reuses
+// them for its 4 pixels; weights come from shared memory as two float4 per tap.
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256) thin_in_conv_c1_kernel(HmConvDesc d, const T* __restrict__ x,
+                                                              const T* __restrict__ w, const float* __restrict__ bias,
+                                                              T* __restrict__ y) {
+  extern __shared__ float ws[];                  // [KH*KW][Cout]
+  for (int i = threadIdx.x; i < KH * KW * d.Cout; i += blockDim.x) ws[i] = ldf(w + i);
+  __syncthreads();
+  const int groups = d.Cout >> 3;
+  const int wq = (d.Wo + 3) >> 2;                // 4-pixel strips per row
+  const long long total = (long long)d.B * d.Ho * wq * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t1 = i / groups;
+    const int sx = (int)(t1 % wq);
+    t1 /= wq;
+    const int oy = (int)(t1 % d.Ho);
+    const int n = (int)(t1 / d.Ho);
+    const int ox0 = sx * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[p][j] = bias ? bias[g * 8 + j] : 0.f;
+#pragma unroll
+    for (int r = 0; r < KH; r++) {
+      const int iy = oy - d.pad + r;
+      if (iy < 0 || iy >= d.H) continue;
+      const T* row = x + ((size_t)n * d.H + iy) * d.W;
+      float xv[KW + 3];
+#pragma unroll
+      for (int q = 0; q < KW + 3; q++) {
+        const int ix = ox0 - d.pad + q;
+        xv[q] = (ix >= 0 && ix < d.W) ? ldf(row + ix) : 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < KW; s++) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + (r * KW + s) * d.Cout + g * 8);
+        const float4 wa = wr[0], wb = wr[1];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          const float v = xv[p + s];
+          acc[p][0] = fmaf(v, wa.x, acc[p][0]); acc[p][1] = fmaf(v, wa.y, acc[p][1]);
+          acc[p][2] = fmaf(v, wa.z, acc[p][2]); acc[p][3] = fmaf(v, wa.w, acc[p][3]);
+          acc[p][4] = fmaf(v, wb.x, acc[p][4]); acc[p][5] = fmaf(v, wb.y, acc[p][5]);
+          acc[p][6] = fmaf(v, wb.z, acc[p][6]); acc[p][7] = fmaf(v, wb.w, acc[p][7]);
+        }
+      }
+    }
+    T* dst = y + (((size_t)n * d.Ho + oy) * d.Wo + ox0) * d.Cout + g * 8;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      if (ox0 + p < d.Wo) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[p][j] = act_fwd(acc[p][j], d.act, d.slope);
+        store8(dst + (size_t)p * d.Cout, acc[p]);
+      }
+    }
+  }
+}
+
+// ---- weight gradient, Cin_total <= 4, stride 1: thread = (filter row r, input channel ci, 8 output channels) ---
+// holds KW x 8 fp32 accumulators; per pixel: one 16-byte load of dy, KW scalar loads of x.
+template <typename T, int KW>
+__global__ void __launch_bounds__(256) thin_in_wgrad_row_kernel(HmConvDesc d, const T* __restrict__ x1,
+                                                                const T* __restrict__ x2, const T* __restrict__ dy,
+                                                                float* dw, int rows_per_block) {
+  const int Ct = d.C1 + d.C2, groups = d.Cout >> 3;
+  const int units = d.kh * Ct * groups;
+  const int lanes = blockDim.x / units;
+  const int u = threadIdx.x % units, pl = threadIdx.x / units;
+  if (pl >= lanes) return;
+  const int g = u % groups;
+  const int ci = (u / groups) % Ct;
+  const int r = u / (groups * Ct);
+  const T* src = ci < d.C1 ? x1 : x2;
+  const int C = ci < d.C1 ? d.C1 : d.C2;
+  const int cc = ci < d.C1 ? ci : ci - d.C1;
+  float acc[KW][8];
+#pragma unroll
+  for (int s = 0; s < KW; s++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[s][j] = 0.f;
+  const int total_rows = d.B * d.Ho;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(total_rows, row0 + rows_per_block);
+  for (int row = row0; row < row1; row++) {
+    const int n = row / d.Ho, oy = row - n * d.Ho;
+    const int iy = oy - d.pad + r;
+    if (iy < 0 || iy >= d.H) continue;
+    const T* xrow = src + ((size_t)n * d.H + iy) * d.W * C + cc;
+    const T* grow = dy + (size_t)row * d.Wo * d.Cout + g * 8;
+    for (int ox = pl; ox < d.Wo; ox += lanes) {
+      float g8[8];
+      load8(grow + (size_t)ox * d.Cout, g8);
+#pragma unroll
+      for (int s = 0; s < KW; s++) {
+        const int ix = ox - d.pad + s;
+        const float xv = (ix >= 0 && ix < d.W) ? ldf(xrow + (size_t)ix * C) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[s][j] = fmaf(xv, g8[j], acc[s][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < KW; s++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      atomicAdd(dw + (size_t)((r * KW + s) * Ct + ci) * d.Cout + g * 8 + j, acc[s][j]);
+}
+
 // ---- weight gradient, Cout <= 4 -------------------------------------------------------------------------------
 // thread = (tap, ci8); x may be read through the virtual nearest/bilinear 2x upsampling.
 template <typename T>
@@ -228,6 +317,20 @@ bool thin_in_conv_launch(const HmConvDesc* d, const void* x1, const void* x2, co
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)d->kh * d->kw * Ct * d->Cout * sizeof(float);
+  if (Ct == 1 && d->stride == 1 && d->kh == d->kw && (d->kh == 5 || d->kh == 3)) {
+    const long long tot4 = (long long)d->B * d->Ho * ((d->Wo + 3) / 4) * (d->Cout / 8);
+    long long b4 = (tot4 + 255) / 256;
+    if (b4 > cap) b4 = cap;
+#define LAUNCH_C1(TT, KK)                                                                                  \
+  thin_in_conv_c1_kernel<TT, KK, KK><<<(unsigned)b4, 256, smem, st>>>(*d, (const TT*)x1, (const TT*)w, bias, (TT*)y)
+    if (d->dtype == HM_F32) {
+      if (d->kh == 5) LAUNCH_C1(float, 5); else LAUNCH_C1(float, 3);
+    } else {
+      if (d->kh == 5) LAUNCH_C1(__half, 5); else LAUNCH_C1(__half, 3);
+    }
+#undef LAUNCH_C1
+    return true;
+  }
   if (d->dtype == HM_F32)
     thin_in_conv_kernel<float><<<(unsigned)blocks, 256, smem, st>>>(*d, (const float*)x1, (const float*)x2,
                                                                     (const float*)w, bias, (float*)y);
@@ -244,6 +347,23 @@ bool thin_wgrad_launch(const HmConvDesc* d, const void* x1, const void* x2, cons
   if (d->transposed) return false;
   if (Ct <= 4 && !d->up && d->os == 1 && d->Cout % 8 == 0 && d->kh * d->kw * (d->Cout / 8) <= 256 &&
       ((uintptr_t)dy & 15) == 0) {
+    const int runits = d->kh * Ct * (d->Cout / 8);
+    if (d->stride == 1 && runits <= 256 && (d->kw == 5 || d->kw == 3)) {
+      const int total_rows = d->B * d->Ho;
+      int blocks = num_sms() * 4;
+      int rpb = (total_rows + blocks - 1) / blocks;
+      if (rpb < 1) rpb = 1;
+      blocks = (total_rows + rpb - 1) / rpb;
+#define LAUNCH_ROW(TT, KK)                                                                                   \
+  thin_in_wgrad_row_kernel<TT, KK><<<blocks, 256, 0, st>>>(*d, (const TT*)x1, (const TT*)x2, (const TT*)dy, dw, rpb)
+      if (d->dtype == HM_F32) {
+        if (d->kw == 5) LAUNCH_ROW(float, 5); else LAUNCH_ROW(float, 3);
+      } else {
+        if (d->kw == 5) LAUNCH_ROW(__half, 5); else LAUNCH_ROW(__half, 3);
+      }
+#undef LAUNCH_ROW
+      return true;
+    }
     const int units = d->kh * d->kw * (d->Cout / 8);
     const int lanes = 256 / units;
     long long blocks = (long long)num_sms() * 4;
