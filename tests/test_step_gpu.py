@@ -69,7 +69,7 @@ def test_full_width_dcgan_forward_and_losses_parity():
 def test_fast_mode_tracks_parity_mode():
     """fp16 storage / fp32 accumulate against the float32 oracle on the 64-px gate over three training steps
     (the two trajectories drift apart slowly): losses within 5e-2 relative (2e-3 absolute for the small
-    generator loss), G(z) within 1e-2 absolute (values in (0,1))."""
+    generator loss), G(z) within 2e-2 absolute (values in (0,1))."""
     cfg = S.experiment_kwargs('gate64')
     om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast")
     for it in range(3):
@@ -79,7 +79,7 @@ def test_fast_mode_tracks_parity_mode():
         assert np.all(np.isfinite(lm))
         np.testing.assert_allclose(lm[:2], lo[:2], rtol=5e-2, atol=2e-3)
     Z = np.random.RandomState(5).rand(4, cfg['latent_dim']).astype(np.float32)
-    np.testing.assert_allclose(m.z_fn_det(Z), om.z_fn_det(Z), atol=1e-2)
+    np.testing.assert_allclose(m.z_fn_det(Z), om.z_fn_det(Z), atol=2e-2)
 
 
 def test_p2p_mode_leaves_dcgan_untouched_and_device_api_matches_host_api():

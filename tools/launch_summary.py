@@ -1,0 +1,37 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel family and the
+slowest individual launches.  usage: python tools/launch_summary.py gpurun_out/launches.csv [min_ms]"""
+import collections
+import csv
+import re
+import sys
+
+
+def main(path, min_ms=1.0):
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith('==')]
+    r = csv.reader(lines)
+    hdr = next(r)
+    ki, vi, ui, gi = (hdr.index(k) for k in ('Kernel Name', 'Metric Value', 'Metric Unit', 'Grid Size'))
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    tot, big = 0.0, []
+    for row in r:
+        if len(row) <= vi:
+            continue
+        v = float(row[vi].replace(',', ''))
+        v = v / 1e6 if row[ui] in ('nsecond', 'ns') else (v / 1e3 if row[ui] in ('usecond', 'us') else v)
+        name = re.sub(r'\(.*', '', row[ki]).replace('void ', '')
+        agg[name][0] += 1
+        agg[name][1] += v
+        tot += v
+        if v >= min_ms:
+            big.append((v, row[gi], name))
+    print('total %.2f ms over %d launches' % (tot, sum(n for n, _ in agg.values())))
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:20]:
+        print('%8.2f ms %5.1f%% n=%4d  %s' % (t, 100 * t / tot, n, k))
+    print('launches >= %.1f ms:' % min_ms)
+    for b in big:
+        print('  %8.2f ms  grid=%-16s %s' % b)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 1.0)
