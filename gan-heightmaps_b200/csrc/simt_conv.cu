@@ -278,6 +278,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     int tap = (int)(k / cout);
     int r = tap / kw, s = tap % kw;
     val = w[(((size_t)co * cin + ci) * kh + r) * kw + s];
+  } else if (mode == 8) {
+    // nearest-2x upsampling + 5x5 'same' convolution == four 3x3 'same' convolutions on the LOW-RES tensor, one per
+    // output phase (oy&1, ox&1):  Wt[(dy*3+dx)][phase*cout+co][ci] = sum_{r in R(py,dy), s in R(px,dx)} W[co][ci][4-r][4-s]
+    // with R(p,d) = { r in 0..4 : floor((p + r - 2) / 2) == d - 1 }   (K-major tcgen05 pack)
+    int ci = (int)(i % cin);
+    long long k = i / cin;
+    int nn = (int)(k % (4 * cout));
+    int tap = (int)(k / (4 * cout));
+    int ph = nn / cout, co = nn - ph * cout;
+    int py = ph >> 1, px = ph & 1, dy_ = tap / 3 - 1, dx_ = tap % 3 - 1;
+    val = 0.f;
+    for (int r = 0; r < 5; r++) {
+      if (((py + r - 2 + 4) >> 1) - 2 != dy_) continue;
+      for (int s = 0; s < 5; s++) {
+        if (((px + s - 2 + 4) >> 1) - 2 != dx_) continue;
+        val += w[(((size_t)co * cin + ci) * 5 + (4 - r)) * 5 + (4 - s)];
+      }
+    }
   } else {
     val = w[i];
   }
@@ -307,6 +325,26 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
     int ci = (int)(t / cout);
     int u = kh - 1 - a, v = kw - 1 - b;
     dw[i] = dwp[((size_t)(u * kw + v) * cin + ci) * cout + co];
+  } else if (mode == 8 || mode == 9) {
+    // fold the gradients of the four 3x3 phase filters back onto the 5x5 master filter (adjoint of pack mode 8).
+    // mode 8: dwp[(tap3, ci)][(phase, co)]   (tcgen05 weight-gradient layout)
+    // mode 9: dwp[phase][(tap3, ci)][co]     (one thin weight-gradient launch per phase)
+    int b = (int)(i % 5);
+    long long t = i / 5;
+    int a = (int)(t % 5);
+    t /= 5;
+    int ci = (int)(t % cin);
+    int co = (int)(t / cin);
+    int r = 4 - a, s = 4 - b;
+    float acc = 0.f;
+    for (int py = 0; py < 2; py++)
+      for (int px = 0; px < 2; px++) {
+        int dy_ = ((py + r - 2 + 4) >> 1) - 2 + 1, dx_ = ((px + s - 2 + 4) >> 1) - 2 + 1;   // 0..2
+        int tap = dy_ * 3 + dx_, ph = py * 2 + px;
+        acc += mode == 8 ? dwp[((size_t)(tap * cin + ci) * 4 + ph) * cout + co]
+                         : dwp[((size_t)ph * 9 * cin + tap * cin + ci) * cout + co];
+      }
+    dw[i] = acc;
   } else {
     dw[i] = dwp[i];
   }
@@ -389,8 +427,10 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG(mode >= 0 && mode <= 7, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode >= 0 && mode <= 8, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
   long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
+  if (mode == 8) n = 36LL * cout * cin;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)
@@ -404,7 +444,8 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
 extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int cout, int cin, int kh,
                                     int kw, void* stream) {
   HM_CHECK_ARG(dwp && dw, "hm_unpack_conv_wgrad: null pointer");
-  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4, "hm_unpack_conv_wgrad: bad mode %d", mode);
+  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9) && kh == 5 && kw == 5),
+               "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;
   unpack_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dwp, dw, mode, cout,
                                                                                      cin, kh, kw, n);

@@ -43,6 +43,9 @@ struct TcParams {
   __half* y2;              // [B,Ho,Wo,Cout-split]  channels [split,Cout)   (concat sources of an input gradient)
   int split, accumulate;   // accumulate bit0: y += , bit1: y2 +=
   int vec_store;           // 1: 16-byte stores (Cout, split multiples of 8); 0: scalar stores of the real columns
+  int d2s;                 // 1: nearest-2x + 5x5 as four 3x3 phase convolutions: N = (phase, co), the epilogue scatters
+                           //    phase (py,px) of low-res pixel (qy,qx) to output pixel (2qy+py, 2qx+px)
+  int cph;                 // channels per phase (= real Cout) when d2s
 };
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -274,6 +277,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       __half* dst = second ? p.y2 + pix * (p.Cout - p.split) + (col0 - p.split) : p.y + pix * p.split + col0;
       const bool accum = (p.accumulate & (second ? 2 : 1)) != 0;
       const bool store = valid && (second ? p.y2 != nullptr : p.y != nullptr);
+      if (p.d2s) {
+        // ---- depth-to-space epilogue ----
+        for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+          uint32_t v[32];
+          if (p.ntile - c0 >= 32) {
+            tmem_ld32(taddr + c0, v);
+          } else {
+            tmem_ld16(taddr + c0, v);
+#pragma unroll
+            for (int j = 16; j < 32; j++) v[j] = 0;
+          }
+          tmem_ld_wait();
+          if (!valid) continue;
+          const int gc = col0 + c0;                            // global column of v[0]
+          if (p.cph % 32 == 0) {                               // the 32 columns lie inside one phase
+            const int ph = gc / p.cph, co = gc - ph * p.cph;
+            if (ph < 4) {
+              const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+              uint32_t packed[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+                if (p.bias) {
+                  a += __ldg(p.bias + co + j);
+                  b += __ldg(p.bias + co + j + 1);
+                }
+                __half2 h = __floats2half2_rn(act_fwd(a, p.act, p.slope), act_fwd(b, p.act, p.slope));
+                packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint4* d4 = reinterpret_cast<uint4*>(p.y + op * p.cph + co);
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+          } else {                                             // thin outputs (cph < 32): column by column
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int col = gc + j;
+              if (col < 4 * p.cph) {
+                const int ph = col / p.cph, co = col - ph * p.cph;
+                const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+                float a = __uint_as_float(v[j]);
+                if (p.bias) a += __ldg(p.bias + co);
+                p.y[op * p.cph + co] = __float2half_rn(act_fwd(a, p.act, p.slope));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       for (int c0 = 0; c0 < p.ntile; c0 += 32) {
         uint32_t v[32];
         if (p.ntile - c0 >= 32) {
@@ -407,8 +463,18 @@ static int pick_ntile(int Cout, int split) {
 
 using namespace hm;
 
+// nearest-2x upsampling feeding a 5x5 'same' stride-1 convolution: evaluated as four 3x3 convolutions on the
+// low-resolution source (pack mode 8), never materialising the upsampled tensor
+static bool is_up2conv(const HmConvDesc* d) {
+  return d->up == HM_UP_NEAREST2 && d->kh == 5 && d->kw == 5 && d->pad == 2 && d->stride == 1 && !d->transposed &&
+         d->C2 == 0 && d->Ho == 2 * d->H && d->Wo == 2 * d->W && d->split == d->Cout && !d->accumulate &&
+         (d->Cout % 32 == 0 || d->Cout <= 4);
+}
+
 extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   if (!d) return 0;
+  if (d->dtype == HM_F16 && is_up2conv(d))
+    return d->C1 % KCH == 0 && d->C1 > 0 && d->os == 1 && !d->ou && !d->ov && d->oH == d->Ho && d->oW == d->Wo;
   if (d->dtype != HM_F16 || d->transposed || d->up || d->stride != 1) return 0;
   if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
   if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
@@ -432,36 +498,39 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     return HM_ERR_CUDA;
   }
   if ((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc) & 15) ||
-      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15))) {
+      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15)) || (is_up2conv(d) && !y)) {
     set_error("hm_tc_conv: pointers must be 16-byte aligned");
     return HM_ERR_ALIGN;
   }
   TcParams p;
-  p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
-  p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = d->Cout;
-  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
-  p.bw = pow2_floor(d->Wo < TILE_M ? d->Wo : TILE_M);
-  p.bh = pow2_floor(d->Ho < TILE_M / p.bw ? d->Ho : TILE_M / p.bw);
+  const bool up2 = is_up2conv(d);
+  p.d2s = up2 ? 1 : 0;
+  p.cph = d->Cout;
+  p.B = d->B; p.Ho = up2 ? d->H : d->Ho; p.Wo = up2 ? d->W : d->Wo;       // tile grid (low-res when phase-decomposed)
+  p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = up2 ? 4 * d->Cout : d->Cout;
+  p.kh = up2 ? 3 : d->kh; p.kw = up2 ? 3 : d->kw; p.pad = up2 ? 1 : d->pad;
+  p.bw = pow2_floor(p.Wo < TILE_M ? p.Wo : TILE_M);
+  p.bh = pow2_floor(p.Ho < TILE_M / p.bw ? p.Ho : TILE_M / p.bw);
   p.bn = TILE_M / (p.bw * p.bh);
-  p.tiles_x = (d->Wo + p.bw - 1) / p.bw;
-  p.tiles_y = (d->Ho + p.bh - 1) / p.bh;
+  p.tiles_x = (p.Wo + p.bw - 1) / p.bw;
+  p.tiles_y = (p.Ho + p.bh - 1) / p.bh;
   p.tiles_n = (d->B + p.bn - 1) / p.bn;
   p.n_mtiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.ntile = pick_ntile(d->Cout, d->split);
-  p.n_ntiles = (d->Cout + p.ntile - 1) / p.ntile;
-  p.vec_store = (d->Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
+  p.ntile = pick_ntile(p.Cout, up2 ? p.Cout : d->split);
+  p.n_ntiles = (p.Cout + p.ntile - 1) / p.ntile;
+  p.vec_store = (p.Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
   const int stage_bytes = A_BYTES + p.ntile * 128;
   int stages = (227 * 1024 - 4096) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y; p.y2 = (__half*)y2;
-  p.split = d->split; p.accumulate = d->accumulate;
+  p.split = up2 ? p.Cout : d->split; p.accumulate = d->accumulate;
 
   CUtensorMap tmA, tmA2, tmB;
   int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn);
   if (!rc) rc = d->C2 ? encode_act(&tmA2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn) : 0;
   if (!d->C2) tmA2 = tmA;
-  if (!rc) rc = encode_wgt(&tmB, w_tc, d->kh * d->kw, d->Cout, p.Cin, p.ntile);
+  if (!rc) rc = encode_wgt(&tmB, w_tc, p.kh * p.kw, p.Cout, p.Cin, p.ntile);
   if (rc) {
     set_error("hm_tc_conv: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
     return HM_ERR_CUDA;

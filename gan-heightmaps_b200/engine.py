@@ -150,8 +150,11 @@ class ConvOp(object):
         self.tc_fwd = self.tc_dg = self.tc_wg = False
         self.wt_f = self.wt_d = self.x1u = self.x2u = None
         rt = net.rt
+        self.up2 = False      # nearest-2x + 5x5 evaluated as four 3x3 phase convolutions on the low-res source
         if rt.precision == "fast" and kind == "conv" and self.stride == 1:
-            self.tc_fwd = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_fwd_desc(rt, 1))))
+            if self.up == _lib.UP_NEAREST2 and self.x2 is None:
+                self.up2 = bool(_lib.query("hm_tc_conv_supported", C.byref(self._fwd_desc(rt, 1))))
+            self.tc_fwd = self.up2 or bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
         self.path = "tcgen05" if self.tc_fwd else "simt"
@@ -170,10 +173,13 @@ class ConvOp(object):
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
         n = self.K * self.Cout
         if self.tc_fwd and self.wt_f is None:
-            self.wt_f = rt.empty((n,))
+            self.wt_f = rt.empty((36 * self.Cin * self.Cout if self.up2 else n,))
         if self.tc_dg and self.wt_d is None:
             self.wt_d = rt.empty((n,))
-        if self.up and (self.tc_fwd or self.tc_wg):
+        self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient: one thin launch per phase
+        if self.thin_up2_wg and (self.dwp is None or self.dwp.numel() < 36 * self.Cin * self.Cout):
+            self.dwp = rt.empty((36 * self.Cin * self.Cout,), torch.float32)
+        if self.up and ((self.tc_fwd and not self.up2) or (self.tc_wg and not self.thin_up2_wg)):
             # the tensor-core kernels read dense NHWC tiles through TMA: materialise the 2x resampling once
             self.x1u = rt.empty((B, self.Hv, self.Wv, self.C1))
             self.x2u = rt.empty((B, self.Hv, self.Wv, self.C2)) if self.x2 is not None else None
@@ -188,8 +194,8 @@ class ConvOp(object):
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
             else:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 5, self.Cout, self.Cin, self.kh, self.kw,
-                        0, 0, rt.cd)
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 8 if self.up2 else 5, self.Cout, self.Cin,
+                        self.kh, self.kw, 0, 0, rt.cd)
             if not self.tc_dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 7 if self.fw_dg else 1, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
@@ -290,8 +296,13 @@ class ConvOp(object):
                     d = self._fwd_desc(rt, n, (u, v))
                     rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f[(u * self.kw + v) * per:]),
                             bias, y, None)
+        elif self.up2:
+            self._xu_valid = False
+            d = self._fwd_desc(rt, n)
+            rt.call("hm_tc_conv", C.byref(d), x1, None, _ptr(self.wt_f), bias, y, None)
         elif self.tc_fwd:
             if self.up:
+                self._xu_valid = True
                 for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
                     if x is not None:
                         rt.call("hm_upsample2_fwd", _ptr(x.b(lo, hi)), _ptr(xu[lo:hi]), rt.cd, n, x.shape[0],
@@ -321,12 +332,24 @@ class ConvOp(object):
                         rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
                                 _ptr(self.dwp[(u * self.kw + v) * per:]))
                 mode = 2
+            elif self.thin_up2_wg:
+                # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
+                # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)
+                per = 9 * self.Cin * self.Cout
+                for ph in range(4):
+                    d = self._fwd_desc(rt, n)
+                    d.up, d.kh, d.kw, d.pad = 0, 3, 3, 1
+                    d.Ho, d.Wo = self.x1.shape[0], self.x1.shape[1]
+                    d.os, d.ou, d.ov = 2, ph >> 1, ph & 1
+                    rt.call("hm_conv_wgrad", C.byref(d), x1, None, _ptr(g), _ptr(self.dwp[ph * per:]))
+                mode = 9
             elif self.tc_wg and (not self.up or self.x1u is not None):
-                if self.up and not self.tc_fwd:        # forward ran on the gather kernel: materialise now
+                if self.up and not getattr(self, "_xu_valid", False):   # forward did not materialise the 2x copy
                     for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
                         if x is not None:
                             rt.call("hm_upsample2_fwd", _ptr(x.b(lo, hi)), _ptr(xu[lo:hi]), rt.cd, n, x.shape[0],
                                     x.shape[1], c, self.up)
+                    self._xu_valid = True
                 u1, u2 = self._srcs(rt, lo, hi, True)
                 d = self._tc_fwd_desc(rt, n)
                 rt.call("hm_tc_wgrad", C.byref(d), u1, u2, _ptr(g), _ptr(self.dwp))

@@ -155,6 +155,15 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
     elif mode == 5:
         src = W.reshape(cout, cin, kh, kw)[:, :, ::-1, ::-1]
         out = src.transpose(2, 3, 0, 1)                      # [r][s][co][ci]
+    elif mode == 8:
+        Wc = W.reshape(cout, cin, 5, 5)[:, :, ::-1, ::-1]                    # Wc[co][ci][r][s] (correlation taps)
+        out = np.zeros((3, 3, 4, cout, cin), np.float32)
+        for py in range(2):
+            for px in range(2):
+                for r in range(5):
+                    for s_ in range(5):
+                        dy_, dx_ = (py + r - 2) // 2 + 1, (px + s_ - 2) // 2 + 1
+                        out[dy_, dx_, py * 2 + px] += Wc[:, :, r, s_]
     elif mode == 7:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
@@ -170,6 +179,19 @@ def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
     n = cout * cin * kh * kw
     src = _a(dwp, n, np.float32)
     dst = _a(dw, n, np.float32)
+    if mode in (8, 9):
+        if mode == 8:
+            g3 = _a(dwp, 36 * cin * cout, np.float32).reshape(3, 3, cin, 4, cout)
+        else:
+            g3 = _a(dwp, 36 * cin * cout, np.float32).reshape(4, 3, 3, cin, cout).transpose(1, 2, 3, 0, 4)
+        gc = np.zeros((5, 5, cin, cout), np.float32)
+        for py in range(2):
+            for px in range(2):
+                for r in range(5):
+                    for s_ in range(5):
+                        gc[r, s_] += g3[(py + r - 2) // 2 + 1, (px + s_ - 2) // 2 + 1, :, py * 2 + px, :]
+        dst[:] = np.ascontiguousarray(gc.transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]).reshape(-1)
+        return 0
     if mode == 0:
         g = src.reshape(kh, kw, cin, cout).transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]
     elif mode == 2:
@@ -415,7 +437,15 @@ def hm_adam(p, g, m, v, n, lr, b1, b2, eps, t, gscale, stream=None):
     return 0
 
 
+def _is_up2conv(d):
+    return (d.up == 1 and d.kh == 5 and d.kw == 5 and d.pad == 2 and d.stride == 1 and not d.transposed and
+            d.C2 == 0 and d.Ho == 2 * d.H and d.Wo == 2 * d.W and d.split == d.Cout and not d.accumulate and
+            (d.Cout % 32 == 0 or d.Cout <= 4))
+
+
 def _tc_ok(d, wgrad):
+    if not wgrad and d.dtype == F16 and _is_up2conv(d):
+        return d.C1 % 64 == 0 and d.C1 > 0 and d.os == 1 and not d.ou and not d.ov and d.oH == d.Ho and d.oW == d.Wo
     ok = d.dtype == F16 and not d.transposed and not d.up and d.stride == 1 and d.os == 1 and not d.ou and not d.ov
     ok = ok and d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0
     ok = ok and d.Ho == d.H + 2 * d.pad - d.kh + 1 and d.Wo == d.W + 2 * d.pad - d.kw + 1
@@ -432,6 +462,18 @@ def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
     """Same contract as hm_conv_gather, weights in the K-major pack [tap][Cout][Cin]."""
     d = dp._obj if hasattr(dp, "_obj") else dp
     assert _tc_ok(d, False)
+    if _is_up2conv(d):
+        # four 3x3 phase convolutions on the low-res source with the mode-8 pack, then depth-to-space
+        B, H, W, Ci, Co = d.B, d.H, d.W, d.C1, d.Cout
+        a = _t(_a(x1, B * H * W * Ci, np.float16)).reshape(B, H, W, Ci).permute(0, 3, 1, 2)
+        wt = _t(_a(w_tc, 36 * Co * Ci, np.float16)).reshape(3, 3, 4 * Co, Ci)
+        out = F.conv2d(a, wt.permute(2, 3, 0, 1).contiguous(), padding=1)          # [B,4Co,H,W]
+        out = out.reshape(B, 2, 2, Co, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B, 2 * H, 2 * W, Co)
+        if bias:
+            out = out + _t(_a(bias, Co, np.float32))
+        out = _act(out, d.act, d.slope)
+        _a(y, B * 4 * H * W * Co, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+        return 0
     Ct = d.C1 + d.C2
     wt = _a(w_tc, d.kh * d.kw * Ct * d.Cout, np.float16).reshape(d.kh * d.kw, d.Cout, Ct)
     wk = np.ascontiguousarray(wt.transpose(0, 2, 1))           # [tap][ci][co] = the gather kernel's pack

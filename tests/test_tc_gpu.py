@@ -22,3 +22,11 @@ def test_tc_conv_matches_simt(case):
 def test_tc_wgrad_matches_simt(case):
     rel, line = tc_probe.run_wgrad_case(*case)
     assert rel <= 3e-3, line
+
+
+@pytest.mark.parametrize("case", tc_probe.UP2_CASES, ids=[c[0] for c in tc_probe.UP2_CASES])
+def test_tc_up2conv_matches_simt_gather(case):
+    """nearest-2x upsampling + 5x5 convolution evaluated as four 3x3 phase convolutions on the low-res tensor
+    (summed fp16 phase filters) against the gather through the virtual upsampling: 5e-3 of the output scale."""
+    rel, line = tc_probe.run_up2_case(*case)
+    assert rel <= 5e-3, line

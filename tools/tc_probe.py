@@ -75,6 +75,51 @@ def run_case(name, B, H, W, C1, C2, Cout, k, pad, act, verbose=True):
     return float(err.max()) / scale, line
 
 
+UP2_CASES = [
+    # name, B, H(low), W(low), Cin, Cout, act
+    ("up2_64_64_w16", 2, 16, 16, 64, 64, 1),
+    ("up2_128_64_w64", 1, 32, 64, 128, 64, 0),
+    ("up2_64_128_w128", 1, 8, 128, 64, 128, 1),
+    ("up2_64_256_w8", 3, 8, 8, 64, 256, 1),
+    ("up2_64_32_w16", 2, 16, 16, 64, 32, 2),
+    ("up2_64_1_thin", 2, 32, 32, 64, 1, 3),
+    ("up2_128_3_thin", 1, 16, 16, 128, 3, 4),
+    ("up2_512_256_4x4", 4, 4, 4, 512, 256, 1),
+]
+
+
+def run_up2_case(name, B, H, W, Ci, Co, act):
+    """nearest-2x + 5x5 'same': tcgen05 phase-decomposed path vs the SIMT gather through the virtual upsampling."""
+    torch.manual_seed(abs(hash(name)) % 1000 + 11)
+    x = torch.randn(B, H, W, Ci, device="cuda").half()
+    Wm = torch.randn(Co, Ci, 5, 5, device="cuda") / np.sqrt(25 * Ci)
+    bias = torch.randn(Co, device="cuda")
+    wp = torch.empty(25 * Ci * Co, device="cuda", dtype=torch.float16)
+    w8 = torch.empty(36 * Ci * Co, device="cuda", dtype=torch.float16)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wp.data_ptr(), 0, Co, Ci, 5, 5, 0, 0, 1, None)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), w8.data_ptr(), 8, Co, Ci, 5, 5, 0, 0, 1, None)
+    d = desc(dtype=1, B=B, H=H, W=W, C1=Ci, C2=0, up=1, kh=5, kw=5, stride=1, pad=2, transposed=0, Ho=2 * H, Wo=2 * W,
+             Cout=Co, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Co, act=act, slope=0.2, accumulate=0)
+    y_ref = torch.zeros(B, 2 * H, 2 * W, Co, device="cuda", dtype=torch.float16)
+    y_tc = torch.full((B, 2 * H, 2 * W, Co), 7.0, device="cuda", dtype=torch.float16)
+    _lib.call("hm_conv_gather", C.byref(d), x.data_ptr(), None, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None,
+              None)
+    _lib.call("hm_tc_conv", C.byref(d), x.data_ptr(), None, w8.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
+    torch.cuda.synchronize()
+    a, b = y_tc.float(), y_ref.float()
+    err = (a - b).abs()
+    scale = float(b.abs().max())
+    line = "up2 %-24s max_err %.4g  scale %.4g  rel %.3g  frac_bad %.4f  untouched %.4f" % (
+        name, float(err.max()), scale, float(err.max()) / scale, float((err > 2e-2 * scale).float().mean()),
+        float((a == 7.0).float().mean()))
+    if float(err.max()) > 5e-3 * scale:
+        bad = (err > 2e-2 * scale)
+        line += "\n    bad by (oy&1, ox&1): %s" % [[round(float(bad[:, py::2, px::2].float().mean()), 3) for px in range(2)]
+                                                    for py in range(2)]
+        line += "\n    bad by channel%%8: %s" % [round(float(bad[..., c::8].float().mean()), 3) for c in range(min(8, Co))]
+    return float(err.max()) / scale, line
+
+
 WGRAD_CASES = [c for c in CASES if c[6] % 64 == 0 and c[6] <= 256]
 
 
@@ -142,6 +187,14 @@ def perf():
 if __name__ == "__main__":
     if sys.argv[1:] == ["perf"]:
         perf()
+        sys.exit(0)
+    if sys.argv[1:] == ["up2"]:
+        for c in UP2_CASES:
+            try:
+                print(run_up2_case(*c)[1], flush=True)
+            except Exception as e:
+                print("up2 %-24s EXC %s" % (c[0], e), flush=True)
+                break
         sys.exit(0)
     if sys.argv[1:] == ["wgrad"]:
         for c in WGRAD_CASES:
