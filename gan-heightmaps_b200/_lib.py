@@ -40,6 +40,7 @@ _PROTOS = {
     "hm_conv_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_conv": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
+    "hm_up2conv_wgrad_phases": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
     "hm_pack_conv_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_unpack_conv_wgrad": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_bn_stats": ([_P, _I, _LL, _I, _P, _P], C.c_int),

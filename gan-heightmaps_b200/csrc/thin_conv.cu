@@ -206,16 +206,29 @@ __global__ void __launch_bounds__(256) thin_in_wgrad_row_kernel(HmConvDesc d, co
     if (iy < 0 || iy >= d.H) continue;
     const T* xrow = src + ((size_t)n * d.H + iy) * d.W * C + cc;
     const T* grow = dy + (size_t)row * d.Wo * d.Cout + g * 8;
-    for (int ox = pl; ox < d.Wo; ox += lanes) {
-      float g8[8];
-      load8(grow + (size_t)ox * d.Cout, g8);
+    for (int ox0 = pl * 4; ox0 < d.Wo; ox0 += lanes * 4) {     // 4 consecutive pixels per iteration
+      float xv[KW + 3];
 #pragma unroll
-      for (int s = 0; s < KW; s++) {
-        const int ix = ox - d.pad + s;
-        const float xv = (ix >= 0 && ix < d.W) ? ldf(xrow + (size_t)ix * C) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc[s][j] = fmaf(xv, g8[j], acc[s][j]);
+      for (int q = 0; q < KW + 3; q++) {
+        const int ix = ox0 - d.pad + q;
+        xv[q] = (ix >= 0 && ix < d.W) ? ldf(xrow + (size_t)ix * C) : 0.f;
       }
+      float g8[4][8];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        if (ox0 + p < d.Wo) {
+          load8(grow + (size_t)(ox0 + p) * d.Cout, g8[p]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) g8[p][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < KW; s++)
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[s][j] = fmaf(xv[p + s], g8[p][j], acc[s][j]);
     }
   }
 #pragma unroll
@@ -251,14 +264,25 @@ __device__ __forceinline__ void gather8(const HmConvDesc& d, const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) thin_out_wgrad_kernel(HmConvDesc d, const T* __restrict__ x1,
                                                              const T* __restrict__ x2, const T* __restrict__ dy,
-                                                             float* dw, long long per_block) {
+                                                             float* dw, int per_block, int phases) {
+  // blockIdx.y = output phase (oy&1, ox&1) when the gradient of a nearest-2x + 5x5 layer is taken as four 3x3
+  // problems on the low-res source (hm_up2conv_wgrad_phases); 0 otherwise.
+  if (phases) {
+    d.ou = blockIdx.y >> 1;
+    d.ov = blockIdx.y & 1;
+  }
   const int Ct = d.C1 + d.C2, taps = d.kh * d.kw, cg = Ct >> 3;
   const int units = taps * cg;
-  const long long M = (long long)d.B * d.Ho * d.Wo;
-  const long long p0 = (long long)blockIdx.x * per_block, p1 = min(M, p0 + per_block);
+  dw += (size_t)blockIdx.y * taps * Ct * d.Cout;
+  const int M = d.B * d.Ho * d.Wo;
+  const int p0 = blockIdx.x * per_block, p1 = min(M, p0 + per_block);
   const int sh = d.up ? 1 : 0;
   const int Hv = d.H << sh, Wv = d.W << sh;
-  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+  const int lanes = blockDim.x / units > 0 ? blockDim.x / units : 1;
+  for (int u0 = 0; u0 < units; u0 += blockDim.x) {          // one pass unless taps*Cin/8 > 256
+    const int u = u0 + (lanes > 1 ? threadIdx.x % units : threadIdx.x);
+    const int pl = lanes > 1 ? threadIdx.x / units : 0;
+    if (u >= units || pl >= lanes) continue;
     const int tap = u / cg, c0 = (u - tap * cg) * 8;
     const int r = tap / d.kw, s = tap - r * d.kw;
     const T* src = c0 < d.C1 ? x1 : x2;
@@ -269,11 +293,11 @@ __global__ void __launch_bounds__(256) thin_out_wgrad_kernel(HmConvDesc d, const
     for (int c = 0; c < 4; c++)
 #pragma unroll
       for (int j = 0; j < 8; j++) acc[c][j] = 0.f;
-    int ox = (int)(p0 % d.Wo);
-    long long t2 = p0 / d.Wo;
-    int oy = (int)(t2 % d.Ho);
-    int n = (int)(t2 / d.Ho);
-    for (long long pix = p0; pix < p1; pix++) {
+    for (int pix = p0 + pl; pix < p1; pix += lanes) {
+      const int ox = pix % d.Wo;
+      const int t2 = pix / d.Wo;
+      const int oy = t2 % d.Ho;
+      const int n = t2 / d.Ho;
       const int iy = oy * d.stride - d.pad + r, ix = ox * d.stride - d.pad + s;
       if (iy >= 0 && iy < Hv && ix >= 0 && ix < Wv) {
         float xv[8];
@@ -286,13 +310,6 @@ __global__ void __launch_bounds__(256) thin_out_wgrad_kernel(HmConvDesc d, const
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[co][j] = fmaf(xv[j], g, acc[co][j]);
           }
-      }
-      if (++ox == d.Wo) {
-        ox = 0;
-        if (++oy == d.Ho) {
-          oy = 0;
-          ++n;
-        }
       }
     }
 #pragma unroll
@@ -340,6 +357,22 @@ bool thin_in_conv_launch(const HmConvDesc* d, const void* x1, const void* x2, co
   return true;
 }
 
+void thin_out_wgrad_go(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw,
+                              cudaStream_t st, int phases) {
+  const long long M = (long long)d->B * d->Ho * d->Wo;
+  long long blocks = (long long)num_sms() * 4 / (phases ? 2 : 1);
+  long long per = (M + blocks - 1) / blocks;
+  if (per < 64) per = 64;
+  blocks = (M + per - 1) / per;
+  dim3 grid((unsigned)blocks, phases ? 4 : 1);
+  if (d->dtype == HM_F32)
+    thin_out_wgrad_kernel<float><<<grid, 256, 0, st>>>(*d, (const float*)x1, (const float*)x2, (const float*)dy, dw,
+                                                       (int)per, phases);
+  else
+    thin_out_wgrad_kernel<__half><<<grid, 256, 0, st>>>(*d, (const __half*)x1, (const __half*)x2, (const __half*)dy,
+                                                        dw, (int)per, phases);
+}
+
 bool thin_wgrad_launch(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw,
                        cudaStream_t st) {
   const int Ct = d->C1 + d->C2;
@@ -378,20 +411,33 @@ bool thin_wgrad_launch(const HmConvDesc* d, const void* x1, const void* x2, cons
                                                                      (const __half*)dy, dw, per);
     return true;
   }
-  if (d->Cout <= 4 && d->C1 % 8 == 0 && d->C2 % 8 == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)x2 & 15) == 0) {
-    long long blocks = (long long)num_sms() * 4;
-    long long per = (M + blocks - 1) / blocks;
-    if (per < 64) per = 64;
-    blocks = (M + per - 1) / per;
-    if (d->dtype == HM_F32)
-      thin_out_wgrad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(*d, (const float*)x1, (const float*)x2,
-                                                                     (const float*)dy, dw, per);
-    else
-      thin_out_wgrad_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(*d, (const __half*)x1, (const __half*)x2,
-                                                                      (const __half*)dy, dw, per);
+  if (d->Cout <= 4 && d->C1 % 8 == 0 && d->C2 % 8 == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)x2 & 15) == 0 &&
+      M < (1LL << 31)) {
+    thin_out_wgrad_go(d, x1, x2, dy, dw, st, 0);
     return true;
   }
   return false;
 }
 
 }  // namespace hm
+
+// Weight gradient of (nearest-2x upsampling -> 5x5 'same' convolution) with <= 4 output channels, as four 3x3
+// problems on the LOW-RES source: dw_phases[phase][(dy*3+dx)*Cin + ci][co] += sum_q x[q + (dy-1,dx-1)][ci] *
+// dy[2q + phase][co].  `d` is the layer's forward descriptor (up = HM_UP_NEAREST2, 5x5, pad 2); fold the result
+// onto the 5x5 filter with hm_unpack_conv_wgrad(mode 9).  fp32, atomically accumulated, caller zeroes.
+extern "C" int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, float* dw_phases,
+                                       void* stream) {
+  HM_CHECK_ARG(d && x && dy && dw_phases, "hm_up2conv_wgrad_phases: null argument");
+  HM_CHECK_ARG(d->up == HM_UP_NEAREST2 && d->kh == 5 && d->kw == 5 && d->pad == 2 && d->stride == 1 && !d->transposed &&
+                   d->C2 == 0 && d->Ho == 2 * d->H && d->Wo == 2 * d->W && d->oH == d->Ho && d->oW == d->Wo,
+               "hm_up2conv_wgrad_phases: descriptor is not a nearest-2x + 5x5 'same' convolution");
+  HM_CHECK_ARG(d->Cout >= 1 && d->Cout <= 4 && d->C1 % 8 == 0 && (((uintptr_t)x) & 15) == 0,
+               "hm_up2conv_wgrad_phases: needs Cout <= 4, Cin %% 8 == 0 and a 16-byte aligned source");
+  HmConvDesc q = *d;
+  q.up = 0; q.kh = q.kw = 3; q.pad = 1;
+  q.Ho = d->H; q.Wo = d->W;            // logical grid = low-res pixels; dy is read at (2q + phase)
+  q.os = 2; q.ou = 0; q.ov = 0;
+  hm::thin_out_wgrad_go(&q, x, nullptr, dy, dw_phases, (cudaStream_t)stream, 1);
+  HM_CHECK_LAUNCH("hm_up2conv_wgrad_phases");
+  return HM_OK;
+}

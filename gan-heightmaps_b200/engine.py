@@ -335,13 +335,8 @@ class ConvOp(object):
             elif self.thin_up2_wg:
                 # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
                 # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)
-                per = 9 * self.Cin * self.Cout
-                for ph in range(4):
-                    d = self._fwd_desc(rt, n)
-                    d.up, d.kh, d.kw, d.pad = 0, 3, 3, 1
-                    d.Ho, d.Wo = self.x1.shape[0], self.x1.shape[1]
-                    d.os, d.ou, d.ov = 2, ph >> 1, ph & 1
-                    rt.call("hm_conv_wgrad", C.byref(d), x1, None, _ptr(g), _ptr(self.dwp[ph * per:]))
+                d = self._fwd_desc(rt, n)
+                rt.call("hm_up2conv_wgrad_phases", C.byref(d), x1, _ptr(g), _ptr(self.dwp))
                 mode = 9
             elif self.tc_wg and (not self.up or self.x1u is not None):
                 if self.up and not getattr(self, "_xu_valid", False):   # forward did not materialise the 2x copy

@@ -122,6 +122,12 @@ int hm_tc_wgrad_supported(const HmConvDesc* d);
 int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw_packed,
                 void* stream);
 
+/* Weight gradient of (Upscale2DLayer(2) -> 5x5 'same' Conv2DLayer) with <= 4 output channels (the generator's last
+ * layer, dcgan.py:31-32) as four 3x3 problems on the low-res source; `d` is the layer's forward descriptor
+ * (up = HM_UP_NEAREST2).  dw_phases is fp32 [4][9*Cin][Cout], atomically accumulated (caller zeroes); fold onto the
+ * 5x5 filter with hm_unpack_conv_wgrad(mode 9). */
+int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, float* dw_phases, void* stream);
+
 /* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
  *  mode 0: Conv2DLayer W (Cout,Cin,kh,kw)      -> Wp[(r*kw+s)*Cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]   (forward)
  *  mode 1: Conv2DLayer W                       -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][kh-1-r][kw-1-s]  (input gradient)

@@ -486,6 +486,20 @@ def hm_tc_wgrad(dp, x1, x2, dy, dw, stream=None):
     return hm_conv_wgrad(dp, x1, x2, dy, dw)
 
 
+def hm_up2conv_wgrad_phases(dp, x, dy, dw, stream=None):
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    B, H, W, Ci, Co = d.B, d.H, d.W, d.C1, d.Cout
+    np_dt = _NP[d.dtype]
+    a = _t(_a(x, B * H * W * Ci, np_dt)).reshape(B, H, W, Ci).permute(0, 3, 1, 2)
+    cols = F.unfold(a, (3, 3), padding=1).reshape(B, Ci, 9, H * W).permute(0, 2, 1, 3).reshape(B, 9 * Ci, H * W)
+    g = _t(_a(dy, B * 4 * H * W * Co, np_dt)).reshape(B, 2 * H, 2 * W, Co)
+    out = _a(dw, 36 * Ci * Co, np.float32).reshape(4, 9 * Ci, Co)
+    for ph in range(4):
+        gp = g[:, (ph >> 1)::2, (ph & 1)::2, :].reshape(B, H * W, Co)
+        out[ph] += torch.einsum("bkl,blc->kc", cols.double(), gp.double()).float().numpy()
+    return 0
+
+
 _FUNCS = {k: v for k, v in globals().items() if k.startswith("hm_")}
 
 

@@ -318,3 +318,29 @@ def test_conv_adjoint_identity_at_full_layer_size(dtype):
     tol = 2e-3 if dtype else 1e-4
     scale = float(y.double().norm() * dy.double().norm())
     assert abs(a - b) <= tol * scale and abs(a - c) <= tol * scale, (a, b, c, scale)
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("Co", [1, 3])
+def test_up2conv_wgrad_phases_and_fold(Co, dtype):
+    """Phase-decomposed weight gradient of (nearest 2x -> 5x5) and its fold back onto the 5x5 filter (unpack mode 9)
+    equal the plain weight gradient through the virtual upsampling (hm_conv_wgrad + unpack mode 0)."""
+    r = np.random.RandomState(3 + Co)
+    B, H, W, Ci = 2, 12, 10, 16
+    d = desc(dtype=dtype, B=B, H=H, W=W, C1=Ci, up=1, kh=5, kw=5, pad=2, Ho=2 * H, Wo=2 * W, oH=2 * H, oW=2 * W,
+             Cout=Co, split=Co)
+    bo = Both()
+    x = bo.t(r.randn(B, H, W, Ci), TD[dtype])
+    dy = bo.t(r.randn(B, 2 * H, 2 * W, Co), TD[dtype])
+    ph = bo.t(np.zeros(36 * Ci * Co))
+    bo.run("hm_up2conv_wgrad_phases", lambda P: (C.byref(d), P(x), P(dy), P(ph)))
+    bo.check(ph, TOL[dtype], "phase gradients")
+    folded = bo.t(np.zeros(25 * Ci * Co))
+    bo.run("hm_unpack_conv_wgrad", lambda P: (P(ph), P(folded), 9, Co, Ci, 5, 5))
+    bo.check(folded, 1e-5, "fold")
+    plain = bo.t(np.zeros(25 * Ci * Co))
+    direct = bo.t(np.zeros(25 * Ci * Co))
+    bo.run("hm_conv_wgrad", lambda P: (C.byref(d), P(x), None, P(dy), P(plain)))
+    bo.run("hm_unpack_conv_wgrad", lambda P: (P(plain), P(direct), 0, Co, Ci, 5, 5))
+    a, b = bo.gpu[folded].cpu().double(), bo.gpu[direct].cpu().double()
+    assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max())
