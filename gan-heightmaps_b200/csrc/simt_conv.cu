@@ -296,6 +296,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
         val += w[(((size_t)co * cin + ci) * 5 + (4 - r)) * 5 + (4 - s)];
       }
     }
+  } else if (mode == 11) {
+    // one-channel-input convolution as a 1x1 convolution over the im2col tensor (hm_im2col_c1):
+    // Wt[co][t] = W[co][0][kh-1-r][kw-1-s] for tap t = r*kw+s < kh*kw, 0 up to 64   (K-major, K = 64)
+    int t = (int)(i % 64);
+    int co = (int)(i / 64);
+    int r = t / kw, s = t % kw;
+    val = t < kh * kw ? w[((size_t)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s)] : 0.f;
   } else {
     val = w[i];
   }
@@ -325,10 +332,11 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
     int ci = (int)(t / cout);
     int u = kh - 1 - a, v = kw - 1 - b;
     dw[i] = dwp[((size_t)(u * kw + v) * cin + ci) * cout + co];
-  } else if (mode == 8 || mode == 9) {
+  } else if (mode == 8 || mode == 9 || mode == 10) {
     // fold the gradients of the four 3x3 phase filters back onto the 5x5 master filter (adjoint of pack mode 8).
     // mode 8: dwp[(tap3, ci)][(phase, co)]   (tcgen05 weight-gradient layout)
     // mode 9: dwp[phase][(tap3, ci)][co]     (one thin weight-gradient launch per phase)
+    // mode 10: dwp[(tap3, ci)][64], column = phase*cout+co  (tcgen05 weight gradient against hm_s2d_pad64)
     int b = (int)(i % 5);
     long long t = i / 5;
     int a = (int)(t % 5);
@@ -341,8 +349,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
       for (int px = 0; px < 2; px++) {
         int dy_ = ((py + r - 2 + 4) >> 1) - 2 + 1, dx_ = ((px + s - 2 + 4) >> 1) - 2 + 1;   // 0..2
         int tap = dy_ * 3 + dx_, ph = py * 2 + px;
-        acc += mode == 8 ? dwp[((size_t)(tap * cin + ci) * 4 + ph) * cout + co]
-                         : dwp[((size_t)ph * 9 * cin + tap * cin + ci) * cout + co];
+        acc += mode == 8    ? dwp[((size_t)(tap * cin + ci) * 4 + ph) * cout + co]
+               : mode == 9 ? dwp[((size_t)ph * 9 * cin + tap * cin + ci) * cout + co]
+                           : dwp[(size_t)(tap * cin + ci) * 64 + ph * cout + co];
       }
     dw[i] = acc;
   } else {
@@ -427,10 +436,12 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG(mode >= 0 && mode <= 8, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
   long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
   if (mode == 8) n = 36LL * cout * cin;
+  if (mode == 11) n = 64LL * cout;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)
@@ -444,7 +455,7 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
 extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int cout, int cin, int kh,
                                     int kw, void* stream) {
   HM_CHECK_ARG(dwp && dw, "hm_unpack_conv_wgrad: null pointer");
-  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9) && kh == 5 && kw == 5),
+  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9 || mode == 10) && kh == 5 && kw == 5),
                "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;
   unpack_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dwp, dw, mode, cout,

@@ -321,6 +321,58 @@ __global__ void __launch_bounds__(256) thin_out_wgrad_kernel(HmConvDesc d, const
   }
 }
 
+// ---- re-layouts that turn the thin layers into tensor-core GEMMs ----------------------------------------------
+// im2col of a ONE-channel image: Xc[p][t] = x[p + tap t - pad] (t < kh*kw), 0 for the padding taps up to 64.
+// A 1->Cout kxk convolution is then the 1x1 convolution Xc[.,64] x Wt[Cout][64] (forward) and its weight
+// gradient the GEMM Xc^T dy, both on the tcgen05 kernels.  One thread = one pixel x 8 taps (16-byte store).
+__global__ void im2col_c1_kernel(const __half* __restrict__ x, __half* __restrict__ xc, int B, int H, int W, int kh,
+                                 int kw, int pad) {
+  const long long total = (long long)B * H * W * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    long long pix = i >> 3;
+    const int ox = (int)(pix % W);
+    long long t2 = pix / W;
+    const int oy = (int)(t2 % H);
+    const int n = (int)(t2 / H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int t = g * 8 + j;
+      const int r = t / kw, s = t - r * kw;
+      const int iy = oy - pad + r, ix = ox - pad + s;
+      v[j] = (t < kh * kw && iy >= 0 && iy < H && ix >= 0 && ix < W)
+                 ? __half2float(x[((size_t)n * H + iy) * W + ix]) : 0.f;
+    }
+    store8(xc + (size_t)pix * 64 + g * 8, v);
+  }
+}
+
+// space-to-depth of a thin gradient, zero-padded to 64 channels: out[q][ph*Co+co] = dy[2q + (ph>>1, ph&1)][co]
+__global__ void s2d_pad64_kernel(const __half* __restrict__ dy, __half* __restrict__ out, int B, int h, int w, int Co) {
+  const long long total = (long long)B * h * w * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    long long pix = i >> 3;
+    const int qx = (int)(pix % w);
+    long long t2 = pix / w;
+    const int qy = (int)(t2 % h);
+    const int n = (int)(t2 / h);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = g * 8 + j;
+      const int ph = c / Co, co = c - ph * Co;
+      v[j] = (c < 4 * Co)
+                 ? __half2float(dy[(((size_t)n * 2 * h + 2 * qy + (ph >> 1)) * (2 * w) + 2 * qx + (ph & 1)) * Co + co])
+                 : 0.f;
+    }
+    store8(out + (size_t)pix * 64 + g * 8, v);
+  }
+}
+
 // ---- dispatch helpers called from simt_conv.cu ----------------------------------------------------------------
 bool thin_in_conv_launch(const HmConvDesc* d, const void* x1, const void* x2, const void* w, const float* bias,
                          void* y, void* y2, cudaStream_t st) {
@@ -420,6 +472,30 @@ bool thin_wgrad_launch(const HmConvDesc* d, const void* x1, const void* x2, cons
 }
 
 }  // namespace hm
+
+extern "C" int hm_im2col_c1(const void* x, void* xc, int B, int H, int W, int kh, int kw, int pad, void* stream) {
+  HM_CHECK_ARG(x && xc && B > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && kh * kw <= 64 && pad >= 0,
+               "hm_im2col_c1: bad argument");
+  HM_CHECK_ARG((((uintptr_t)xc) & 15) == 0, "hm_im2col_c1: output must be 16-byte aligned");
+  const long long total = (long long)B * H * W * 8;
+  long long blocks = (total + 255) / 256, cap = (long long)hm::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  hm::im2col_c1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)xc, B, H, W, kh,
+                                                                          kw, pad);
+  HM_CHECK_LAUNCH("hm_im2col_c1");
+  return HM_OK;
+}
+
+extern "C" int hm_s2d_pad64(const void* dy, void* out, int B, int h, int w, int Co, void* stream) {
+  HM_CHECK_ARG(dy && out && B > 0 && h > 0 && w > 0 && Co > 0 && 4 * Co <= 64, "hm_s2d_pad64: bad argument");
+  HM_CHECK_ARG((((uintptr_t)out) & 15) == 0, "hm_s2d_pad64: output must be 16-byte aligned");
+  const long long total = (long long)B * h * w * 8;
+  long long blocks = (total + 255) / 256, cap = (long long)hm::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  hm::s2d_pad64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)dy, (__half*)out, B, h, w, Co);
+  HM_CHECK_LAUNCH("hm_s2d_pad64");
+  return HM_OK;
+}
 
 // Weight gradient of (nearest-2x upsampling -> 5x5 'same' convolution) with <= 4 output channels, as four 3x3
 // problems on the LOW-RES source: dw_phases[phase][(dy*3+dx)*Cin + ci][co] += sum_q x[q + (dy-1,dx-1)][ci] *

@@ -157,6 +157,12 @@ class ConvOp(object):
             self.tc_fwd = self.up2 or bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
+        # one-channel input (first discriminator layer): im2col to 64 "tap channels", then a 1x1 tensor-core GEMM
+        self.col1 = (rt.precision == "fast" and kind == "conv" and self.Cin == 1 and self.x2 is None and not self.up
+                     and self.stride == 1 and self.kh * self.kw <= 64 and 2 * self.pad == self.kh - 1
+                     and self.kh == self.kw and self.Cout % 64 == 0 and self.Cout <= 256)
+        if self.col1:
+            self.tc_fwd = True
         self.path = "tcgen05" if self.tc_fwd else "simt"
         # input gradient of a thin-output stride-1 convolution (dy has <= 4 channels): forward-form gather of dy,
         # which the library serves with its thin-input kernel
@@ -172,13 +178,21 @@ class ConvOp(object):
         if self.up and self.src.srcs[0].kind != "input":
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
         n = self.K * self.Cout
+        if self.col1:
+            self.xc = rt.empty((B, self.Hv, self.Wv, 64))
+            if self.wt_f is None:
+                self.wt_f = rt.empty((64 * self.Cout,))
+                self.dwp = rt.empty((64 * self.Cout,), torch.float32)
         if self.tc_fwd and self.wt_f is None:
             self.wt_f = rt.empty((36 * self.Cin * self.Cout if self.up2 else n,))
         if self.tc_dg and self.wt_d is None:
             self.wt_d = rt.empty((n,))
-        self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient: one thin launch per phase
-        if self.thin_up2_wg and (self.dwp is None or self.dwp.numel() < 36 * self.Cin * self.Cout):
-            self.dwp = rt.empty((36 * self.Cin * self.Cout,), torch.float32)
+        self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient of the thin phase-decomposed layer
+        if self.thin_up2_wg:
+            # tensor cores: s2d(dy) zero-padded to 64 channels against the low-res source (3x3 taps)
+            self.dy64 = rt.empty((B, self.x1.shape[0], self.x1.shape[1], 64))
+            if self.dwp is None or self.dwp.numel() < 9 * self.Cin * 64:
+                self.dwp = rt.empty((9 * self.Cin * 64,), torch.float32)
         if self.up and ((self.tc_fwd and not self.up2) or (self.tc_wg and not self.thin_up2_wg)):
             # the tensor-core kernels read dense NHWC tiles through TMA: materialise the 2x resampling once
             self.x1u = rt.empty((B, self.Hv, self.Wv, self.C1))
@@ -190,7 +204,9 @@ class ConvOp(object):
         if self.kind == "dense":
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 4, self.Cout, self.Cin, 1, 1, 0, 0, rt.cd)
         elif self.kind == "conv":
-            if not self.tc_fwd:
+            if self.col1:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 11, self.Cout, 1, self.kh, self.kw, 0, 0, rt.cd)
+            elif not self.tc_fwd:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
             else:
@@ -242,6 +258,12 @@ class ConvOp(object):
         """Forward descriptor over the MATERIALISED (already upsampled) source, for the tensor-core kernels."""
         d = self._fwd_desc(rt, n)
         d.H, d.W, d.up = self.Hv, self.Wv, 0
+        return d
+
+    def _col1_desc(self, rt, n):
+        """The 1x1 convolution over the im2col tensor (64 tap-channels) that stands for a one-channel-input conv."""
+        d = self._fwd_desc(rt, n)
+        d.C1, d.C2, d.kh, d.kw, d.pad, d.up = 64, 0, 1, 1, 0, 0
         return d
 
     def _tc_dgrad_desc(self, rt, n, acc):
@@ -296,6 +318,10 @@ class ConvOp(object):
                     d = self._fwd_desc(rt, n, (u, v))
                     rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f[(u * self.kw + v) * per:]),
                             bias, y, None)
+        elif self.col1:
+            rt.call("hm_im2col_c1", x1, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.kh, self.kw, self.pad)
+            d = self._col1_desc(rt, n)
+            rt.call("hm_tc_conv", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(self.wt_f), bias, y, None)
         elif self.up2:
             self._xu_valid = False
             d = self._fwd_desc(rt, n)
@@ -332,12 +358,20 @@ class ConvOp(object):
                         rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
                                 _ptr(self.dwp[(u * self.kw + v) * per:]))
                 mode = 2
+            elif self.col1:
+                d = self._col1_desc(rt, n)
+                rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
+                mode = 0              # rows [0, kh*kw) of the [64][Cout] result are the packed gradient
             elif self.thin_up2_wg:
                 # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
                 # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)
+                h, w = self.x1.shape[0], self.x1.shape[1]
+                rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, h, w, self.Cout)
                 d = self._fwd_desc(rt, n)
-                rt.call("hm_up2conv_wgrad_phases", C.byref(d), x1, _ptr(g), _ptr(self.dwp))
-                mode = 9
+                d.up, d.kh, d.kw, d.pad = 0, 3, 3, 1
+                d.Ho, d.Wo, d.oH, d.oW, d.Cout, d.split = h, w, h, w, 64, 64
+                rt.call("hm_tc_wgrad", C.byref(d), x1, None, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
+                mode = 10
             elif self.tc_wg and (not self.up or self.x1u is not None):
                 if self.up and not getattr(self, "_xu_valid", False):   # forward did not materialise the 2x copy
                     for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):

@@ -122,6 +122,16 @@ int hm_tc_wgrad_supported(const HmConvDesc* d);
 int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw_packed,
                 void* stream);
 
+/* Re-layouts that put the two thin layers of the DCGAN on the tensor cores (fp16 only):
+ *  hm_im2col_c1: xc[B,H,W,64], xc[p][t] = x[p + tap t - pad] for the kh*kw taps of a ONE-channel image, 0 beyond; the
+ *    first discriminator convolution (dcgan.py:42, Cin = 1) is then the 1x1 convolution xc x pack(mode 11) and its
+ *    weight gradient hm_tc_wgrad on (xc, dy), whose first kh*kw rows are the usual packed gradient;
+ *  hm_s2d_pad64: out[B,h,w,64], out[q][ph*Co+co] = dy[2q+phase ph][co], 0 beyond 4*Co; the weight gradient of the
+ *    generator's last layer (dcgan.py:31-32, Cout = 1) is hm_tc_wgrad(3x3 on the low-res source, out) folded with
+ *    hm_unpack_conv_wgrad(mode 10). */
+int hm_im2col_c1(const void* x, void* xc, int B, int H, int W, int kh, int kw, int pad, void* stream);
+int hm_s2d_pad64(const void* dy, void* out, int B, int h, int w, int Co, void* stream);
+
 /* Weight gradient of (Upscale2DLayer(2) -> 5x5 'same' Conv2DLayer) with <= 4 output channels (the generator's last
  * layer, dcgan.py:31-32) as four 3x3 problems on the low-res source; `d` is the layer's forward descriptor
  * (up = HM_UP_NEAREST2).  dw_phases is fp32 [4][9*Cin][Cout], atomically accumulated (caller zeroes); fold onto the

@@ -164,6 +164,10 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     for s_ in range(5):
                         dy_, dx_ = (py + r - 2) // 2 + 1, (px + s_ - 2) // 2 + 1
                         out[dy_, dx_, py * 2 + px] += Wc[:, :, r, s_]
+    elif mode == 11:
+        Wc = W.reshape(cout, kh * kw)[:, ::-1]                    # flipped taps, row-major (r, s)
+        out = np.zeros((cout, 64), np.float32)
+        out[:, :kh * kw] = Wc
     elif mode == 7:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
@@ -179,8 +183,10 @@ def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
     n = cout * cin * kh * kw
     src = _a(dwp, n, np.float32)
     dst = _a(dw, n, np.float32)
-    if mode in (8, 9):
-        if mode == 8:
+    if mode in (8, 9, 10):
+        if mode == 10:
+            g3 = _a(dwp, 9 * cin * 64, np.float32).reshape(3, 3, cin, 64)[..., :4 * cout].reshape(3, 3, cin, 4, cout)
+        elif mode == 8:
             g3 = _a(dwp, 36 * cin * cout, np.float32).reshape(3, 3, cin, 4, cout)
         else:
             g3 = _a(dwp, 36 * cin * cout, np.float32).reshape(4, 3, 3, cin, cout).transpose(1, 2, 3, 0, 4)
@@ -484,6 +490,25 @@ def hm_tc_wgrad(dp, x1, x2, dy, dw, stream=None):
     d = dp._obj if hasattr(dp, "_obj") else dp
     assert _tc_ok(d, True)
     return hm_conv_wgrad(dp, x1, x2, dy, dw)
+
+
+def hm_im2col_c1(x, xc, B, H, W, kh, kw, pad, stream=None):
+    a = _t(_a(x, B * H * W, np.float16)).reshape(B, 1, H, W)
+    cols = F.unfold(a, (kh, kw), padding=pad)                                  # [B, kh*kw, L]
+    Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    assert (Ho, Wo) == (H, W)
+    out = torch.zeros(B, H, W, 64)
+    out[..., :kh * kw] = cols.reshape(B, kh * kw, H, W).permute(0, 2, 3, 1)
+    _a(xc, B * H * W * 64, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+    return 0
+
+
+def hm_s2d_pad64(dy, out, B, h, w, Co, stream=None):
+    g = _a(dy, B * 4 * h * w * Co, np.float16).reshape(B, h, 2, w, 2, Co)
+    o = np.zeros((B, h, w, 64), np.float16)
+    o[..., :4 * Co] = g.transpose(0, 1, 3, 2, 4, 5).reshape(B, h, w, 4 * Co)
+    _a(out, B * h * w * 64, np.float16)[:] = o.reshape(-1)
+    return 0
 
 
 def hm_up2conv_wgrad_phases(dp, x, dy, dw, stream=None):

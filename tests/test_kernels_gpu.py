@@ -344,3 +344,26 @@ def test_up2conv_wgrad_phases_and_fold(Co, dtype):
     bo.run("hm_unpack_conv_wgrad", lambda P: (P(plain), P(direct), 0, Co, Ci, 5, 5))
     a, b = bo.gpu[folded].cpu().double(), bo.gpu[direct].cpu().double()
     assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max())
+
+
+def test_im2col_and_s2d_relayouts():
+    r = np.random.RandomState(21)
+    bo = Both()
+    B, H, W = 2, 9, 12
+    x = bo.t(r.randn(B, H, W, 1), torch.float16)
+    xc = bo.t(np.ones((B, H, W, 64)), torch.float16)
+    bo.run("hm_im2col_c1", lambda P: (P(x), P(xc), B, H, W, 5, 5, 2))
+    assert torch.equal(bo.gpu[xc].cpu(), bo.cpu[xc])
+    for Co in (1, 3):
+        dy = bo.t(r.randn(B, 2 * H, 2 * W, Co), torch.float16)
+        out = bo.t(np.ones((B, H, W, 64)), torch.float16)
+        bo.run("hm_s2d_pad64", lambda P: (P(dy), P(out), B, H, W, Co))
+        assert torch.equal(bo.gpu[out].cpu(), bo.cpu[out])
+    w = bo.t(r.randn(64, 1, 5, 5))
+    wp = bo.t(np.ones(64 * 64), torch.float16)
+    bo.run("hm_pack_conv_weight", lambda P: (P(w), P(wp), 11, 64, 1, 5, 5, 0, 0, 1))
+    assert torch.equal(bo.gpu[wp].cpu(), bo.cpu[wp])
+    g = bo.t(r.randn(9 * 16 * 64))
+    o = bo.t(np.zeros(25 * 16 * 3))
+    bo.run("hm_unpack_conv_wgrad", lambda P: (P(g), P(o), 10, 3, 16, 5, 5))
+    bo.check(o, 1e-6, "unpack mode 10")
