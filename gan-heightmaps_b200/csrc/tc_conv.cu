@@ -142,6 +142,149 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float slope) {
+  if (ACT == HM_ACT_LRELU) return fmaxf(v, 0.f) + slope * fminf(v, 0.f);
+  if (ACT == HM_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == HM_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (ACT == HM_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// 32 accumulator columns -> +bias (shared memory, float4 reads) -> activation -> 16 packed half2
+template <int ACT>
+__device__ __forceinline__ void epi_pack32(const uint32_t* v, const float* bias32, float slope, uint32_t* packed) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias32 + j);
+    const float a0 = act_t<ACT>(__uint_as_float(v[j]) + b.x, slope);
+    const float a1 = act_t<ACT>(__uint_as_float(v[j + 1]) + b.y, slope);
+    const float a2 = act_t<ACT>(__uint_as_float(v[j + 2]) + b.z, slope);
+    const float a3 = act_t<ACT>(__uint_as_float(v[j + 3]) + b.w, slope);
+    __half2 h0 = __floats2half2_rn(a0, a1), h1 = __floats2half2_rn(a2, a3);
+    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+    packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+  }
+}
+
+// The whole epilogue role: for every tile of this CTA wait for the accumulator, drain it, release it.
+template <int ACT>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t ctrl, const float* bias_s,
+                                              int warp, int lane, int total_tiles) {
+  const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+  const int row = q * 32 + lane;
+  const int px_per_img = p.bw * p.bh;
+  const int in = row / px_per_img;
+  const int rem = row - in * px_per_img;
+  const int iy = rem / p.bw, ix = rem - iy * p.bw;
+  const uint32_t tfull0 = ctrl + 8u * (2 * p.stages), tempty0 = ctrl + 8u * (2 * p.stages + 2);
+  int it = 0;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+    const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+    const int tx = mt % p.tiles_x;
+    const int ty = (mt / p.tiles_x) % p.tiles_y;
+    const int tn = mt / (p.tiles_x * p.tiles_y);
+    const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
+    const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
+    const int acc = it & 1;
+    mbar_wait(tfull0 + 8u * acc, (it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.ntile;
+    const int col0 = nt * p.ntile;
+    const float* bias_t = bias_s + col0;
+    if (p.d2s) {
+      // ---- depth-to-space: column = (phase, co); phase (py,px) of low-res pixel (oy,ox) -> (2oy+py, 2ox+px)
+      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+        uint32_t v[32];
+        if (p.ntile - c0 >= 32) {
+          tmem_ld32(taddr + c0, v);
+        } else {
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int j = 16; j < 32; j++) v[j] = 0;
+        }
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int gc = col0 + c0;
+        if (p.cph % 32 == 0) {
+          const int ph = gc / p.cph, co = gc - ph * p.cph;
+          const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+          uint32_t packed[16];
+          epi_pack32<ACT>(v, bias_t + c0, p.slope, packed);
+          uint4* d4 = reinterpret_cast<uint4*>(p.y + op * p.cph + co);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int col = gc + j;
+            if (col < 4 * p.cph) {
+              const int ph = col / p.cph, co = col - ph * p.cph;
+              const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+              p.y[op * p.cph + co] = __float2half_rn(act_t<ACT>(__uint_as_float(v[j]) + bias_t[c0 + j], p.slope));
+            }
+          }
+        }
+      }
+    } else {
+      const size_t pix = (size_t)((size_t)n * p.Ho + oy) * p.Wo + ox;
+      const bool second = col0 >= p.split;
+      __half* dst = second ? p.y2 + pix * (p.Cout - p.split) + (col0 - p.split) : p.y + pix * p.split + col0;
+      const bool accum = (p.accumulate & (second ? 2 : 1)) != 0;
+      const bool store = valid && (second ? p.y2 != nullptr : p.y != nullptr);
+      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+        uint32_t v[32];
+        if (p.ntile - c0 >= 32) {
+          tmem_ld32(taddr + c0, v);
+        } else {
+          tmem_ld16(taddr + c0, v);
+#pragma unroll
+          for (int j = 16; j < 32; j++) v[j] = 0;
+        }
+        tmem_ld_wait();
+        if (!store) continue;
+        const int ncols = min(32, p.ntile - c0);
+        if (p.vec_store) {
+          uint32_t packed[16];
+          if (accum) {                                        // y += : add the stored fp16 values in fp32 first
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              if (j * 8 < ncols) {
+                const uint4 pv = reinterpret_cast<const uint4*>(dst + c0)[j];
+                const uint32_t w4[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&w4[k]));
+                  v[j * 8 + 2 * k] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * k]) + pf.x);
+                  v[j * 8 + 2 * k + 1] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * k + 1]) + pf.y);
+                }
+              }
+            }
+          }
+          epi_pack32<ACT>(v, bias_t + c0, p.slope, packed);
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (j * 8 < ncols) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        } else {  // thin outputs: the N tile is zero-padded by TMA, store only the real columns
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (col0 + c0 + j < p.Cout) {
+              float a = __uint_as_float(v[j]) + bias_t[c0 + j];
+              if (accum) a += __half2float(dst[c0 + j]);
+              dst[c0 + j] = __float2half_rn(act_t<ACT>(a, p.slope));
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -149,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_bytes = A_BYTES + p.ntile * 128;
   const uint32_t ctrl = base + p.stages * stage_bytes;        // 1024-aligned
-  // control block: full[stages] | empty[stages] | tfull[2] | tempty[2] | tmem base address
+  // control block: full[stages] | empty[stages] | tfull[2] | tempty[2] | tmem base address | (+1024) bias[<=1024]
   auto full_bar = [&](int s) { return ctrl + 8u * s; };
   auto empty_bar = [&](int s) { return ctrl + 8u * (p.stages + s); };
   auto tfull_bar = [&](int a) { return ctrl + 8u * (2 * p.stages + a); };
@@ -157,6 +300,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_slot = ctrl + 8u * (2 * p.stages + 4);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);     // [n_ntiles * ntile] (<= 1024) floats
+  {
+    const int ncols = p.n_ntiles * p.ntile;
+    const int creal = p.d2s ? p.cph : p.Cout;
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+      const int c = p.d2s ? i % p.cph : i;
+      bias_s[i] = (p.bias && c < creal && (!p.d2s || i < 4 * p.cph)) ? p.bias[c] : 0.f;
+    }
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tmem_cols = p.ntile <= 64 ? 128 : (p.ntile <= 128 ? 256 : 512);
@@ -253,144 +405,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int px_per_img = p.bw * p.bh;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-      const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
-      const int tx = mt % p.tiles_x;
-      const int ty = (mt / p.tiles_x) % p.tiles_y;
-      const int tn = mt / (p.tiles_x * p.tiles_y);
-      const int in = row / px_per_img;
-      const int rem = row - in * px_per_img;
-      const int iy = rem / p.bw, ix = rem - iy * p.bw;
-      const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
-      const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
-      const int acc = it & 1;
-      mbar_wait(tfull_bar(acc), (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.ntile;
-      const int col0 = nt * p.ntile;
-      const size_t pix = (size_t)((size_t)n * p.Ho + oy) * p.Wo + ox;
-      const bool second = col0 >= p.split;
-      __half* dst = second ? p.y2 + pix * (p.Cout - p.split) + (col0 - p.split) : p.y + pix * p.split + col0;
-      const bool accum = (p.accumulate & (second ? 2 : 1)) != 0;
-      const bool store = valid && (second ? p.y2 != nullptr : p.y != nullptr);
-      if (p.d2s) {
-        // ---- depth-to-space epilogue ----
-        for (int c0 = 0; c0 < p.ntile; c0 += 32) {
-          uint32_t v[32];
-          if (p.ntile - c0 >= 32) {
-            tmem_ld32(taddr + c0, v);
-          } else {
-            tmem_ld16(taddr + c0, v);
-#pragma unroll
-            for (int j = 16; j < 32; j++) v[j] = 0;
-          }
-          tmem_ld_wait();
-          if (!valid) continue;
-          const int gc = col0 + c0;                            // global column of v[0]
-          if (p.cph % 32 == 0) {                               // the 32 columns lie inside one phase
-            const int ph = gc / p.cph, co = gc - ph * p.cph;
-            if (ph < 4) {
-              const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
-              uint32_t packed[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-                if (p.bias) {
-                  a += __ldg(p.bias + co + j);
-                  b += __ldg(p.bias + co + j + 1);
-                }
-                __half2 h = __floats2half2_rn(act_fwd(a, p.act, p.slope), act_fwd(b, p.act, p.slope));
-                packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              uint4* d4 = reinterpret_cast<uint4*>(p.y + op * p.cph + co);
-#pragma unroll
-              for (int j = 0; j < 4; j++)
-                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            }
-          } else {                                             // thin outputs (cph < 32): column by column
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const int col = gc + j;
-              if (col < 4 * p.cph) {
-                const int ph = col / p.cph, co = col - ph * p.cph;
-                const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
-                float a = __uint_as_float(v[j]);
-                if (p.bias) a += __ldg(p.bias + co);
-                p.y[op * p.cph + co] = __float2half_rn(act_fwd(a, p.act, p.slope));
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        continue;
-      }
-      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
-        uint32_t v[32];
-        if (p.ntile - c0 >= 32) {
-          tmem_ld32(taddr + c0, v);
-        } else {
-          tmem_ld16(taddr + c0, v);
-#pragma unroll
-          for (int j = 16; j < 32; j++) v[j] = 0;
-        }
-        tmem_ld_wait();
-        const int ncols = min(32, p.ntile - c0);
-        if (store) {
-          uint32_t packed[16];
-          uint4 prev[4];
-          if (accum) {
-            if (p.vec_store) {
-#pragma unroll
-              for (int j = 0; j < 4; j++)
-                if (j * 8 < ncols) prev[j] = reinterpret_cast<const uint4*>(dst + c0)[j];
-            } else {
-              __half* ph = reinterpret_cast<__half*>(prev);
-#pragma unroll
-              for (int j = 0; j < 32; j++) ph[j] = (col0 + c0 + j < p.Cout) ? dst[c0 + j] : __float2half(0.f);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-            if (p.bias) {
-              const int co = nt * p.ntile + c0 + j;
-              a += __ldg(p.bias + min(co, p.Cout - 1));
-              b += __ldg(p.bias + min(co + 1, p.Cout - 1));
-            }
-            a = act_fwd(a, p.act, p.slope);
-            b = act_fwd(b, p.act, p.slope);
-            if (accum) {
-              const uint32_t pv = reinterpret_cast<const uint32_t*>(prev)[j >> 1];
-              const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pv));
-              a += pf.x;
-              b += pf.y;
-            }
-            __half2 h = __floats2half2_rn(a, b);
-            packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          if (p.vec_store) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (j * 8 < ncols)
-                d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          } else {  // thin outputs (Cout < 16 or not a multiple of 8): the N tile is zero-padded by TMA, store the real columns
-            const __half* ph = reinterpret_cast<const __half*>(packed);
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (col0 + c0 + j < p.Cout) dst[c0 + j] = ph[j];
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    switch (p.act) {
+      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
+      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
     }
   }
   tc_fence_before();
@@ -520,7 +540,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.n_ntiles = (p.Cout + p.ntile - 1) / p.ntile;
   p.vec_store = (p.Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
   const int stage_bytes = A_BYTES + p.ntile * 128;
-  int stages = (227 * 1024 - 4096) / stage_bytes;
+  int stages = (227 * 1024 - 6144) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y; p.y2 = (__half*)y2;
@@ -535,7 +555,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     set_error("hm_tc_conv: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
     return HM_ERR_CUDA;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 2048 /*control block*/;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 1024 + 4096 /*control block + bias*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
