@@ -35,6 +35,7 @@ struct TcParams {
   int bw, bh, bn;          // pixel box of one M tile
   int tiles_x, tiles_y, tiles_n, n_mtiles;
   int ntile, n_ntiles;     // N tile (<=256, multiple of 16)
+  int S, n_super;          // S consecutive M tiles share every B (weight) stage: S*ntile*2 <= 512 TMEM columns
   int stages;
   int act;
   float slope;
@@ -180,18 +181,21 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   const uint32_t tfull0 = ctrl + 8u * (2 * p.stages), tempty0 = ctrl + 8u * (2 * p.stages + 2);
   int it = 0;
   for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-    const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+    const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
+    const int nv = min(p.S, p.n_mtiles - st * p.S);
+    const int acc = it & 1;
+    mbar_wait(tfull0 + 8u * acc, (it >> 1) & 1);
+    tc_fence_after();
+    const int col0 = nt * p.ntile;
+    const float* bias_t = bias_s + col0;
+   for (int sub = 0; sub < nv; sub++) {
+    const int mt = st * p.S + sub;
     const int tx = mt % p.tiles_x;
     const int ty = (mt / p.tiles_x) % p.tiles_y;
     const int tn = mt / (p.tiles_x * p.tiles_y);
     const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
     const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
-    const int acc = it & 1;
-    mbar_wait(tfull0 + 8u * acc, (it >> 1) & 1);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.ntile;
-    const int col0 = nt * p.ntile;
-    const float* bias_t = bias_s + col0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.S * p.ntile) + sub * p.ntile;
     if (p.d2s) {
       // ---- depth-to-space: column = (phase, co); phase (py,px) of low-res pixel (oy,ox) -> (2oy+py, 2ox+px)
       for (int c0 = 0; c0 < p.ntile; c0 += 32) {
@@ -279,6 +283,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         }
       }
     }
+   }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
@@ -290,7 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = A_BYTES + p.ntile * 128;
+  const uint32_t a_bytes = p.S * A_BYTES;
+  const uint32_t stage_bytes = a_bytes + p.ntile * 128;
   const uint32_t ctrl = base + p.stages * stage_bytes;        // 1024-aligned
   // control block: full[stages] | empty[stages] | tfull[2] | tempty[2] | tmem base address | (+1024) bias[<=1024]
   auto full_bar = [&](int s) { return ctrl + 8u * s; };
@@ -311,7 +317,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tmem_cols = p.ntile <= 64 ? 128 : (p.ntile <= 128 ? 256 : 512);
+  const int acc_cols = p.S * p.ntile;                    // columns of one accumulator set (double-buffered)
+  const int tmem_cols = 2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; s++) {
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
 
-  const int total_tiles = p.n_mtiles * p.n_ntiles;
+  const int total_tiles = p.n_super * p.n_ntiles;        // work items: (super tile of S M tiles, N tile)
   const int ksteps_per_tap = p.Cin / KCH;
   const int taps = p.kh * p.kw;
 
@@ -347,23 +354,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int tn = mt / (p.tiles_x * p.tiles_y);
-        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = tn * p.bn;
+        const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
+        const int nv = min(p.S, p.n_mtiles - st * p.S);      // M tiles present in this super tile
+        int ox0[4], oy0[4], n0[4];
+        for (int i = 0; i < nv; i++) {
+          const int mt = st * p.S + i;
+          ox0[i] = (mt % p.tiles_x) * p.bw;
+          oy0[i] = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
+          n0[i] = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
+        }
         for (int tap = 0; tap < taps; tap++) {
           const int r = tap / p.kw, s = tap - r * p.kw;
           for (int cc = 0; cc < ksteps_per_tap; cc++) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = base + stage * stage_bytes;
-            mbar_expect_tx(full_bar(stage), stage_bytes);
+            mbar_expect_tx(full_bar(stage), nv * A_BYTES + p.ntile * 128);
             const int c = cc * KCH;
-            if (c < p.C1)
-              tma_load_4d(&tmA, sa, full_bar(stage), c, ox0 - p.pad + s, oy0 - p.pad + r, n0);
-            else
-              tma_load_4d(&tmA2, sa, full_bar(stage), c - p.C1, ox0 - p.pad + s, oy0 - p.pad + r, n0);
-            tma_load_3d(&tmB, sa + A_BYTES, full_bar(stage), c, nt * p.ntile, tap);
+            for (int i = 0; i < nv; i++) {
+              if (c < p.C1)
+                tma_load_4d(&tmA, sa + i * A_BYTES, full_bar(stage), c, ox0[i] - p.pad + s, oy0[i] - p.pad + r, n0[i]);
+              else
+                tma_load_4d(&tmA2, sa + i * A_BYTES, full_bar(stage), c - p.C1, ox0[i] - p.pad + s,
+                            oy0[i] - p.pad + r, n0[i]);
+            }
+            tma_load_3d(&tmB, sa + a_bytes, full_bar(stage), c, nt * p.ntile, tap);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -383,17 +397,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.ntile;
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        const int st = t / p.n_ntiles;
+        const int nv = min(p.S, p.n_mtiles - st * p.S);
         const int ksteps = taps * ksteps_per_tap;
         for (int ks = 0; ks < ksteps; ks++) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes;
-          const uint64_t ad = umma_desc_k_sw128(sa);
-          const uint64_t bd = umma_desc_k_sw128(sa + A_BYTES);
+          const uint64_t bd = umma_desc_k_sw128(sa + a_bytes);
+          for (int i = 0; i < nv; i++) {                      // every M tile of the super tile reuses this B stage
+            const uint64_t ad = umma_desc_k_sw128(sa + i * A_BYTES);
 #pragma unroll
-          for (int k = 0; k < KCH / 16; k++)                  // +32 B per K=16 slice inside the swizzle atom
-            tc_mma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0);
+            for (int k = 0; k < KCH / 16; k++)                // +32 B per K=16 slice inside the swizzle atom
+              tc_mma_f16(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0);
+          }
           tc_commit(empty_bar(stage));                        // frees the stage when these MMAs retire
           if (++stage == p.stages) {
             stage = 0;
@@ -539,7 +557,13 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.ntile = pick_ntile(p.Cout, up2 ? p.Cout : d->split);
   p.n_ntiles = (p.Cout + p.ntile - 1) / p.ntile;
   p.vec_store = (p.Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
-  const int stage_bytes = A_BYTES + p.ntile * 128;
+  int S = 256 / p.ntile;                                   // 2 (double buffer) * S * ntile <= 512 TMEM columns
+  if (S < 1) S = 1;
+  if (S > 4) S = 4;
+  while (S > 1 && ((p.n_mtiles + S - 1) / S) * p.n_ntiles < num_sms()) S >>= 1;   // keep every SM busy on small layers
+  p.S = S;
+  p.n_super = (p.n_mtiles + S - 1) / S;
+  const int stage_bytes = S * A_BYTES + p.ntile * 128;
   int stages = (227 * 1024 - 6144) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
@@ -565,7 +589,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     }
     attr_set = true;
   }
-  int grid = p.n_mtiles * p.n_ntiles;
+  int grid = p.n_super * p.n_ntiles;
   if (grid > num_sms()) grid = num_sms();
   tc_conv_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmA2, tmB, p);
   HM_CHECK_LAUNCH("hm_tc_conv");
