@@ -18,6 +18,7 @@
 //   * Epilogue: tcgen05.ld 32 lanes x 32 columns -> bias, activation -> fp16 -> 16-byte stores
 //     into the NHWC output.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "hm_common.cuh"
 
@@ -37,6 +38,7 @@ struct TcParams {
   int ntile, n_ntiles;     // N tile (<=256, multiple of 16)
   int S, n_super;          // S consecutive M tiles share every B (weight) stage: S*ntile*2 <= 512 TMEM columns
   int stages;
+  int a_slots, b_slots, rb_bytes;   // row-box variant: A ring (one box per filter row), B ring (one slot per tap)
   int act;
   float slope;
   const float* bias;       // [Cout] or null
@@ -170,15 +172,14 @@ __device__ __forceinline__ void epi_pack32(const uint32_t* v, const float* bias3
 
 // The whole epilogue role: for every tile of this CTA wait for the accumulator, drain it, release it.
 template <int ACT>
-__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t ctrl, const float* bias_s,
-                                              int warp, int lane, int total_tiles) {
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              const float* bias_s, int warp, int lane, int total_tiles) {
   const int q = warp & 3;                                   // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
   const int px_per_img = p.bw * p.bh;
   const int in = row / px_per_img;
   const int rem = row - in * px_per_img;
   const int iy = rem / p.bw, ix = rem - iy * p.bw;
-  const uint32_t tfull0 = ctrl + 8u * (2 * p.stages), tempty0 = ctrl + 8u * (2 * p.stages + 2);
   int it = 0;
   for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
     const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
@@ -424,11 +425,178 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else {
     // ===================== epilogue (warps 2..5) =====================
     switch (p.act) {
-      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
-      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, ctrl, bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// K-major SW128 descriptor whose start is any 128-byte line of a swizzled buffer (not a 1024-byte atom boundary):
+// the "base offset" field carries the line's phase inside the 8-line swizzle pattern.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_line(uint32_t saddr) {
+  return umma_desc_k_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-box variant (tiles that are 128 consecutive pixels of ONE image row, i.e. W >= 128): instead of one A tile per
+// tap, ONE box of 128+kw-1 pixel lines per filter ROW is loaded; the kw taps of that row are the same lines read
+// from start offsets 0, 128, 256 ... bytes (UMMA descriptor start = box + s*128).  L2->SM traffic for A drops from
+// kh*kw to ~kh tiles per 64-channel slice; the weight slices stream through their own ring.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_conv_rb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_slot_bytes = p.S * p.rb_bytes;               // rb_bytes is a multiple of 1024
+  const uint32_t b_slot_bytes = p.ntile * 128;
+  const uint32_t b_base = base + p.a_slots * a_slot_bytes;
+  const uint32_t ctrl = b_base + p.b_slots * b_slot_bytes;
+  auto afull = [&](int s) { return ctrl + 8u * s; };
+  auto aempty = [&](int s) { return ctrl + 8u * (p.a_slots + s); };
+  auto bfull = [&](int s) { return ctrl + 8u * (2 * p.a_slots + s); };
+  auto bempty = [&](int s) { return ctrl + 8u * (2 * p.a_slots + p.b_slots + s); };
+  auto tfull_bar = [&](int a) { return ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + a); };
+  auto tempty_bar = [&](int a) { return ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + 2 + a); };
+  const uint32_t tmem_slot = ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);
+  {
+    const int ncols = p.n_ntiles * p.ntile;
+    const int creal = p.d2s ? p.cph : p.Cout;
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+      const int c = p.d2s ? i % p.cph : i;
+      bias_s[i] = (p.bias && c < creal && (!p.d2s || i < 4 * p.cph)) ? p.bias[c] : 0.f;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int acc_cols = p.S * p.ntile;
+  const int tmem_cols = 2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_slots; s++) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < p.b_slots; s++) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const int total_tiles = p.n_super * p.n_ntiles;
+  const int cchunks = p.Cin / KCH;
+  const uint32_t box_bytes = (uint32_t)(TILE_M + p.kw - 1) * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
+        const int nv = min(p.S, p.n_mtiles - st * p.S);
+        int ox0[4], oy0[4], n0[4];
+        for (int i = 0; i < nv; i++) {
+          const int mt = st * p.S + i;
+          ox0[i] = (mt % p.tiles_x) * p.bw;
+          oy0[i] = (mt / p.tiles_x) % p.tiles_y;                 // bh == 1
+          n0[i] = mt / (p.tiles_x * p.tiles_y);                  // bn == 1
+        }
+        for (int r = 0; r < p.kh; r++) {
+          for (int cc = 0; cc < cchunks; cc++) {
+            const int c = cc * KCH;
+            mbar_wait(aempty(as), aph ^ 1);
+            mbar_expect_tx(afull(as), nv * box_bytes);
+            for (int i = 0; i < nv; i++) {
+              const uint32_t dst = base + as * a_slot_bytes + i * p.rb_bytes;
+              if (c < p.C1)
+                tma_load_4d(&tmA, dst, afull(as), c, ox0[i] - p.pad, oy0[i] - p.pad + r, n0[i]);
+              else
+                tma_load_4d(&tmA2, dst, afull(as), c - p.C1, ox0[i] - p.pad, oy0[i] - p.pad + r, n0[i]);
+            }
+            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+            for (int s = 0; s < p.kw; s++) {
+              mbar_wait(bempty(bs), bph ^ 1);
+              mbar_expect_tx(bfull(bs), b_slot_bytes);
+              tma_load_3d(&tmB, b_base + bs * b_slot_bytes, bfull(bs), c, nt * p.ntile, r * p.kw + s);
+              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.ntile);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        const int st = t / p.n_ntiles;
+        const int nv = min(p.S, p.n_mtiles - st * p.S);
+        bool first = true;
+        for (int r = 0; r < p.kh; r++) {
+          for (int cc = 0; cc < cchunks; cc++) {
+            mbar_wait(afull(as), aph);
+            tc_fence_after();
+            const uint32_t a_addr = base + as * a_slot_bytes;
+            for (int s = 0; s < p.kw; s++) {
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after();
+              const uint64_t bd = umma_desc_k_sw128(b_base + bs * b_slot_bytes);
+              for (int i = 0; i < nv; i++) {
+                const uint64_t ad = umma_desc_k_sw128_line(a_addr + i * p.rb_bytes + s * 128);
+#pragma unroll
+                for (int k = 0; k < KCH / 16; k++)
+                  tc_mma_f16(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+              }
+              first = false;
+              tc_commit(bempty(bs));
+              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+            }
+            tc_commit(aempty(as));
+            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+          }
+        }
+        tc_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    switch (p.act) {
+      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
+      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
     }
   }
   tc_fence_before();
@@ -578,6 +746,44 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   if (rc) {
     set_error("hm_tc_conv: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
     return HM_ERR_CUDA;
+  }
+  // Row-box variant: tiles are row segments (bw == 128) and the filter is wider than one tap.
+  static int rb_enabled = -1;
+  if (rb_enabled < 0) {
+    const char* e = getenv("HMGAN_TC_ROWBOX");
+    rb_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (rb_enabled && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
+    p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;
+    p.a_slots = (S * p.rb_bytes > 40 * 1024) ? 2 : 3;
+    int b_slots = (227 * 1024 - 6144 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
+    if (b_slots > 8) b_slots = 8;
+    if (b_slots >= 2) {
+      p.b_slots = b_slots;
+      CUtensorMap rA, rA2;
+      rc = encode_act(&rA, x1, d->B, d->H, d->W, d->C1, TILE_M + p.kw - 1, 1, 1);
+      if (!rc) rc = d->C2 ? encode_act(&rA2, x2, d->B, d->H, d->W, d->C2, TILE_M + p.kw - 1, 1, 1) : 0;
+      if (!d->C2) rA2 = rA;
+      if (rc) {
+        set_error("hm_tc_conv: cuTensorMapEncodeTiled failed for the row box (CUresult %d)", rc);
+        return HM_ERR_CUDA;
+      }
+      const size_t smem_rb = (size_t)p.a_slots * S * p.rb_bytes + (size_t)p.b_slots * p.ntile * 128 + 1024 + 1024 + 4096;
+      static bool rb_attr = false;
+      if (!rb_attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+          set_error("hm_tc_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+          return HM_ERR_CUDA;
+        }
+        rb_attr = true;
+      }
+      int grid_rb = p.n_super * p.n_ntiles;
+      if (grid_rb > num_sms()) grid_rb = num_sms();
+      tc_conv_rb_kernel<<<grid_rb, TC_THREADS, smem_rb, (cudaStream_t)stream>>>(rA, rA2, tmB, p);
+      HM_CHECK_LAUNCH("hm_tc_conv(row box)");
+      return HM_OK;
+    }
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 1024 + 4096 /*control block + bias*/;
   static bool attr_set = false;

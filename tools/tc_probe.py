@@ -25,6 +25,10 @@ CASES = [
     ("2x2valid_512_512", 4, 2, 2, 512, 0, 512, 2, 0, 0),
     ("3x3_64_48_w12_ragged", 3, 10, 12, 64, 0, 48, 3, 1, 3),
     ("5x5_256_256_8x8_b3", 3, 8, 8, 256, 0, 256, 5, 2, 1),
+    ("5x5_64_64_w512_rb", 1, 6, 512, 64, 0, 64, 5, 2, 1),
+    ("5x5_128_128_w128_rb", 2, 20, 128, 128, 0, 128, 5, 2, 1),
+    ("3x3_cat64+64_256_w256_rb", 1, 5, 256, 64, 64, 256, 3, 1, 0),
+    ("5x5_64_1_w256_thin_rb", 1, 9, 256, 64, 0, 1, 5, 2, 3),
     ("5x5_64_1_w64_thin", 2, 64, 64, 64, 0, 1, 5, 2, 3),
     ("3x3_128_3_w32_thin", 2, 32, 32, 128, 0, 3, 3, 1, 4),
     ("1x1_128_12_w16_thin", 2, 16, 16, 128, 0, 12, 1, 0, 0),
