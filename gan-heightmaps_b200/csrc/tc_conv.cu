@@ -38,6 +38,7 @@ struct TcParams {
   int ntile, n_ntiles;     // N tile (<=256, multiple of 16)
   int S, n_super;          // S consecutive M tiles share every B (weight) stage: S*ntile*2 <= 512 TMEM columns
   int stages;
+  int rb_mode;                      // experiment: how the unaligned descriptor start is encoded
   int a_slots, b_slots, rb_bytes;   // row-box variant: A ring (one box per filter row), B ring (one slot per tap)
   int act;
   float slope;
@@ -440,9 +441,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// K-major SW128 descriptor whose start is any 128-byte line of a swizzled buffer (not a 1024-byte atom boundary):
-// the "base offset" field carries the line's phase inside the 8-line swizzle pattern.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128_line(uint32_t saddr) {
+// K-major SW128 descriptor whose start is any 128-byte line of a swizzled buffer (not a 1024-byte atom boundary).
+// Measured on B200 (tools/tc_probe.py *_rb cases): the 128B swizzle is a function of the absolute shared-memory
+// address, so the plain descriptor with base_offset = 0 reads lines written by TMA correctly from any line start;
+// setting base_offset = (addr >> 7) & 7 (mode 1) gives wrong results.  mode stays selectable for that experiment.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_line(uint32_t saddr, int mode) {
+  if (mode == 0) return umma_desc_k_sw128(saddr);
   return umma_desc_k_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
 }
 
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               tc_fence_after();
               const uint64_t bd = umma_desc_k_sw128(b_base + bs * b_slot_bytes);
               for (int i = 0; i < nv; i++) {
-                const uint64_t ad = umma_desc_k_sw128_line(a_addr + i * p.rb_bytes + s * 128);
+                const uint64_t ad = umma_desc_k_sw128_line(a_addr + i * p.rb_bytes + s * 128, p.rb_mode);
 #pragma unroll
                 for (int k = 0; k < KCH / 16; k++)
                   tc_mma_f16(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
@@ -755,6 +759,10 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   }
   if (rb_enabled && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
     p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;
+    {
+      const char* e = getenv("HMGAN_RB_MODE");
+      p.rb_mode = e ? atoi(e) : 0;
+    }
     p.a_slots = (S * p.rb_bytes > 40 * 1024) ? 2 : 3;
     int b_slots = (227 * 1024 - 6144 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
     if (b_slots > 8) b_slots = 8;
