@@ -114,6 +114,9 @@ class Pix2Pix(object):
         self.losses = rt.zeros((5,), torch.float32)
         self.train_keys = ['dcgan_gen', 'dcgan_disc', 'p2p_gen', 'p2p_recon', 'p2p_disc']
         self._stage = {}
+        self._graphs = {}
+        self._graphs_ok = (rt.device.type == "cuda" and self.opt == "rmsprop" and
+                           os.environ.get("HMGAN_CUDA_GRAPHS", "1") != "0")
         self.train_fn = lambda Z, X, Y: self._step_host(Z, X, Y, True)
         self.loss_fn = lambda Z, X, Y: self._step_host(Z, X, Y, False)
         self.gen_fn = lambda X: self._gen_p2p(X, False)
@@ -169,7 +172,42 @@ class Pix2Pix(object):
 
     def step_device(self, Zd, Xd, Yd, train=True):
         """One train_fn / loss_fn evaluation on float32 NCHW DEVICE tensors; the five
-        losses stay on the device in self.losses (no host synchronisation)."""
+        losses stay on the device in self.losses (no host synchronisation).
+
+        On a CUDA device the ~1000 kernel launches of a step are captured once into a CUDA graph per
+        (batch size, train flag) -- after two eager warm-up calls that size every buffer -- and replayed
+        afterwards, so the host cost of a step is one graph launch (all buffers are static, tensor maps and
+        descriptors are kernel arguments, the learning rate is read from device memory).  Set
+        HMGAN_CUDA_GRAPHS=0 to always run eagerly; Adam runs eagerly (its step count is a kernel argument)."""
+        if not self._graphs_ok:
+            return self._step_eager(Zd, Xd, Yd, train)
+        key = (tuple(Zd.shape), tuple(Xd.shape), tuple(Yd.shape), bool(train))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = {"calls": 0, "graph": None}
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] <= 2:
+                return self._step_eager(Zd, Xd, Yd, train)
+            # capture: static input buffers, then record the step on torch's capture stream
+            st["Z"], st["X"], st["Y"] = Zd.clone(), Xd.clone(), Yd.clone()
+            self._sync_lr()
+            torch.cuda.synchronize(self.rt.device)
+            g = torch.cuda.CUDAGraph()
+            l0 = self.rt.launches
+            with torch.cuda.graph(g):
+                self._step_eager(st["Z"], st["X"], st["Y"], train)
+            st["launches"] = self.rt.launches - l0
+            st["graph"] = g
+        for dst, src in ((st["Z"], Zd), (st["X"], Xd), (st["Y"], Yd)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._sync_lr()
+        st["graph"].replay()
+        self.rt.launches += st["launches"]
+        return self.losses
+
+    def _step_eager(self, Zd, Xd, Yd, train=True):
         rt = self.rt
         B = int(Xd.shape[0])
         S = self.in_shp
