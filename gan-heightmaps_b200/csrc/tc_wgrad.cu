@@ -15,6 +15,7 @@
 //   * Epilogue: tcgen05.ld -> fp32 atomic adds into the packed gradient [kh*kw*Cin][Cout] (the layout of
 //     hm_conv_wgrad, so hm_unpack_conv_wgrad applies unchanged).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "hm_common.cuh"
 
@@ -251,6 +252,177 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row-box variant (pixel tiles that are 128 consecutive pixels of one image row): the x operand of the taps
+// (r, 0..kw-1) of one filter row and one 64-channel block is ONE TMA box of 128+kw-1 pixel lines; a tap is the same
+// box read from line offset s (the 128B swizzle is address-based, see tc_conv.cu).  A CTA loads, per pixel tile, only
+// the distinct (row, channel-block) boxes its units need instead of one 16 KB tile per unit.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgRbParams {
+  WgParams w;
+  int rb_bytes;        // bytes reserved per box (multiple of 1024)
+  int max_boxes;       // boxes per A slot
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+    tc_wgrad_rb_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
+                       const __grid_constant__ CUtensorMap tmDY, const WgRbParams q) {
+  const WgParams& p = q.w;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (wg_smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t nblk = p.Cout / 64;
+  const uint32_t b_bytes = nblk * BLK_BYTES;
+  const uint32_t a_bytes = (uint32_t)q.max_boxes * q.rb_bytes;
+  const uint32_t a_base = base + p.b_slots * b_bytes;
+  const uint32_t ctrl = a_base + p.a_slots * a_bytes;
+  auto afull = [&](int s) { return ctrl + 8u * s; };
+  auto aempty = [&](int s) { return ctrl + 8u * (p.a_slots + s); };
+  auto bfull = [&](int s) { return ctrl + 8u * (2 * p.a_slots + s); };
+  auto bempty = [&](int s) { return ctrl + 8u * (2 * p.a_slots + p.b_slots + s); };
+  const uint32_t tfull = ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots);
+  const uint32_t tmem_slot = tfull + 8u;
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(smem_raw + (tmem_slot - wg_smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_slots; s++) {
+      wg_mbar_init(afull(s), 1);
+      wg_mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < p.b_slots; s++) {
+      wg_mbar_init(bfull(s), 1);
+      wg_mbar_init(bempty(s), 1);
+    }
+    wg_mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDY) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_p;
+
+  const int mg = blockIdx.x % p.n_mgroups;
+  const int z = blockIdx.x / p.n_mgroups;
+  const int mt0 = (int)(((long long)mg * p.n_mtiles) / p.n_mgroups);
+  const int mt1 = (int)(((long long)(mg + 1) * p.n_mtiles) / p.n_mgroups);
+  const int pt0 = (int)(((long long)z * p.n_ptiles) / p.zsplit);
+  const int pt1 = (int)(((long long)(z + 1) * p.n_ptiles) / p.zsplit);
+  const int cblocks = p.Cin / 64;
+  // units [u_lo, u_hi) of this CTA; box id of a unit = (filter row, channel block); boxes are numbered in order of
+  // first use, which is ascending because units ascend in (tap, cb) order
+  const int u_lo = 2 * mt0;
+  const int u_hi = min(2 * mt1, p.units);
+  auto box_of = [&](int u) {                       // index into this CTA's box list
+    const int tap = u / cblocks, cb = u - tap * cblocks;
+    const int r = tap / p.kw;
+    const int tap0 = u_lo / cblocks;
+    const int r0 = tap0 / p.kw;
+    return (r - r0) * cblocks + cb;                // rows r0.. each with cblocks boxes (some unused at the ends)
+  };
+  const int r_first = (u_lo / cblocks) / p.kw;
+  const int r_last = ((u_hi - 1) / cblocks) / p.kw;
+  const int n_boxes = (r_last - r_first + 1) * cblocks;
+  const uint32_t box_bytes = (uint32_t)(128 + p.kw - 1) * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int pt = pt0; pt < pt1; pt++) {
+        const int ox0 = (pt % p.tiles_x) * 128;
+        const int oy0 = (pt / p.tiles_x) % p.tiles_y;
+        const int n0 = pt / (p.tiles_x * p.tiles_y);
+        wg_wait(bempty(bs), bph ^ 1);
+        wg_expect_tx(bfull(bs), b_bytes);
+        for (uint32_t j = 0; j < nblk; j++)
+          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), j * 64, ox0, oy0, n0);
+        if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+        wg_wait(aempty(as), aph ^ 1);
+        wg_expect_tx(afull(as), n_boxes * box_bytes);
+        for (int b = 0; b < n_boxes; b++) {
+          const int r = r_first + b / cblocks, cb = b % cblocks;
+          const int c = cb * 64;
+          const uint32_t dst = a_base + as * a_bytes + b * q.rb_bytes;
+          if (c < p.C1)
+            wg_tma_4d(&tmX, dst, afull(as), c, ox0 - p.pad, oy0 - p.pad + r, n0);
+          else
+            wg_tma_4d(&tmX2, dst, afull(as), c - p.C1, ox0 - p.pad, oy0 - p.pad + r, n0);
+        }
+        if (++as == p.a_slots) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int pt = pt0; pt < pt1; pt++) {
+        wg_wait(bfull(bs), bph);
+        wg_wait(afull(as), aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t b_addr = base + bs * b_bytes;
+        const uint32_t a_addr = a_base + as * a_bytes;
+        for (int mt = mt0; mt < mt1; mt++) {
+          int u0 = 2 * mt, u1 = 2 * mt + 1;
+          if (u1 >= p.units) u1 = u0;                                  // odd tail: rows 64..127 are ignored
+          const int s0 = (u0 / cblocks) % p.kw, s1 = (u1 / cblocks) % p.kw;
+          const uint32_t ad0 = a_addr + box_of(u0) * q.rb_bytes + s0 * 128;
+          const uint32_t ad1 = a_addr + box_of(u1) * q.rb_bytes + s1 * 128;
+          const uint32_t lbo = ad1 - ad0;                              // >= 0: units ascend with the box order
+          const uint32_t d_tmem = tmem_base + (mt - mt0) * p.Cout;
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) {
+            const uint64_t ad = umma_desc_mn_sw128(ad0 + kk * 2048, lbo);
+            const uint64_t bd = umma_desc_mn_sw128(b_addr + kk * 2048, BLK_BYTES);
+            wg_mma(d_tmem, ad, bd, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        wg_commit(aempty(as));
+        wg_commit(bempty(bs));
+        if (++as == p.a_slots) { as = 0; aph ^= 1; }
+        if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+      }
+      wg_commit(tfull);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    if (pt1 > pt0) {
+      wg_wait(tfull, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int mt = mt0; mt < mt1; mt++) {
+        const int k = mt * 128 + row;
+        const bool valid = k < p.units * 64;
+        float* dst = p.dw + (size_t)k * p.Cout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (mt - mt0) * p.Cout;
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+          uint32_t v[32];
+          wg_ld32(taddr + c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -349,6 +521,58 @@ extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, 
   if (rc) {
     set_error("hm_tc_wgrad: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
     return HM_ERR_CUDA;
+  }
+  // Row-box variant when the pixel tiles are row segments and the filter has several taps per row
+  static int rb_enabled = -1;
+  if (rb_enabled < 0) {
+    const char* e = getenv("HMGAN_TC_ROWBOX");
+    rb_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (rb_enabled && p.bw == 128 && p.bh == 1 && p.bn == 1 && d->kw > 1 && d->kw <= 9) {
+    WgRbParams q;
+    q.w = p;
+    q.rb_bytes = (((128 + d->kw - 1) * 128) + 1023) / 1024 * 1024;
+    const int cblocks = p.Cin / 64;
+    // worst case over m-groups of (filter rows spanned) * cblocks
+    int max_boxes = 0;
+    for (int mg = 0; mg < p.n_mgroups; mg++) {
+      const int mt0 = (int)(((long long)mg * p.n_mtiles) / p.n_mgroups);
+      const int mt1 = (int)(((long long)(mg + 1) * p.n_mtiles) / p.n_mgroups);
+      const int u_lo = 2 * mt0, u_hi = (2 * mt1 < p.units ? 2 * mt1 : p.units);
+      if (u_hi <= u_lo) continue;
+      const int r0 = (u_lo / cblocks) / d->kw, r1 = ((u_hi - 1) / cblocks) / d->kw;
+      const int nb = (r1 - r0 + 1) * cblocks;
+      if (nb > max_boxes) max_boxes = nb;
+    }
+    q.max_boxes = max_boxes;
+    const size_t a_rb = (size_t)max_boxes * q.rb_bytes;
+    q.w.b_slots = 2;
+    int a_sl = (int)((227 * 1024 - 4096 - (size_t)q.w.b_slots * b_bytes) / a_rb);
+    if (a_sl > 3) a_sl = 3;
+    if (a_sl >= 2) {
+      q.w.a_slots = a_sl;
+      CUtensorMap rX, rX2;
+      rc = wg_encode_act(&rX, x1, d->B, d->H, d->W, d->C1, 128 + d->kw - 1, 1, 1);
+      if (!rc && d->C2) rc = wg_encode_act(&rX2, x2, d->B, d->H, d->W, d->C2, 128 + d->kw - 1, 1, 1);
+      if (!d->C2) rX2 = rX;
+      if (rc) {
+        set_error("hm_tc_wgrad: cuTensorMapEncodeTiled failed for the row box (CUresult %d)", rc);
+        return HM_ERR_CUDA;
+      }
+      const size_t smem_rb = (size_t)q.w.b_slots * b_bytes + (size_t)q.w.a_slots * a_rb + 1024 + 1024;
+      static bool rb_attr = false;
+      if (!rb_attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+          set_error("hm_tc_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+          return HM_ERR_CUDA;
+        }
+        rb_attr = true;
+      }
+      tc_wgrad_rb_kernel<<<p.n_mgroups * p.zsplit, WG_THREADS, smem_rb, (cudaStream_t)stream>>>(rX, rX2, tmDY, q);
+      HM_CHECK_LAUNCH("hm_tc_wgrad(row box)");
+      return HM_OK;
+    }
   }
   const size_t smem = (size_t)p.b_slots * b_bytes + (size_t)p.a_slots * a_bytes + 1024 + 1024;
   static bool attr_set = false;
