@@ -296,6 +296,19 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
         val += w[(((size_t)co * cin + ci) * 5 + (4 - r)) * 5 + (4 - s)];
       }
     }
+  } else if (mode == 12) {
+    // input gradient of a 3x3 stride-2 pad-1 convolution as a 2x2-tap convolution of dy with N = (phase, ci):
+    // Wt[(dy*2+dx)][phase*cin+ci][co] = W[co][ci][2-r][2-s], r = r(py,dy), s = r(px,dx) with r(0,0)=1, r(1,0)=2, r(1,1)=0;
+    // (py,dy) = (0,1) has no tap -> 0.   (K-major tcgen05 pack, K = co)
+    int co = (int)(i % cout);
+    long long k = i / cout;
+    int nn = (int)(k % (4 * cin));
+    int tap = (int)(k / (4 * cin));
+    int ph = nn / cin, ci = nn - ph * cin;
+    int py = ph >> 1, px = ph & 1, dy_ = tap >> 1, dx_ = tap & 1;
+    int r = py == 0 ? (dy_ == 0 ? 1 : -1) : (dy_ == 0 ? 2 : 0);
+    int s = px == 0 ? (dx_ == 0 ? 1 : -1) : (dx_ == 0 ? 2 : 0);
+    val = (r >= 0 && s >= 0) ? w[(((size_t)co * cin + ci) * 3 + (2 - r)) * 3 + (2 - s)] : 0.f;
   } else if (mode == 11) {
     // one-channel-input convolution as a 1x1 convolution over the im2col tensor (hm_im2col_c1):
     // Wt[co][t] = W[co][0][kh-1-r][kw-1-s] for tap t = r*kw+s < kh*kw, 0 up to 64   (K-major, K = 64)
@@ -436,12 +449,14 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
   long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
   if (mode == 8) n = 36LL * cout * cin;
   if (mode == 11) n = 64LL * cout;
+  if (mode == 12) n = 16LL * cout * cin;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)

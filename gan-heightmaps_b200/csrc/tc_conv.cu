@@ -33,6 +33,7 @@ struct TcParams {
   int B, Ho, Wo;           // output grid
   int Cin, C1, Cout;       // K per tap (C1 from source 1, Cin-C1 from source 2), total N
   int kh, kw, pad;
+  int stride;              // 1, or 2 (forward only: the A box is loaded with TMA element strides of 2)
   int bw, bh, bn;          // pixel box of one M tile
   int tiles_x, tiles_y, tiles_n, n_mtiles;
   int ntile, n_ntiles;     // N tile (<=256, multiple of 16)
@@ -216,8 +217,21 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
           const int ph = gc / p.cph, co = gc - ph * p.cph;
           const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
           uint32_t packed[16];
-          epi_pack32<ACT>(v, bias_t + c0, p.slope, packed);
           uint4* d4 = reinterpret_cast<uint4*>(p.y + op * p.cph + co);
+          if (p.accumulate & 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint4 pv = d4[j];
+              const uint32_t w4[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&w4[k]));
+                v[j * 8 + 2 * k] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * k]) + pf.x);
+                v[j * 8 + 2 * k + 1] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * k + 1]) + pf.y);
+              }
+            }
+          }
+          epi_pack32<ACT>(v, bias_t + c0, p.slope, packed);
 #pragma unroll
           for (int j = 0; j < 4; j++)
             d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
@@ -228,7 +242,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
             if (col < 4 * p.cph) {
               const int ph = col / p.cph, co = col - ph * p.cph;
               const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
-              p.y[op * p.cph + co] = __float2half_rn(act_t<ACT>(__uint_as_float(v[j]) + bias_t[c0 + j], p.slope));
+              float a = __uint_as_float(v[j]) + bias_t[c0 + j];
+              if (p.accumulate & 1) a += __half2float(p.y[op * p.cph + co]);
+              p.y[op * p.cph + co] = __float2half_rn(act_t<ACT>(a, p.slope));
             }
           }
         }
@@ -374,10 +390,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int c = cc * KCH;
             for (int i = 0; i < nv; i++) {
               if (c < p.C1)
-                tma_load_4d(&tmA, sa + i * A_BYTES, full_bar(stage), c, ox0[i] - p.pad + s, oy0[i] - p.pad + r, n0[i]);
+                tma_load_4d(&tmA, sa + i * A_BYTES, full_bar(stage), c, ox0[i] * p.stride - p.pad + s,
+                            oy0[i] * p.stride - p.pad + r, n0[i]);
               else
-                tma_load_4d(&tmA2, sa + i * A_BYTES, full_bar(stage), c - p.C1, ox0[i] - p.pad + s,
-                            oy0[i] - p.pad + r, n0[i]);
+                tma_load_4d(&tmA2, sa + i * A_BYTES, full_bar(stage), c - p.C1, ox0[i] * p.stride - p.pad + s,
+                            oy0[i] * p.stride - p.pad + r, n0[i]);
             }
             tma_load_3d(&tmB, sa + a_bytes, full_bar(stage), c, nt * p.ntile, tap);
             if (++stage == p.stages) {
@@ -635,11 +652,13 @@ static inline int pow2_floor(int v) {
 }
 
 // NHWC fp16 activation tensor [B,H,W,C], box {64, bw, bh, bn}
-static int encode_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn) {
+static int encode_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn,
+                      int stride = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  // with element strides the box is given in traversed source elements: bw*stride of them yield bw loaded pixels
+  cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -681,11 +700,29 @@ static bool is_up2conv(const HmConvDesc* d) {
          (d->Cout % 32 == 0 || d->Cout <= 4);
 }
 
+// input gradient of a 3x3 stride-2 pad-1 convolution (descriptor in hm_conv_gather's transposed form): evaluated as a
+// 2x2-tap convolution of dy on ITS grid with N = (input-pixel phase, ci) and the depth-to-space epilogue; w_tc is pack
+// mode 12 (taps the phase does not use are zero)
+static bool is_dgrad_s2(const HmConvDesc* d) {
+  return d->transposed == 1 && d->stride == 2 && d->kh == 3 && d->kw == 3 && d->pad == 1 && !d->up &&
+         d->Ho == 2 * d->H && d->Wo == 2 * d->W;
+}
+
 extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   if (!d) return 0;
   if (d->dtype == HM_F16 && is_up2conv(d))
     return d->C1 % KCH == 0 && d->C1 > 0 && d->os == 1 && !d->ou && !d->ov && d->oH == d->Ho && d->oW == d->Wo;
-  if (d->dtype != HM_F16 || d->transposed || d->up || d->stride != 1) return 0;
+  if (d->dtype == HM_F16 && is_dgrad_s2(d))
+    return d->C1 % KCH == 0 && d->C1 > 0 && d->C2 == 0 && d->os == 1 && !d->ou && !d->ov && d->oH == d->Ho &&
+           d->oW == d->Wo && d->split == d->Cout && (d->Cout % 32 == 0 || d->Cout <= 4);
+  if (d->dtype != HM_F16 || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
+  if (d->stride == 2) {
+    if (d->Ho != (d->H + 2 * d->pad - d->kh) / 2 + 1 || d->Wo != (d->W + 2 * d->pad - d->kw) / 2 + 1) return 0;
+    if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
+    if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
+    if (d->Cout < 1 || pick_ntile(d->Cout, d->split) == 0) return 0;
+    return d->oH == d->Ho && d->oW == d->Wo;
+  }
   if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
   if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
   if (d->Cout < 1 || pick_ntile(d->Cout, d->split) == 0) return 0;
@@ -708,17 +745,19 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     return HM_ERR_CUDA;
   }
   if ((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc) & 15) ||
-      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15)) || (is_up2conv(d) && !y)) {
+      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15)) || ((is_up2conv(d) || is_dgrad_s2(d)) && !y)) {
     set_error("hm_tc_conv: pointers must be 16-byte aligned");
     return HM_ERR_ALIGN;
   }
   TcParams p;
-  const bool up2 = is_up2conv(d);
+  const bool dg2 = is_dgrad_s2(d);
+  const bool up2 = is_up2conv(d) || dg2;                                  // both use the phase / depth-to-space form
   p.d2s = up2 ? 1 : 0;
   p.cph = d->Cout;
+  p.stride = (!up2 && d->stride == 2) ? 2 : 1;
   p.B = d->B; p.Ho = up2 ? d->H : d->Ho; p.Wo = up2 ? d->W : d->Wo;       // tile grid (low-res when phase-decomposed)
   p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = up2 ? 4 * d->Cout : d->Cout;
-  p.kh = up2 ? 3 : d->kh; p.kw = up2 ? 3 : d->kw; p.pad = up2 ? 1 : d->pad;
+  p.kh = dg2 ? 2 : (up2 ? 3 : d->kh); p.kw = dg2 ? 2 : (up2 ? 3 : d->kw); p.pad = dg2 ? 0 : (up2 ? 1 : d->pad);
   p.bw = pow2_floor(p.Wo < TILE_M ? p.Wo : TILE_M);
   p.bh = pow2_floor(p.Ho < TILE_M / p.bw ? p.Ho : TILE_M / p.bw);
   p.bn = TILE_M / (p.bw * p.bh);
@@ -743,8 +782,8 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.split = up2 ? p.Cout : d->split; p.accumulate = d->accumulate;
 
   CUtensorMap tmA, tmA2, tmB;
-  int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn);
-  if (!rc) rc = d->C2 ? encode_act(&tmA2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn) : 0;
+  int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn, p.stride);
+  if (!rc) rc = d->C2 ? encode_act(&tmA2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn, p.stride) : 0;
   if (!d->C2) tmA2 = tmA;
   if (!rc) rc = encode_wgt(&tmB, w_tc, p.kh * p.kw, p.Cout, p.Cin, p.ntile);
   if (rc) {
@@ -757,7 +796,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     const char* e = getenv("HMGAN_TC_ROWBOX");
     rb_enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (rb_enabled && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
+  if (rb_enabled && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
     p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;
     {
       const char* e = getenv("HMGAN_RB_MODE");

@@ -27,7 +27,7 @@ constexpr int BLK_BYTES = 128 * 64 * 2;     // one [128 pixel][64 channel] fp16 
 struct WgParams {
   int B, Ho, Wo;
   int Cin, C1, Cout;
-  int kh, kw, pad;
+  int kh, kw, pad, stride;
   int bw, bh, bn, tiles_x, tiles_y, tiles_n, n_ptiles;
   int units;            // 64-row blocks of the (tap, ci) axis = kh*kw*Cin/64
   int n_mtiles;         // ceil(units/2)
@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
             const int c = cb * 64;
             const uint32_t dst = a_base + as * a_bytes + h * BLK_BYTES;
             if (c < p.C1)
-              wg_tma_4d(&tmX, dst, afull(as), c, ox0 - p.pad + s, oy0 - p.pad + r, n0);
+              wg_tma_4d(&tmX, dst, afull(as), c, ox0 * p.stride - p.pad + s, oy0 * p.stride - p.pad + r, n0);
             else
-              wg_tma_4d(&tmX2, dst, afull(as), c - p.C1, ox0 - p.pad + s, oy0 - p.pad + r, n0);
+              wg_tma_4d(&tmX2, dst, afull(as), c - p.C1, ox0 * p.stride - p.pad + s, oy0 * p.stride - p.pad + r, n0);
           }
           if (++as == p.a_slots) { as = 0; aph ^= 1; }
         }
@@ -437,11 +437,12 @@ static EncodeTiledFn wg_encode_fn() {
   }
   return fn;
 }
-static int wg_encode_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn) {
+static int wg_encode_act(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bn,
+                         int stride = 1) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = wg_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -459,11 +460,12 @@ using namespace hm;
 
 extern "C" int hm_tc_wgrad_supported(const HmConvDesc* d) {
   if (!d) return 0;
-  if (d->dtype != HM_F16 || d->transposed || d->up || d->stride != 1) return 0;
+  if (d->dtype != HM_F16 || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
   if (d->os != 1 || d->ou || d->ov) return 0;
   if (d->C1 % 64 || d->C2 % 64 || d->C1 <= 0) return 0;
   if (d->Cout % 64 || d->Cout > 256 || d->Cout <= 0) return 0;
-  if (d->Ho != d->H + 2 * d->pad - d->kh + 1 || d->Wo != d->W + 2 * d->pad - d->kw + 1) return 0;
+  if (d->Ho != (d->H + 2 * d->pad - d->kh) / d->stride + 1 || d->Wo != (d->W + 2 * d->pad - d->kw) / d->stride + 1)
+    return 0;
   if (d->oH != d->Ho || d->oW != d->Wo) return 0;
   return 1;
 }
@@ -487,7 +489,7 @@ extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, 
   WgParams p;
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
   p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = d->Cout;
-  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad;
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
   p.bw = wg_pow2_floor(d->Wo < 128 ? d->Wo : 128);
   p.bh = wg_pow2_floor(d->Ho < 128 / p.bw ? d->Ho : 128 / p.bw);
   p.bn = 128 / (p.bw * p.bh);
@@ -514,8 +516,8 @@ extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, 
   p.a_slots = a_slots;
   p.dw = dw;
   CUtensorMap tmX, tmX2, tmDY;
-  int rc = wg_encode_act(&tmX, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn);
-  if (!rc && d->C2) rc = wg_encode_act(&tmX2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn);
+  int rc = wg_encode_act(&tmX, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn, p.stride);
+  if (!rc && d->C2) rc = wg_encode_act(&tmX2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn, p.stride);
   if (!d->C2) tmX2 = tmX;
   if (!rc) rc = wg_encode_act(&tmDY, dy, d->B, d->Ho, d->Wo, d->Cout, p.bw, p.bh, p.bn);
   if (rc) {
@@ -528,7 +530,7 @@ extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, 
     const char* e = getenv("HMGAN_TC_ROWBOX");
     rb_enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (rb_enabled && p.bw == 128 && p.bh == 1 && p.bn == 1 && d->kw > 1 && d->kw <= 9) {
+  if (rb_enabled && d->stride == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 && d->kw > 1 && d->kw <= 9) {
     WgRbParams q;
     q.w = p;
     q.rb_bytes = (((128 + d->kw - 1) * 128) + 1023) / 1024 * 1024;

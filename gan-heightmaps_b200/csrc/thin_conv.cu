@@ -325,27 +325,33 @@ __global__ void __launch_bounds__(256) thin_out_wgrad_kernel(HmConvDesc d, const
 // im2col of a ONE-channel image: Xc[p][t] = x[p + tap t - pad] (t < kh*kw), 0 for the padding taps up to 64.
 // A 1->Cout kxk convolution is then the 1x1 convolution Xc[.,64] x Wt[Cout][64] (forward) and its weight
 // gradient the GEMM Xc^T dy, both on the tcgen05 kernels.  One thread = one pixel x 8 taps (16-byte store).
-__global__ void im2col_c1_kernel(const __half* __restrict__ x, __half* __restrict__ xc, int B, int H, int W, int kh,
-                                 int kw, int pad) {
-  const long long total = (long long)B * H * W * 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 7);
-    long long pix = i >> 3;
-    const int ox = (int)(pix % W);
-    long long t2 = pix / W;
-    const int oy = (int)(t2 % H);
-    const int n = (int)(t2 / H);
-    float v[8];
+__global__ void __launch_bounds__(256) im2col_c1_kernel(const __half* __restrict__ x, __half* __restrict__ xc, int B,
+                                                        int H, int W, int kh, int kw, int pad) {
+  // a thread always serves the same 8 taps (grid stride is a multiple of 8): decode them once
+  const int g = threadIdx.x & 7;
+  int dr[8], ds[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int t = g * 8 + j;
+    dr[j] = t < kh * kw ? t / kw - pad : (1 << 20);          // out-of-range marker: never inside the image
+    ds[j] = t < kh * kw ? t % kw - pad : 0;
+  }
+  const unsigned total = (unsigned)B * H * W;                  // pixels (< 2^31 for every supported size)
+  const unsigned step = (gridDim.x * blockDim.x) >> 3;
+  unsigned pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  for (; pix < total; pix += step) {
+    const unsigned ox = pix % W;
+    const unsigned t2 = pix / W;
+    const unsigned oy = t2 % H;
+    const __half* img = x + (size_t)(t2 - oy) * W;             // start of this image
+    uint4 out;
+    __half* o = reinterpret_cast<__half*>(&out);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int t = g * 8 + j;
-      const int r = t / kw, s = t - r * kw;
-      const int iy = oy - pad + r, ix = ox - pad + s;
-      v[j] = (t < kh * kw && iy >= 0 && iy < H && ix >= 0 && ix < W)
-                 ? __half2float(x[((size_t)n * H + iy) * W + ix]) : 0.f;
+      const int iy = (int)oy + dr[j], ix = (int)ox + ds[j];
+      o[j] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[iy * W + ix] : __float2half(0.f);
     }
-    store8(xc + (size_t)pix * 64 + g * 8, v);
+    *reinterpret_cast<uint4*>(xc + (size_t)pix * 64 + g * 8) = out;
   }
 }
 

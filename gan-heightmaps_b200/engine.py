@@ -151,12 +151,18 @@ class ConvOp(object):
         self.wt_f = self.wt_d = self.x1u = self.x2u = None
         rt = net.rt
         self.up2 = False      # nearest-2x + 5x5 evaluated as four 3x3 phase convolutions on the low-res source
-        if rt.precision == "fast" and kind == "conv" and self.stride == 1:
-            if self.up == _lib.UP_NEAREST2 and self.x2 is None:
+        self.dg2 = False      # input gradient of a 3x3 stride-2 conv as a 2x2-tap phase convolution of dy (pack mode 12)
+        if rt.precision == "fast" and kind == "conv" and self.stride in (1, 2):
+            if self.up == _lib.UP_NEAREST2 and self.x2 is None and self.stride == 1:
                 self.up2 = bool(_lib.query("hm_tc_conv_supported", C.byref(self._fwd_desc(rt, 1))))
             self.tc_fwd = self.up2 or bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
-            self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
+            if self.stride == 1:
+                self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
+            elif not self.up and self.x2 is None:
+                dd = self._dgrad_desc(rt, 1, 0)
+                dd.split = dd.Cout
+                self.tc_dg = self.dg2 = bool(_lib.query("hm_tc_conv_supported", C.byref(dd)))
         # one-channel input (first discriminator layer): im2col to 64 "tap channels", then a 1x1 tensor-core GEMM
         self.col1 = (rt.precision == "fast" and kind == "conv" and self.Cin == 1 and self.x2 is None and not self.up
                      and self.stride == 1 and self.kh * self.kw <= 64 and 2 * self.pad == self.kh - 1
@@ -186,7 +192,7 @@ class ConvOp(object):
         if self.tc_fwd and self.wt_f is None:
             self.wt_f = rt.empty((36 * self.Cin * self.Cout if self.up2 else n,))
         if self.tc_dg and self.wt_d is None:
-            self.wt_d = rt.empty((n,))
+            self.wt_d = rt.empty((16 * self.Cin * self.Cout if self.dg2 else n,))
         self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient of the thin phase-decomposed layer
         if self.thin_up2_wg:
             # tensor cores: s2d(dy) zero-padded to 64 channels against the low-res source (3x3 taps)
@@ -216,8 +222,8 @@ class ConvOp(object):
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 7 if self.fw_dg else 1, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
             else:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 6, self.Cout, self.Cin, self.kh, self.kw,
-                        0, 0, rt.cd)
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 12 if self.dg2 else 6, self.Cout, self.Cin,
+                        self.kh, self.kw, 0, 0, rt.cd)
         else:
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -424,7 +430,7 @@ class ConvOp(object):
             y1 = _ptr(self.x1.g(lo, hi)) if t1 else None
             y2 = _ptr(self.x2.g(lo, hi)) if t2 else None
             if self.tc_dg:
-                d = self._tc_dgrad_desc(rt, n, acc)
+                d = self._dgrad_desc(rt, n, acc) if self.dg2 else self._tc_dgrad_desc(rt, n, acc)
                 rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, y1, y2)
             else:
                 d = self._tc_dgrad_desc(rt, n, acc) if self.fw_dg else self._dgrad_desc(rt, n, acc)

@@ -148,6 +148,8 @@ int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, 
  *  mode 6: Conv2DLayer W, tcgen05 input-gradient pack     -> Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
  *          (the input gradient of a stride-1 'same' convolution is the forward correlation of dy with this
  *           pack and pad' = k-1-pad)
+ *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, mode 12: input
+ *          gradient of a 3x3 stride-2 convolution as a 2x2-tap phase convolution of dy (see csrc/simt_conv.cu)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)
  * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the

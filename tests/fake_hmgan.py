@@ -164,6 +164,16 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     for s_ in range(5):
                         dy_, dx_ = (py + r - 2) // 2 + 1, (px + s_ - 2) // 2 + 1
                         out[dy_, dx_, py * 2 + px] += Wc[:, :, r, s_]
+    elif mode == 12:
+        Wc = W.reshape(cout, cin, 3, 3)[:, :, ::-1, ::-1]                     # correlation taps Wc[co][ci][r][s]
+        out = np.zeros((2, 2, 4, cin, cout), np.float32)
+        rmap = {(0, 0): 1, (1, 0): 2, (1, 1): 0}
+        for py in range(2):
+            for px in range(2):
+                for dy_ in range(2):
+                    for dx_ in range(2):
+                        if (py, dy_) in rmap and (px, dx_) in rmap:
+                            out[dy_, dx_, py * 2 + px] = Wc[:, :, rmap[(py, dy_)], rmap[(px, dx_)]].T
     elif mode == 11:
         Wc = W.reshape(cout, kh * kw)[:, ::-1]                    # flipped taps, row-major (r, s)
         out = np.zeros((cout, 64), np.float32)
@@ -449,7 +459,24 @@ def _is_up2conv(d):
             (d.Cout % 32 == 0 or d.Cout <= 4))
 
 
+def _is_dgrad_s2(d):
+    return (d.transposed == 1 and d.stride == 2 and d.kh == 3 and d.kw == 3 and d.pad == 1 and not d.up and
+            d.Ho == 2 * d.H and d.Wo == 2 * d.W)
+
+
 def _tc_ok(d, wgrad):
+    if not wgrad and d.dtype == F16 and _is_dgrad_s2(d):
+        return (d.C1 % 64 == 0 and d.C1 > 0 and d.C2 == 0 and d.os == 1 and not d.ou and not d.ov and d.oH == d.Ho
+                and d.oW == d.Wo and d.split == d.Cout and (d.Cout % 32 == 0 or d.Cout <= 4))
+    if d.stride == 2 and not d.transposed and not d.up and d.dtype == F16:
+        ok = d.os == 1 and not d.ou and not d.ov and d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0
+        ok = ok and d.Ho == (d.H + 2 * d.pad - d.kh) // 2 + 1 and d.Wo == (d.W + 2 * d.pad - d.kw) // 2 + 1
+        ok = ok and d.oH == d.Ho and d.oW == d.Wo
+        if wgrad:
+            return ok and d.Cout % 64 == 0 and 0 < d.Cout <= 256
+        if d.Cout % 16 or d.split % 16:
+            return ok and d.split == d.Cout and 0 < d.Cout <= 256
+        return ok and 0 < d.split <= d.Cout
     if not wgrad and d.dtype == F16 and _is_up2conv(d):
         return d.C1 % 64 == 0 and d.C1 > 0 and d.os == 1 and not d.ou and not d.ov and d.oH == d.Ho and d.oW == d.Wo
     ok = d.dtype == F16 and not d.transposed and not d.up and d.stride == 1 and d.os == 1 and not d.ou and not d.ov
@@ -479,6 +506,18 @@ def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
             out = out + _t(_a(bias, Co, np.float32))
         out = _act(out, d.act, d.slope)
         _a(y, B * 4 * H * W * Co, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+        return 0
+    if _is_dgrad_s2(d):
+        # 2x2-tap convolution of dy on its own grid with N = (phase, ci), then depth-to-space (pack mode 12)
+        B, H, W, Co, Ci = d.B, d.H, d.W, d.C1, d.Cout
+        g = _t(_a(x1, B * H * W * Co, np.float16)).reshape(B, H, W, Co).permute(0, 3, 1, 2)
+        wt = _t(_a(w_tc, 16 * Co * Ci, np.float16)).reshape(2, 2, 4 * Ci, Co)
+        out = F.conv2d(F.pad(g, (0, 1, 0, 1)), wt.permute(2, 3, 0, 1).contiguous())           # [B,4Ci,H,W]
+        out = out.reshape(B, 2, 2, Ci, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B, 2 * H, 2 * W, Ci)
+        dst = _a(y, B * 4 * H * W * Ci, np.float16)
+        if d.accumulate & 1:
+            out = out + _t(dst).reshape(out.shape)
+        dst[:] = out.numpy().reshape(-1).astype(np.float16)
         return 0
     Ct = d.C1 + d.C2
     wt = _a(w_tc, d.kh * d.kw * Ct * d.Cout, np.float16).reshape(d.kh * d.kw, d.Cout, Ct)

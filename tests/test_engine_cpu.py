@@ -207,3 +207,39 @@ def test_fast_mode_lowering_uses_tensor_core_kernels_where_eligible(cpu_backend,
     assert calls.get("hm_tc_conv", 0) >= 10 and calls.get("hm_tc_wgrad", 0) >= 6, calls
     paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
     assert "tcgen05" in paths and "simt" in paths
+
+
+def test_fast_mode_stride2_layers_route_to_tensor_cores(cpu_backend, monkeypatch):
+    """pix2pix encoder / PatchGAN 3x3 stride-2 convolutions with 64-multiple channels: forward and weight gradient
+    through hm_tc_conv / hm_tc_wgrad with TMA element strides, input gradient as the 2x2-tap phase convolution
+    (pack mode 12).  A two-level U-Net-like chain is checked against the float32 oracle ops."""
+    import lasagne_compat as LC
+    import engine
+    from oracle import lasagne_ops as LO
+    r = np.random.RandomState(0)
+    inp = LC.InputLayer((None, 64, 16, 16))
+    c1 = LC.Conv2DLayer(inp, 128, 3, stride=2, pad='same', nonlinearity=LC.linear)
+    a1 = LC.NonlinearityLayer(c1, LC.leaky_rectify)
+    c2 = LC.Conv2DLayer(a1, 64, 3, stride=2, pad='same', nonlinearity=LC.linear)
+    rt = engine.Runtime("cpu", "fast", loss_scale=1.0)
+    net = engine.Net(rt, c2, name="s2", rng=r)
+    ops = [op for op in net.ops if isinstance(op, engine.ConvOp)]
+    assert all(op.tc_fwd and op.tc_wg for op in ops) and ops[1].dg2
+    x = r.randn(2, 64, 16, 16).astype(np.float32)
+    net.ensure(2)
+    net.inputs[0].buf.copy_(torch.from_numpy(x.transpose(0, 2, 3, 1)).half())
+    out = net.forward(2)
+    W1, b1, W2, b2 = [torch.tensor(v) for v in net.get_all_param_values()]
+    xt = torch.tensor(x, requires_grad=True)
+    W1.requires_grad_(True), W2.requires_grad_(True)
+    ref = LO.conv2d(LO.leaky_rectify(LO.conv2d(xt, W1, b1, 2, "same"), 0.01), W2, b2, 2, "same")
+    np.testing.assert_allclose(out.float().numpy(), ref.detach().permute(0, 2, 3, 1).numpy(), rtol=2e-2, atol=2e-2)
+    gy = r.randn(*ref.shape).astype(np.float32)
+    ref.backward(torch.tensor(gy))
+    net.out.grad.copy_(torch.from_numpy(gy.transpose(0, 2, 3, 1)).half())
+    net.backward(0, 2, wgrad=True)
+    g = net.get_grads()
+    # relative L2 error: a handful of leaky-rectify inputs within fp16 rounding of zero change sign between the two
+    # runs, which moves single terms of a weight gradient (max-norm comparisons would see those)
+    for a, b in ((g[0], W1.grad.numpy()), (g[2], W2.grad.numpy())):
+        assert np.linalg.norm((a - b).ravel()) <= 2e-2 * np.linalg.norm(b.ravel())

@@ -30,3 +30,11 @@ def test_tc_up2conv_matches_simt_gather(case):
     (summed fp16 phase filters) against the gather through the virtual upsampling: 5e-3 of the output scale."""
     rel, line = tc_probe.run_up2_case(*case)
     assert rel <= 5e-3, line
+
+
+@pytest.mark.parametrize("case", tc_probe.S2_CASES, ids=[c[0] for c in tc_probe.S2_CASES])
+def test_tc_stride2_conv_fwd_wgrad_dgrad(case):
+    """3x3 stride-2 convolutions (pix2pix encoder / PatchGAN): TMA element-stride forward and weight gradient,
+    phase-decomposed input gradient, each against the SIMT kernel on the same fp16 data (3e-3 of the scale)."""
+    rel, line = tc_probe.run_s2_case(*case)
+    assert rel <= 3e-3, line

@@ -124,6 +124,79 @@ def run_up2_case(name, B, H, W, Ci, Co, act):
     return float(err.max()) / scale, line
 
 
+S2_CASES = [
+    # name, B, H, W, C1, C2, Cout
+    ("s2_64_128_w32", 2, 32, 32, 64, 0, 128),
+    ("s2_128_256_w128", 1, 64, 128, 128, 0, 256),
+    ("s2_256_512_w16", 2, 16, 16, 256, 0, 512),
+    ("s2_64+64_64_w256", 1, 16, 256, 64, 64, 64),
+    ("s2_512_512_4x4", 4, 4, 4, 512, 0, 512),
+    ("s2_64_64_w20_ragged", 1, 12, 20, 64, 0, 64),
+]
+
+
+def run_s2_case(name, B, H, W, C1, C2, Co):
+    """3x3 stride-2 pad-1: tcgen05 forward / weight gradient / input gradient vs the SIMT kernels."""
+    torch.manual_seed(abs(hash(name)) % 1000 + 3)
+    Ct = C1 + C2
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    x1 = torch.randn(B, H, W, C1, device="cuda").half()
+    x2 = torch.randn(B, H, W, C2, device="cuda").half() if C2 else None
+    p2 = x2.data_ptr() if C2 else None
+    Wm = torch.randn(Co, Ct, 3, 3, device="cuda") / np.sqrt(9 * Ct)
+    bias = torch.randn(Co, device="cuda")
+    packs = {}
+    for mode, n in ((0, 9 * Ct * Co), (5, 9 * Ct * Co), (1, 9 * Ct * Co), (12, 16 * Ct * Co)):
+        packs[mode] = torch.empty(n, device="cuda", dtype=torch.float16)
+        _lib.call("hm_pack_conv_weight", Wm.data_ptr(), packs[mode].data_ptr(), mode, Co, Ct, 3, 3, 0, 0, 1, None)
+    d = desc(dtype=1, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=3, kw=3, stride=2, pad=1, transposed=0, Ho=Ho, Wo=Wo,
+             Cout=Co, oH=Ho, oW=Wo, os=1, ou=0, ov=0, split=Co, act=1, slope=0.01, accumulate=0)
+    lines = []
+    worst = 0.0
+    # forward
+    y_ref = torch.zeros(B, Ho, Wo, Co, device="cuda", dtype=torch.float16)
+    y_tc = torch.full((B, Ho, Wo, Co), 7.0, device="cuda", dtype=torch.float16)
+    _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, packs[0].data_ptr(), bias.data_ptr(), y_ref.data_ptr(),
+              None, None)
+    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, packs[5].data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None,
+              None)
+    # weight gradient
+    dy = torch.randn(B, Ho, Wo, Co, device="cuda").half()
+    g_ref = torch.zeros(9 * Ct, Co, device="cuda")
+    g_tc = torch.zeros(9 * Ct, Co, device="cuda")
+    _lib.call("hm_conv_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), g_ref.data_ptr(), None)
+    wg_ok = Co % 64 == 0 and Co <= 256
+    if wg_ok:
+        _lib.call("hm_tc_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), g_tc.data_ptr(), None)
+    torch.cuda.synchronize()
+    pairs = [("fwd", y_tc.float(), y_ref.float())]
+    if wg_ok:
+        pairs.append(("wgrad", g_tc, g_ref))
+    # input gradient (single source only; even sizes)
+    if C2 == 0 and H % 2 == 0 and W % 2 == 0:
+        dd = desc(dtype=1, B=B, H=Ho, W=Wo, C1=Co, C2=0, up=0, kh=3, kw=3, stride=2, pad=1, transposed=1, Ho=H, Wo=W,
+                  Cout=Ct, oH=H, oW=W, os=1, ou=0, ov=0, split=Ct, act=0, slope=0.0, accumulate=1)
+        init = torch.randn(B, H, W, Ct, device="cuda").half()
+        dx_ref, dx_tc = init.clone(), init.clone()
+        _lib.call("hm_conv_gather", C.byref(dd), dy.data_ptr(), None, packs[1].data_ptr(), None, dx_ref.data_ptr(), None,
+                  None)
+        _lib.call("hm_tc_conv", C.byref(dd), dy.data_ptr(), None, packs[12].data_ptr(), None, dx_tc.data_ptr(), None, None)
+        torch.cuda.synchronize()
+        pairs.append(("dgrad", dx_tc.float(), dx_ref.float()))
+    for what, a, b in pairs:
+        err = (a - b).abs()
+        scale = float(b.abs().max())
+        rel = float(err.max()) / scale
+        worst = max(worst, rel)
+        lines.append("s2 %-22s %-5s max_err %.4g scale %.4g rel %.3g frac_bad %.4f" % (
+            name, what, float(err.max()), scale, rel, float((err > 2e-2 * scale).float().mean())))
+        if rel > 5e-3 and what == "dgrad":
+            bad = err > 2e-2 * scale
+            lines.append("    bad by (y&1,x&1): %s" % [[round(float(bad[:, py::2, px::2].float().mean()), 3) for px in range(2)]
+                                                        for py in range(2)])
+    return worst, "\n".join(lines)
+
+
 WGRAD_CASES = [c for c in CASES if c[6] % 64 == 0 and c[6] <= 256]
 
 
@@ -191,6 +264,14 @@ def perf():
 if __name__ == "__main__":
     if sys.argv[1:] == ["perf"]:
         perf()
+        sys.exit(0)
+    if sys.argv[1:] == ["s2"]:
+        for c in S2_CASES:
+            try:
+                print(run_s2_case(*c)[1], flush=True)
+            except Exception as e:
+                print("s2 %-22s EXC %s" % (c[0], e), flush=True)
+                break
         sys.exit(0)
     if sys.argv[1:] == ["up2"]:
         for c in UP2_CASES:
