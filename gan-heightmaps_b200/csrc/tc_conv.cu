@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_slot = ctrl + 8u * (2 * p.stages + 4);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
-  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);     // [n_ntiles * ntile] (<= 1024) floats
+  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);     // [n_ntiles * ntile] (<= 2048) floats
   {
     const int ncols = p.n_ntiles * p.ntile;
     const int creal = p.d2s ? p.cph : p.Cout;
@@ -767,6 +767,10 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.n_mtiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.ntile = pick_ntile(p.Cout, up2 ? p.Cout : d->split);
   p.n_ntiles = (p.Cout + p.ntile - 1) / p.ntile;
+  if (p.n_ntiles * p.ntile > 2048) {
+    set_error("hm_tc_conv: more than 2048 GEMM columns (%d) are not supported", p.n_ntiles * p.ntile);
+    return HM_ERR_UNSUPPORTED;
+  }
   p.vec_store = (p.Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
   int S = 256 / p.ntile;                                   // 2 (double buffer) * S * ntile <= 512 TMEM columns
   if (S < 1) S = 1;
@@ -775,7 +779,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   p.S = S;
   p.n_super = (p.n_mtiles + S - 1) / S;
   const int stage_bytes = S * A_BYTES + p.ntile * 128;
-  int stages = (227 * 1024 - 6144) / stage_bytes;
+  int stages = (227 * 1024 - 10240) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y; p.y2 = (__half*)y2;
@@ -803,7 +807,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       p.rb_mode = e ? atoi(e) : 0;
     }
     p.a_slots = (S * p.rb_bytes > 40 * 1024) ? 2 : 3;
-    int b_slots = (227 * 1024 - 6144 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
+    int b_slots = (227 * 1024 - 10240 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
     if (b_slots > 8) b_slots = 8;
     if (b_slots >= 2) {
       p.b_slots = b_slots;
@@ -815,7 +819,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
         set_error("hm_tc_conv: cuTensorMapEncodeTiled failed for the row box (CUresult %d)", rc);
         return HM_ERR_CUDA;
       }
-      const size_t smem_rb = (size_t)p.a_slots * S * p.rb_bytes + (size_t)p.b_slots * p.ntile * 128 + 1024 + 1024 + 4096;
+      const size_t smem_rb = (size_t)p.a_slots * S * p.rb_bytes + (size_t)p.b_slots * p.ntile * 128 + 1024 + 1024 + 8192;
       static bool rb_attr = false;
       if (!rb_attr) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -832,7 +836,7 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       return HM_OK;
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 1024 + 4096 /*control block + bias*/;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 1024 + 8192 /*control block + bias (<= 2048 columns)*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
