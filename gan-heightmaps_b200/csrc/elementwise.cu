@@ -700,6 +700,21 @@ __global__ void copy_v8_kernel(const T* __restrict__ s, T* __restrict__ d, long 
 
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+// dst[m][0..nc) (+)= src[m][c0..c0+nc)  (channel slice of an NHWC tensor; concat gradients)
+template <typename T>
+__global__ void slice_channels_kernel(const T* __restrict__ src, T* dst, long long M, int C, int c0, int nc,
+                                      int accumulate) {
+  const long long n = M * nc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / nc;
+    const int c = (int)(i - m * nc);
+    float v = ldf(src + m * C + c0 + c);
+    if (accumulate) v += ldf(dst + i);
+    stf(dst + i, v);
+  }
+}
+
 // ---- losses ---------------------------------------------------------------
 template <typename T>
 __global__ void adv_loss_kernel(const T* __restrict__ h, T* dh, long long R, int G, int out_act, float target,
@@ -1058,6 +1073,16 @@ extern "C" int hm_permute(const void* src, void* dst, int dtype, int B, int C, i
   DISPATCH_T(dtype, (permute_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, B, C,
                                                                                      H, W, inverse)));
   HM_CHECK_LAUNCH("hm_permute");
+  return HM_OK;
+}
+
+extern "C" int hm_slice_channels(const void* src, void* dst, int dtype, long long M, int C, int c0, int nc,
+                                 int accumulate, void* stream) {
+  CHECK_DTYPE(dtype, "hm_slice_channels");
+  HM_CHECK_ARG(src && dst && M > 0 && C > 0 && c0 >= 0 && nc > 0 && c0 + nc <= C, "hm_slice_channels: bad argument");
+  DISPATCH_T(dtype, (slice_channels_kernel<T><<<ew_grid(M * nc), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)src, (T*)dst, M, C, c0, nc, accumulate)));
+  HM_CHECK_LAUNCH("hm_slice_channels");
   return HM_OK;
 }
 

@@ -35,7 +35,8 @@ struct WgParams {
   int n_mgroups;        // ceil(n_mtiles/acc)
   int zsplit;           // CTAs along the pixel axis
   int a_slots, b_slots;
-  float* dw;            // [units*64][Cout] fp32
+  float* dw;            // [units*64][pitch] fp32; this launch fills columns [n_off, n_off + Cout)
+  int n_off, pitch;     // N tiling when the layer has more than 256 output channels
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         wg_wait(bempty(bs), bph ^ 1);
         wg_expect_tx(bfull(bs), b_bytes);
         for (uint32_t j = 0; j < nblk; j++)
-          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), j * 64, ox0, oy0, n0);
+          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), p.n_off + j * 64, ox0, oy0, n0);
         if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         for (int mt = mt0; mt < mt1; mt++) {
           wg_wait(aempty(as), aph ^ 1);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       for (int mt = mt0; mt < mt1; mt++) {
         const int k = mt * 128 + row;                        // row of the packed gradient
         const bool valid = k < p.units * 64;
-        float* dst = p.dw + (size_t)k * p.Cout;
+        float* dst = p.dw + (size_t)k * p.pitch + p.n_off;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (mt - mt0) * p.Cout;
         for (int c0 = 0; c0 < p.Cout; c0 += 32) {
           uint32_t v[32];
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         wg_wait(bempty(bs), bph ^ 1);
         wg_expect_tx(bfull(bs), b_bytes);
         for (uint32_t j = 0; j < nblk; j++)
-          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), j * 64, ox0, oy0, n0);
+          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), p.n_off + j * 64, ox0, oy0, n0);
         if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         wg_wait(aempty(as), aph ^ 1);
         wg_expect_tx(afull(as), n_boxes * box_bytes);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       for (int mt = mt0; mt < mt1; mt++) {
         const int k = mt * 128 + row;
         const bool valid = k < p.units * 64;
-        float* dst = p.dw + (size_t)k * p.Cout;
+        float* dst = p.dw + (size_t)k * p.pitch + p.n_off;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (mt - mt0) * p.Cout;
         for (int c0 = 0; c0 < p.Cout; c0 += 32) {
           uint32_t v[32];
@@ -463,15 +464,31 @@ extern "C" int hm_tc_wgrad_supported(const HmConvDesc* d) {
   if (d->dtype != HM_F16 || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
   if (d->os != 1 || d->ou || d->ov) return 0;
   if (d->C1 % 64 || d->C2 % 64 || d->C1 <= 0) return 0;
-  if (d->Cout % 64 || d->Cout > 256 || d->Cout <= 0) return 0;
+  if (d->Cout % 64 || d->Cout <= 0 || (d->Cout > 256 && d->Cout % 256)) return 0;
   if (d->Ho != (d->H + 2 * d->pad - d->kh) / d->stride + 1 || d->Wo != (d->W + 2 * d->pad - d->kw) / d->stride + 1)
     return 0;
   if (d->oH != d->Ho || d->oW != d->Wo) return 0;
   return 1;
 }
 
+static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw, void* stream,
+                         int n_off, int ntile);
+
 extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw,
                            void* stream) {
+  HM_CHECK_ARG(d && x1 && dy && dw, "hm_tc_wgrad: null argument");
+  if (hm_tc_wgrad_supported(d) && d->Cout > 256) {
+    for (int n_off = 0; n_off < d->Cout; n_off += 256) {
+      int rc = tc_wgrad_tile(d, x1, x2, dy, dw, stream, n_off, 256);
+      if (rc) return rc;
+    }
+    return HM_OK;
+  }
+  return tc_wgrad_tile(d, x1, x2, dy, dw, stream, 0, d ? d->Cout : 0);
+}
+
+static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw, void* stream,
+                         int n_off, int ntile) {
   HM_CHECK_ARG(d && x1 && dy && dw, "hm_tc_wgrad: null argument");
   if (!hm_tc_wgrad_supported(d)) {
     set_error("hm_tc_wgrad: shape not supported by the tcgen05 path (need fp16, stride 1, C%%64==0, Cout%%64==0, <=256)");
@@ -488,7 +505,8 @@ extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, 
   }
   WgParams p;
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
-  p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = d->Cout;
+  p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = ntile;
+  p.n_off = n_off; p.pitch = d->Cout;
   p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
   p.bw = wg_pow2_floor(d->Wo < 128 ? d->Wo : 128);
   p.bh = wg_pow2_floor(d->Ho < 128 / p.bw ? d->Ho : 128 / p.bw);

@@ -151,6 +151,8 @@ class ConvOp(object):
         self.wt_f = self.wt_d = self.x1u = self.x2u = None
         rt = net.rt
         self.up2 = False      # nearest-2x + 5x5 evaluated as four 3x3 phase convolutions on the low-res source
+        self.dg2_cat = False
+        self.gcat = None
         self.dg2 = False      # input gradient of a 3x3 stride-2 conv as a 2x2-tap phase convolution of dy (pack mode 12)
         if rt.precision == "fast" and kind == "conv" and self.stride in (1, 2):
             if self.up == _lib.UP_NEAREST2 and self.x2 is None and self.stride == 1:
@@ -159,10 +161,14 @@ class ConvOp(object):
             self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
             if self.stride == 1:
                 self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
-            elif not self.up and self.x2 is None:
+            elif not self.up:
                 dd = self._dgrad_desc(rt, 1, 0)
                 dd.split = dd.Cout
-                self.tc_dg = self.dg2 = bool(_lib.query("hm_tc_conv_supported", C.byref(dd)))
+                ok = bool(_lib.query("hm_tc_conv_supported", C.byref(dd)))
+                if self.x2 is None:
+                    self.tc_dg = self.dg2 = ok
+                else:
+                    self.dg2_cat = ok        # gradient of the whole (thin) concat on the tensor cores, then sliced
         # one-channel input (first discriminator layer): im2col to 64 "tap channels", then a 1x1 tensor-core GEMM
         self.col1 = (rt.precision == "fast" and kind == "conv" and self.Cin == 1 and self.x2 is None and not self.up
                      and self.stride == 1 and self.kh * self.kw <= 64 and 2 * self.pad == self.kh - 1
@@ -191,6 +197,10 @@ class ConvOp(object):
                 self.dwp = rt.empty((64 * self.Cout,), torch.float32)
         if self.tc_fwd and self.wt_f is None:
             self.wt_f = rt.empty((36 * self.Cin * self.Cout if self.up2 else n,))
+        if self.dg2_cat:
+            self.gcat = rt.empty((B, self.Hv, self.Wv, self.Cin))
+            if self.wt_d is None:
+                self.wt_d = rt.empty((16 * self.Cin * self.Cout,))
         if self.tc_dg and self.wt_d is None:
             self.wt_d = rt.empty((16 * self.Cin * self.Cout if self.dg2 else n,))
         self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient of the thin phase-decomposed layer
@@ -218,7 +228,10 @@ class ConvOp(object):
             else:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 8 if self.up2 else 5, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
-            if not self.tc_dg:
+            if self.dg2_cat:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 12, self.Cout, self.Cin, self.kh, self.kw,
+                        0, 0, rt.cd)
+            elif not self.tc_dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 7 if self.fw_dg else 1, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
             else:
@@ -429,7 +442,17 @@ class ConvOp(object):
             acc = (self.x1.take_acc() if t1 else 0) | ((self.x2.take_acc() << 1) if t2 else 0)
             y1 = _ptr(self.x1.g(lo, hi)) if t1 else None
             y2 = _ptr(self.x2.g(lo, hi)) if t2 else None
-            if self.tc_dg:
+            if self.dg2_cat:
+                d = self._dgrad_desc(rt, n, 0)
+                d.split = d.Cout
+                gc = self.gcat[lo:hi]
+                rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, _ptr(gc), None)
+                M = n * self.Hv * self.Wv
+                if t1:
+                    rt.call("hm_slice_channels", _ptr(gc), y1, rt.cd, M, self.Cin, 0, self.C1, acc & 1)
+                if t2:
+                    rt.call("hm_slice_channels", _ptr(gc), y2, rt.cd, M, self.Cin, self.C1, self.C2, (acc >> 1) & 1)
+            elif self.tc_dg:
                 d = self._dgrad_desc(rt, n, acc) if self.dg2 else self._tc_dgrad_desc(rt, n, acc)
                 rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, y1, y2)
             else:

@@ -207,6 +207,10 @@ int hm_upsample2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int
 int hm_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W, void* stream);
 int hm_nhwc_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, int W, void* stream);
 int hm_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, void* stream);
+/* dst[M][nc] (+)= src[M][C] channels [c0, c0+nc): the part of a ConcatLayer's gradient that belongs to one input
+ * (p2p.py:279-281). */
+int hm_slice_channels(const void* src, void* dst, int dtype, long long M, int C, int c0, int nc, int accumulate,
+                      void* stream);
 /* ReshapeLayer((-1,C,H,W)) after the generator's DenseLayer (dcgan.py:18): the flat feature vector is in
  * NCHW order, the convolutions want NHWC.  inverse=0: src[B][C][H][W] -> dst[B][H][W][C]; inverse=1 the
  * other way (the backward pass).  Same dtype on both sides. */

@@ -386,6 +386,14 @@ def hm_permute(src, dst, dtype, B, Cn, H, W, inverse, stream=None):
     return 0
 
 
+def hm_slice_channels(src, dst, dtype, M, Cn, c0, nc, accumulate, stream=None):
+    s_ = _a(src, M * Cn, _NP[dtype]).reshape(M, Cn)[:, c0:c0 + nc].astype(np.float32)
+    d_ = _a(dst, M * nc, _NP[dtype])
+    out = s_.reshape(-1) + (d_.astype(np.float32) if accumulate else 0)
+    d_[:] = out.astype(_NP[dtype])
+    return 0
+
+
 def hm_cast(src, sd, dst, dd, n, stream=None):
     _a(dst, n, _NP[dd])[:] = _a(src, n, _NP[sd]).astype(_NP[dd])
     return 0
@@ -473,7 +481,7 @@ def _tc_ok(d, wgrad):
         ok = ok and d.Ho == (d.H + 2 * d.pad - d.kh) // 2 + 1 and d.Wo == (d.W + 2 * d.pad - d.kw) // 2 + 1
         ok = ok and d.oH == d.Ho and d.oW == d.Wo
         if wgrad:
-            return ok and d.Cout % 64 == 0 and 0 < d.Cout <= 256
+            return ok and d.Cout % 64 == 0 and (0 < d.Cout <= 256 or d.Cout % 256 == 0)
         if d.Cout % 16 or d.split % 16:
             return ok and d.split == d.Cout and 0 < d.Cout <= 256
         return ok and 0 < d.split <= d.Cout
@@ -484,7 +492,7 @@ def _tc_ok(d, wgrad):
     ok = ok and d.Ho == d.H + 2 * d.pad - d.kh + 1 and d.Wo == d.W + 2 * d.pad - d.kw + 1
     ok = ok and d.oH == d.Ho and d.oW == d.Wo
     if wgrad:
-        return ok and d.Cout % 64 == 0 and 0 < d.Cout <= 256
+        return ok and d.Cout % 64 == 0 and (0 < d.Cout <= 256 or d.Cout % 256 == 0)
     if d.Cout % 16 or d.split % 16:
         return ok and d.split == d.Cout and 0 < d.Cout <= 256
     ntile = [n for n in range(256, 15, -16) if d.Cout % n == 0 and d.split % n == 0]

@@ -125,3 +125,27 @@ def test_fast_mode_tensor_core_step_tracks_oracle():
             continue                     # biases in front of a BatchNorm: true gradient is zero
         rel = float(np.linalg.norm((a * scale - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
         assert rel <= 0.2, ('G', i, rel)
+
+
+def test_fast_mode_full_width_joint_step_tracks_oracle():
+    """BASELINE configs[2] architecture (all four networks at full width, 512x512, bilinear U-Net) at batch 2 in
+    fp16 fast mode -- tensor-core forward / input-gradient / weight-gradient kernels incl. the stride-2 and
+    concat+bilinear layers -- against the float32 oracle: the five losses within 3e-2; PatchGAN and U-Net weight
+    gradients within 0.15 in relative L2 norm (fp16 storage; leaky-rectify sign flips near zero)."""
+    cfg = S.experiment_kwargs('test1_nobn_bilin_both')
+    om, m = build_pair(cfg, 'both', device="cuda", precision="fast")
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=2)
+    lo = om.train_fn(Z, X, Y)
+    lm = m.train_fn(Z, X, Y)
+    assert np.all(np.isfinite(lm))
+    np.testing.assert_allclose(lm, lo, rtol=3e-2, atol=1e-3)
+    scale = 1.0 / m.rt.loss_scale
+    for k, net in (('Dp', m.Dp), ('P', m.P)):
+        tr = [q for q in net.params if q.trainable]
+        for i, (a, b, q) in enumerate(zip(net.get_grads(), om.last_grads[k], tr)):
+            if q.kind != "W":
+                continue
+            rel = float(np.linalg.norm((a * scale - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
+            assert rel <= 0.15, (k, i, q.shape, rel)
+    paths = [op.path for op in m.P.ops + m.Dp.ops if hasattr(op, "path")]
+    assert paths.count("tcgen05") >= 16, paths

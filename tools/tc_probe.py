@@ -165,7 +165,7 @@ def run_s2_case(name, B, H, W, C1, C2, Co):
     g_ref = torch.zeros(9 * Ct, Co, device="cuda")
     g_tc = torch.zeros(9 * Ct, Co, device="cuda")
     _lib.call("hm_conv_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), g_ref.data_ptr(), None)
-    wg_ok = Co % 64 == 0 and Co <= 256
+    wg_ok = Co % 64 == 0 and (Co <= 256 or Co % 256 == 0)
     if wg_ok:
         _lib.call("hm_tc_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), g_tc.data_ptr(), None)
     torch.cuda.synchronize()
@@ -197,7 +197,7 @@ def run_s2_case(name, B, H, W, C1, C2, Co):
     return worst, "\n".join(lines)
 
 
-WGRAD_CASES = [c for c in CASES if c[6] % 64 == 0 and c[6] <= 256]
+WGRAD_CASES = [c for c in CASES if c[6] % 64 == 0 and (c[6] <= 256 or c[6] % 256 == 0)]
 
 
 def run_wgrad_case(name, B, H, W, C1, C2, Cout, k, pad, act):
