@@ -374,13 +374,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
         const int nv = min(p.S, p.n_mtiles - st * p.S);      // M tiles present in this super tile
-        int ox0[4], oy0[4], n0[4];
-        for (int i = 0; i < nv; i++) {
-          const int mt = st * p.S + i;
-          ox0[i] = (mt % p.tiles_x) * p.bw;
-          oy0[i] = ((mt / p.tiles_x) % p.tiles_y) * p.bh;
-          n0[i] = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
-        }
         for (int tap = 0; tap < taps; tap++) {
           const int r = tap / p.kw, s = tap - r * p.kw;
           for (int cc = 0; cc < ksteps_per_tap; cc++) {
@@ -388,13 +381,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t sa = base + stage * stage_bytes;
             mbar_expect_tx(full_bar(stage), nv * A_BYTES + p.ntile * 128);
             const int c = cc * KCH;
+#pragma unroll 1
             for (int i = 0; i < nv; i++) {
+              const int mt = st * p.S + i;
+              const int ox = (mt % p.tiles_x) * p.bw * p.stride - p.pad + s;
+              const int oy = ((mt / p.tiles_x) % p.tiles_y) * p.bh * p.stride - p.pad + r;
+              const int on = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
               if (c < p.C1)
-                tma_load_4d(&tmA, sa + i * A_BYTES, full_bar(stage), c, ox0[i] * p.stride - p.pad + s,
-                            oy0[i] * p.stride - p.pad + r, n0[i]);
+                tma_load_4d(&tmA, sa + i * A_BYTES, full_bar(stage), c, ox, oy, on);
               else
-                tma_load_4d(&tmA2, sa + i * A_BYTES, full_bar(stage), c - p.C1, ox0[i] * p.stride - p.pad + s,
-                            oy0[i] * p.stride - p.pad + r, n0[i]);
+                tma_load_4d(&tmA2, sa + i * A_BYTES, full_bar(stage), c - p.C1, ox, oy, on);
             }
             tma_load_3d(&tmB, sa + a_bytes, full_bar(stage), c, nt * p.ntile, tap);
             if (++stage == p.stages) {
@@ -541,24 +537,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
         const int nv = min(p.S, p.n_mtiles - st * p.S);
-        int ox0[4], oy0[4], n0[4];
-        for (int i = 0; i < nv; i++) {
-          const int mt = st * p.S + i;
-          ox0[i] = (mt % p.tiles_x) * p.bw;
-          oy0[i] = (mt / p.tiles_x) % p.tiles_y;                 // bh == 1
-          n0[i] = mt / (p.tiles_x * p.tiles_y);                  // bn == 1
-        }
         for (int r = 0; r < p.kh; r++) {
           for (int cc = 0; cc < cchunks; cc++) {
             const int c = cc * KCH;
             mbar_wait(aempty(as), aph ^ 1);
             mbar_expect_tx(afull(as), nv * box_bytes);
+            // NOTE: keep this loop rolled and free of local arrays: with the tile coordinates precomputed into
+            // per-thread arrays nvcc 12.9 unrolled/peeled it and boxes i >= 1 of every first chunk never landed
+            // (tools/tc_probe.py *_S4 cases)
+#pragma unroll 1
             for (int i = 0; i < nv; i++) {
+              const int mt = st * p.S + i;                         // bh == bn == 1: a tile is a row segment
+              const int ox = (mt % p.tiles_x) * p.bw - p.pad;
+              const int oy = (mt / p.tiles_x) % p.tiles_y - p.pad + r;
+              const int on = mt / (p.tiles_x * p.tiles_y);
               const uint32_t dst = base + as * a_slot_bytes + i * p.rb_bytes;
               if (c < p.C1)
-                tma_load_4d(&tmA, dst, afull(as), c, ox0[i] - p.pad, oy0[i] - p.pad + r, n0[i]);
+                tma_load_4d(&tmA, dst, afull(as), c, ox, oy, on);
               else
-                tma_load_4d(&tmA2, dst, afull(as), c - p.C1, ox0[i] - p.pad, oy0[i] - p.pad + r, n0[i]);
+                tma_load_4d(&tmA2, dst, afull(as), c - p.C1, ox, oy, on);
             }
             if (++as == p.a_slots) { as = 0; aph ^= 1; }
             for (int s = 0; s < p.kw; s++) {
@@ -775,6 +772,15 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   int S = 256 / p.ntile;                                   // 2 (double buffer) * S * ntile <= 512 TMEM columns
   if (S < 1) S = 1;
   if (S > 4) S = 4;
+  {
+    static int smax = -1;                                  // diagnostic cap on the super-tile size
+    if (smax < 0) {
+      const char* e = getenv("HMGAN_TC_SMAX");
+      smax = e ? atoi(e) : 4;
+      if (smax < 1) smax = 1;
+    }
+    if (S > smax) S = smax;
+  }
   while (S > 1 && ((p.n_mtiles + S - 1) / S) * p.n_ntiles < num_sms()) S >>= 1;   // keep every SM busy on small layers
   p.S = S;
   p.n_super = (p.n_mtiles + S - 1) / S;
@@ -807,8 +813,16 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       p.rb_mode = e ? atoi(e) : 0;
     }
     p.a_slots = (S * p.rb_bytes > 40 * 1024) ? 2 : 3;
+    {
+      const char* e = getenv("HMGAN_RB_ASLOTS");            // diagnostic override
+      if (e && atoi(e) >= 1) p.a_slots = atoi(e);
+    }
     int b_slots = (227 * 1024 - 10240 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
     if (b_slots > 8) b_slots = 8;
+    {
+      const char* e = getenv("HMGAN_RB_BSLOTS");            // diagnostic override
+      if (e && atoi(e) >= 2 && atoi(e) < b_slots) b_slots = atoi(e);
+    }
     if (b_slots >= 2) {
       p.b_slots = b_slots;
       CUtensorMap rA, rA2;

@@ -129,25 +129,30 @@ def test_fast_mode_tensor_core_step_tracks_oracle():
 
 def test_fast_mode_full_width_joint_step_tracks_oracle():
     """BASELINE configs[2] architecture (all four networks at full width, 512x512, bilinear U-Net) at batch 2 in
-    fp16 fast mode -- tensor-core forward / input-gradient / weight-gradient kernels incl. the stride-2 and
-    concat+bilinear layers -- against the float32 oracle: the five losses within 3e-2; PatchGAN and (decoder-side) U-Net weight
-    gradients within 0.15 in relative L2 norm (fp16 storage; leaky-rectify sign flips near zero)."""
+    fp16 fast mode -- tensor-core forward / input-gradient / weight-gradient kernels incl. the stride-2, the
+    concat+bilinear and the super-tile row-box layers -- against the float32 oracle: the five losses within 3e-3.
+
+    Weight gradients, relative L2 error per array.  PatchGAN (no BatchNorm): <= 2e-2.  U-Net: the step is
+    ill-conditioned at batch 2 -- the 1x1 / 2x2 bottleneck BatchNorms see 2..8 values per channel, so inv_std
+    amplifies any rounding.  Measured on the ORACLE alone (float32, only X rounded to fp16, /tmp experiment recorded
+    in DESIGN.md): the decoder arrays move by 0.001 (dconv9), 0.007, 0.023, 0.05, 0.064, 0.079, 0.097, 0.12, 0.13
+    (dconv1) and every encoder array by 0.6-0.7.  fp16 storage of every activation is a larger perturbation than
+    that, so the bounds are: the seven arrays nearest the loss <= 0.15 (measured 0.002 ... 0.13), the rest <= 0.5
+    (measured 0.15 ... 0.23; a wrong kernel gives 0.7-1.0, as the row-box super-tile bug did)."""
     cfg = S.experiment_kwargs('test1_nobn_bilin_both')
     om, m = build_pair(cfg, 'both', device="cuda", precision="fast")
     Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=2)
     lo = om.train_fn(Z, X, Y)
     lm = m.train_fn(Z, X, Y)
     assert np.all(np.isfinite(lm))
-    np.testing.assert_allclose(lm, lo, rtol=3e-2, atol=1e-3)
+    np.testing.assert_allclose(lm, lo, rtol=3e-3, atol=1e-4)
     scale = 1.0 / m.rt.loss_scale
-    # PatchGAN (no BatchNorm): every weight gradient.  U-Net: the decoder-side arrays nearest the loss; deeper
-    # ones pass through BatchNorm layers that see 2..8 values per channel at batch 2 (1x1 / 2x2 bottleneck), where
-    # float32-vs-fp16 rounding is amplified by inv_std up to 100x and an elementwise comparison means nothing.
-    for k, net, keep in (('Dp', m.Dp, None), ('P', m.P, 12)):
+    for k, net in (('Dp', m.Dp), ('P', m.P)):
         tr = [q for q in net.params if q.trainable]
         rows = [(i, a, b, q) for i, (a, b, q) in enumerate(zip(net.get_grads(), om.last_grads[k], tr)) if q.kind == "W"]
-        for i, a, b, q in (rows if keep is None else rows[-keep:]):
+        for j, (i, a, b, q) in enumerate(rows):
             rel = float(np.linalg.norm((a * scale - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
-            assert rel <= 0.15, (k, i, q.shape, rel)
+            bound = 2e-2 if k == 'Dp' else (0.15 if j >= len(rows) - 7 else 0.5)
+            assert rel <= bound, (k, i, q.shape, rel, bound)
     paths = [op.path for op in m.P.ops + m.Dp.ops if hasattr(op, "path")]
     assert paths.count("tcgen05") >= 16, paths

@@ -33,6 +33,11 @@ CASES = [
     ("3x3_128_3_w32_thin", 2, 32, 32, 128, 0, 3, 3, 1, 4),
     ("1x1_128_12_w16_thin", 2, 16, 16, 128, 0, 12, 1, 0, 0),
     ("5x5_64_40_w16_thin", 1, 16, 16, 64, 0, 40, 5, 2, 1),
+    # large enough for super tiles of 4 / 2 M tiles (S = 256/ntile while every SM still gets a work item)
+    ("3x3_cat128+128_64_w256_rb_S4", 2, 160, 256, 128, 128, 64, 3, 1, 0),
+    ("5x5_128_64_w256_rb_S4", 2, 160, 256, 128, 0, 64, 5, 2, 0),
+    ("5x5_64_128_w256_rb_S2", 2, 160, 256, 64, 0, 128, 5, 2, 1),
+    ("3x3_64_64_w64_S4", 20, 64, 64, 64, 0, 64, 3, 1, 1),
 ]
 
 
