@@ -1,0 +1,343 @@
+// One-channel-source convolutions on tcgen05 with the im2col operand built in shared memory (sm_100a, fast mode).
+//
+// The two ends of the DCGAN pair touch 512x512 one-channel images next to 64-channel tensors:
+//   * the discriminator's first layer  conv5x5(1 -> 64) + LeakyReLU + 2x2 max-pool  (reference
+//     architectures/dcgan.py:42-47), whose un-pooled output (64 ch @ 512^2) is 4x the bytes of anything else in the step;
+//   * the input gradient of the generator's last layer  nearest-2x -> conv5x5(64 -> 1)  (dcgan.py:31-32).
+// Both are the SAME gather: every output element q of the half-resolution grid reads the 6x6 patch
+//     A[q][u*6+v] = img[2*qy - 2 + u][2*qx - 2 + v]          (zero outside the image)
+// of a one-channel image and multiplies it with a [N][36] matrix:
+//   * pooled first layer: N = 4*64 = (window position d, co); Wk[(d,co)][(u,v)] = Wf[co][u-dy][v-dx] (pack mode 15);
+//     the epilogue takes the max over d (and its arg), adds the bias, applies the activation and writes the POOLED
+//     tensor + the argmax bytes -- the full-resolution activation never exists;
+//   * last-layer input gradient: N = 64 = ci; Wk[ci][(u,v)] = the four 3x3 phase filters of pack mode 8, transposed
+//     (pack mode 14); dy[512^2] goes straight to dx_low[256^2][64].
+// A CTA tile is 128 output elements (bw x bh of the half-res grid).  Builder warps stage the (2bh+4) x (2bw+4) image
+// patch in shared memory (registers prefetch the next tile's patch), each builder thread then writes ITS row of the
+// [128][64] fp16 operand tile in the 128B-swizzled K-major layout tcgen05 reads (K = 36, zero-padded to 48), one
+// elected thread issues 3 tcgen05.mma (M=128, N, K=16) into a double-buffered TMEM accumulator, four epilogue warps
+// drain it.  Weights ([N][64] fp16, <= 32 KB) are loaded once per CTA by TMA.
+#include <cuda.h>
+
+#include "hm_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace hm {
+using namespace ptx;
+
+constexpr int C1_THREADS = 288;        // warp 0: weights TMA + MMA issuer; warps 1-4: builders; warps 5-8: epilogue
+constexpr int C1_STAGES = 3;
+constexpr int C1_A_BYTES = 128 * 128;  // one [128 rows][64 k] fp16 operand tile
+constexpr int C1_PATCH_WORDS = 784;    // >= max over (bw,bh) of (2bh+4)*(bw+2) 32-bit words (780 at bw=128 or bw=1)
+constexpr int C1_PRE = 7;              // patch words per builder thread
+
+struct C1Params {
+  int B, H, W, Hq, Wq;
+  int bw, bh, tiles_x, tiles_y, n_tiles;
+  int N;                // GEMM columns: 64 (plain) or 256 (pooled: 4 window positions x 64 channels)
+  int pool;
+  int act;
+  float slope;
+  const __half* x;      // [B,H,W] one channel
+  const float* bias;    // [64] or null
+  __half* y;            // [B,Hq,Wq,64]
+  uint8_t* idx;         // [B,Hq,Wq,64] argmax (pooled form)
+};
+
+template <int ACT>
+__device__ __forceinline__ float c1_act(float v, float slope) {
+  if (ACT == HM_ACT_LRELU) return fmaxf(v, 0.f) + slope * fminf(v, 0.f);
+  if (ACT == HM_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+template <int ACT>
+__device__ __forceinline__ void c1_epilogue(const C1Params& p, uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
+                                            const float* bias_s, int warp, int lane) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int iy = row / p.bw, ix = row - iy * p.bw;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int accstride = p.pool ? 256 : 64;
+  int it = 0;
+  for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
+    const int acc = it & 1;
+    mbar_wait(t_full0 + 8u * acc, (it >> 1) & 1);
+    tc_fence_after();
+    const int b = t / per_img, rem = t - b * per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
+    const bool valid = wy < p.Hq && wx < p.Wq;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * accstride;
+    const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
+    if (p.pool) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        tmem_ld16(taddr + c0, v0);
+        tmem_ld16(taddr + 64 + c0, v1);
+        tmem_ld16(taddr + 128 + c0, v2);
+        tmem_ld16(taddr + 192 + c0, v3);
+        tmem_ld_wait();
+        if (!valid) continue;
+        uint32_t packed[8], kb[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          float r2[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            float m = __uint_as_float(v0[j + e]);
+            uint32_t k = 0;
+            const float a1 = __uint_as_float(v1[j + e]), a2 = __uint_as_float(v2[j + e]), a3 = __uint_as_float(v3[j + e]);
+            if (a1 > m) { m = a1; k = 1; }
+            if (a2 > m) { m = a2; k = 2; }
+            if (a3 > m) { m = a3; k = 3; }
+            r2[e] = c1_act<ACT>(m + bias_s[c0 + j + e], p.slope);
+            kb[(j + e) >> 2] |= k << (8 * ((j + e) & 3));
+          }
+          __half2 h = __floats2half2_rn(r2[0], r2[1]);
+          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(p.y + o + c0);
+        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        *reinterpret_cast<uint4*>(p.idx + o + c0) = make_uint4(kb[0], kb[1], kb[2], kb[3]);
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          __half2 h = __floats2half2_rn(c1_act<ACT>(__uint_as_float(v[j]) + bias_s[c0 + j], p.slope),
+                                        c1_act<ACT>(__uint_as_float(v[j + 1]) + bias_s[c0 + j + 1], p.slope));
+          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(p.y + o + c0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t_empty0 + 8u * acc);
+  }
+}
+
+__global__ void __launch_bounds__(C1_THREADS, 1)
+    c1s2_conv_kernel(const __grid_constant__ CUtensorMap tmW, const C1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_bytes = (uint32_t)p.N * 128u;
+  const uint32_t a_off = w_bytes;
+  const uint32_t patch_off = a_off + C1_STAGES * C1_A_BYTES;
+  const uint32_t ctrl_off = patch_off + 2 * C1_PATCH_WORDS * 4;
+  const uint32_t ctrl = base + ctrl_off;
+  const uint32_t w_full = ctrl;
+  auto a_full = [&](int s) { return ctrl + 8u * (1 + s); };
+  auto a_empty = [&](int s) { return ctrl + 8u * (1 + C1_STAGES + s); };
+  auto t_full = [&](int a) { return ctrl + 8u * (1 + 2 * C1_STAGES + a); };
+  auto t_empty = [&](int a) { return ctrl + 8u * (3 + 2 * C1_STAGES + a); };
+  const uint32_t tmem_slot = ctrl + 8u * (5 + 2 * C1_STAGES);
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gbase + ctrl_off + 8 * (5 + 2 * C1_STAGES));
+  float* bias_s = (float*)(gbase + ctrl_off + 256);
+  uint32_t* patch = (uint32_t*)(gbase + patch_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = p.pool ? 512u : 128u;
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < C1_STAGES; s++) {
+      mbar_init(a_full(s), 128);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(t_full(a), 1);
+      mbar_init(t_empty(a), 4);
+    }
+    mbar_fence_init();
+    prefetch_tensormap(&tmW);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp >= 1 && warp <= 4) {            // zero the operand stages once: chunk 5 and the tail of chunk 4 stay zero
+    uint4* a4 = reinterpret_cast<uint4*>(gbase + a_off);
+    for (int i = threadIdx.x - 32; i < C1_STAGES * C1_A_BYTES / 16; i += 128) a4[i] = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const int per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ===================== weights + MMA issuer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, w_bytes);
+      tma_load_2d(&tmW, base, w_full, 0, 0);
+      mbar_wait(w_full, 0);
+      const uint32_t idesc = idesc_f16(p.N);
+      const uint64_t bd = desc_k_sw128(base);
+      const int accstride = p.pool ? 256 : 64;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
+        const int s = it % C1_STAGES, ph = (it / C1_STAGES) & 1, acc = it & 1;
+        mbar_wait(t_empty(acc), ((it >> 1) & 1) ^ 1);
+        mbar_wait(a_full(s), ph);
+        tc_fence_after();
+        const uint64_t ad = desc_k_sw128(base + a_off + s * C1_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 3; k++)            // K = 48 = taps 0..35 + zero padding; +32 B per K=16 slice
+          tc_mma_f16(tmem_base + acc * accstride, ad + 2 * k, bd + 2 * k, idesc, k != 0);
+        tc_commit(a_empty(s));
+        tc_commit(t_full(acc));
+      }
+    }
+  } else if (warp <= 4) {
+    // ===================== builders =====================
+    const int tb = threadIdx.x - 32;
+    const int iy = tb / p.bw, ix = tb - iy * p.bw;
+    const int PWW = p.bw + 2, n_words = (2 * p.bh + 4) * PWW;
+    uint32_t pre[C1_PRE];
+    auto prefetch = [&](int t) {
+      const int b = t / per_img, rem = t - b * per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int Y0 = 2 * ty * p.bh - 2, X0 = 2 * tx * p.bw - 2;
+      const __half* img = p.x + (size_t)b * p.H * p.W;
+#pragma unroll
+      for (int j = 0; j < C1_PRE; j++) {
+        const int i = tb + 128 * j;
+        uint32_t v = 0;
+        if (i < n_words) {
+          const int pr = i / PWW, pw = i - pr * PWW;
+          const int Y = Y0 + pr, X = X0 + 2 * pw;
+          if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
+        }
+        pre[j] = v;
+      }
+    };
+    int t = blockIdx.x;
+    if (t < p.n_tiles) prefetch(t);
+    int it = 0;
+    for (; t < p.n_tiles; t += gridDim.x, it++) {
+      uint32_t* pb = patch + (it & 1) * C1_PATCH_WORDS;
+#pragma unroll
+      for (int j = 0; j < C1_PRE; j++) {
+        const int i = tb + 128 * j;
+        if (i < n_words) pb[i] = pre[j];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (t + (int)gridDim.x < p.n_tiles) prefetch(t + gridDim.x);
+      const int s = it % C1_STAGES, ph = (it / C1_STAGES) & 1;
+      mbar_wait(a_empty(s), ph ^ 1);
+      uint32_t wd[20];
+#pragma unroll
+      for (int u = 0; u < 6; u++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) wd[u * 3 + j] = pb[(2 * iy + u) * PWW + ix + j];
+      wd[18] = wd[19] = 0;
+      uint8_t* arow = gbase + a_off + s * C1_A_BYTES;
+#pragma unroll
+      for (int c = 0; c < 5; c++)
+        *reinterpret_cast<uint4*>(arow + sw128_off(tb, c)) = make_uint4(wd[4 * c], wd[4 * c + 1], wd[4 * c + 2], wd[4 * c + 3]);
+      fence_proxy_async();
+      mbar_arrive(a_full(s));
+    }
+  } else {
+    // ===================== epilogue (warps 5..8) =====================
+    switch (p.act) {
+      case HM_ACT_LRELU: c1_epilogue<HM_ACT_LRELU>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane); break;
+      case HM_ACT_RELU: c1_epilogue<HM_ACT_RELU>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane); break;
+      default: c1_epilogue<HM_ACT_LINEAR>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*C1EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static C1EncodeTiledFn c1_encode_fn() {
+  static C1EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess &&
+        r == cudaDriverEntryPointSuccess)
+      fn = (C1EncodeTiledFn)q;
+  }
+  return fn;
+}
+
+}  // namespace hm
+
+using namespace hm;
+
+// y[B,H/2,W/2,64] = act( A . Wk^T + bias ),  A[q][u*6+v] = x[2qy-2+u][2qx-2+v]  (x: one-channel fp16 image [B,H,W]).
+//   ncols == 64 : plain form, wk = [64][64] fp16 (columns >= 36 ignored), idx must be NULL;
+//   ncols == 256: pooled form, wk = [(d,co)][64]; y = act(max_d + bias[co]), idx = argmax d (first maximum).
+extern "C" int hm_c1s2_conv(const void* x, const void* wk, const float* bias, void* y, uint8_t* idx, int B, int H, int W,
+                            int ncols, int act, float slope, void* stream) {
+  HM_CHECK_ARG(x && wk && y && B > 0 && H > 0 && W > 0, "hm_c1s2_conv: bad argument");
+  HM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "hm_c1s2_conv: the image must have even height and width (%dx%d)", H, W);
+  HM_CHECK_ARG((ncols == 64 && !idx) || (ncols == 256 && idx), "hm_c1s2_conv: ncols must be 64 (idx NULL) or 256 (pooled, idx given)");
+  HM_CHECK_ARG(act == HM_ACT_LINEAR || act == HM_ACT_LRELU || act == HM_ACT_RELU, "hm_c1s2_conv: activation %d is not supported", act);
+  if ((((uintptr_t)x) & 3) || (((uintptr_t)wk | (uintptr_t)y | (uintptr_t)idx) & 15)) {
+    set_error("hm_c1s2_conv: x must be 4-byte, wk / y / idx 16-byte aligned");
+    return HM_ERR_ALIGN;
+  }
+  if (!c1_encode_fn()) {
+    set_error("hm_c1s2_conv: cuTensorMapEncodeTiled is not available from this driver");
+    return HM_ERR_CUDA;
+  }
+  C1Params p;
+  p.B = B; p.H = H; p.W = W; p.Hq = H / 2; p.Wq = W / 2;
+  int bw = 1;
+  while (bw * 2 <= p.Wq && bw < 128) bw *= 2;
+  p.bw = bw; p.bh = 128 / bw;
+  p.tiles_x = (p.Wq + p.bw - 1) / p.bw;
+  p.tiles_y = (p.Hq + p.bh - 1) / p.bh;
+  p.n_tiles = B * p.tiles_x * p.tiles_y;
+  p.N = ncols; p.pool = idx ? 1 : 0; p.act = act; p.slope = slope;
+  p.x = (const __half*)x; p.bias = bias; p.y = (__half*)y; p.idx = idx;
+  CUtensorMap tmW;
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)ncols};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)ncols};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = c1_encode_fn()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wk), dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("hm_c1s2_conv: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+      return HM_ERR_CUDA;
+    }
+  }
+  // >= 120 KB so that only one CTA (which may own all 512 TMEM columns) is resident per SM
+  size_t smem = 1024 + (size_t)ncols * 128 + C1_STAGES * C1_A_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(c1s2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      set_error("hm_c1s2_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+      return HM_ERR_CUDA;
+    }
+    attr = true;
+  }
+  int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  c1s2_conv_kernel<<<grid, C1_THREADS, smem, (cudaStream_t)stream>>>(tmW, p);
+  HM_CHECK_LAUNCH("hm_c1s2_conv");
+  return HM_OK;
+}

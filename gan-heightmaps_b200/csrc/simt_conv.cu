@@ -316,6 +316,36 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     int co = (int)(i / 64);
     int r = t / kw, s = t % kw;
     val = t < kh * kw ? w[((size_t)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s)] : 0.f;
+  } else if (mode == 14) {
+    // hm_c1s2_conv, plain form: input gradient of (nearest-2x -> 5x5 'same' conv, Cout == 1) as a 6x6 stride-2 gather of
+    // the one-channel dy:  Wk[ci][u*6+v] = sum_{r in R(u&1, 2-(u>>1)), s in R(v&1, 2-(v>>1))} W[0][ci][4-r][4-s],
+    // R(p,d) as in mode 8;  columns 36..63 are zero.   (K-major, K = 64)
+    int k = (int)(i % 64);
+    int ci = (int)(i / 64);
+    val = 0.f;
+    if (k < 36) {
+      int uu = k / 6, vv = k % 6;
+      int py = uu & 1, px = vv & 1, dy_ = 2 - (uu >> 1), dx_ = 2 - (vv >> 1);     // phase, 3x3 tap (0..2)
+      for (int r = 0; r < 5; r++) {
+        if (((py + r - 2 + 4) >> 1) - 2 + 1 != dy_) continue;
+        for (int q = 0; q < 5; q++) {
+          if (((px + q - 2 + 4) >> 1) - 2 + 1 != dx_) continue;
+          val += w[((size_t)ci * 5 + (4 - r)) * 5 + (4 - q)];
+        }
+      }
+    }
+  } else if (mode == 15) {
+    // hm_c1s2_conv, pooled form: conv5x5 'same' (Cin == 1) evaluated at the four positions d = (dy,dx) of every 2x2
+    // pooling window from the window's 6x6 patch:  Wk[d*cout+co][u*6+v] = W[co][0][4-(u-dy)][4-(v-dx)] where the
+    // tap (u-dy, v-dx) lies inside the 5x5 filter, else 0;  columns 36..63 are zero.   (K-major, K = 64)
+    int k = (int)(i % 64);
+    int nn = (int)(i / 64);
+    int dd = nn / cout, co = nn - dd * cout;
+    val = 0.f;
+    if (k < 36) {
+      int r = k / 6 - (dd >> 1), q = k % 6 - (dd & 1);
+      if (r >= 0 && r < 5 && q >= 0 && q < 5) val = w[((size_t)co * 5 + (4 - r)) * 5 + (4 - q)];
+    }
   } else {
     val = w[i];
   }
@@ -449,7 +479,10 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12, "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || mode == 14 || mode == 15,
+               "hm_pack_conv_weight: bad mode %d", mode);
+  HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
+  HM_CHECK_ARG(mode != 15 || (cin == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 15 needs Cin == 1 and a 5x5 filter");
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
@@ -457,6 +490,8 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   if (mode == 8) n = 36LL * cout * cin;
   if (mode == 11) n = 64LL * cout;
   if (mode == 12) n = 16LL * cout * cin;
+  if (mode == 14) n = 64LL * cin;
+  if (mode == 15) n = 256LL * cout;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)

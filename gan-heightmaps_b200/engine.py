@@ -176,6 +176,13 @@ class ConvOp(object):
         if self.col1:
             self.tc_fwd = True
         self.path = "tcgen05" if self.tc_fwd else "simt"
+        # hm_c1s2_conv (in-kernel im2col of a one-channel image): (a) this layer + its 2x2 max-pool in one pass, set by
+        # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
+        self.pool_fused = None
+        self.wk = None
+        self.c1dg = (rt.precision == "fast" and kind == "conv" and self.up == _lib.UP_NEAREST2 and self.x2 is None
+                     and self.Cout == 1 and self.Cin == 64 and self.kh == 5 and self.kw == 5 and self.pad == 2
+                     and self.stride == 1)
         # input gradient of a thin-output stride-1 convolution (dy has <= 4 channels): forward-form gather of dy,
         # which the library serves with its thin-input kernel
         self.fw_dg = kind == "conv" and self.stride == 1 and self.Cout <= 4 and not self.tc_dg
@@ -187,8 +194,12 @@ class ConvOp(object):
             self.wp_f = rt.empty((n,))
             self.wp_d = rt.empty((n,)) if self.kind != "dense" else None
             self.dwp = rt.empty((n,), torch.float32)
-        if self.up and self.src.srcs[0].kind != "input":
+        if self.up and self.src.srcs[0].kind != "input" and not self.c1dg:
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
+        if self.c1dg and self.wk is None:
+            self.wk = rt.empty((64 * 64,))
+        if self.pool_fused is not None and self.wk is None:
+            self.wk = rt.empty((256 * 64,))
         n = self.K * self.Cout
         if self.col1:
             self.xc = rt.empty((B, self.Hv, self.Wv, 64))
@@ -228,6 +239,10 @@ class ConvOp(object):
             else:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 8 if self.up2 else 5, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
+            if self.pool_fused is not None:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 15, self.Cout, 1, 5, 5, 0, 0, rt.cd)
+            if self.c1dg:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 14, 1, self.Cin, 5, 5, 0, 0, rt.cd)
             if self.dg2_cat:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 12, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
@@ -337,6 +352,11 @@ class ConvOp(object):
                     d = self._fwd_desc(rt, n, (u, v))
                     rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f[(u * self.kw + v) * per:]),
                             bias, y, None)
+        elif self.pool_fused is not None:
+            # conv + bias + activation + 2x2 max-pool in one pass; the full-resolution activation is never written
+            pool = self.pool_fused
+            rt.call("hm_c1s2_conv", x1, _ptr(self.wk), bias, _ptr(pool.out.b(lo, hi)), _ptr(pool.idx[lo:hi]), n,
+                    self.Hv, self.Wv, 256, ACT[self.act.name], self.act.slope)
         elif self.col1:
             rt.call("hm_im2col_c1", x1, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.kh, self.kw, self.pad)
             d = self._col1_desc(rt, n)
@@ -378,6 +398,8 @@ class ConvOp(object):
                                 _ptr(self.dwp[(u * self.kw + v) * per:]))
                 mode = 2
             elif self.col1:
+                if self.pool_fused is not None:      # the fused forward pass did not write the im2col tensor
+                    rt.call("hm_im2col_c1", x1, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.kh, self.kw, self.pad)
                 d = self._col1_desc(rt, n)
                 rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
                 mode = 0              # rows [0, kh*kw) of the [64][Cout] result are the packed gradient
@@ -420,8 +442,15 @@ class ConvOp(object):
             return
         if self.kind == "dense":
             raise NotImplementedError("input gradient of a DenseLayer (only ever fed by the latent input)")
-        if self.up:
+        if self.c1dg and t1 and not self.x1.gw:
+            # dy[B,2H,2W,1] -> dx[B,H,W,64] in one pass (four 3x3 phase filters as a 6x6 stride-2 gather of dy)
+            self.x1.gw = True
+            rt.call("hm_c1s2_conv", _ptr(g), _ptr(self.wk), None, _ptr(self.x1.g(lo, hi)), None, n, self.Hv, self.Wv,
+                    64, 0, 0.0)
+        elif self.up:
             # gradient on the virtual (2x) grid, then the adjoint of the resampling
+            if self.gup is None:
+                self.gup = rt.empty((self.net.B, self.Hv, self.Wv, self.Cin))
             gu = self.gup[lo:hi]
             flat = gu.view(-1)
             n1 = n * self.Hv * self.Wv * self.C1
@@ -520,6 +549,7 @@ class PoolOp(object):
     def __init__(self, net, x, out, act):
         self.net, self.x, self.out, self.act = net, x, out, act
         self.idx = None
+        self.fused = False
 
     def alloc(self, rt, B):
         H, W, Cn = self.out.shape
@@ -529,6 +559,8 @@ class PoolOp(object):
         pass
 
     def fwd(self, rt, lo, hi, det):
+        if self.fused:            # written by the producing convolution (hm_c1s2_conv)
+            return
         H, W, Cn = self.x.shape
         rt.call("hm_maxpool2_fwd", _ptr(self.x.b(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
                 rt.cd, hi - lo, H, W, Cn)
@@ -724,7 +756,13 @@ class Net(object):
             pact = prod[0].act if prod and isinstance(prod[0], ConvOp) else L.linear
             if pact.name not in ("linear", "leaky_rectify", "rectify"):
                 pact = L.linear
-            self.ops.append(PoolOp(self, x, out, pact))
+            pop = PoolOp(self, x, out, pact)
+            self.ops.append(pop)
+            cv = prod[0] if prod and isinstance(prod[0], ConvOp) else None
+            if (cv is not None and cv.col1 and cv.Cout == 64 and cv.kh == 5 and cv.pad == 2 and x.consumers == 1
+                    and cv.act.name in ("linear", "leaky_rectify", "rectify") and x.shape[0] % 2 == 0
+                    and x.shape[1] % 2 == 0):
+                cv.pool_fused, pop.fused = pop, True
             return out
         if isinstance(layer, (L.Conv2DLayer, L.TransposedConv2DLayer, L.DenseLayer)):
             src = self._lower(layer.input_layer, None)

@@ -138,6 +138,18 @@ int hm_s2d_pad64(const void* dy, void* out, int B, int h, int w, int Co, void* s
  * 5x5 filter with hm_unpack_conv_wgrad(mode 9). */
 int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, float* dw_phases, void* stream);
 
+/* One-channel-source convolution with the im2col operand built in shared memory (tcgen05, fp16 only; csrc/c1_conv.cu).
+ * x is a ONE-channel image [B,H,W] (H, W even); every element q of the half-resolution grid reads the 6x6 patch
+ * A[q][u*6+v] = x[2qy-2+u][2qx-2+v] (zero outside) and y[B,H/2,W/2,64] = act(A . wk^T + bias):
+ *   ncols == 64 : wk = [64][64] fp16 (hm_pack_conv_weight mode 14: the input gradient of the generator's last layer,
+ *                 nearest-2x -> conv5x5(64 -> 1), dcgan.py:31-32, straight from dy[B,H,W] to dx[B,H/2,W/2,64]); idx NULL;
+ *   ncols == 256: wk = [(d,co)][64] (mode 15: the discriminator's first layer conv5x5(1 -> 64) + activation + 2x2
+ *                 max-pool, dcgan.py:42-47, in one pass): y = act(max_d + bias[co]), idx[B,H/2,W/2,64] = argmax d
+ *                 (d = 2*dy+dx, first maximum), the layout hm_maxpool2_fwd writes.
+ * act: HM_ACT_LINEAR, HM_ACT_LRELU or HM_ACT_RELU (monotonic, so it commutes with the max). */
+int hm_c1s2_conv(const void* x, const void* wk, const float* bias, void* y, uint8_t* idx, int B, int H, int W,
+                 int ncols, int act, float slope, void* stream);
+
 /* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
  *  mode 0: Conv2DLayer W (Cout,Cin,kh,kw)      -> Wp[(r*kw+s)*Cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]   (forward)
  *  mode 1: Conv2DLayer W                       -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][kh-1-r][kw-1-s]  (input gradient)
@@ -148,7 +160,7 @@ int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, 
  *  mode 6: Conv2DLayer W, tcgen05 input-gradient pack     -> Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
  *          (the input gradient of a stride-1 'same' convolution is the forward correlation of dy with this
  *           pack and pad' = k-1-pad)
- *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, mode 12: input
+ *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, modes 14/15: hm_c1s2_conv operands, mode 12: input
  *          gradient of a 3x3 stride-2 convolution as a 2x2-tap phase convolution of dy (see csrc/simt_conv.cu)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)

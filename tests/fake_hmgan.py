@@ -178,6 +178,25 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
         Wc = W.reshape(cout, kh * kw)[:, ::-1]                    # flipped taps, row-major (r, s)
         out = np.zeros((cout, 64), np.float32)
         out[:, :kh * kw] = Wc
+    elif mode == 14:
+        Wc = W.reshape(cin, 5, 5)[:, ::-1, ::-1]                                 # Cout == 1: correlation taps Wc[ci][r][s]
+        out = np.zeros((cin, 64), np.float32)
+        for uu in range(6):
+            for vv in range(6):
+                py, px, dy_, dx_ = uu & 1, vv & 1, 2 - (uu >> 1), 2 - (vv >> 1)
+                for r in range(5):
+                    for s_ in range(5):
+                        if (py + r - 2) // 2 + 1 == dy_ and (px + s_ - 2) // 2 + 1 == dx_:
+                            out[:, uu * 6 + vv] += Wc[:, r, s_]
+    elif mode == 15:
+        Wc = W.reshape(cout, 5, 5)[:, ::-1, ::-1]                                # Cin == 1: correlation taps Wc[co][r][s]
+        out = np.zeros((4, cout, 64), np.float32)
+        for dd in range(4):
+            for uu in range(6):
+                for vv in range(6):
+                    r, s_ = uu - (dd >> 1), vv - (dd & 1)
+                    if 0 <= r < 5 and 0 <= s_ < 5:
+                        out[dd, :, uu * 6 + vv] = Wc[:, r, s_]
     elif mode == 7:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
@@ -547,6 +566,24 @@ def hm_im2col_c1(x, xc, B, H, W, kh, kw, pad, stream=None):
     out = torch.zeros(B, H, W, 64)
     out[..., :kh * kw] = cols.reshape(B, kh * kw, H, W).permute(0, 2, 3, 1)
     _a(xc, B * H * W * 64, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+    return 0
+
+
+def hm_c1s2_conv(x, wk, bias, y, idx, B, H, W, ncols, act, slope, stream=None):
+    """A[q][u*6+v] = x[2qy-2+u][2qx-2+v]; y = act(A . wk^T + bias) (ncols 64) or its max over the 4 column groups."""
+    a = _t(_a(x, B * H * W, np.float16)).reshape(B, 1, H, W)
+    cols = F.unfold(a, (6, 6), padding=2, stride=2)                            # [B, 36, Hq*Wq]
+    Hq, Wq = H // 2, W // 2
+    wk_ = _t(_a(wk, ncols * 64, np.float16)).reshape(ncols, 64)[:, :36]
+    out = torch.einsum("bkl,nk->bln", cols, wk_).reshape(B, Hq, Wq, ncols)
+    bv = _t(_a(bias, 64, np.float32)) if bias else torch.zeros(64)
+    if ncols == 256:
+        o4 = out.reshape(B, Hq, Wq, 4, 64)
+        m, k = o4.max(dim=3)
+        _a(idx, B * Hq * Wq * 64, np.uint8)[:] = k.numpy().reshape(-1).astype(np.uint8)
+        out = m
+    res = _act(out + bv, act, slope)
+    _a(y, B * Hq * Wq * 64, np.float16)[:] = res.numpy().reshape(-1).astype(np.float16)
     return 0
 
 

@@ -205,6 +205,9 @@ def test_fast_mode_lowering_uses_tensor_core_kernels_where_eligible(cpu_backend,
     lm = m.train_fn(Z, X, Y)
     np.testing.assert_allclose(lm[:2], lo[:2], rtol=2e-2, atol=1e-4)
     assert calls.get("hm_tc_conv", 0) >= 10 and calls.get("hm_tc_wgrad", 0) >= 6, calls
+    # the one-channel ends: D's conv5x5(1->64)+LeakyReLU+max-pool in one pass (real+fake batch), and the input gradient of
+    # G's nearest-2x -> conv5x5(64->1), both through hm_c1s2_conv
+    assert calls.get("hm_c1s2_conv", 0) >= 2 and m.D.ops[0].pool_fused is not None and m.G.ops[-1].c1dg, calls
     paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
     assert "tcgen05" in paths and "simt" in paths
 

@@ -38,3 +38,12 @@ def test_tc_stride2_conv_fwd_wgrad_dgrad(case):
     phase-decomposed input gradient, each against the SIMT kernel on the same fp16 data (3e-3 of the scale)."""
     rel, line = tc_probe.run_s2_case(*case)
     assert rel <= 3e-3, line
+
+
+@pytest.mark.parametrize("case", tc_probe.C1_CASES, ids=[c[0] for c in tc_probe.C1_CASES])
+def test_c1s2_conv_pooled_first_layer_and_last_layer_input_gradient(case):
+    """hm_c1s2_conv (in-kernel im2col of a one-channel image, tcgen05): the discriminator's conv5x5(1->64)+LeakyReLU+
+    max-pool in one pass (values and argmax) and the generator's last-layer input gradient, against torch float32 on
+    the same fp16 data: 3e-3 of the output scale (fp16 operands and output, fp32 accumulation)."""
+    rel, line = tc_probe.run_c1_case(*case)
+    assert rel <= 3e-3, line

@@ -234,6 +234,91 @@ def run_wgrad_case(name, B, H, W, C1, C2, Cout, k, pad, act):
     return float(err.max()) / scale, line
 
 
+C1_CASES = [
+    # name, B, H, W, pooled
+    ("c1_pool_64", 2, 64, 64, 1),
+    ("c1_pool_512", 1, 512, 512, 1),
+    ("c1_pool_ragged_24x40", 3, 24, 40, 1),
+    ("c1_pool_2x260", 2, 2, 260, 1),
+    ("c1_dgrad_64", 2, 64, 64, 0),
+    ("c1_dgrad_512", 1, 512, 512, 0),
+    ("c1_dgrad_ragged_24x40", 3, 24, 40, 0),
+]
+
+
+def run_c1_case(name, B, H, W, pooled):
+    """hm_c1s2_conv against torch (fp32 on the same fp16-rounded data).
+    pooled: conv5x5(1->64, true convolution) + bias + LeakyReLU(0.2) + 2x2 max-pool (discriminator layer 1);
+    plain:  input gradient of nearest-2x -> conv5x5(64->1) (generator output layer) for a given dy[B,H,W]."""
+    import torch.nn.functional as F
+    torch.manual_seed(abs(hash(name)) % 1000)
+    if pooled:
+        x = torch.randn(B, H, W, device="cuda").half()
+        Wm = torch.randn(64, 1, 5, 5, device="cuda") * 0.2
+        bias = torch.randn(64, device="cuda") * 0.1
+        wk = torch.empty(256 * 64, device="cuda", dtype=torch.float16)
+        _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wk.data_ptr(), 15, 64, 1, 5, 5, 0, 0, 1, None)
+        y = torch.full((B, H // 2, W // 2, 64), 7.0, device="cuda", dtype=torch.float16)
+        idx = torch.full((B, H // 2, W // 2, 64), 9, device="cuda", dtype=torch.uint8)
+        _lib.call("hm_c1s2_conv", x.data_ptr(), wk.data_ptr(), bias.data_ptr(), y.data_ptr(), idx.data_ptr(), B, H, W,
+                  256, 1, 0.2, None)
+        torch.cuda.synchronize()
+        full = F.leaky_relu(F.conv2d(x.float()[:, None], Wm.half().float().flip(2, 3), bias, padding=2), 0.2)   # [B,64,H,W]
+        ref = F.max_pool2d(full, 2).permute(0, 2, 3, 1)
+        a = y.float()
+        scale = float(ref.abs().max())
+        err = float((a - ref).abs().max()) / scale
+        # the argmax must point at an element that attains the pooled value (ties / fp16-near-ties may differ)
+        k = idx.long()
+        assert int(k.max()) <= 3, "argmax byte out of range (untouched output?)"
+        fw = full.permute(0, 2, 3, 1).reshape(B, H // 2, 2, W // 2, 2, 64).permute(0, 1, 3, 5, 2, 4).reshape(B, H // 2, W // 2, 64, 4)
+        picked = torch.gather(fw, 4, k[..., None])[..., 0]
+        ierr = float((picked - ref).abs().max()) / scale
+        agree = float((fw.argmax(4) == k).float().mean())
+        line = "%-26s max_err/scale %.3g  picked-vs-max %.3g  argmax agreement %.4f" % (name, err, ierr, agree)
+        return max(err, ierr), line
+    dy = torch.randn(B, H, W, device="cuda").half()
+    Wm = torch.randn(1, 64, 5, 5, device="cuda") * 0.1
+    wk = torch.empty(64 * 64, device="cuda", dtype=torch.float16)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wk.data_ptr(), 14, 1, 64, 5, 5, 0, 0, 1, None)
+    dx = torch.full((B, H // 2, W // 2, 64), 7.0, device="cuda", dtype=torch.float16)
+    _lib.call("hm_c1s2_conv", dy.data_ptr(), wk.data_ptr(), None, dx.data_ptr(), None, B, H, W, 64, 0, 0.0, None)
+    torch.cuda.synchronize()
+    xl = torch.zeros(B, 64, H // 2, W // 2, device="cuda", requires_grad=True)
+    out = F.conv2d(F.interpolate(xl, scale_factor=2, mode="nearest"), Wm.flip(2, 3), padding=2)
+    out.backward(dy.float()[:, None])
+    ref = xl.grad.permute(0, 2, 3, 1)
+    scale = float(ref.abs().max())
+    err = float((dx.float() - ref).abs().max()) / scale
+    return err, "%-26s max_err/scale %.3g" % (name, err)
+
+
+def perf_c1():
+    for pooled, nm in ((1, "D1 conv5x5(1->64)+lrelu+pool @512^2 x64"), (0, "G-out dgrad 1->64 @512^2 x32")):
+        B = 64 if pooled else 32
+        x = torch.randn(B, 512, 512, device="cuda").half()
+        Wm = torch.randn(64, 1, 5, 5, device="cuda") if pooled else torch.randn(1, 64, 5, 5, device="cuda")
+        n = 256 if pooled else 64
+        wk = torch.empty(n * 64, device="cuda", dtype=torch.float16)
+        _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wk.data_ptr(), 15 if pooled else 14, 64 if pooled else 1,
+                  1 if pooled else 64, 5, 5, 0, 0, 1, None)
+        y = torch.empty(B, 256, 256, 64, device="cuda", dtype=torch.float16)
+        idx = torch.empty(B, 256, 256, 64, device="cuda", dtype=torch.uint8) if pooled else None
+        fn = lambda: _lib.call("hm_c1s2_conv", x.data_ptr(), wk.data_ptr(), None, y.data_ptr(),
+                               idx.data_ptr() if pooled else None, B, 512, 512, n, 1 if pooled else 0, 0.2, None)
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        gb = (y.numel() * 2 + (idx.numel() if pooled else 0) + x.numel() * 2) / 1e9
+        print("perf %-44s %8.3f ms  %7.1f GB/s (algorithmic bytes %.2f GB)" % (nm, ms, gb / ms * 1e3, gb), flush=True)
+
+
 def perf():
     """Device time of the tensor-core kernels at the hottest DCGAN layer shapes (CUDA events, 5 launches)."""
     shapes = [("D2 64->128 @256^2 x64", 64, 256, 256, 64, 128, 5, 2),
@@ -269,6 +354,15 @@ def perf():
 if __name__ == "__main__":
     if sys.argv[1:] == ["perf"]:
         perf()
+        sys.exit(0)
+    if sys.argv[1:] == ["c1"]:
+        for c in C1_CASES:
+            try:
+                print(run_c1_case(*c)[1], flush=True)
+            except Exception as e:
+                print("c1 %-24s EXC %s" % (c[0], e), flush=True)
+                break
+        perf_c1()
         sys.exit(0)
     if sys.argv[1:] == ["s2"]:
         for c in S2_CASES:
