@@ -341,3 +341,405 @@ extern "C" int hm_c1s2_conv(const void* x, const void* wk, const float* bias, vo
   HM_CHECK_LAUNCH("hm_c1s2_conv");
   return HM_OK;
 }
+
+// =================================================================================================================
+// Backward of the pooled first layer (conv5x5(1 -> 64) + activation + 2x2 max-pool), straight from the gradient of
+// the POOLED tensor: the full-resolution gradient (64 ch @ 512^2, 3/4 of it zeros) is never written.
+//   G'[w][(d,co)] = g[w][co] * act'(p[w][co]) * [idx[w][co] == d]            (w = pooling window, d = position in it)
+//   weight/bias gradient:  dWk[(d,co)][k] += sum_w G'[w][(d,co)] * A[w][k]    A = the 6x6 patch operand of the forward
+//                          pass with A[w][36] = 1 (so column 36 collects the bias gradient);  MN-major tcgen05 operands
+//   input gradient:        U[w][k] = sum_(d,co) G'[w][(d,co)] * Wk[(d,co)][k]  (K-major operands), then hm_c1s2_col2im
+//                          folds the 36 patch contributions of every window onto the image.
+// Two builder groups (128 threads each) alternate tiles so that the global-load latency of one tile hides behind the
+// other's build; each builder thread owns one window: it reads g, p, idx (320 B), writes its row of the four G' tiles
+// (and of the patch tile) in the 128B-swizzled layout, and arrives on the stage's mbarrier.
+// =================================================================================================================
+namespace hm {
+
+constexpr int CB_THREADS = 416;         // warp 0: MMA (+ weights TMA); warps 1-4, 5-8: builder groups; warps 9-12: epilogue
+constexpr int CB_G_BYTES = 4 * C1_A_BYTES;            // four [128 w][64 co] tiles
+constexpr int CB_STAGE_BYTES = CB_G_BYTES + C1_A_BYTES;
+
+struct CbParams {
+  int B, H, W, Hq, Wq;
+  int bw, bh, tiles_x, tiles_y, n_tiles;
+  int act;
+  float slope;
+  int want_dw, want_u;
+  const __half* x;      // [B,H,W]
+  const __half* g;      // [B,Hq,Wq,64] gradient of the pooled output
+  const __half* pl;     // [B,Hq,Wq,64] pooled output (for act')
+  const uint8_t* idx;   // [B,Hq,Wq,64]
+  float* dwk;           // [256][64] fp32, atomically accumulated
+  __half* u;            // [B,Hq,Wq,64]
+};
+
+__global__ void __launch_bounds__(CB_THREADS, 1)
+    c1s2_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const CbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_bytes = 256u * 128u;                              // Wk2: four [64 k][64 co] tiles
+  const uint32_t st_off = w_bytes;                                   // stages: [G' tiles d=0..3][patch tile]
+  const uint32_t patch_off = st_off + 2 * CB_STAGE_BYTES;
+  const uint32_t ctrl_off = patch_off + 2 * C1_PATCH_WORDS * 4;
+  const uint32_t ctrl = base + ctrl_off;
+  const uint32_t w_full = ctrl;
+  auto full = [&](int s) { return ctrl + 8u * (1 + s); };
+  auto empty = [&](int s) { return ctrl + 8u * (3 + s); };
+  auto u_full = [&](int a) { return ctrl + 8u * (5 + a); };
+  auto u_empty = [&](int a) { return ctrl + 8u * (7 + a); };
+  const uint32_t dw_full = ctrl + 8u * 9;
+  const uint32_t tmem_slot = ctrl + 8u * 10;
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gbase + ctrl_off + 80);
+  uint32_t* patch = (uint32_t*)(gbase + patch_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(full(s), 128);
+      mbar_init(empty(s), 1);
+      mbar_init(u_full(s), 1);
+      mbar_init(u_empty(s), 4);
+    }
+    mbar_init(dw_full, 1);
+    mbar_fence_init();
+    prefetch_tensormap(&tmW);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp >= 1 && warp <= 8) {          // zero the stages once (patch-tile chunks 5..7 are never written afterwards)
+    uint4* a4 = reinterpret_cast<uint4*>(gbase + st_off);
+    for (int i = threadIdx.x - 32; i < 2 * CB_STAGE_BYTES / 16; i += 256) a4[i] = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      if (p.want_u) {
+        mbar_expect_tx(w_full, w_bytes);
+        tma_load_2d(&tmW, base, w_full, 0, 0);
+        mbar_wait(w_full, 0);
+      }
+      const uint32_t id_mn = idesc_f16(64, 1, 1), id_k = idesc_f16(64);
+      for (int it = 0; it < my_tiles; it++) {
+        const int s = it & 1, n = it >> 1;
+        const uint32_t g_addr = base + st_off + s * CB_STAGE_BYTES, a_addr = g_addr + CB_G_BYTES;
+        mbar_wait(full(s), n & 1);
+        tc_fence_after();
+        if (p.want_dw) {
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)                 // 16 windows (two 8-row swizzle atoms) per MMA
+              tc_mma_f16(tmem_base + h * 64, desc_mn_sw128(g_addr + h * 2 * C1_A_BYTES + kk * 2048, C1_A_BYTES),
+                         desc_mn_sw128(a_addr + kk * 2048, C1_A_BYTES), id_mn, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (p.want_u) {
+          const int acc = it & 1;
+          mbar_wait(u_empty(acc), (n & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int d = 0; d < 4; d++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              tc_mma_f16(tmem_base + 128 + acc * 64, desc_k_sw128(g_addr + d * C1_A_BYTES) + 2 * k,
+                         desc_k_sw128(base + d * 8192) + 2 * k, id_k, (d | k) != 0);
+          tc_commit(empty(s));
+          tc_commit(u_full(acc));
+        } else {
+          tc_commit(empty(s));
+        }
+      }
+      if (p.want_dw) tc_commit(dw_full);
+    }
+  } else if (warp <= 8) {
+    // ===================== builders: group 0 = warps 1..4 (even tiles), group 1 = warps 5..8 (odd tiles) ==========
+    const int grp = (warp - 1) >> 2;
+    const int tb = threadIdx.x - 32 - grp * 128;
+    const int iy = tb / p.bw, ix = tb - iy * p.bw;
+    const int PWW = p.bw + 2, n_words = (2 * p.bh + 4) * PWW;
+    uint32_t* pb = patch + grp * C1_PATCH_WORDS;
+    uint8_t* stg = gbase + st_off + grp * CB_STAGE_BYTES;
+    const float neg = p.act == HM_ACT_LRELU ? p.slope : (p.act == HM_ACT_RELU ? 0.f : 1.f);
+    for (int it = grp; it < my_tiles; it += 2) {
+      const int t = blockIdx.x + it * gridDim.x;
+      const int b = t / per_img, rem = t - b * per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
+      const bool valid = wy < p.Hq && wx < p.Wq;
+      const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
+      mbar_wait(empty(grp), ((it >> 1) & 1) ^ 1);
+      if (p.want_dw) {
+        const int Y0 = 2 * ty * p.bh - 2, X0 = 2 * tx * p.bw - 2;
+        const __half* img = p.x + (size_t)b * p.H * p.W;
+        for (int i = tb; i < n_words; i += 128) {
+          const int pr = i / PWW, pw = i - pr * PWW;
+          const int Y = Y0 + pr, X = X0 + 2 * pw;
+          uint32_t v = 0;
+          if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
+          pb[i] = v;
+        }
+      }
+      // gradient rows: two halves of 32 channels, loads issued together
+#pragma unroll 1
+      for (int hh = 0; hh < 2; hh++) {
+        uint4 gv[4], pv[4];
+        uint2 kv[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (valid) {
+            gv[c] = *reinterpret_cast<const uint4*>(p.g + o + hh * 32 + c * 8);
+            pv[c] = *reinterpret_cast<const uint4*>(p.pl + o + hh * 32 + c * 8);
+            kv[c] = *reinterpret_cast<const uint2*>(p.idx + o + hh * 32 + c * 8);
+          } else {
+            gv[c] = pv[c] = make_uint4(0, 0, 0, 0);
+            kv[c] = make_uint2(0, 0);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
+          uint32_t hv[4];                     // g * act'(p), 8 halves
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
+            const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pw4[j]));
+            const float a0 = p.act == HM_ACT_RELU ? (pf.x > 0.f ? 1.f : 0.f) : (pf.x >= 0.f ? 1.f : neg);
+            const float a1 = p.act == HM_ACT_RELU ? (pf.y > 0.f ? 1.f : 0.f) : (pf.y >= 0.f ? 1.f : neg);
+            __half2 h = __floats2half2_rn(gf.x * a0, gf.y * a1);
+            hv[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int chunk = hh * 4 + c;
+#pragma unroll
+          for (int d = 0; d < 4; d++) {
+            uint32_t m[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint32_t kk = j < 2 ? kv[c].x : kv[c].y;
+              const uint32_t k0 = (kk >> (16 * (j & 1))) & 0xff, k1 = (kk >> (16 * (j & 1) + 8)) & 0xff;
+              m[j] = hv[j] & ((k0 == (uint32_t)d ? 0x0000ffffu : 0u) | (k1 == (uint32_t)d ? 0xffff0000u : 0u));
+            }
+            *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(tb, chunk)) = make_uint4(m[0], m[1], m[2], m[3]);
+          }
+        }
+      }
+      if (p.want_dw) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        uint32_t wd[20];
+#pragma unroll
+        for (int u = 0; u < 6; u++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) wd[u * 3 + j] = pb[(2 * iy + u) * PWW + ix + j];
+        wd[18] = 0x00003C00u;                 // A[w][36] = 1: column 36 of the weight gradient is the bias gradient
+        wd[19] = 0;
+#pragma unroll
+        for (int c = 0; c < 5; c++)
+          *reinterpret_cast<uint4*>(stg + CB_G_BYTES + sw128_off(tb, c)) =
+              make_uint4(wd[4 * c], wd[4 * c + 1], wd[4 * c + 2], wd[4 * c + 3]);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // patch buffer free for the next tile
+      }
+      fence_proxy_async();
+      mbar_arrive(full(grp));
+    }
+  } else {
+    // ===================== epilogue (warps 9..12) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int iy = row / p.bw, ix = row - iy * p.bw;
+    if (p.want_u) {
+      for (int it = 0; it < my_tiles; it++) {
+        const int acc = it & 1;
+        mbar_wait(u_full(acc), (it >> 1) & 1);
+        tc_fence_after();
+        const int t = blockIdx.x + it * gridDim.x;
+        const int b = t / per_img, rem = t - b * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
+        const bool valid = wy < p.Hq && wx < p.Wq;
+        const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + acc * 64;
+        uint32_t v[32], v2[16];
+        tmem_ld32(taddr, v);
+        tmem_ld16(taddr + 32, v2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(u_empty(acc));
+        if (valid) {
+          uint32_t pk[20];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            __half2 h = __floats2half2_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            __half2 h = __floats2half2_rn(__uint_as_float(v2[j]), __uint_as_float(v2[j + 1]));
+            pk[16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(p.u + o);
+#pragma unroll
+          for (int j = 0; j < 5; j++) d4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+      }
+    }
+    if (p.want_dw && my_tiles > 0) {
+      mbar_wait(dw_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 64;
+        uint32_t v[32], v2[16];
+        tmem_ld32(taddr, v);
+        tmem_ld16(taddr + 32, v2);
+        tmem_ld_wait();
+        float* dst = p.dwk + (size_t)(h * 128 + row) * 64;
+#pragma unroll
+        for (int j = 0; j < 32; j++) atomicAdd(dst + j, __uint_as_float(v[j]));
+#pragma unroll
+        for (int j = 0; j < 5; j++) atomicAdd(dst + 32 + j, __uint_as_float(v2[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dwk[(d,co)][k] -> master gradient dW[co][0][a][b] (adjoint of pack mode 15) and db[co] (column 36)
+__global__ void c1s2_bwd_fold_kernel(const float* __restrict__ dwk, float* __restrict__ dw, float* __restrict__ db,
+                                     int cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cout * 25) {
+    const int co = i / 25, a = (i % 25) / 5, bb = i % 5;
+    const int r = 4 - a, s = 4 - bb;
+    float acc = 0.f;
+    for (int d = 0; d < 4; d++) acc += dwk[(size_t)(d * cout + co) * 64 + (r + (d >> 1)) * 6 + (s + (d & 1))];
+    dw[i] = acc;
+  } else if (i < cout * 26 && db) {
+    const int co = i - cout * 25;
+    float acc = 0.f;
+    for (int d = 0; d < 4; d++) acc += dwk[(size_t)(d * cout + co) * 64 + 36];
+    db[co] = acc;
+  }
+}
+
+// dx[b][Y][X] = sum over the (up to 9) windows whose 6x6 patch covers pixel (Y,X) of U[window][patch position];
+// one thread per window writes its 2x2 pixels.
+__global__ void c1s2_col2im_kernel(const __half* __restrict__ u, __half* __restrict__ dx, int B, int Hq, int Wq) {
+  const long long n = (long long)B * Hq * Wq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int wx = (int)(i % Wq);
+    long long t = i / Wq;
+    const int wy = (int)(t % Hq);
+    const int b = (int)(t / Hq);
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int yy = wy + 1 - a;
+      if (yy < 0 || yy >= Hq) continue;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const int xx = wx + 1 - c;
+        if (xx < 0 || xx >= Wq) continue;
+        const __half* row = u + (((size_t)b * Hq + yy) * Wq + xx) * 64;
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(row + (2 * a) * 6 + 2 * c));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(row + (2 * a + 1) * 6 + 2 * c));
+        s00 += lo.x; s01 += lo.y; s10 += hi.x; s11 += hi.y;
+      }
+    }
+    const int W = 2 * Wq;
+    __half* o = dx + ((size_t)b * 2 * Hq + 2 * wy) * W + 2 * wx;
+    *reinterpret_cast<__half2*>(o) = __floats2half2_rn(s00, s01);
+    *reinterpret_cast<__half2*>(o + W) = __floats2half2_rn(s10, s11);
+  }
+}
+
+}  // namespace hm
+
+// Backward of hm_c1s2_conv's pooled form from the gradient g of the pooled tensor (see the kernel comment).
+//   dwk != NULL: dwk[256][64] fp32 += weight-gradient partials (caller zeroes; fold with hm_c1s2_bwd_fold);
+//   u   != NULL: u[B,H/2,W/2,64] = patch-space input gradient (needs wk2 = pack mode 16; fold with hm_c1s2_col2im).
+extern "C" int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, const uint8_t* idx, const void* wk2,
+                           float* dwk, void* u, int B, int H, int W, int act, float slope, void* stream) {
+  HM_CHECK_ARG(g && pooled && idx && B > 0 && H > 0 && W > 0 && (dwk || u), "hm_c1s2_bwd: bad argument");
+  HM_CHECK_ARG(!dwk || x, "hm_c1s2_bwd: the weight gradient needs the source image");
+  HM_CHECK_ARG(!u || wk2, "hm_c1s2_bwd: the input gradient needs the weights (pack mode 16)");
+  HM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "hm_c1s2_bwd: the image must have even height and width (%dx%d)", H, W);
+  HM_CHECK_ARG(act == HM_ACT_LINEAR || act == HM_ACT_LRELU || act == HM_ACT_RELU, "hm_c1s2_bwd: activation %d is not supported", act);
+  if ((((uintptr_t)x) & 3) || (((uintptr_t)g | (uintptr_t)pooled | (uintptr_t)wk2 | (uintptr_t)u) & 15) || (((uintptr_t)idx) & 7)) {
+    set_error("hm_c1s2_bwd: x must be 4-byte, idx 8-byte, g / pooled / wk2 / u 16-byte aligned");
+    return HM_ERR_ALIGN;
+  }
+  if (!c1_encode_fn()) {
+    set_error("hm_c1s2_bwd: cuTensorMapEncodeTiled is not available from this driver");
+    return HM_ERR_CUDA;
+  }
+  CbParams p;
+  p.B = B; p.H = H; p.W = W; p.Hq = H / 2; p.Wq = W / 2;
+  int bw = 1;
+  while (bw * 2 <= p.Wq && bw < 128) bw *= 2;
+  p.bw = bw; p.bh = 128 / bw;
+  p.tiles_x = (p.Wq + p.bw - 1) / p.bw;
+  p.tiles_y = (p.Hq + p.bh - 1) / p.bh;
+  p.n_tiles = B * p.tiles_x * p.tiles_y;
+  p.act = act; p.slope = slope; p.want_dw = dwk ? 1 : 0; p.want_u = u ? 1 : 0;
+  p.x = (const __half*)x; p.g = (const __half*)g; p.pl = (const __half*)pooled; p.idx = idx; p.dwk = dwk; p.u = (__half*)u;
+  CUtensorMap tmW;
+  {
+    cuuint64_t dims[2] = {64, 256};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t es[2] = {1, 1};
+    void* wp = const_cast<void*>(wk2 ? wk2 : g);         // unused (never dereferenced) without the input gradient
+    CUresult r = c1_encode_fn()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wp, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("hm_c1s2_bwd: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+      return HM_ERR_CUDA;
+    }
+  }
+  const size_t smem = 1024 + 256 * 128 + 2 * CB_STAGE_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(c1s2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("hm_c1s2_bwd: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+      return HM_ERR_CUDA;
+    }
+    attr = true;
+  }
+  int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  c1s2_bwd_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(tmW, p);
+  HM_CHECK_LAUNCH("hm_c1s2_bwd");
+  return HM_OK;
+}
+
+extern "C" int hm_c1s2_bwd_fold(const float* dwk, float* dw, float* db, int cout, void* stream) {
+  HM_CHECK_ARG(dwk && dw && cout == 64, "hm_c1s2_bwd_fold: bad argument (cout must be 64)");
+  c1s2_bwd_fold_kernel<<<(cout * 26 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dwk, dw, db, cout);
+  HM_CHECK_LAUNCH("hm_c1s2_bwd_fold");
+  return HM_OK;
+}
+
+extern "C" int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream) {
+  HM_CHECK_ARG(u && dx && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "hm_c1s2_col2im: bad argument");
+  HM_CHECK_ARG((((uintptr_t)u) & 15) == 0 && (((uintptr_t)dx) & 3) == 0, "hm_c1s2_col2im: misaligned pointer");
+  const long long n = (long long)B * (H / 2) * (W / 2);
+  long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  c1s2_col2im_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)u, (__half*)dx, B, H / 2, W / 2);
+  HM_CHECK_LAUNCH("hm_c1s2_col2im");
+  return HM_OK;
+}

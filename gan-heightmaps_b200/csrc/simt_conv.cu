@@ -346,6 +346,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       int r = k / 6 - (dd >> 1), q = k % 6 - (dd & 1);
       if (r >= 0 && r < 5 && q >= 0 && q < 5) val = w[((size_t)co * 5 + (4 - r)) * 5 + (4 - q)];
     }
+  } else if (mode == 16) {
+    // hm_c1s2_bwd input-gradient operand: mode 15 transposed per window position, Wk2[d*64+k][co] = Wk15[d*cout+co][k]
+    int co = (int)(i % cout);
+    int row = (int)(i / cout);
+    int dd = row / 64, k = row % 64;
+    val = 0.f;
+    if (k < 36) {
+      int r = k / 6 - (dd >> 1), q = k % 6 - (dd & 1);
+      if (r >= 0 && r < 5 && q >= 0 && q < 5) val = w[((size_t)co * 5 + (4 - r)) * 5 + (4 - q)];
+    }
   } else {
     val = w[i];
   }
@@ -479,10 +489,12 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || mode == 14 || mode == 15,
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 16),
                "hm_pack_conv_weight: bad mode %d", mode);
   HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
-  HM_CHECK_ARG(mode != 15 || (cin == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 15 needs Cin == 1 and a 5x5 filter");
+  HM_CHECK_ARG((mode != 15 && mode != 16) || (cin == 1 && kh == 5 && kw == 5),
+               "hm_pack_conv_weight: modes 15/16 need Cin == 1 and a 5x5 filter");
+  HM_CHECK_ARG(mode != 16 || cout == 64, "hm_pack_conv_weight: mode 16 needs Cout == 64");
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
@@ -491,7 +503,7 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   if (mode == 11) n = 64LL * cout;
   if (mode == 12) n = 16LL * cout * cin;
   if (mode == 14) n = 64LL * cin;
-  if (mode == 15) n = 256LL * cout;
+  if (mode == 15 || mode == 16) n = 256LL * cout;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)

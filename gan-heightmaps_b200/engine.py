@@ -198,8 +198,13 @@ class ConvOp(object):
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
         if self.c1dg and self.wk is None:
             self.wk = rt.empty((64 * 64,))
-        if self.pool_fused is not None and self.wk is None:
-            self.wk = rt.empty((256 * 64,))
+        if self.pool_fused is not None:
+            if self.wk is None:
+                self.wk = rt.empty((256 * 64,))
+                self.wk2 = rt.empty((256 * 64,))
+                self.dwk = rt.zeros((256 * 64,), torch.float32)
+            self.ubuf = rt.empty((B, self.Hv // 2, self.Wv // 2, 64))      # patch-space input gradient
+            return          # no im2col tensor, no packed-gradient buffers: forward and backward are hm_c1s2_* calls
         n = self.K * self.Cout
         if self.col1:
             self.xc = rt.empty((B, self.Hv, self.Wv, 64))
@@ -231,6 +236,10 @@ class ConvOp(object):
         if self.kind == "dense":
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 4, self.Cout, self.Cin, 1, 1, 0, 0, rt.cd)
         elif self.kind == "conv":
+            if self.pool_fused is not None:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 15, self.Cout, 1, 5, 5, 0, 0, rt.cd)
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk2), 16, self.Cout, 1, 5, 5, 0, 0, rt.cd)
+                return
             if self.col1:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 11, self.Cout, 1, self.kh, self.kw, 0, 0, rt.cd)
             elif not self.tc_fwd:
@@ -239,8 +248,6 @@ class ConvOp(object):
             else:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 8 if self.up2 else 5, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
-            if self.pool_fused is not None:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 15, self.Cout, 1, 5, 5, 0, 0, rt.cd)
             if self.c1dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 14, 1, self.Cin, 5, 5, 0, 0, rt.cd)
             if self.dg2_cat:
@@ -344,7 +351,7 @@ class ConvOp(object):
         x1 = _ptr(self.x1.b(lo, hi))
         x2 = _ptr(self.x2.b(lo, hi)) if self.x2 is not None else None
         bias = _ptr(self.net.pview(self.bias))
-        y = _ptr(self.out.b(lo, hi))
+        y = _ptr(self.out.b(lo, hi)) if self.out.buf is not None else None
         if self.kind == "deconv":
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -379,7 +386,32 @@ class ConvOp(object):
             d = self._fwd_desc(rt, n)
             rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f), bias, y, None)
 
+    def _bwd_pool_fused(self, rt, lo, hi, wgrad, input_grad):
+        """conv5x5(1->64)+activation+max-pool backward straight from the pooled tensor's gradient (hm_c1s2_bwd):
+        the full-resolution gradient of the un-pooled activation is never written."""
+        n = hi - lo
+        pool = self.pool_fused
+        g, pl, idx = _ptr(pool.out.g(lo, hi)), _ptr(pool.out.b(lo, hi)), _ptr(pool.idx[lo:hi])
+        t1 = self.x1.want_grad or (input_grad and self.x1.kind == "input" and self.x1.grad is not None)
+        act, slope = ACT[self.act.name], self.act.slope
+        x1 = _ptr(self.x1.b(lo, hi))
+        u = _ptr(self.ubuf[lo:hi]) if t1 else None
+        if wgrad:
+            self.dwk.zero_()
+        if wgrad or t1:
+            rt.call("hm_c1s2_bwd", x1, g, pl, idx, _ptr(self.wk2) if t1 else None, _ptr(self.dwk) if wgrad else None,
+                    u, n, self.Hv, self.Wv, act, slope)
+        if wgrad:
+            rt.call("hm_c1s2_bwd_fold", _ptr(self.dwk), _ptr(self.net.gview(self.W)), _ptr(self.net.gview(self.bias)),
+                    self.Cout)
+        if t1:
+            if self.x1.take_acc():
+                raise NotImplementedError("accumulating into the source gradient of the fused first layer")
+            rt.call("hm_c1s2_col2im", u, _ptr(self.x1.g(lo, hi)), n, self.Hv, self.Wv)
+
     def bwd(self, rt, lo, hi, wgrad, input_grad):
+        if self.pool_fused is not None:
+            return self._bwd_pool_fused(rt, lo, hi, wgrad, input_grad)
         n = hi - lo
         g = self.out.g(lo, hi)
         if self.act.name != "linear" and not self.out.grad_is_preact:
@@ -398,8 +430,6 @@ class ConvOp(object):
                                 _ptr(self.dwp[(u * self.kw + v) * per:]))
                 mode = 2
             elif self.col1:
-                if self.pool_fused is not None:      # the fused forward pass did not write the im2col tensor
-                    rt.call("hm_im2col_c1", x1, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.kh, self.kw, self.pad)
                 d = self._col1_desc(rt, n)
                 rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
                 mode = 0              # rows [0, kh*kw) of the [64][Cout] result are the packed gradient
@@ -566,6 +596,8 @@ class PoolOp(object):
                 rt.cd, hi - lo, H, W, Cn)
 
     def bwd(self, rt, lo, hi, wgrad, input_grad):
+        if self.fused:            # the producing convolution's backward reads the pooled gradient itself (hm_c1s2_bwd)
+            return
         H, W, Cn = self.x.shape
         assert self.x.consumers == 1
         self.x.gw = True
@@ -763,6 +795,7 @@ class Net(object):
                     and cv.act.name in ("linear", "leaky_rectify", "rectify") and x.shape[0] % 2 == 0
                     and x.shape[1] % 2 == 0):
                 cv.pool_fused, pop.fused = pop, True
+                x.fused_away = True          # the un-pooled activation and its gradient are never materialised
             return out
         if isinstance(layer, (L.Conv2DLayer, L.TransposedConv2DLayer, L.DenseLayer)):
             src = self._lower(layer.input_layer, None)
@@ -815,6 +848,8 @@ class Net(object):
         rt = self.rt
         if B > self.B:
             for v in self.vals:
+                if v.kind == "buf" and getattr(v, "fused_away", False):
+                    continue
                 if v.kind == "buf":
                     v.buf = rt.empty((B,) + v.shape)
                     v.grad = rt.empty((B,) + v.shape)

@@ -149,6 +149,17 @@ int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, 
  * act: HM_ACT_LINEAR, HM_ACT_LRELU or HM_ACT_RELU (monotonic, so it commutes with the max). */
 int hm_c1s2_conv(const void* x, const void* wk, const float* bias, void* y, uint8_t* idx, int B, int H, int W,
                  int ncols, int act, float slope, void* stream);
+/* Backward of the pooled form from g = d loss / d (pooled output) [B,H/2,W/2,64]; `pooled`, `idx` as written by the
+ * forward pass.  With G'[w][(d,co)] = g[w][co] * act'(pooled[w][co]) * [idx[w][co] == d]:
+ *   dwk != NULL: dwk[(d,co)][k] (fp32 [256][64], caller zeroes) += sum_w G'[w][(d,co)] * A[w][k], A[w][36] = 1;
+ *                hm_c1s2_bwd_fold turns it into dW[co][0][5][5] (Lasagne layout) and db[co];
+ *   u   != NULL: u[B,H/2,W/2,64], u[w][k] = sum_(d,co) G'[w][(d,co)] * wk2[d*64+k][co] (wk2 = pack mode 16);
+ *                hm_c1s2_col2im sums the patch contributions into dx[B,H,W] (one channel).
+ * The full-resolution gradient of the un-pooled activation is never materialised. */
+int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, const uint8_t* idx, const void* wk2, float* dwk,
+                void* u, int B, int H, int W, int act, float slope, void* stream);
+int hm_c1s2_bwd_fold(const float* dwk, float* dw, float* db, int cout, void* stream);
+int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
 
 /* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
  *  mode 0: Conv2DLayer W (Cout,Cin,kh,kw)      -> Wp[(r*kw+s)*Cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]   (forward)

@@ -197,6 +197,15 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     r, s_ = uu - (dd >> 1), vv - (dd & 1)
                     if 0 <= r < 5 and 0 <= s_ < 5:
                         out[dd, :, uu * 6 + vv] = Wc[:, r, s_]
+    elif mode == 16:
+        Wc = W.reshape(cout, 5, 5)[:, ::-1, ::-1]
+        out = np.zeros((4, 64, cout), np.float32)
+        for dd in range(4):
+            for uu in range(6):
+                for vv in range(6):
+                    r, s_ = uu - (dd >> 1), vv - (dd & 1)
+                    if 0 <= r < 5 and 0 <= s_ < 5:
+                        out[dd, uu * 6 + vv, :] = Wc[:, r, s_]
     elif mode == 7:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
@@ -584,6 +593,49 @@ def hm_c1s2_conv(x, wk, bias, y, idx, B, H, W, ncols, act, slope, stream=None):
         out = m
     res = _act(out + bv, act, slope)
     _a(y, B * Hq * Wq * 64, np.float16)[:] = res.numpy().reshape(-1).astype(np.float16)
+    return 0
+
+
+def hm_c1s2_bwd(x, g, pooled, idx, wk2, dwk, u, B, H, W, act, slope, stream=None):
+    Hq, Wq = H // 2, W // 2
+    n = B * Hq * Wq * 64
+    gg = _t(_a(g, n, np.float16)) * _act_grad_from_out(_t(_a(pooled, n, np.float16)), act, slope)
+    gg = gg.half().float().reshape(B * Hq * Wq, 64)                            # the kernel rounds g*act' to fp16
+    k = torch.from_numpy(_a(idx, n, np.uint8).astype(np.int64)).reshape(B * Hq * Wq, 64)
+    G4 = torch.stack([gg * (k == d) for d in range(4)], 1).reshape(B * Hq * Wq, 256)   # [(w)][(d,co)]
+    if dwk:
+        a = _t(_a(x, B * H * W, np.float16)).reshape(B, 1, H, W)
+        cols = F.unfold(a, (6, 6), padding=2, stride=2).permute(0, 2, 1).reshape(B * Hq * Wq, 36)
+        A = torch.zeros(B * Hq * Wq, 64)
+        A[:, :36] = cols
+        A[:, 36] = 1.0
+        _a(dwk, 256 * 64, np.float32)[:] += (G4.double().t() @ A.double()).float().numpy().reshape(-1)
+    if u:
+        w2 = _t(_a(wk2, 256 * 64, np.float16)).reshape(4, 64, 64)             # [d][k][co]
+        U = torch.einsum("wdc,dkc->wk", G4.reshape(-1, 4, 64), w2)
+        _a(u, n, np.float16)[:] = U.numpy().reshape(-1).astype(np.float16)
+    return 0
+
+
+def hm_c1s2_bwd_fold(dwk, dw, db, cout, stream=None):
+    D = _a(dwk, 256 * 64, np.float32).reshape(4, cout, 64)
+    out = np.zeros((cout, 5, 5), np.float32)
+    for a in range(5):
+        for b in range(5):
+            r, s_ = 4 - a, 4 - b
+            for dd in range(4):
+                out[:, a, b] += D[dd, :, (r + (dd >> 1)) * 6 + (s_ + (dd & 1))]
+    _a(dw, cout * 25, np.float32)[:] = out.reshape(-1)
+    if db:
+        _a(db, cout, np.float32)[:] = D[:, :, 36].sum(0)
+    return 0
+
+
+def hm_c1s2_col2im(u, dx, B, H, W, stream=None):
+    Hq, Wq = H // 2, W // 2
+    U = _t(_a(u, B * Hq * Wq * 64, np.float16)).reshape(B, Hq * Wq, 64)[:, :, :36].permute(0, 2, 1)   # [B,36,L]
+    img = F.fold(U, (H, W), (6, 6), padding=2, stride=2)                       # adjoint of the 6x6 stride-2 unfold
+    _a(dx, B * H * W, np.float16)[:] = img.numpy().reshape(-1).astype(np.float16)
     return 0
 
 

@@ -47,3 +47,12 @@ def test_c1s2_conv_pooled_first_layer_and_last_layer_input_gradient(case):
     the same fp16 data: 3e-3 of the output scale (fp16 operands and output, fp32 accumulation)."""
     rel, line = tc_probe.run_c1_case(*case)
     assert rel <= 3e-3, line
+
+
+@pytest.mark.parametrize("case", tc_probe.C1B_CASES, ids=[c[0] for c in tc_probe.C1B_CASES])
+def test_c1s2_bwd_pooled_first_layer_gradients(case):
+    """hm_c1s2_bwd + hm_c1s2_bwd_fold + hm_c1s2_col2im: weight, bias and input gradient of the discriminator's
+    conv5x5(1->64)+LeakyReLU+max-pool straight from the pooled tensor's gradient, against float32 torch adjoints
+    on the same fp16 data: 3e-3 of each gradient's scale (g*act' and the patch-space gradient are rounded to fp16)."""
+    rel, line = tc_probe.run_c1bwd_case(*case)
+    assert rel <= 3e-3, line

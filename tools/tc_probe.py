@@ -293,6 +293,103 @@ def run_c1_case(name, B, H, W, pooled):
     return err, "%-26s max_err/scale %.3g" % (name, err)
 
 
+C1B_CASES = [
+    # name, B, H, W
+    ("c1bwd_64", 2, 64, 64),
+    ("c1bwd_512", 2, 512, 512),
+    ("c1bwd_ragged_24x40", 3, 24, 40),
+    ("c1bwd_2x260", 2, 2, 260),
+]
+
+
+def run_c1bwd_case(name, B, H, W):
+    """hm_c1s2_bwd (+ fold, col2im) against the float32 adjoints of conv5x5(1->64)+bias+LeakyReLU(0.2)+max-pool on the
+    same fp16 data; the forward pass (pooled values, argmax routing) comes from hm_c1s2_conv."""
+    import torch.nn.functional as F
+    torch.manual_seed(abs(hash(name)) % 1000)
+    x = torch.randn(B, H, W, device="cuda").half()
+    Wm = (torch.randn(64, 1, 5, 5, device="cuda") * 0.2).half().float()
+    bias = torch.randn(64, device="cuda") * 0.1
+    Hq, Wq = H // 2, W // 2
+    wk = torch.empty(256 * 64, device="cuda", dtype=torch.float16)
+    wk2 = torch.empty(256 * 64, device="cuda", dtype=torch.float16)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wk.data_ptr(), 15, 64, 1, 5, 5, 0, 0, 1, None)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wk2.data_ptr(), 16, 64, 1, 5, 5, 0, 0, 1, None)
+    pooled = torch.empty(B, Hq, Wq, 64, device="cuda", dtype=torch.float16)
+    idx = torch.empty(B, Hq, Wq, 64, device="cuda", dtype=torch.uint8)
+    _lib.call("hm_c1s2_conv", x.data_ptr(), wk.data_ptr(), bias.data_ptr(), pooled.data_ptr(), idx.data_ptr(), B, H, W,
+              256, 1, 0.2, None)
+    g = torch.randn(B, Hq, Wq, 64, device="cuda").half()
+    dwk = torch.zeros(256 * 64, device="cuda")
+    u = torch.full((B, Hq, Wq, 64), 7.0, device="cuda", dtype=torch.float16)
+    dx = torch.full((B, H, W), 7.0, device="cuda", dtype=torch.float16)
+    dw = torch.zeros(64 * 25, device="cuda")
+    db = torch.zeros(64, device="cuda")
+    # the two uses of the step: weight gradient only, then input gradient only; and both at once must agree
+    _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), None, dwk.data_ptr(), None,
+              B, H, W, 1, 0.2, None)
+    _lib.call("hm_c1s2_bwd", None, g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(),
+              B, H, W, 1, 0.2, None)
+    _lib.call("hm_c1s2_bwd_fold", dwk.data_ptr(), dw.data_ptr(), db.data_ptr(), 64, None)
+    _lib.call("hm_c1s2_col2im", u.data_ptr(), dx.data_ptr(), B, H, W, None)
+    dwk2 = torch.zeros(256 * 64, device="cuda")
+    u2 = torch.zeros_like(u)
+    _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(),
+              dwk2.data_ptr(), u2.data_ptr(), B, H, W, 1, 0.2, None)
+    torch.cuda.synchronize()
+    # reference in float32 with the kernel's own routing (argmax bytes) and activation derivative (sign of the pooled
+    # value): full-resolution gradient, then the convolution's adjoints as GEMMs over unfolded patches
+    gp = g.float() * torch.where(pooled.float() >= 0, 1.0, 0.2)
+    gp = gp.half().float()
+    dyf = torch.zeros(B, Hq, 2, Wq, 2, 64, device="cuda")
+    k = idx.long()
+    for d in range(4):
+        dyf[:, :, d >> 1, :, d & 1, :] = gp * (k == d)
+    dyf = dyf.reshape(B, H * W, 64)                                               # [B, L, co]
+    cols = F.unfold(x.float()[:, None], 5, padding=2)                             # [B, 25, L], tap (r,s) = x[p+(r,s)-2]
+    Wf = Wm.flip(2, 3).reshape(64, 25)                                            # correlation taps
+    gW = torch.einsum("bkl,blc->ck", cols.double(), dyf.double()).float().reshape(64, 1, 5, 5).flip(2, 3)
+    gb = dyf.sum((0, 1))
+    gx = F.fold(torch.einsum("ck,blc->bkl", Wf, dyf), (H, W), 5, padding=2)[:, 0]
+    def rel(a, b):
+        return float((a - b).abs().max()) / float(b.abs().max())
+    e_w = rel(dw.reshape(64, 1, 5, 5), gW)
+    e_b = rel(db, gb)
+    e_x = rel(dx.float(), gx)
+    kk = torch.arange(64, device="cuda")
+    live = (kk < 37)
+    e_both = max(rel(dwk2.reshape(256, 64)[:, live], dwk.reshape(256, 64)[:, live]),
+                 float((u2[..., :36].float() - u[..., :36].float()).abs().max()) / float(u[..., :36].float().abs().max()))
+    line = "%-22s dW %.3g  db %.3g  dx %.3g  both-vs-separate %.3g" % (name, e_w, e_b, e_x, e_both)
+    return max(e_w, e_b, e_x, e_both), line
+
+
+def perf_c1bwd():
+    B, H, W = 64, 512, 512
+    x = torch.randn(B, H, W, device="cuda").half()
+    g = torch.randn(B, 256, 256, 64, device="cuda").half()
+    pooled = torch.randn(B, 256, 256, 64, device="cuda").half()
+    idx = torch.randint(0, 4, (B, 256, 256, 64), device="cuda", dtype=torch.uint8)
+    wk2 = torch.randn(256 * 64, device="cuda").half()
+    dwk = torch.zeros(256 * 64, device="cuda")
+    u = torch.empty(B, 256, 256, 64, device="cuda", dtype=torch.float16)
+    dx = torch.empty(B, H, W, device="cuda", dtype=torch.float16)
+    runs = (("D1 bwd weight gradient x64", lambda: _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), None, dwk.data_ptr(), None, 64, H, W, 1, 0.2, None), 64 * 65536 * (128 + 128 + 64) / 1e9),
+            ("D1 bwd input gradient x32 (patch space)", lambda: _lib.call("hm_c1s2_bwd", None, g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(), 32, H, W, 1, 0.2, None), 32 * 65536 * (128 + 128 + 64 + 80) / 1e9),
+            ("D1 bwd col2im x32", lambda: _lib.call("hm_c1s2_col2im", u.data_ptr(), dx.data_ptr(), 32, H, W, None), 32 * 65536 * (72 + 8) / 1e9))
+    for nm, fn, gb in runs:
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print("perf %-44s %8.3f ms  %7.1f GB/s (algorithmic bytes %.2f GB)" % (nm, ms, gb / ms * 1e3, gb), flush=True)
+
+
 def perf_c1():
     for pooled, nm in ((1, "D1 conv5x5(1->64)+lrelu+pool @512^2 x64"), (0, "G-out dgrad 1->64 @512^2 x32")):
         B = 64 if pooled else 32
@@ -363,6 +460,15 @@ if __name__ == "__main__":
                 print("c1 %-24s EXC %s" % (c[0], e), flush=True)
                 break
         perf_c1()
+        sys.exit(0)
+    if sys.argv[1:] == ["c1bwd"]:
+        for c in C1B_CASES:
+            try:
+                print(run_c1bwd_case(*c)[1], flush=True)
+            except Exception as e:
+                print("c1bwd %-22s EXC %s" % (c[0], e), flush=True)
+                break
+        perf_c1bwd()
         sys.exit(0)
     if sys.argv[1:] == ["s2"]:
         for c in S2_CASES:
