@@ -57,7 +57,7 @@ _PROTOS = {
     "hm_act_bwd": ([_P, _P, _P, _I, _LL, _I, _F, _I, _P], C.c_int),
     "hm_col_sum": ([_P, _I, _LL, _I, _P, _P], C.c_int),
     "hm_maxpool2_fwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
-    "hm_maxpool2_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P], C.c_int),
+    "hm_maxpool2_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P], C.c_int),
     "hm_upsample2_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_upsample2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -475,59 +475,68 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
       const bool valid = wy < p.Hq && wx < p.Wq;
       const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
-      mbar_wait(empty(grp), ((it >> 1) & 1) ^ 1);
+      // issue every global load of this tile up front (24 gradient / activation / argmax loads + the patch words):
+      // one round trip per tile instead of three
+      uint4 gv[8], pv[8];
+      uint2 kv[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (valid) {
+          gv[c] = *reinterpret_cast<const uint4*>(p.g + o + c * 8);
+          pv[c] = *reinterpret_cast<const uint4*>(p.pl + o + c * 8);
+          kv[c] = *reinterpret_cast<const uint2*>(p.idx + o + c * 8);
+        } else {
+          gv[c] = pv[c] = make_uint4(0, 0, 0, 0);
+          kv[c] = make_uint2(0, 0);
+        }
+      }
+      uint32_t pre[C1_PRE];
       if (p.want_dw) {
         const int Y0 = 2 * ty * p.bh - 2, X0 = 2 * tx * p.bw - 2;
         const __half* img = p.x + (size_t)b * p.H * p.W;
-        for (int i = tb; i < n_words; i += 128) {
-          const int pr = i / PWW, pw = i - pr * PWW;
-          const int Y = Y0 + pr, X = X0 + 2 * pw;
+#pragma unroll
+        for (int j = 0; j < C1_PRE; j++) {
+          const int i = tb + 128 * j;
           uint32_t v = 0;
-          if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
-          pb[i] = v;
+          if (i < n_words) {
+            const int pr = i / PWW, pw = i - pr * PWW;
+            const int Y = Y0 + pr, X = X0 + 2 * pw;
+            if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
+          }
+          pre[j] = v;
         }
       }
-      // gradient rows: two halves of 32 channels, loads issued together
-#pragma unroll 1
-      for (int hh = 0; hh < 2; hh++) {
-        uint4 gv[4], pv[4];
-        uint2 kv[4];
+      mbar_wait(empty(grp), ((it >> 1) & 1) ^ 1);
+      if (p.want_dw) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          if (valid) {
-            gv[c] = *reinterpret_cast<const uint4*>(p.g + o + hh * 32 + c * 8);
-            pv[c] = *reinterpret_cast<const uint4*>(p.pl + o + hh * 32 + c * 8);
-            kv[c] = *reinterpret_cast<const uint2*>(p.idx + o + hh * 32 + c * 8);
-          } else {
-            gv[c] = pv[c] = make_uint4(0, 0, 0, 0);
-            kv[c] = make_uint2(0, 0);
-          }
+        for (int j = 0; j < C1_PRE; j++) {
+          const int i = tb + 128 * j;
+          if (i < n_words) pb[i] = pre[j];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
+        uint32_t hv[4];                     // g * act'(p), 8 halves
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
+          const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pw4[j]));
+          const float a0 = p.act == HM_ACT_RELU ? (pf.x > 0.f ? 1.f : 0.f) : (pf.x >= 0.f ? 1.f : neg);
+          const float a1 = p.act == HM_ACT_RELU ? (pf.y > 0.f ? 1.f : 0.f) : (pf.y >= 0.f ? 1.f : neg);
+          __half2 h = __floats2half2_rn(gf.x * a0, gf.y * a1);
+          hv[j] = *reinterpret_cast<uint32_t*>(&h);
         }
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
-          uint32_t hv[4];                     // g * act'(p), 8 halves
+        for (int d = 0; d < 4; d++) {
+          uint32_t m[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
-            const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pw4[j]));
-            const float a0 = p.act == HM_ACT_RELU ? (pf.x > 0.f ? 1.f : 0.f) : (pf.x >= 0.f ? 1.f : neg);
-            const float a1 = p.act == HM_ACT_RELU ? (pf.y > 0.f ? 1.f : 0.f) : (pf.y >= 0.f ? 1.f : neg);
-            __half2 h = __floats2half2_rn(gf.x * a0, gf.y * a1);
-            hv[j] = *reinterpret_cast<uint32_t*>(&h);
+            const uint32_t kk = j < 2 ? kv[c].x : kv[c].y;
+            const uint32_t k0 = (kk >> (16 * (j & 1))) & 0xff, k1 = (kk >> (16 * (j & 1) + 8)) & 0xff;
+            m[j] = hv[j] & ((k0 == (uint32_t)d ? 0x0000ffffu : 0u) | (k1 == (uint32_t)d ? 0xffff0000u : 0u));
           }
-          const int chunk = hh * 4 + c;
-#pragma unroll
-          for (int d = 0; d < 4; d++) {
-            uint32_t m[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const uint32_t kk = j < 2 ? kv[c].x : kv[c].y;
-              const uint32_t k0 = (kk >> (16 * (j & 1))) & 0xff, k1 = (kk >> (16 * (j & 1) + 8)) & 0xff;
-              m[j] = hv[j] & ((k0 == (uint32_t)d ? 0x0000ffffu : 0u) | (k1 == (uint32_t)d ? 0xffff0000u : 0u));
-            }
-            *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(tb, chunk)) = make_uint4(m[0], m[1], m[2], m[3]);
-          }
+          *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(tb, c)) = make_uint4(m[0], m[1], m[2], m[3]);
         }
       }
       if (p.want_dw) {

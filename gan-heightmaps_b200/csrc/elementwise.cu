@@ -566,9 +566,13 @@ __global__ void maxpool2_fwd_v8_kernel(const T* __restrict__ x, T* __restrict__ 
 }
 
 template <typename T>
-__global__ void maxpool2_bwd_v8_kernel(const T* __restrict__ dp, const T* __restrict__ p,
-                                       const uint8_t* __restrict__ idx, T* __restrict__ dx, int B, int H, int W, int C,
-                                       int act, float slope) {
+__global__ void __launch_bounds__(256)
+    maxpool2_bwd_v8_kernel(const T* __restrict__ dp, const T* __restrict__ p, const uint8_t* __restrict__ idx,
+                           T* __restrict__ dx, int B, int H, int W, int C, int act, float slope, float* db) {
+  // db (optional): per-channel sum of the scattered gradient = bias gradient of the convolution that fed the pool.
+  // Needs 256 % (C/8) == 0 so that a thread keeps its channel group over the grid-stride loop.
+  __shared__ float shb[256 * 8];
+  float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int Hp = H >> 1, Wp = W >> 1, cg = C >> 3;
   const long long n8 = (long long)B * Hp * Wp * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
@@ -588,6 +592,7 @@ __global__ void maxpool2_bwd_v8_kernel(const T* __restrict__ dp, const T* __rest
     for (int j = 0; j < 8; j++) {
       const float gg = gv[j] * act_grad_from_out(pv[j], act, slope);
       const uint32_t k = ((j < 4 ? kk.x : kk.y) >> (8 * (j & 3))) & 0xff;
+      bs[j] += gg;
       o0[j] = k == 0 ? gg : 0.f;
       o1[j] = k == 1 ? gg : 0.f;
       o2[j] = k == 2 ? gg : 0.f;
@@ -598,6 +603,18 @@ __global__ void maxpool2_bwd_v8_kernel(const T* __restrict__ dp, const T* __rest
     store8(base + C, o1);
     store8(base + (size_t)W * C, o2);
     store8(base + (size_t)W * C + C, o3);
+  }
+  if (db) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) shb[threadIdx.x * 8 + j] = bs[j];
+    __syncthreads();
+    if ((int)threadIdx.x < cg) {
+      for (int l = threadIdx.x + cg; l < 256; l += cg)
+#pragma unroll
+        for (int j = 0; j < 8; j++) bs[j] += shb[l * 8 + j];
+#pragma unroll
+      for (int j = 0; j < 8; j++) atomicAdd(db + threadIdx.x * 8 + j, bs[j]);
+    }
   }
 }
 
@@ -990,20 +1007,22 @@ extern "C" int hm_maxpool2_fwd(const void* x, void* p, uint8_t* idx, int dtype, 
 }
 
 extern "C" int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx, void* dx, int dtype, int B,
-                               int H, int W, int C, int act, float slope, void* stream) {
+                               int H, int W, int C, int act, float slope, float* db, void* stream) {
   CHECK_DTYPE(dtype, "hm_maxpool2_bwd");
   HM_CHECK_ARG(dp && p && idx && dx && B > 0 && H >= 2 && W >= 2 && C > 0, "hm_maxpool2_bwd: bad argument");
-  HM_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "hm_maxpool2_bwd: odd spatial size");
   long long n = (long long)B * (H / 2) * (W / 2) * C;
   if (C % 8 == 0 && al16(dp) && al16(p) && al16(dx) && (((uintptr_t)idx) & 7) == 0) {
+    const bool fuse_db = db && (256 % (C / 8) == 0);
     DISPATCH_T(dtype, (maxpool2_bwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
-                          (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope)));
+                          (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope, fuse_db ? db : nullptr)));
     HM_CHECK_LAUNCH("hm_maxpool2_bwd");
+    if (db && !fuse_db) return hm_col_sum(dx, dtype, (long long)B * H * W, C, db, stream);
     return HM_OK;
   }
   DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope)));
   HM_CHECK_LAUNCH("hm_maxpool2_bwd");
+  if (db) return hm_col_sum(dx, dtype, (long long)B * H * W, C, db, stream);
   return HM_OK;
 }
 

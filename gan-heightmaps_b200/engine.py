@@ -179,6 +179,7 @@ class ConvOp(object):
         # hm_c1s2_conv (in-kernel im2col of a one-channel image): (a) this layer + its 2x2 max-pool in one pass, set by
         # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
         self.pool_fused = None
+        self.db_done = False
         self.wk = None
         self.c1dg = (rt.precision == "fast" and kind == "conv" and self.up == _lib.UP_NEAREST2 and self.x2 is None
                      and self.Cout == 1 and self.Cin == 64 and self.kh == 5 and self.kw == 5 and self.pad == 2
@@ -460,10 +461,13 @@ class ConvOp(object):
                 mode = 4 if self.kind == "dense" else 0
             rt.call("hm_unpack_conv_wgrad", _ptr(self.dwp), _ptr(self.net.gview(self.W)), mode, self.Cout,
                     self.Cin, self.kh, self.kw)
-            M = n * self.out.shape[0] * self.out.shape[1]
-            db = self.net.gview(self.bias)
-            db.zero_()
-            rt.call("hm_col_sum", _ptr(g), rt.cd, M, self.Cout, _ptr(db))
+            if self.db_done:              # the max-pool backward already summed the bias gradient
+                self.db_done = False
+            else:
+                M = n * self.out.shape[0] * self.out.shape[1]
+                db = self.net.gview(self.bias)
+                db.zero_()
+                rt.call("hm_col_sum", _ptr(g), rt.cd, M, self.Cout, _ptr(db))
         # input gradient
         t1 = self.x1.want_grad or (input_grad and self.x1.kind == "input" and self.x1.grad is not None)
         t2 = self.x2 is not None and (self.x2.want_grad or (input_grad and self.x2.kind == "input"
@@ -580,6 +584,7 @@ class PoolOp(object):
         self.net, self.x, self.out, self.act = net, x, out, act
         self.idx = None
         self.fused = False
+        self.prod = None          # the ConvOp that wrote x (set by Net)
 
     def alloc(self, rt, B):
         H, W, Cn = self.out.shape
@@ -601,8 +606,15 @@ class PoolOp(object):
         H, W, Cn = self.x.shape
         assert self.x.consumers == 1
         self.x.gw = True
+        db = None
+        if wgrad and self.prod is not None and self.prod.kind == "conv":
+            # the scattered gradient is exactly what the producing convolution sums for its bias gradient
+            dbt = self.net.gview(self.prod.bias)
+            dbt.zero_()
+            db = _ptr(dbt)
+            self.prod.db_done = True
         rt.call("hm_maxpool2_bwd", _ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
-                _ptr(self.x.g(lo, hi)), rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope)
+                _ptr(self.x.g(lo, hi)), rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope, db)
 
 
 class PermuteOp(object):
@@ -791,6 +803,7 @@ class Net(object):
             pop = PoolOp(self, x, out, pact)
             self.ops.append(pop)
             cv = prod[0] if prod and isinstance(prod[0], ConvOp) else None
+            pop.prod = cv
             if (cv is not None and cv.col1 and cv.Cout == 64 and cv.kh == 5 and cv.pad == 2 and x.consumers == 1
                     and cv.act.name in ("linear", "leaky_rectify", "rectify") and x.shape[0] % 2 == 0
                     and x.shape[1] % 2 == 0):

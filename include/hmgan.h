@@ -217,9 +217,10 @@ int hm_col_sum(const void* dy, int dtype, long long M, int C, float* db, void* s
 int hm_maxpool2_fwd(const void* x, void* p, uint8_t* idx, int dtype, int B, int H, int W, int C,
                     void* stream);
 /* dx[.. 2x2 ..] = (k==idx) ? dp * act'(p) : 0   — unpool fused with the backward of the
- * (monotonic) activation that preceded the pool. */
+ * (monotonic) activation that preceded the pool.  db (optional, fp32 [C], caller zeroes) += sum over all pixels of
+ * dx: the bias gradient of the convolution that produced the pooled tensor (saves a pass over dx). */
 int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx, void* dx, int dtype, int B,
-                    int H, int W, int C, int act, float slope, void* stream);
+                    int H, int W, int C, int act, float slope, float* db, void* stream);
 /* Adjoint of the virtual upsampling: dx[B,H,W,C] (+)= U^T dy[B,2H,2W,C]; mode = HmUp. */
 int hm_upsample2_bwd(const void* dy, void* dx, int dtype, int B, int H, int W, int C, int mode,
                      int accumulate, void* stream);

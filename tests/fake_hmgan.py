@@ -358,7 +358,7 @@ def hm_maxpool2_fwd(x, p, idx, dtype, B, H, W, Cn, stream=None):
     return 0
 
 
-def hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, stream=None):
+def hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, db=None, stream=None):
     Hp, Wp = H // 2, W // 2
     n = B * Hp * Wp * Cn
     g = _t(_a(dp, n, _NP[dtype])).reshape(B, Hp, Wp, Cn)
@@ -369,6 +369,8 @@ def hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, stream=None)
     for j, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
         out[:, a::2, b::2] = torch.where(k == j, g, torch.zeros_like(g))
     _a(dx, B * H * W * Cn, _NP[dtype])[:] = out.numpy().reshape(-1).astype(_NP[dtype])
+    if db:
+        _a(db, Cn, np.float32)[:] += g.reshape(-1, Cn).double().sum(0).float().numpy()
     return 0
 
 

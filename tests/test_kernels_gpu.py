@@ -202,8 +202,20 @@ def test_pool_upsample_act_layout(dtype):
     assert torch.equal(bo.gpu[idx].cpu(), bo.cpu[idx])
     dp = bo.t(r.randn(B, H // 2, W // 2, Cn), TD[dtype])
     dx = bo.t(np.zeros((B, H, W, Cn)), TD[dtype])
-    bo.run("hm_maxpool2_bwd", lambda P: (P(dp), P(p), P(idx), P(dx), dtype, B, H, W, Cn, 1, 0.2))
+    bo.run("hm_maxpool2_bwd", lambda P: (P(dp), P(p), P(idx), P(dx), dtype, B, H, W, Cn, 1, 0.2, None))
     bo.check(dx, 1e-3 if dtype else 1e-6, "maxpool bwd")
+    # with the fused bias gradient, on a vector-path shape (C % 8 == 0, 256 % (C/8) == 0) and on the scalar path
+    for (B2, H2, W2, C2) in ((2, 8, 12, 64), (3, 8, 12, 5)):
+        x2 = bo.t(r.randn(B2, H2, W2, C2), TD[dtype])
+        p2 = bo.t(np.zeros((B2, H2 // 2, W2 // 2, C2)), TD[dtype])
+        i2 = bo.t(np.zeros((B2, H2 // 2, W2 // 2, C2)), torch.uint8)
+        bo.run("hm_maxpool2_fwd", lambda P: (P(x2), P(p2), P(i2), dtype, B2, H2, W2, C2))
+        dp2 = bo.t(r.randn(B2, H2 // 2, W2 // 2, C2), TD[dtype])
+        dx2 = bo.t(np.zeros((B2, H2, W2, C2)), TD[dtype])
+        db2 = bo.t(np.zeros(C2))
+        bo.run("hm_maxpool2_bwd", lambda P: (P(dp2), P(p2), P(i2), P(dx2), dtype, B2, H2, W2, C2, 1, 0.2, P(db2)))
+        bo.check(dx2, 1e-3 if dtype else 1e-6, "maxpool bwd (+db)")
+        bo.check(db2, 2e-3 if dtype else 1e-5, "maxpool bwd bias gradient")
     for mode in (1, 2):
         up = bo.t(np.zeros((B, 2 * H, 2 * W, Cn)), TD[dtype])
         bo.run("hm_upsample2_fwd", lambda P: (P(x), P(up), dtype, B, H, W, Cn, mode))
