@@ -44,7 +44,10 @@ _PROTOS = {
     "hm_im2col_c1": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_s2d_pad64": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "hm_c1s2_conv": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
-    "hm_c1s2_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
+    "hm_c1s2_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
+    "hm_maxpool2_bwd_scaled": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P], C.c_int),
+    "hm_scale_rows": ([_P, _P, _P, _I, _LL, _LL, _P], C.c_int),
+    "hm_adv_loss_pair": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "hm_c1s2_bwd_fold": ([_P, _P, _P, _I, _P], C.c_int),
     "hm_c1s2_col2im": ([_P, _P, _I, _I, _I, _P], C.c_int),
     "hm_pack_conv_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

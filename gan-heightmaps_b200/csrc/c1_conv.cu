@@ -372,6 +372,7 @@ struct CbParams {
   const uint8_t* idx;   // [B,Hq,Wq,64]
   float* dwk;           // [256][64] fp32, atomically accumulated
   __half* u;            // [B,Hq,Wq,64]
+  const float* img_scale;   // [B] or null: g is multiplied by img_scale[image] (per-sample weighting of dW, db)
 };
 
 __global__ void __launch_bounds__(CB_THREADS, 1)
@@ -475,6 +476,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
       const bool valid = wy < p.Hq && wx < p.Wq;
       const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
+      const float isc = p.img_scale ? p.img_scale[b] : 1.f;
       // issue every global load of this tile up front (24 gradient / activation / argmax loads + the patch words):
       // one round trip per tile instead of three
       uint4 gv[8], pv[8];
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pw4[j]));
           const float a0 = p.act == HM_ACT_RELU ? (pf.x > 0.f ? 1.f : 0.f) : (pf.x >= 0.f ? 1.f : neg);
           const float a1 = p.act == HM_ACT_RELU ? (pf.y > 0.f ? 1.f : 0.f) : (pf.y >= 0.f ? 1.f : neg);
-          __half2 h = __floats2half2_rn(gf.x * a0, gf.y * a1);
+          __half2 h = __floats2half2_rn(gf.x * a0 * isc, gf.y * a1 * isc);
           hv[j] = *reinterpret_cast<uint32_t*>(&h);
         }
 #pragma unroll
@@ -678,9 +680,11 @@ __global__ void c1s2_col2im_kernel(const __half* __restrict__ u, __half* __restr
 
 // Backward of hm_c1s2_conv's pooled form from the gradient g of the pooled tensor (see the kernel comment).
 //   dwk != NULL: dwk[256][64] fp32 += weight-gradient partials (caller zeroes; fold with hm_c1s2_bwd_fold);
-//   u   != NULL: u[B,H/2,W/2,64] = patch-space input gradient (needs wk2 = pack mode 16; fold with hm_c1s2_col2im).
+//   u   != NULL: u[B,H/2,W/2,64] = patch-space input gradient (needs wk2 = pack mode 16; fold with hm_c1s2_col2im);
+//   img_scale (optional, [B]): g of image b is multiplied by img_scale[b] first.
 extern "C" int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, const uint8_t* idx, const void* wk2,
-                           float* dwk, void* u, int B, int H, int W, int act, float slope, void* stream) {
+                           float* dwk, void* u, const float* img_scale, int B, int H, int W, int act, float slope,
+                           void* stream) {
   HM_CHECK_ARG(g && pooled && idx && B > 0 && H > 0 && W > 0 && (dwk || u), "hm_c1s2_bwd: bad argument");
   HM_CHECK_ARG(!dwk || x, "hm_c1s2_bwd: the weight gradient needs the source image");
   HM_CHECK_ARG(!u || wk2, "hm_c1s2_bwd: the input gradient needs the weights (pack mode 16)");
@@ -704,6 +708,7 @@ extern "C" int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, con
   p.n_tiles = B * p.tiles_x * p.tiles_y;
   p.act = act; p.slope = slope; p.want_dw = dwk ? 1 : 0; p.want_u = u ? 1 : 0;
   p.x = (const __half*)x; p.g = (const __half*)g; p.pl = (const __half*)pooled; p.idx = idx; p.dwk = dwk; p.u = (__half*)u;
+  p.img_scale = img_scale;
   CUtensorMap tmW;
   {
     cuuint64_t dims[2] = {64, 256};

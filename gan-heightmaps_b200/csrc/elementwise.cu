@@ -568,7 +568,10 @@ __global__ void maxpool2_fwd_v8_kernel(const T* __restrict__ x, T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256)
     maxpool2_bwd_v8_kernel(const T* __restrict__ dp, const T* __restrict__ p, const uint8_t* __restrict__ idx,
-                           T* __restrict__ dx, int B, int H, int W, int C, int act, float slope, float* db) {
+                           T* __restrict__ dx, int B, int H, int W, int C, int act, float slope, float* db,
+                           T* __restrict__ dxs, const float* __restrict__ scale) {
+  // dxs/scale (optional): second copy dxs = scale[image] * dx, and db then sums the SCALED gradient (per-sample
+  // weighting of the weight/bias gradients, hm_maxpool2_bwd_scaled).
   // db (optional): per-channel sum of the scattered gradient = bias gradient of the convolution that fed the pool.
   // Needs 256 % (C/8) == 0 so that a thread keeps its channel group over the grid-stride loop.
   __shared__ float shb[256 * 8];
@@ -587,12 +590,13 @@ __global__ void __launch_bounds__(256)
     load8(dp + i * 8, gv);
     load8(p + i * 8, pv);
     const uint2 kk = *reinterpret_cast<const uint2*>(idx + i * 8);
+    const float sc = scale ? scale[b] : 1.f;
     float o0[8], o1[8], o2[8], o3[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const float gg = gv[j] * act_grad_from_out(pv[j], act, slope);
       const uint32_t k = ((j < 4 ? kk.x : kk.y) >> (8 * (j & 3))) & 0xff;
-      bs[j] += gg;
+      bs[j] += gg * sc;
       o0[j] = k == 0 ? gg : 0.f;
       o1[j] = k == 1 ? gg : 0.f;
       o2[j] = k == 2 ? gg : 0.f;
@@ -603,6 +607,15 @@ __global__ void __launch_bounds__(256)
     store8(base + C, o1);
     store8(base + (size_t)W * C, o2);
     store8(base + (size_t)W * C + C, o3);
+    if (dxs) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) { o0[j] *= sc; o1[j] *= sc; o2[j] *= sc; o3[j] *= sc; }
+      T* bs2 = dxs + (base - dx);
+      store8(bs2, o0);
+      store8(bs2 + C, o1);
+      store8(bs2 + (size_t)W * C, o2);
+      store8(bs2 + (size_t)W * C + C, o3);
+    }
   }
   if (db) {
 #pragma unroll
@@ -774,6 +787,63 @@ __global__ void adv_loss_kernel(const T* __restrict__ h, T* dh, long long R, int
     v = warp_sum(v);
     if (l == 0) atomicAdd(loss, weight * v / (float)R);
   }
+}
+
+// Fake half of a scalar-output discriminator, both of its losses at once (see hm_adv_loss_pair in hmgan.h).
+template <typename T>
+__global__ void adv_loss_pair_kernel(const T* __restrict__ h, T* dh, T* dhw, float* sw, float* sg, long long R, int G,
+                                     int out_act, int lsgan, int relu_head, float gscale, float* loss_disc,
+                                     float* loss_gen) {
+  float l0 = 0.f, l1 = 0.f;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R;
+       r += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < G; g++) s += ldf(h + r * G + g);
+    const float out = act_fwd(s / (float)G, out_act, 0.f);
+    float la, lb, da, db_;
+    if (lsgan) {
+      la = out * out;                  da = 2.f * out;                 // target 0 (discriminator loss on a fake)
+      lb = (out - 1.f) * (out - 1.f);  db_ = 2.f * (out - 1.f);        // target 1 (generator loss)
+    } else {
+      la = -logf(1.f - out);           da = 1.f / (1.f - out);
+      lb = -logf(out);                 db_ = -1.f / out;
+    }
+    l0 += la;
+    l1 += lb;
+    const float k = gscale * act_grad_from_out(out, out_act, 0.f) / ((float)R * (float)G);
+    const float a = da * k, b = db_ * k;
+    const float c = fabsf(a) >= fabsf(b) ? a : b;
+    sw[r] = c != 0.f ? a / c : 0.f;
+    sg[r] = c != 0.f ? b / c : 0.f;
+    for (int g = 0; g < G; g++) {
+      const bool on = !relu_head || ldf(h + r * G + g) > 0.f;
+      stf(dh + r * G + g, on ? c : 0.f);
+      stf(dhw + r * G + g, on ? a : 0.f);
+    }
+  }
+  l0 = warp_sum(l0);
+  l1 = warp_sum(l1);
+  __shared__ float sh0[32], sh1[32];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh0[w] = l0; sh1[w] = l1; }
+  __syncthreads();
+  if (w == 0) {
+    float v0 = l < (blockDim.x >> 5) ? sh0[l] : 0.f, v1 = l < (blockDim.x >> 5) ? sh1[l] : 0.f;
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    if (l == 0) {
+      atomicAdd(loss_disc, v0 / (float)R);
+      atomicAdd(loss_gen, v1 / (float)R);
+    }
+  }
+}
+
+template <typename T>
+__global__ void scale_rows_kernel(const T* __restrict__ src, const float* __restrict__ scale, T* __restrict__ dst,
+                                  long long R, long long L) {
+  const long long n = R * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    stf(dst + i, ldf(src + i) * scale[i / L]);
 }
 
 template <typename T>
@@ -1014,7 +1084,8 @@ extern "C" int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx
   if (C % 8 == 0 && al16(dp) && al16(p) && al16(dx) && (((uintptr_t)idx) & 7) == 0) {
     const bool fuse_db = db && (256 % (C / 8) == 0);
     DISPATCH_T(dtype, (maxpool2_bwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
-                          (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope, fuse_db ? db : nullptr)));
+                          (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope, fuse_db ? db : nullptr,
+                          (T*)nullptr, nullptr)));
     HM_CHECK_LAUNCH("hm_maxpool2_bwd");
     if (db && !fuse_db) return hm_col_sum(dx, dtype, (long long)B * H * W, C, db, stream);
     return HM_OK;
@@ -1134,6 +1205,45 @@ extern "C" int hm_adv_loss(const void* h, void* dh, int dtype, long long R, int 
                         (const T*)h, (T*)dh, R, G, out_act, target, lsgan, relu_head, weight, gscale, accumulate,
                         loss)));
   HM_CHECK_LAUNCH("hm_adv_loss");
+  return HM_OK;
+}
+
+extern "C" int hm_maxpool2_bwd_scaled(const void* dp, const void* p, const uint8_t* idx, void* dx, void* dxs,
+                                      const float* scale, int dtype, int B, int H, int W, int C, int act, float slope,
+                                      float* db, void* stream) {
+  CHECK_DTYPE(dtype, "hm_maxpool2_bwd_scaled");
+  HM_CHECK_ARG(dp && p && idx && dx && dxs && scale && B > 0 && H >= 2 && W >= 2 && C > 0,
+               "hm_maxpool2_bwd_scaled: bad argument");
+  if (!(C % 8 == 0 && 256 % (C / 8) == 0 && al16(dp) && al16(p) && al16(dx) && al16(dxs) && (((uintptr_t)idx) & 7) == 0)) {
+    set_error("hm_maxpool2_bwd_scaled: needs C %% 8 == 0, 256 %% (C/8) == 0 and 16-byte aligned tensors (C = %d)", C);
+    return HM_ERR_UNSUPPORTED;
+  }
+  long long n = (long long)B * (H / 2) * (W / 2) * C;
+  DISPATCH_T(dtype, (maxpool2_bwd_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dp, (const T*)p, idx, (T*)dx, B, H, W, C, act, slope, db, (T*)dxs, scale)));
+  HM_CHECK_LAUNCH("hm_maxpool2_bwd_scaled");
+  return HM_OK;
+}
+
+extern "C" int hm_adv_loss_pair(const void* h, void* dh, void* dhw, float* sw, float* sg, int dtype, long long R, int G,
+                                int out_act, int lsgan, int relu_head, float gscale, float* loss_disc, float* loss_gen,
+                                void* stream) {
+  CHECK_DTYPE(dtype, "hm_adv_loss_pair");
+  HM_CHECK_ARG(h && dh && dhw && sw && sg && loss_disc && loss_gen && R > 0 && G > 0, "hm_adv_loss_pair: bad argument");
+  DISPATCH_T(dtype, (adv_loss_pair_kernel<T><<<ew_grid(R, 256, 2), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)h, (T*)dh, (T*)dhw, sw, sg, R, G, out_act, lsgan, relu_head, gscale, loss_disc,
+                        loss_gen)));
+  HM_CHECK_LAUNCH("hm_adv_loss_pair");
+  return HM_OK;
+}
+
+extern "C" int hm_scale_rows(const void* src, const float* scale, void* dst, int dtype, long long R, long long L,
+                             void* stream) {
+  CHECK_DTYPE(dtype, "hm_scale_rows");
+  HM_CHECK_ARG(src && scale && dst && R > 0 && L > 0, "hm_scale_rows: bad argument");
+  DISPATCH_T(dtype, (scale_rows_kernel<T><<<ew_grid(R * L), 256, 0, (cudaStream_t)stream>>>((const T*)src, scale, (T*)dst,
+                                                                                           R, L)));
+  HM_CHECK_LAUNCH("hm_scale_rows");
   return HM_OK;
 }
 

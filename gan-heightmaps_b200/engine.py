@@ -77,6 +77,7 @@ class Val(object):
         self.vid, self.kind, self.shape, self.srcs, self.up = vid, kind, tuple(shape), tuple(srcs), up
         self.buf = None
         self.grad = None
+        self.grad_w = None               # per-sample-weighted copy of grad (single-pass discriminator backward)
         self.consumers = 0
         self.grad_is_preact = False      # consumer hands back d/d(pre-activation)
         self.want_grad = kind == "buf"
@@ -396,19 +397,27 @@ class ConvOp(object):
         t1 = self.x1.want_grad or (input_grad and self.x1.kind == "input" and self.x1.grad is not None)
         act, slope = ACT[self.act.name], self.act.slope
         x1 = _ptr(self.x1.b(lo, hi))
-        u = _ptr(self.ubuf[lo:hi]) if t1 else None
+        net = self.net
+        ws = _ptr(net.wscale) if net.wscale is not None else None
+        ia, ib = net.ig_range if (net.ig_range is not None and t1) else (lo, hi)
+        same = (ia, ib) == (lo, hi) and ws is None
         if wgrad:
             self.dwk.zero_()
-        if wgrad or t1:
-            rt.call("hm_c1s2_bwd", x1, g, pl, idx, _ptr(self.wk2) if t1 else None, _ptr(self.dwk) if wgrad else None,
-                    u, n, self.Hv, self.Wv, act, slope)
+        if wgrad and t1 and same:         # one launch produces both
+            rt.call("hm_c1s2_bwd", x1, g, pl, idx, _ptr(self.wk2), _ptr(self.dwk), _ptr(self.ubuf[lo:hi]), None, n,
+                    self.Hv, self.Wv, act, slope)
+        else:
+            if wgrad:
+                rt.call("hm_c1s2_bwd", x1, g, pl, idx, None, _ptr(self.dwk), None, ws, n, self.Hv, self.Wv, act, slope)
+            if t1:
+                rt.call("hm_c1s2_bwd", None, _ptr(pool.out.g(ia, ib)), _ptr(pool.out.b(ia, ib)), _ptr(pool.idx[ia:ib]),
+                        _ptr(self.wk2), None, _ptr(self.ubuf[ia:ib]), None, ib - ia, self.Hv, self.Wv, act, slope)
         if wgrad:
-            rt.call("hm_c1s2_bwd_fold", _ptr(self.dwk), _ptr(self.net.gview(self.W)), _ptr(self.net.gview(self.bias)),
-                    self.Cout)
+            rt.call("hm_c1s2_bwd_fold", _ptr(self.dwk), _ptr(net.gview(self.W)), _ptr(net.gview(self.bias)), self.Cout)
         if t1:
             if self.x1.take_acc():
                 raise NotImplementedError("accumulating into the source gradient of the fused first layer")
-            rt.call("hm_c1s2_col2im", u, _ptr(self.x1.g(lo, hi)), n, self.Hv, self.Wv)
+            rt.call("hm_c1s2_col2im", _ptr(self.ubuf[ia:ib]), _ptr(self.x1.g(ia, ib)), ib - ia, self.Hv, self.Wv)
 
     def bwd(self, rt, lo, hi, wgrad, input_grad):
         if self.pool_fused is not None:
@@ -420,6 +429,9 @@ class ConvOp(object):
                     ACT[self.act.name], self.act.slope, 0)
         x1 = _ptr(self.x1.b(lo, hi))
         x2 = _ptr(self.x2.b(lo, hi)) if self.x2 is not None else None
+        g_plain = g
+        if wgrad and self.net.wscale is not None:
+            g = self.out.grad_w[lo:hi]        # weight and bias gradients see the per-sample-weighted gradient
         if wgrad:
             self.dwp.zero_()
             if self.kind == "deconv":
@@ -469,6 +481,7 @@ class ConvOp(object):
                 db.zero_()
                 rt.call("hm_col_sum", _ptr(g), rt.cd, M, self.Cout, _ptr(db))
         # input gradient
+        g = g_plain
         t1 = self.x1.want_grad or (input_grad and self.x1.kind == "input" and self.x1.grad is not None)
         t2 = self.x2 is not None and (self.x2.want_grad or (input_grad and self.x2.kind == "input"
                                                              and self.x2.grad is not None))
@@ -613,6 +626,11 @@ class PoolOp(object):
             dbt.zero_()
             db = _ptr(dbt)
             self.prod.db_done = True
+        if self.net.wscale is not None:
+            rt.call("hm_maxpool2_bwd_scaled", _ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
+                    _ptr(self.x.g(lo, hi)), _ptr(self.x.grad_w[lo:hi]), _ptr(self.net.wscale), rt.cd, hi - lo, H, W, Cn,
+                    ACT[self.act.name], self.act.slope, db)
+            return
         rt.call("hm_maxpool2_bwd", _ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
                 _ptr(self.x.g(lo, hi)), rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope, db)
 
@@ -690,6 +708,8 @@ class Net(object):
         self.opt_state = {}
         self.B = 0
         self._packed = False
+        self.single_pass = False
+        self.wscale = self.ig_range = None
         if rng is not None:
             self.set_all_param_values([L.init_param(rng, p) for p in self.params])
 
@@ -866,6 +886,8 @@ class Net(object):
                 if v.kind == "buf":
                     v.buf = rt.empty((B,) + v.shape)
                     v.grad = rt.empty((B,) + v.shape)
+                    if self.single_pass and any(isinstance(o, ConvOp) and o.out is v for o in self.ops):
+                        v.grad_w = rt.empty((B,) + v.shape)
                 elif v.kind == "input":
                     v.buf = rt.empty((B,) + v.shape)
             for op in self.ops:
@@ -891,13 +913,51 @@ class Net(object):
             op.fwd(self.rt, lo, hi, deterministic)
         return self.out.buf[lo:hi]
 
-    def backward(self, lo, hi, wgrad=True, input_grad=False):
-        """self.out.grad[lo:hi] must hold d loss / d out."""
+    def backward(self, lo, hi, wgrad=True, input_grad=False, wscale=None, ig_range=None):
+        """self.out.grad[lo:hi] must hold d loss / d out.
+
+        wscale (fp32 device vector, one weight per sample of [lo,hi)) switches on the single-pass weighted mode of a
+        network that supports it (single_pass_ok): the input-gradient chain runs on the plain gradients, every
+        weight/bias gradient on the weighted copies (Val.grad_w; self.out.grad_w must hold the weighted d loss / d out),
+        and the network-input gradient is only produced for samples ig_range = (a, b)."""
         for v in self.vals:
             v.gw = False
         self.out.gw = True
-        for op in reversed(self.ops):
-            op.bwd(self.rt, lo, hi, wgrad, input_grad)
+        self.wscale, self.ig_range = wscale, ig_range
+        try:
+            for op in reversed(self.ops):
+                op.bwd(self.rt, lo, hi, wgrad, input_grad)
+        finally:
+            self.wscale, self.ig_range = None, None
+
+    def single_pass_ok(self):
+        """True if the weighted single-pass backward is implemented for this program: a scalar head, a first layer
+        fused with its pool (hm_c1s2_*), then only [convolution -> 2x2 max-pool] pairs and the head convolution."""
+        if self.rt.precision != "fast" or self.head is None or not self.ops:
+            return False
+        if not (isinstance(self.ops[0], ConvOp) and self.ops[0].pool_fused is not None):
+            return False
+        for i, op in enumerate(self.ops):
+            if isinstance(op, PoolOp):
+                Cn = op.x.shape[2]
+                if not op.fused and (op.prod is None or Cn % 8 or 256 % (Cn // 8)):
+                    return False
+            elif isinstance(op, ConvOp):
+                last = i == len(self.ops) - 1
+                if op.kind != "conv" or op.x2 is not None or op.up:
+                    return False
+                if not last and not (i + 1 < len(self.ops) and isinstance(self.ops[i + 1], PoolOp)
+                                     and self.ops[i + 1].x is op.out):
+                    return False
+                if last and op.act.name != "linear" and not op.out.grad_is_preact:
+                    return False
+            else:
+                return False
+        return True
+
+    def enable_single_pass(self):
+        self.single_pass = True
+        self.B = 0                      # (re)allocate with the weighted gradient copies
 
     def apply_update(self, opt, lr_dev, gscale, hyper):
         """lasagne.updates.rmsprop / adam over the whole flat parameter vector."""

@@ -98,6 +98,12 @@ class Pix2Pix(object):
             self.P = engine.Net(rt, p2p_gen, name="p2p_gen", rng=rng)
             self.Dp = engine.Net(rt, p2p_disc["out"], input_layers=p2p_disc["inputs"], name="p2p_disc", rng=rng)
         self.nets = {'dcgan': {'gen': self.G, 'disc': self.D}, 'p2p': {'gen': self.P, 'disc': self.Dp}}
+        # one weighted backward pass through the DCGAN discriminator instead of two (hm_adv_loss_pair, include/hmgan.h)
+        self._single_pass = (self.D is not None and os.environ.get("HMGAN_SINGLE_PASS_D", "1") != "0"
+                             and self.D.single_pass_ok())
+        if self._single_pass:
+            self.D.enable_single_pass()
+        self._wscale = None
         # optimiser
         if not isinstance(opt, L._Optimiser):
             raise TypeError("opt must be lasagne_compat.rmsprop or lasagne_compat.adam")
@@ -227,15 +233,35 @@ class Pix2Pix(object):
             h = D.forward(2 * B)                                            # D(x), D(G(z))   :94-95
             dh = D.out.grad if do else None
             self._adv(D, h[:B], dh[:B] if do else None, 1., 1, ls)          # disc_loss_dcgan :108
-            self._adv(D, h[B:], dh[B:2 * B] if do else None, 0., 1, ls)
-            if do:
-                D.backward(0, 2 * B, wgrad=True, input_grad=False)
-            self._adv(D, h[B:], dh[B:2 * B] if do else None, 1., 0, ls)     # gen_loss_dcgan  :107
-            if do:
-                D.backward(B, 2 * B, wgrad=False, input_grad=True)
-                self._copy(D.inputs[0].grad[B:2 * B], G.out.grad[:B])
+            if do and self._single_pass:
+                # D(G(z)) enters disc_loss_dcgan (target 0) and gen_loss_dcgan (target 1): per sample the two backward
+                # passes through D differ by a scalar, so ONE pass carries both (weights sw on dW, sg on dG(z))
+                head = D.head
+                if self._wscale is None or self._wscale.numel() != 3 * B:
+                    self._wscale = torch.ones(3 * B, dtype=torch.float32, device=rt.device)   # [1]*B | sw | sg
+                ws = self._wscale
+                dhw = D.out.grad_w
+                R = h[B:].numel() // head["G"]
+                self._copy(dh[:B], dhw[:B])
+                rt.call("hm_adv_loss_pair", _ptr(h[B:]), _ptr(dh[B:2 * B]), _ptr(dhw[B:2 * B]), _ptr(ws[B:]),
+                        _ptr(ws[2 * B:]), rt.cd, R, head["G"], _lib.ACT[head["out_act"]], 1 if self.lsgan else 0,
+                        1 if head["relu_head"] else 0, ls, _ptr(self.losses[1:]), _ptr(self.losses[0:]))
+                D.backward(0, 2 * B, wgrad=True, input_grad=True, wscale=ws[:2 * B], ig_range=(B, 2 * B))
+                n_in = D.inputs[0].grad[B:2 * B].numel() // B
+                rt.call("hm_scale_rows", _ptr(D.inputs[0].grad[B:2 * B]), _ptr(ws[2 * B:]), _ptr(G.out.grad[:B]),
+                        rt.cd, B, n_in)
                 G.backward(0, B, wgrad=True)
                 upd += [G, D]
+            else:
+                self._adv(D, h[B:], dh[B:2 * B] if do else None, 0., 1, ls)
+                if do:
+                    D.backward(0, 2 * B, wgrad=True, input_grad=False)
+                self._adv(D, h[B:], dh[B:2 * B] if do else None, 1., 0, ls)     # gen_loss_dcgan  :107
+                if do:
+                    D.backward(B, 2 * B, wgrad=False, input_grad=True)
+                    self._copy(D.inputs[0].grad[B:2 * B], G.out.grad[:B])
+                    G.backward(0, B, wgrad=True)
+                    upd += [G, D]
         if self.have_p2p:
             P, Dp = self.P, self.Dp
             do = train and self.train_mode in ('both', 'p2p')

@@ -157,7 +157,8 @@ int hm_c1s2_conv(const void* x, const void* wk, const float* bias, void* y, uint
  *                hm_c1s2_col2im sums the patch contributions into dx[B,H,W] (one channel).
  * The full-resolution gradient of the un-pooled activation is never materialised. */
 int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, const uint8_t* idx, const void* wk2, float* dwk,
-                void* u, int B, int H, int W, int act, float slope, void* stream);
+                void* u, const float* img_scale /* [B] or NULL: g of image b times img_scale[b] */, int B, int H, int W,
+                int act, float slope, void* stream);
 int hm_c1s2_bwd_fold(const float* dwk, float* dw, float* db, int cout, void* stream);
 int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
 
@@ -221,6 +222,13 @@ int hm_maxpool2_fwd(const void* x, void* p, uint8_t* idx, int dtype, int B, int 
  * dx: the bias gradient of the convolution that produced the pooled tensor (saves a pass over dx). */
 int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx, void* dx, int dtype, int B,
                     int H, int W, int C, int act, float slope, float* db, void* stream);
+/* The same with a per-image weight: dx as above, dxs = scale[image] * dx (a second tensor of dx's shape) and
+ * db += scale[image] * (sum of dx).  Used by the single-pass discriminator backward (hm_adv_loss_pair): the
+ * input-gradient chain runs on dx, weight and bias gradients on dxs.  Needs C % 8 == 0 and 256 % (C/8) == 0. */
+int hm_maxpool2_bwd_scaled(const void* dp, const void* p, const uint8_t* idx, void* dx, void* dxs, const float* scale,
+                           int dtype, int B, int H, int W, int C, int act, float slope, float* db, void* stream);
+/* dst[r][:] = scale[r] * src[r][:]  (R rows of L elements). */
+int hm_scale_rows(const void* src, const float* scale, void* dst, int dtype, long long R, long long L, void* stream);
 /* Adjoint of the virtual upsampling: dx[B,H,W,C] (+)= U^T dy[B,2H,2W,C]; mode = HmUp. */
 int hm_upsample2_bwd(const void* dy, void* dx, int dtype, int B, int H, int W, int C, int mode,
                      int accumulate, void* stream);
@@ -249,6 +257,18 @@ int hm_permute(const void* src, void* dst, int dtype, int B, int C, int H, int W
 int hm_adv_loss(const void* h, void* dh, int dtype, long long R, int G, int out_act, float target,
                 int lsgan, int relu_head, float weight, float gscale, int accumulate, float* loss,
                 void* stream);
+/* Both adversarial losses of the FAKE half of a scalar-output discriminator in one go (pix2pix.py:107-108: the
+ * generator loss, target 1, and the fake term of the discriminator loss, target 0, are functions of the same D(G(z))).
+ * A discriminator without BatchNorm is sample-wise independent and its backward pass is linear in the output
+ * gradient, so for sample r the two backward passes differ only by the scalar factors a_r = dl(out_r,0)/dout and
+ * b_r = dl(out_r,1)/dout.  This writes ONE output gradient dh[r,g] = c_r * mask (c_r = the larger of a_r, b_r in
+ * magnitude, so nothing underflows in fp16), the weights sw[r] = a_r/c_r (apply to this sample's contribution to the
+ * discriminator's weight gradients) and sg[r] = b_r/c_r (apply to its input gradient, which goes to the generator),
+ * dhw[r,g] = a_r * mask (= sw * dh, the head convolution's weight-gradient operand), and adds mean_r l(out_r,0) to
+ * loss_disc[0], mean_r l(out_r,1) to loss_gen[0].  Arguments as hm_adv_loss. */
+int hm_adv_loss_pair(const void* h, void* dh, void* dhw, float* sw, float* sg, int dtype, long long R, int G,
+                     int out_act, int lsgan, int relu_head, float gscale, float* loss_disc, float* loss_gen,
+                     void* stream);
 /* Reconstruction loss: l1: mean|p-y| , l2: mean (p-y)^2 ; dp (+)= gscale*weight*dl/dp. */
 int hm_recon_loss(const void* p, const void* y, void* dp, int dtype, long long n, int l2,
                   float weight, float gscale, int accumulate, float* loss, void* stream);

@@ -374,6 +374,51 @@ def hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, db=None, str
     return 0
 
 
+def hm_maxpool2_bwd_scaled(dp, p, idx, dx, dxs, scale, dtype, B, H, W, Cn, act, slope, db=None, stream=None):
+    hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, None)
+    sc = _t(_a(scale, B, np.float32)).view(B, 1, 1, 1)
+    Hp, Wp = H // 2, W // 2
+    n = B * Hp * Wp * Cn
+    g = _t(_a(dp, n, _NP[dtype])).reshape(B, Hp, Wp, Cn) * _act_grad_from_out(
+        _t(_a(p, n, _NP[dtype])).reshape(B, Hp, Wp, Cn), act, slope)
+    k = torch.from_numpy(_a(idx, n, np.uint8).astype(np.int64)).reshape(B, Hp, Wp, Cn)
+    out = torch.zeros(B, H, W, Cn)
+    for j, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        out[:, a::2, b::2] = torch.where(k == j, g * sc, torch.zeros_like(g))
+    _a(dxs, B * H * W * Cn, _NP[dtype])[:] = out.numpy().reshape(-1).astype(_NP[dtype])
+    if db:
+        _a(db, Cn, np.float32)[:] += (g * sc).reshape(-1, Cn).double().sum(0).float().numpy()
+    return 0
+
+
+def hm_scale_rows(src, scale, dst, dtype, R, L, stream=None):
+    v = _t(_a(src, R * L, _NP[dtype])).reshape(R, L) * _t(_a(scale, R, np.float32)).view(R, 1)
+    _a(dst, R * L, _NP[dtype])[:] = v.numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
+def hm_adv_loss_pair(h, dh, dhw, sw, sg, dtype, R, G, out_act, lsgan, relu_head, gscale, loss_disc, loss_gen,
+                     stream=None):
+    hv = _t(_a(h, R * G, _NP[dtype])).reshape(R, G)
+    out = _act(hv.mean(1), out_act, 0.0)
+    if lsgan:
+        la, da, lb, db_ = out ** 2, 2 * out, (out - 1) ** 2, 2 * (out - 1)
+    else:
+        la, da, lb, db_ = -torch.log(1 - out), 1 / (1 - out), -torch.log(out), -1 / out
+    _a(loss_disc, 1, np.float32)[0] += np.float32(float(la.mean()))
+    _a(loss_gen, 1, np.float32)[0] += np.float32(float(lb.mean()))
+    k = gscale * _act_grad_from_out(out, out_act, 0.0) / (R * G)
+    a, b = da * k, db_ * k
+    c = torch.where(a.abs() >= b.abs(), a, b)
+    safe = torch.where(c != 0, c, torch.ones_like(c))
+    _a(sw, R, np.float32)[:] = torch.where(c != 0, a / safe, torch.zeros_like(c)).numpy()
+    _a(sg, R, np.float32)[:] = torch.where(c != 0, b / safe, torch.zeros_like(c)).numpy()
+    mask = (hv > 0).float() if relu_head else torch.ones_like(hv)
+    _a(dh, R * G, _NP[dtype])[:] = (c.view(R, 1) * mask).numpy().reshape(-1).astype(_NP[dtype])
+    _a(dhw, R * G, _NP[dtype])[:] = (a.view(R, 1) * mask).numpy().reshape(-1).astype(_NP[dtype])
+    return 0
+
+
 def hm_upsample2_fwd(x, y, dtype, B, H, W, Cn, mode, stream=None):
     v = _t(_a(x, B * H * W * Cn, _NP[dtype])).reshape(B, H, W, Cn).permute(0, 3, 1, 2)
     out = v.repeat_interleave(2, 2).repeat_interleave(2, 3) if mode == 1 else _bilinear2(v)
@@ -598,10 +643,12 @@ def hm_c1s2_conv(x, wk, bias, y, idx, B, H, W, ncols, act, slope, stream=None):
     return 0
 
 
-def hm_c1s2_bwd(x, g, pooled, idx, wk2, dwk, u, B, H, W, act, slope, stream=None):
+def hm_c1s2_bwd(x, g, pooled, idx, wk2, dwk, u, img_scale, B, H, W, act, slope, stream=None):
     Hq, Wq = H // 2, W // 2
     n = B * Hq * Wq * 64
     gg = _t(_a(g, n, np.float16)) * _act_grad_from_out(_t(_a(pooled, n, np.float16)), act, slope)
+    if img_scale:
+        gg = (gg.reshape(B, -1) * _t(_a(img_scale, B, np.float32)).view(B, 1)).reshape(-1)
     gg = gg.half().float().reshape(B * Hq * Wq, 64)                            # the kernel rounds g*act' to fp16
     k = torch.from_numpy(_a(idx, n, np.uint8).astype(np.int64)).reshape(B * Hq * Wq, 64)
     G4 = torch.stack([gg * (k == d) for d in range(4)], 1).reshape(B * Hq * Wq, 256)   # [(w)][(d,co)]

@@ -110,6 +110,7 @@ def test_fast_mode_tensor_core_step_tracks_oracle():
     om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast")
     paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
     assert paths.count("tcgen05") >= 6, paths
+    assert m._single_pass and m.D.ops[0].pool_fused is not None and m.G.ops[-1].c1dg
     Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=1)
     lo = om.train_fn(Z, X, Y)
     lm = m.train_fn(Z, X, Y)
@@ -156,3 +157,34 @@ def test_fast_mode_full_width_joint_step_tracks_oracle():
             assert rel <= bound, (k, i, q.shape, rel, bound)
     paths = [op.path for op in m.P.ops + m.Dp.ops if hasattr(op, "path")]
     assert paths.count("tcgen05") >= 16, paths
+
+
+def test_single_pass_discriminator_backward_equals_two_passes_at_full_width(monkeypatch):
+    """BASELINE configs[1] architecture (512x512, full width) at batch 2, fast mode: the weighted single backward pass
+    through D (hm_adv_loss_pair: disc-loss weights on the weight gradients, gen-loss weights on dG(z)) against the
+    reference's two separate passes (pix2pix.py:107-108,131-135) on the same weights and inputs.  Same kernels, same
+    fp16 storage; only the scalar per-sample factors move, so every gradient array agrees to 2e-2 in relative L2 norm
+    (fp16 rounding of differently-scaled intermediates) and the losses to 1e-5."""
+    cfg = S.experiment_kwargs('test1_nobn_bilin_both')
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=3)
+    res = {}
+    for sp in ("1", "0"):
+        monkeypatch.setenv("HMGAN_SINGLE_PASS_D", sp)
+        _, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast")
+        assert m._single_pass == (sp == "1")
+        # a head bias of 0.6 puts D(.) near 0.6, where neither per-sample factor is negligible (at the Glorot
+        # initialisation D(G(z)) ~ 1e-6 and the fake samples hardly touch D's weight gradient in either scheme)
+        vals = m.D.get_all_param_values()
+        vals[-1][:] = 0.6
+        m.D.set_all_param_values(vals)
+        lm = m.train_fn(Z, X, Y)
+        res[sp] = (lm, m.D.get_grads(), m.G.get_grads(), [q for q in m.G.params if q.trainable])
+        del m
+        torch.cuda.empty_cache()
+    np.testing.assert_allclose(res["1"][0][:2], res["0"][0][:2], rtol=1e-3, atol=1e-6)
+    for k, idx in (("D", 1), ("G", 2)):
+        for i, (a, b) in enumerate(zip(res["1"][idx], res["0"][idx])):
+            if k == "G" and res["0"][3][i].kind == "b" and i < len(res["0"][idx]) - 1:
+                continue                 # biases in front of a BatchNorm: the true gradient is zero, both are noise
+            rel = float(np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
+            assert rel <= 2e-2, (k, i, a.shape, rel)

@@ -327,15 +327,15 @@ def run_c1bwd_case(name, B, H, W):
     db = torch.zeros(64, device="cuda")
     # the two uses of the step: weight gradient only, then input gradient only; and both at once must agree
     _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), None, dwk.data_ptr(), None,
-              B, H, W, 1, 0.2, None)
+              None, B, H, W, 1, 0.2, None)
     _lib.call("hm_c1s2_bwd", None, g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(),
-              B, H, W, 1, 0.2, None)
+              None, B, H, W, 1, 0.2, None)
     _lib.call("hm_c1s2_bwd_fold", dwk.data_ptr(), dw.data_ptr(), db.data_ptr(), 64, None)
     _lib.call("hm_c1s2_col2im", u.data_ptr(), dx.data_ptr(), B, H, W, None)
     dwk2 = torch.zeros(256 * 64, device="cuda")
     u2 = torch.zeros_like(u)
     _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(),
-              dwk2.data_ptr(), u2.data_ptr(), B, H, W, 1, 0.2, None)
+              dwk2.data_ptr(), u2.data_ptr(), None, B, H, W, 1, 0.2, None)
     torch.cuda.synchronize()
     # reference in float32 with the kernel's own routing (argmax bytes) and activation derivative (sign of the pooled
     # value): full-resolution gradient, then the convolution's adjoints as GEMMs over unfolded patches
@@ -374,8 +374,8 @@ def perf_c1bwd():
     dwk = torch.zeros(256 * 64, device="cuda")
     u = torch.empty(B, 256, 256, 64, device="cuda", dtype=torch.float16)
     dx = torch.empty(B, H, W, device="cuda", dtype=torch.float16)
-    runs = (("D1 bwd weight gradient x64", lambda: _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), None, dwk.data_ptr(), None, 64, H, W, 1, 0.2, None), 64 * 65536 * (128 + 128 + 64) / 1e9),
-            ("D1 bwd input gradient x32 (patch space)", lambda: _lib.call("hm_c1s2_bwd", None, g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(), 32, H, W, 1, 0.2, None), 32 * 65536 * (128 + 128 + 64 + 80) / 1e9),
+    runs = (("D1 bwd weight gradient x64", lambda: _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), None, dwk.data_ptr(), None, None, 64, H, W, 1, 0.2, None), 64 * 65536 * (128 + 128 + 64) / 1e9),
+            ("D1 bwd input gradient x32 (patch space)", lambda: _lib.call("hm_c1s2_bwd", None, g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(), None, 32, H, W, 1, 0.2, None), 32 * 65536 * (128 + 128 + 64 + 80) / 1e9),
             ("D1 bwd col2im x32", lambda: _lib.call("hm_c1s2_col2im", u.data_ptr(), dx.data_ptr(), 32, H, W, None), 32 * 65536 * (72 + 8) / 1e9))
     for nm, fn, gb in runs:
         fn()
