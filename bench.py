@@ -55,7 +55,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -153,7 +153,7 @@ def cpu_baseline(workload, sample_b, steps=1, warmup=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dcgan", choices=["dcgan", "both"])
@@ -237,9 +237,17 @@ def main():
     ms_e2e = timed(lambda: m.train_fn(Zp, Xp, Yp), a.steps)
     e2e = B * world * a.steps / (ms_e2e * 1e-3)
     if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
         return
     pk = peaks()
     kname, kflop, kms, kpath = time_dominant_kernel(m)
+    traffic = None
+    try:       # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            traffic = json.load(f).get(kname, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     k_tflops = kflop / (kms * 1e-3) / 1e12
     step_tflops = value / world * GFLOP_PER_IMG[a.workload] / 1e3
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="f16" if a.precision == "fast" else "f32",
@@ -247,7 +255,7 @@ def main():
                     "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / a.steps},
                gpu_launches=int(launches), clocks=clk,
                roofline={"bound": "tensor", "achieved": k_tflops, "peak": pk["burst"], "unit": "TFLOP/s",
-                         "frac": k_tflops / pk["burst"], "traffic": None, "kernel": kname, "kernel_path": kpath,
+                         "frac": k_tflops / pk["burst"], "traffic": traffic, "kernel": kname, "kernel_path": kpath,
                          "kernel_ms": kms, "peak_source": pk["src"] + " (burst: kernel timed alone)",
                          "step_achieved": step_tflops, "step_frac_of_sustained": step_tflops / pk["sustained"]},
                losses=[float(v) for v in losses])
@@ -257,6 +265,9 @@ def main():
                                "sample": "%d images of the same workload, 1 warm-up + 1 timed full step "
                                          "(%.1f s/step)" % (a.cpu_sample, dt)}
     print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

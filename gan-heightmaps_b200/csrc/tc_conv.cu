@@ -818,7 +818,14 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       if (e && atoi(e) >= 1) p.a_slots = atoi(e);
     }
     int b_slots = (227 * 1024 - 10240 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
-    if (b_slots > 8) b_slots = 8;
+    {
+      static int bcap = -1;                                 // tuning knob: depth of the weight ring
+      if (bcap < 0) {
+        const char* e = getenv("HMGAN_RB_BCAP");
+        bcap = (e && atoi(e) >= 2) ? atoi(e) : 8;
+      }
+      if (b_slots > bcap) b_slots = bcap;
+    }
     {
       const char* e = getenv("HMGAN_RB_BSLOTS");            // diagnostic override
       if (e && atoi(e) >= 2 && atoi(e) < b_slots) b_slots = atoi(e);
