@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1)
 
   if (warp == 0) {
     // ===================== weights + MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(w_full, w_bytes);
       tma_load_2d(&tmW, base, w_full, 0, 0);
       mbar_wait(w_full, 0);
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
 
   if (warp == 0) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.want_u) {
         mbar_expect_tx(w_full, w_bytes);
         tma_load_2d(&tmW, base, w_full, 0, 0);

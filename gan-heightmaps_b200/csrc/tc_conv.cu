@@ -97,6 +97,20 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t dst,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// true in exactly one lane of a converged warp.  The role loops below run WARP-UNIFORMLY (all 32 lanes wait on the
+// barriers and compute the same descriptors, which therefore live in uniform registers) and only the instructions that
+// must be issued once sit under elect_one(): nvcc then emits ONE predicated UTCHMMA / UTMALDG.  Issued from inside an
+// `if (lane == 0)` region the same inline asm compiles to an ELECT / BRA.U.ANY waterfall loop per instruction, which
+// made the single issuing thread the bottleneck (134 cycles per M=128,N=128,K=16 MMA instead of 64; tools/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -173,9 +187,14 @@ __device__ __forceinline__ void epi_pack32(const uint32_t* v, const float* bias3
 }
 
 // The whole epilogue role: for every tile of this CTA wait for the accumulator, drain it, release it.
+// pair_rank < 0: single-CTA kernels (work items blockIdx.x, +gridDim.x, ...; tempty0 is a local barrier).
+// pair_rank = 0/1: CTA pair (cta_group::2): work items are shared by the pair, this CTA owns sub-tiles
+// [ (2*st + rank)*S, +S ) of super tile st, and releases the accumulator on the LEADER's barrier (tempty0 is then a
+// shared::cluster address).
 template <int ACT>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                              const float* bias_s, int warp, int lane, int total_tiles) {
+                                              const float* bias_s, int warp, int lane, int total_tiles,
+                                              int pair_rank = -1) {
   const int q = warp & 3;                                   // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
   const int px_per_img = p.bw * p.bh;
@@ -183,16 +202,19 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   const int rem = row - in * px_per_img;
   const int iy = rem / p.bw, ix = rem - iy * p.bw;
   int it = 0;
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+  const int t0 = pair_rank < 0 ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
+  const int tstep = pair_rank < 0 ? (int)gridDim.x : (int)(gridDim.x >> 1);
+  for (int t = t0; t < total_tiles; t += tstep, it++) {
     const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
-    const int nv = min(p.S, p.n_mtiles - st * p.S);
+    const int mt0 = pair_rank < 0 ? st * p.S : (2 * st + pair_rank) * p.S;
+    const int nv = max(0, min(p.S, p.n_mtiles - mt0));
     const int acc = it & 1;
     mbar_wait(tfull0 + 8u * acc, (it >> 1) & 1);
     tc_fence_after();
     const int col0 = nt * p.ntile;
     const float* bias_t = bias_s + col0;
    for (int sub = 0; sub < nv; sub++) {
-    const int mt = st * p.S + sub;
+    const int mt = mt0 + sub;
     const int tx = mt % p.tiles_x;
     const int ty = (mt / p.tiles_x) % p.tiles_y;
     const int tn = mt / (p.tiles_x * p.tiles_y);
@@ -304,7 +326,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
    }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+    if (elect_one()) {
+      if (pair_rank < 0)
+        mbar_arrive(tempty0 + 8u * acc);
+      else
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty0 + 8u * acc) : "memory");
+    }
   }
 }
 
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -403,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(p.ntile);
       int stage = 0;
       uint32_t phase = 0;
@@ -461,6 +488,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128_line(uint32_t saddr, int mode) {
   if (mode == 0) return umma_desc_k_sw128(saddr);
   return umma_desc_k_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
+}
+
+// One filter tap of the row-box kernels for NS sub-tiles, fully unrolled: NS*4 back-to-back MMAs.  Descriptors are
+// (constant high word, 32-bit low word); a_lo advances by a_sub per sub-tile, the accumulator column by ntile.
+constexpr uint32_t UMMA_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | (uint64_t)lo; }
+__device__ __forceinline__ uint32_t umma_lo_of(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+template <int NS>
+__device__ __forceinline__ void mma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t a_sub, uint32_t b_lo, uint32_t ntile,
+                                        uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+#pragma unroll
+    for (int k = 0; k < KCH / 16; k++)
+      tc_mma_f16(d_tmem + i * ntile, umma_desc_lo(a_lo + i * a_sub + 2 * k), umma_desc_lo(b_lo + 2 * k), idesc,
+                 acc_first | (uint32_t)k);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -531,16 +575,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t box_bytes = (uint32_t)(TILE_M + p.kw - 1) * 128u;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
-        const int nv = min(p.S, p.n_mtiles - st * p.S);
-        for (int r = 0; r < p.kh; r++) {
-          for (int cc = 0; cc < cchunks; cc++) {
-            const int c = cc * KCH;
-            mbar_wait(aempty(as), aph ^ 1);
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
+      const int nv = min(p.S, p.n_mtiles - st * p.S);
+      for (int r = 0; r < p.kh; r++) {
+        for (int cc = 0; cc < cchunks; cc++) {
+          const int c = cc * KCH;
+          mbar_wait(aempty(as), aph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(afull(as), nv * box_bytes);
             // NOTE: keep this loop rolled and free of local arrays: with the tile coordinates precomputed into
             // per-thread arrays nvcc 12.9 unrolled/peeled it and boxes i >= 1 of every first chunk never landed
@@ -557,23 +602,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               else
                 tma_load_4d(&tmA2, dst, afull(as), c - p.C1, ox, oy, on);
             }
-            if (++as == p.a_slots) { as = 0; aph ^= 1; }
-            for (int s = 0; s < p.kw; s++) {
-              mbar_wait(bempty(bs), bph ^ 1);
+          }
+          __syncwarp();
+          if (++as == p.a_slots) { as = 0; aph ^= 1; }
+          for (int s = 0; s < p.kw; s++) {
+            mbar_wait(bempty(bs), bph ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(bfull(bs), b_slot_bytes);
               tma_load_3d(&tmB, b_base + bs * b_slot_bytes, bfull(bs), c, nt * p.ntile, r * p.kw + s);
-              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
             }
+            __syncwarp();
+            if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ===================== MMA issuer: ONE elected lane runs the whole role =====================
+    // The tensor pipe queues only a few MMAs, so every pause of the issuing thread (barrier polls, warp syncs,
+    // descriptor arithmetic) longer than ~2 MMAs starves it (tools/mma_rate.cu).  Hence: a single lane, no per-tap
+    // warp synchronisation, the wait for the NEXT weight slice placed behind the current slice's MMAs, descriptors
+    // advanced by additions.
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(p.ntile);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
+      const uint32_t mode_bits = 0;   // (rb_mode experiment retired: plain descriptors)
+      (void)mode_bits;
+      bool have_b = false;            // bfull(bs) of the upcoming tap has already been waited for
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
@@ -581,33 +638,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
         const int st = t / p.n_ntiles;
         const int nv = min(p.S, p.n_mtiles - st * p.S);
-        bool first = true;
+        uint32_t first = 0;           // accumulate flag of the very first MMA of every sub-tile
         for (int r = 0; r < p.kh; r++) {
           for (int cc = 0; cc < cchunks; cc++) {
             mbar_wait(afull(as), aph);
-            tc_fence_after();
-            const uint32_t a_addr = base + as * a_slot_bytes;
+            const uint32_t a_lo0 = umma_lo_of(base + as * a_slot_bytes);
+            const uint32_t a_sub = (uint32_t)p.rb_bytes >> 4;
             for (int s = 0; s < p.kw; s++) {
-              mbar_wait(bfull(bs), bph);
+              if (!have_b) mbar_wait(bfull(bs), bph);
+              have_b = false;
               tc_fence_after();
-              const uint64_t bd = umma_desc_k_sw128(b_base + bs * b_slot_bytes);
-              for (int i = 0; i < nv; i++) {
-                const uint64_t ad = umma_desc_k_sw128_line(a_addr + i * p.rb_bytes + s * 128, p.rb_mode);
-#pragma unroll
-                for (int k = 0; k < KCH / 16; k++)
-                  tc_mma_f16(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-              }
-              first = false;
+              const uint32_t b_lo = umma_lo_of(b_base + bs * b_slot_bytes);
+              const uint32_t a_lo = a_lo0 + (uint32_t)s * 8u;          // +128 bytes per tap (address field is >> 4)
+              if (nv == 2) mma_tap<2>(d_tmem, a_lo, a_sub, b_lo, p.ntile, idesc, first);
+              else if (nv == 4) mma_tap<4>(d_tmem, a_lo, a_sub, b_lo, p.ntile, idesc, first);
+              else if (nv == 1) mma_tap<1>(d_tmem, a_lo, a_sub, b_lo, p.ntile, idesc, first);
+              else mma_tap<3>(d_tmem, a_lo, a_sub, b_lo, p.ntile, idesc, first);
+              first = 1;
               tc_commit(bempty(bs));
+              const bool last_s = s == p.kw - 1;
+              if (last_s) tc_commit(aempty(as));
+              if (last_s && r == p.kh - 1 && cc == cchunks - 1) tc_commit(tfull_bar(acc));
               if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+              // poll for the next weight slice while the MMAs just issued execute (same A slot: no other wait needed)
+              if (!last_s) {
+                mbar_wait(bfull(bs), bph);
+                have_b = true;
+              }
             }
-            tc_commit(aempty(as));
             if (++as == p.a_slots) { as = 0; aph ^= 1; }
           }
         }
-        tc_commit(tfull_bar(acc));
       }
     }
+    __syncwarp();
   } else {
     switch (p.act) {
       case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
@@ -622,6 +686,225 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the row-box kernel (tcgen05 cta_group::2, cluster of two CTAs on two SMs).
+// The SS-mode MMA is bound by shared-memory operand bandwidth (~64 B/clk/SM measured): an
+// M=128,N,K=16 MMA reads 4096 + 32 N bytes per N/2 cycles.  With cta_group::2 one instruction computes M = 256 rows
+// (128 per CTA, each from its own shared memory and into its own TMEM) and every CTA supplies only HALF of the N
+// weight rows, so the per-SM operand traffic drops to 4096 + 16 N bytes per N/2 cycles and the weight ring to half.
+//   * both CTAs run a TMA producer for their own pixels and their half of each weight slice; every load signals the
+//     LEADER's (rank 0) full barriers (cp.async.bulk.tensor ... cta_group::2 with the leader's barrier address);
+//   * only the leader issues tcgen05.mma.cta_group::2; tcgen05.commit ... multicast::cluster frees the stages in
+//     both CTAs and publishes the accumulators to both epilogues;
+//   * the epilogue warps of both CTAs release the accumulator on the leader's barrier (count 8).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* tm, uint32_t dst, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* tm, uint32_t dst, uint32_t leader_bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` (same offset) in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor for the pair: M = 256 (128 rows per CTA), N = n
+__host__ __device__ constexpr uint32_t umma_idesc_f16_pair(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    tc_conv_rb2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_slot_bytes = p.S * p.rb_bytes;
+  const uint32_t b_slot_bytes = (p.ntile / 2) * 128;                 // this CTA's half of a weight slice
+  const uint32_t b_base = base + p.a_slots * a_slot_bytes;
+  const uint32_t ctrl = b_base + p.b_slots * b_slot_bytes;
+  auto afull = [&](int s) { return ctrl + 8u * s; };
+  auto aempty = [&](int s) { return ctrl + 8u * (p.a_slots + s); };
+  auto bfull = [&](int s) { return ctrl + 8u * (2 * p.a_slots + s); };
+  auto bempty = [&](int s) { return ctrl + 8u * (2 * p.a_slots + p.b_slots + s); };
+  auto tfull_bar = [&](int a) { return ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + a); };
+  auto tempty_bar = [&](int a) { return ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + 2 + a); };
+  const uint32_t tmem_slot = ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);
+  {
+    const int ncols = p.n_ntiles * p.ntile;
+    const int creal = p.d2s ? p.cph : p.Cout;
+    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+      const int c = p.d2s ? i % p.cph : i;
+      bias_s[i] = (p.bias && c < creal && (!p.d2s || i < 4 * p.cph)) ? p.bias[c] : 0.f;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int acc_cols = p.S * p.ntile;
+  const int tmem_cols = 2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_slots; s++) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < p.b_slots; s++) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);                        // four epilogue warps in each CTA of the pair
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // both CTAs' barriers exist before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int total_tiles = p.n_super * p.n_ntiles;        // n_super counts super tiles of 2*S M tiles here
+  const int cchunks = p.Cin / KCH;
+  const uint32_t box_bytes = (uint32_t)(TILE_M + p.kw - 1) * 128u;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = pair; t < total_tiles; t += n_pairs) {
+        const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
+        const int mt0 = (2 * st + (int)rank) * p.S;
+        for (int r = 0; r < p.kh; r++) {
+          for (int cc = 0; cc < cchunks; cc++) {
+            const int c = cc * KCH;
+            mbar_wait(aempty(as), aph ^ 1);
+            const uint32_t lead_afull = mapa_shared(afull(as), 0);
+            if (rank == 0) mbar_expect_tx(afull(as), 2u * p.S * box_bytes);
+            // (tiles past the end of the list load out-of-bounds boxes: zero fill, same byte count)
+#pragma unroll 1
+            for (int i = 0; i < p.S; i++) {
+              const int mt = mt0 + i;
+              const int ox = (mt % p.tiles_x) * p.bw - p.pad;
+              const int oy = (mt / p.tiles_x) % p.tiles_y - p.pad + r;
+              const int on = mt / (p.tiles_x * p.tiles_y);
+              const uint32_t dst = base + as * a_slot_bytes + i * p.rb_bytes;
+              if (c < p.C1)
+                tma_load_4d_pair(&tmA, dst, lead_afull, c, ox, oy, on);
+              else
+                tma_load_4d_pair(&tmA2, dst, lead_afull, c - p.C1, ox, oy, on);
+            }
+            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+            for (int s = 0; s < p.kw; s++) {
+              mbar_wait(bempty(bs), bph ^ 1);
+              if (rank == 0) mbar_expect_tx(bfull(bs), 2u * b_slot_bytes);
+              tma_load_3d_pair(&tmB, b_base + bs * b_slot_bytes, mapa_shared(bfull(bs), 0), c,
+                               nt * p.ntile + (int)rank * (p.ntile / 2), r * p.kw + s);
+              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_f16_pair(p.ntile);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int t = pair; t < total_tiles; t += n_pairs, it++) {
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        bool first = true;
+        for (int r = 0; r < p.kh; r++) {
+          for (int cc = 0; cc < cchunks; cc++) {
+            mbar_wait(afull(as), aph);
+            tc_fence_after();
+            const uint32_t a_addr = base + as * a_slot_bytes;
+            for (int s = 0; s < p.kw; s++) {
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after();
+              const uint64_t bd = umma_desc_k_sw128(b_base + bs * b_slot_bytes);
+              for (int i = 0; i < p.S; i++) {
+                const uint64_t ad = umma_desc_k_sw128(a_addr + i * p.rb_bytes + s * 128);
+#pragma unroll
+                for (int k = 0; k < KCH / 16; k++)
+                  tc_mma_f16_pair(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+              }
+              first = false;
+              tc_commit_pair(bempty(bs));
+              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+            }
+            tc_commit_pair(aempty(as));
+            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+          }
+        }
+        tc_commit_pair(tfull_bar(acc));
+      }
+    }
+  } else {
+    const uint32_t lead_tempty = mapa_shared(tempty_bar(0), 0);
+    switch (p.act) {
+      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
+      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
+      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
+      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
+      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // nobody's TMEM / barriers are in use by the peer any more
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -805,6 +1088,65 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   if (rb_enabled < 0) {
     const char* e = getenv("HMGAN_TC_ROWBOX");
     rb_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  // CTA-pair (cta_group::2) row-box variant: N tiles of 64..256 columns, enough tiles for 74 pairs
+  static int pair_enabled = -1;
+  if (pair_enabled < 0) {
+    // validated (tools/tc_probe.py, tests) but measured 3-8 % SLOWER than the single-CTA kernel on these layers
+    // (profiles/r1_tc_pair_experiment.txt), so it is opt-in
+    const char* e = getenv("HMGAN_TC_PAIR");
+    pair_enabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (rb_enabled && pair_enabled && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9 &&
+      p.ntile >= 64 && p.ntile % 32 == 0 && (num_sms() % 2) == 0) {
+    TcParams q = p;
+    int S2 = 256 / q.ntile;
+    if (S2 < 1) S2 = 1;
+    if (S2 > 4) S2 = 4;
+    {
+      const char* e = getenv("HMGAN_TC_SMAX");
+      if (e && atoi(e) >= 1 && S2 > atoi(e)) S2 = atoi(e);
+    }
+    const int n_pairs = num_sms() / 2;
+    while (S2 > 1 && ((q.n_mtiles + 2 * S2 - 1) / (2 * S2)) * q.n_ntiles < n_pairs) S2 >>= 1;
+    if (((q.n_mtiles + 2 * S2 - 1) / (2 * S2)) * q.n_ntiles >= n_pairs) {
+      q.S = S2;
+      q.n_super = (q.n_mtiles + 2 * S2 - 1) / (2 * S2);
+      q.rb_bytes = (((TILE_M + q.kw - 1) * 128) + 1023) / 1024 * 1024;
+      q.rb_mode = 0;
+      q.a_slots = (S2 * q.rb_bytes > 40 * 1024) ? 2 : 3;
+      const int b_slot = (q.ntile / 2) * 128;
+      int b_slots = (227 * 1024 - 10240 - q.a_slots * S2 * q.rb_bytes) / b_slot;
+      if (b_slots > 12) b_slots = 12;
+      if (b_slots >= 2) {
+        q.b_slots = b_slots;
+        CUtensorMap rA, rA2, hB;
+        rc = encode_act(&rA, x1, d->B, d->H, d->W, d->C1, TILE_M + q.kw - 1, 1, 1);
+        if (!rc) rc = d->C2 ? encode_act(&rA2, x2, d->B, d->H, d->W, d->C2, TILE_M + q.kw - 1, 1, 1) : 0;
+        if (!d->C2) rA2 = rA;
+        if (!rc) rc = encode_wgt(&hB, w_tc, q.kh * q.kw, q.Cout, q.Cin, q.ntile / 2);
+        if (rc) {
+          set_error("hm_tc_conv: cuTensorMapEncodeTiled failed for the pair variant (CUresult %d)", rc);
+          return HM_ERR_CUDA;
+        }
+        const size_t smem_p = (size_t)q.a_slots * S2 * q.rb_bytes + (size_t)q.b_slots * b_slot + 1024 + 1024 + 8192;
+        static bool pair_attr = false;
+        if (!pair_attr) {
+          cudaError_t e = cudaFuncSetAttribute(tc_conv_rb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          if (e != cudaSuccess) {
+            set_error("hm_tc_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+            return HM_ERR_CUDA;
+          }
+          pair_attr = true;
+        }
+        int grid_p = q.n_super * q.n_ntiles * 2;
+        if (grid_p > num_sms()) grid_p = num_sms();
+        // at least 120 KB of dynamic shared memory keeps one CTA (which may own all 512 TMEM columns) per SM
+        tc_conv_rb2_kernel<<<grid_p, TC_THREADS, smem_p < 120 * 1024 ? 120 * 1024 : smem_p, (cudaStream_t)stream>>>(rA, rA2, hB, q);
+        HM_CHECK_LAUNCH("hm_tc_conv(row box, CTA pair)");
+        return HM_OK;
+      }
+    }
   }
   if (rb_enabled && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
     p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;

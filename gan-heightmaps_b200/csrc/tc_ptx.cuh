@@ -52,6 +52,17 @@ static __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm)
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// true in exactly one lane of a fully converged warp (call from warp-uniform code: the compiler then keeps tcgen05 / TMA
+// operands in uniform registers and emits ONE predicated instruction instead of a per-lane waterfall loop)
+static __device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 static __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 static __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 static __device__ __forceinline__ void tc_commit(uint32_t bar) {

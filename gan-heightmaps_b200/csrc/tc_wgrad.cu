@@ -68,6 +68,17 @@ __device__ __forceinline__ void wg_tma_4d(const CUtensorMap* tm, uint32_t dst, u
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// one lane of the converged warp (see elect_one() in tc_conv.cu: avoids the per-instruction waterfall loops that
+// `if (lane == 0)` regions compile to for tcgen05 / TMA instructions)
+__device__ __forceinline__ bool wg_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void wg_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const int cblocks = p.Cin / 64;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (wg_elect_one()) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int pt = pt0; pt < pt1; pt++) {
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (wg_elect_one()) {
       const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const uint32_t box_bytes = (uint32_t)(128 + p.kw - 1) * 128u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (wg_elect_one()) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int pt = pt0; pt < pt1; pt++) {
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (wg_elect_one()) {
       const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;

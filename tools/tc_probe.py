@@ -423,6 +423,11 @@ def perf():
               ("G7 64->64 @256^2 x32", 32, 256, 256, 64, 64, 5, 2),
               ("D5 128->256 @32^2 x64", 64, 32, 32, 128, 256, 5, 2),
               ("D7 256->256 @8^2 x64", 64, 8, 8, 256, 256, 5, 2)]
+    if os.environ.get("HMGAN_PERF_EXTRA"):
+        shapes = [("X 64->256 @256^2 x16", 16, 256, 256, 64, 256, 5, 2),
+                  ("X 64->128 @256^2 x32", 32, 256, 256, 64, 128, 5, 2),
+                  ("X 128->64 @256^2 x32", 32, 256, 256, 128, 64, 5, 2),
+                  ("X 256->256 @128^2 x16", 16, 128, 128, 256, 256, 3, 1)]
     for (name, B, H, W, Ci, Co, k, pad) in shapes:
         x = torch.randn(B, H, W, Ci, device="cuda").half()
         dy = torch.randn(B, H, W, Co, device="cuda").half()
