@@ -507,6 +507,67 @@ __device__ __forceinline__ void mma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t
   }
 }
 
+// MMA-issuer role of the row-box kernel with the tap loop fully unrolled (KW taps per filter row, NS sub-tiles) for a
+// weight ring whose length is a multiple of KW: the ring slot of tap s is (ring row)*KW + s, so every barrier address and
+// descriptor inside a row is the row's base plus a compile-time constant.  Per tap the issuing lane then executes one
+// barrier poll, NS*4 UTCHMMA and one commit; the poll for the NEXT tap (or next row's operands) sits behind the MMAs.
+template <int KW, int NS>
+__device__ __forceinline__ void rb_mma_role_unrolled(const TcParams& p, uint32_t base, uint32_t b_base, uint32_t ctrl,
+                                                     uint32_t tmem_base, int total_tiles, int cchunks) {
+  const uint32_t a_slot_bytes = p.S * p.rb_bytes, b_slot_bytes = p.ntile * 128;
+  const uint32_t afull0 = ctrl, aempty0 = ctrl + 8u * p.a_slots, bfull0 = ctrl + 8u * (2 * p.a_slots),
+                 bempty0 = ctrl + 8u * (2 * p.a_slots + p.b_slots), tfull0 = ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots),
+                 tempty0 = tfull0 + 16u;
+  const uint32_t idesc = umma_idesc_f16(p.ntile);
+  const uint32_t a_sub = (uint32_t)p.rb_bytes >> 4, b_sub = b_slot_bytes >> 4;
+  const uint32_t a_lo_base = umma_lo_of(base), b_lo_base = umma_lo_of(b_base);
+  const int ring_rows = p.b_slots / KW;
+  const int acc_cols = p.S * p.ntile;
+  int as = 0, brow = 0, it = 0;
+  uint32_t aph = 0, bph = 0;
+  const int steps = p.kh * cchunks;                                   // A slots (filter row x channel chunk) per tile
+  // operands of the very first step
+  mbar_wait(afull0 + 8u * as, aph);
+  mbar_wait(bfull0 + 8u * (brow * KW), bph);
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+    const int acc = it & 1;
+    mbar_wait(tempty0 + 8u * acc, ((it >> 1) & 1) ^ 1);
+    const uint32_t d_tmem = tmem_base + acc * acc_cols;
+    uint32_t first = 0;
+    const bool more_tiles = t + (int)gridDim.x < total_tiles;
+    for (int st = 0; st < steps; st++) {
+      const uint32_t a_lo0 = a_lo_base + (uint32_t)as * (a_slot_bytes >> 4);
+      const uint32_t b_lo0 = b_lo_base + (uint32_t)(brow * KW) * b_sub;
+      const uint32_t bf = bfull0 + 8u * (brow * KW), be = bempty0 + 8u * (brow * KW);
+      const bool last_step = st == steps - 1;
+      // next step's ring positions (needed for the look-ahead waits)
+      int as_n = as + 1, brow_n = brow + 1;
+      uint32_t aph_n = aph, bph_n = bph;
+      if (as_n == p.a_slots) { as_n = 0; aph_n ^= 1; }
+      if (brow_n == ring_rows) { brow_n = 0; bph_n ^= 1; }
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < KW; s++) {
+        mma_tap<NS>(d_tmem, a_lo0 + 8u * s, a_sub, b_lo0 + (uint32_t)s * b_sub, p.ntile, idesc, first);
+        first = 1;
+        tc_commit(be + 8u * s);
+        if (s == KW - 1) {
+          tc_commit(aempty0 + 8u * as);
+          if (last_step) tc_commit(tfull0 + 8u * acc);
+          if (!last_step || more_tiles) {                              // operands of the next step
+            mbar_wait(afull0 + 8u * as_n, aph_n);
+            mbar_wait(bfull0 + 8u * (brow_n * KW), bph_n);
+          }
+        } else {
+          mbar_wait(bf + 8u * (s + 1), bph);
+        }
+        tc_fence_after();
+      }
+      as = as_n; aph = aph_n; brow = brow_n; bph = bph_n;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Row-box variant (tiles that are 128 consecutive pixels of ONE image row, i.e. W >= 128): instead of one A tile per
 // tap, ONE box of 128+kw-1 pixel lines per filter ROW is loaded; the kw taps of that row are the same lines read
@@ -623,13 +684,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // descriptor arithmetic) longer than ~2 MMAs starves it (tools/mma_rate.cu).  Hence: a single lane, no per-tap
     // warp synchronisation, the wait for the NEXT weight slice placed behind the current slice's MMAs, descriptors
     // advanced by additions.
-    if (elect_one()) {
+    const bool unrolled = (p.kw == 5 || p.kw == 3) && p.b_slots % p.kw == 0 && (p.S == 1 || p.S == 2 || p.S == 4);
+    if (unrolled && elect_one()) {
+      // (tail super tiles run all S sub-tiles; the surplus accumulators are never read)
+#define RB_ROLE(KW_, NS_) rb_mma_role_unrolled<KW_, NS_>(p, base, b_base, ctrl, tmem_base, total_tiles, cchunks)
+      if (p.kw == 5) {
+        if (p.S == 1) RB_ROLE(5, 1); else if (p.S == 2) RB_ROLE(5, 2); else RB_ROLE(5, 4);
+      } else {
+        if (p.S == 1) RB_ROLE(3, 1); else if (p.S == 2) RB_ROLE(3, 2); else RB_ROLE(3, 4);
+      }
+#undef RB_ROLE
+    } else if (!unrolled && elect_one()) {
       const uint32_t idesc = umma_idesc_f16(p.ntile);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
-      const uint32_t mode_bits = 0;   // (rb_mode experiment retired: plain descriptors)
-      (void)mode_bits;
       bool have_b = false;            // bfull(bs) of the upcoming tap has already been waited for
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
         const int acc = it & 1;
@@ -1160,11 +1229,15 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       if (e && atoi(e) >= 1) p.a_slots = atoi(e);
     }
     int b_slots = (227 * 1024 - 10240 - p.a_slots * S * p.rb_bytes) / (p.ntile * 128);
+    if (p.kw == 5 || p.kw == 3) {                           // ring of whole filter rows: enables the unrolled MMA role
+      if (b_slots >= 2 * p.kw) b_slots = 2 * p.kw;
+      else if (b_slots >= p.kw) b_slots = p.kw;
+    }
     {
       static int bcap = -1;                                 // tuning knob: depth of the weight ring
       if (bcap < 0) {
         const char* e = getenv("HMGAN_RB_BCAP");
-        bcap = (e && atoi(e) >= 2) ? atoi(e) : 8;
+        bcap = (e && atoi(e) >= 2) ? atoi(e) : 10;
       }
       if (b_slots > bcap) b_slots = bcap;
     }
