@@ -335,6 +335,23 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   }
 }
 
+// One filter tap of the row-box kernels for NS sub-tiles, fully unrolled: NS*4 back-to-back MMAs.  Descriptors are
+// (constant high word, 32-bit low word); a_lo advances by a_sub per sub-tile, the accumulator column by ntile.
+constexpr uint32_t UMMA_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | (uint64_t)lo; }
+__device__ __forceinline__ uint32_t umma_lo_of(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+template <int NS>
+__device__ __forceinline__ void mma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t a_sub, uint32_t b_lo, uint32_t ntile,
+                                        uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+#pragma unroll
+    for (int k = 0; k < KCH / 16; k++)
+      tc_mma_f16(d_tmem + i * ntile, umma_desc_lo(a_lo + i * a_sub + 2 * k), umma_desc_lo(b_lo + 2 * k), idesc,
+                 acc_first | (uint32_t)k);
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -431,36 +448,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
+      // single issuing lane; 32-bit descriptor arithmetic; the NEXT stage's barrier is polled right behind the MMAs of
+      // the current one (the tensor pipe queues only a few MMAs: tools/mma_rate.cu)
       const uint32_t idesc = umma_idesc_f16(p.ntile);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const int ksteps = taps * ksteps_per_tap;
+      if ((int)blockIdx.x < total_tiles) mbar_wait(full_bar(0), 0);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
         const int acc = it & 1;
         mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
         const int st = t / p.n_ntiles;
         const int nv = min(p.S, p.n_mtiles - st * p.S);
-        const int ksteps = taps * ksteps_per_tap;
+        const bool more_tiles = t + (int)gridDim.x < total_tiles;
+        uint32_t first = 0;
         for (int ks = 0; ks < ksteps; ks++) {
-          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * stage_bytes;
-          const uint64_t bd = umma_desc_k_sw128(sa + a_bytes);
-          for (int i = 0; i < nv; i++) {                      // every M tile of the super tile reuses this B stage
-            const uint64_t ad = umma_desc_k_sw128(sa + i * A_BYTES);
-#pragma unroll
-            for (int k = 0; k < KCH / 16; k++)                // +32 B per K=16 slice inside the swizzle atom
-              tc_mma_f16(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (ks | k) != 0);
-          }
+          const uint32_t a_lo = umma_lo_of(base + stage * stage_bytes);
+          const uint32_t b_lo = a_lo + (a_bytes >> 4);
+          if (nv == 1) mma_tap<1>(d_tmem, a_lo, A_BYTES >> 4, b_lo, p.ntile, idesc, first);
+          else if (nv == 2) mma_tap<2>(d_tmem, a_lo, A_BYTES >> 4, b_lo, p.ntile, idesc, first);
+          else if (nv == 4) mma_tap<4>(d_tmem, a_lo, A_BYTES >> 4, b_lo, p.ntile, idesc, first);
+          else mma_tap<3>(d_tmem, a_lo, A_BYTES >> 4, b_lo, p.ntile, idesc, first);
+          first = 1;
           tc_commit(empty_bar(stage));                        // frees the stage when these MMAs retire
+          if (ks == ksteps - 1) tc_commit(tfull_bar(acc));    // accumulator complete
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
+          if (ks + 1 < ksteps || more_tiles) mbar_wait(full_bar(stage), phase);
         }
-        tc_commit(tfull_bar(acc));                            // accumulator complete
       }
     }
   } else {
@@ -488,23 +508,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128_line(uint32_t saddr, int mode) {
   if (mode == 0) return umma_desc_k_sw128(saddr);
   return umma_desc_k_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
-}
-
-// One filter tap of the row-box kernels for NS sub-tiles, fully unrolled: NS*4 back-to-back MMAs.  Descriptors are
-// (constant high word, 32-bit low word); a_lo advances by a_sub per sub-tile, the accumulator column by ntile.
-constexpr uint32_t UMMA_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | (uint64_t)lo; }
-__device__ __forceinline__ uint32_t umma_lo_of(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
-template <int NS>
-__device__ __forceinline__ void mma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t a_sub, uint32_t b_lo, uint32_t ntile,
-                                        uint32_t idesc, uint32_t acc_first) {
-#pragma unroll
-  for (int i = 0; i < NS; i++) {
-#pragma unroll
-    for (int k = 0; k < KCH / 16; k++)
-      tc_mma_f16(d_tmem + i * ntile, umma_desc_lo(a_lo + i * a_sub + 2 * k), umma_desc_lo(b_lo + 2 * k), idesc,
-                 acc_first | (uint32_t)k);
-  }
 }
 
 // MMA-issuer role of the row-box kernel with the tap loop fully unrolled (KW taps per filter row, NS sub-tiles) for a

@@ -207,29 +207,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     }
   } else if (warp == 1) {
     if (wg_elect_one()) {
+      // single issuing lane, 32-bit descriptor arithmetic, the NEXT step's barriers polled right behind the MMAs
       const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
+      constexpr uint32_t HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);    // SBO 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t LBO = (uint32_t)(BLK_BYTES >> 4) << 16;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int pt = pt0; pt < pt1; pt++) {
+      if (pt1 > pt0 && mt1 > mt0) {
         wg_wait(bfull(bs), bph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b_addr = base + bs * b_bytes;
+        wg_wait(afull(as), aph);
+      }
+      for (int pt = pt0; pt < pt1; pt++) {
+        const uint32_t b_lo = (((base + bs * b_bytes) & 0x3FFFF) >> 4) | LBO;
+        const uint32_t accum0 = pt > pt0 ? 1u : 0u;
         for (int mt = mt0; mt < mt1; mt++) {
-          wg_wait(afull(as), aph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_addr = a_base + as * a_bytes;
+          const uint32_t a_lo = (((a_base + as * a_bytes) & 0x3FFFF) >> 4) | LBO;
           const uint32_t d_tmem = tmem_base + (mt - mt0) * p.Cout;
 #pragma unroll
-          for (int kk = 0; kk < 8; kk++) {                   // 16 pixels (two 8-row swizzle atoms) per MMA
-            const uint64_t ad = umma_desc_mn_sw128(a_addr + kk * 2048, BLK_BYTES);
-            const uint64_t bd = umma_desc_mn_sw128(b_addr + kk * 2048, BLK_BYTES);
-            wg_mma(d_tmem, ad, bd, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < 8; kk++)                     // 16 pixels (two 8-row swizzle atoms) per MMA
+            wg_mma(d_tmem, ((uint64_t)HI << 32) | (uint64_t)(a_lo + kk * 128), ((uint64_t)HI << 32) | (uint64_t)(b_lo + kk * 128),
+                   idesc, accum0 | (uint32_t)kk);
           wg_commit(aempty(as));
           if (++as == p.a_slots) { as = 0; aph ^= 1; }
+          const bool last_mt = mt == mt1 - 1;
+          if (last_mt) {
+            wg_commit(bempty(bs));
+            if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+            if (pt + 1 < pt1) {
+              wg_wait(bfull(bs), bph);
+              wg_wait(afull(as), aph);
+            }
+          } else {
+            wg_wait(afull(as), aph);
+          }
         }
-        wg_commit(bempty(bs));
-        if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
       }
       wg_commit(tfull);
     }
@@ -373,34 +385,55 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     }
   } else if (warp == 1) {
     if (wg_elect_one()) {
+      // The tensor pipe queues only a few MMAs (tools/mma_rate.cu), so the issuing lane must not pause between groups:
+      // the per-M-tile operand offsets (which need integer divisions) are computed ONCE, descriptors are 32-bit adds,
+      // and the barriers of the NEXT pixel tile are polled right behind the MMAs of the current one.
       const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int pt = pt0; pt < pt1; pt++) {
-        wg_wait(bfull(bs), bph);
-        wg_wait(afull(as), aph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t b_addr = base + bs * b_bytes;
-        const uint32_t a_addr = a_base + as * a_bytes;
-        for (int mt = mt0; mt < mt1; mt++) {
+      const int nmt = mt1 - mt0;                                       // <= 8 accumulators (512 / Cout)
+      uint32_t rel[8];                                                 // (offset in the A slot >> 4) | (LBO >> 4) << 16
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        rel[i] = 0;
+        if (i < nmt) {
+          const int mt = mt0 + i;
           int u0 = 2 * mt, u1 = 2 * mt + 1;
           if (u1 >= p.units) u1 = u0;                                  // odd tail: rows 64..127 are ignored
           const int s0 = (u0 / cblocks) % p.kw, s1 = (u1 / cblocks) % p.kw;
-          const uint32_t ad0 = a_addr + box_of(u0) * q.rb_bytes + s0 * 128;
-          const uint32_t ad1 = a_addr + box_of(u1) * q.rb_bytes + s1 * 128;
-          const uint32_t lbo = ad1 - ad0;                              // >= 0: units ascend with the box order
-          const uint32_t d_tmem = tmem_base + (mt - mt0) * p.Cout;
+          const uint32_t o0 = box_of(u0) * q.rb_bytes + s0 * 128;
+          const uint32_t o1 = box_of(u1) * q.rb_bytes + s1 * 128;
+          rel[i] = (o0 >> 4) | ((((o1 - o0) >> 4) & 0x3FFFu) << 16);   // units ascend with the box order: o1 >= o0
+        }
+      }
+      constexpr uint32_t HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);    // SBO 1024 B, version 1, SWIZZLE_128B
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      if (pt1 > pt0) {
+        wg_wait(bfull(bs), bph);
+        wg_wait(afull(as), aph);
+      }
+      for (int pt = pt0; pt < pt1; pt++) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t b_lo = (((base + bs * b_bytes) & 0x3FFFF) >> 4) | ((uint32_t)(BLK_BYTES >> 4) << 16);
+        const uint32_t a_lo = ((a_base + as * a_bytes) & 0x3FFFF) >> 4;
+        const uint32_t accum0 = pt > pt0 ? 1u : 0u;
 #pragma unroll
-          for (int kk = 0; kk < 8; kk++) {
-            const uint64_t ad = umma_desc_mn_sw128(ad0 + kk * 2048, lbo);
-            const uint64_t bd = umma_desc_mn_sw128(b_addr + kk * 2048, BLK_BYTES);
-            wg_mma(d_tmem, ad, bd, idesc, (pt > pt0 || kk > 0) ? 1u : 0u);
+        for (int i = 0; i < 8; i++) {
+          if (i < nmt) {
+            const uint32_t d_tmem = tmem_base + i * p.Cout;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)                             // 16 pixels (two 8-row swizzle atoms) per MMA
+              wg_mma(d_tmem, ((uint64_t)HI << 32) | (uint64_t)(a_lo + rel[i] + kk * 128),
+                     ((uint64_t)HI << 32) | (uint64_t)(b_lo + kk * 128), idesc, accum0 | (uint32_t)kk);
           }
         }
         wg_commit(aempty(as));
         wg_commit(bempty(bs));
         if (++as == p.a_slots) { as = 0; aph ^= 1; }
         if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+        if (pt + 1 < pt1) {                                            // next pixel tile's operands
+          wg_wait(bfull(bs), bph);
+          wg_wait(afull(as), aph);
+        }
       }
       wg_commit(tfull);
     }
