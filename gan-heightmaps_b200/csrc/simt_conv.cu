@@ -356,6 +356,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       int r = k / 6 - (dd >> 1), q = k % 6 - (dd & 1);
       if (r >= 0 && r < 5 && q >= 0 && q < 5) val = w[((size_t)co * 5 + (4 - r)) * 5 + (4 - q)];
     }
+  } else if (mode == 17) {
+    // Deconv2DLayer W (cin,cout,2,2), stride 2, all four output phases at once (hm_tc_conv, transposed == 2):
+    // Wt[(u*2+v)*cout + co][ci] = W[ci][co][1-u][1-v]   (K-major, K = ci)
+    int ci = (int)(i % cin);
+    int nn = (int)(i / cin);
+    int ph = nn / cout, co = nn - ph * cout;
+    val = w[(((size_t)ci * cout + co) * 2 + (1 - (ph >> 1))) * 2 + (1 - (ph & 1))];
+  } else if (mode == 18) {
+    // its input gradient as a 1x1 convolution of s2d(dy) (hm_s2d_pad64: 64 channels, (phase, co) in the first 4*cout):
+    // Wt[ci][k] = W[ci][co][1-u][1-v] for k = (u*2+v)*cout + co < 4*cout, else 0   (K-major, K = 64)
+    int k = (int)(i % 64);
+    int ci = (int)(i / 64);
+    val = 0.f;
+    if (k < 4 * cout) {
+      int ph = k / cout, co = k - ph * cout;
+      val = w[(((size_t)ci * cout + co) * 2 + (1 - (ph >> 1))) * 2 + (1 - (ph & 1))];
+    }
   } else {
     val = w[i];
   }
@@ -407,6 +424,16 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
                            : dwp[(size_t)(tap * cin + ci) * 64 + ph * cout + co];
       }
     dw[i] = acc;
+  } else if (mode == 17) {
+    // master deconv W[ci][co][a][b] (2x2, stride 2) from dwp[ci][64], column (u*2+v)*cout + co, (u,v) = (1-a, 1-b):
+    // the tensor-core weight gradient of x against hm_s2d_pad64(dy)
+    int b = (int)(i % 2);
+    long long t = i / 2;
+    int a = (int)(t % 2);
+    t /= 2;
+    int co = (int)(t % cout);
+    int ci = (int)(t / cout);
+    dw[i] = dwp[(size_t)ci * 64 + ((1 - a) * 2 + (1 - b)) * cout + co];
   } else {
     dw[i] = dwp[i];
   }
@@ -489,12 +516,14 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 16),
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 18),
                "hm_pack_conv_weight: bad mode %d", mode);
   HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
   HM_CHECK_ARG((mode != 15 && mode != 16) || (cin == 1 && kh == 5 && kw == 5),
                "hm_pack_conv_weight: modes 15/16 need Cin == 1 and a 5x5 filter");
   HM_CHECK_ARG(mode != 16 || cout == 64, "hm_pack_conv_weight: mode 16 needs Cout == 64");
+  HM_CHECK_ARG((mode != 17 && mode != 18) || (kh == 2 && kw == 2), "hm_pack_conv_weight: modes 17/18 are defined for 2x2 filters");
+  HM_CHECK_ARG(mode != 18 || 4 * cout <= 64, "hm_pack_conv_weight: mode 18 needs 4*Cout <= 64");
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
@@ -504,6 +533,8 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   if (mode == 12) n = 16LL * cout * cin;
   if (mode == 14) n = 64LL * cin;
   if (mode == 15 || mode == 16) n = 256LL * cout;
+  if (mode == 17) n = 4LL * cout * cin;
+  if (mode == 18) n = 64LL * cin;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)
@@ -517,7 +548,8 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
 extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int cout, int cin, int kh,
                                     int kw, void* stream) {
   HM_CHECK_ARG(dwp && dw, "hm_unpack_conv_wgrad: null pointer");
-  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9 || mode == 10) && kh == 5 && kw == 5),
+  HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9 || mode == 10) && kh == 5 && kw == 5) ||
+                   (mode == 17 && kh == 2 && kw == 2 && 4 * cout <= 64),
                "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;
   unpack_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dwp, dw, mode, cout,

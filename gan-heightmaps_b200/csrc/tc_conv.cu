@@ -1060,8 +1060,20 @@ static bool is_dgrad_s2(const HmConvDesc* d) {
          d->Ho == 2 * d->H && d->Wo == 2 * d->W;
 }
 
+// Deconv2DLayer with a 2x2 filter and stride 2 (reference architectures/p2p.py:23-24,272; no overlap): every input
+// pixel q produces the 2x2 output block y[2q + (u,v)][co] = sum_ci x[q][ci] * W[ci][co][1-u][1-v], i.e. a 1x1
+// convolution with N = (phase, co) columns (pack mode 17) followed by the depth-to-space scatter of the epilogue.
+// Descriptor: transposed == 2, kh = kw = 2, stride = 2, H x W = INPUT grid, Ho = 2H, Wo = 2W.
+static bool is_deconv_d2s(const HmConvDesc* d) {
+  return d->transposed == 2 && d->kh == 2 && d->kw == 2 && d->stride == 2 && d->pad == 0 && !d->up &&
+         d->Ho == 2 * d->H && d->Wo == 2 * d->W && d->oH == d->Ho && d->oW == d->Wo && d->os == 1 && !d->ou && !d->ov &&
+         d->split == d->Cout && !d->accumulate;
+}
+
 extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   if (!d) return 0;
+  if (d->dtype == HM_F16 && is_deconv_d2s(d))
+    return d->C1 % KCH == 0 && d->C2 % KCH == 0 && d->C1 > 0 && (d->Cout % 32 == 0 || d->Cout <= 4) && 4 * d->Cout <= 2048;
   if (d->dtype == HM_F16 && is_up2conv(d))
     return d->C1 % KCH == 0 && d->C1 > 0 && d->os == 1 && !d->ou && !d->ov && d->oH == d->Ho && d->oW == d->Wo;
   if (d->dtype == HM_F16 && is_dgrad_s2(d))
@@ -1097,19 +1109,22 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
     return HM_ERR_CUDA;
   }
   if ((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_tc) & 15) ||
-      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15)) || ((is_up2conv(d) || is_dgrad_s2(d)) && !y)) {
+      ((d->Cout % 16 == 0) && (((uintptr_t)y | (uintptr_t)y2) & 15)) ||
+      ((is_up2conv(d) || is_dgrad_s2(d) || is_deconv_d2s(d)) && !y)) {
     set_error("hm_tc_conv: pointers must be 16-byte aligned");
     return HM_ERR_ALIGN;
   }
   TcParams p;
   const bool dg2 = is_dgrad_s2(d);
-  const bool up2 = is_up2conv(d) || dg2;                                  // both use the phase / depth-to-space form
+  const bool dc2 = is_deconv_d2s(d);
+  const bool up2 = is_up2conv(d) || dg2 || dc2;                           // all use the phase / depth-to-space form
   p.d2s = up2 ? 1 : 0;
   p.cph = d->Cout;
   p.stride = (!up2 && d->stride == 2) ? 2 : 1;
   p.B = d->B; p.Ho = up2 ? d->H : d->Ho; p.Wo = up2 ? d->W : d->Wo;       // tile grid (low-res when phase-decomposed)
   p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = up2 ? 4 * d->Cout : d->Cout;
-  p.kh = dg2 ? 2 : (up2 ? 3 : d->kh); p.kw = dg2 ? 2 : (up2 ? 3 : d->kw); p.pad = dg2 ? 0 : (up2 ? 1 : d->pad);
+  p.kh = dc2 ? 1 : (dg2 ? 2 : (up2 ? 3 : d->kh)); p.kw = dc2 ? 1 : (dg2 ? 2 : (up2 ? 3 : d->kw));
+  p.pad = (dg2 || dc2) ? 0 : (up2 ? 1 : d->pad);
   p.bw = pow2_floor(p.Wo < TILE_M ? p.Wo : TILE_M);
   p.bh = pow2_floor(p.Ho < TILE_M / p.bw ? p.Ho : TILE_M / p.bw);
   p.bn = TILE_M / (p.bw * p.bh);

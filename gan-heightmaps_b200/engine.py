@@ -176,6 +176,13 @@ class ConvOp(object):
                      and self.kh == self.kw and self.Cout % 64 == 0 and self.Cout <= 256)
         if self.col1:
             self.tc_fwd = True
+        # Deconv2DLayer 2x2 stride 2 (no overlap) as ONE tensor-core launch: 1x1 convolution with N = (phase, co) and a
+        # depth-to-space epilogue; its gradients through hm_s2d_pad64 (dy regrouped to (phase, co) channels)
+        self.dc2 = False
+        if (rt.precision == "fast" and kind == "deconv" and self.kh == 2 and self.kw == 2 and self.stride == 2
+                and not self.up and 4 * self.Cout <= 64 and self.C1 % 64 == 0 and self.C2 % 64 == 0):
+            self.dc2 = bool(_lib.query("hm_tc_conv_supported", C.byref(self._dc2_desc(rt, 1))))
+            self.tc_fwd = self.dc2
         self.path = "tcgen05" if self.tc_fwd else "simt"
         # hm_c1s2_conv (in-kernel im2col of a one-channel image): (a) this layer + its 2x2 max-pool in one pass, set by
         # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
@@ -198,6 +205,12 @@ class ConvOp(object):
             self.dwp = rt.empty((n,), torch.float32)
         if self.up and self.src.srcs[0].kind != "input" and not self.c1dg:
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
+        if self.dc2:
+            self.dy64 = rt.empty((B, self.x1.shape[0], self.x1.shape[1], 64))
+            if self.wt_f is None:
+                self.wt_f = rt.empty((4 * self.Cout * self.Cin,))
+                self.wt_d = rt.empty((64 * self.Cin,))
+                self.dwp = rt.empty((64 * self.Cin,), torch.float32)
         if self.c1dg and self.wk is None:
             self.wk = rt.empty((64 * 64,))
         if self.pool_fused is not None:
@@ -261,6 +274,9 @@ class ConvOp(object):
             else:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 12 if self.dg2 else 6, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
+        elif self.dc2:
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 17, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 18, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
         else:
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -295,6 +311,34 @@ class ConvOp(object):
             d.kh, d.kw, d.stride, d.pad = self.kh, self.kw, self.stride, self.pad
             d.Ho, d.Wo = oH, oW
             d.os, d.ou, d.ov = 1, 0, 0
+        return d
+
+    def _dc2_desc(self, rt, n):
+        """Deconv2DLayer 2x2 stride 2, all four phases (hm_tc_conv, transposed == 2): H x W is the INPUT grid."""
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W, d.C1, d.C2, d.up = n, self.x1.shape[0], self.x1.shape[1], self.C1, self.C2, 0
+        d.kh = d.kw = 2
+        d.stride, d.pad, d.transposed = 2, 0, 2
+        d.Ho, d.Wo, d.Cout = self.out.shape[0], self.out.shape[1], self.Cout
+        d.oH, d.oW, d.os, d.ou, d.ov = d.Ho, d.Wo, 1, 0, 0
+        d.split = self.Cout
+        d.act, d.slope = ACT[self.act.name], self.act.slope
+        d.accumulate = 0
+        return d
+
+    def _dc2_1x1_desc(self, rt, n, c1, c2, cout, split=None, acc=0):
+        """1x1 convolution on the deconv's INPUT grid (weight / input gradient against s2d(dy))."""
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W, d.C1, d.C2, d.up = n, self.x1.shape[0], self.x1.shape[1], c1, c2, 0
+        d.kh = d.kw = 1
+        d.stride, d.pad, d.transposed = 1, 0, 0
+        d.Ho, d.Wo, d.Cout = d.H, d.W, cout
+        d.oH, d.oW, d.os, d.ou, d.ov = d.H, d.W, 1, 0, 0
+        d.split = cout if split is None else split
+        d.act, d.slope = 0, 0.0
+        d.accumulate = acc
         return d
 
     def _tc_fwd_desc(self, rt, n):
@@ -354,7 +398,9 @@ class ConvOp(object):
         x2 = _ptr(self.x2.b(lo, hi)) if self.x2 is not None else None
         bias = _ptr(self.net.pview(self.bias))
         y = _ptr(self.out.b(lo, hi)) if self.out.buf is not None else None
-        if self.kind == "deconv":
+        if self.dc2:
+            rt.call("hm_tc_conv", C.byref(self._dc2_desc(rt, n)), x1, x2, _ptr(self.wt_f), bias, y, None)
+        elif self.kind == "deconv":
             per = self.Cin * self.Cout
             for u in range(self.kh):
                 for v in range(self.kw):
@@ -434,7 +480,14 @@ class ConvOp(object):
             g = self.out.grad_w[lo:hi]        # weight and bias gradients see the per-sample-weighted gradient
         if wgrad:
             self.dwp.zero_()
-            if self.kind == "deconv":
+            if self.dc2:
+                # dW[ci][(phase,co)] = x^T . s2d(dy): a 1x1 tensor-core weight gradient on the input grid
+                h, w = self.x1.shape[0], self.x1.shape[1]
+                rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, h, w, self.Cout)
+                d = self._dc2_1x1_desc(rt, n, self.C1, self.C2, 64)
+                rt.call("hm_tc_wgrad", C.byref(d), x1, x2, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
+                mode = 17
+            elif self.kind == "deconv":
                 per = self.Cin * self.Cout
                 for u in range(self.kh):
                     for v in range(self.kw):
@@ -489,7 +542,16 @@ class ConvOp(object):
             return
         if self.kind == "dense":
             raise NotImplementedError("input gradient of a DenseLayer (only ever fed by the latent input)")
-        if self.c1dg and t1 and not self.x1.gw:
+        if self.dc2 and (t1 or t2):
+            # dx[q][ci] = sum_(phase,co) dy[2q+phase][co] W[ci][co][phase]: 1x1 convolution of s2d(dy) (pack mode 18),
+            # channels [0,C1) to the first source's gradient, the rest to the second's
+            if not wgrad:
+                rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, self.x1.shape[0], self.x1.shape[1], self.Cout)
+            acc = (self.x1.take_acc() if t1 else 0) | ((self.x2.take_acc() << 1) if t2 else 0)
+            d = self._dc2_1x1_desc(rt, n, 64, 0, self.Cin, split=self.C1, acc=acc)
+            rt.call("hm_tc_conv", C.byref(d), _ptr(self.dy64[lo:hi]), None, _ptr(self.wt_d), None,
+                    _ptr(self.x1.g(lo, hi)) if t1 else None, _ptr(self.x2.g(lo, hi)) if t2 else None)
+        elif self.c1dg and t1 and not self.x1.gw:
             # dy[B,2H,2W,1] -> dx[B,H,W,64] in one pass (four 3x3 phase filters as a 6x6 stride-2 gather of dy)
             self.x1.gw = True
             rt.call("hm_c1s2_conv", _ptr(g), _ptr(self.wk), None, _ptr(self.x1.g(lo, hi)), None, n, self.Hv, self.Wv,

@@ -177,8 +177,8 @@ class Pix2Pix(object):
                      _ptr(self.losses[slot:]))
 
     def step_device(self, Zd, Xd, Yd, train=True):
-        """One train_fn / loss_fn evaluation on float32 NCHW DEVICE tensors; the five
-        losses stay on the device in self.losses (no host synchronisation).
+        """One train_fn / loss_fn evaluation on float32 NCHW DEVICE tensors (Yd may be None for a model without the
+        pix2pix stage); the five losses stay on the device in self.losses (no host synchronisation).
 
         On a CUDA device the ~1000 kernel launches of a step are captured once into a CUDA graph per
         (batch size, train flag) -- after two eager warm-up calls that size every buffer -- and replayed
@@ -187,7 +187,7 @@ class Pix2Pix(object):
         HMGAN_CUDA_GRAPHS=0 to always run eagerly; Adam runs eagerly (its step count is a kernel argument)."""
         if not self._graphs_ok:
             return self._step_eager(Zd, Xd, Yd, train)
-        key = (tuple(Zd.shape), tuple(Xd.shape), tuple(Yd.shape), bool(train))
+        key = (tuple(Zd.shape), tuple(Xd.shape), tuple(Yd.shape) if Yd is not None else None, bool(train))
         st = self._graphs.get(key)
         if st is None:
             st = self._graphs[key] = {"calls": 0, "graph": None}
@@ -196,7 +196,7 @@ class Pix2Pix(object):
             if st["calls"] <= 2:
                 return self._step_eager(Zd, Xd, Yd, train)
             # capture: static input buffers, then record the step on torch's capture stream
-            st["Z"], st["X"], st["Y"] = Zd.clone(), Xd.clone(), Yd.clone()
+            st["Z"], st["X"], st["Y"] = Zd.clone(), Xd.clone(), (Yd.clone() if Yd is not None else None)
             self._sync_lr()
             torch.cuda.synchronize(self.rt.device)
             g = torch.cuda.CUDAGraph()
@@ -206,7 +206,7 @@ class Pix2Pix(object):
             st["launches"] = self.rt.launches - l0
             st["graph"] = g
         for dst, src in ((st["Z"], Zd), (st["X"], Xd), (st["Y"], Yd)):
-            if dst.data_ptr() != src.data_ptr():
+            if dst is not None and dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._sync_lr()
         st["graph"].replay()
@@ -309,7 +309,7 @@ class Pix2Pix(object):
     def _step_host(self, Z, X, Y, train):
         Zd = self._to_dev("Z", Z)
         Xd = self._to_dev("X", X)
-        Yd = self._to_dev("Y", Y)
+        Yd = self._to_dev("Y", Y) if self.have_p2p else None      # a DCGAN-only model never reads the texture batch
         losses = self.step_device(Zd, Xd, Yd, train).cpu().numpy()
         return [np.float32(v) for v in losses]
 

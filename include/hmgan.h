@@ -172,7 +172,7 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  *  mode 6: Conv2DLayer W, tcgen05 input-gradient pack     -> Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
  *          (the input gradient of a stride-1 'same' convolution is the forward correlation of dy with this
  *           pack and pad' = k-1-pad)
- *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, modes 14/15: hm_c1s2_conv operands, mode 12: input
+ *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, modes 14/15/16: hm_c1s2_* operands, modes 17/18: Deconv2DLayer 2x2 stride 2 on the tensor cores (all phases; its input gradient over hm_s2d_pad64), mode 12: input
  *          gradient of a 3x3 stride-2 convolution as a 2x2-tap phase convolution of dy (see csrc/simt_conv.cu)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)

@@ -206,6 +206,13 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     r, s_ = uu - (dd >> 1), vv - (dd & 1)
                     if 0 <= r < 5 and 0 <= s_ < 5:
                         out[dd, uu * 6 + vv, :] = Wc[:, r, s_]
+    elif mode == 17:
+        Wd = W.reshape(cin, cout, 2, 2)[:, :, ::-1, ::-1]                          # Wd[ci][co][u][v] = W[ci][co][1-u][1-v]
+        out = Wd.transpose(2, 3, 1, 0).reshape(4 * cout, cin)                      # [(u,v,co)][ci]
+    elif mode == 18:
+        Wd = W.reshape(cin, cout, 2, 2)[:, :, ::-1, ::-1]
+        out = np.zeros((cin, 64), np.float32)
+        out[:, :4 * cout] = Wd.transpose(0, 2, 3, 1).reshape(cin, 4 * cout)        # [ci][(u,v,co)]
     elif mode == 7:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
@@ -235,6 +242,10 @@ def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
                     for s_ in range(5):
                         gc[r, s_] += g3[(py + r - 2) // 2 + 1, (px + s_ - 2) // 2 + 1, :, py * 2 + px, :]
         dst[:] = np.ascontiguousarray(gc.transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]).reshape(-1)
+        return 0
+    if mode == 17:
+        g4 = _a(dwp, cin * 64, np.float32).reshape(cin, 64)[:, :4 * cout].reshape(cin, 2, 2, cout)   # [ci][u][v][co]
+        dst[:] = np.ascontiguousarray(g4.transpose(0, 3, 1, 2)[:, :, ::-1, ::-1]).reshape(-1)
         return 0
     if mode == 0:
         g = src.reshape(kh, kw, cin, cout).transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]
@@ -547,7 +558,15 @@ def _is_dgrad_s2(d):
             d.Ho == 2 * d.H and d.Wo == 2 * d.W)
 
 
+def _is_deconv_d2s(d):
+    return (d.transposed == 2 and d.kh == 2 and d.kw == 2 and d.stride == 2 and d.pad == 0 and not d.up
+            and d.Ho == 2 * d.H and d.Wo == 2 * d.W and d.oH == d.Ho and d.oW == d.Wo and d.os == 1 and not d.ou
+            and not d.ov and d.split == d.Cout and not d.accumulate)
+
+
 def _tc_ok(d, wgrad):
+    if not wgrad and d.dtype == F16 and _is_deconv_d2s(d):
+        return d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0 and (d.Cout % 32 == 0 or d.Cout <= 4)
     if not wgrad and d.dtype == F16 and _is_dgrad_s2(d):
         return (d.C1 % 64 == 0 and d.C1 > 0 and d.C2 == 0 and d.os == 1 and not d.ou and not d.ov and d.oH == d.Ho
                 and d.oW == d.Wo and d.split == d.Cout and (d.Cout % 32 == 0 or d.Cout <= 4))
@@ -585,6 +604,19 @@ def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
         wt = _t(_a(w_tc, 36 * Co * Ci, np.float16)).reshape(3, 3, 4 * Co, Ci)
         out = F.conv2d(a, wt.permute(2, 3, 0, 1).contiguous(), padding=1)          # [B,4Co,H,W]
         out = out.reshape(B, 2, 2, Co, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B, 2 * H, 2 * W, Co)
+        if bias:
+            out = out + _t(_a(bias, Co, np.float32))
+        out = _act(out, d.act, d.slope)
+        _a(y, B * 4 * H * W * Co, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+        return 0
+    if d.transposed == 2:
+        # Deconv2DLayer 2x2 stride 2: 1x1 convolution with N = (phase, co) (pack mode 17), then depth-to-space
+        B, H, W, Ci, Co = d.B, d.H, d.W, d.C1 + d.C2, d.Cout
+        a = _t(_a(x1, B * H * W * d.C1, np.float16)).reshape(B * H * W, d.C1)
+        if d.C2:
+            a = torch.cat([a, _t(_a(x2, B * H * W * d.C2, np.float16)).reshape(B * H * W, d.C2)], 1)
+        wt = _t(_a(w_tc, 4 * Co * Ci, np.float16)).reshape(4 * Co, Ci)
+        out = (a @ wt.t()).reshape(B, H, W, 2, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Co)
         if bias:
             out = out + _t(_a(bias, Co, np.float32))
         out = _act(out, d.act, d.slope)

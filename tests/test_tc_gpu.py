@@ -56,3 +56,12 @@ def test_c1s2_bwd_pooled_first_layer_gradients(case):
     on the same fp16 data: 3e-3 of each gradient's scale (g*act' and the patch-space gradient are rounded to fp16)."""
     rel, line = tc_probe.run_c1bwd_case(*case)
     assert rel <= 3e-3, line
+
+
+@pytest.mark.parametrize("case", tc_probe.DC2_CASES, ids=[c[0] for c in tc_probe.DC2_CASES])
+def test_tc_deconv_2x2_stride2_all_phases(case):
+    """Deconv2DLayer 2x2 stride 2 (pix2pix U-Net output layer, reference architectures/p2p.py:272) as one tensor-core
+    launch (1x1 GEMM with N = (phase, co) + depth-to-space epilogue, concat source, tanh) and its input gradient over
+    hm_s2d_pad64, against torch conv_transpose2d / its adjoint in float32: 3e-3 of the output scale."""
+    rel, line = tc_probe.run_dc2_case(*case)
+    assert rel <= 3e-3, line

@@ -234,6 +234,58 @@ def run_wgrad_case(name, B, H, W, C1, C2, Cout, k, pad, act):
     return float(err.max()) / scale, line
 
 
+DC2_CASES = [
+    # name, B, H, W (input grid), C1, C2, Cout, act
+    ("dc2_128_3_w256_tanh", 1, 256, 256, 64, 64, 3, 4),
+    ("dc2_64_1_w16", 2, 16, 16, 64, 0, 1, 0),
+    ("dc2_128_3_ragged_10x12", 3, 10, 12, 128, 0, 3, 0),
+]
+
+
+def run_dc2_case(name, B, H, W, C1, C2, Co, act):
+    """Deconv2DLayer 2x2 stride 2 through hm_tc_conv (transposed == 2, pack mode 17) and its input gradient
+    (hm_s2d_pad64 + 1x1 hm_tc_conv with pack mode 18) against torch conv_transpose2d in float32 on the same fp16 data."""
+    import torch.nn.functional as F
+    torch.manual_seed(abs(hash(name)) % 1000)
+    Ci = C1 + C2
+    x1 = torch.randn(B, H, W, C1, device="cuda").half()
+    x2 = torch.randn(B, H, W, C2, device="cuda").half() if C2 else None
+    Wm = (torch.randn(Ci, Co, 2, 2, device="cuda") / np.sqrt(Ci)).half().float()
+    bias = torch.randn(Co, device="cuda") * 0.1
+    wt = torch.empty(4 * Co * Ci, device="cuda", dtype=torch.float16)
+    wd = torch.empty(64 * Ci, device="cuda", dtype=torch.float16)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wt.data_ptr(), 17, Co, Ci, 2, 2, 0, 0, 1, None)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wd.data_ptr(), 18, Co, Ci, 2, 2, 0, 0, 1, None)
+    d = desc(dtype=1, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=2, kw=2, stride=2, pad=0, transposed=2, Ho=2 * H, Wo=2 * W,
+             Cout=Co, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Co, act=act, slope=0.2, accumulate=0)
+    y = torch.full((B, 2 * H, 2 * W, Co), 7.0, device="cuda", dtype=torch.float16)
+    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), x2.data_ptr() if C2 else None, wt.data_ptr(), bias.data_ptr(),
+              y.data_ptr(), None, None)
+    xin = torch.cat([x1, x2], 3) if C2 else x1
+    # Lasagne Deconv2DLayer(flip_filters=False) == conv_transpose2d with the filter rotated by 180 degrees
+    ref = F.conv_transpose2d(xin.float().permute(0, 3, 1, 2), Wm.flip(2, 3), bias, stride=2)
+    if act == 4:
+        ref = torch.tanh(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    e_f = float((y.float() - ref).abs().max()) / float(ref.abs().max())
+    # input gradient
+    dy = torch.randn(B, 2 * H, 2 * W, Co, device="cuda").half()
+    dy64 = torch.empty(B, H, W, 64, device="cuda", dtype=torch.float16)
+    _lib.call("hm_s2d_pad64", dy.data_ptr(), dy64.data_ptr(), B, H, W, Co, None)
+    g1 = torch.full((B, H, W, C1), 7.0, device="cuda", dtype=torch.float16)
+    g2 = torch.full((B, H, W, max(C2, 1)), 7.0, device="cuda", dtype=torch.float16)
+    dd = desc(dtype=1, B=B, H=H, W=W, C1=64, C2=0, up=0, kh=1, kw=1, stride=1, pad=0, transposed=0, Ho=H, Wo=W, Cout=Ci,
+              oH=H, oW=W, os=1, ou=0, ov=0, split=C1, act=0, slope=0.0, accumulate=0)
+    _lib.call("hm_tc_conv", C.byref(dd), dy64.data_ptr(), None, wd.data_ptr(), None, g1.data_ptr(),
+              g2.data_ptr() if C2 else None, None)
+    gref = F.conv2d(dy.float().permute(0, 3, 1, 2), Wm.flip(2, 3), stride=2).permute(0, 2, 3, 1)      # adjoint of the above
+    torch.cuda.synchronize()
+    got = torch.cat([g1, g2], 3) if C2 else g1
+    e_g = float((got.float() - gref).abs().max()) / float(gref.abs().max())
+    return max(e_f, e_g), "%-26s fwd %.3g  dgrad %.3g" % (name, e_f, e_g)
+
+
 C1_CASES = [
     # name, B, H, W, pooled
     ("c1_pool_64", 2, 64, 64, 1),
@@ -456,6 +508,14 @@ def perf():
 if __name__ == "__main__":
     if sys.argv[1:] == ["perf"]:
         perf()
+        sys.exit(0)
+    if sys.argv[1:] == ["dc2"]:
+        for c in DC2_CASES:
+            try:
+                print(run_dc2_case(*c)[1], flush=True)
+            except Exception as e:
+                print("dc2 %-24s EXC %s" % (c[0], e), flush=True)
+                break
         sys.exit(0)
     if sys.argv[1:] == ["c1"]:
         for c in C1_CASES:
