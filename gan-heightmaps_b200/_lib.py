@@ -43,6 +43,7 @@ _PROTOS = {
     "hm_up2conv_wgrad_phases": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
     "hm_im2col_c1": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_s2d_pad64": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "hm_im2col_thin": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_c1s2_conv": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "hm_c1s2_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
     "hm_maxpool2_bwd_scaled": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P], C.c_int),

@@ -356,6 +356,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
       int r = k / 6 - (dd >> 1), q = k % 6 - (dd & 1);
       if (r >= 0 && r < 5 && q >= 0 && q < 5) val = w[((size_t)co * 5 + (4 - r)) * 5 + (4 - q)];
     }
+  } else if (mode == 19) {
+    // thin-source convolution as a 1x1 convolution over hm_im2col_thin's tensor:
+    // Wt[co][(r*kw+s)*cin + ci] = W[co][ci][kh-1-r][kw-1-s] for (r*kw+s)*cin + ci < kh*kw*cin, 0 up to 64  (K-major)
+    int k = (int)(i % 64);
+    int co = (int)(i / 64);
+    val = 0.f;
+    if (k < kh * kw * cin) {
+      int tap = k / cin, ci = k - tap * cin;
+      int r = tap / kw, q = tap % kw;
+      val = w[(((size_t)co * cin + ci) * kh + (kh - 1 - r)) * kw + (kw - 1 - q)];
+    }
   } else if (mode == 17) {
     // Deconv2DLayer W (cin,cout,2,2), stride 2, all four output phases at once (hm_tc_conv, transposed == 2):
     // Wt[(u*2+v)*cout + co][ci] = W[ci][co][1-u][1-v]   (K-major, K = ci)
@@ -516,7 +527,7 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 18),
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 19),
                "hm_pack_conv_weight: bad mode %d", mode);
   HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
   HM_CHECK_ARG((mode != 15 && mode != 16) || (cin == 1 && kh == 5 && kw == 5),
@@ -524,6 +535,7 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   HM_CHECK_ARG(mode != 16 || cout == 64, "hm_pack_conv_weight: mode 16 needs Cout == 64");
   HM_CHECK_ARG((mode != 17 && mode != 18) || (kh == 2 && kw == 2), "hm_pack_conv_weight: modes 17/18 are defined for 2x2 filters");
   HM_CHECK_ARG(mode != 18 || 4 * cout <= 64, "hm_pack_conv_weight: mode 18 needs 4*Cout <= 64");
+  HM_CHECK_ARG(mode != 19 || kh * kw * cin <= 64, "hm_pack_conv_weight: mode 19 needs kh*kw*Cin <= 64");
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
@@ -535,6 +547,7 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   if (mode == 15 || mode == 16) n = 256LL * cout;
   if (mode == 17) n = 4LL * cout * cin;
   if (mode == 18) n = 64LL * cin;
+  if (mode == 19) n = 64LL * cout;
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)

@@ -355,6 +355,48 @@ __global__ void __launch_bounds__(256) im2col_c1_kernel(const __half* __restrict
   }
 }
 
+// General thin-source im2col (1..4 source channels, possibly split over two tensors = a ConcatLayer, stride 1 or 2):
+// xc[B,Ho,Wo,64], xc[p][(r*kw+s)*C + c] = src[p*stride + (r,s) - pad][c], zero beyond kh*kw*C and outside the image.
+// One thread = one output pixel x 8 columns (16-byte store); a thread always serves the same 8 columns.
+__global__ void __launch_bounds__(256) im2col_thin_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
+                                                          __half* __restrict__ xc, int B, int H, int W, int C1, int C2,
+                                                          int kh, int kw, int stride, int pad, int Ho, int Wo) {
+  const int g = threadIdx.x & 7;
+  const int Ct = C1 + C2;
+  int dr[8], ds[8], dc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = g * 8 + j;
+    const int tap = k / Ct;
+    dc[j] = k - tap * Ct;
+    dr[j] = k < kh * kw * Ct ? tap / kw - pad : (1 << 20);     // out-of-range marker: never inside the image
+    ds[j] = k < kh * kw * Ct ? tap % kw - pad : 0;
+  }
+  const unsigned total = (unsigned)B * Ho * Wo;
+  const unsigned step = (gridDim.x * blockDim.x) >> 3;
+  unsigned pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  for (; pix < total; pix += step) {
+    const unsigned ox = pix % Wo;
+    const unsigned t2 = pix / Wo;
+    const unsigned oy = t2 % Ho;
+    const unsigned b = t2 / Ho;
+    const size_t img = (size_t)b * H * W;
+    uint4 out;
+    __half* o = reinterpret_cast<__half*>(&out);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int iy = (int)oy * stride + dr[j], ix = (int)ox * stride + ds[j];
+      __half v = __float2half(0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const size_t q = img + (size_t)iy * W + ix;
+        v = dc[j] < C1 ? x1[q * C1 + dc[j]] : x2[q * C2 + (dc[j] - C1)];
+      }
+      o[j] = v;
+    }
+    *reinterpret_cast<uint4*>(xc + (size_t)pix * 64 + g * 8) = out;
+  }
+}
+
 // space-to-depth of a thin gradient, zero-padded to 64 channels: out[q][ph*Co+co] = dy[2q + (ph>>1, ph&1)][co]
 __global__ void s2d_pad64_kernel(const __half* __restrict__ dy, __half* __restrict__ out, int B, int h, int w, int Co) {
   const long long total = (long long)B * h * w * 8;
@@ -489,6 +531,22 @@ extern "C" int hm_im2col_c1(const void* x, void* xc, int B, int H, int W, int kh
   hm::im2col_c1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)xc, B, H, W, kh,
                                                                           kw, pad);
   HM_CHECK_LAUNCH("hm_im2col_c1");
+  return HM_OK;
+}
+
+extern "C" int hm_im2col_thin(const void* x1, const void* x2, void* xc, int B, int H, int W, int C1, int C2, int kh,
+                              int kw, int stride, int pad, int Ho, int Wo, void* stream) {
+  HM_CHECK_ARG(x1 && xc && B > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0 &&
+                   Ho > 0 && Wo > 0, "hm_im2col_thin: bad argument");
+  HM_CHECK_ARG(kh * kw * (C1 + C2) <= 64, "hm_im2col_thin: kh*kw*(C1+C2) = %d exceeds 64 columns", kh * kw * (C1 + C2));
+  HM_CHECK_ARG(C2 == 0 || x2, "hm_im2col_thin: C2 > 0 but x2 is null");
+  HM_CHECK_ARG((((uintptr_t)xc) & 15) == 0, "hm_im2col_thin: output must be 16-byte aligned");
+  const long long total = (long long)B * Ho * Wo * 8;
+  long long blocks = (total + 255) / 256, cap = (long long)hm::num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  hm::im2col_thin_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)x1, (const __half*)x2, (__half*)xc,
+                                                                            B, H, W, C1, C2, kh, kw, stride, pad, Ho, Wo);
+  HM_CHECK_LAUNCH("hm_im2col_thin");
   return HM_OK;
 }
 

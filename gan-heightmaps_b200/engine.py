@@ -176,6 +176,13 @@ class ConvOp(object):
                      and self.kh == self.kw and self.Cout % 64 == 0 and self.Cout <= 256)
         if self.col1:
             self.tc_fwd = True
+        # other thin-source convolutions (<= 4 input channels, e.g. the PatchGAN's 4-channel concat and the U-Net's first
+        # layer, 3x3 stride 2): hm_im2col_thin to 64 "tap-channels", then 1x1 tensor-core GEMMs (forward, weight gradient)
+        self.colk = (rt.precision == "fast" and kind == "conv" and not self.col1 and self.Cin <= 4 and not self.up
+                     and self.stride in (1, 2) and self.kh * self.kw * self.Cin <= 64 and self.Cout % 64 == 0
+                     and self.Cout <= 256)
+        if self.colk:
+            self.tc_fwd = True
         # Deconv2DLayer 2x2 stride 2 (no overlap) as ONE tensor-core launch: 1x1 convolution with N = (phase, co) and a
         # depth-to-space epilogue; its gradients through hm_s2d_pad64 (dy regrouped to (phase, co) channels)
         self.dc2 = False
@@ -188,6 +195,7 @@ class ConvOp(object):
         # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
         self.pool_fused = None
         self.db_done = False
+        self.bias_grad_zero = False
         self.wk = None
         self.c1dg = (rt.precision == "fast" and kind == "conv" and self.up == _lib.UP_NEAREST2 and self.x2 is None
                      and self.Cout == 1 and self.Cin == 64 and self.kh == 5 and self.kw == 5 and self.pad == 2
@@ -221,8 +229,8 @@ class ConvOp(object):
             self.ubuf = rt.empty((B, self.Hv // 2, self.Wv // 2, 64))      # patch-space input gradient
             return          # no im2col tensor, no packed-gradient buffers: forward and backward are hm_c1s2_* calls
         n = self.K * self.Cout
-        if self.col1:
-            self.xc = rt.empty((B, self.Hv, self.Wv, 64))
+        if self.col1 or self.colk:
+            self.xc = rt.empty((B, self.out.shape[0], self.out.shape[1], 64))
             if self.wt_f is None:
                 self.wt_f = rt.empty((64 * self.Cout,))
                 self.dwp = rt.empty((64 * self.Cout,), torch.float32)
@@ -257,6 +265,9 @@ class ConvOp(object):
                 return
             if self.col1:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 11, self.Cout, 1, self.kh, self.kw, 0, 0, rt.cd)
+            elif self.colk:
+                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 19, self.Cout, self.Cin, self.kh, self.kw, 0, 0,
+                        rt.cd)
             elif not self.tc_fwd:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
@@ -348,9 +359,10 @@ class ConvOp(object):
         return d
 
     def _col1_desc(self, rt, n):
-        """The 1x1 convolution over the im2col tensor (64 tap-channels) that stands for a one-channel-input conv."""
+        """The 1x1 convolution over the im2col tensor (64 tap-channels) that stands for a thin-source conv."""
         d = self._fwd_desc(rt, n)
-        d.C1, d.C2, d.kh, d.kw, d.pad, d.up = 64, 0, 1, 1, 0, 0
+        d.H, d.W = self.out.shape[0], self.out.shape[1]
+        d.C1, d.C2, d.kh, d.kw, d.pad, d.up, d.stride = 64, 0, 1, 1, 0, 0, 1
         return d
 
     def _tc_dgrad_desc(self, rt, n, acc):
@@ -412,8 +424,12 @@ class ConvOp(object):
             pool = self.pool_fused
             rt.call("hm_c1s2_conv", x1, _ptr(self.wk), bias, _ptr(pool.out.b(lo, hi)), _ptr(pool.idx[lo:hi]), n,
                     self.Hv, self.Wv, 256, ACT[self.act.name], self.act.slope)
-        elif self.col1:
-            rt.call("hm_im2col_c1", x1, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.kh, self.kw, self.pad)
+        elif self.col1 or self.colk:
+            if self.col1:
+                rt.call("hm_im2col_c1", x1, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.kh, self.kw, self.pad)
+            else:
+                rt.call("hm_im2col_thin", x1, x2, _ptr(self.xc[lo:hi]), n, self.Hv, self.Wv, self.C1, self.C2, self.kh,
+                        self.kw, self.stride, self.pad, self.out.shape[0], self.out.shape[1])
             d = self._col1_desc(rt, n)
             rt.call("hm_tc_conv", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(self.wt_f), bias, y, None)
         elif self.up2:
@@ -495,10 +511,10 @@ class ConvOp(object):
                         rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
                                 _ptr(self.dwp[(u * self.kw + v) * per:]))
                 mode = 2
-            elif self.col1:
+            elif self.col1 or self.colk:
                 d = self._col1_desc(rt, n)
                 rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
-                mode = 0              # rows [0, kh*kw) of the [64][Cout] result are the packed gradient
+                mode = 0              # rows [0, kh*kw*Cin) of the [64][Cout] result are the packed gradient
             elif self.thin_up2_wg:
                 # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
                 # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)
@@ -528,6 +544,8 @@ class ConvOp(object):
                     self.Cin, self.kh, self.kw)
             if self.db_done:              # the max-pool backward already summed the bias gradient
                 self.db_done = False
+            elif self.bias_grad_zero:
+                self.net.gview(self.bias).zero_()
             else:
                 M = n * self.out.shape[0] * self.out.shape[1]
                 db = self.net.gview(self.bias)
@@ -855,6 +873,12 @@ class Net(object):
                 raise NotImplementedError("BatchNorm of a virtual tensor")
             out = self._new("buf", x.shape, [x])
             self.ops.append(BNActOp(self, layer, x, out, act))
+            if self.rt.precision == "fast" and x.consumers == 1:
+                # batch-statistics BatchNorm removes the per-channel mean: the bias of the convolution that feeds ONLY
+                # this layer has an exactly zero gradient (the reference computes rounding noise there); skip the pass
+                for o in self.ops:
+                    if isinstance(o, ConvOp) and o.out is x:
+                        o.bias_grad_zero = True
             return out
         if isinstance(layer, L.ReshapeLayer):
             if act.name != "linear":

@@ -131,6 +131,12 @@ int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void*
  *    hm_unpack_conv_wgrad(mode 10). */
 int hm_im2col_c1(const void* x, void* xc, int B, int H, int W, int kh, int kw, int pad, void* stream);
 int hm_s2d_pad64(const void* dy, void* out, int B, int h, int w, int Co, void* stream);
+/* hm_im2col_thin: the same for 1..4 source channels (optionally split over two tensors = a ConcatLayer, p2p.py:279-281) and
+ * stride 1 or 2: xc[B,Ho,Wo,64], xc[p][(r*kw+s)*C + c] = src[p*stride + (r,s) - pad][c], 0 beyond kh*kw*C <= 64.  The
+ * PatchGAN's and the U-Net's first convolutions (p2p.py:145,285; 3x3 stride 2, 4 and 1 input channels) are then 1x1
+ * tensor-core GEMMs over xc (pack / unpack mode 19). */
+int hm_im2col_thin(const void* x1, const void* x2, void* xc, int B, int H, int W, int C1, int C2, int kh, int kw,
+                   int stride, int pad, int Ho, int Wo, void* stream);
 
 /* Weight gradient of (Upscale2DLayer(2) -> 5x5 'same' Conv2DLayer) with <= 4 output channels (the generator's last
  * layer, dcgan.py:31-32) as four 3x3 problems on the low-res source; `d` is the layer's forward descriptor
@@ -172,7 +178,7 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  *  mode 6: Conv2DLayer W, tcgen05 input-gradient pack     -> Wt[(r*kw+s)][ci][co] = W[co][ci][r][s]
  *          (the input gradient of a stride-1 'same' convolution is the forward correlation of dy with this
  *           pack and pad' = k-1-pad)
- *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, modes 14/15/16: hm_c1s2_* operands, modes 17/18: Deconv2DLayer 2x2 stride 2 on the tensor cores (all phases; its input gradient over hm_s2d_pad64), mode 12: input
+ *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, modes 14/15/16: hm_c1s2_* operands, mode 19: thin-source convolution over hm_im2col_thin's tensor, modes 17/18: Deconv2DLayer 2x2 stride 2 on the tensor cores (all phases; its input gradient over hm_s2d_pad64), mode 12: input
  *          gradient of a 3x3 stride-2 convolution as a 2x2-tap phase convolution of dy (see csrc/simt_conv.cu)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)

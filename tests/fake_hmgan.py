@@ -206,6 +206,10 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     r, s_ = uu - (dd >> 1), vv - (dd & 1)
                     if 0 <= r < 5 and 0 <= s_ < 5:
                         out[dd, uu * 6 + vv, :] = Wc[:, r, s_]
+    elif mode == 19:
+        Wc = W.reshape(cout, cin, kh, kw)[:, :, ::-1, ::-1]                        # correlation taps Wc[co][ci][r][s]
+        out = np.zeros((cout, 64), np.float32)
+        out[:, :kh * kw * cin] = Wc.transpose(0, 2, 3, 1).reshape(cout, kh * kw * cin)      # [co][(r,s,ci)]
     elif mode == 17:
         Wd = W.reshape(cin, cout, 2, 2)[:, :, ::-1, ::-1]                          # Wd[ci][co][u][v] = W[ci][co][1-u][1-v]
         out = Wd.transpose(2, 3, 1, 0).reshape(4 * cout, cin)                      # [(u,v,co)][ci]
@@ -654,6 +658,21 @@ def hm_im2col_c1(x, xc, B, H, W, kh, kw, pad, stream=None):
     out = torch.zeros(B, H, W, 64)
     out[..., :kh * kw] = cols.reshape(B, kh * kw, H, W).permute(0, 2, 3, 1)
     _a(xc, B * H * W * 64, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+    return 0
+
+
+def hm_im2col_thin(x1, x2, xc, B, H, W, C1, C2, kh, kw, stride, pad, Ho, Wo, stream=None):
+    a = _t(_a(x1, B * H * W * C1, np.float16)).reshape(B, H, W, C1)
+    if C2:
+        a = torch.cat([a, _t(_a(x2, B * H * W * C2, np.float16)).reshape(B, H, W, C2)], 3)
+    Ct = C1 + C2
+    cols = F.unfold(a.permute(0, 3, 1, 2), (kh, kw), padding=pad, stride=stride)        # [B, Ct*kh*kw, L], (c, r, s) order
+    L = cols.shape[2]
+    assert L == Ho * Wo, (L, Ho, Wo)
+    cols = cols.reshape(B, Ct, kh * kw, L).permute(0, 3, 2, 1).reshape(B, Ho, Wo, kh * kw * Ct)   # (tap, c) order
+    out = torch.zeros(B, Ho, Wo, 64)
+    out[..., :kh * kw * Ct] = cols
+    _a(xc, B * Ho * Wo * 64, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
     return 0
 
 
