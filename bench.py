@@ -237,8 +237,7 @@ def main():
     ms_e2e = timed(lambda: m.train_fn(Zp, Xp, Yp), a.steps)
     e2e = B * world * a.steps / (ms_e2e * 1e-3)
     if rank != 0:
-        dist.barrier()
-        dist.destroy_process_group()
+        _finish(world)
         return
     pk = peaks()
     kname, kflop, kms, kpath = time_dominant_kernel(m)
@@ -267,9 +266,17 @@ def main():
                                "sample": "%d images of the same workload, 1 warm-up + 1 timed full step "
                                          "(%.1f s/step)" % (a.cpu_sample, dt)}
     print(json.dumps(out))
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank runs leave without tearing the NCCL communicator down: destroy_process_group() was observed to hang
+    here (the captured CUDA graphs hold collectives of that communicator), and a rank that lingers would stall the
+    launcher.  Everything this process had to say is flushed first."""
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
