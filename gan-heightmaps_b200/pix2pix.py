@@ -213,22 +213,29 @@ class Pix2Pix(object):
         self.rt.launches += st["launches"]
         return self.losses
 
-    def _step_eager(self, Zd, Xd, Yd, train=True):
+    def _step_eager(self, Zd, Xd, Yd, train=True, part=0):
+        """part 0: the whole step.  part 1: only what depends on Z alone (G's forward pass); part 2: everything else.
+        The host path captures the two parts as separate CUDA graphs so that the X/Y upload overlaps part 1."""
         rt = self.rt
         B = int(Xd.shape[0])
         S = self.in_shp
         ls = rt.loss_scale
-        self.losses.zero_()
+        if part in (0, 1):
+            self.losses.zero_()
+            if self.have_dcgan:
+                self.G.ensure(B)
+                self.D.ensure(2 * B, input_grads=(0,))
+                rt.call("hm_cast", _ptr(Zd), _lib.F32, _ptr(self.G.inputs[0].buf), rt.cd, Zd.numel())
+                self.G.forward(B)                                           # G(z)            :92
+            if part == 1:
+                return self.losses
         upd = []
         if self.have_dcgan:
             G, D = self.G, self.D
             do = train and self.train_mode in ('both', 'dcgan')
-            G.ensure(B)
-            D.ensure(2 * B, input_grads=(0,))
             ca = 1 if self.is_a_grayscale else 3
-            rt.call("hm_cast", _ptr(Zd), _lib.F32, _ptr(G.inputs[0].buf), rt.cd, Zd.numel())
             self._load_nchw(Xd, D.inputs[0].buf, B, ca, S, S)
-            gz = G.forward(B)                                               # G(z)            :92
+            gz = G.out.buf[:B]
             self._copy(gz, D.inputs[0].buf[B:2 * B])
             h = D.forward(2 * B)                                            # D(x), D(G(z))   :94-95
             dh = D.out.grad if do else None
@@ -306,7 +313,58 @@ class Pix2Pix(object):
                 net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
         return self.losses
 
+    def _host_tensor(self, a):
+        if isinstance(a, torch.Tensor):
+            return a if a.dtype == torch.float32 else a.float()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+    def _step_host_overlapped(self, Z, X, Y, train):
+        """train_fn / loss_fn from HOST inputs with the step captured as TWO graphs: part 1 (G's forward pass, needs only
+        Z) starts at once while X (and Y) are still being uploaded on a side stream; part 2 waits for them.  Returns None
+        until the graphs exist (two eager calls size every buffer first)."""
+        Zs, Xs = self._host_tensor(Z), self._host_tensor(X)
+        Ys = self._host_tensor(Y) if self.have_p2p else None
+        key = ("host", tuple(Zs.shape), tuple(Xs.shape), tuple(Ys.shape) if Ys is not None else None, bool(train))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = {"calls": 0, "gA": None}
+        dev = self.rt.device
+        if st["gA"] is None:
+            st["calls"] += 1
+            if st["calls"] <= 2:
+                return None
+            st["Z"], st["X"] = Zs.to(dev), Xs.to(dev)
+            st["Y"] = Ys.to(dev) if Ys is not None else None
+            self._sync_lr()
+            torch.cuda.synchronize(dev)
+            l0 = self.rt.launches
+            gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gA):
+                self._step_eager(st["Z"], st["X"], st["Y"], train, part=1)
+            with torch.cuda.graph(gB, pool=gA.pool()):
+                self._step_eager(st["Z"], st["X"], st["Y"], train, part=2)
+            st["launches"] = self.rt.launches - l0
+            st["gA"], st["gB"] = gA, gB
+            st["side"], st["ev"] = torch.cuda.Stream(dev), torch.cuda.Event()
+        self._sync_lr()
+        main = torch.cuda.current_stream(dev)
+        st["Z"].copy_(Zs, non_blocking=True)
+        st["gA"].replay()
+        with torch.cuda.stream(st["side"]):        # the previous step ended with a host synchronisation: X/Y are free
+            st["X"].copy_(Xs, non_blocking=True)
+            if Ys is not None:
+                st["Y"].copy_(Ys, non_blocking=True)
+            st["ev"].record(st["side"])
+        main.wait_event(st["ev"])
+        st["gB"].replay()
+        self.rt.launches += st["launches"]
+        return self.losses
+
     def _step_host(self, Z, X, Y, train):
+        if self._graphs_ok and os.environ.get("HMGAN_OVERLAP_H2D", "1") != "0":
+            out = self._step_host_overlapped(Z, X, Y, train)
+            if out is not None:
+                return [np.float32(v) for v in out.cpu().numpy()]
         Zd = self._to_dev("Z", Z)
         Xd = self._to_dev("X", X)
         Yd = self._to_dev("Y", Y) if self.have_p2p else None      # a DCGAN-only model never reads the texture batch
