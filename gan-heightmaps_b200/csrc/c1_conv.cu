@@ -516,29 +516,29 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           if (i < n_words) pb[i] = pre[j];
         }
       }
+      // g' = g * act'(p) * isc in half2 arithmetic: the factor is one of two constants selected by the sign of p
+      const __half2 zero2 = __float2half2_rn(0.f);
+      const uint32_t f_pos = __half_as_ushort(__float2half_rn(isc)) * 0x00010001u;
+      const uint32_t f_neg = __half_as_ushort(__float2half_rn(neg * isc)) * 0x00010001u;
 #pragma unroll
       for (int c = 0; c < 8; c++) {
         const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
-        uint32_t hv[4];                     // g * act'(p), 8 halves
+        uint32_t hv[4];                     // 8 halves
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gw[j]));
-          const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pw4[j]));
-          const float a0 = p.act == HM_ACT_RELU ? (pf.x > 0.f ? 1.f : 0.f) : (pf.x >= 0.f ? 1.f : neg);
-          const float a1 = p.act == HM_ACT_RELU ? (pf.y > 0.f ? 1.f : 0.f) : (pf.y >= 0.f ? 1.f : neg);
-          __half2 h = __floats2half2_rn(gf.x * a0 * isc, gf.y * a1 * isc);
-          hv[j] = *reinterpret_cast<uint32_t*>(&h);
+          const __half2 p2 = *reinterpret_cast<const __half2*>(&pw4[j]);
+          const uint32_t pm = p.act == HM_ACT_RELU ? __hgt2_mask(p2, zero2) : __hge2_mask(p2, zero2);   // 0xffff per lane
+          const uint32_t fb = (f_pos & pm) | (f_neg & ~pm);
+          const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&fb));
+          hv[j] = *reinterpret_cast<const uint32_t*>(&h);
         }
+        // per window position d: keep the channels whose argmax byte equals d (byte compare, bytes spread to halves)
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-          uint32_t m[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const uint32_t kk = j < 2 ? kv[c].x : kv[c].y;
-            const uint32_t k0 = (kk >> (16 * (j & 1))) & 0xff, k1 = (kk >> (16 * (j & 1) + 8)) & 0xff;
-            m[j] = hv[j] & ((k0 == (uint32_t)d ? 0x0000ffffu : 0u) | (k1 == (uint32_t)d ? 0xffff0000u : 0u));
-          }
-          *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(tb, c)) = make_uint4(m[0], m[1], m[2], m[3]);
+          const uint32_t e0 = __vcmpeq4(kv[c].x, 0x01010101u * (uint32_t)d), e1 = __vcmpeq4(kv[c].y, 0x01010101u * (uint32_t)d);
+          const uint32_t m0 = hv[0] & __byte_perm(e0, 0, 0x1100), m1 = hv[1] & __byte_perm(e0, 0, 0x3322);
+          const uint32_t m2 = hv[2] & __byte_perm(e1, 0, 0x1100), m3 = hv[3] & __byte_perm(e1, 0, 0x3322);
+          *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(tb, c)) = make_uint4(m0, m1, m2, m3);
         }
       }
       if (p.want_dw) {

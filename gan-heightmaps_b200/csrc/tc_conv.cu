@@ -39,7 +39,6 @@ struct TcParams {
   int ntile, n_ntiles;     // N tile (<=256, multiple of 16)
   int S, n_super;          // S consecutive M tiles share every B (weight) stage: S*ntile*2 <= 512 TMEM columns
   int stages;
-  int rb_mode;                      // experiment: how the unaligned descriptor start is encoded
   int a_slots, b_slots, rb_bytes;   // row-box variant: A ring (one box per filter row), B ring (one slot per tap)
   int act;
   float slope;
@@ -501,14 +500,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// K-major SW128 descriptor whose start is any 128-byte line of a swizzled buffer (not a 1024-byte atom boundary).
-// Measured on B200 (tools/tc_probe.py *_rb cases): the 128B swizzle is a function of the absolute shared-memory
-// address, so the plain descriptor with base_offset = 0 reads lines written by TMA correctly from any line start;
-// setting base_offset = (addr >> 7) & 7 (mode 1) gives wrong results.  mode stays selectable for that experiment.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128_line(uint32_t saddr, int mode) {
-  if (mode == 0) return umma_desc_k_sw128(saddr);
-  return umma_desc_k_sw128(saddr) | ((uint64_t)((saddr >> 7) & 7) << 49);
-}
+// NOTE (measured on B200, tools/tc_probe.py *_rb cases): the 128B swizzle is a function of the absolute shared-memory
+// address, so a K-major SW128 descriptor may start at ANY 128-byte line of a TMA-written buffer (not only at a
+// 1024-byte atom boundary) with base_offset = 0; encoding (addr >> 7) & 7 as base_offset gives wrong results.  The
+// row-box kernels rely on this: tap s of a filter row reads the row's box from start + 128*s bytes.
 
 // MMA-issuer role of the row-box kernel with the tap loop fully unrolled (KW taps per filter row, NS sub-tiles) for a
 // weight ring whose length is a multiple of KW: the ring slot of tap s is (ring row)*KW + s, so every barrier address and
@@ -1200,7 +1195,6 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       q.S = S2;
       q.n_super = (q.n_mtiles + 2 * S2 - 1) / (2 * S2);
       q.rb_bytes = (((TILE_M + q.kw - 1) * 128) + 1023) / 1024 * 1024;
-      q.rb_mode = 0;
       q.a_slots = (S2 * q.rb_bytes > 40 * 1024) ? 2 : 3;
       const int b_slot = (q.ntile / 2) * 128;
       int b_slots = (227 * 1024 - 10240 - q.a_slots * S2 * q.rb_bytes) / b_slot;
@@ -1237,10 +1231,6 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   }
   if (rb_enabled && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
     p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;
-    {
-      const char* e = getenv("HMGAN_RB_MODE");
-      p.rb_mode = e ? atoi(e) : 0;
-    }
     p.a_slots = (S * p.rb_bytes > 40 * 1024) ? 2 : 3;
     {
       const char* e = getenv("HMGAN_RB_ASLOTS");            // diagnostic override

@@ -246,3 +246,47 @@ def test_fast_mode_stride2_layers_route_to_tensor_cores(cpu_backend, monkeypatch
     # runs, which moves single terms of a weight gradient (max-norm comparisons would see those)
     for a, b in ((g[0], W1.grad.numpy()), (g[2], W2.grad.numpy())):
         assert np.linalg.norm((a - b).ravel()) <= 2e-2 * np.linalg.norm(b.ravel())
+
+
+def test_fast_mode_unet_ends_route_to_tensor_cores(cpu_backend):
+    """The pix2pix ends in fast mode: a thin-source 3x3 stride-2 convolution over a ConcatLayer of a 1- and a 3-channel
+    image (PatchGAN layer 1, reference architectures/p2p.py:279-285) runs as hm_im2col_thin + 1x1 tensor-core GEMMs, and
+    a Deconv2DLayer 2x2 stride 2 -> 3 channels with tanh over a ConcatLayer (U-Net output layer, p2p.py:272-275) as ONE
+    hm_tc_conv launch (pack mode 17) with gradients over hm_s2d_pad64.  Forward and every gradient against the float32
+    oracle ops (fp16 storage: 2e-2 in relative L2 norm)."""
+    import lasagne_compat as LC
+    import engine
+    from oracle import lasagne_ops as LO
+    r = np.random.RandomState(3)
+    ia, ib = LC.InputLayer((None, 1, 16, 16)), LC.InputLayer((None, 3, 16, 16))
+    c1 = LC.Conv2DLayer(LC.ConcatLayer([ia, ib]), 64, 3, stride=2, pad='same', nonlinearity=LC.linear)      # 4 -> 64 @8x8
+    c2 = LC.Conv2DLayer(LC.NonlinearityLayer(c1, LC.leaky_rectify), 64, 3, stride=1, pad='same', nonlinearity=LC.linear)
+    cat = LC.NonlinearityLayer(LC.ConcatLayer([c2, c1]), LC.leaky_rectify)                                   # 128 ch
+    out = LC.NonlinearityLayer(LC.TransposedConv2DLayer(cat, 3, 2, stride=2, nonlinearity=LC.linear), LC.tanh)
+    rt = engine.Runtime("cpu", "fast", loss_scale=1.0)
+    net = engine.Net(rt, out, input_layers=[ia, ib], name="ends", rng=r)
+    convs = [op for op in net.ops if isinstance(op, engine.ConvOp)]
+    assert convs[0].colk and convs[0].x2 is not None and convs[-1].dc2 and convs[-1].x2 is not None
+    A, Bm = r.randn(2, 1, 16, 16).astype(np.float32), r.randn(2, 3, 16, 16).astype(np.float32)
+    net.ensure(2, input_grads=(1,))
+    net.inputs[0].buf.copy_(torch.from_numpy(A.transpose(0, 2, 3, 1)).half())
+    net.inputs[1].buf.copy_(torch.from_numpy(Bm.transpose(0, 2, 3, 1)).half())
+    y = net.forward(2)
+    W1, b1, W2, b2, W3, b3 = [torch.tensor(v, requires_grad=True) for v in net.get_all_param_values()]
+    ta, tb = torch.tensor(A), torch.tensor(Bm, requires_grad=True)
+    h1 = LO.conv2d(torch.cat([ta, tb], 1), W1, b1, 2, "same")
+    h2 = LO.conv2d(LO.leaky_rectify(h1, 0.01), W2, b2, 1, "same")
+    ref = torch.tanh(LO.deconv2d(LO.leaky_rectify(torch.cat([h2, h1], 1), 0.01), W3, b3, 2))
+    np.testing.assert_allclose(y.float().numpy(), ref.detach().permute(0, 2, 3, 1).numpy(), rtol=2e-2, atol=2e-2)
+    gy = r.randn(*ref.shape).astype(np.float32)
+    ref.backward(torch.tensor(gy))
+    net.out.grad.copy_(torch.from_numpy(gy.transpose(0, 2, 3, 1)).half())
+    net.backward(0, 2, wgrad=True, input_grad=True)
+
+    def rel(a, b):
+        return np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30)
+    g = net.get_grads()
+    for a, b in zip(g, (W1.grad, b1.grad, W2.grad, b2.grad, W3.grad, b3.grad)):
+        assert rel(a, b.numpy()) <= 2e-2, (a.shape, rel(a, b.numpy()))
+    gb = net.inputs[1].grad[:2].float().numpy()
+    assert rel(gb, tb.grad.permute(0, 2, 3, 1).numpy()) <= 2e-2
