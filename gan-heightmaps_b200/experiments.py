@@ -3,11 +3,11 @@
     python experiments.py <experiment_name> <mode>        mode in {train, interp, gen}
 
 The closures and their keyword sets are those of the reference; `theano.shared`
-and the Lasagne names it star-imports come from lasagne_compat.  The HDF5 + Keras
-augmentation data path (reference util.py:20-62, experiments.py:10-18) is outside
-this round's scope: `get_iterators` needs h5py and yields
-un-augmented batches; set HMGAN_SYNTHETIC=<N> to train on N seeded synthetic
-512x512 pairs instead (what bench.py and the tests use).
+and the Lasagne names it star-imports come from lasagne_compat.  `get_iterators`
+(reference experiments.py:10-18) opens the HDF5 file with h5py when it is installed and
+wraps its xt/yt/xv/yv datasets in util.Hdf5Iterator (flips as augmentation; Keras'
+arbitrary-angle rotation is not reimplemented); set HMGAN_SYNTHETIC=<N> to train on N
+seeded synthetic 512x512 pairs instead (what bench.py and the tests use).
 """
 import os
 import sys
@@ -17,27 +17,7 @@ import numpy as np
 from pix2pix import Pix2Pix
 from lasagne_compat import *          # noqa: F401,F403  (linear, tanh, rmsprop, adam, floatX, shared ...)
 from lasagne_compat import floatX, shared, linear, tanh, rmsprop
-from util import SyntheticIterator
-
-
-class _H5Iterator(object):
-    """Minimal stand-in for the reference's Hdf5Iterator (util.py:45-62): uint8 NHWC on disk ->
-    float32 NCHW, A scaled to [0,1], B to [-1,1] (util.py:31-36).  No augmentation."""
-
-    def __init__(self, X, Y, bs):
-        self.X, self.Y, self.bs, self.N, self.i = X, Y, bs, X.shape[0], 0
-
-    def next(self):
-        n = self.N // self.bs
-        j = self.i % max(n, 1)
-        self.i += 1
-        x = np.asarray(self.X[j * self.bs:(j + 1) * self.bs]).astype(np.float32)
-        y = np.asarray(self.Y[j * self.bs:(j + 1) * self.bs]).astype(np.float32)
-        if x.ndim == 3:
-            x = x[..., None]
-        x = x.swapaxes(3, 2).swapaxes(2, 1) / 255.0
-        y = (y.swapaxes(3, 2).swapaxes(2, 1) - 127.5) / 127.5
-        return np.ascontiguousarray(x), np.ascontiguousarray(y)
+from util import SyntheticIterator, Hdf5Iterator, FlipAugmenter
 
 
 def get_iterators(dataset, batch_size, is_a_grayscale, is_b_grayscale, da=True):
@@ -50,7 +30,12 @@ def get_iterators(dataset, batch_size, is_a_grayscale, is_b_grayscale, da=True):
         raise RuntimeError("h5py is not installed: cannot open %s.  Set HMGAN_SYNTHETIC=<N> to run on N synthetic "
                            "pairs (the HDF5 data path is out of this round's scope)." % dataset)
     f = h5py.File(dataset, "r")
-    return _H5Iterator(f['xt'], f['yt'], batch_size), _H5Iterator(f['xv'], f['yv'], batch_size)
+    imgen = FlipAugmenter(horizontal_flip=True, vertical_flip=True) if da else None     # (rotation_range is not reimplemented)
+    it_train = Hdf5Iterator(f['xt'], f['yt'], batch_size, imgen, is_a_grayscale=is_a_grayscale,
+                            is_b_grayscale=is_b_grayscale)
+    it_val = Hdf5Iterator(f['xv'], f['yv'], batch_size, imgen, is_a_grayscale=is_a_grayscale,
+                          is_b_grayscale=is_b_grayscale)
+    return it_train, it_val
 
 
 def _model(gen_params_p2p, train_mode='both'):

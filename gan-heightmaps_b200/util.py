@@ -1,12 +1,88 @@
-"""Host-side image helpers used by the trainer's dump/sampling methods
-(reference util.py:69-116) and a synthetic stand-in for Hdf5Iterator
-(reference util.py:45-62): objects with ``.N`` and ``.next()`` returning
-``(X, Y)`` float32 NCHW batches.  The HDF5 data path itself is out of scope for
-this round."""
+"""Host-side data and image helpers with the reference's surface (reference util.py):
+``Hdf5Iterator`` / ``iterate_hdf5`` (util.py:10-62: uint8 NHWC arrays -> shuffled float32 NCHW batches, A scaled to
+[0,1] or [-1,1], paired augmentation through a shared seed), the dump/sampling helpers (util.py:69-116), and a
+synthetic iterator with the same ``.N`` / ``.next()`` surface for benchmarks and tests.  Keras' ImageDataGenerator is
+not a dependency: any object with Keras' ``flow(x, None, batch_size=, seed=)`` protocol works as ``imgen``;
+``FlipAugmenter`` provides the flips (arbitrary-angle rotation with reflect fill is not reimplemented)."""
 import struct
 import zlib
 
 import numpy as np
+
+
+def _get_slices(length, bs):
+    """Consecutive batch slices covering [0, length); the last one may be short (reference util.py:10-18)."""
+    return [slice(b * bs, (b + 1) * bs) for b in range((length + bs - 1) // bs)]
+
+
+def iterate_hdf5(imgen=None, is_a_grayscale=True, is_b_grayscale=False, is_uint8=True):
+    """Generator factory of the reference (util.py:20-42).  X_arr / y_arr are array-likes indexed by slices (numpy
+    arrays or h5py datasets) in NHWC layout; every pass over the data visits the batch slices in an order shuffled by
+    `rnd_state` (None: in order); uint8 data are normalised (grayscale: /255, otherwise (x-127.5)/127.5); with an
+    `imgen`, X and Y are augmented identically through a shared seed."""
+    def _iterate_hdf5(X_arr, y_arr, bs, rnd_state=np.random.RandomState(0)):
+        assert X_arr.shape[0] == y_arr.shape[0]
+        while True:
+            slices = _get_slices(X_arr.shape[0], bs)
+            if rnd_state is not None:
+                rnd_state.shuffle(slices)
+            for elem in slices:
+                this_X = np.asarray(X_arr[elem]).astype("float32")
+                this_Y = np.asarray(y_arr[elem]).astype("float32")
+                if this_X.ndim == 3:
+                    this_X = this_X[..., None]
+                if this_Y.ndim == 3:
+                    this_Y = this_Y[..., None]
+                this_X = np.ascontiguousarray(this_X.transpose(0, 3, 1, 2))          # NHWC -> NCHW
+                this_Y = np.ascontiguousarray(this_Y.transpose(0, 3, 1, 2))
+                if is_uint8:
+                    this_X = (this_X / 255.0) if is_a_grayscale else (this_X - 127.5) / 127.5
+                    this_Y = (this_Y / 255.0) if is_b_grayscale else (this_Y - 127.5) / 127.5
+                if imgen is not None:
+                    seed = rnd_state.randint(0, 100000) if rnd_state is not None else 0
+                    this_X = next(imgen.flow(this_X, None, batch_size=bs, seed=seed))
+                    this_Y = next(imgen.flow(this_Y, None, batch_size=bs, seed=seed))
+                yield this_X.astype("float32"), this_Y.astype("float32")
+    return _iterate_hdf5
+
+
+class Hdf5Iterator(object):
+    """The reference's iterator object (util.py:45-62): ``.N`` = number of examples, ``.next()`` -> (X, Y)."""
+
+    def __init__(self, X, y, bs, imgen, is_a_grayscale, is_b_grayscale, is_uint8=True):
+        assert X.shape[0] == y.shape[0]
+        # a private RandomState(0) per iterator: the reference's default argument is one object shared by every
+        # iterator of the process, which couples the train and validation shuffles to call order
+        self.fn = iterate_hdf5(imgen, is_a_grayscale, is_b_grayscale, is_uint8)(X, y, bs, np.random.RandomState(0))
+        self.N = X.shape[0]
+
+    def __iter__(self):
+        return self
+
+    def next(self):
+        return next(self.fn)
+
+    __next__ = next
+
+
+class FlipAugmenter(object):
+    """Keras-free stand-in for ImageDataGenerator(horizontal_flip=, vertical_flip=) (reference experiments.py:13):
+    ``flow(x, None, batch_size=, seed=)`` yields x with every sample flipped or not by a RandomState(seed), so X and Y
+    passed with the same seed get the same flips."""
+
+    def __init__(self, horizontal_flip=True, vertical_flip=True):
+        self.h, self.v = horizontal_flip, vertical_flip
+
+    def flow(self, x, y=None, batch_size=32, seed=None):
+        r = np.random.RandomState(seed)
+        while True:
+            out = np.array(x, copy=True)
+            for i in range(out.shape[0]):
+                if self.h and r.rand() < 0.5:
+                    out[i] = out[i][:, :, ::-1]
+                if self.v and r.rand() < 0.5:
+                    out[i] = out[i][:, ::-1, :]
+            yield out
 
 
 def convert_to_rgb(img, is_grayscale=False):

@@ -1,0 +1,72 @@
+"""The data iterator of the reference (util.py:10-62) restated in gan-heightmaps_b200/util.py: slicing, per-pass
+shuffling with RandomState(0), uint8 NHWC -> float32 NCHW normalisation, paired augmentation through a shared seed."""
+import os
+import sys
+
+import numpy as np
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gan-heightmaps_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+import util   # noqa: E402
+
+
+def _data(n=10, s=8):
+    r = np.random.RandomState(1)
+    return r.randint(0, 256, (n, s, s, 1)).astype(np.uint8), r.randint(0, 256, (n, s, s, 3)).astype(np.uint8)
+
+
+def test_slices_cover_everything_with_a_short_tail():
+    sl = util._get_slices(10, 4)
+    assert [(s.start, s.stop) for s in sl] == [(0, 4), (4, 8), (8, 12)]
+    assert util._get_slices(0, 4) == []
+
+
+def test_normalisation_layout_and_shuffle_follow_the_reference():
+    X, Y = _data()
+    it = util.Hdf5Iterator(X, Y, 4, None, is_a_grayscale=True, is_b_grayscale=False)
+    assert it.N == 10
+    # the visiting order of one pass: the reference shuffles the slice list with RandomState(0)
+    order = util._get_slices(10, 4)
+    np.random.RandomState(0).shuffle(order)
+    seen = []
+    for sl in order:
+        x, y = it.next()
+        assert x.dtype == np.float32 and y.dtype == np.float32
+        assert x.shape == (len(range(*sl.indices(10))), 1, 8, 8) and y.shape[1:] == (3, 8, 8)
+        np.testing.assert_allclose(x, X[sl].transpose(0, 3, 1, 2).astype(np.float32) / 255.0, rtol=0, atol=1e-7)
+        np.testing.assert_allclose(y, (Y[sl].transpose(0, 3, 1, 2).astype(np.float32) - 127.5) / 127.5, rtol=0, atol=1e-6)
+        assert 0.0 <= x.min() and x.max() <= 1.0 and -1.0 <= y.min() and y.max() <= 1.0
+        seen.append(sl.start)
+    assert sorted(seen) == [0, 4, 8]
+    x, _ = it.next()                       # the next pass starts with a fresh shuffle of the same generator
+    assert x.shape[0] in (2, 4)
+
+
+def test_grayscale_b_and_float_inputs():
+    X, Y = _data()
+    it = util.Hdf5Iterator(X, Y[..., :1], 5, None, is_a_grayscale=False, is_b_grayscale=True)
+    x, y = it.next()
+    assert -1.0 <= x.min() and x.max() <= 1.0 and 0.0 <= y.min() and y.max() <= 1.0
+    itf = util.Hdf5Iterator(X.astype(np.float32), Y.astype(np.float32), 5, None, True, False, is_uint8=False)
+    x, y = itf.next()
+    assert x.max() > 1.5                    # untouched
+
+
+def test_paired_augmentation_uses_one_seed_for_both_images():
+    X, Y = _data(8, 6)
+    Y3 = np.repeat(X, 3, axis=3)           # Y is a copy of X: after augmentation they must still coincide
+    it = util.Hdf5Iterator(X, Y3, 4, util.FlipAugmenter(True, True), is_a_grayscale=True, is_b_grayscale=True)
+    flipped = False
+    for _ in range(6):
+        x, y = it.next()
+        np.testing.assert_allclose(np.repeat(x, 3, axis=1), y, atol=1e-7)
+        flipped = True
+    assert flipped
+
+
+def test_synthetic_iterator_surface():
+    it = util.SyntheticIterator(8, 2, 16, seed=3)
+    x, y = it.next()
+    assert it.N == 8 and x.shape == (2, 1, 16, 16) and y.shape == (2, 3, 16, 16)
+    assert x.dtype == np.float32 and 0 <= x.min() and x.max() <= 1 and -1 <= y.min() and y.max() <= 1
