@@ -54,7 +54,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(const __grid_constant_
           // mode bit2: every group reads a different A tile (6 tiles) and B tile (2 tiles): streaming operands
           const uint32_t ao = (mode & 4) ? (uint32_t)(g % 5) * 16384u : 0u;
           const uint32_t bo = (mode & 4) ? (uint32_t)(g & 1) * 32768u : 0u;
-          tc_mma_f16(d, desc_k_sw128(a_addr + ao) + 2 * k, desc_k_sw128(b_addr + bo) + 2 * k, idesc, 1);
+          if (mode & 16)        // MN-major operands (the weight-gradient kernels): K = 16 rows of 128 B, +2048 B per step
+            tc_mma_f16(d, desc_mn_sw128(a_addr + ao + k * 2048, 16384), desc_mn_sw128(b_addr + bo + k * 2048, 16384),
+                       idesc_f16(N, 1, 1), 1);
+          else
+            tc_mma_f16(d, desc_k_sw128(a_addr + ao) + 2 * k, desc_k_sw128(b_addr + bo) + 2 * k, idesc, 1);
         }
         if (((uint32_t)g & cmask) == cmask) tc_commit(smem_u32(&cbar[(g >> 2) & 7]));
       }
@@ -108,10 +112,10 @@ int main() {
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   const int iters = 40000;
   for (int grid : {148})
-    for (int mode : {4, 12})
-      for (int fill : {1})
-      for (int ce : {2})
-        for (int N : {64, 128, 256}) {
+    for (int mode : {12, 28})
+      for (int fill : {0, 1})
+      for (int ce : {0})
+        for (int N : {64, 128}) {
           mma_rate_kernel<<<grid, 128, 216 * 1024>>>(tm, N, iters, mode, fill, ce, d);
           cudaError_t e = cudaGetLastError();
           if (e == cudaSuccess) e = cudaDeviceSynchronize();
