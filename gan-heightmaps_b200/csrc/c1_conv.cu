@@ -613,9 +613,14 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         tmem_ld_wait();
         float* dst = p.dwk + (size_t)(h * 128 + row) * 64;
 #pragma unroll
-        for (int j = 0; j < 32; j++) atomicAdd(dst + j, __uint_as_float(v[j]));
-#pragma unroll
-        for (int j = 0; j < 5; j++) atomicAdd(dst + 32 + j, __uint_as_float(v2[j]));
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                       : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32), "f"(__uint_as_float(v2[0])),
+                     "f"(__uint_as_float(v2[1])), "f"(__uint_as_float(v2[2])), "f"(__uint_as_float(v2[3]))
+                     : "memory");
+        atomicAdd(dst + 36, __uint_as_float(v2[4]));
       }
     }
   }

@@ -79,6 +79,13 @@ __device__ __forceinline__ bool wg_elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// 16-byte vector reduction into global memory (sm_90+): one L2 transaction for four consecutive floats.  The epilogue
+// of these kernels is nothing but fp32 reductions (64K per CTA); scalar atomicAdd made it ~20 % of the kernel.
+__device__ __forceinline__ void wg_red4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
 __device__ __forceinline__ void wg_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4) wg_red4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
       }
@@ -454,7 +461,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4) wg_red4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
       }
@@ -568,7 +575,7 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
   if (z > p.n_ptiles) z = p.n_ptiles;
   p.zsplit = z;
   const int b_bytes = (p.Cout / 64) * BLK_BYTES, a_bytes = 2 * BLK_BYTES;
-  p.b_slots = 2;
+  p.b_slots = (3 * b_bytes + 4 * a_bytes <= 227 * 1024 - 4096) ? 3 : 2;
   int a_slots = (227 * 1024 - 4096 - p.b_slots * b_bytes) / a_bytes;
   if (a_slots > 6) a_slots = 6;
   if (a_slots < 2) {
@@ -610,8 +617,17 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
     }
     q.max_boxes = max_boxes;
     const size_t a_rb = (size_t)max_boxes * q.rb_bytes;
-    q.w.b_slots = 2;
-    int a_sl = (int)((227 * 1024 - 4096 - (size_t)q.w.b_slots * b_bytes) / a_rb);
+    // ring depths: a dy tile (b) and the x boxes (a) of one pixel tile are consumed together, so both rings want >= 3
+    // slots to cover the TMA latency (one pixel tile is only ~2000 MMA cycles); fall back to 2 where memory is short
+    const size_t budget = 227 * 1024 - 4096;
+    static int wg_bslots = -1;
+    if (wg_bslots < 0) {
+      const char* e = getenv("HMGAN_WG_BSLOTS");
+      wg_bslots = (e && atoi(e) >= 2) ? atoi(e) : 3;
+    }
+    q.w.b_slots = wg_bslots;
+    while (q.w.b_slots > 2 && (size_t)q.w.b_slots * b_bytes + 3 * a_rb > budget) q.w.b_slots--;
+    int a_sl = (int)((budget - (size_t)q.w.b_slots * b_bytes) / a_rb);
     if (a_sl > 3) a_sl = 3;
     if (a_sl >= 2) {
       q.w.a_slots = a_sl;
