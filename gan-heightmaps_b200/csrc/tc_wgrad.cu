@@ -570,7 +570,12 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
   p.n_mtiles = (p.units + 1) / 2;
   p.acc = 512 / p.Cout;
   p.n_mgroups = (p.n_mtiles + p.acc - 1) / p.acc;
-  int z = (2 * num_sms()) / p.n_mgroups;          // ~2 waves of work items
+  static int waves = -1;                          // tuning knob: work items per SM (split-K depth)
+  if (waves < 0) {
+    const char* e = getenv("HMGAN_WG_WAVES");
+    waves = (e && atoi(e) >= 1) ? atoi(e) : 1;    // measured: 1 wave beats 2..4 on every layer (fewer partial sums to reduce)
+  }
+  int z = (waves * num_sms()) / p.n_mgroups;      // ~`waves` waves of work items
   if (z < 1) z = 1;
   if (z > p.n_ptiles) z = p.n_ptiles;
   p.zsplit = z;
