@@ -50,7 +50,17 @@ class Runtime(object):
             loss_scale = 1.0 if precision == "parity" else 1024.0
         self.loss_scale = float(loss_scale)
         self.launches = 0
+        # SyncBN: a torch.distributed process group over which every BatchNorm layer averages its batch
+        # statistics (forward) and its two backward reductions, so that N ranks with B samples each compute exactly the
+        # BatchNorm of one rank with N*B samples.  None (default) = per-rank statistics, the DDP convention.
+        self.sync_bn_group = None
         _lib.load()
+
+    def allreduce_mean(self, t):
+        """Average a small device tensor over the SyncBN group (sum, then 1/world: gloo has no AVG)."""
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.sync_bn_group)
+        t.div_(dist.get_world_size(self.sync_bn_group))
 
     @property
     def stream(self):
@@ -645,6 +655,8 @@ class BNActOp(object):
         else:
             self.sums.zero_()
             rt.call("hm_bn_stats", _ptr(self.x.b(lo, hi)), rt.cd, M, self.Cn, _ptr(self.sums))
+            if rt.sync_bn_group is not None:       # mean over ranks of [sum x, sum x^2]: equal shards, so sums / M is global
+                rt.allreduce_mean(self.sums)
             sums = _ptr(self.sums)
         rt.call("hm_bn_finalize", sums, M, self.Cn, _ptr(net.pview(self.gamma)), _ptr(net.pview(self.beta)),
                 _ptr(rm), _ptr(ri), self.layer.epsilon, self.layer.alpha, 0 if det else 1,
@@ -661,6 +673,10 @@ class BNActOp(object):
         self.red.zero_()
         rt.call("hm_bn_bwd_reduce", _ptr(da), _ptr(a), _ptr(x), rt.cd, M, self.Cn, _ptr(bm), _ptr(bi),
                 ACT[self.act.name], self.act.slope, _ptr(self.red))
+        if rt.sync_bn_group is not None:
+            # [sum g, sum g*xhat] averaged over ranks: dx then uses the global-batch means, and d gamma / d beta come
+            # out as (global sum) / world -- what the later sum all-reduce + 1/world of the gradients expects
+            rt.allreduce_mean(self.red)
         assert self.x.consumers == 1
         self.x.gw = True
         rt.call("hm_bn_bwd_apply", _ptr(da), _ptr(a), _ptr(x), _ptr(self.x.g(lo, hi)), rt.cd, M, self.Cn,

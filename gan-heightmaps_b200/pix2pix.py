@@ -19,7 +19,8 @@ Differences from the reference, all additive:
     applications with shared weights;
   * gen_fn_p2p=None builds a DCGAN-only model (the 64-px gate of BASELINE.json);
   * keyword-only extras: device, precision ('parity' fp32 | 'fast' fp16), seed,
-    process_group (data-parallel gradient all-reduce over NCCL).
+    process_group (data-parallel gradient all-reduce over NCCL), sync_bn (BatchNorm
+    statistics over the whole process group instead of per rank).
 """
 import gzip
 import os
@@ -52,7 +53,7 @@ class Pix2Pix(object):
                  in_shp, latent_dim, is_a_grayscale, is_b_grayscale,
                  alpha=100, opt=adam, opt_args=None,
                  train_mode='both', reconstruction='l1', sampler=np.random.rand, lsgan=False, verbose=True,
-                 device="cuda", precision=None, seed=None, process_group=None, loss_scale=None):
+                 device="cuda", precision=None, seed=None, process_group=None, loss_scale=None, sync_bn=False):
         assert train_mode in ['dcgan', 'p2p', 'both']
         assert reconstruction in ['l1', 'l2']
         if opt_args is None:
@@ -71,6 +72,10 @@ class Pix2Pix(object):
             precision = os.environ.get("HMGAN_PRECISION", "parity")
         self.rt = rt = engine.Runtime(device, precision, loss_scale)
         self.pg = process_group
+        if sync_bn:
+            if process_group is None:
+                raise ValueError("sync_bn=True needs a process_group")
+            rt.sync_bn_group = process_group
         # the reference draws its Glorot weights from the global, unseeded np.random
         rng = np.random.RandomState(seed) if seed is not None else np.random.mtrand._rand
         self.have_dcgan = gen_fn_dcgan is not None

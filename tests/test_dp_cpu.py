@@ -85,3 +85,61 @@ def test_two_rank_step_keeps_replicas_identical_and_averages_gradients(tmp_path)
             np.testing.assert_allclose(r0["D%d" % i], want, rtol=1e-5, atol=1e-7, err_msg="D param %d" % i)
     finally:
         _lib.call, _lib.query, _lib.load = saved
+
+
+def _worker_syncbn(rank, world, port, out_dir):
+    for p in (ROOT, PKG, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_hmgan
+    import _lib
+    _lib.call, _lib.query, _lib.load = fake_hmgan.call, fake_hmgan.query, (lambda: None)
+    from oracle import step as S
+    import test_engine_cpu as T
+    cfg = S.experiment_kwargs('gate64')
+    cfg = dict(cfg, D=dict(cfg['D']), G=dict(cfg['G']))
+    om, m = T.build_pair(cfg, 'dcgan', with_p2p=False)
+    m.pg = dist.group.WORLD
+    m.rt.sync_bn_group = dist.group.WORLD            # what Pix2Pix(..., process_group=pg, sync_bn=True) sets
+    Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=11)
+    sl = slice(2 * rank, 2 * rank + 2)
+    losses = m.train_fn(Z[sl], X[sl], Y[sl])
+    out = {"losses": np.asarray(losses)}
+    out.update({"gG%d" % i: v / world for i, v in enumerate(m.G.get_grads())})       # all-reduced sums -> means
+    out.update({"gD%d" % i: v / world for i, v in enumerate(m.D.get_grads())})
+    out.update({"sG%d" % i: v for i, v in enumerate(m.G.get_all_param_values())})
+    if rank == 0:                                    # the single-process reference on the WHOLE batch
+        lo = om.train_fn(Z, X, Y)
+        out["olosses"] = np.asarray(lo)
+        out.update({"oG%d" % i: v for i, v in enumerate(om.last_grads['G'])})
+        out.update({"oD%d" % i: v for i, v in enumerate(om.last_grads['D'])})
+        out.update({"osG%d" % i: v for i, v in enumerate(om.get_all_param_values('G'))})
+    np.savez(os.path.join(out_dir, "sync%d.npz" % rank), **out)
+    dist.destroy_process_group()
+
+
+def test_sync_batchnorm_makes_two_ranks_equal_one_rank_on_the_whole_batch(tmp_path):
+    """SyncBN: with BatchNorm statistics and backward reductions averaged over the process group, two
+    ranks holding half of a batch each reproduce the single-process step on the whole batch: every gradient of G
+    (which has BatchNorm after every layer) and D, the mean of the per-rank losses, and G's updated parameters
+    including the BatchNorm running statistics (identical on both ranks)."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    mp.spawn(_worker_syncbn, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(str(tmp_path / "sync0.npz"))
+    r1 = np.load(str(tmp_path / "sync1.npz"))
+    np.testing.assert_allclose(0.5 * (r0["losses"][:2] + r1["losses"][:2]), r0["olosses"][:2], rtol=1e-4, atol=1e-6)
+    nG = len([k for k in r0.files if k.startswith("oG")])
+    nD = len([k for k in r0.files if k.startswith("oD")])
+    for net, n in (("G", nG), ("D", nD)):
+        for i in range(n):
+            a, b = r0["g%s%d" % (net, i)], r0["o%s%d" % (net, i)]
+            np.testing.assert_array_equal(a, r1["g%s%d" % (net, i)])
+            scale = float(np.abs(b).max()) + 1e-12
+            assert float(np.abs(a - b).max()) <= 2e-3 * scale + 1e-7, (net, i, float(np.abs(a - b).max()), scale)
+    nS = len([k for k in r0.files if k.startswith("osG")])
+    for i in range(nS):          # parameters after the update, BatchNorm running mean / inv_std included
+        np.testing.assert_array_equal(r0["sG%d" % i], r1["sG%d" % i])
+        np.testing.assert_allclose(r0["sG%d" % i], r0["osG%d" % i], rtol=2e-3, atol=2e-4, err_msg="G value %d" % i)
