@@ -290,3 +290,50 @@ def test_fast_mode_unet_ends_route_to_tensor_cores(cpu_backend):
         assert rel(a, b.numpy()) <= 2e-2, (a.shape, rel(a, b.numpy()))
     gb = net.inputs[1].grad[:2].float().numpy()
     assert rel(gb, tb.grad.permute(0, 2, 3, 1).numpy()) <= 2e-2
+
+
+def test_single_pass_discriminator_backward_equals_two_passes(cpu_backend, monkeypatch):
+    """Host logic of the weighted single backward pass through D (hm_adv_loss_pair; pix2pix.py:107-108 share D(G(z)))
+    against the reference's two separate passes, on the CPU emulation: same losses, and every gradient of D and G
+    equal to fp16-rounding noise (both schedules store the same tensors in fp16; only per-sample scalars move)."""
+    cfg = dict(in_shp=64, latent_dim=32,
+               G=dict(nch=256, num_repeats=0, div=[2, 2, 4, 4]),
+               D=dict(nch=64, num_repeats=0, bn=False, nonlinearity='linear', div=[1, 1, 1, 1]))
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 64, seed=4)
+    res = {}
+    for sp in ("1", "0"):
+        monkeypatch.setenv("HMGAN_SINGLE_PASS_D", sp)
+        _, m = build_pair(cfg, 'dcgan', with_p2p=False, precision="fast")
+        assert m._single_pass == (sp == "1")
+        vals = m.D.get_all_param_values()
+        vals[-1][:] = 0.6                      # D(.) ~ 0.6: neither per-sample factor is negligible
+        m.D.set_all_param_values(vals)
+        res[sp] = (m.train_fn(Z, X, Y), m.D.get_grads(), m.G.get_grads(), [q for q in m.G.params if q.trainable])
+    np.testing.assert_allclose(res["1"][0][:2], res["0"][0][:2], rtol=1e-4, atol=1e-6)
+    for k, idx in (("D", 1), ("G", 2)):
+        for i, (a, b) in enumerate(zip(res["1"][idx], res["0"][idx])):
+            if k == "G" and res["0"][3][i].kind == "b" and i < len(res["0"][idx]) - 1:
+                continue                       # biases in front of a BatchNorm: zero gradient in both
+            rel = float(np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
+            assert rel <= 2e-2, (k, i, a.shape, rel)
+
+
+def test_step_split_into_two_parts_equals_the_whole_step(cpu_backend):
+    """The host path replays the step as two CUDA graphs (part 1 = what needs only Z, part 2 = the rest).  On the CPU
+    the same split, run eagerly, must give bit-identical losses and parameters to the unsplit step."""
+    cfg = S.experiment_kwargs('gate64')
+    Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=6)
+    outs = []
+    for split in (False, True):
+        _, m = build_pair(cfg, 'dcgan', with_p2p=False)
+        Zd, Xd = torch.from_numpy(Z), torch.from_numpy(X)
+        for _ in range(2):
+            if split:
+                m._step_eager(Zd, Xd, None, True, part=1)
+                losses = m._step_eager(Zd, Xd, None, True, part=2)
+            else:
+                losses = m._step_eager(Zd, Xd, None, True)
+        outs.append((losses.clone().numpy(), m.G.get_all_param_values(), m.D.get_all_param_values()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
+        np.testing.assert_array_equal(a, b)
