@@ -52,6 +52,8 @@ _PROTOS = {
     "hm_c1s2_bwd_fold": ([_P, _P, _P, _I, _P], C.c_int),
     "hm_c1s2_col2im": ([_P, _P, _I, _I, _I, _P], C.c_int),
     "hm_pack_conv_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "hm_pack_conv_weight_multi": ([_P, _I, _LL, _I, _P], C.c_int),
+    "hm_pack_conv_weight_count": ([_I, _I, _I, _I, _I], C.c_longlong),
     "hm_unpack_conv_wgrad": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_bn_stats": ([_P, _I, _LL, _I, _P, _P], C.c_int),
     "hm_bn_finalize": ([_P, _LL, _I, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P], C.c_int),
@@ -100,6 +102,27 @@ def load():
 
 def exported_symbols():
     return sorted(list(_PROTOS) + ["hm_tc_conv_supported", "hm_tc_wgrad_supported"])
+
+
+def pack_count(mode, cout, cin, kh, kw):
+    """Elements written by hm_pack_conv_weight(mode, ...): mirrors hm_pack_conv_weight_count (tests/test_abi_cpu.py
+    checks the two against each other)."""
+    if mode == 2:
+        return cin * cout
+    return {8: 36 * cout * cin, 11: 64 * cout, 12: 16 * cout * cin, 14: 64 * cin, 15: 256 * cout, 16: 256 * cout,
+            17: 4 * cout * cin, 18: 64 * cin, 19: 64 * cout}.get(mode, cout * cin * kh * kw)
+
+
+def pack_job_table(jobs):
+    """bytes of an HmPackJob[] (include/hmgan.h) for a list of hm_pack_conv_weight argument tuples
+    (w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype); returns (bytes, max_n)."""
+    import struct
+    out, max_n = b"", 0
+    for (w, wp, mode, cout, cin, kh, kw, u, v, _dt) in jobs:
+        n = pack_count(mode, cout, cin, kh, kw)
+        max_n = max(max_n, n)
+        out += struct.pack("<QQiiiiiiiiq", int(w), int(wp), mode, cout, cin, kh, kw, u, v, 0, n)
+    return out, max_n
 
 
 def call(name, *args):

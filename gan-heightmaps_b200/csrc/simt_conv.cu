@@ -226,10 +226,8 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(HmConvDesc d, const T* _
 
 // ---- weight packing --------------------------------------------------------
 template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int mode, int cout,
-                                   int cin, int kh, int kw, int u, int v, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void pack_elem(const float* __restrict__ w, T* __restrict__ wp, int mode, int cout,
+                                          int cin, int kh, int kw, int u, int v, long long i) {
   float val;
   if (mode == 0) {  // Wp[(r*kw+s)*cin+ci][co] = W[co][ci][kh-1-r][kw-1-s]
     int co = (int)(i % cout);
@@ -390,6 +388,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   stf(wp + i, val);
 }
 
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int mode, int cout,
+                                   int cin, int kh, int kw, int u, int v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pack_elem<T>(w, wp, mode, cout, cin, kh, kw, u, v, i);
+}
+
+// every pack of a network in ONE launch: blockIdx.y selects the job (a table in device memory), blockIdx.x strides over
+// its elements.  A training step re-packs ~35 small weight tensors after the update; as separate launches they cost more
+// in launch gaps than in work.
+template <typename T>
+__global__ void pack_weight_multi_kernel(const HmPackJob* __restrict__ jobs) {
+  const HmPackJob j = jobs[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += (long long)gridDim.x * blockDim.x)
+    pack_elem<T>(j.w, (T*)j.wp, j.mode, j.cout, j.cin, j.kh, j.kw, j.u, j.v, i);
+}
+
 // packed fp32 gradient -> master layout gradient
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int mode,
                                     int cout, int cin, int kh, int kw, long long n) {
@@ -524,6 +539,39 @@ extern "C" int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2
   return HM_OK;
 }
 
+static long long pack_count(int mode, int cout, int cin, int kh, int kw) {
+  long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
+  if (mode == 8) n = 36LL * cout * cin;
+  if (mode == 11) n = 64LL * cout;
+  if (mode == 12) n = 16LL * cout * cin;
+  if (mode == 14) n = 64LL * cin;
+  if (mode == 15 || mode == 16) n = 256LL * cout;
+  if (mode == 17) n = 4LL * cout * cin;
+  if (mode == 18) n = 64LL * cin;
+  if (mode == 19) n = 64LL * cout;
+  return n;
+}
+
+extern "C" long long hm_pack_conv_weight_count(int mode, int cout, int cin, int kh, int kw) {
+  return pack_count(mode, cout, cin, kh, kw);
+}
+
+extern "C" int hm_pack_conv_weight_multi(const HmPackJob* jobs_dev, int n_jobs, long long max_n, int dst_dtype,
+                                         void* stream) {
+  HM_CHECK_ARG(jobs_dev && n_jobs > 0 && n_jobs <= 65535 && max_n > 0, "hm_pack_conv_weight_multi: bad argument");
+  HM_CHECK_ARG(dst_dtype == HM_F32 || dst_dtype == HM_F16, "hm_pack_conv_weight_multi: bad dtype %d", dst_dtype);
+  long long bx = (max_n + 255) / 256;
+  if (bx > 64) bx = 64;                                   // grid-stride inside a job
+  dim3 grid((unsigned)bx, (unsigned)n_jobs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_dtype == HM_F32)
+    pack_weight_multi_kernel<float><<<grid, 256, 0, st>>>(jobs_dev);
+  else
+    pack_weight_multi_kernel<__half><<<grid, 256, 0, st>>>(jobs_dev);
+  HM_CHECK_LAUNCH("hm_pack_conv_weight_multi");
+  return HM_OK;
+}
+
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
@@ -539,15 +587,7 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
   HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
-  long long n = (mode == 2) ? (long long)cin * cout : (long long)cout * cin * kh * kw;
-  if (mode == 8) n = 36LL * cout * cin;
-  if (mode == 11) n = 64LL * cout;
-  if (mode == 12) n = 16LL * cout * cin;
-  if (mode == 14) n = 64LL * cin;
-  if (mode == 15 || mode == 16) n = 256LL * cout;
-  if (mode == 17) n = 4LL * cout * cin;
-  if (mode == 18) n = 64LL * cin;
-  if (mode == 19) n = 64LL * cout;
+  const long long n = pack_count(mode, cout, cin, kh, kw);
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == HM_F32)

@@ -21,6 +21,7 @@ Graph canonicalisation (all exact, elementwise ops commute with concatenation):
     inside the adversarial-loss kernel.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -54,6 +55,8 @@ class Runtime(object):
         # statistics (forward) and its two backward reductions, so that N ranks with B samples each compute exactly the
         # BatchNorm of one rank with N*B samples.  None (default) = per-rank statistics, the DDP convention.
         self.sync_bn_group = None
+        self._pack_jobs = None
+        self._pack_tables = {}
         _lib.load()
 
     def allreduce_mean(self, t):
@@ -69,8 +72,35 @@ class Runtime(object):
         return None
 
     def call(self, name, *args):
+        if self._pack_jobs is not None and name == "hm_pack_conv_weight":
+            self._pack_jobs.append(args)             # deferred: one hm_pack_conv_weight_multi launch per network
+            return
         self.launches += 1
         _lib.call(name, *args, self.stream)
+
+    def begin_pack_batch(self):
+        self._pack_jobs = []
+
+    def end_pack_batch(self):
+        """Issue the deferred weight packs as ONE launch (the job table lives in device memory and is cached: the
+        pointers of a network's packs never change, so CUDA-graph capture sees no allocation or copy)."""
+        jobs, self._pack_jobs = self._pack_jobs, None
+        if not jobs:
+            return
+        # measured on B200: no gain over the ~35 separate launches inside the captured graph (14.6 vs 14.5 ms/step),
+        # so batching is opt-in
+        if len(jobs) < 3 or os.environ.get("HMGAN_BATCH_PACKS", "0") != "1":
+            for a in jobs:
+                self.call("hm_pack_conv_weight", *a)
+            return
+        key = tuple(jobs)
+        ent = self._pack_tables.get(key)
+        if ent is None:
+            raw, max_n = _lib.pack_job_table(jobs)
+            tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+            ent = self._pack_tables[key] = (tab, len(jobs), max_n)
+        tab, n_jobs, max_n = ent
+        self.call("hm_pack_conv_weight_multi", tab.data_ptr(), n_jobs, max_n, jobs[0][9])
 
     def empty(self, shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.tdtype, device=self.device)
@@ -1002,8 +1032,12 @@ class Net(object):
                 v.grad = rt.empty((self.B,) + v.shape)
 
     def pack(self):
-        for op in self.ops:
-            op.pack(self.rt)
+        self.rt.begin_pack_batch()
+        try:
+            for op in self.ops:
+                op.pack(self.rt)
+        finally:
+            self.rt.end_pack_batch()
         self._packed = True
 
     def forward(self, B, lo=0, hi=None, deterministic=False):

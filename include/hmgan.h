@@ -187,6 +187,16 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  * (over)writes the master-layout gradient. */
 int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                         int u, int v, int dst_dtype, void* stream);
+/* All packs of a network in one launch.  jobs_dev: n_jobs HmPackJob records in DEVICE memory (same fields as the
+ * arguments of hm_pack_conv_weight; n = hm_pack_conv_weight_count(mode, ...) elements), max_n = the largest n. */
+typedef struct HmPackJob {
+  const float* w;
+  void* wp;
+  int32_t mode, cout, cin, kh, kw, u, v, pad_;
+  long long n;
+} HmPackJob;
+long long hm_pack_conv_weight_count(int mode, int cout, int cin, int kh, int kw);
+int hm_pack_conv_weight_multi(const HmPackJob* jobs_dev, int n_jobs, long long max_n, int dst_dtype, void* stream);
 int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int cout, int cin, int kh, int kw,
                          void* stream);
 

@@ -228,6 +228,17 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
     return 0
 
 
+def hm_pack_conv_weight_multi(jobs, n_jobs, max_n, dst_dtype, stream=None):
+    """HmPackJob[] in (host) memory: {w, wp, mode, cout, cin, kh, kw, u, v, pad, n}, 56 bytes each."""
+    import struct
+    raw = bytes(_a(jobs, n_jobs * 56, np.uint8))
+    for i in range(n_jobs):
+        w, wp, mode, cout, cin, kh, kw, u, v, _pad, n = struct.unpack_from("<QQiiiiiiiiq", raw, i * 56)
+        assert 0 < n <= max_n
+        hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype)
+    return 0
+
+
 def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
     n = cout * cin * kh * kw
     src = _a(dwp, n, np.float32)

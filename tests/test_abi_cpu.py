@@ -19,7 +19,7 @@ import _lib   # noqa: E402
 def _declared():
     src = open(os.path.join(ROOT, "include", "hmgan.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:int|const char\s*\*)\s+(hm_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|long long|const char\s*\*)\s+(hm_[a-z0-9_]+)\s*\(", src, flags=re.M)))
 
 
 @pytest.fixture(scope="module")
@@ -61,3 +61,14 @@ def test_bad_arguments_are_reported_not_fatal(lib):
     rc = lib.hm_c1s2_conv(None, None, None, None, None, 1, 8, 8, 64, 0, C.c_float(0.0), None)
     assert rc < 0 and b"hm_c1s2_conv" in lib.hm_last_error_string()
     assert lib.hm_tc_conv_supported(None) == 0
+
+
+def test_pack_element_counts_agree_between_python_and_the_library(lib):
+    """_lib.pack_count (used to fill the HmPackJob table of hm_pack_conv_weight_multi) == hm_pack_conv_weight_count."""
+    lib.hm_pack_conv_weight_count.restype = C.c_longlong
+    for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 14, 15, 16, 17, 18, 19):
+        for (cout, cin, kh, kw) in ((64, 1, 5, 5), (128, 64, 5, 5), (3, 128, 2, 2), (64, 4, 3, 3), (1, 64, 5, 5)):
+            assert _lib.pack_count(mode, cout, cin, kh, kw) == lib.hm_pack_conv_weight_count(mode, cout, cin, kh, kw), \
+                (mode, cout, cin, kh, kw)
+    raw, max_n = _lib.pack_job_table([(0x1000, 0x2000, 5, 128, 64, 5, 5, 0, 0, 1), (0x3000, 0x4000, 15, 64, 1, 5, 5, 0, 0, 1)])
+    assert len(raw) == 2 * 56 and max_n == 128 * 64 * 25

@@ -337,3 +337,20 @@ def test_step_split_into_two_parts_equals_the_whole_step(cpu_backend):
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_batched_weight_packs_equal_separate_packs(cpu_backend, monkeypatch):
+    """HMGAN_BATCH_PACKS=1 defers a network's weight packs into one hm_pack_conv_weight_multi launch (job table in
+    device memory): same step result as the separate launches."""
+    cfg = S.experiment_kwargs('gate64')
+    Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=8)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("HMGAN_BATCH_PACKS", flag)
+        _, m = build_pair(cfg, 'dcgan', with_p2p=False)
+        losses = [m.train_fn(Z, X, Y) for _ in range(2)]
+        outs.append((np.asarray(losses), m.D.get_all_param_values()))
+        assert bool(m.rt._pack_tables) == (flag == "1")
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        np.testing.assert_array_equal(a, b)
