@@ -262,7 +262,7 @@ def main():
                          "kernel_ms": kms, "peak_source": pk["src"] + " (burst: kernel timed alone)",
                          "step_achieved": step_tflops, "step_frac_of_sustained": step_tflops / pk["sustained"]},
                losses=[float(v) for v in losses])
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
         v, dt = cpu_baseline(a.workload, a.cpu_sample)
         out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": "%d images of the same workload, 1 warm-up + 1 timed full step "
