@@ -243,10 +243,11 @@ def main():
         return
     pk = peaks()
     kname, kflop, kms, kpath = time_dominant_kernel(m)
-    traffic = None
-    try:       # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+    traffic, ncu_tensor = None, None
+    try:       # DRAM bytes per launch / tensor-pipe activity of that kernel from the committed `ncu --set full` capture
         with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            traffic = json.load(f).get(kname, {}).get("dram_bytes_per_launch")
+            rec = json.load(f).get(kname, {})
+        traffic, ncu_tensor = rec.get("dram_bytes_per_launch"), rec.get("tensor_pipe_active_pct")
     except Exception:
         pass
     k_tflops = kflop / (kms * 1e-3) / 1e12
@@ -260,6 +261,7 @@ def main():
                roofline={"bound": "tensor", "achieved": k_tflops, "peak": pk["burst"], "unit": "TFLOP/s",
                          "frac": k_tflops / pk["burst"], "traffic": traffic, "kernel": kname, "kernel_path": kpath,
                          "kernel_ms": kms, "peak_source": pk["src"] + " (burst: kernel timed alone)",
+                         "ncu_tensor_pipe_active_pct": ncu_tensor,
                          "step_achieved": step_tflops, "step_frac_of_sustained": step_tflops / pk["sustained"]},
                losses=[float(v) for v in losses])
     if not a.no_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
