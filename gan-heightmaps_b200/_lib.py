@@ -69,6 +69,7 @@ _PROTOS = {
     "hm_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_nhwc_to_nchw": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_cast": ([_P, _I, _P, _I, _LL, _P], C.c_int),
+    "hm_u8_normalize": ([_P, _P, _I, _LL, _I, _P], C.c_int),
     "hm_slice_channels": ([_P, _P, _I, _LL, _I, _I, _I, _I, _P], C.c_int),
     "hm_permute": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_adv_loss": ([_P, _P, _I, _LL, _I, _I, _F, _I, _I, _F, _F, _I, _P, _P], C.c_int),

@@ -1196,6 +1196,51 @@ extern "C" int hm_cast(const void* src, int sd, void* dst, int dd, long long n, 
   return HM_OK;
 }
 
+// uint8 NHWC image data (the reference's on-disk layout) -> compute-dtype NHWC with the iterator's normalisation done in
+// float32 as numpy does it (reference util.py:33-35): x/255 for grayscale images, (x-127.5)/127.5 otherwise.  IEEE
+// subtraction and division, so the fp32 result equals the host iterator's bit for bit.
+__device__ __forceinline__ float u8_norm(unsigned v, int tanh_range) {
+  float f = (float)v;
+  return tanh_range ? __fdiv_rn(__fsub_rn(f, 127.5f), 127.5f) : __fdiv_rn(f, 255.0f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) u8_norm_v16_kernel(const uint4* __restrict__ s, T* __restrict__ d, long long n16,
+                                                          int tanh_range) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(s + i);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) f[k] = u8_norm((w[k >> 2] >> (8 * (k & 3))) & 0xffu, tanh_range);
+    store8(d + i * 16, f);
+    store8(d + i * 16 + 8, f + 8);
+  }
+}
+
+template <typename T>
+__global__ void u8_norm_kernel(const uint8_t* __restrict__ s, T* __restrict__ d, long long n, int tanh_range) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    stf(d + i, u8_norm(s[i], tanh_range));
+}
+
+extern "C" int hm_u8_normalize(const uint8_t* src, void* dst, int dtype, long long n, int tanh_range, void* stream) {
+  CHECK_DTYPE(dtype, "hm_u8_normalize");
+  HM_CHECK_ARG(src && dst && n > 0, "hm_u8_normalize: bad argument");
+  HM_CHECK_ARG(tanh_range == 0 || tanh_range == 1, "hm_u8_normalize: bad range selector %d", tanh_range);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n % 16 == 0 && al16(src) && al16(dst)) {
+    DISPATCH_T(dtype, (u8_norm_v16_kernel<T><<<ew_grid(n / 16), 256, 0, st>>>((const uint4*)src, (T*)dst, n / 16,
+                                                                            tanh_range)));
+  } else {
+    DISPATCH_T(dtype, (u8_norm_kernel<T><<<ew_grid(n), 256, 0, st>>>(src, (T*)dst, n, tanh_range)));
+  }
+  HM_CHECK_LAUNCH("hm_u8_normalize");
+  return HM_OK;
+}
+
 extern "C" int hm_adv_loss(const void* h, void* dh, int dtype, long long R, int G, int out_act, float target,
                            int lsgan, int relu_head, float weight, float gscale, int accumulate, float* loss,
                            void* stream) {

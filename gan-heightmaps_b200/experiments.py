@@ -5,8 +5,8 @@
 The closures and their keyword sets are those of the reference; `theano.shared`
 and the Lasagne names it star-imports come from lasagne_compat.  `get_iterators`
 (reference experiments.py:10-18) opens the HDF5 file with h5py when it is installed and
-wraps its xt/yt/xv/yv datasets in util.Hdf5Iterator (flips as augmentation; Keras'
-arbitrary-angle rotation is not reimplemented); set HMGAN_SYNTHETIC=<N> to train on N
+wraps its xt/yt/xv/yv datasets in util.Hdf5Iterator (flips and arbitrary-angle rotation with reflect
+fill as augmentation, util.RotateFlipAugmenter; raw uint8 batches normalised on the device); set HMGAN_SYNTHETIC=<N> to train on N
 seeded synthetic 512x512 pairs instead (what bench.py and the tests use).
 """
 import os
@@ -17,7 +17,7 @@ import numpy as np
 from pix2pix import Pix2Pix
 from lasagne_compat import *          # noqa: F401,F403  (linear, tanh, rmsprop, adam, floatX, shared ...)
 from lasagne_compat import floatX, shared, linear, tanh, rmsprop
-from util import SyntheticIterator, Hdf5Iterator, FlipAugmenter
+from util import SyntheticIterator, Hdf5Iterator, FlipAugmenter, RotateFlipAugmenter
 
 
 def get_iterators(dataset, batch_size, is_a_grayscale, is_b_grayscale, da=True):
@@ -30,11 +30,15 @@ def get_iterators(dataset, batch_size, is_a_grayscale, is_b_grayscale, da=True):
         raise RuntimeError("h5py is not installed: cannot open %s.  Set HMGAN_SYNTHETIC=<N> to run on N synthetic "
                            "pairs (the HDF5 data path is out of this round's scope)." % dataset)
     f = h5py.File(dataset, "r")
-    imgen = FlipAugmenter(horizontal_flip=True, vertical_flip=True) if da else None     # (rotation_range is not reimplemented)
+    imgen = None
+    if da:          # reference experiments.py:13 (flips + arbitrary rotation with reflect fill); HMGAN_DA=flip: flips only
+        imgen = (FlipAugmenter(True, True) if os.environ.get("HMGAN_DA", "") == "flip"
+                 else RotateFlipAugmenter(True, True, rotation_range=360, fill_mode="reflect"))
+    raw = os.environ.get("HMGAN_DEVICE_NORMALISE", "1") != "0"     # raw uint8 batches, normalised on the device
     it_train = Hdf5Iterator(f['xt'], f['yt'], batch_size, imgen, is_a_grayscale=is_a_grayscale,
-                            is_b_grayscale=is_b_grayscale)
+                            is_b_grayscale=is_b_grayscale, device_normalise=raw)
     it_val = Hdf5Iterator(f['xv'], f['yv'], batch_size, imgen, is_a_grayscale=is_a_grayscale,
-                          is_b_grayscale=is_b_grayscale)
+                          is_b_grayscale=is_b_grayscale, device_normalise=raw)
     return it_train, it_val
 
 

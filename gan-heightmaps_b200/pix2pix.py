@@ -20,7 +20,11 @@ Differences from the reference, all additive:
   * gen_fn_p2p=None builds a DCGAN-only model (the 64-px gate of BASELINE.json);
   * keyword-only extras: device, precision ('parity' fp32 | 'fast' fp16), seed,
     process_group (data-parallel gradient all-reduce over NCCL), sync_bn (BatchNorm
-    statistics over the whole process group instead of per rank).
+    statistics over the whole process group instead of per rank);
+  * X / Y may also be RAW uint8 NHWC batches, as the HDF5 file stores them
+    (util.Hdf5Iterator(..., device_normalise=True)): the iterator's /255 or
+    (x-127.5)/127.5 (reference util.py:33-35) then runs on the device
+    (hm_u8_normalize) and the upload is a quarter of the float32 bytes.
 """
 import gzip
 import os
@@ -34,7 +38,7 @@ import _lib
 import engine
 import lasagne_compat as L
 from lasagne_compat import adam, floatX, shared
-from util import convert_to_rgb, plot_grid, imsave
+from util import convert_to_rgb, plot_grid, imsave, as_float_nchw
 
 _ptr = engine._ptr
 
@@ -139,21 +143,26 @@ class Pix2Pix(object):
     # host <-> device staging
     # ------------------------------------------------------------------ #
     def _to_dev(self, name, a):
-        """numpy float32 -> device float32 staging buffer (reused across steps)."""
-        if isinstance(a, torch.Tensor):           # e.g. a pinned host tensor: copied as it is
-            src = a if a.dtype == torch.float32 else a.float()
-        else:
-            src = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        """numpy float32 (or raw uint8 image data) -> device staging buffer of the same type (reused across steps)."""
+        src = self._host_tensor(a)
         t = self._stage.get(name)
-        if t is None or t.shape != src.shape:
-            t = self.rt.empty(tuple(src.shape), torch.float32)
+        if t is None or t.shape != src.shape or t.dtype != src.dtype:
+            t = self.rt.empty(tuple(src.shape), src.dtype)
             self._stage[name] = t
         t.copy_(src, non_blocking=True)
         return t
 
-    def _load_nchw(self, src_f32, dst, B, Cn, H, W):
-        """NCHW float32 device tensor -> NHWC compute-dtype buffer dst[:B]."""
-        self.rt.call("hm_nchw_to_nhwc", _ptr(src_f32), _ptr(dst), self.rt.cd, B, Cn, H, W)
+    def _load_nchw(self, src, dst, B, Cn, H, W, gray=True):
+        """Image batch on the device -> NHWC compute-dtype buffer dst[:B].  float32: the reference's NCHW convention.
+        uint8: raw NHWC data as the HDF5 file stores them (reference util.py:28-35), normalised here instead of on the
+        host (`gray`: x/255, otherwise (x-127.5)/127.5)."""
+        if src.dtype == torch.uint8:
+            if src.numel() != B * Cn * H * W:
+                raise ValueError("uint8 image batch of %d elements, expected [%d,%d,%d,%d] NHWC"
+                                 % (src.numel(), B, H, W, Cn))
+            self.rt.call("hm_u8_normalize", _ptr(src), _ptr(dst), self.rt.cd, src.numel(), 0 if gray else 1)
+            return
+        self.rt.call("hm_nchw_to_nhwc", _ptr(src), _ptr(dst), self.rt.cd, B, Cn, H, W)
 
     def _store_nchw(self, src, B, Cn, H, W):
         out = self.rt.empty((B, Cn, H, W), torch.float32)
@@ -192,7 +201,8 @@ class Pix2Pix(object):
         HMGAN_CUDA_GRAPHS=0 to always run eagerly; Adam runs eagerly (its step count is a kernel argument)."""
         if not self._graphs_ok:
             return self._step_eager(Zd, Xd, Yd, train)
-        key = (tuple(Zd.shape), tuple(Xd.shape), tuple(Yd.shape) if Yd is not None else None, bool(train))
+        key = (tuple(Zd.shape), tuple(Xd.shape), Xd.dtype, tuple(Yd.shape) if Yd is not None else None,
+               Yd.dtype if Yd is not None else None, bool(train))
         st = self._graphs.get(key)
         if st is None:
             st = self._graphs[key] = {"calls": 0, "graph": None}
@@ -239,7 +249,7 @@ class Pix2Pix(object):
             G, D = self.G, self.D
             do = train and self.train_mode in ('both', 'dcgan')
             ca = 1 if self.is_a_grayscale else 3
-            self._load_nchw(Xd, D.inputs[0].buf, B, ca, S, S)
+            self._load_nchw(Xd, D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
             gz = G.out.buf[:B]
             self._copy(gz, D.inputs[0].buf[B:2 * B])
             h = D.forward(2 * B)                                            # D(x), D(G(z))   :94-95
@@ -281,11 +291,11 @@ class Pix2Pix(object):
             Dp.ensure(2 * B, input_grads=(1,))
             ca = 1 if self.is_a_grayscale else 3
             cb = 1 if self.is_b_grayscale else 3
-            self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S)
+            self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
             a_in, b_in = Dp.inputs
-            self._load_nchw(Xd, a_in.buf, B, ca, S, S)
+            self._load_nchw(Xd, a_in.buf, B, ca, S, S, self.is_a_grayscale)
             self._copy(a_in.buf[:B], a_in.buf[B:2 * B])
-            self._load_nchw(Yd, b_in.buf, B, cb, S, S)
+            self._load_nchw(Yd, b_in.buf, B, cb, S, S, self.is_b_grayscale)
             px = P.forward(B)                                               # P(X)            :99
             self._copy(px, b_in.buf[B:2 * B])
             h = Dp.forward(2 * B)                                           # Dp(X,Y), Dp(X,P(X)) :98,101
@@ -319,8 +329,12 @@ class Pix2Pix(object):
         return self.losses
 
     def _host_tensor(self, a):
+        """float32 host tensor of a numpy array / tensor; raw uint8 image data stay uint8 (normalised on the device)."""
         if isinstance(a, torch.Tensor):
-            return a if a.dtype == torch.float32 else a.float()
+            return a if a.dtype in (torch.float32, torch.uint8) else a.float()
+        a = np.asarray(a)
+        if a.dtype == np.uint8:
+            return torch.from_numpy(np.ascontiguousarray(a))
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
     def _step_host_overlapped(self, Z, X, Y, train):
@@ -329,7 +343,8 @@ class Pix2Pix(object):
         until the graphs exist (two eager calls size every buffer first)."""
         Zs, Xs = self._host_tensor(Z), self._host_tensor(X)
         Ys = self._host_tensor(Y) if self.have_p2p else None
-        key = ("host", tuple(Zs.shape), tuple(Xs.shape), tuple(Ys.shape) if Ys is not None else None, bool(train))
+        key = ("host", tuple(Zs.shape), tuple(Xs.shape), Xs.dtype, tuple(Ys.shape) if Ys is not None else None,
+               Ys.dtype if Ys is not None else None, bool(train))
         st = self._graphs.get(key)
         if st is None:
             st = self._graphs[key] = {"calls": 0, "gA": None}
@@ -392,10 +407,14 @@ class Pix2Pix(object):
         if not self.have_p2p:
             raise RuntimeError("this model was built without a pix2pix stage")
         Xd = self._to_dev("X", X)
-        B, ca, S, _ = Xd.shape
+        if Xd.dtype == torch.uint8:                # raw NHWC data ([B,S,S] or [B,S,S,C])
+            B, S = int(Xd.shape[0]), int(Xd.shape[1])
+            ca = int(Xd.shape[3]) if Xd.dim() == 4 else 1
+        else:
+            B, ca, S, _ = Xd.shape
         P = self.P
         P.ensure(B)
-        self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S)
+        self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
         out = P.forward(B, deterministic=det)
         H, W, Cn = P.out.shape
         return self._store_nchw(out, B, Cn, H, W).cpu().numpy()
@@ -487,7 +506,8 @@ class Pix2Pix(object):
         ctr = 0
         for n in range(num_batches):
             this_x, this_y = itr.next()
-            pred_y = this_y if dont_predict else fn(this_x)
+            pred_y = as_float_nchw(this_y, self.is_b_grayscale) if dont_predict else fn(this_x)
+            this_x = as_float_nchw(this_x, self.is_a_grayscale)
             for i in range(pred_y.shape[0]):
                 imsave("%s/%i.a.png" % (out_dir, ctr), convert_to_rgb(this_x[i], is_grayscale=self.is_a_grayscale))
                 imsave("%s/%i.b.png" % (out_dir, ctr), convert_to_rgb(pred_y[i], is_grayscale=self.is_b_grayscale))

@@ -15,13 +15,62 @@ def _get_slices(length, bs):
     return [slice(b * bs, (b + 1) * bs) for b in range((length + bs - 1) // bs)]
 
 
-def iterate_hdf5(imgen=None, is_a_grayscale=True, is_b_grayscale=False, is_uint8=True):
+def normalise_uint8(a, is_grayscale):
+    """Raw uint8 NHWC images -> the float32 NCHW batch the reference's iterator yields (util.py:28-35): the host
+    restatement of hm_u8_normalize + layout change, used by the dump helpers and as the parity check of the device path."""
+    a = np.asarray(a)
+    if a.ndim == 3:
+        a = a[..., None]
+    f = np.ascontiguousarray(a.transpose(0, 3, 1, 2)).astype("float32")
+    return ((f / 255.0) if is_grayscale else (f - 127.5) / 127.5).astype("float32")
+
+
+def as_float_nchw(a, is_grayscale):
+    """A batch as the dump helpers need it: float32 NCHW as it is, raw uint8 NHWC normalised on the host."""
+    return normalise_uint8(a, is_grayscale) if np.asarray(a).dtype == np.uint8 else a
+
+
+def iterate_hdf5(imgen=None, is_a_grayscale=True, is_b_grayscale=False, is_uint8=True, device_normalise=False):
     """Generator factory of the reference (util.py:20-42).  X_arr / y_arr are array-likes indexed by slices (numpy
     arrays or h5py datasets) in NHWC layout; every pass over the data visits the batch slices in an order shuffled by
     `rnd_state` (None: in order); uint8 data are normalised (grayscale: /255, otherwise (x-127.5)/127.5); with an
-    `imgen`, X and Y are augmented identically through a shared seed."""
+    `imgen`, X and Y are augmented identically through a shared seed.
+
+    device_normalise=True (uint8 data only; not in the reference) yields the RAW uint8 NHWC batches instead -- same
+    order, same augmentation, applied to the bytes -- for Pix2Pix.train_fn / loss_fn / gen_fn to normalise on the
+    device (hm_u8_normalize): a quarter of the host->device bytes and no float32 pass over the batch on the host."""
+    def _iterate_raw(X_arr, y_arr, bs, rnd_state):
+        while True:
+            slices = _get_slices(X_arr.shape[0], bs)
+            if rnd_state is not None:
+                rnd_state.shuffle(slices)
+            for elem in slices:
+                out = []
+                seed = None
+                for arr in (X_arr, y_arr):
+                    a = np.asarray(arr[elem])
+                    if a.dtype != np.uint8:
+                        raise TypeError("device_normalise needs uint8 data, got %s" % a.dtype)
+                    if a.ndim == 3:
+                        a = a[..., None]
+                    if imgen is not None:
+                        if seed is None:
+                            seed = rnd_state.randint(0, 100000) if rnd_state is not None else 0
+                        a = next(imgen.flow(a.transpose(0, 3, 1, 2), None, batch_size=bs, seed=seed))
+                        a = np.asarray(a).transpose(0, 2, 3, 1)
+                        if a.dtype != np.uint8:      # an interpolating augmenter: back to the byte grid
+                            a = np.clip(np.rint(a), 0, 255).astype(np.uint8)
+                    out.append(np.ascontiguousarray(a))
+                yield out[0], out[1]
+
     def _iterate_hdf5(X_arr, y_arr, bs, rnd_state=np.random.RandomState(0)):
         assert X_arr.shape[0] == y_arr.shape[0]
+        if device_normalise:
+            if not is_uint8:
+                raise ValueError("device_normalise=True is for uint8 data (is_uint8=True)")
+            for batch in _iterate_raw(X_arr, y_arr, bs, rnd_state):      # endless
+                yield batch
+            return
         while True:
             slices = _get_slices(X_arr.shape[0], bs)
             if rnd_state is not None:
@@ -49,11 +98,12 @@ def iterate_hdf5(imgen=None, is_a_grayscale=True, is_b_grayscale=False, is_uint8
 class Hdf5Iterator(object):
     """The reference's iterator object (util.py:45-62): ``.N`` = number of examples, ``.next()`` -> (X, Y)."""
 
-    def __init__(self, X, y, bs, imgen, is_a_grayscale, is_b_grayscale, is_uint8=True):
+    def __init__(self, X, y, bs, imgen, is_a_grayscale, is_b_grayscale, is_uint8=True, device_normalise=False):
         assert X.shape[0] == y.shape[0]
         # a private RandomState(0) per iterator: the reference's default argument is one object shared by every
         # iterator of the process, which couples the train and validation shuffles to call order
-        self.fn = iterate_hdf5(imgen, is_a_grayscale, is_b_grayscale, is_uint8)(X, y, bs, np.random.RandomState(0))
+        self.fn = iterate_hdf5(imgen, is_a_grayscale, is_b_grayscale, is_uint8, device_normalise)(
+            X, y, bs, np.random.RandomState(0))
         self.N = X.shape[0]
 
     def __iter__(self):
@@ -83,6 +133,55 @@ class FlipAugmenter(object):
                 if self.v and r.rand() < 0.5:
                     out[i] = out[i][:, ::-1, :]
             yield out
+
+
+class RotateFlipAugmenter(object):
+    """Keras-free restatement of what the reference builds for training (experiments.py:13):
+    ``ImageDataGenerator(horizontal_flip=True, vertical_flip=True, rotation_range=360, fill_mode="reflect")`` used through
+    ``flow(x, None, batch_size=bs, seed=seed).next()`` on an NCHW batch (util.py:38-40).
+
+    Keras is not vendored in the reference and no version is pinned, so this follows the published Keras 2.0.x
+    algorithm [upstream, recalled]: the generator is seeded with `seed` (a private RandomState here; Keras seeds the
+    global np.random), the batch is a random permutation of the samples (flow's shuffle=True default), and each sample
+    draws theta ~ U(-rotation_range, rotation_range) degrees, is rotated about the image centre (offset H/2+0.5) by
+    scipy.ndimage.affine_transform with order 0 (nearest) and the fill mode, then flipped left-right and up-down with
+    probability 1/2 each.  X and Y batches passed with the same seed get the same permutation, angle and flips, which
+    is all the reference relies on.  Order-0 resampling only moves pixels, so it commutes with the normalisation and
+    works on raw uint8 batches as well."""
+
+    def __init__(self, horizontal_flip=True, vertical_flip=True, rotation_range=360., fill_mode="reflect", cval=0.):
+        self.h, self.v, self.rot, self.fill, self.cval = horizontal_flip, vertical_flip, rotation_range, fill_mode, cval
+
+    def random_transform(self, x, r):
+        """One CHW sample; r: the RandomState all draws come from."""
+        from scipy import ndimage
+        if self.rot:
+            theta = np.pi / 180 * r.uniform(-self.rot, self.rot)
+            if theta != 0:
+                c, s_ = np.cos(theta), np.sin(theta)
+                rot = np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1]])
+                H, W = x.shape[1], x.shape[2]
+                oy, ox = float(H) / 2 + 0.5, float(W) / 2 + 0.5
+                off = np.array([[1, 0, oy], [0, 1, ox], [0, 0, 1]])
+                back = np.array([[1, 0, -oy], [0, 1, -ox], [0, 0, 1]])
+                m = off.dot(rot).dot(back)
+                x = np.stack([ndimage.affine_transform(ch, m[:2, :2], m[:2, 2], order=0, mode=self.fill,
+                                                       cval=self.cval) for ch in x], axis=0)
+        if self.h and r.random_sample() < 0.5:
+            x = x[:, :, ::-1]
+        if self.v and r.random_sample() < 0.5:
+            x = x[:, ::-1, :]
+        return x
+
+    def flow(self, x, y=None, batch_size=32, seed=None):
+        x = np.asarray(x)
+        n = x.shape[0]
+        seen = 0
+        while True:
+            r = np.random.RandomState(None if seed is None else seed + seen)
+            order = r.permutation(n)[:batch_size]
+            yield np.stack([self.random_transform(x[j], r) for j in order], axis=0).astype(x.dtype)
+            seen += 1
 
 
 def convert_to_rgb(img, is_grayscale=False):
@@ -132,7 +231,8 @@ def plot_grid(out_filename, itr, out_fn, is_a_grayscale, is_b_grayscale, N=4):
         row = []
         for c in range(N):
             a, b = itr.next()
-            bp = out_fn(a) if out_fn is not None else b
+            bp = out_fn(a) if out_fn is not None else as_float_nchw(b, is_b_grayscale)
+            a = as_float_nchw(a, is_a_grayscale)
             row.append(compose_imgs(a[0], bp[0], is_a_grayscale=is_a_grayscale, is_b_grayscale=is_b_grayscale))
         rows.append(np.concatenate(row, axis=1))
     imsave(out_filename, np.concatenate(rows, axis=0))

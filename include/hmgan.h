@@ -255,6 +255,10 @@ int hm_upsample2_fwd(const void* x, void* y, int dtype, int B, int H, int W, int
 int hm_nchw_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int H, int W, void* stream);
 int hm_nhwc_to_nchw(const void* src, float* dst, int dtype, int B, int C, int H, int W, void* stream);
 int hm_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, void* stream);
+/* uint8 image data in the reference's on-disk NHWC layout -> dtype NHWC, normalised on the device as the reference's
+ * iterator does on the host in float32 (util.py:33-35): tanh_range 0: x/255 (grayscale images), 1: (x-127.5)/127.5.
+ * n = number of elements (B*H*W*C).  The float32 result is bit-identical to numpy's. */
+int hm_u8_normalize(const uint8_t* src, void* dst, int dtype, long long n, int tanh_range, void* stream);
 /* dst[M][nc] (+)= src[M][C] channels [c0, c0+nc): the part of a ConcatLayer's gradient that belongs to one input
  * (p2p.py:279-281). */
 int hm_slice_channels(const void* src, void* dst, int dtype, long long M, int C, int c0, int nc, int accumulate,

@@ -500,6 +500,13 @@ def hm_cast(src, sd, dst, dd, n, stream=None):
     return 0
 
 
+def hm_u8_normalize(src, dst, dtype, n, tanh_range, stream=None):
+    v = _a(src, n, np.uint8).astype(np.float32)
+    v = (v - np.float32(127.5)) / np.float32(127.5) if tanh_range else v / np.float32(255.0)
+    _a(dst, n, _NP[dtype])[:] = v.astype(_NP[dtype])
+    return 0
+
+
 def hm_adv_loss(h, dh, dtype, R, G, out_act, target, lsgan, relu_head, weight, gscale, accumulate, loss,
                 stream=None):
     hv = _t(_a(h, R * G, _NP[dtype])).reshape(R, G)

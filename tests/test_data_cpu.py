@@ -70,3 +70,56 @@ def test_synthetic_iterator_surface():
     x, y = it.next()
     assert it.N == 8 and x.shape == (2, 1, 16, 16) and y.shape == (2, 3, 16, 16)
     assert x.dtype == np.float32 and 0 <= x.min() and x.max() <= 1 and -1 <= y.min() and y.max() <= 1
+
+
+def test_raw_uint8_iterator_yields_the_bytes_behind_the_float_batches():
+    """device_normalise=True: same visiting order and the same paired augmentation, but raw uint8 NHWC batches whose
+    host normalisation (util.normalise_uint8 = reference util.py:28-35) reproduces the float iterator bit for bit."""
+    X, Y = _data(10, 8)
+    for imgen in (None, util.FlipAugmenter(True, True), util.RotateFlipAugmenter(True, True, 360, "reflect")):
+        itf = util.Hdf5Iterator(X, Y, 4, imgen, is_a_grayscale=True, is_b_grayscale=False)
+        itr = util.Hdf5Iterator(X, Y, 4, imgen, is_a_grayscale=True, is_b_grayscale=False, device_normalise=True)
+        for _ in range(5):
+            xf, yf = itf.next()
+            xr, yr = itr.next()
+            assert xr.dtype == np.uint8 and yr.dtype == np.uint8 and xr.flags.c_contiguous and yr.flags.c_contiguous
+            assert xr.shape == (xf.shape[0], 8, 8, 1) and yr.shape == (yf.shape[0], 8, 8, 3)
+            np.testing.assert_array_equal(util.normalise_uint8(xr, True), xf)
+            np.testing.assert_array_equal(util.normalise_uint8(yr, False), yf)
+            assert util.as_float_nchw(xf, True) is xf
+
+
+def test_raw_iterator_rejects_float_data():
+    X, Y = _data(4, 4)
+    it = util.Hdf5Iterator(X.astype(np.float32), Y, 2, None, True, False, device_normalise=True)
+    try:
+        it.next()
+    except TypeError:
+        return
+    raise AssertionError("float data accepted by the raw uint8 iterator")
+
+
+def test_rotate_flip_augmenter_follows_the_keras_protocol():
+    """Same seed -> same permutation, angle and flips for X and Y; a rotation by a multiple of 90 degrees about the
+    Keras centre (H/2+0.5) with reflect fill is a pure pixel move for the interior; no rotation and no flips is the
+    identity up to the batch permutation."""
+    X, _ = _data(6, 9)
+    x = X.transpose(0, 3, 1, 2)
+    y = np.repeat(x, 3, axis=1)
+    aug = util.RotateFlipAugmenter(True, True, rotation_range=360, fill_mode="reflect")
+    for seed in (0, 7, 123):
+        a = next(aug.flow(x, None, batch_size=6, seed=seed))
+        b = next(aug.flow(y, None, batch_size=6, seed=seed))
+        assert a.shape == x.shape and a.dtype == x.dtype
+        np.testing.assert_array_equal(np.repeat(a, 3, axis=1), b)
+    ident = util.RotateFlipAugmenter(False, False, rotation_range=0)
+    out = next(ident.flow(x, None, batch_size=6, seed=3))
+    perm = np.random.RandomState(3).permutation(6)
+    np.testing.assert_array_equal(out, x[perm])
+    # every output pixel of a rotated sample is one of the sample's own pixel values (order-0 resampling + reflect)
+    rot_only = util.RotateFlipAugmenter(False, False, rotation_range=360, fill_mode="reflect")
+    r = np.random.RandomState(5)
+    s = rot_only.random_transform(x[0], r)
+    assert set(np.unique(s)) <= set(np.unique(x[0]))
+    # batches smaller than batch_size (the last slice of a pass) come back whole
+    assert next(aug.flow(x[:2], None, batch_size=4, seed=1)).shape[0] == 2

@@ -354,3 +354,29 @@ def test_batched_weight_packs_equal_separate_packs(cpu_backend, monkeypatch):
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_raw_uint8_batches_give_the_step_of_the_host_normalised_batches(cpu_backend):
+    """train_fn / gen_fn fed raw uint8 NHWC data (util.Hdf5Iterator(device_normalise=True)) normalise on the device
+    (hm_u8_normalize); losses, updated parameters and P(X) must equal, bit for bit in parity mode, those of the float32
+    NCHW batches the reference's iterator computes on the host (util.py:28-35)."""
+    import util
+    cfg = dict(TINY)
+    r = np.random.RandomState(3)
+    Xu = r.randint(0, 256, (2, 512, 512, 1)).astype(np.uint8)
+    Yu = r.randint(0, 256, (2, 512, 512, 3)).astype(np.uint8)
+    Z = np.random.RandomState(1).rand(2, cfg['latent_dim']).astype(np.float32)
+    outs = []
+    for raw in (False, True):
+        _, m = build_pair(cfg, 'both')
+        X, Y = (Xu, Yu) if raw else (util.normalise_uint8(Xu, True), util.normalise_uint8(Yu, False))
+        losses = [m.train_fn(Z, X, Y) for _ in range(2)]
+        params = [a for net in (m.G, m.D, m.P, m.Dp) for a in net.get_all_param_values()]
+        outs.append((np.array(losses), params, m.gen_fn_det(X[:1]), m.gen_fn(Xu[:1, :, :, 0] if raw else X[:1])))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
+    with pytest.raises(ValueError):
+        m.train_fn(Z, Xu[:, :256], Yu)          # wrong image size
