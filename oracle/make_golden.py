@@ -40,10 +40,33 @@ def gate64(steps=3):
     return out
 
 
+def joint_tiny512(steps=1):
+    """The joint 'both' step (reference experiments.py:98-119 topology: G, D, P with bilinear up-sampling, Dp; alpha=100,
+    L1 + LSGAN, rmsprop) at toy widths on 2 synthetic 512x512 pairs: the five losses, a 16x16-strided sample and the
+    moments of the deterministic P(X), update norms of all four parameter sets."""
+    cfg = S.experiment_kwargs('tiny512')
+    m = S.OracleModel(S.build_nets(cfg, seed=2), alpha=100., opt='rmsprop', lr=1e-3, train_mode='both', lsgan=True)
+    keys = ('G', 'D', 'P', 'Dp')
+    p0 = {k: m.get_all_param_values(k) for k in keys}
+    losses = []
+    for it in range(steps):
+        Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=3 + it)
+        losses.append(m.train_fn(Z, X, Y))
+    _, X, _ = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=3)
+    px = m.gen_fn_det(X[:1])
+    out = dict(losses=np.asarray(losses, np.float32), px_det_sample=px[:, :, ::16, ::16].copy(),
+               px_det_moments=np.asarray([px.astype(np.float64).mean(), px.astype(np.float64).std()], np.float64))
+    for k in keys:
+        p1 = m.get_all_param_values(k)
+        out['upd_norm_' + k] = np.asarray([np.linalg.norm((a - b).ravel()) for a, b in zip(p1, p0[k])], np.float64)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, "gate64.npz"), **gate64())
-    print("wrote", os.path.join(OUT, "gate64.npz"))
+    for name, fn in (("gate64", gate64), ("joint_tiny512", joint_tiny512)):
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **fn())
+        print("wrote", os.path.join(OUT, name + ".npz"))
 
 
 if __name__ == "__main__":

@@ -187,6 +187,15 @@ def experiment_kwargs(name):
             in_shp=64, latent_dim=100,
             G=dict(nch=128, num_repeats=0, div=[2, 2, 4, 4]),
             D=dict(nch=64, num_repeats=0, bn=False, nonlinearity='linear', div=[8, 4, 2, 1]))
+    if name == 'tiny512':
+        # the full test1_nobn_bilin_both topology (all four networks, 512x512, 7+7+17+5 layers) at toy widths: what
+        # the joint-step parity tests and tests/golden/joint_tiny512.npz run
+        return dict(
+            in_shp=512, latent_dim=16,
+            G=dict(nch=64, num_repeats=0, div=[2, 2, 4, 4, 8, 8, 8]),
+            D=dict(nch=512, num_repeats=0, bn=False, nonlinearity='linear', div=[128, 64, 64, 64, 32, 32, 32]),
+            P=dict(nf=4, act='tanh', num_repeats=0, bilinear_upsample=True),
+            Dp=dict(nf=4, bn=False, num_repeats=0, act='linear', mul_factor=[1, 2, 4, 8]))
     raise KeyError(name)
 
 

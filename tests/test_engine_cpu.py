@@ -101,12 +101,7 @@ def test_gate64_dcgan_step_matches_oracle(cpu_backend):
     _check_params(om, m, rtol=2e-3, atol=2e-4)     # BN running statistics moved identically
 
 
-TINY = dict(
-    in_shp=512, latent_dim=16,
-    G=dict(nch=64, num_repeats=0, div=[2, 2, 4, 4, 8, 8, 8]),
-    D=dict(nch=512, num_repeats=0, bn=False, nonlinearity='linear', div=[128, 64, 64, 64, 32, 32, 32]),
-    P=dict(nf=4, act='tanh', num_repeats=0, bilinear_upsample=True),
-    Dp=dict(nf=4, bn=False, num_repeats=0, act='linear', mul_factor=[1, 2, 4, 8]))
+TINY = S.experiment_kwargs('tiny512')
 
 
 @pytest.mark.parametrize("bilinear", [True, False])
