@@ -20,7 +20,13 @@
  *     internal synchronisation, so a whole step can be captured in a CUDA graph;
  *   - return value: 0 on success, a negative HmStatus on error; nothing throws
  *     across the ABI; hm_last_error_string() describes the last error of the
- *     calling thread.
+ *     calling thread;
+ *   - one CUDA device per process (the design is one process per GPU): the SM
+ *     count and the opt-in shared-memory attributes of the kernels are cached
+ *     process-wide on first use, for the device current at that moment.  Calls
+ *     from several host threads on different streams are safe (those caches are
+ *     idempotent, the error string is thread-local); the HMGAN_* environment
+ *     variables the kernels' host wrappers consult are diagnostic knobs.
  */
 #ifndef HMGAN_H_
 #define HMGAN_H_
