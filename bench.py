@@ -33,11 +33,32 @@ GFLOP_PER_IMG = {"dcgan": 391.3, "both": 683.2}        # SURVEY.md §8d (fwd + w
 BATCH = {"dcgan": 32, "both": 16}                       # BASELINE.json configs[1], configs[2]
 
 
+def _peak_value(p, key):
+    """A number stored under `key`, plainly or as {"value": ...}; values quoted in PFLOP/s or TB/s are rescaled."""
+    v = p[key]
+    if isinstance(v, dict):
+        v = v.get("value", v.get("median", v.get("max")))
+    v = float(v)
+    if v <= 0:
+        raise ValueError(key)
+    return v * 1000.0 if v < 20.0 else v
+
+
 def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written; B200_PROFILING.md) or the recipe's stated fallback."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return dict(burst=p["bf16_tflops"], sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"], src="measured")
+        burst = _peak_value(p, "bf16_tflops")
+        try:
+            sustained = _peak_value(p, "bf16_tflops_sustained")
+        except Exception:
+            sustained = burst
+        try:
+            hbm = _peak_value(p, "hbm_gbs")
+        except Exception:
+            hbm = 6650.0
+        return dict(burst=burst, sustained=sustained, hbm=hbm, src="measured")
     except Exception:
         return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
 
