@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box visit that collects everything a round needs, so that box acquisition is paid once:
+#
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r2'
+#
+# stages (each under its own timeout; a failing stage does not stop the next):
+#   1. pytest -m gpu                                    -> gpurun_out/<tag>_pytest_gpu.log
+#   2. smoke()                                          -> gpurun_out/<tag>_smoke.log
+#   3. bench.py, default arguments (N=1)                -> gpurun_out/<tag>_bench.json
+#   4. bench.py --workload both (joint step)            -> gpurun_out/<tag>_bench_joint.json
+#   5. ncu launch list of one bench step                -> gpurun_out/<tag>_launches.csv  (+ per-kernel summary .txt)
+#   6. ncu --set full of the dominant kernels           -> gpurun_out/<tag>_ncu_full.txt  (tools/tc_probe.py perf)
+# Skip stages with SKIP="1 6" (space-separated numbers).  Numbers printed under ncu are never bench values.
+tag=${1:-rX}
+out=gpurun_out
+mkdir -p $out
+skip=" ${SKIP:-} "
+run() { case "$skip" in *" $1 "*) echo "[gpu_round] stage $1 skipped"; return 1;; esac; echo "[gpu_round] stage $1: $2"; return 0; }
+
+run 1 "pytest -m gpu" && { timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; tail -3 $out/${tag}_pytest_gpu.log; }
+run 2 "smoke" && { timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $out/${tag}_smoke.log 2>&1; tail -2 $out/${tag}_smoke.log; }
+run 3 "bench N=1" && { timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.json; }
+run 4 "bench joint" && { timeout 600 python bench.py --workload both --no-cpu-baseline > $out/${tag}_bench_joint.json 2> $out/${tag}_bench_joint.err; tail -c 300 $out/${tag}_bench_joint.json; }
+run 5 "ncu launch list" && {
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_launches.log 2>&1
+  python tools/launch_summary.py $out/${tag}_launches.csv > $out/${tag}_launches_step.txt 2>&1; head -12 $out/${tag}_launches_step.txt; }
+run 6 "ncu --set full (dominant kernels)" && {
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_ -s 2 -c 10 -o $out/${tag}_ncu_full -f \
+      python tools/tc_probe.py perf > $out/${tag}_ncu_full.log 2>&1
+  ncu -i $out/${tag}_ncu_full.ncu-rep --page raw --csv \
+      --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg.per_second \
+      > $out/${tag}_ncu_full.txt 2>&1; head -5 $out/${tag}_ncu_full.txt; }
+echo "[gpu_round] done"

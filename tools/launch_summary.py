@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel family and the
-slowest individual launches.  usage: python tools/launch_summary.py gpurun_out/launches.csv [min_ms]"""
+slowest individual launches (of the last complete training step when the capture holds several).  usage: python tools/launch_summary.py gpurun_out/launches.csv [min_ms]"""
 import collections
 import csv
 import re
@@ -12,11 +12,21 @@ def main(path, min_ms=1.0):
     r = csv.reader(lines)
     hdr = next(r)
     ki, vi, ui, gi = (hdr.index(k) for k in ('Kernel Name', 'Metric Value', 'Metric Unit', 'Grid Size'))
+    rows = [row for row in r if len(row) > vi]
+    # a training step ends with the optimiser launches: keep only the last complete step when there are several
+    marks = [i for i, row in enumerate(rows) if 'rmsprop' in row[ki] or 'adam_kernel' in row[ki]]
+    groups = []
+    for i in marks:
+        if groups and i == groups[-1][1] + 1:
+            groups[-1][1] = i
+        else:
+            groups.append([i, i])
+    if len(groups) >= 2:
+        rows = rows[groups[-2][1] + 1:groups[-1][1] + 1]
+        print('last full training step (%d of %d launches)' % (len(rows), len(marks) and groups[-1][1] + 1))
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot, big = 0.0, []
-    for row in r:
-        if len(row) <= vi:
-            continue
+    for row in rows:
         v = float(row[vi].replace(',', ''))
         v = v / 1e6 if row[ui] in ('nsecond', 'ns') else (v / 1e3 if row[ui] in ('usecond', 'us') else v)
         name = re.sub(r'\(.*', '', row[ki]).replace('void ', '')
