@@ -57,6 +57,8 @@ class Runtime(object):
         self.sync_bn_group = None
         self._pack_jobs = None
         self._pack_tables = {}
+        self._wgrad_stream = None
+        self._wgrad_forked = False
         _lib.load()
 
     def allreduce_mean(self, t):
@@ -70,6 +72,24 @@ class Runtime(object):
         if self.device.type == "cuda":
             return torch.cuda.current_stream(self.device).cuda_stream
         return None
+
+    def wgrad_stream(self):
+        """Side stream for the weight-gradient half of a convolution's backward pass, or None.
+
+        Opt-in (HMGAN_WGRAD_STREAM=1, CUDA only; not yet measured on B200): dW and dX of a layer both need only dY, and
+        the small layers' kernels fill a fraction of the 148 SMs, so issuing dW on a second stream lets it run beside
+        the input-gradient chain of the layers below.  Net.backward joins the stream before it returns, so the fork is
+        invisible to callers and is captured into the step's CUDA graph as ordinary cross-stream dependencies."""
+        if self.device.type != "cuda" or os.environ.get("HMGAN_WGRAD_STREAM", "0") != "1":
+            return None
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(self.device)
+        return self._wgrad_stream
+
+    def join_wgrad_stream(self):
+        if self._wgrad_forked:
+            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
+            self._wgrad_forked = False
 
     def call(self, name, *args):
         if self._pack_jobs is not None and name == "hm_pack_conv_weight":
@@ -535,64 +555,79 @@ class ConvOp(object):
         if wgrad and self.net.wscale is not None:
             g = self.out.grad_w[lo:hi]        # weight and bias gradients see the per-sample-weighted gradient
         if wgrad:
-            self.dwp.zero_()
-            if self.dc2:
-                # dW[ci][(phase,co)] = x^T . s2d(dy): a 1x1 tensor-core weight gradient on the input grid
-                h, w = self.x1.shape[0], self.x1.shape[1]
-                rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, h, w, self.Cout)
-                d = self._dc2_1x1_desc(rt, n, self.C1, self.C2, 64)
-                rt.call("hm_tc_wgrad", C.byref(d), x1, x2, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
-                mode = 17
-            elif self.kind == "deconv":
-                per = self.Cin * self.Cout
-                for u in range(self.kh):
-                    for v in range(self.kw):
-                        d = self._fwd_desc(rt, n, (u, v))
-                        rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
-                                _ptr(self.dwp[(u * self.kw + v) * per:]))
-                mode = 2
-            elif self.col1 or self.colk:
-                d = self._col1_desc(rt, n)
-                rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
-                mode = 0              # rows [0, kh*kw*Cin) of the [64][Cout] result are the packed gradient
-            elif self.thin_up2_wg:
-                # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
-                # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)
-                h, w = self.x1.shape[0], self.x1.shape[1]
-                rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, h, w, self.Cout)
-                d = self._fwd_desc(rt, n)
-                d.up, d.kh, d.kw, d.pad = 0, 3, 3, 1
-                d.Ho, d.Wo, d.oH, d.oW, d.Cout, d.split = h, w, h, w, 64, 64
-                rt.call("hm_tc_wgrad", C.byref(d), x1, None, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
-                mode = 10
-            elif self.tc_wg and (not self.up or self.x1u is not None):
-                if self.up and not getattr(self, "_xu_valid", False):   # forward did not materialise the 2x copy
-                    for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
-                        if x is not None:
-                            rt.call("hm_upsample2_fwd", _ptr(x.b(lo, hi)), _ptr(xu[lo:hi]), rt.cd, n, x.shape[0],
-                                    x.shape[1], c, self.up)
-                    self._xu_valid = True
-                u1, u2 = self._srcs(rt, lo, hi, True)
-                d = self._tc_fwd_desc(rt, n)
-                rt.call("hm_tc_wgrad", C.byref(d), u1, u2, _ptr(g), _ptr(self.dwp))
-                mode = 0
+            side = None if self.dc2 else rt.wgrad_stream()     # (dc2: the input gradient reads the wgrad block's s2d copy)
+            if side is None:
+                self._bwd_wgrad(rt, lo, hi, g, x1, x2)
             else:
-                d = self._fwd_desc(rt, n)
-                rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g), _ptr(self.dwp))
-                mode = 4 if self.kind == "dense" else 0
-            rt.call("hm_unpack_conv_wgrad", _ptr(self.dwp), _ptr(self.net.gview(self.W)), mode, self.Cout,
-                    self.Cin, self.kh, self.kw)
-            if self.db_done:              # the max-pool backward already summed the bias gradient
-                self.db_done = False
-            elif self.bias_grad_zero:
-                self.net.gview(self.bias).zero_()
-            else:
-                M = n * self.out.shape[0] * self.out.shape[1]
-                db = self.net.gview(self.bias)
-                db.zero_()
-                rt.call("hm_col_sum", _ptr(g), rt.cd, M, self.Cout, _ptr(db))
-        # input gradient
-        g = g_plain
+                side.wait_stream(torch.cuda.current_stream(rt.device))      # dY (and its activation backward) is ready
+                with torch.cuda.stream(side):
+                    self._bwd_wgrad(rt, lo, hi, g, x1, x2)
+                rt._wgrad_forked = True
+        self._bwd_dgrad(rt, lo, hi, g_plain, wgrad, input_grad)
+
+    def _bwd_wgrad(self, rt, lo, hi, g, x1, x2):
+        """Weight and bias gradient of the layer from dY = g (reads g, the layer's sources and per-layer scratch only)."""
+        n = hi - lo
+        self.dwp.zero_()
+        if self.dc2:
+            # dW[ci][(phase,co)] = x^T . s2d(dy): a 1x1 tensor-core weight gradient on the input grid
+            h, w = self.x1.shape[0], self.x1.shape[1]
+            rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, h, w, self.Cout)
+            d = self._dc2_1x1_desc(rt, n, self.C1, self.C2, 64)
+            rt.call("hm_tc_wgrad", C.byref(d), x1, x2, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
+            mode = 17
+        elif self.kind == "deconv":
+            per = self.Cin * self.Cout
+            for u in range(self.kh):
+                for v in range(self.kw):
+                    d = self._fwd_desc(rt, n, (u, v))
+                    rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g),
+                            _ptr(self.dwp[(u * self.kw + v) * per:]))
+            mode = 2
+        elif self.col1 or self.colk:
+            d = self._col1_desc(rt, n)
+            rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
+            mode = 0              # rows [0, kh*kw*Cin) of the [64][Cout] result are the packed gradient
+        elif self.thin_up2_wg:
+            # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
+            # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)
+            h, w = self.x1.shape[0], self.x1.shape[1]
+            rt.call("hm_s2d_pad64", _ptr(g), _ptr(self.dy64[lo:hi]), n, h, w, self.Cout)
+            d = self._fwd_desc(rt, n)
+            d.up, d.kh, d.kw, d.pad = 0, 3, 3, 1
+            d.Ho, d.Wo, d.oH, d.oW, d.Cout, d.split = h, w, h, w, 64, 64
+            rt.call("hm_tc_wgrad", C.byref(d), x1, None, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
+            mode = 10
+        elif self.tc_wg and (not self.up or self.x1u is not None):
+            if self.up and not getattr(self, "_xu_valid", False):   # forward did not materialise the 2x copy
+                for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
+                    if x is not None:
+                        rt.call("hm_upsample2_fwd", _ptr(x.b(lo, hi)), _ptr(xu[lo:hi]), rt.cd, n, x.shape[0],
+                                x.shape[1], c, self.up)
+                self._xu_valid = True
+            u1, u2 = self._srcs(rt, lo, hi, True)
+            d = self._tc_fwd_desc(rt, n)
+            rt.call("hm_tc_wgrad", C.byref(d), u1, u2, _ptr(g), _ptr(self.dwp))
+            mode = 0
+        else:
+            d = self._fwd_desc(rt, n)
+            rt.call("hm_conv_wgrad", C.byref(d), x1, x2, _ptr(g), _ptr(self.dwp))
+            mode = 4 if self.kind == "dense" else 0
+        rt.call("hm_unpack_conv_wgrad", _ptr(self.dwp), _ptr(self.net.gview(self.W)), mode, self.Cout,
+                self.Cin, self.kh, self.kw)
+        if self.db_done:              # the max-pool backward already summed the bias gradient
+            self.db_done = False
+        elif self.bias_grad_zero:
+            self.net.gview(self.bias).zero_()
+        else:
+            M = n * self.out.shape[0] * self.out.shape[1]
+            db = self.net.gview(self.bias)
+            db.zero_()
+            rt.call("hm_col_sum", _ptr(g), rt.cd, M, self.Cout, _ptr(db))
+
+    def _bwd_dgrad(self, rt, lo, hi, g, wgrad, input_grad):
+        """Input gradient(s) of the layer from dY = g."""
+        n = hi - lo
         t1 = self.x1.want_grad or (input_grad and self.x1.kind == "input" and self.x1.grad is not None)
         t2 = self.x2 is not None and (self.x2.want_grad or (input_grad and self.x2.kind == "input"
                                                              and self.x2.grad is not None))
@@ -1065,6 +1100,7 @@ class Net(object):
                 op.bwd(self.rt, lo, hi, wgrad, input_grad)
         finally:
             self.wscale, self.ig_range = None, None
+            self.rt.join_wgrad_stream()
 
     def single_pass_ok(self):
         """True if the weighted single-pass backward is implemented for this program: a scalar head, a first layer
