@@ -16,6 +16,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// HMGAN_EW_HOIST=1 selects the *_v8u / *_v8h variants below (opt-in until measured on B200)
+static inline bool ew_hoist() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HMGAN_EW_HOIST");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static inline unsigned ew_grid(long long n, int threads = 256, int per_sm = 8) {
   long long b = (n + threads - 1) / threads;
   long long cap = (long long)num_sms() * per_sm;
@@ -515,6 +525,231 @@ __global__ void bn_bwd_apply_v8_kernel(const T* __restrict__ da, const T* __rest
   }
 }
 
+// ---------------------------------------------------------------------------
+// Variants with more memory-level parallelism / less per-iteration work (opt-in, HMGAN_EW_HOIST=1: written after the
+// profiles showed the BatchNorm passes at ~45 % of the HBM peak, not yet measured on B200).
+//   * reductions: every thread keeps UNR rows in flight (independent 16-byte loads issued before any use);
+//   * apply: when the grid stride is a multiple of the channel-group count, a thread sees the SAME 8 channels in every
+//     iteration, so the per-channel constants are loaded once instead of 40 scalar loads per 64 bytes of traffic.
+// ---------------------------------------------------------------------------
+constexpr int EW_UNR = 4;
+
+template <typename T, int MODE>  // MODE 0: sum,sumsq ; 1: sum only
+__global__ void __launch_bounds__(256) col_reduce_v8u_kernel(const T* __restrict__ x, long long M, int C,
+                                                             double* sums, float* fsum) {
+  __shared__ float sh0[256 * 8], sh1[MODE == 0 ? 256 * 8 : 8];
+  const int cg = C >> 3;
+  const int ct = cg < 256 ? cg : 256;
+  const int lanes = 256 / ct;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  const long long step = (long long)gridDim.x * lanes;
+  for (int g0 = 0; g0 < cg; g0 += ct) {
+    const int g = g0 + tc;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
+    if (active && g < cg) {
+      const T* px = x + g * 8;
+      long long m = (long long)blockIdx.x * lanes + tr;
+      for (; m + (EW_UNR - 1) * step < M; m += EW_UNR * step) {
+        float v[EW_UNR][8];
+#pragma unroll
+        for (int u = 0; u < EW_UNR; u++) load8(px + (size_t)(m + u * step) * C, v[u]);
+#pragma unroll
+        for (int u = 0; u < EW_UNR; u++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            s0[j] += v[u][j];
+            if (MODE == 0) s1[j] += v[u][j] * v[u][j];
+          }
+      }
+      for (; m < M; m += step) {
+        float v[8];
+        load8(px + (size_t)m * C, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += v[j];
+          if (MODE == 0) s1[j] += v[j] * v[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sh0[threadIdx.x * 8 + j] = s0[j];
+      if (MODE == 0) sh1[threadIdx.x * 8 + j] = s1[j];
+    }
+    __syncthreads();
+    if (tr == 0 && g < cg) {
+      for (int l = 1; l < lanes; l++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += sh0[(l * ct + tc) * 8 + j];
+          if (MODE == 0) s1[j] += sh1[(l * ct + tc) * 8 + j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (MODE == 0) {
+          atomicAdd(sums + g * 8 + j, (double)s0[j]);
+          atomicAdd(sums + C + g * 8 + j, (double)s1[j]);
+        } else {
+          atomicAdd(fsum + g * 8 + j, s0[j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    bn_bwd_reduce_v8u_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x, long long M,
+                             int C, const float* __restrict__ mean, const float* __restrict__ inv_std, int act,
+                             float slope, double* red) {
+  __shared__ float sh0[256 * 8], sh1[256 * 8];
+  const int cg = C >> 3;
+  const int ct = cg < 256 ? cg : 256;
+  const int lanes = 256 / ct;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  const long long step = (long long)gridDim.x * lanes;
+  for (int g0 = 0; g0 < cg; g0 += ct) {
+    const int g = g0 + tc;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
+    if (active && g < cg) {
+      float mu[8], is[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        mu[j] = mean[g * 8 + j];
+        is[j] = inv_std[g * 8 + j];
+      }
+      long long m = (long long)blockIdx.x * lanes + tr;
+      for (; m + step < M; m += 2 * step) {                 // two rows in flight: six independent 16-byte loads
+        const size_t o0 = (size_t)m * C + g * 8, o1 = (size_t)(m + step) * C + g * 8;
+        float g0v[8], a0v[8], x0v[8], g1v[8], a1v[8], x1v[8];
+        load8(da + o0, g0v);
+        load8(a + o0, a0v);
+        load8(x + o0, x0v);
+        load8(da + o1, g1v);
+        load8(a + o1, a1v);
+        load8(x + o1, x1v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gg0 = g0v[j] * act_grad_from_out(a0v[j], act, slope);
+          const float gg1 = g1v[j] * act_grad_from_out(a1v[j], act, slope);
+          s0[j] += gg0;
+          s1[j] += gg0 * (x0v[j] - mu[j]) * is[j];
+          s0[j] += gg1;
+          s1[j] += gg1 * (x1v[j] - mu[j]) * is[j];
+        }
+      }
+      for (; m < M; m += step) {
+        const size_t o = (size_t)m * C + g * 8;
+        float gv[8], av[8], xv[8];
+        load8(da + o, gv);
+        load8(a + o, av);
+        load8(x + o, xv);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gg = gv[j] * act_grad_from_out(av[j], act, slope);
+          s0[j] += gg;
+          s1[j] += gg * (xv[j] - mu[j]) * is[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sh0[threadIdx.x * 8 + j] = s0[j];
+      sh1[threadIdx.x * 8 + j] = s1[j];
+    }
+    __syncthreads();
+    if (tr == 0 && g < cg) {
+      for (int l = 1; l < lanes; l++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += sh0[(l * ct + tc) * 8 + j];
+          s1[j] += sh1[(l * ct + tc) * 8 + j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        atomicAdd(red + g * 8 + j, (double)s0[j]);
+        atomicAdd(red + C + g * 8 + j, (double)s1[j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// requires (gridDim.x * blockDim.x) % (C/8) == 0 (checked by the host wrapper): the channel group of a thread is then
+// the same in every grid-stride iteration
+template <typename T>
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_v8h_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x,
+                            T* __restrict__ dx, long long M, int C, const float* __restrict__ mean,
+                            const float* __restrict__ inv_std, const float* __restrict__ gamma, int act, float slope,
+                            const double* __restrict__ red, float* dgamma, float* dbeta) {
+  const int cg = C >> 3;
+  const long long n8 = M * cg;
+  const float invM = 1.f / (float)M;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n8) return;
+  const int c0 = (int)(i0 % cg) * 8;
+  float mu[8], is[8], gi[8], r0m[8], r1m[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = c0 + j;
+    const float r0 = (float)red[c], r1 = (float)red[C + c];
+    mu[j] = mean[c];
+    is[j] = inv_std[c];
+    gi[j] = gamma[c] * is[j];
+    r0m[j] = r0 * invM;
+    r1m[j] = r1 * invM;
+    if (i0 < cg) {
+      if (dgamma) dgamma[c] = r1;
+      if (dbeta) dbeta[c] = r0;
+    }
+  }
+  for (long long i = i0; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float gv[8], av[8], xv[8], o[8];
+    load8(da + i * 8, gv);
+    load8(a + i * 8, av);
+    load8(x + i * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float gg = gv[j] * act_grad_from_out(av[j], act, slope);
+      const float xh = (xv[j] - mu[j]) * is[j];
+      o[j] = gi[j] * (gg - r0m[j] - xh * r1m[j]);
+    }
+    store8(dx + i * 8, o);
+  }
+}
+
+// same idea for the forward apply: scale/shift of a thread's 8 channels are loop invariants
+template <typename T>
+__global__ void __launch_bounds__(256)
+    bn_apply_act_v8h_kernel(const T* __restrict__ x, T* __restrict__ a, long long n8, int C,
+                            const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope) {
+  const int cg = C >> 3;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n8) return;
+  const int c0 = (int)(i0 % cg) * 8;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c0 + j];
+    sf[j] = shift[c0 + j];
+  }
+  for (long long i = i0; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = act_fwd(v[j] * sc[j] + sf[j], act, slope);
+    store8(a + i * 8, v);
+  }
+}
+
 template <typename T>
 __global__ void act_bwd_v8_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* dx, long long n8, int act,
                                   float slope, int accumulate) {
@@ -938,8 +1173,13 @@ extern "C" int hm_bn_stats(const void* x, int dtype, long long M, int C, double*
   if (C % 8 == 0 && al16(x)) {
     int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
     unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
-    DISPATCH_T(dtype, (col_reduce_v8_kernel<T, 0><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums,
-                                                                                       nullptr)));
+    if (ew_hoist()) {
+      DISPATCH_T(dtype, (col_reduce_v8u_kernel<T, 0><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums,
+                                                                                          nullptr)));
+    } else {
+      DISPATCH_T(dtype, (col_reduce_v8_kernel<T, 0><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums,
+                                                                                         nullptr)));
+    }
     HM_CHECK_LAUNCH("hm_bn_stats");
     return HM_OK;
   }
@@ -957,8 +1197,13 @@ extern "C" int hm_col_sum(const void* dy, int dtype, long long M, int C, float* 
   if (C % 8 == 0 && al16(dy)) {
     int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
     unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
-    DISPATCH_T(dtype, (col_reduce_v8_kernel<T, 1><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)dy, M, C, nullptr,
-                                                                                       db)));
+    if (ew_hoist()) {
+      DISPATCH_T(dtype, (col_reduce_v8u_kernel<T, 1><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)dy, M, C, nullptr,
+                                                                                          db)));
+    } else {
+      DISPATCH_T(dtype, (col_reduce_v8_kernel<T, 1><<<g8, 256, 0, (cudaStream_t)stream>>>((const T*)dy, M, C, nullptr,
+                                                                                         db)));
+    }
     HM_CHECK_LAUNCH("hm_col_sum");
     return HM_OK;
   }
@@ -990,8 +1235,14 @@ extern "C" int hm_bn_apply_act(const void* x, void* a, int dtype, long long M, i
   HM_CHECK_ARG(x && a && scale && shift && M > 0 && C > 0, "hm_bn_apply_act: bad argument");
   long long n = M * C;
   if (C % 8 == 0 && al16(x) && al16(a)) {
-    DISPATCH_T(dtype, (bn_apply_act_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
-                          (const T*)x, (T*)a, n / 8, C, scale, shift, act, slope)));
+    const unsigned ga = ew_grid(n / 8);
+    if (ew_hoist() && ((long long)ga * 256) % (C / 8) == 0) {
+      DISPATCH_T(dtype, (bn_apply_act_v8h_kernel<T><<<ga, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)x, (T*)a, n / 8, C, scale, shift, act, slope)));
+    } else {
+      DISPATCH_T(dtype, (bn_apply_act_v8_kernel<T><<<ga, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)x, (T*)a, n / 8, C, scale, shift, act, slope)));
+    }
     HM_CHECK_LAUNCH("hm_bn_apply_act");
     return HM_OK;
   }
@@ -1009,8 +1260,13 @@ extern "C" int hm_bn_bwd_reduce(const void* da, const void* a, const void* x, in
   if (C % 8 == 0 && al16(da) && al16(a) && al16(x)) {
     int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
     unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
-    DISPATCH_T(dtype, (bn_bwd_reduce_v8_kernel<T><<<g8, 256, 0, (cudaStream_t)stream>>>(
-                          (const T*)da, (const T*)a, (const T*)x, M, C, mean, inv_std, act, slope, red)));
+    if (ew_hoist()) {
+      DISPATCH_T(dtype, (bn_bwd_reduce_v8u_kernel<T><<<g8, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)da, (const T*)a, (const T*)x, M, C, mean, inv_std, act, slope, red)));
+    } else {
+      DISPATCH_T(dtype, (bn_bwd_reduce_v8_kernel<T><<<g8, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)da, (const T*)a, (const T*)x, M, C, mean, inv_std, act, slope, red)));
+    }
     HM_CHECK_LAUNCH("hm_bn_bwd_reduce");
     return HM_OK;
   }
@@ -1030,9 +1286,16 @@ extern "C" int hm_bn_bwd_apply(const void* da, const void* a, const void* x, voi
                "hm_bn_bwd_apply: bad argument");
   long long n = M * C;
   if (C % 8 == 0 && al16(da) && al16(a) && al16(x) && al16(dx)) {
-    DISPATCH_T(dtype, (bn_bwd_apply_v8_kernel<T><<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
-                          (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope, red,
-                          dgamma, dbeta)));
+    const unsigned ga = ew_grid(n / 8);
+    if (ew_hoist() && ((long long)ga * 256) % (C / 8) == 0) {
+      DISPATCH_T(dtype, (bn_bwd_apply_v8h_kernel<T><<<ga, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope,
+                            red, dgamma, dbeta)));
+    } else {
+      DISPATCH_T(dtype, (bn_bwd_apply_v8_kernel<T><<<ga, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope,
+                            red, dgamma, dbeta)));
+    }
     HM_CHECK_LAUNCH("hm_bn_bwd_apply");
     return HM_OK;
   }

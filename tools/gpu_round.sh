@@ -10,6 +10,7 @@
 #   4. bench.py --workload both (joint step)            -> gpurun_out/<tag>_bench_joint.json
 #   5. ncu launch list of one bench step                -> gpurun_out/<tag>_launches.csv  (+ per-kernel summary .txt)
 #   6. ncu --set full of the dominant kernels           -> gpurun_out/<tag>_ncu_full.txt  (tools/tc_probe.py perf)
+#   7. opt-in variants not yet measured (A/B)           -> gpurun_out/<tag>_pytest_gpu_experimental.log, _bench_experimental.txt
 # Skip stages with SKIP="1 6" (space-separated numbers).  Numbers printed under ncu are never bench values.
 tag=${1:-rX}
 out=gpurun_out
@@ -31,4 +32,13 @@ run 6 "ncu --set full (dominant kernels)" && {
   ncu -i $out/${tag}_ncu_full.ncu-rep --page raw --csv \
       --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg.per_second \
       > $out/${tag}_ncu_full.txt 2>&1; head -5 $out/${tag}_ncu_full.txt; }
+# 7. the written-but-unmeasured variants: full GPU suite and the bench with them switched on
+run 7 "experimental variants (EW_HOIST, WGRAD_STREAM)" && {
+  HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1 HMGAN_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q \
+      > $out/${tag}_pytest_gpu_experimental.log 2>&1; tail -3 $out/${tag}_pytest_gpu_experimental.log
+  for v in "HMGAN_EW_HOIST=1" "HMGAN_WGRAD_STREAM=1" "HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1"; do
+    echo "[gpu_round] bench with $v"
+    env $v timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | \
+        python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'])"
+  done > $out/${tag}_bench_experimental.txt 2>&1; cat $out/${tag}_bench_experimental.txt; }
 echo "[gpu_round] done"
