@@ -39,6 +39,7 @@ _PROTOS = {
     "hm_conv_gather": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "hm_conv_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_conv": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
+    "hm_tc_conv_ws": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P], C.c_int),
     "hm_tc_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
     "hm_up2conv_wgrad_phases": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
     "hm_im2col_c1": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
@@ -97,12 +98,14 @@ def load():
     for name in ("hm_tc_conv_supported", "hm_tc_wgrad_supported"):
         getattr(lib, name).argtypes = [C.POINTER(ConvDesc)]
         getattr(lib, name).restype = C.c_int
+    lib.hm_tc_conv_ws_bytes.argtypes = [C.POINTER(ConvDesc)]
+    lib.hm_tc_conv_ws_bytes.restype = C.c_longlong
     _lib = lib
     return lib
 
 
 def exported_symbols():
-    return sorted(list(_PROTOS) + ["hm_tc_conv_supported", "hm_tc_wgrad_supported"])
+    return sorted(list(_PROTOS) + ["hm_tc_conv_supported", "hm_tc_wgrad_supported", "hm_tc_conv_ws_bytes"])
 
 
 def pack_count(mode, cout, cin, kh, kw):

@@ -975,6 +975,247 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+// ---- split-K variant for the small layers ------------------------------------------------------------------------
+// (opt-in: HMGAN_TC_SPLITK=1 and a caller workspace, hm_tc_conv_ws; written from the round-1 launch list, where the
+// 4x4..16x16 layers run 4..128 CTAs for 20-90 us each because one CTA walks all K = taps*Cin/64 stages of its tile;
+// NOT yet measured on B200.)
+// Work item = (M tile, N tile, K slice): the slice's partial accumulator is added to an fp32 workspace
+// ws[pixel][GEMM column] with red.global.add.v4.f32; tc_splitk_finish_kernel then applies bias / activation /
+// accumulate / depth-to-space exactly like epilogue_loop and leaves the workspace zeroed for the next launch.
+struct TcSplitParams {
+  TcParams p;        // S = 1, n_super = n_mtiles
+  float* ws;         // [B*Ho*Wo][ws_cols] fp32, zero on entry
+  int ws_cols;       // n_ntiles * ntile
+  int ksplit;        // K slices per tile (<= taps * Cin/64)
+};
+
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_conv_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                          const __grid_constant__ CUtensorMap tmB, const TcSplitParams q) {
+  const TcParams& p = q.p;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = A_BYTES + p.ntile * 128;
+  const uint32_t ctrl = base + p.stages * stage_bytes;        // 1024-aligned
+  // control block: full[stages] | empty[stages] | tfull[2] | tempty[2] | tmem base address
+  auto full_bar = [&](int s) { return ctrl + 8u * s; };
+  auto empty_bar = [&](int s) { return ctrl + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return ctrl + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return ctrl + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = ctrl + 8u * (2 * p.stages + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int acc_cols = p.ntile;                          // one M tile per work item, double-buffered accumulator
+  const int tmem_cols = 2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+
+  const int ksteps_per_tap = p.Cin / KCH;
+  const int ksteps = p.kh * p.kw * ksteps_per_tap;
+  const int total_items = p.n_mtiles * p.n_ntiles * q.ksplit;     // item = (tile, K slice); tile = (M tile, N tile)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int t = w / q.ksplit, sl = w - t * q.ksplit;
+        const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+        const int ks0 = (int)(((long long)sl * ksteps) / q.ksplit);
+        const int ks1 = (int)(((long long)(sl + 1) * ksteps) / q.ksplit);
+        const int bx = (mt % p.tiles_x) * p.bw * p.stride - p.pad;
+        const int by = ((mt / p.tiles_x) % p.tiles_y) * p.bh * p.stride - p.pad;
+        const int on = (mt / (p.tiles_x * p.tiles_y)) * p.bn;
+#pragma unroll 1
+        for (int ks = ks0; ks < ks1; ks++) {
+          const int tap = ks / ksteps_per_tap, cc = ks - tap * ksteps_per_tap;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = base + stage * stage_bytes;
+          mbar_expect_tx(full_bar(stage), A_BYTES + p.ntile * 128);
+          const int c = cc * KCH;
+          if (c < p.C1)
+            tma_load_4d(&tmA, sa, full_bar(stage), c, bx + s, by + r, on);
+          else
+            tma_load_4d(&tmA2, sa, full_bar(stage), c - p.C1, bx + s, by + r, on);
+          tma_load_3d(&tmB, sa + A_BYTES, full_bar(stage), c, nt * p.ntile, tap);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(p.ntile);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x, it++) {
+        const int t = w / q.ksplit, sl = w - t * q.ksplit;
+        const int ks0 = (int)(((long long)sl * ksteps) / q.ksplit);
+        const int ks1 = (int)(((long long)(sl + 1) * ksteps) / q.ksplit);
+        const int acc = it & 1;
+        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        uint32_t first = 0;
+        for (int ks = ks0; ks < ks1; ks++) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_lo = umma_lo_of(base + stage * stage_bytes);
+          const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+          mma_tap<1>(d_tmem, a_lo, A_BYTES >> 4, b_lo, p.ntile, idesc, first);
+          first = 1;
+          tc_commit(empty_bar(stage));                        // frees the stage when these MMAs retire
+          if (ks == ks1 - 1) tc_commit(tfull_bar(acc));       // partial accumulator complete
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5): partial sums -> fp32 workspace =====================
+    const int qd = warp & 3;                                  // TMEM lane quarter this warp may access
+    const int row = qd * 32 + lane;
+    const int px_per_img = p.bw * p.bh;
+    const int in = row / px_per_img;
+    const int rem = row - in * px_per_img;
+    const int iy = rem / p.bw, ix = rem - iy * p.bw;
+    int it = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, it++) {
+      const int t = w / q.ksplit;
+      const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
+      const int acc = it & 1;
+      mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+      tc_fence_after();
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int tn = mt / (p.tiles_x * p.tiles_y);
+      const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
+      const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
+      const size_t pix = (size_t)((size_t)n * p.Ho + oy) * p.Wo + ox;
+      float* dst = q.ws + pix * q.ws_cols + nt * p.ntile;
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * acc_cols;
+      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+        uint32_t v[32];
+        const bool full32 = p.ntile - c0 >= 32;
+        if (full32) tmem_ld32(taddr + c0, v);
+        else tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        if (full32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) red_add_v4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) red_add_v4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ws[pixel][column] -> bias, (+ stored value), activation -> fp16 output (plain / two concat targets / depth-to-space),
+// 8 columns per thread; the workspace is zeroed behind the read.
+__global__ void __launch_bounds__(256) tc_splitk_finish_kernel(const TcSplitParams q) {
+  const TcParams& p = q.p;
+  const int groups = q.ws_cols >> 3;
+  const long long npix = (long long)p.B * p.Ho * p.Wo;
+  const long long total = npix * groups;
+  const int creal = p.d2s ? 4 * p.cph : p.Cout;            // GEMM columns that exist (the N tile may be zero-padded)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / groups;
+    const int col = (int)(i - pix * groups) * 8;
+    float4* w4 = reinterpret_cast<float4*>(q.ws + pix * q.ws_cols + col);
+    const float4 lo = w4[0], hi = w4[1];
+    w4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    w4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    const int ox = (int)(pix % p.Wo);
+    const int oy = (int)((pix / p.Wo) % p.Ho);
+    const int n = (int)(pix / ((long long)p.Wo * p.Ho));
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c = col + j;
+      if (c >= creal) continue;
+      __half* dst;
+      int cb;                                                // channel whose bias applies
+      bool accum;
+      if (p.d2s) {
+        const int ph = c / p.cph, co = c - ph * p.cph;
+        const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+        dst = p.y + op * p.cph + co;
+        cb = co;
+        accum = (p.accumulate & 1) != 0;
+      } else if (c < p.split) {
+        dst = p.y ? p.y + (size_t)pix * p.split + c : nullptr;
+        cb = c;
+        accum = (p.accumulate & 1) != 0;
+      } else {
+        dst = p.y2 ? p.y2 + (size_t)pix * (p.Cout - p.split) + (c - p.split) : nullptr;
+        cb = c;
+        accum = (p.accumulate & 2) != 0;
+      }
+      if (!dst) continue;
+      float a = v[j] + (p.bias ? p.bias[cb] : 0.f);
+      if (accum) a += __half2float(*dst);
+      switch (p.act) {
+        case HM_ACT_LRELU: a = act_t<HM_ACT_LRELU>(a, p.slope); break;
+        case HM_ACT_RELU: a = act_t<HM_ACT_RELU>(a, p.slope); break;
+        case HM_ACT_SIGMOID: a = act_t<HM_ACT_SIGMOID>(a, p.slope); break;
+        case HM_ACT_TANH: a = act_t<HM_ACT_TANH>(a, p.slope); break;
+        default: break;
+      }
+      *dst = __float2half_rn(a);
+    }
+  }
+}
+
 // ---- host side ---------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1090,9 +1331,58 @@ extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   return 1;
 }
 
+static bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HMGAN_TC_SPLITK");      // opt-in until measured on B200
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// K slices per tile for the split-K variant (1 = do not split): only layers whose tiles fill less than half of the SMs
+// and that walk at least 8 K stages per tile; at least 4 stages per slice.
+static int splitk_factor(long long tiles, int ksteps) {
+  const int sms = num_sms();
+  if (tiles < 1 || tiles * 2 > sms || ksteps < 8) return 1;
+  long long k = sms / tiles;
+  if (k > ksteps / 4) k = ksteps / 4;
+  return k < 2 ? 1 : (int)k;
+}
+
+// Bytes of zeroed fp32 workspace hm_tc_conv_ws may use for this problem: 0 when the split-K variant would not be chosen
+// (switched off, unsupported shape, or enough tiles to fill the machine).  An upper bound that depends on d alone.
+extern "C" long long hm_tc_conv_ws_bytes(const HmConvDesc* d) {
+  if (!d || !splitk_enabled() || !hm_tc_conv_supported(d)) return 0;
+  const bool phase = is_up2conv(d) || is_dgrad_s2(d) || is_deconv_d2s(d);
+  const long long gh = phase ? d->H : d->Ho, gw = phase ? d->W : d->Wo;        // tile grid
+  if (gw >= TILE_M) return 0;                                                   // row-box kernels take those layers
+  const long long cols = ((phase ? 4LL * d->Cout : d->Cout) + 15) / 16 * 16;
+  const long long npix = (long long)d->B * gh * gw;
+  const long long min_tiles = (npix + TILE_M - 1) / TILE_M * ((cols + 255) / 256);
+  if (min_tiles * 2 > num_sms()) return 0;
+  return npix * cols * 4;
+}
+
+static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+                        void* y, void* y2, void* ws, size_t ws_bytes, void* stream);
+
 // y[B,Ho,Wo,Cout] = act( corr(x1|x2, w_tc) + bias );  w_tc is the pack [kh*kw][Cout][C1+C2] (fp16, K-major).
 extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
                           void* y, void* y2, void* stream) {
+  return tc_conv_impl(d, x1, x2, w_tc, bias, y, y2, nullptr, 0, stream);
+}
+
+// The same with a caller-provided workspace of ws_bytes >= hm_tc_conv_ws_bytes(d) ZEROED bytes (left zeroed on return,
+// so one buffer serves every call on a stream): lets small layers split K over otherwise idle SMs.
+extern "C" int hm_tc_conv_ws(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+                             void* y, void* y2, void* ws, long long ws_bytes, void* stream) {
+  HM_CHECK_ARG(!ws || ((((uintptr_t)ws) & 15) == 0 && ws_bytes >= 0), "hm_tc_conv_ws: workspace must be 16-byte aligned");
+  return tc_conv_impl(d, x1, x2, w_tc, bias, y, y2, ws, (size_t)ws_bytes, stream);
+}
+
+static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+                        void* y, void* y2, void* ws, size_t ws_bytes, void* stream) {
   HM_CHECK_ARG(d && x1 && w_tc && (y || y2), "hm_tc_conv: null argument");
   if (!hm_tc_conv_supported(d)) {
     set_error("hm_tc_conv: shape not supported by the tcgen05 path (need fp16, stride 1, C%%64==0, Cout%%16==0)");
@@ -1277,6 +1567,45 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
       if (grid_rb > num_sms()) grid_rb = num_sms();
       tc_conv_rb_kernel<<<grid_rb, TC_THREADS, smem_rb, (cudaStream_t)stream>>>(rA, rA2, tmB, p);
       HM_CHECK_LAUNCH("hm_tc_conv(row box)");
+      return HM_OK;
+    }
+  }
+  if (ws && splitk_enabled()) {
+    const int ksteps = p.kh * p.kw * (p.Cin / KCH);
+    const int ksplit = splitk_factor((long long)p.n_mtiles * p.n_ntiles, ksteps);
+    const size_t need = (size_t)d->B * p.Ho * p.Wo * (size_t)(p.n_ntiles * p.ntile) * 4;
+    if (ksplit > 1 && ws_bytes >= need) {
+      TcSplitParams q;
+      q.p = p;
+      q.p.S = 1;
+      q.p.n_super = p.n_mtiles;
+      const int sk_stage = A_BYTES + p.ntile * 128;
+      int sk_stages = (227 * 1024 - 10240) / sk_stage;
+      if (sk_stages > 8) sk_stages = 8;
+      q.p.stages = sk_stages;
+      q.ws = (float*)ws;
+      q.ws_cols = p.n_ntiles * p.ntile;
+      q.ksplit = ksplit;
+      static bool sk_attr = false;
+      if (!sk_attr) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+          set_error("hm_tc_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+          return HM_ERR_CUDA;
+        }
+        sk_attr = true;
+      }
+      const size_t sk_smem = (size_t)sk_stages * sk_stage + 1024 /*alignment slack*/ + 1024 /*control block*/;
+      long long items = (long long)p.n_mtiles * p.n_ntiles * ksplit;
+      int sk_grid = items > num_sms() ? num_sms() : (int)items;
+      tc_conv_splitk_kernel<<<sk_grid, TC_THREADS, sk_smem < 120 * 1024 ? 120 * 1024 : sk_smem, (cudaStream_t)stream>>>(
+          tmA, tmA2, tmB, q);
+      HM_CHECK_LAUNCH("hm_tc_conv(split K)");
+      const long long groups = (long long)d->B * p.Ho * p.Wo * (q.ws_cols / 8);
+      long long fb = (groups + 255) / 256;
+      if (fb > (long long)num_sms() * 8) fb = (long long)num_sms() * 8;
+      tc_splitk_finish_kernel<<<(unsigned)fb, 256, 0, (cudaStream_t)stream>>>(q);
+      HM_CHECK_LAUNCH("hm_tc_conv(split K finish)");
       return HM_OK;
     }
   }

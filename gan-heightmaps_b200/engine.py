@@ -59,6 +59,8 @@ class Runtime(object):
         self._pack_tables = {}
         self._wgrad_stream = None
         self._wgrad_forked = False
+        self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "0") == "1"
+        self._tc_ws = None
         _lib.load()
 
     def allreduce_mean(self, t):
@@ -96,6 +98,17 @@ class Runtime(object):
             self._pack_jobs.append(args)             # deferred: one hm_pack_conv_weight_multi launch per network
             return
         self.launches += 1
+        if name == "hm_tc_conv" and self._splitk:
+            # opt-in split-K for the layers that fill only a few SMs (HMGAN_TC_SPLITK=1, include/hmgan.h): one zeroed
+            # fp32 workspace shared by every convolution of this runtime (calls are serialised on the main stream and
+            # each leaves it zeroed); it is sized during the eager warm-up calls, never while a graph is captured
+            need = _lib.query("hm_tc_conv_ws_bytes", args[0])
+            if need > 0:
+                if self._tc_ws is None or self._tc_ws.numel() * 4 < need:
+                    self._tc_ws = self.zeros(((need + 3) // 4,), torch.float32)
+                self.launches += 1               # the finishing pass
+                _lib.call("hm_tc_conv_ws", *args, self._tc_ws.data_ptr(), self._tc_ws.numel() * 4, self.stream)
+                return
         _lib.call(name, *args, self.stream)
 
     def begin_pack_batch(self):

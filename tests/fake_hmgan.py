@@ -615,6 +615,11 @@ def _tc_ok(d, wgrad):
     return ok and 0 < d.split <= d.Cout and bool(ntile)
 
 
+def hm_tc_conv_ws(dp, x1, x2, w_tc, bias, y, y2, ws, ws_bytes, stream=None):
+    """hm_tc_conv with a workspace the emulation has no use for (it must stay zero)."""
+    return hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream)
+
+
 def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
     """Same contract as hm_conv_gather, weights in the K-major pack [tap][Cout][Cin]."""
     d = dp._obj if hasattr(dp, "_obj") else dp
@@ -784,6 +789,8 @@ _FUNCS = {k: v for k, v in globals().items() if k.startswith("hm_")}
 
 def query(name, dp):
     d = dp._obj if hasattr(dp, "_obj") else dp
+    if name == "hm_tc_conv_ws_bytes":
+        return 0                       # the emulation never splits K
     return int(_tc_ok(d, name == "hm_tc_wgrad_supported"))
 
 

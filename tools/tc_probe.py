@@ -12,6 +12,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gan-heightmaps_b200"))
 import _lib  # noqa: E402
 
+_WS = {}
+
+
+def _tc_conv(dref, x1, x2, w, bias, y, y2, stream=None):
+    """hm_tc_conv; with HMGAN_TC_SPLITK=1 through hm_tc_conv_ws with a zeroed workspace where the library asks for one
+    (the opt-in split-K variant of the small layers), checking that the workspace comes back zeroed."""
+    if os.environ.get("HMGAN_TC_SPLITK", "0") == "1":
+        need = _lib.query("hm_tc_conv_ws_bytes", dref)
+        if need > 0:
+            ws = _WS.get(need)
+            if ws is None:
+                ws = _WS[need] = torch.zeros((need + 3) // 4, dtype=torch.float32, device="cuda")
+            _lib.call("hm_tc_conv_ws", dref, x1, x2, w, bias, y, y2, ws.data_ptr(), ws.numel() * 4, stream)
+            torch.cuda.synchronize()
+            assert float(ws.abs().max()) == 0.0, "split-K workspace not left zeroed"
+            return
+    _lib.call("hm_tc_conv", dref, x1, x2, w, bias, y, y2, stream)
+
+
 CASES = [
     # name, B, H, W, C1, C2, Cout, k, pad, act
     ("1x1_64_64_w16", 2, 16, 16, 64, 0, 64, 1, 0, 0),
@@ -67,7 +86,7 @@ def run_case(name, B, H, W, C1, C2, Cout, k, pad, act, verbose=True):
     p2 = x2.data_ptr() if C2 else None
     _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None,
               None)
-    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
+    _tc_conv(C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
     torch.cuda.synchronize()
     a, b = y_tc.float(), y_ref.float()
     err = (a - b).abs()
@@ -113,7 +132,7 @@ def run_up2_case(name, B, H, W, Ci, Co, act):
     y_tc = torch.full((B, 2 * H, 2 * W, Co), 7.0, device="cuda", dtype=torch.float16)
     _lib.call("hm_conv_gather", C.byref(d), x.data_ptr(), None, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None,
               None)
-    _lib.call("hm_tc_conv", C.byref(d), x.data_ptr(), None, w8.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
+    _tc_conv(C.byref(d), x.data_ptr(), None, w8.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
     torch.cuda.synchronize()
     a, b = y_tc.float(), y_ref.float()
     err = (a - b).abs()
@@ -163,7 +182,7 @@ def run_s2_case(name, B, H, W, C1, C2, Co):
     y_tc = torch.full((B, Ho, Wo, Co), 7.0, device="cuda", dtype=torch.float16)
     _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, packs[0].data_ptr(), bias.data_ptr(), y_ref.data_ptr(),
               None, None)
-    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, packs[5].data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None,
+    _tc_conv(C.byref(d), x1.data_ptr(), p2, packs[5].data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None,
               None)
     # weight gradient
     dy = torch.randn(B, Ho, Wo, Co, device="cuda").half()
@@ -185,7 +204,7 @@ def run_s2_case(name, B, H, W, C1, C2, Co):
         dx_ref, dx_tc = init.clone(), init.clone()
         _lib.call("hm_conv_gather", C.byref(dd), dy.data_ptr(), None, packs[1].data_ptr(), None, dx_ref.data_ptr(), None,
                   None)
-        _lib.call("hm_tc_conv", C.byref(dd), dy.data_ptr(), None, packs[12].data_ptr(), None, dx_tc.data_ptr(), None, None)
+        _tc_conv(C.byref(dd), dy.data_ptr(), None, packs[12].data_ptr(), None, dx_tc.data_ptr(), None, None)
         torch.cuda.synchronize()
         pairs.append(("dgrad", dx_tc.float(), dx_ref.float()))
     for what, a, b in pairs:
@@ -259,7 +278,7 @@ def run_dc2_case(name, B, H, W, C1, C2, Co, act):
     d = desc(dtype=1, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=2, kw=2, stride=2, pad=0, transposed=2, Ho=2 * H, Wo=2 * W,
              Cout=Co, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Co, act=act, slope=0.2, accumulate=0)
     y = torch.full((B, 2 * H, 2 * W, Co), 7.0, device="cuda", dtype=torch.float16)
-    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), x2.data_ptr() if C2 else None, wt.data_ptr(), bias.data_ptr(),
+    _tc_conv(C.byref(d), x1.data_ptr(), x2.data_ptr() if C2 else None, wt.data_ptr(), bias.data_ptr(),
               y.data_ptr(), None, None)
     xin = torch.cat([x1, x2], 3) if C2 else x1
     # Lasagne Deconv2DLayer(flip_filters=False) == conv_transpose2d with the filter rotated by 180 degrees
@@ -277,7 +296,7 @@ def run_dc2_case(name, B, H, W, C1, C2, Co, act):
     g2 = torch.full((B, H, W, max(C2, 1)), 7.0, device="cuda", dtype=torch.float16)
     dd = desc(dtype=1, B=B, H=H, W=W, C1=64, C2=0, up=0, kh=1, kw=1, stride=1, pad=0, transposed=0, Ho=H, Wo=W, Cout=Ci,
               oH=H, oW=W, os=1, ou=0, ov=0, split=C1, act=0, slope=0.0, accumulate=0)
-    _lib.call("hm_tc_conv", C.byref(dd), dy64.data_ptr(), None, wd.data_ptr(), None, g1.data_ptr(),
+    _tc_conv(C.byref(dd), dy64.data_ptr(), None, wd.data_ptr(), None, g1.data_ptr(),
               g2.data_ptr() if C2 else None, None)
     gref = F.conv2d(dy.float().permute(0, 3, 1, 2), Wm.flip(2, 3), stride=2).permute(0, 2, 3, 1)      # adjoint of the above
     torch.cuda.synchronize()
@@ -489,7 +508,7 @@ def perf():
         d = desc(dtype=1, B=B, H=H, W=W, C1=Ci, C2=0, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=H, Wo=W,
                  Cout=Co, oH=H, oW=W, os=1, ou=0, ov=0, split=Co, act=1, slope=0.2, accumulate=0)
         flop = 2.0 * B * H * W * k * k * Ci * Co
-        for what, fn in (("fwd  ", lambda: _lib.call("hm_tc_conv", C.byref(d), x.data_ptr(), None, wt.data_ptr(), None,
+        for what, fn in (("fwd  ", lambda: _tc_conv(C.byref(d), x.data_ptr(), None, wt.data_ptr(), None,
                                                       y.data_ptr(), None, None)),
                          ("wgrad", lambda: _lib.call("hm_tc_wgrad", C.byref(d), x.data_ptr(), None, dy.data_ptr(),
                                                       dw.data_ptr(), None))):
