@@ -21,54 +21,59 @@ import numpy as np
 class ReduceLROnPlateau(object):
     def __init__(self, learning_rate, factor=0.1, patience=10, verbose=0, mode='auto', epsilon=1e-4, cooldown=0,
                  min_lr=0):
-        if factor >= 1.0:
-            raise ValueError('ReduceLROnPlateau does not support a factor >= 1.0.')
+        if not factor < 1.0:
+            raise ValueError('ReduceLROnPlateau needs a factor < 1.0, got %r' % (factor,))
         self.learning_rate = learning_rate          # shared scalar: get_value() / set_value()
         self.factor, self.patience, self.verbose = factor, patience, verbose
         self.mode, self.epsilon, self.cooldown, self.min_lr = mode, epsilon, cooldown, min_lr
         self._reset()
 
+    # -- state ------------------------------------------------------------- #
     def _reset(self):
+        """Fresh counters; validates the mode (unknown -> 'auto' with a RuntimeWarning)."""
         if self.mode not in ('auto', 'min', 'max'):
-            warnings.warn('Learning Rate Plateau Reducing mode %s is unknown, fallback to auto mode.' % self.mode,
-                          RuntimeWarning)
+            warnings.warn('ReduceLROnPlateau: unknown mode %r, using auto' % (self.mode,), RuntimeWarning)
             self.mode = 'auto'
-        if self.mode == 'min':
-            self.monitor_op = lambda value, best: bool(np.less(value, best - self.epsilon))
-            self.best = np.inf
-        else:
-            self.monitor_op = lambda value, best: bool(np.greater(value, best + self.epsilon))
-            self.best = -np.inf
-        self.cooldown_counter = 0
+        self._minimise = self.mode == 'min'          # 'auto' behaves as 'max' (see the module docstring)
+        self.best = np.inf if self._minimise else -np.inf
         self.wait = 0
-        self.lr_epsilon = self.min_lr * 1e-4
+        self.cooldown_counter = 0
+        self.lr_epsilon = 1e-4 * self.min_lr
 
-    def on_train_begin(self, logs=None):
-        self._reset()
+    def monitor_op(self, value, best):
+        """True if `value` improves on `best` by more than epsilon in the monitored direction."""
+        return bool(value < best - self.epsilon) if self._minimise else bool(value > best + self.epsilon)
 
     def in_cooldown(self):
         return self.cooldown_counter > 0
 
+    # -- callbacks --------------------------------------------------------- #
+    def on_train_begin(self, logs=None):
+        self._reset()
+
     def on_epoch_end(self, monitor, epoch, logs=None):
         if monitor is None:
-            warnings.warn('Learning Rate Plateau Reducing requires a monitored value', RuntimeWarning)
+            warnings.warn('ReduceLROnPlateau: no monitored value given', RuntimeWarning)
             return
-        if self.in_cooldown():
+        cooling = self.in_cooldown()
+        if cooling:
             self.cooldown_counter -= 1
             self.wait = 0
+            cooling = self.in_cooldown()
         if self.monitor_op(monitor, self.best):
-            self.best = monitor
-            self.wait = 0
+            self.best, self.wait = monitor, 0
+        elif not cooling:
+            if self.wait >= self.patience:
+                self._reduce(epoch)
+            self.wait += 1
+
+    def _reduce(self, epoch):
+        lr = float(self.learning_rate.get_value())
+        if lr <= self.min_lr + self.lr_epsilon:
             return
-        if self.in_cooldown():
-            return
-        if self.wait >= self.patience:
-            old_lr = float(self.learning_rate.get_value())
-            if old_lr > self.min_lr + self.lr_epsilon:
-                new_lr = max(old_lr * self.factor, self.min_lr)
-                self.learning_rate.set_value(new_lr)
-                if self.verbose > 0:
-                    print('\nEpoch %05d: reducing learning rate to %s.' % (epoch, new_lr))
-                self.cooldown_counter = self.cooldown
-                self.wait = 0
-        self.wait += 1
+        lr = max(lr * self.factor, self.min_lr)
+        self.learning_rate.set_value(lr)
+        if self.verbose > 0:
+            print('\nEpoch %05d: reducing learning rate to %s.' % (epoch, lr))
+        self.cooldown_counter = self.cooldown
+        self.wait = 0
