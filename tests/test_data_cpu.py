@@ -123,3 +123,32 @@ def test_rotate_flip_augmenter_follows_the_keras_protocol():
     assert set(np.unique(s)) <= set(np.unique(x[0]))
     # batches smaller than batch_size (the last slice of a pass) come back whole
     assert next(aug.flow(x[:2], None, batch_size=4, seed=1)).shape[0] == 2
+
+
+def test_get_iterators_opens_the_hdf5_layout_of_the_reference(monkeypatch):
+    """experiments.get_iterators (reference experiments.py:10-18): datasets xt/yt/xv/yv of one HDF5 file, wrapped in
+    Hdf5Iterator with the training augmentation.  h5py is not installed here, so a stand-in module serves numpy arrays
+    under the same File(...)[name] protocol."""
+    import types
+    X, Y = _data(6, 8)
+    store = {"xt": X, "yt": Y, "xv": X[:4], "yv": Y[:4]}
+    fake = types.ModuleType("h5py")
+    fake.File = lambda path, mode="r": store
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    monkeypatch.delenv("HMGAN_SYNTHETIC", raising=False)
+    import torch  # noqa: F401  (experiments imports the trainer)
+    import experiments
+    for raw, dtype in (("1", np.uint8), ("0", np.float32)):
+        monkeypatch.setenv("HMGAN_DEVICE_NORMALISE", raw)
+        it_train, it_val = experiments.get_iterators("whatever.h5", 2, True, False, da=True)
+        assert it_train.N == 6 and it_val.N == 4
+        x, y = it_train.next()
+        assert x.dtype == dtype and y.dtype == dtype and x.shape[0] == 2
+        assert (x.shape[1:] == (8, 8, 1) and y.shape[1:] == (8, 8, 3)) if raw == "1" else \
+               (x.shape[1:] == (1, 8, 8) and y.shape[1:] == (3, 8, 8))
+    monkeypatch.setenv("HMGAN_DEVICE_NORMALISE", "1")
+    it_train, _ = experiments.get_iterators("whatever.h5", 2, True, False, da=False)
+    x, _ = it_train.next()
+    order = util._get_slices(6, 2)
+    np.random.RandomState(0).shuffle(order)
+    np.testing.assert_array_equal(x, X[order[0]])               # no augmentation: the raw bytes of the first slice
