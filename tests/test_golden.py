@@ -64,4 +64,4 @@ def test_cuda_joint_step_matches_golden():
     np.testing.assert_allclose(m.train_fn(Z, X, Y), JOINT['losses'][0], rtol=1e-3, atol=1e-6)
     px = m.gen_fn_det(X[:1])
     np.testing.assert_allclose(px[:, :, ::16, ::16], JOINT['px_det_sample'], rtol=2e-3, atol=2e-4)
-    np.testing.assert_allclose([px.mean(), px.std()], JOINT['px_det_moments'], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose([px.mean(), px.std()], JOINT['px_det_moments'], rtol=2e-3, atol=5e-4)
