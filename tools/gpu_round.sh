@@ -33,10 +33,10 @@ run 6 "ncu --set full (dominant kernels)" && {
       --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg.per_second \
       > $out/${tag}_ncu_full.txt 2>&1; head -5 $out/${tag}_ncu_full.txt; }
 # 7. the written-but-unmeasured variants: full GPU suite and the bench with them switched on
-run 7 "experimental variants (EW_HOIST, WGRAD_STREAM, TC_SPLITK)" && {
-  HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1 HMGAN_TC_SPLITK=1 HMGAN_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q \
+run 7 "experimental variants (EW_HOIST, WGRAD_STREAM, TC_SPLITK, C1_EPI2)" && {
+  HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1 HMGAN_TC_SPLITK=1 HMGAN_C1_EPI2=1 HMGAN_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q \
       > $out/${tag}_pytest_gpu_experimental.log 2>&1; tail -3 $out/${tag}_pytest_gpu_experimental.log
-  for v in "HMGAN_EW_HOIST=1" "HMGAN_WGRAD_STREAM=1" "HMGAN_TC_SPLITK=1" "HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1 HMGAN_TC_SPLITK=1"; do
+  for v in "HMGAN_EW_HOIST=1" "HMGAN_WGRAD_STREAM=1" "HMGAN_TC_SPLITK=1" "HMGAN_C1_EPI2=1" "HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1 HMGAN_TC_SPLITK=1 HMGAN_C1_EPI2=1"; do
     echo "[gpu_round] bench with $v"
     env $v timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | \
         python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['e2e']['value'])"
