@@ -10,6 +10,7 @@
 #   4. bench.py --workload both (joint step)            -> gpurun_out/<tag>_bench_joint.json
 #   5. ncu launch list of one bench step                -> gpurun_out/<tag>_launches.csv  (+ per-kernel summary .txt)
 #   6. ncu --set full of the dominant kernels           -> gpurun_out/<tag>_ncu_full.txt  (tools/tc_probe.py perf)
+#   8. ncu --set full of one eager step's HBM-side kernels -> gpurun_out/<tag>_ncu_step.{ncu-rep,txt}
 #   7. opt-in variants not yet measured (A/B)           -> gpurun_out/<tag>_pytest_gpu_experimental.log, _bench_experimental.txt
 # Skip stages with SKIP="1 6" (space-separated numbers).  Numbers printed under ncu are never bench values.
 tag=${1:-rX}
@@ -32,6 +33,15 @@ run 6 "ncu --set full (dominant kernels)" && {
   ncu -i $out/${tag}_ncu_full.ncu-rep --page raw --csv \
       --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg.per_second \
       > $out/${tag}_ncu_full.txt 2>&1; head -5 $out/${tag}_ncu_full.txt; }
+# 8 (listed first so that SKIP numbering stays stable). `ncu --set full` of the HBM-side and row-box kernels of ONE eager
+# training step (tools/op_times.py runs two warm-up steps, then one; 36 matching launches per step): the input for the
+# next fusions
+run 8 "ncu --set full, one eager step, HBM-side kernels" && {
+  timeout 900 ncu --set full --clock-control none -k regex:'c1s2|bn_bwd|maxpool2_bwd|tc_conv_rb' --launch-skip 72 -c 36 \
+      -o $out/${tag}_ncu_step -f python tools/op_times.py > $out/${tag}_ncu_step.log 2>&1
+  ncu -i $out/${tag}_ncu_step.ncu-rep --page raw --csv \
+      --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__grid_size,launch__registers_per_thread \
+      > $out/${tag}_ncu_step.txt 2>&1; head -5 $out/${tag}_ncu_step.txt; }
 # 7. the written-but-unmeasured variants: full GPU suite and the bench with them switched on
 run 7 "experimental variants (EW_HOIST, WGRAD_STREAM, TC_SPLITK, C1_EPI2)" && {
   HMGAN_EW_HOIST=1 HMGAN_WGRAD_STREAM=1 HMGAN_TC_SPLITK=1 HMGAN_C1_EPI2=1 HMGAN_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q \
