@@ -33,11 +33,13 @@ def _nl(name):
     return {"linear": L.linear, "tanh": L.tanh, "sigmoid": L.sigmoid}[name]
 
 
-def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with_p2p=True, seed=2, device="cpu"):
+def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with_p2p=True, seed=2, device="cpu",
+               lsgan=True, reconstruction='l1'):
     """The same seeded weights in the oracle and in the product model."""
     which = ('G', 'D', 'P', 'Dp') if with_p2p else ('G', 'D')
     nets = S.build_nets(cfg, seed=seed, which=which)
-    om = S.OracleModel(nets, alpha=100., opt=opt, lr=lr, train_mode=train_mode, lsgan=True)
+    om = S.OracleModel(nets, alpha=100., opt=opt, lr=lr, train_mode=train_mode, lsgan=lsgan,
+                       reconstruction=reconstruction)
     dp = dict(cfg['D'])
     dp['nonlinearity'] = _nl(dp['nonlinearity'])
     kw = dict(gen_fn_dcgan=dcgan.default_generator, disc_fn_dcgan=dcgan.default_discriminator,
@@ -49,7 +51,7 @@ def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with
         dpp['act'] = _nl(dpp['act'])
         kw.update(gen_fn_p2p=p2p.g_unet, disc_fn_p2p=p2p.discriminator, gen_params_p2p=pp, disc_params_p2p=dpp)
     m = Pix2Pix(in_shp=cfg['in_shp'], latent_dim=cfg['latent_dim'], is_a_grayscale=True, is_b_grayscale=False,
-                lsgan=True, opt=L.rmsprop if opt == "rmsprop" else L.adam,
+                lsgan=lsgan, reconstruction=reconstruction, opt=L.rmsprop if opt == "rmsprop" else L.adam,
                 opt_args={'learning_rate': L.shared(L.floatX(lr))}, train_mode=train_mode, verbose=False,
                 device=device, precision=precision, seed=0, **kw)
     for k, net in (('G', m.G), ('D', m.D), ('P', m.P), ('Dp', m.Dp)):
@@ -375,3 +377,27 @@ def test_raw_uint8_batches_give_the_step_of_the_host_normalised_batches(cpu_back
     np.testing.assert_array_equal(outs[0][3], outs[1][3])
     with pytest.raises(ValueError):
         m.train_fn(Z, Xu[:, :256], Yu)          # wrong image size
+
+
+def test_reference_default_objective_adam_and_cross_entropy(cpu_backend):
+    """The Pix2Pix constructor's own defaults (reference pix2pix.py:24-31): opt=adam, lsgan=False (binary
+    cross-entropy on sigmoid discriminators), here with reconstruction='l2' -- the experiments override all three, so
+    nothing else exercises hm_adam, the cross-entropy branch of hm_adv_loss and the L2 branch of hm_recon_loss against
+    the oracle.  Two steps (Adam's bias correction depends on the step count)."""
+    cfg = dict(TINY)
+    cfg['D'] = dict(TINY['D'], nonlinearity='sigmoid')
+    cfg['Dp'] = dict(TINY['Dp'], act='sigmoid')
+    om, m = build_pair(cfg, 'both', opt="adam", lr=2e-4, lsgan=False, reconstruction='l2')
+    for it in range(2):
+        Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=30 + it)
+        lo = om.train_fn(Z, X, Y)
+        lm = m.train_fn(Z, X, Y)
+        np.testing.assert_allclose(lm, lo, rtol=1e-3, atol=1e-6)
+    # Adam's first steps are ~lr * sign(g) whatever |g| is, so elements whose gradient is rounding noise (G's, through the
+    # max-pool argmax ties described above) move by +-lr in either implementation: compare robustly -- the second
+    # step's losses above already agree to 1e-3 -- by the fraction of elements further apart than half a step
+    for k, net in (('G', m.G), ('D', m.D), ('P', m.P), ('Dp', m.Dp)):
+        a = np.concatenate([x.ravel() for x in om.get_all_param_values(k)])
+        b = np.concatenate([x.ravel() for x in net.get_all_param_values()])
+        far = float((np.abs(a - b) > 1e-4).mean())
+        assert far < (0.03 if k == 'G' else 2e-3), (k, far)
