@@ -50,3 +50,16 @@ def test_weight_gradients_on_a_side_stream_change_nothing(case, monkeypatch):
     np.testing.assert_allclose(l1, l0, rtol=tol, atol=1e-5)
     for a, b in zip(p0, p1):
         np.testing.assert_allclose(b, a, rtol=0, atol=5e-3 * (np.abs(a).max() + 1e-6))
+
+
+def test_default_objective_adam_cross_entropy_l2_on_the_gpu():
+    """GPU counterpart of tests/test_engine_cpu.py::test_reference_default_objective_adam_and_cross_entropy (written
+    after the last GPU visit of round 1; move to tests/test_step_gpu.py once it has run)."""
+    from test_engine_cpu import TINY
+    cfg = dict(TINY)
+    cfg['D'] = dict(TINY['D'], nonlinearity='sigmoid')
+    cfg['Dp'] = dict(TINY['Dp'], act='sigmoid')
+    om, m = build_pair(cfg, 'both', opt="adam", lr=2e-4, lsgan=False, reconstruction='l2', device="cuda")
+    for it in range(2):
+        Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=30 + it)
+        np.testing.assert_allclose(m.train_fn(Z, X, Y), om.train_fn(Z, X, Y), rtol=1e-3, atol=1e-6)
