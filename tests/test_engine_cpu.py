@@ -401,3 +401,17 @@ def test_reference_default_objective_adam_and_cross_entropy(cpu_backend):
         b = np.concatenate([x.ravel() for x in net.get_all_param_values()])
         far = float((np.abs(a - b) > 1e-4).mean())
         assert far < (0.03 if k == 'G' else 2e-3), (k, far)
+
+
+def test_num_repeats_adds_convolutions_per_level(cpu_backend):
+    """num_repeats=1 (reference dcgan.py:21-22,41-42: an extra conv -> [BN] -> LReLU block per resolution; 0 in every
+    experiment) lowers and trains like the oracle.  G's gradient goes through twice as many layers of D here; its
+    tolerance is the joint test's (float32 rounding decides a few max-pool argmax ties differently)."""
+    cfg = S.experiment_kwargs('gate64')
+    cfg['G'] = dict(cfg['G'], num_repeats=1)
+    cfg['D'] = dict(cfg['D'], num_repeats=1)
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False)
+    assert len(m.G.get_all_param_values()) == 2 + 4 + 6 * 8 + 2 and len(m.D.get_all_param_values()) == 2 * 8 + 2
+    Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=6)
+    np.testing.assert_allclose(m.train_fn(Z, X, Y)[:2], om.train_fn(Z, X, Y)[:2], rtol=1e-4, atol=1e-6)
+    _check_grads(om, m, ('G', 'D'), 1e-3, {'G': 1e-2})
