@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhmgan.so")
 
-F32, F16 = 0, 1
+F32, F16, BF16X3 = 0, 1, 2
 ACT = {"linear": 0, "leaky_rectify": 1, "rectify": 2, "sigmoid": 3, "tanh": 4}
 UP_NONE, UP_NEAREST2, UP_BILINEAR2 = 0, 1, 2
 
@@ -41,6 +41,7 @@ _PROTOS = {
     "hm_tc_conv": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_conv_ws": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P], C.c_int),
     "hm_tc_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
+    "hm_split_bf16x3": ([_P, _P, _LL, _I, _I, _I, _P], C.c_int),
     "hm_up2conv_wgrad_phases": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
     "hm_im2col_c1": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_s2d_pad64": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
@@ -77,6 +78,8 @@ _PROTOS = {
     "hm_recon_loss": ([_P, _P, _P, _I, _LL, _I, _F, _F, _I, _P, _P], C.c_int),
     "hm_rmsprop": ([_P, _P, _P, _LL, _P, _F, _F, _F, _P], C.c_int),
     "hm_adam": ([_P, _P, _P, _P, _LL, _P, _F, _F, _F, _I, _F, _P], C.c_int),
+    "hm_adam_dev": ([_P, _P, _P, _P, _LL, _P, _F, _F, _F, _P, _F, _P], C.c_int),
+    "hm_inc_i32": ([_P, _P], C.c_int),
 }
 
 _lib = None

@@ -267,147 +267,6 @@ __global__ void __launch_bounds__(C1_THREADS, 1)
   }
 }
 
-// The same kernel with TWO epilogue warp groups, one per TMEM accumulator (opt-in: HMGAN_C1_EPI2=1; written because the
-// pooled epilogue -- 256 accumulator columns -> max / argmax / bias / activation per row, one warp per scheduler with the
-// tcgen05.ld latency exposed -- takes several times the 384 cycles of a tile's MMAs; not yet measured on B200).
-constexpr int C1_THREADS_E2 = C1_THREADS + 128;
-__global__ void __launch_bounds__(C1_THREADS_E2, 1)
-    c1s2_conv_e2_kernel(const __grid_constant__ CUtensorMap tmW, const C1Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t w_bytes = (uint32_t)p.N * 128u;
-  const uint32_t a_off = w_bytes;
-  const uint32_t patch_off = a_off + C1_STAGES * C1_A_BYTES;
-  const uint32_t ctrl_off = patch_off + 2 * C1_PATCH_WORDS * 4;
-  const uint32_t ctrl = base + ctrl_off;
-  const uint32_t w_full = ctrl;
-  auto a_full = [&](int s) { return ctrl + 8u * (1 + s); };
-  auto a_empty = [&](int s) { return ctrl + 8u * (1 + C1_STAGES + s); };
-  auto t_full = [&](int a) { return ctrl + 8u * (1 + 2 * C1_STAGES + a); };
-  auto t_empty = [&](int a) { return ctrl + 8u * (3 + 2 * C1_STAGES + a); };
-  const uint32_t tmem_slot = ctrl + 8u * (5 + 2 * C1_STAGES);
-  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gbase + ctrl_off + 8 * (5 + 2 * C1_STAGES));
-  float* bias_s = (float*)(gbase + ctrl_off + 256);
-  uint32_t* patch = (uint32_t*)(gbase + patch_off);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = p.pool ? 512u : 128u;
-  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
-  if (threadIdx.x == 0) {
-    mbar_init(w_full, 1);
-    for (int s = 0; s < C1_STAGES; s++) {
-      mbar_init(a_full(s), 128);
-      mbar_init(a_empty(s), 1);
-    }
-    for (int a = 0; a < 2; a++) {
-      mbar_init(t_full(a), 1);
-      mbar_init(t_empty(a), 4);
-    }
-    mbar_fence_init();
-    prefetch_tensormap(&tmW);
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-  if (warp >= 1 && warp <= 4) {            // zero the operand stages once: chunk 5 and the tail of chunk 4 stay zero
-    uint4* a4 = reinterpret_cast<uint4*>(gbase + a_off);
-    for (int i = threadIdx.x - 32; i < C1_STAGES * C1_A_BYTES / 16; i += 128) a4[i] = make_uint4(0, 0, 0, 0);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_p;
-  const int per_img = p.tiles_x * p.tiles_y;
-
-  if (warp == 0) {
-    // ===================== weights + MMA issuer =====================
-    if (elect_one()) {
-      mbar_expect_tx(w_full, w_bytes);
-      tma_load_2d(&tmW, base, w_full, 0, 0);
-      mbar_wait(w_full, 0);
-      const uint32_t idesc = idesc_f16(p.N);
-      const uint64_t bd = desc_k_sw128(base);
-      const int accstride = p.pool ? 256 : 64;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
-        const int s = it % C1_STAGES, ph = (it / C1_STAGES) & 1, acc = it & 1;
-        mbar_wait(t_empty(acc), ((it >> 1) & 1) ^ 1);
-        mbar_wait(a_full(s), ph);
-        tc_fence_after();
-        const uint64_t ad = desc_k_sw128(base + a_off + s * C1_A_BYTES);
-#pragma unroll
-        for (int k = 0; k < 3; k++)            // K = 48 = taps 0..35 + zero padding; +32 B per K=16 slice
-          tc_mma_f16(tmem_base + acc * accstride, ad + 2 * k, bd + 2 * k, idesc, k != 0);
-        tc_commit(a_empty(s));
-        tc_commit(t_full(acc));
-      }
-    }
-  } else if (warp <= 4) {
-    // ===================== builders =====================
-    const int tb = threadIdx.x - 32;
-    const int iy = tb / p.bw, ix = tb - iy * p.bw;
-    const int PWW = p.bw + 2, n_words = (2 * p.bh + 4) * PWW;
-    uint32_t pre[C1_PRE];
-    auto prefetch = [&](int t) {
-      const int b = t / per_img, rem = t - b * per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int Y0 = 2 * ty * p.bh - 2, X0 = 2 * tx * p.bw - 2;
-      const __half* img = p.x + (size_t)b * p.H * p.W;
-#pragma unroll
-      for (int j = 0; j < C1_PRE; j++) {
-        const int i = tb + 128 * j;
-        uint32_t v = 0;
-        if (i < n_words) {
-          const int pr = i / PWW, pw = i - pr * PWW;
-          const int Y = Y0 + pr, X = X0 + 2 * pw;
-          if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
-        }
-        pre[j] = v;
-      }
-    };
-    int t = blockIdx.x;
-    if (t < p.n_tiles) prefetch(t);
-    int it = 0;
-    for (; t < p.n_tiles; t += gridDim.x, it++) {
-      uint32_t* pb = patch + (it & 1) * C1_PATCH_WORDS;
-#pragma unroll
-      for (int j = 0; j < C1_PRE; j++) {
-        const int i = tb + 128 * j;
-        if (i < n_words) pb[i] = pre[j];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (t + (int)gridDim.x < p.n_tiles) prefetch(t + gridDim.x);
-      const int s = it % C1_STAGES, ph = (it / C1_STAGES) & 1;
-      mbar_wait(a_empty(s), ph ^ 1);
-      uint32_t wd[20];
-#pragma unroll
-      for (int u = 0; u < 6; u++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) wd[u * 3 + j] = pb[(2 * iy + u) * PWW + ix + j];
-      wd[18] = wd[19] = 0;
-      uint8_t* arow = gbase + a_off + s * C1_A_BYTES;
-#pragma unroll
-      for (int c = 0; c < 5; c++)
-        *reinterpret_cast<uint4*>(arow + sw128_off(tb, c)) = make_uint4(wd[4 * c], wd[4 * c + 1], wd[4 * c + 2], wd[4 * c + 3]);
-      fence_proxy_async();
-      mbar_arrive(a_full(s));
-    }
-  } else {
-    // ===================== epilogue: warps 5..8 drain accumulator 0 (even tiles), warps 9..12 accumulator 1 =========
-    const int eg = (warp - 5) >> 2;
-    switch (p.act) {
-      case HM_ACT_LRELU: c1_epilogue<HM_ACT_LRELU>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane, eg, 2); break;
-      case HM_ACT_RELU: c1_epilogue<HM_ACT_RELU>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane, eg, 2); break;
-      default: c1_epilogue<HM_ACT_LINEAR>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane, eg, 2); break;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
-  }
-}
-
 typedef CUresult (*C1EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -481,25 +340,6 @@ extern "C" int hm_c1s2_conv(const void* x, const void* wk, const float* bias, vo
     attr = true;
   }
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  static int epi2 = -1;
-  if (epi2 < 0) {
-    const char* e = getenv("HMGAN_C1_EPI2");               // opt-in until measured on B200
-    epi2 = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (epi2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(c1s2_conv_e2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      if (e != cudaSuccess) {
-        set_error("hm_c1s2_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-        return HM_ERR_CUDA;
-      }
-      attr2 = true;
-    }
-    c1s2_conv_e2_kernel<<<grid, C1_THREADS_E2, smem, (cudaStream_t)stream>>>(tmW, p);
-    HM_CHECK_LAUNCH("hm_c1s2_conv(two epilogue groups)");
-    return HM_OK;
-  }
   c1s2_conv_kernel<<<grid, C1_THREADS, smem, (cudaStream_t)stream>>>(tmW, p);
   HM_CHECK_LAUNCH("hm_c1s2_conv");
   return HM_OK;

@@ -1142,6 +1142,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// adam with the step count in DEVICE memory (so that a captured CUDA graph advances it on every replay)
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, const float* __restrict__ lr_p, float b1, float b2,
+                                float eps, const int* __restrict__ t_p, float gscale) {
+  const float t = (float)*t_p;
+  const float a_t = *lr_p * (sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t)));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - a_t * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void inc_i32_kernel(int* t) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *t += 1;
+}
+
 }  // namespace hm
 
 using namespace hm;
@@ -1579,5 +1599,20 @@ extern "C" int hm_adam(float* p, const float* g, float* m, float* v, long long n
   float corr = sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
   adam_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, corr, gscale);
   HM_CHECK_LAUNCH("hm_adam");
+  return HM_OK;
+}
+
+extern "C" int hm_inc_i32(int* counter, void* stream) {
+  HM_CHECK_ARG(counter, "hm_inc_i32: null pointer");
+  inc_i32_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counter);
+  HM_CHECK_LAUNCH("hm_inc_i32");
+  return HM_OK;
+}
+
+extern "C" int hm_adam_dev(float* p, const float* g, float* m, float* v, long long n, const float* lr, float b1,
+                           float b2, float eps, const int* t_dev, float gscale, void* stream) {
+  HM_CHECK_ARG(p && g && m && v && lr && t_dev && n > 0, "hm_adam_dev: bad argument");
+  adam_dev_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, t_dev, gscale);
+  HM_CHECK_LAUNCH("hm_adam_dev");
   return HM_OK;
 }

@@ -50,6 +50,8 @@ struct TcParams {
   int d2s;                 // 1: nearest-2x + 5x5 as four 3x3 phase convolutions: N = (phase, co), the epilogue scatters
                            //    phase (py,px) of low-res pixel (qy,qx) to output pixel (2qy+py, 2qx+px)
   int cph;                 // channels per phase (= real Cout) when d2s
+  int bf16;                // operands are bfloat16 (HM_BF16X3: hi/lo splits of fp32 tensors) instead of fp16
+  int out32;               // y / y2 are float tensors (HM_BF16X3): the fp32 accumulator is stored unrounded
 };
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -159,6 +161,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
+// the same with A,B = BF16 (a_format, b_format = 1 at bits 7 and 10) when bf16 != 0
+__host__ __device__ constexpr uint32_t umma_idesc_16(int n, int bf16) {
+  return umma_idesc_f16(n) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u);
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_t(float v, float slope) {
@@ -185,12 +191,45 @@ __device__ __forceinline__ void epi_pack32(const uint32_t* v, const float* bias3
   }
 }
 
+// HM_BF16X3 epilogue: up to 32 accumulator columns -> (+ stored value) + bias -> activation -> FLOAT stores (the fp32
+// accumulator is kept unrounded: the operands were bf16 hi/lo splits of fp32 tensors, see hm_split_bf16x3)
+template <int ACT>
+__device__ __forceinline__ void epi_store32_f32(float* dst, const uint32_t* v, const float* bias32, float slope,
+                                                int ncols, bool accum, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < ncols) {
+        const float4 b = *reinterpret_cast<const float4*>(bias32 + j);
+        float4 o = make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                               __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
+        if (accum) {
+          const float4 pv = *reinterpret_cast<const float4*>(dst + j);
+          o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
+        }
+        o.x = act_fwd(o.x, ACT, slope); o.y = act_fwd(o.y, ACT, slope);
+        o.z = act_fwd(o.z, ACT, slope); o.w = act_fwd(o.w, ACT, slope);
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      if (j < ncols) {
+        float a = __uint_as_float(v[j]) + bias32[j];
+        if (accum) a += dst[j];
+        dst[j] = act_fwd(a, ACT, slope);
+      }
+    }
+  }
+}
+
 // The whole epilogue role: for every tile of this CTA wait for the accumulator, drain it, release it.
 // pair_rank < 0: single-CTA kernels (work items blockIdx.x, +gridDim.x, ...; tempty0 is a local barrier).
 // pair_rank = 0/1: CTA pair (cta_group::2): work items are shared by the pair, this CTA owns sub-tiles
 // [ (2*st + rank)*S, +S ) of super tile st, and releases the accumulator on the LEADER's barrier (tempty0 is then a
 // shared::cluster address).
-template <int ACT>
+template <int ACT, bool OUT32 = false>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               const float* bias_s, int warp, int lane, int total_tiles,
                                               int pair_rank = -1) {
@@ -234,6 +273,28 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         tmem_ld_wait();
         if (!valid) continue;
         const int gc = col0 + c0;
+        if (OUT32) {
+          float* y32 = reinterpret_cast<float*>(p.y);
+          if (p.cph % 32 == 0) {
+            const int ph = gc / p.cph, co = gc - ph * p.cph;
+            const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+            epi_store32_f32<ACT>(y32 + op * p.cph + co, v, bias_t + c0, p.slope, min(32, p.ntile - c0),
+                                 (p.accumulate & 1) != 0, true);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const int col = gc + j;
+              if (col < 4 * p.cph) {
+                const int ph = col / p.cph, co = col - ph * p.cph;
+                const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
+                float a = __uint_as_float(v[j]) + bias_t[c0 + j];
+                if (p.accumulate & 1) a += y32[op * p.cph + co];
+                y32[op * p.cph + co] = act_fwd(a, ACT, p.slope);
+              }
+            }
+          }
+          continue;
+        }
         if (p.cph % 32 == 0) {
           const int ph = gc / p.cph, co = gc - ph * p.cph;
           const size_t op = ((size_t)((size_t)n * 2 * p.Ho + 2 * oy + (ph >> 1)) * (2 * p.Wo) + 2 * ox + (ph & 1));
@@ -288,6 +349,13 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         tmem_ld_wait();
         if (!store) continue;
         const int ncols = min(32, p.ntile - c0);
+        if (OUT32) {
+          float* d32 = second ? reinterpret_cast<float*>(p.y2) + pix * (p.Cout - p.split) + (col0 - p.split)
+                              : reinterpret_cast<float*>(p.y) + pix * p.split + col0;
+          epi_store32_f32<ACT>(d32 + c0, v, bias_t + c0, p.slope, p.vec_store ? ncols : min(ncols, p.Cout - col0 - c0),
+                               accum, p.vec_store != 0);
+          continue;
+        }
         if (p.vec_store) {
           uint32_t packed[16];
           if (accum) {                                        // y += : add the stored fp16 values in fp32 first
@@ -332,6 +400,31 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty0 + 8u * acc) : "memory");
     }
   }
+}
+
+// activation / output-type dispatch of the epilogue role
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                                  const float* bias_s, int warp, int lane, int total_tiles,
+                                                  int pair_rank = -1) {
+#define HM_EPI(A_, O_) epilogue_loop<A_, O_>(p, tmem_base, tfull0, tempty0, bias_s, warp, lane, total_tiles, pair_rank)
+  if (p.out32) {
+    switch (p.act) {
+      case HM_ACT_LRELU: HM_EPI(HM_ACT_LRELU, true); break;
+      case HM_ACT_RELU: HM_EPI(HM_ACT_RELU, true); break;
+      case HM_ACT_SIGMOID: HM_EPI(HM_ACT_SIGMOID, true); break;
+      case HM_ACT_TANH: HM_EPI(HM_ACT_TANH, true); break;
+      default: HM_EPI(HM_ACT_LINEAR, true); break;
+    }
+  } else {
+    switch (p.act) {
+      case HM_ACT_LRELU: HM_EPI(HM_ACT_LRELU, false); break;
+      case HM_ACT_RELU: HM_EPI(HM_ACT_RELU, false); break;
+      case HM_ACT_SIGMOID: HM_EPI(HM_ACT_SIGMOID, false); break;
+      case HM_ACT_TANH: HM_EPI(HM_ACT_TANH, false); break;
+      default: HM_EPI(HM_ACT_LINEAR, false); break;
+    }
+  }
+#undef HM_EPI
 }
 
 // One filter tap of the row-box kernels for NS sub-tiles, fully unrolled: NS*4 back-to-back MMAs.  Descriptors are
@@ -449,7 +542,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (elect_one()) {
       // single issuing lane; 32-bit descriptor arithmetic; the NEXT stage's barrier is polled right behind the MMAs of
       // the current one (the tensor pipe queues only a few MMAs: tools/mma_rate.cu)
-      const uint32_t idesc = umma_idesc_f16(p.ntile);
+      const uint32_t idesc = umma_idesc_16(p.ntile, p.bf16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -484,13 +577,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    switch (p.act) {
-      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-    }
+    epilogue_dispatch(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -516,7 +603,7 @@ __device__ __forceinline__ void rb_mma_role_unrolled(const TcParams& p, uint32_t
   const uint32_t afull0 = ctrl, aempty0 = ctrl + 8u * p.a_slots, bfull0 = ctrl + 8u * (2 * p.a_slots),
                  bempty0 = ctrl + 8u * (2 * p.a_slots + p.b_slots), tfull0 = ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots),
                  tempty0 = tfull0 + 16u;
-  const uint32_t idesc = umma_idesc_f16(p.ntile);
+  const uint32_t idesc = umma_idesc_16(p.ntile, p.bf16);
   const uint32_t a_sub = (uint32_t)p.rb_bytes >> 4, b_sub = b_slot_bytes >> 4;
   const uint32_t a_lo_base = umma_lo_of(base), b_lo_base = umma_lo_of(b_base);
   const int ring_rows = p.b_slots / KW;
@@ -693,7 +780,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
 #undef RB_ROLE
     } else if (!unrolled && elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(p.ntile);
+      const uint32_t idesc = umma_idesc_16(p.ntile, p.bf16);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
@@ -740,13 +827,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     __syncwarp();
   } else {
-    switch (p.act) {
-      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles); break;
-    }
+    epilogue_dispatch(p, tmem_base, tfull_bar(0), tempty_bar(0), bias_s, warp, lane, total_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -958,13 +1039,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     }
   } else {
     const uint32_t lead_tempty = mapa_shared(tempty_bar(0), 0);
-    switch (p.act) {
-      case HM_ACT_LRELU: epilogue_loop<HM_ACT_LRELU>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
-      case HM_ACT_RELU: epilogue_loop<HM_ACT_RELU>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
-      case HM_ACT_SIGMOID: epilogue_loop<HM_ACT_SIGMOID>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
-      case HM_ACT_TANH: epilogue_loop<HM_ACT_TANH>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
-      default: epilogue_loop<HM_ACT_LINEAR>(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank); break;
-    }
+    epilogue_dispatch(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank);
   }
   tc_fence_before();
   __syncthreads();
@@ -1080,7 +1155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(p.ntile);
+      const uint32_t idesc = umma_idesc_16(p.ntile, p.bf16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -1306,16 +1381,19 @@ static bool is_deconv_d2s(const HmConvDesc* d) {
          d->split == d->Cout && !d->accumulate;
 }
 
+// fp16 tensors, or bf16 hi/lo splits of fp32 tensors with float results (HM_BF16X3, hm_split_bf16x3)
+static inline bool tc_dtype_ok(int dt) { return dt == HM_F16 || dt == HM_BF16X3; }
+
 extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   if (!d) return 0;
-  if (d->dtype == HM_F16 && is_deconv_d2s(d))
+  if (tc_dtype_ok(d->dtype) && is_deconv_d2s(d))
     return d->C1 % KCH == 0 && d->C2 % KCH == 0 && d->C1 > 0 && (d->Cout % 32 == 0 || d->Cout <= 4) && 4 * d->Cout <= 2048;
-  if (d->dtype == HM_F16 && is_up2conv(d))
+  if (tc_dtype_ok(d->dtype) && is_up2conv(d))
     return d->C1 % KCH == 0 && d->C1 > 0 && d->os == 1 && !d->ou && !d->ov && d->oH == d->Ho && d->oW == d->Wo;
-  if (d->dtype == HM_F16 && is_dgrad_s2(d))
+  if (tc_dtype_ok(d->dtype) && is_dgrad_s2(d))
     return d->C1 % KCH == 0 && d->C1 > 0 && d->C2 == 0 && d->os == 1 && !d->ou && !d->ov && d->oH == d->Ho &&
            d->oW == d->Wo && d->split == d->Cout && (d->Cout % 32 == 0 || d->Cout <= 4);
-  if (d->dtype != HM_F16 || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
+  if (!tc_dtype_ok(d->dtype) || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
   if (d->stride == 2) {
     if (d->Ho != (d->H + 2 * d->pad - d->kh) / 2 + 1 || d->Wo != (d->W + 2 * d->pad - d->kw) / 2 + 1) return 0;
     if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
@@ -1353,7 +1431,7 @@ static int splitk_factor(long long tiles, int ksteps) {
 // Bytes of zeroed fp32 workspace hm_tc_conv_ws may use for this problem: 0 when the split-K variant would not be chosen
 // (switched off, unsupported shape, or enough tiles to fill the machine).  An upper bound that depends on d alone.
 extern "C" long long hm_tc_conv_ws_bytes(const HmConvDesc* d) {
-  if (!d || !splitk_enabled() || !hm_tc_conv_supported(d)) return 0;
+  if (!d || !splitk_enabled() || d->dtype != HM_F16 || !hm_tc_conv_supported(d)) return 0;
   const bool phase = is_up2conv(d) || is_dgrad_s2(d) || is_deconv_d2s(d);
   const long long gh = phase ? d->H : d->Ho, gw = phase ? d->W : d->Wo;        // tile grid
   if (gw >= TILE_M) return 0;                                                   // row-box kernels take those layers
@@ -1445,6 +1523,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   p.stages = stages;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y; p.y2 = (__half*)y2;
   p.split = up2 ? p.Cout : d->split; p.accumulate = d->accumulate;
+  p.bf16 = p.out32 = d->dtype == HM_BF16X3 ? 1 : 0;
 
   CUtensorMap tmA, tmA2, tmB;
   int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn, p.stride);
@@ -1469,7 +1548,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
     const char* e = getenv("HMGAN_TC_PAIR");
     pair_enabled = (e && e[0] == '1') ? 1 : 0;
   }
-  if (rb_enabled && pair_enabled && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9 &&
+  if (rb_enabled && pair_enabled && !p.bf16 && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9 &&
       p.ntile >= 64 && p.ntile % 32 == 0 && (num_sms() % 2) == 0) {
     TcParams q = p;
     int S2 = 256 / q.ntile;
@@ -1570,7 +1649,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
       return HM_OK;
     }
   }
-  if (ws && splitk_enabled()) {
+  if (ws && splitk_enabled() && !p.bf16) {
     const int ksteps = p.kh * p.kw * (p.Cin / KCH);
     const int ksplit = splitk_factor((long long)p.n_mtiles * p.n_ntiles, ksteps);
     const size_t need = (size_t)d->B * p.Ho * p.Wo * (size_t)(p.n_ntiles * p.ntile) * 4;

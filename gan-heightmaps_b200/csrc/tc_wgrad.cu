@@ -37,6 +37,7 @@ struct WgParams {
   int a_slots, b_slots;
   float* dw;            // [units*64][pitch] fp32; this launch fills columns [n_off, n_off + Cout)
   int n_off, pitch;     // N tiling when the layer has more than 256 output channels
+  int bf16;             // operands are bfloat16 (HM_BF16X3: batch-stacked hi/lo splits of fp32 tensors) instead of fp16
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   } else if (warp == 1) {
     if (wg_elect_one()) {
       // single issuing lane, 32-bit descriptor arithmetic, the NEXT step's barriers polled right behind the MMAs
-      const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
+      const uint32_t idesc = umma_idesc_f16_mn(p.Cout) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       constexpr uint32_t HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);    // SBO 1024 B, version 1, SWIZZLE_128B
       constexpr uint32_t LBO = (uint32_t)(BLK_BYTES >> 4) << 16;
       int as = 0, bs = 0;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       // The tensor pipe queues only a few MMAs (tools/mma_rate.cu), so the issuing lane must not pause between groups:
       // the per-M-tile operand offsets (which need integer divisions) are computed ONCE, descriptors are 32-bit adds,
       // and the barriers of the NEXT pixel tile are polled right behind the MMAs of the current one.
-      const uint32_t idesc = umma_idesc_f16_mn(p.Cout);
+      const uint32_t idesc = umma_idesc_f16_mn(p.Cout) | (p.bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       const int nmt = mt1 - mt0;                                       // <= 8 accumulators (512 / Cout)
       uint32_t rel[8];                                                 // (offset in the A slot >> 4) | (LBO >> 4) << 16
 #pragma unroll
@@ -512,7 +513,7 @@ using namespace hm;
 
 extern "C" int hm_tc_wgrad_supported(const HmConvDesc* d) {
   if (!d) return 0;
-  if (d->dtype != HM_F16 || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
+  if ((d->dtype != HM_F16 && d->dtype != HM_BF16X3) || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
   if (d->os != 1 || d->ou || d->ov) return 0;
   if (d->C1 % 64 || d->C2 % 64 || d->C1 <= 0) return 0;
   if (d->Cout % 64 || d->Cout <= 0 || (d->Cout > 256 && d->Cout % 256)) return 0;
@@ -558,6 +559,7 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
   p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
   p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = ntile;
   p.n_off = n_off; p.pitch = d->Cout;
+  p.bf16 = d->dtype == HM_BF16X3 ? 1 : 0;
   p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
   p.bw = wg_pow2_floor(d->Wo < 128 ? d->Wo : 128);
   p.bh = wg_pow2_floor(d->Ho < 128 / p.bw ? d->Ho : 128 / p.bw);

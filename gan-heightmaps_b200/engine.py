@@ -42,13 +42,20 @@ class Runtime(object):
 
     def __init__(self, device="cuda", precision="parity", loss_scale=None):
         self.device = torch.device(device)
-        if precision not in ("parity", "fast"):
-            raise ValueError("precision must be 'parity' (fp32) or 'fast' (fp16 storage, fp32 accumulate)")
+        if precision not in ("parity", "fast", "tc32"):
+            raise ValueError("precision must be 'parity' (fp32, SIMT kernels), 'tc32' (fp32 storage, the tcgen05 kernels on "
+                             "three-plane bf16 operand splits: float32-grade) or 'fast' (fp16 storage, fp32 accumulate)")
         self.precision = precision
-        self.cd = _lib.F32 if precision == "parity" else _lib.F16
-        self.tdtype = torch.float32 if precision == "parity" else torch.float16
+        self.cd = _lib.F16 if precision == "fast" else _lib.F32
+        self.tdtype = torch.float16 if precision == "fast" else torch.float32
+        # tc: GEMM-shaped convolutions run on the tcgen05 kernels; split: their operands are three-plane bf16 splits of the
+        # fp32 tensors (HM_BF16X3, csrc/split_bf16.cu) and their results fp32 -- the mode the 1e-3 parity gate runs in
+        self.tc = precision in ("fast", "tc32")
+        self.split = precision == "tc32"
+        self.tc_dtype = torch.bfloat16 if self.split else self.tdtype
+        self._scratch = {}
         if loss_scale is None:
-            loss_scale = 1.0 if precision == "parity" else 1024.0
+            loss_scale = 1024.0 if precision == "fast" else 1.0
         self.loss_scale = float(loss_scale)
         self.launches = 0
         # SyncBN: a torch.distributed process group over which every BatchNorm layer averages its batch
@@ -59,6 +66,8 @@ class Runtime(object):
         self._pack_tables = {}
         self._wgrad_stream = None
         self._wgrad_forked = False
+        self._wgrad_side = (self.device.type == "cuda" and not self.split
+                            and os.environ.get("HMGAN_WGRAD_STREAM", "0") == "1")
         self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "0") == "1"
         self._tc_ws = None
         _lib.load()
@@ -82,7 +91,7 @@ class Runtime(object):
         the small layers' kernels fill a fraction of the 148 SMs, so issuing dW on a second stream lets it run beside
         the input-gradient chain of the layers below.  Net.backward joins the stream before it returns, so the fork is
         invisible to callers and is captured into the step's CUDA graph as ordinary cross-stream dependencies."""
-        if self.device.type != "cuda" or os.environ.get("HMGAN_WGRAD_STREAM", "0") != "1":
+        if not self._wgrad_side:
             return None
         if self._wgrad_stream is None:
             self._wgrad_stream = torch.cuda.Stream(self.device)
@@ -111,7 +120,77 @@ class Runtime(object):
                 return
         _lib.call(name, *args, self.stream)
 
+    # -- tensor-core entry points (fast: fp16 tensors as they are; tc32: three-plane bf16 splits of the fp32 tensors) -------- #
+    def scratch(self, key, nbytes):
+        """Reusable device scratch (launches on one stream are ordered, so one buffer per role serves every layer).
+        Grows only during the eager warm-up steps, never while a CUDA graph is captured."""
+        t = self._scratch.get(key)
+        if t is None or t.numel() < nbytes:
+            t = self._scratch[key] = torch.empty((int(nbytes),), dtype=torch.uint8, device=self.device)
+        return t.data_ptr()
+
+    def tc_desc(self, d, wgrad=False):
+        """The descriptor the tcgen05 entry points see: unchanged in fast mode; in tc32 mode the sources carry three
+        bf16 planes per fp32 channel, six along the reduction axis (forward / input gradient: the channels; weight
+        gradient: the batch)."""
+        if not self.split:
+            return d
+        d2 = _lib.ConvDesc.from_buffer_copy(d)
+        d2.dtype = _lib.BF16X3
+        if wgrad:
+            d2.B = 6 * d.B
+        else:
+            d2.C1, d2.C2 = 6 * d.C1, 6 * d.C2
+        return d2
+
+    def tc_supported(self, d, wgrad=False):
+        return bool(_lib.query("hm_tc_wgrad_supported" if wgrad else "hm_tc_conv_supported",
+                               C.byref(self.tc_desc(d, wgrad))))
+
+    def tc_conv(self, d, x1, x2, w, bias, y, y2):
+        """hm_tc_conv on the layer's tensors (device pointers)."""
+        if self.split:
+            rows = d.B * d.H * d.W
+            s1 = self.scratch("x1", rows * 6 * d.C1 * 2)
+            self.call("hm_split_bf16x3", x1, s1, rows, d.C1, d.C1, 0)
+            x1 = s1
+            if d.C2:
+                s2 = self.scratch("x2", rows * 6 * d.C2 * 2)
+                self.call("hm_split_bf16x3", x2, s2, rows, d.C2, d.C2, 0)
+                x2 = s2
+        self.call("hm_tc_conv", C.byref(self.tc_desc(d)), x1, x2, w, bias, y, y2)
+
+    def tc_wgrad(self, d, x1, x2, dy, dwp):
+        """hm_tc_wgrad on the layer's tensors (device pointers)."""
+        if self.split:
+            rows = d.B * d.H * d.W
+            s1 = self.scratch("x1", rows * 6 * d.C1 * 2)
+            self.call("hm_split_bf16x3", x1, s1, rows, d.C1, d.C1, 2)
+            x1 = s1
+            if d.C2:
+                s2 = self.scratch("x2", rows * 6 * d.C2 * 2)
+                self.call("hm_split_bf16x3", x2, s2, rows, d.C2, d.C2, 2)
+                x2 = s2
+            orow = d.B * d.Ho * d.Wo
+            sd = self.scratch("dy", orow * 6 * d.Cout * 2)
+            self.call("hm_split_bf16x3", dy, sd, orow, d.Cout, d.Cout, 3)
+            dy = sd
+        self.call("hm_tc_wgrad", C.byref(self.tc_desc(d, True)), x1, x2, dy, dwp)
+
+    def tc_pack(self, w, dst, mode, cout, cin, kh, kw, K, c1=None):
+        """K-major tensor-core weight pack (hm_pack_conv_weight modes 5/6/8/12/...; K = innermost extent of the pack).
+        tc32: packed in fp32 first, then split along K into the six b-side planes (per ConcatLayer segment when c1 < K)."""
+        if not self.split:
+            self.call("hm_pack_conv_weight", w, dst, mode, cout, cin, kh, kw, 0, 0, self.cd)
+            return
+        n = _lib.pack_count(mode, cout, cin, kh, kw)
+        tmp = self.scratch("pack", n * 4)
+        self.call("hm_pack_conv_weight", w, tmp, mode, cout, cin, kh, kw, 0, 0, _lib.F32)
+        self.call("hm_split_bf16x3", tmp, dst, n // K, K, K if c1 is None else c1, 1)
+
     def begin_pack_batch(self):
+        if self.split:              # the split reads the fp32 pack from a shared scratch buffer: keep program order
+            return
         self._pack_jobs = []
 
     def end_pack_batch(self):
@@ -228,17 +307,18 @@ class ConvOp(object):
         self.dg2_cat = False
         self.gcat = None
         self.dg2 = False      # input gradient of a 3x3 stride-2 conv as a 2x2-tap phase convolution of dy (pack mode 12)
-        if rt.precision == "fast" and kind == "conv" and self.stride in (1, 2):
+        if rt.tc and kind == "conv" and self.stride in (1, 2):
             if self.up == _lib.UP_NEAREST2 and self.x2 is None and self.stride == 1:
-                self.up2 = bool(_lib.query("hm_tc_conv_supported", C.byref(self._fwd_desc(rt, 1))))
-            self.tc_fwd = self.up2 or bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_fwd_desc(rt, 1))))
-            self.tc_wg = bool(_lib.query("hm_tc_wgrad_supported", C.byref(self._tc_fwd_desc(rt, 1))))
+                # (thin outputs take the fp16-only hm_s2d_pad64 route for their weight gradient: fast mode only)
+                self.up2 = (not rt.split or self.Cout > 4) and rt.tc_supported(self._fwd_desc(rt, 1))
+            self.tc_fwd = self.up2 or rt.tc_supported(self._tc_fwd_desc(rt, 1))
+            self.tc_wg = rt.tc_supported(self._tc_fwd_desc(rt, 1), wgrad=True)
             if self.stride == 1:
-                self.tc_dg = bool(_lib.query("hm_tc_conv_supported", C.byref(self._tc_dgrad_desc(rt, 1, 0))))
+                self.tc_dg = rt.tc_supported(self._tc_dgrad_desc(rt, 1, 0))
             elif not self.up:
                 dd = self._dgrad_desc(rt, 1, 0)
                 dd.split = dd.Cout
-                ok = bool(_lib.query("hm_tc_conv_supported", C.byref(dd)))
+                ok = rt.tc_supported(dd)
                 if self.x2 is None:
                     self.tc_dg = self.dg2 = ok
                 else:
@@ -302,19 +382,20 @@ class ConvOp(object):
             self.ubuf = rt.empty((B, self.Hv // 2, self.Wv // 2, 64))      # patch-space input gradient
             return          # no im2col tensor, no packed-gradient buffers: forward and backward are hm_c1s2_* calls
         n = self.K * self.Cout
+        tcm = 6 if rt.split else 1        # tc32: six bf16 planes (h m h l h m) per packed fp32 weight
         if self.col1 or self.colk:
             self.xc = rt.empty((B, self.out.shape[0], self.out.shape[1], 64))
             if self.wt_f is None:
                 self.wt_f = rt.empty((64 * self.Cout,))
                 self.dwp = rt.empty((64 * self.Cout,), torch.float32)
         if self.tc_fwd and self.wt_f is None:
-            self.wt_f = rt.empty((36 * self.Cin * self.Cout if self.up2 else n,))
+            self.wt_f = rt.empty((tcm * (36 * self.Cin * self.Cout if self.up2 else n),), rt.tc_dtype)
         if self.dg2_cat:
             self.gcat = rt.empty((B, self.Hv, self.Wv, self.Cin))
             if self.wt_d is None:
-                self.wt_d = rt.empty((16 * self.Cin * self.Cout,))
+                self.wt_d = rt.empty((tcm * 16 * self.Cin * self.Cout,), rt.tc_dtype)
         if self.tc_dg and self.wt_d is None:
-            self.wt_d = rt.empty((16 * self.Cin * self.Cout if self.dg2 else n,))
+            self.wt_d = rt.empty((tcm * (16 * self.Cin * self.Cout if self.dg2 else n),), rt.tc_dtype)
         self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient of the thin phase-decomposed layer
         if self.thin_up2_wg:
             # tensor cores: s2d(dy) zero-padded to 64 channels against the low-res source (3x3 taps)
@@ -345,19 +426,18 @@ class ConvOp(object):
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 0, self.Cout, self.Cin, self.kh, self.kw,
                         0, 0, rt.cd)
             else:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 8 if self.up2 else 5, self.Cout, self.Cin,
-                        self.kh, self.kw, 0, 0, rt.cd)
+                rt.tc_pack(_ptr(w), _ptr(self.wt_f), 8 if self.up2 else 5, self.Cout, self.Cin, self.kh, self.kw,
+                           self.Cin, self.C1)
             if self.c1dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 14, 1, self.Cin, 5, 5, 0, 0, rt.cd)
             if self.dg2_cat:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 12, self.Cout, self.Cin, self.kh, self.kw,
-                        0, 0, rt.cd)
+                rt.tc_pack(_ptr(w), _ptr(self.wt_d), 12, self.Cout, self.Cin, self.kh, self.kw, self.Cout)
             elif not self.tc_dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 7 if self.fw_dg else 1, self.Cout, self.Cin,
                         self.kh, self.kw, 0, 0, rt.cd)
             else:
-                rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 12 if self.dg2 else 6, self.Cout, self.Cin,
-                        self.kh, self.kw, 0, 0, rt.cd)
+                rt.tc_pack(_ptr(w), _ptr(self.wt_d), 12 if self.dg2 else 6, self.Cout, self.Cin, self.kh, self.kw,
+                           self.Cout)
         elif self.dc2:
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 17, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 18, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
@@ -508,7 +588,7 @@ class ConvOp(object):
         elif self.up2:
             self._xu_valid = False
             d = self._fwd_desc(rt, n)
-            rt.call("hm_tc_conv", C.byref(d), x1, None, _ptr(self.wt_f), bias, y, None)
+            rt.tc_conv(d, x1, None, _ptr(self.wt_f), bias, y, None)
         elif self.tc_fwd:
             if self.up:
                 self._xu_valid = True
@@ -518,7 +598,7 @@ class ConvOp(object):
                                 x.shape[1], c, self.up)
             u1, u2 = self._srcs(rt, lo, hi, True)
             d = self._tc_fwd_desc(rt, n)
-            rt.call("hm_tc_conv", C.byref(d), u1, u2, _ptr(self.wt_f), bias, y, None)
+            rt.tc_conv(d, u1, u2, _ptr(self.wt_f), bias, y, None)
         else:
             d = self._fwd_desc(rt, n)
             rt.call("hm_conv_gather", C.byref(d), x1, x2, _ptr(self.wp_f), bias, y, None)
@@ -620,7 +700,7 @@ class ConvOp(object):
                 self._xu_valid = True
             u1, u2 = self._srcs(rt, lo, hi, True)
             d = self._tc_fwd_desc(rt, n)
-            rt.call("hm_tc_wgrad", C.byref(d), u1, u2, _ptr(g), _ptr(self.dwp))
+            rt.tc_wgrad(d, u1, u2, _ptr(g), _ptr(self.dwp))
             mode = 0
         else:
             d = self._fwd_desc(rt, n)
@@ -673,7 +753,7 @@ class ConvOp(object):
             y2 = flat[n1:] if t2 else None
             if self.tc_dg:
                 d = self._tc_dgrad_desc(rt, n, 0)
-                rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, _ptr(y1), _ptr(y2))
+                rt.tc_conv(d, _ptr(g), None, _ptr(self.wt_d), None, _ptr(y1), _ptr(y2))
             else:
                 d = self._tc_dgrad_desc(rt, n, 0) if self.fw_dg else self._dgrad_desc(rt, n, 0)
                 rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, _ptr(y1), _ptr(y2))
@@ -690,7 +770,7 @@ class ConvOp(object):
                 d = self._dgrad_desc(rt, n, 0)
                 d.split = d.Cout
                 gc = self.gcat[lo:hi]
-                rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, _ptr(gc), None)
+                rt.tc_conv(d, _ptr(g), None, _ptr(self.wt_d), None, _ptr(gc), None)
                 M = n * self.Hv * self.Wv
                 if t1:
                     rt.call("hm_slice_channels", _ptr(gc), y1, rt.cd, M, self.Cin, 0, self.C1, acc & 1)
@@ -698,7 +778,7 @@ class ConvOp(object):
                     rt.call("hm_slice_channels", _ptr(gc), y2, rt.cd, M, self.Cin, self.C1, self.C2, (acc >> 1) & 1)
             elif self.tc_dg:
                 d = self._dgrad_desc(rt, n, acc) if self.dg2 else self._tc_dgrad_desc(rt, n, acc)
-                rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, y1, y2)
+                rt.tc_conv(d, _ptr(g), None, _ptr(self.wt_d), None, y1, y2)
             else:
                 d = self._tc_dgrad_desc(rt, n, acc) if self.fw_dg else self._dgrad_desc(rt, n, acc)
                 rt.call("hm_conv_gather", C.byref(d), _ptr(g), None, _ptr(self.wp_d), None, y1, y2)
@@ -881,6 +961,7 @@ class Net(object):
         self.sflat = rt.zeros((max(ns, 1),), torch.float32)
         self.opt_state = {}
         self.B = 0
+        self.generation = 0
         self._packed = False
         self.single_pass = False
         self.wscale = self.ig_range = None
@@ -1074,6 +1155,7 @@ class Net(object):
                 op.alloc(rt, B)
             self.B = B
             self._packed = False
+            self.generation += 1          # captured CUDA graphs hold the old buffers' addresses (Pix2Pix re-captures)
         for i in input_grads:
             v = self.inputs[i]
             if v.grad is None or v.grad.shape[0] < self.B:
@@ -1158,11 +1240,12 @@ class Net(object):
             if "m" not in self.opt_state:
                 self.opt_state["m"] = rt.zeros((n,), torch.float32)
                 self.opt_state["v"] = rt.zeros((n,), torch.float32)
-                self.opt_state["t"] = 0
-            self.opt_state["t"] += 1
-            rt.call("hm_adam", _ptr(self.pflat), _ptr(self.gflat), _ptr(self.opt_state["m"]),
+                # the step count lives in device memory, so a captured CUDA graph keeps counting on every replay
+                self.opt_state["t"] = rt.zeros((1,), torch.int32)
+            rt.call("hm_inc_i32", _ptr(self.opt_state["t"]))
+            rt.call("hm_adam_dev", _ptr(self.pflat), _ptr(self.gflat), _ptr(self.opt_state["m"]),
                     _ptr(self.opt_state["v"]), n, _ptr(lr_dev), hyper.get("beta1", 0.9),
-                    hyper.get("beta2", 0.999), hyper.get("epsilon", 1e-8), self.opt_state["t"], gscale)
+                    hyper.get("beta2", 0.999), hyper.get("epsilon", 1e-8), _ptr(self.opt_state["t"]), gscale)
         else:
             raise NotImplementedError("optimiser %r" % opt)
         self._packed = False

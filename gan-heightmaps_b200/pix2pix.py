@@ -107,6 +107,13 @@ class Pix2Pix(object):
             self.P = engine.Net(rt, p2p_gen, name="p2p_gen", rng=rng)
             self.Dp = engine.Net(rt, p2p_disc["out"], input_layers=p2p_disc["inputs"], name="p2p_disc", rng=rng)
         self.nets = {'dcgan': {'gen': self.G, 'disc': self.D}, 'p2p': {'gen': self.P, 'disc': self.Dp}}
+        for tag, net in (("disc_fn_dcgan", self.D), ("disc_fn_p2p", self.Dp)):
+            # real and fake samples go through a discriminator as ONE 2B batch; BatchNorm statistics would then be taken
+            # over the merged batch, whereas the reference applies the network twice (pix2pix.py:94-95,98,101), each with
+            # its own batch statistics.  No experiment builds such a discriminator (bn=False everywhere): refuse it.
+            if net is not None and any(isinstance(op, engine.BNActOp) for op in net.ops):
+                raise NotImplementedError("%s with bn=True: BatchNorm inside a discriminator is not implemented (real "
+                                          "and fake batches would share statistics)" % tag)
         # one weighted backward pass through the DCGAN discriminator instead of two (hm_adv_loss_pair, include/hmgan.h)
         self._single_pass = (self.D is not None and os.environ.get("HMGAN_SINGLE_PASS_D", "1") != "0"
                              and self.D.single_pass_ok())
@@ -130,8 +137,7 @@ class Pix2Pix(object):
         self.train_keys = ['dcgan_gen', 'dcgan_disc', 'p2p_gen', 'p2p_recon', 'p2p_disc']
         self._stage = {}
         self._graphs = {}
-        self._graphs_ok = (rt.device.type == "cuda" and self.opt == "rmsprop" and
-                           os.environ.get("HMGAN_CUDA_GRAPHS", "1") != "0")
+        self._graphs_ok = rt.device.type == "cuda" and os.environ.get("HMGAN_CUDA_GRAPHS", "1") != "0"
         self.train_fn = lambda Z, X, Y: self._step_host(Z, X, Y, True)
         self.loss_fn = lambda Z, X, Y: self._step_host(Z, X, Y, False)
         self.gen_fn = lambda X: self._gen_p2p(X, False)
@@ -198,14 +204,16 @@ class Pix2Pix(object):
         (batch size, train flag) -- after two eager warm-up calls that size every buffer -- and replayed
         afterwards, so the host cost of a step is one graph launch (all buffers are static, tensor maps and
         descriptors are kernel arguments, the learning rate is read from device memory).  Set
-        HMGAN_CUDA_GRAPHS=0 to always run eagerly; Adam runs eagerly (its step count is a kernel argument)."""
+        HMGAN_CUDA_GRAPHS=0 to always run eagerly.  Invariants that keep replays correct: (i) the packed compute-dtype
+        weight copies are refreshed INSIDE the step right after the update, and by the host before any launch when
+        set_all_param_values / a reallocation invalidated them (_ensure_packed), so no graph depends on a host flag;
+        (ii) a graph is dropped and re-captured when any network reallocated its buffers after the capture
+        (Net.generation); (iii) Adam's step count lives in device memory."""
         if not self._graphs_ok:
             return self._step_eager(Zd, Xd, Yd, train)
         key = (tuple(Zd.shape), tuple(Xd.shape), Xd.dtype, tuple(Yd.shape) if Yd is not None else None,
                Yd.dtype if Yd is not None else None, bool(train))
-        st = self._graphs.get(key)
-        if st is None:
-            st = self._graphs[key] = {"calls": 0, "graph": None}
+        st = self._graph_state(key, "graph")
         if st["graph"] is None:
             st["calls"] += 1
             if st["calls"] <= 2:
@@ -213,6 +221,7 @@ class Pix2Pix(object):
             # capture: static input buffers, then record the step on torch's capture stream
             st["Z"], st["X"], st["Y"] = Zd.clone(), Xd.clone(), (Yd.clone() if Yd is not None else None)
             self._sync_lr()
+            self._ensure_packed()
             torch.cuda.synchronize(self.rt.device)
             g = torch.cuda.CUDAGraph()
             l0 = self.rt.launches
@@ -220,13 +229,39 @@ class Pix2Pix(object):
                 self._step_eager(st["Z"], st["X"], st["Y"], train)
             st["launches"] = self.rt.launches - l0
             st["graph"] = g
+            st["gen"] = self._generations()
         for dst, src in ((st["Z"], Zd), (st["X"], Xd), (st["Y"], Yd)):
             if dst is not None and dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._sync_lr()
+        self._ensure_packed()
         st["graph"].replay()
         self.rt.launches += st["launches"]
         return self.losses
+
+    def _nets(self):
+        return [n for n in (self.G, self.D, self.P, self.Dp) if n is not None]
+
+    def _generations(self):
+        return tuple(n.generation for n in self._nets())
+
+    def _graph_state(self, key, slot):
+        """Capture state of one (shapes, train flag) key.  A graph holds raw addresses of the networks' buffers: when a
+        network has reallocated since the capture (Net.ensure with a larger batch from ANY entry point) the graph is
+        dropped and captured again after two fresh eager calls."""
+        st = self._graphs.get(key)
+        if st is not None and st.get(slot) is not None and st.get("gen") != self._generations():
+            st = None
+        if st is None:
+            st = self._graphs[key] = {"calls": 0, slot: None}
+        return st
+
+    def _ensure_packed(self):
+        """Refresh the packed weight copies of any network whose master parameters changed outside a step
+        (set_all_param_values, load_model) or whose buffers were reallocated; eager launches, never captured."""
+        for n in self._nets():
+            if not n._packed and n.B > 0:
+                n.pack()
 
     def _step_eager(self, Zd, Xd, Yd, train=True, part=0):
         """part 0: the whole step.  part 1: only what depends on Z alone (G's forward pass); part 2: everything else.
@@ -326,6 +361,7 @@ class Pix2Pix(object):
                     dist.all_reduce(net.gflat, op=dist.ReduceOp.SUM, group=self.pg)
             for net in upd:
                 net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
+                net.pack()       # packed copies follow the master weights inside the step (and inside its CUDA graph)
         return self.losses
 
     def _host_tensor(self, a):
@@ -345,9 +381,7 @@ class Pix2Pix(object):
         Ys = self._host_tensor(Y) if self.have_p2p else None
         key = ("host", tuple(Zs.shape), tuple(Xs.shape), Xs.dtype, tuple(Ys.shape) if Ys is not None else None,
                Ys.dtype if Ys is not None else None, bool(train))
-        st = self._graphs.get(key)
-        if st is None:
-            st = self._graphs[key] = {"calls": 0, "gA": None}
+        st = self._graph_state(key, "gA")
         dev = self.rt.device
         if st["gA"] is None:
             st["calls"] += 1
@@ -356,6 +390,7 @@ class Pix2Pix(object):
             st["Z"], st["X"] = Zs.to(dev), Xs.to(dev)
             st["Y"] = Ys.to(dev) if Ys is not None else None
             self._sync_lr()
+            self._ensure_packed()
             torch.cuda.synchronize(dev)
             l0 = self.rt.launches
             gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -365,8 +400,10 @@ class Pix2Pix(object):
                 self._step_eager(st["Z"], st["X"], st["Y"], train, part=2)
             st["launches"] = self.rt.launches - l0
             st["gA"], st["gB"] = gA, gB
+            st["gen"] = self._generations()
             st["side"], st["ev"] = torch.cuda.Stream(dev), torch.cuda.Event()
         self._sync_lr()
+        self._ensure_packed()
         main = torch.cuda.current_stream(dev)
         st["Z"].copy_(Zs, non_blocking=True)
         st["gA"].replay()
@@ -434,12 +471,17 @@ class Pix2Pix(object):
         assert mode in ['both', 'dcgan', 'p2p']
         with gzip.open(filename) as g:
             dd = pickle.load(g, encoding='latin1')      # reference checkpoints are Python-2 pickles
-        if mode in ('both', 'dcgan'):
-            self.G.set_all_param_values(dd['dcgan']['gen'])
-            self.D.set_all_param_values(dd['dcgan']['disc'])
-        if mode in ('both', 'p2p'):
-            self.P.set_all_param_values(dd['p2p']['gen'])
-            self.Dp.set_all_param_values(dd['p2p']['disc'])
+        for stage, ok in (('dcgan', mode in ('both', 'dcgan')), ('p2p', mode in ('both', 'p2p'))):
+            for role in ('gen', 'disc'):
+                net, vals = self.nets[stage][role], dd[stage][role]
+                if not ok:
+                    continue
+                if net is None:           # a model built without this stage (gen_fn_p2p=None / gen_fn_dcgan=None)
+                    if len(vals):
+                        raise ValueError("checkpoint holds %s/%s parameters but this model was built without that "
+                                         "network (use mode=%r)" % (stage, role, 'dcgan' if stage == 'p2p' else 'p2p'))
+                    continue
+                net.set_all_param_values(vals)
 
     # ------------------------------------------------------------------ #
     # training loop (reference pix2pix.py:187-275)

@@ -46,7 +46,9 @@ typedef enum HmStatus {
   HM_ERR_ALIGN = -4
 } HmStatus;
 
-typedef enum HmDType { HM_F32 = 0, HM_F16 = 1 } HmDType;
+/* HM_BF16X3 (tensor-core kernels only): the operands are three-plane bfloat16 splits of float32 tensors written by
+ * hm_split_bf16x3 and the results are float32 -- float32-grade contractions on the tcgen05 pipe ("tc32" mode). */
+typedef enum HmDType { HM_F32 = 0, HM_F16 = 1, HM_BF16X3 = 2 } HmDType;
 
 typedef enum HmAct {
   HM_ACT_LINEAR = 0,  /* lasagne.nonlinearities.linear                       */
@@ -136,6 +138,19 @@ int hm_tc_conv_ws(const HmConvDesc* d, const void* x1, const void* x2, const voi
 int hm_tc_wgrad_supported(const HmConvDesc* d);
 int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw_packed,
                 void* stream);
+
+/* float32-grade contractions on the same tcgen05 kernels (dtype HM_BF16X3, the "tc32" parity mode; csrc/split_bf16.cu).
+ * hm_split_bf16x3 splits a float32 [rows][C] tensor into three bfloat16 planes  a = h + m + l  (h = bf16(a),
+ * m = bf16(a - h), l = bf16(a - h - m); exact to 2^-24) and writes SIX planes along the axis the GEMM reduces over:
+ *   layout 0: dst[rows][6C] = [h|h|m|h|l|m]  -- sources of hm_tc_conv (forward and input-gradient forms); pass C1, C2 = 6x;
+ *   layout 1: dst[rows][6C] = [h|m|h|l|h|m]  -- the float32 K-major weight pack (hm_pack_conv_weight with dst_dtype HM_F32,
+ *             rows = elements / K); c1 < C splits the two ConcatLayer segments [0,c1) and [c1,C) separately;
+ *   layout 2: dst[6][rows][C] = h;h;m;h;l;m  -- x of hm_tc_wgrad, stacked along the batch axis (pass B = 6x);
+ *   layout 3: dst[6][rows][C] = h;m;h;l;h;m  -- dy of hm_tc_wgrad.
+ * With these operands the kernels accumulate h.h + h.m + m.h + h.l + l.h + m.m in fp32 TMEM (every product exact, the
+ * dropped terms <= 2^-24 relative) and hm_tc_conv stores FLOAT32 results (y, y2 are float tensors; `accumulate` adds to
+ * float values). */
+int hm_split_bf16x3(const float* src, void* dst, long long rows, int C, int c1, int layout, void* stream);
 
 /* Re-layouts that put the two thin layers of the DCGAN on the tensor cores (fp16 only):
  *  hm_im2col_c1: xc[B,H,W,64], xc[p][t] = x[p + tap t - pad] for the kh*kw taps of a ONE-channel image, 0 beyond; the
@@ -316,6 +331,11 @@ int hm_rmsprop(float* p, const float* g, float* acc, long long n, const float* l
 /* adam (lasagne 0.2.dev1): t is the NEW step count. */
 int hm_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr, float b1,
             float b2, float eps, int t, float gscale, void* stream);
+/* The same with the step count in device memory: *t_dev is the NEW step count (>= 1), advanced on the stream by
+ * hm_inc_i32 before the call, so a captured CUDA graph of the step keeps counting on every replay. */
+int hm_adam_dev(float* p, const float* g, float* m, float* v, long long n, const float* lr, float b1,
+                float b2, float eps, const int* t_dev, float gscale, void* stream);
+int hm_inc_i32(int* counter, void* stream);
 
 #ifdef __cplusplus
 }

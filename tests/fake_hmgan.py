@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-F32, F16 = 0, 1
+F32, F16, BF16X3 = 0, 1, 2
 _NP = {F32: np.float32, F16: np.float16}
 
 
@@ -569,6 +569,56 @@ def hm_adam(p, g, m, v, n, lr, b1, b2, eps, t, gscale, stream=None):
     return 0
 
 
+def hm_inc_i32(counter, stream=None):
+    _a(counter, 1, np.int32)[0] += 1
+    return 0
+
+
+def hm_adam_dev(p, g, m, v, n, lr, b1, b2, eps, t_dev, gscale, stream=None):
+    return hm_adam(p, g, m, v, n, lr, b1, b2, eps, int(_a(t_dev, 1, np.int32)[0]), gscale)
+
+
+def _bf16_round(a):
+    """float32 array -> nearest-even bfloat16, as uint16 bit patterns."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    return r
+
+
+def _bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def hm_split_bf16x3(src, dst, rows, Cn, c1, layout, stream=None):
+    a = _a(src, rows * Cn, np.float32).reshape(rows, Cn)
+    h = _bf16_round(a)
+    r1 = a - _bf16_to_f32(h)
+    m = _bf16_round(r1)
+    l = _bf16_round(r1 - _bf16_to_f32(m))
+    planes = (h, m, h, l, h, m) if layout & 1 else (h, h, m, h, l, m)
+    out = _a(dst, 6 * rows * Cn, np.uint16)
+    if layout >= 2:
+        o = out.reshape(6, rows, Cn)
+        for k in range(6):
+            o[k] = planes[k]
+    else:
+        o = out.reshape(rows, 6 * Cn)
+        for (a0, a1, base) in ((0, c1, 0), (c1, Cn, 6 * c1)):
+            w = a1 - a0
+            for k in range(6):
+                if w > 0:
+                    o[:, base + k * w:base + (k + 1) * w] = planes[k][:, a0:a1]
+    return 0
+
+
+def _bf16x3_as_f32(d, ptrs_counts):
+    """HM_BF16X3 problem -> the same problem on float32 copies of its bf16 operands (keeps the arrays alive)."""
+    d2 = type(d).from_buffer_copy(d)
+    d2.dtype = F32
+    keep = [None if not ptr else np.ascontiguousarray(_bf16_to_f32(_a(ptr, n, np.uint16))) for ptr, n in ptrs_counts]
+    return d2, keep, [None if k is None else k.ctypes.data for k in keep]
+
+
 def _is_up2conv(d):
     return (d.up == 1 and d.kh == 5 and d.kw == 5 and d.pad == 2 and d.stride == 1 and not d.transposed and
             d.C2 == 0 and d.Ho == 2 * d.H and d.Wo == 2 * d.W and d.split == d.Cout and not d.accumulate and
@@ -587,6 +637,9 @@ def _is_deconv_d2s(d):
 
 
 def _tc_ok(d, wgrad):
+    if d.dtype == BF16X3:            # bf16 hi/lo splits of fp32 tensors: same shape rules as fp16
+        d = type(d).from_buffer_copy(d)
+        d.dtype = F16
     if not wgrad and d.dtype == F16 and _is_deconv_d2s(d):
         return d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0 and (d.Cout % 32 == 0 or d.Cout <= 4)
     if not wgrad and d.dtype == F16 and _is_dgrad_s2(d):
@@ -624,45 +677,52 @@ def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
     """Same contract as hm_conv_gather, weights in the K-major pack [tap][Cout][Cin]."""
     d = dp._obj if hasattr(dp, "_obj") else dp
     assert _tc_ok(d, False)
+    f16 = np.float16
+    if d.dtype == BF16X3:
+        nsrc = d.B * d.H * d.W
+        nw = (36 if _is_up2conv(d) else 4 if d.transposed == 2 else 16 if _is_dgrad_s2(d) else d.kh * d.kw) * \
+            d.Cout * (d.C1 + d.C2)
+        d, _keep, (x1, x2, w_tc) = _bf16x3_as_f32(d, ((x1, nsrc * d.C1), (x2, nsrc * d.C2), (w_tc, nw)))
+        dp, f16 = d, np.float32
     if _is_up2conv(d):
         # four 3x3 phase convolutions on the low-res source with the mode-8 pack, then depth-to-space
         B, H, W, Ci, Co = d.B, d.H, d.W, d.C1, d.Cout
-        a = _t(_a(x1, B * H * W * Ci, np.float16)).reshape(B, H, W, Ci).permute(0, 3, 1, 2)
-        wt = _t(_a(w_tc, 36 * Co * Ci, np.float16)).reshape(3, 3, 4 * Co, Ci)
+        a = _t(_a(x1, B * H * W * Ci, f16)).reshape(B, H, W, Ci).permute(0, 3, 1, 2)
+        wt = _t(_a(w_tc, 36 * Co * Ci, f16)).reshape(3, 3, 4 * Co, Ci)
         out = F.conv2d(a, wt.permute(2, 3, 0, 1).contiguous(), padding=1)          # [B,4Co,H,W]
         out = out.reshape(B, 2, 2, Co, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B, 2 * H, 2 * W, Co)
         if bias:
             out = out + _t(_a(bias, Co, np.float32))
         out = _act(out, d.act, d.slope)
-        _a(y, B * 4 * H * W * Co, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+        _a(y, B * 4 * H * W * Co, f16)[:] = out.numpy().reshape(-1).astype(f16)
         return 0
     if d.transposed == 2:
         # Deconv2DLayer 2x2 stride 2: 1x1 convolution with N = (phase, co) (pack mode 17), then depth-to-space
         B, H, W, Ci, Co = d.B, d.H, d.W, d.C1 + d.C2, d.Cout
-        a = _t(_a(x1, B * H * W * d.C1, np.float16)).reshape(B * H * W, d.C1)
+        a = _t(_a(x1, B * H * W * d.C1, f16)).reshape(B * H * W, d.C1)
         if d.C2:
-            a = torch.cat([a, _t(_a(x2, B * H * W * d.C2, np.float16)).reshape(B * H * W, d.C2)], 1)
-        wt = _t(_a(w_tc, 4 * Co * Ci, np.float16)).reshape(4 * Co, Ci)
+            a = torch.cat([a, _t(_a(x2, B * H * W * d.C2, f16)).reshape(B * H * W, d.C2)], 1)
+        wt = _t(_a(w_tc, 4 * Co * Ci, f16)).reshape(4 * Co, Ci)
         out = (a @ wt.t()).reshape(B, H, W, 2, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, Co)
         if bias:
             out = out + _t(_a(bias, Co, np.float32))
         out = _act(out, d.act, d.slope)
-        _a(y, B * 4 * H * W * Co, np.float16)[:] = out.numpy().reshape(-1).astype(np.float16)
+        _a(y, B * 4 * H * W * Co, f16)[:] = out.numpy().reshape(-1).astype(f16)
         return 0
     if _is_dgrad_s2(d):
         # 2x2-tap convolution of dy on its own grid with N = (phase, ci), then depth-to-space (pack mode 12)
         B, H, W, Co, Ci = d.B, d.H, d.W, d.C1, d.Cout
-        g = _t(_a(x1, B * H * W * Co, np.float16)).reshape(B, H, W, Co).permute(0, 3, 1, 2)
-        wt = _t(_a(w_tc, 16 * Co * Ci, np.float16)).reshape(2, 2, 4 * Ci, Co)
+        g = _t(_a(x1, B * H * W * Co, f16)).reshape(B, H, W, Co).permute(0, 3, 1, 2)
+        wt = _t(_a(w_tc, 16 * Co * Ci, f16)).reshape(2, 2, 4 * Ci, Co)
         out = F.conv2d(F.pad(g, (0, 1, 0, 1)), wt.permute(2, 3, 0, 1).contiguous())           # [B,4Ci,H,W]
         out = out.reshape(B, 2, 2, Ci, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B, 2 * H, 2 * W, Ci)
-        dst = _a(y, B * 4 * H * W * Ci, np.float16)
+        dst = _a(y, B * 4 * H * W * Ci, f16)
         if d.accumulate & 1:
             out = out + _t(dst).reshape(out.shape)
-        dst[:] = out.numpy().reshape(-1).astype(np.float16)
+        dst[:] = out.numpy().reshape(-1).astype(f16)
         return 0
     Ct = d.C1 + d.C2
-    wt = _a(w_tc, d.kh * d.kw * Ct * d.Cout, np.float16).reshape(d.kh * d.kw, d.Cout, Ct)
+    wt = _a(w_tc, d.kh * d.kw * Ct * d.Cout, f16).reshape(d.kh * d.kw, d.Cout, Ct)
     wk = np.ascontiguousarray(wt.transpose(0, 2, 1))           # [tap][ci][co] = the gather kernel's pack
     return hm_conv_gather(dp, x1, x2, wk.ctypes.data, bias, y, y2)
 
@@ -670,6 +730,10 @@ def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
 def hm_tc_wgrad(dp, x1, x2, dy, dw, stream=None):
     d = dp._obj if hasattr(dp, "_obj") else dp
     assert _tc_ok(d, True)
+    if d.dtype == BF16X3:
+        nsrc = d.B * d.H * d.W
+        dp, _keep, (x1, x2, dy) = _bf16x3_as_f32(d, ((x1, nsrc * d.C1), (x2, nsrc * d.C2),
+                                                     (dy, d.B * d.Ho * d.Wo * d.Cout)))
     return hm_conv_wgrad(dp, x1, x2, dy, dw)
 
 

@@ -82,6 +82,28 @@ def _check_grads(om, m, keys, rtol, rtol_by_net=None):
             assert err <= rtol * float(np.abs(b).max()) + 1e-5 * net_scale, (k, i, err, float(np.abs(b).max()))
 
 
+def _check_grads_l2(om, m, keys, tol, scale=1.0, tol_by_net=None):
+    """Per-array relative L2 error of the weight gradients (`scale` undoes the loss scale).  Arrays whose true gradient
+    is zero (conv biases in front of a BatchNorm) are compared with the network's largest gradient norm.
+
+    On max-pool ties: a 2x2 window whose two largest values agree to float32 rounding sends its gradient to a
+    different pixel under ANY arithmetic that is not bit-identical to the oracle's.  Measured on the CPU emulation of
+    the tc32 mode (64-px DCGAN, batch 2; forward values agree with the SIMT float32 path to 2e-6): ONE window of 65536
+    in the discriminator's second pool flips, which moves d loss / d G(z) by 5e-4 and the generator's gradient arrays by
+    1e-3 (max norm and L2 alike) while the discriminator's own arrays stay at 2e-5.  Callers therefore give the
+    generator -- whose whole gradient is routed through the discriminator's pools -- a separate bound (tol_by_net)."""
+    nets = {'G': m.G, 'D': m.D, 'P': m.P, 'Dp': m.Dp}
+    base = tol
+    for k in keys:
+        tol = (tol_by_net or {}).get(k, base)
+        ref = om.last_grads[k]
+        net_norm = max(float(np.linalg.norm(b.ravel())) for b in ref)
+        for i, (a, b) in enumerate(zip(nets[k].get_grads(), ref)):
+            err = float(np.linalg.norm((a * scale - b).ravel()))
+            assert err <= tol * float(np.linalg.norm(b.ravel())) + 1e-5 * net_norm, \
+                (k, i, a.shape, err / (float(np.linalg.norm(b.ravel())) + 1e-30))
+
+
 def test_gate64_dcgan_step_matches_oracle(cpu_backend):
     cfg = S.experiment_kwargs('gate64')
     om, m = build_pair(cfg, 'dcgan', with_p2p=False)

@@ -65,3 +65,35 @@ def test_tc_deconv_2x2_stride2_all_phases(case):
     hm_s2d_pad64, against torch conv_transpose2d / its adjoint in float32: 3e-3 of the output scale."""
     rel, line = tc_probe.run_dc2_case(*case)
     assert rel <= 3e-3, line
+
+
+# ---- HM_BF16X3 ("tc32" precision): float32-grade contractions on the same tcgen05 kernels ---------------------------------
+# Operands are three-plane bf16 splits of float32 tensors (hm_split_bf16x3), six exact products accumulated in fp32 TMEM,
+# float32 results; compared with the SIMT float32 kernels: 5e-5 of the output scale (measured <= 2.5e-5: summation-order noise of up to
+# ~10^4-term fp32 sums; a dropped or misplaced plane shows up at >= 4e-3).
+TC32_TOL = 5e-5
+
+
+@pytest.mark.parametrize("case", tc_probe.CASES, ids=[c[0] for c in tc_probe.CASES])
+def test_tc32_conv_matches_simt_fp32(case):
+    rel, line = tc_probe.run_case32(*case)
+    assert rel <= TC32_TOL, line
+
+
+@pytest.mark.parametrize("case", tc_probe.WGRAD_CASES, ids=[c[0] for c in tc_probe.WGRAD_CASES])
+def test_tc32_wgrad_matches_simt_fp32(case):
+    rel, line = tc_probe.run_wgrad_case32(*case)
+    assert rel <= TC32_TOL, line
+
+
+@pytest.mark.parametrize("case", [c for c in tc_probe.UP2_CASES if c[5] % 32 == 0 or c[5] <= 4],
+                         ids=[c[0] for c in tc_probe.UP2_CASES if c[5] % 32 == 0 or c[5] <= 4])
+def test_tc32_up2conv_matches_simt_fp32(case):
+    rel, line = tc_probe.run_up2_case32(*case)
+    assert rel <= TC32_TOL, line
+
+
+@pytest.mark.parametrize("case", tc_probe.S2_CASES, ids=[c[0] for c in tc_probe.S2_CASES])
+def test_tc32_stride2_fwd_wgrad_dgrad_match_simt_fp32(case):
+    rel, line = tc_probe.run_s2_case32(*case)
+    assert rel <= TC32_TOL, line

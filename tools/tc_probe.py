@@ -253,6 +253,156 @@ def run_wgrad_case(name, B, H, W, C1, C2, Cout, k, pad, act):
     return float(err.max()) / scale, line
 
 
+# ---- HM_BF16X3 ("tc32"): the same tcgen05 kernels on three-plane bf16 splits of fp32 tensors vs the SIMT fp32 kernels ----
+def _split(t, layout, c1=None):
+    """hm_split_bf16x3 of a float32 [..., C] tensor -> bf16 tensor with six planes along the reduction axis."""
+    t = t.contiguous()
+    Cn = t.shape[-1]
+    rows = t.numel() // Cn
+    out = torch.empty(6 * t.numel(), device="cuda", dtype=torch.bfloat16)
+    _lib.call("hm_split_bf16x3", t.data_ptr(), out.data_ptr(), rows, Cn, Cn if c1 is None else c1, layout, None)
+    return out
+
+
+def _pack32(Wm, mode, Co, Ci, kh, kw, K, c1=None):
+    """fp32 pack of `mode`, then the b-side split along its innermost extent K."""
+    n = int(_lib.query("hm_pack_conv_weight_count", mode, Co, Ci, kh, kw))
+    tmp = torch.empty(n, device="cuda", dtype=torch.float32)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), tmp.data_ptr(), mode, Co, Ci, kh, kw, 0, 0, 0, None)
+    return _split(tmp.view(n // K, K), 1, c1)
+
+
+def _cmp32(tag, name, a, b):
+    err = (a - b).abs()
+    scale = float(b.abs().max())
+    rel = float(err.max()) / scale
+    return rel, "%s %-28s max_err %.4g scale %.4g rel %.3g" % (tag, name, float(err.max()), scale, rel)
+
+
+def run_case32(name, B, H, W, C1, C2, Cout, k, pad, act, verbose=True):
+    torch.manual_seed(abs(hash(name)) % 1000)
+    Ct = C1 + C2
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x1 = torch.randn(B, H, W, C1, device="cuda")
+    x2 = torch.randn(B, H, W, C2, device="cuda") if C2 else None
+    Wm = torch.randn(Cout, Ct, k, k, device="cuda") / np.sqrt(k * k * Ct)
+    bias = torch.randn(Cout, device="cuda")
+    wp = torch.empty(k * k * Ct * Cout, device="cuda")
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wp.data_ptr(), 0, Cout, Ct, k, k, 0, 0, 0, None)
+    wt = _pack32(Wm, 5, Cout, Ct, k, k, Ct, C1)
+    d = desc(dtype=0, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=Ho, Wo=Wo,
+             Cout=Cout, oH=Ho, oW=Wo, os=1, ou=0, ov=0, split=Cout, act=act, slope=0.2, accumulate=0)
+    y_ref = torch.zeros(B, Ho, Wo, Cout, device="cuda")
+    y_tc = torch.full((B, Ho, Wo, Cout), 7.0, device="cuda")
+    p2 = x2.data_ptr() if C2 else None
+    _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None, None)
+    s1 = _split(x1, 0)
+    s2 = _split(x2, 0) if C2 else None
+    d2 = desc(**{f: getattr(d, f) for f, _ in d._fields_})
+    d2.dtype, d2.C1, d2.C2 = 2, 6 * C1, 6 * C2
+    _lib.call("hm_tc_conv", C.byref(d2), s1.data_ptr(), s2.data_ptr() if C2 else None, wt.data_ptr(), bias.data_ptr(),
+              y_tc.data_ptr(), None, None)
+    torch.cuda.synchronize()
+    return _cmp32("tc32", name, y_tc, y_ref)
+
+
+def run_wgrad_case32(name, B, H, W, C1, C2, Cout, k, pad, act):
+    torch.manual_seed(abs(hash(name)) % 1000 + 5)
+    Ct = C1 + C2
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x1 = torch.randn(B, H, W, C1, device="cuda")
+    x2 = torch.randn(B, H, W, C2, device="cuda") if C2 else None
+    dy = torch.randn(B, Ho, Wo, Cout, device="cuda")
+    d = desc(dtype=0, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=Ho, Wo=Wo,
+             Cout=Cout, oH=Ho, oW=Wo, os=1, ou=0, ov=0, split=Cout, act=0, slope=0.0, accumulate=0)
+    ref = torch.zeros(k * k * Ct, Cout, device="cuda")
+    out = torch.zeros(k * k * Ct, Cout, device="cuda")
+    p2 = x2.data_ptr() if C2 else None
+    _lib.call("hm_conv_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), ref.data_ptr(), None)
+    s1, s2, sd = _split(x1, 2), (_split(x2, 2) if C2 else None), _split(dy, 3)
+    d2 = desc(**{f: getattr(d, f) for f, _ in d._fields_})
+    d2.dtype, d2.B = 2, 6 * B
+    _lib.call("hm_tc_wgrad", C.byref(d2), s1.data_ptr(), s2.data_ptr() if C2 else None, sd.data_ptr(), out.data_ptr(), None)
+    torch.cuda.synchronize()
+    return _cmp32("tc32 wgrad", name, out, ref)
+
+
+def run_up2_case32(name, B, H, W, Ci, Co, act):
+    torch.manual_seed(abs(hash(name)) % 1000 + 11)
+    x = torch.randn(B, H, W, Ci, device="cuda")
+    Wm = torch.randn(Co, Ci, 5, 5, device="cuda") / np.sqrt(25 * Ci)
+    bias = torch.randn(Co, device="cuda")
+    wp = torch.empty(25 * Ci * Co, device="cuda")
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wp.data_ptr(), 0, Co, Ci, 5, 5, 0, 0, 0, None)
+    w8 = _pack32(Wm, 8, Co, Ci, 5, 5, Ci)
+    d = desc(dtype=0, B=B, H=H, W=W, C1=Ci, C2=0, up=1, kh=5, kw=5, stride=1, pad=2, transposed=0, Ho=2 * H, Wo=2 * W,
+             Cout=Co, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Co, act=act, slope=0.2, accumulate=0)
+    y_ref = torch.zeros(B, 2 * H, 2 * W, Co, device="cuda")
+    y_tc = torch.full((B, 2 * H, 2 * W, Co), 7.0, device="cuda")
+    _lib.call("hm_conv_gather", C.byref(d), x.data_ptr(), None, wp.data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None, None)
+    sx = _split(x, 0)
+    d2 = desc(**{f: getattr(d, f) for f, _ in d._fields_})
+    d2.dtype, d2.C1 = 2, 6 * Ci
+    _lib.call("hm_tc_conv", C.byref(d2), sx.data_ptr(), None, w8.data_ptr(), bias.data_ptr(), y_tc.data_ptr(), None, None)
+    torch.cuda.synchronize()
+    return _cmp32("tc32 up2", name, y_tc, y_ref)
+
+
+def run_s2_case32(name, B, H, W, C1, C2, Co):
+    torch.manual_seed(abs(hash(name)) % 1000 + 3)
+    Ct = C1 + C2
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    x1 = torch.randn(B, H, W, C1, device="cuda")
+    x2 = torch.randn(B, H, W, C2, device="cuda") if C2 else None
+    p2 = x2.data_ptr() if C2 else None
+    Wm = torch.randn(Co, Ct, 3, 3, device="cuda") / np.sqrt(9 * Ct)
+    bias = torch.randn(Co, device="cuda")
+    packs = {}
+    for mode in (0, 1):
+        packs[mode] = torch.empty(9 * Ct * Co, device="cuda")
+        _lib.call("hm_pack_conv_weight", Wm.data_ptr(), packs[mode].data_ptr(), mode, Co, Ct, 3, 3, 0, 0, 0, None)
+    w5, w12 = _pack32(Wm, 5, Co, Ct, 3, 3, Ct, C1), _pack32(Wm, 12, Co, Ct, 3, 3, Co)
+    d = desc(dtype=0, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=3, kw=3, stride=2, pad=1, transposed=0, Ho=Ho, Wo=Wo,
+             Cout=Co, oH=Ho, oW=Wo, os=1, ou=0, ov=0, split=Co, act=1, slope=0.01, accumulate=0)
+    y_ref = torch.zeros(B, Ho, Wo, Co, device="cuda")
+    y_tc = torch.full((B, Ho, Wo, Co), 7.0, device="cuda")
+    _lib.call("hm_conv_gather", C.byref(d), x1.data_ptr(), p2, packs[0].data_ptr(), bias.data_ptr(), y_ref.data_ptr(), None, None)
+    s1, s2 = _split(x1, 0), (_split(x2, 0) if C2 else None)
+    d2 = desc(**{f: getattr(d, f) for f, _ in d._fields_})
+    d2.dtype, d2.C1, d2.C2 = 2, 6 * C1, 6 * C2
+    _lib.call("hm_tc_conv", C.byref(d2), s1.data_ptr(), s2.data_ptr() if C2 else None, w5.data_ptr(), bias.data_ptr(),
+              y_tc.data_ptr(), None, None)
+    dy = torch.randn(B, Ho, Wo, Co, device="cuda")
+    g_ref = torch.zeros(9 * Ct, Co, device="cuda")
+    g_tc = torch.zeros(9 * Ct, Co, device="cuda")
+    _lib.call("hm_conv_wgrad", C.byref(d), x1.data_ptr(), p2, dy.data_ptr(), g_ref.data_ptr(), None)
+    pairs = [("fwd", y_tc, y_ref)]
+    if Co % 64 == 0 and (Co <= 256 or Co % 256 == 0):
+        t1, t2, td = _split(x1, 2), (_split(x2, 2) if C2 else None), _split(dy, 3)
+        d3 = desc(**{f: getattr(d, f) for f, _ in d._fields_})
+        d3.dtype, d3.B = 2, 6 * B
+        _lib.call("hm_tc_wgrad", C.byref(d3), t1.data_ptr(), t2.data_ptr() if C2 else None, td.data_ptr(), g_tc.data_ptr(), None)
+        pairs.append(("wgrad", g_tc, g_ref))
+    if C2 == 0 and H % 2 == 0 and W % 2 == 0:
+        dd = desc(dtype=0, B=B, H=Ho, W=Wo, C1=Co, C2=0, up=0, kh=3, kw=3, stride=2, pad=1, transposed=1, Ho=H, Wo=W,
+                  Cout=Ct, oH=H, oW=W, os=1, ou=0, ov=0, split=Ct, act=0, slope=0.0, accumulate=1)
+        init = torch.randn(B, H, W, Ct, device="cuda")
+        dx_ref, dx_tc = init.clone(), init.clone()
+        _lib.call("hm_conv_gather", C.byref(dd), dy.data_ptr(), None, packs[1].data_ptr(), None, dx_ref.data_ptr(), None, None)
+        sdy = _split(dy, 0)
+        dd2 = desc(**{f: getattr(dd, f) for f, _ in dd._fields_})
+        dd2.dtype, dd2.C1 = 2, 6 * Co
+        _lib.call("hm_tc_conv", C.byref(dd2), sdy.data_ptr(), None, w12.data_ptr(), None, dx_tc.data_ptr(), None, None)
+        pairs.append(("dgrad", dx_tc, dx_ref))
+    torch.cuda.synchronize()
+    worst, lines = 0.0, []
+    for what, a, b in pairs:
+        rel, line = _cmp32("tc32 s2 " + what, name, a, b)
+        worst = max(worst, rel)
+        lines.append(line)
+    return worst, "\n".join(lines)
+
+
 DC2_CASES = [
     # name, B, H, W (input grid), C1, C2, Cout, act
     ("dc2_128_3_w256_tanh", 1, 256, 256, 64, 64, 3, 4),
@@ -553,6 +703,15 @@ if __name__ == "__main__":
                 print("c1bwd %-22s EXC %s" % (c[0], e), flush=True)
                 break
         perf_c1bwd()
+        sys.exit(0)
+    if sys.argv[1:] == ["tc32"]:
+        for fn, cases in ((run_case32, CASES), (run_wgrad_case32, WGRAD_CASES), (run_up2_case32, UP2_CASES),
+                          (run_s2_case32, S2_CASES)):
+            for c in cases:
+                try:
+                    print(fn(*c)[1], flush=True)
+                except Exception as e:
+                    print("tc32 %-28s EXC %s" % (c[0], e), flush=True)
         sys.exit(0)
     if sys.argv[1:] == ["s2"]:
         for c in S2_CASES:
