@@ -29,8 +29,13 @@ for p in (ROOT, PKG):
 import numpy as np
 import torch
 
-GFLOP_PER_IMG = {"dcgan": 391.3, "both": 683.2}        # SURVEY.md §8d (fwd + wgrad + needed dgrad, 2 FLOP/MAC)
-BATCH = {"dcgan": 32, "both": 16}                       # BASELINE.json configs[1], configs[2]
+GFLOP_PER_IMG = {"dcgan": 391.3, "both": 683.2, "p2p": 292.0}   # SURVEY.md §8d (fwd + wgrad + needed dgrad, 2 FLOP/MAC)
+BATCH = {"dcgan": 32, "both": 16, "p2p": 16}            # BASELINE.json configs[1], configs[2], configs[4] (128 / 8 GPUs)
+WORKLOAD_NAME = {
+    "dcgan": "DCGAN 512x512 heightmap train step, batch %d/GPU, z=1000 (BASELINE configs[1])",
+    "both": "DCGAN+pix2pix joint train step, 512x512, batch %d/GPU, L1+LSGAN (BASELINE configs[2])",
+    "p2p": "pix2pix U-Net 512x512 -> 512x512 RGB + PatchGAN train step, batch %d/GPU (BASELINE configs[4])",
+}
 
 
 def _peak_value(p, key):
@@ -112,17 +117,31 @@ def build_model(workload, device, precision, pg=None, verbose=False):
     from architectures import p2p, dcgan
     from lasagne_compat import linear, tanh, rmsprop, shared, floatX
     from pix2pix import Pix2Pix
-    both = workload == "both"
+    with_p2p, with_dcgan = workload in ("both", "p2p"), workload in ("both", "dcgan")
     return Pix2Pix(
-        gen_fn_dcgan=dcgan.default_generator, disc_fn_dcgan=dcgan.default_discriminator,
+        gen_fn_dcgan=dcgan.default_generator if with_dcgan else None,
+        disc_fn_dcgan=dcgan.default_discriminator if with_dcgan else None,
         gen_params_dcgan={'num_repeats': 0, 'div': [2, 2, 4, 4, 8, 8, 8]},
         disc_params_dcgan={'num_repeats': 0, 'bn': False, 'nonlinearity': linear, 'div': [8, 4, 4, 4, 2, 2, 2]},
-        gen_fn_p2p=p2p.g_unet if both else None, disc_fn_p2p=p2p.discriminator if both else None,
+        gen_fn_p2p=p2p.g_unet if with_p2p else None, disc_fn_p2p=p2p.discriminator if with_p2p else None,
         gen_params_p2p={'nf': 64, 'act': tanh, 'num_repeats': 0, 'bilinear_upsample': True},
         disc_params_p2p={'nf': 64, 'bn': False, 'num_repeats': 0, 'act': linear, 'mul_factor': [1, 2, 4, 8]},
         in_shp=512, latent_dim=1000, is_a_grayscale=True, is_b_grayscale=False, lsgan=True, opt=rmsprop,
-        opt_args={'learning_rate': shared(floatX(1e-4))}, train_mode='both' if both else 'dcgan', verbose=verbose,
+        opt_args={'learning_rate': shared(floatX(1e-4))}, train_mode=workload, verbose=verbose,
         device=device, precision=precision, seed=2, process_group=pg)
+
+
+def liven_head(m, value):
+    """At the Glorot initialisation the ReLU head of the DCGAN discriminator (reference architectures/dcgan.py:50) is
+    dead on synthetic inputs: D(.) = 0 for every sample, both losses are exactly 1 and EVERY gradient tensor of the step
+    is exactly zero.  The kernels run the same launches either way, but multiplying zeros draws less power, so the
+    clocks -- and the measured rate -- would be those of an idle-data step, not of training.  A head bias of `value`
+    puts D(.) near it, as it is after the first few real updates; the step then moves dense gradients."""
+    if m.D is None or not value:
+        return
+    vals = m.D.get_all_param_values()
+    vals[-1][:] = value
+    m.D.set_all_param_values(vals)
 
 
 def time_dominant_kernel(m, reps=5):
@@ -158,9 +177,8 @@ def cpu_baseline(workload, sample_b, steps=1, warmup=1):
     from oracle import step as S
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = S.experiment_kwargs('test1_nobn_bilin_both')
-    which = ('G', 'D', 'P', 'Dp') if workload == "both" else ('G', 'D')
-    om = S.OracleModel(S.build_nets(cfg, seed=2, which=which), opt='rmsprop', lr=1e-4,
-                       train_mode='both' if workload == "both" else 'dcgan', lsgan=True)
+    which = {"both": ('G', 'D', 'P', 'Dp'), "dcgan": ('G', 'D'), "p2p": ('P', 'Dp')}[workload]
+    om = S.OracleModel(S.build_nets(cfg, seed=2, which=which), opt='rmsprop', lr=1e-4, train_mode=workload, lsgan=True)
     Z, X, Y = S.synthetic_batch(sample_b, cfg['latent_dim'], 512, seed=0)
     for _ in range(warmup):
         om.train_fn(Z, X, Y)
@@ -171,39 +189,121 @@ def cpu_baseline(workload, sample_b, steps=1, warmup=1):
     return sample_b / dt, dt
 
 
+def measure(workload, B, steps, warmup, precision, local, rank, world, pg, sample_clocks, head_bias=0.6):
+    """Build the model of `workload`, run W warm-up + K timed steps device-resident and again end to end from pinned
+    host memory.  Returns (result dict, model)."""
+    import torch.distributed as dist
+    m = build_model(workload, "cuda:%d" % local, precision, pg)
+    liven_head(m, head_bias)
+    from util import synthetic_batch
+    Z, X, Y = synthetic_batch(B, 1000, 512, seed=100 + rank)
+    Zd, Xd, Yd = (torch.from_numpy(t).cuda() for t in (Z, X, Y))
+    Zp, Xp, Yp = (torch.from_numpy(t).pin_memory() for t in (Z, X, Y))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # W untimed warm-up steps; never fewer than 3, so that the two buffer-sizing eager steps and the CUDA-graph capture of
+    # the third call are outside the timed region whatever --warmup says
+    for _ in range(max(warmup, 3)):
+        m.step_device(Zd, Xd, Yd, True)
+    clocks = ClockSampler(local) if (sample_clocks and rank == 0) else None
+    if clocks:
+        clocks.start()
+    l0 = m.rt.launches
+    ms = timed(lambda: m.step_device(Zd, Xd, Yd, True), steps)
+    launches = m.rt.launches - l0
+    clk = clocks.stop() if clocks else None
+    losses = m.losses.cpu().numpy()
+    # end to end through the public API: pinned host inputs, losses read back every step
+    for _ in range(3):                    # the host path captures its own graphs on its third call
+        m.train_fn(Zp, Xp, Yp)
+    ms_e2e = timed(lambda: m.train_fn(Zp, Xp, Yp), steps)
+    # data-parallel replicas must hold identical parameters after the same all-reduced updates
+    identical = True
+    if world > 1:
+        for net in m._nets():
+            cs = net.pflat.double().sum().reshape(1)
+            lo, hi = cs.clone(), cs.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            identical = identical and bool((lo == hi).item())
+    with_y = workload in ("both", "p2p")
+    with_z = workload in ("both", "dcgan")
+    pk = peaks()
+    value = B * world * steps / (ms * 1e-3)
+    step_tflops = value / world * GFLOP_PER_IMG[workload] / 1e3
+    res = dict(value=value, ms_per_step=ms / steps,
+               e2e={"value": B * world * steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    # only the tensors a model reads are copied (a DCGAN-only model never reads Y, a pix2pix-only one Z)
+                    "h2d_bytes_per_step": int((Z.nbytes if with_z else 0) + X.nbytes + (Y.nbytes if with_y else 0)),
+                    "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / steps},
+               gpu_launches=int(launches), clocks=clk, losses=[float(v) for v in losses],
+               step_achieved_tflops=step_tflops, step_frac_of_burst=step_tflops / pk["burst"],
+               step_frac_of_sustained=step_tflops / pk["sustained"], replicas_identical=identical)
+    return res, m
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dcgan", choices=["dcgan", "both"])
+    ap.add_argument("--workload", default="dcgan", choices=["dcgan", "both", "p2p"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: BASELINE.json's)")
-    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity", "tc32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=2)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] / configs[4] lines")
+    ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--head-bias", type=float, default=0.6,
+                    help="bias of the DCGAN discriminator's head (0 = leave the Glorot init: dead head, all-zero gradients)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     B = a.batch or BATCH[a.workload]
-    wl_name = ("DCGAN 512x512 heightmap train step, batch %d/GPU, z=1000 (BASELINE configs[1])" % B
-               if a.workload == "dcgan" else
-               "DCGAN+pix2pix joint train step, 512x512, batch %d/GPU, L1+LSGAN (BASELINE configs[2])" % B)
-    config = {"workload": wl_name, "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+    config = {"workload": WORKLOAD_NAME[a.workload] % B, "per_gpu_batch": B, "global_batch": B * world,
+              "parallelism": "dp%d" % world,
               "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
-              "precision": a.precision}
+              "precision": a.precision,
+              "init": "Glorot-uniform (seed 2); DCGAN discriminator head bias %g so that its ReLU head is alive and the "
+                      "step moves dense gradients" % a.head_bias if a.head_bias else "Glorot-uniform (seed 2)"}
     base = {"metric": "512px heightmap+texture images/sec/GPU at 1/2/4/8 B200; tensor-pipe %",
             "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": config}
 
     if a.impl == "reference":
+        # The reference's own CPU path cannot run here (Python 2 + Theano/Lasagne, SURVEY.md 8c): its restatement
+        # (oracle/, torch-CPU float32, every host thread) is timed on a BOUNDED sample of the same workload -- a few
+        # full train steps on `--cpu-sample` images -- and the line says what it ran: steps, warm-up and batch are the
+        # ones executed, not the GPU arm's.
         if rank != 0:
             return
-        v, dt = cpu_baseline(a.workload, a.cpu_sample, steps=max(1, min(a.steps, 3)), warmup=min(a.warmup, 1))
+        k, w = max(1, min(a.steps, 4)), min(a.warmup, 1)
+        v, dt = cpu_baseline(a.workload, a.cpu_sample, steps=k, warmup=w)
         cores = os.cpu_count() or 1
-        sample = "%d images/step of the same 512x512 workload (full step: fwd+bwd+update)" % a.cpu_sample
-        out = dict(base, impl="reference", value=v, ms_per_step=dt * 1e3, dtype="f32",
+        sample = ("%d timed + %d warm-up full train steps (fwd+bwd+update) on %d images of the same 512x512 workload; "
+                  "the GPU arm's step has %d images" % (k, w, a.cpu_sample, B))
+        cfg_ref = dict(config, per_gpu_batch=a.cpu_sample, global_batch=a.cpu_sample, parallelism="cpu",
+                       precision="float32 (oracle port)", gpu_arm_per_gpu_batch=B)
+        out = dict(base, config=cfg_ref, steps=k, warmup=w, n_gpus=world, impl="reference", value=v,
+                   ms_per_step=dt * 1e3, dtype="f32",
                    cpu_baseline={"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
                    e2e={"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    gpu_launches=0)
@@ -217,91 +317,74 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
-    m = build_model(a.workload, "cuda:%d" % local, a.precision, pg)
-    from util import synthetic_batch
-    Z, X, Y = synthetic_batch(B, 1000, 512, seed=100 + rank)
-    Zd, Xd, Yd = (torch.from_numpy(t).cuda() for t in (Z, X, Y))
-    Zp, Xp, Yp = (torch.from_numpy(t).pin_memory() for t in (Z, X, Y))
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        sync()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # W untimed warm-up steps; never fewer than 3, so that the two buffer-sizing eager steps and the CUDA-graph capture of
-    # the third call are outside the timed region whatever --warmup says
-    for _ in range(max(a.warmup, 3)):
-        m.step_device(Zd, Xd, Yd, True)
-    clocks = ClockSampler(local)
+    res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias)
+    out = None
     if rank == 0:
-        clocks.start()
-    l0 = m.rt.launches
-    ms = timed(lambda: m.step_device(Zd, Xd, Yd, True), a.steps)
-    launches = m.rt.launches - l0
-    clk = clocks.stop() if rank == 0 else None
-    losses = m.losses.cpu().numpy()
-    value = B * world * a.steps / (ms * 1e-3)
-    # end to end through the public API: pinned host inputs, losses read back every step
-    for _ in range(3):                    # the host path captures its own pair of graphs on its third call
-        m.train_fn(Zp, Xp, Yp)
-    ms_e2e = timed(lambda: m.train_fn(Zp, Xp, Yp), a.steps)
-    e2e = B * world * a.steps / (ms_e2e * 1e-3)
-    if rank != 0:
-        _finish(world)
-        return
-    pk = peaks()
-    kname, kflop, kms, kpath = time_dominant_kernel(m)
-    traffic, ncu_tensor = None, None
-    try:       # DRAM bytes per launch / tensor-pipe activity of that kernel from the committed `ncu --set full` capture
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            rec = json.load(f).get(kname, {})
-        traffic, ncu_tensor = rec.get("dram_bytes_per_launch"), rec.get("tensor_pipe_active_pct")
-    except Exception:
-        pass
-    k_tflops = kflop / (kms * 1e-3) / 1e12
-    step_tflops = value / world * GFLOP_PER_IMG[a.workload] / 1e3
-    out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="f16" if a.precision == "fast" else "f32",
-               e2e={"value": e2e, "unit": "images/s",
-                    # a DCGAN-only model never reads the texture batch Y, so train_fn does not copy it
-                    "h2d_bytes_per_step": int(Z.nbytes + X.nbytes + (Y.nbytes if a.workload == "both" else 0)),
-                    "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / a.steps},
-               gpu_launches=int(launches), clocks=clk,
-               roofline={"bound": "tensor", "achieved": k_tflops, "peak": pk["burst"], "unit": "TFLOP/s",
-                         "frac": k_tflops / pk["burst"], "traffic": traffic, "kernel": kname, "kernel_path": kpath,
-                         "kernel_ms": kms, "peak_source": pk["src"] + " (burst: kernel timed alone)",
-                         "ncu_tensor_pipe_active_pct": ncu_tensor,
-                         "step_achieved": step_tflops, "step_frac_of_sustained": step_tflops / pk["sustained"]},
-               losses=[float(v) for v in losses])
-    if not a.no_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
-        v, dt = cpu_baseline(a.workload, a.cpu_sample)
-        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                               "sample": "%d images of the same workload, 1 warm-up + 1 timed full step "
-                                         "(%.1f s/step)" % (a.cpu_sample, dt)}
-    print(json.dumps(out))
-    _finish(world)
+        pk = peaks()
+        kname, kflop, kms, kpath = time_dominant_kernel(m)
+        traffic, ncu_tensor = None, None
+        try:       # DRAM bytes per launch / tensor-pipe activity of that kernel from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                rec = json.load(f).get(kname, {})
+            traffic, ncu_tensor = rec.get("dram_bytes_per_launch"), rec.get("tensor_pipe_active_pct")
+        except Exception:
+            pass
+        k_tflops = kflop / (kms * 1e-3) / 1e12
+        out = dict(base, value=res["value"], ms_per_step=res["ms_per_step"],
+                   dtype={"fast": "f16", "tc32": "bf16x3"}.get(a.precision, "f32"), e2e=res["e2e"],
+                   gpu_launches=res["gpu_launches"], clocks=res["clocks"],
+                   roofline={"bound": "tensor", "achieved": k_tflops, "peak": pk["burst"], "unit": "TFLOP/s",
+                             "frac": k_tflops / pk["burst"], "traffic": traffic, "kernel": kname, "kernel_path": kpath,
+                             "kernel_ms": kms, "peak_source": pk["src"] + " (burst: kernel timed alone)",
+                             "ncu_tensor_pipe_active_pct": ncu_tensor,
+                             # the timed region is a fraction of a second at full clocks: the burst peak is the honest
+                             # denominator of the whole step, the sustained one is quoted beside it
+                             "step_achieved": res["step_achieved_tflops"],
+                             "step_frac_of_burst": res["step_frac_of_burst"],
+                             "step_frac_of_sustained": res["step_frac_of_sustained"]},
+                   losses=res["losses"])
+        if world > 1:
+            out["replicas_identical"] = res["replicas_identical"]
+    del m
+    torch.cuda.empty_cache()
+    # the other single-GPU configurations BASELINE.json names, each as its own full measurement (own model, own
+    # warm-up, own timed steps): configs[2] joint step and configs[4] pix2pix-only step at its per-GPU batch
+    ok = res["replicas_identical"]
+    if not a.no_secondary and a.workload == "dcgan" and not a.batch:
+        sec = {}
+        for wl in ("both", "p2p"):
+            r2, m2 = measure(wl, BATCH[wl], min(a.steps, 20), a.warmup, a.precision, local, rank, world, pg, False, a.head_bias)
+            del m2
+            torch.cuda.empty_cache()
+            ok = ok and r2["replicas_identical"]
+            r2.pop("clocks")
+            sec[wl] = dict(r2, workload=WORKLOAD_NAME[wl] % BATCH[wl], per_gpu_batch=BATCH[wl], steps=min(a.steps, 20),
+                           gflop_per_image=GFLOP_PER_IMG[wl])
+        if out is not None:
+            out["secondary"] = sec
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
+            v, dt = cpu_baseline(a.workload, a.cpu_sample)
+            out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": "%d images of the same workload, 1 warm-up + 1 timed full step "
+                                             "(%.1f s/step)" % (a.cpu_sample, dt)}
+        print(json.dumps(out))
+    _finish(world, ok)
 
 
-def _finish(world):
-    """Multi-rank runs leave without tearing the NCCL communicator down: destroy_process_group() was observed to hang
-    here (the captured CUDA graphs hold collectives of that communicator), and a rank that lingers would stall the
-    launcher.  Everything this process had to say is flushed first."""
+def _finish(world, ok=True):
+    """Tear the NCCL communicator down (the models and their captured graphs, which hold collectives of that
+    communicator, are gone by now); a replica mismatch fails the run."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if os.environ.get("HMGAN_BENCH_HARD_EXIT", "0") == "1":
+            os._exit(0 if ok else 1)
+        dist.destroy_process_group()
+    if not ok:
+        sys.exit("bench.py: data-parallel replicas diverged (parameter checksums differ across ranks)")
 
 
 if __name__ == "__main__":

@@ -69,8 +69,42 @@ class Runtime(object):
         self._wgrad_side = (self.device.type == "cuda" and not self.split
                             and os.environ.get("HMGAN_WGRAD_STREAM", "0") == "1")
         self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "0") == "1"
-        self._tc_ws = None
+        self._tc_ws = {}
+        # lanes: the step forks independent work onto an auxiliary stream (Runtime.fork); per-lane scratch is keyed by
+        # the lane NAME, which is the same during the eager warm-up calls and under CUDA-graph capture
+        self.lane = "main"
+        self._aux_stream = None
+        self._fork_ok = (self.device.type == "cuda" and precision == "fast"
+                         and os.environ.get("HMGAN_FORK", "1") != "0")
         _lib.load()
+
+    class _Fork(object):
+        def __init__(self, rt):
+            self.rt = rt
+
+        def __enter__(self):
+            rt = self.rt
+            if rt._aux_stream is None:
+                rt._aux_stream = torch.cuda.Stream(rt.device)
+            rt._aux_stream.wait_stream(torch.cuda.current_stream(rt.device))      # everything issued so far is visible
+            self.ctx = torch.cuda.stream(rt._aux_stream)
+            self.ctx.__enter__()
+            rt.lane = "aux"
+            return self
+
+        def __exit__(self, *exc):
+            self.rt.lane = "main"
+            return self.ctx.__exit__(*exc)
+
+    def fork(self):
+        """`with rt.fork():` issues the enclosed launches on the auxiliary stream, ordered after everything already
+        issued on the current stream; join() makes the current stream wait for them.  Works eagerly and under CUDA-graph
+        capture (cross-stream edges of the captured graph).  Only independent work may go there."""
+        return Runtime._Fork(self)
+
+    def join(self):
+        if self._aux_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._aux_stream)
 
     def allreduce_mean(self, t):
         """Average a small device tensor over the SyncBN group (sum, then 1/world: gloo has no AVG)."""
@@ -108,15 +142,16 @@ class Runtime(object):
             return
         self.launches += 1
         if name == "hm_tc_conv" and self._splitk:
-            # opt-in split-K for the layers that fill only a few SMs (HMGAN_TC_SPLITK=1, include/hmgan.h): one zeroed
-            # fp32 workspace shared by every convolution of this runtime (calls are serialised on the main stream and
-            # each leaves it zeroed); it is sized during the eager warm-up calls, never while a graph is captured
+            # split-K for the layers that fill only a few SMs (include/hmgan.h): one zeroed fp32 workspace per LANE
+            # (= stream role, see fork(): calls on a stream are serialised and each leaves its workspace zeroed); sized during the eager warm-up calls, never while a graph is captured
             need = _lib.query("hm_tc_conv_ws_bytes", args[0])
             if need > 0:
-                if self._tc_ws is None or self._tc_ws.numel() * 4 < need:
-                    self._tc_ws = self.zeros(((need + 3) // 4,), torch.float32)
+                key = self.lane
+                ws = self._tc_ws.get(key)
+                if ws is None or ws.numel() * 4 < need:
+                    ws = self._tc_ws[key] = self.zeros(((need + 3) // 4,), torch.float32)
                 self.launches += 1               # the finishing pass
-                _lib.call("hm_tc_conv_ws", *args, self._tc_ws.data_ptr(), self._tc_ws.numel() * 4, self.stream)
+                _lib.call("hm_tc_conv_ws", *args, ws.data_ptr(), ws.numel() * 4, self.stream)
                 return
         _lib.call(name, *args, self.stream)
 
@@ -1134,6 +1169,17 @@ class Net(object):
             self.pview(p).copy_(torch.from_numpy(np.ascontiguousarray(v).reshape(-1)))
         self._packed = False
 
+    def param_offset(self, op_index):
+        """Offset in the flat trainable vector of the first parameter owned by ops[op_index:] (parameters are laid out in
+        layer order, so the gradients of ops[op_index:] are the tail [offset, n_trainable))."""
+        offs = []
+        for op in self.ops[op_index:]:
+            for p in (getattr(op, "W", None), getattr(op, "bias", None), getattr(op, "beta", None),
+                      getattr(op, "gamma", None)):
+                if p is not None and p.trainable:
+                    offs.append(self._loc[id(p)][1])
+        return min(offs) if offs else self.n_trainable
+
     def get_grads(self):
         return [self.gview(p).detach().cpu().numpy().reshape(p.shape).copy() for p in self.params if p.trainable]
 
@@ -1179,23 +1225,30 @@ class Net(object):
             op.fwd(self.rt, lo, hi, deterministic)
         return self.out.buf[lo:hi]
 
-    def backward(self, lo, hi, wgrad=True, input_grad=False, wscale=None, ig_range=None):
+    def backward(self, lo, hi, wgrad=True, input_grad=False, wscale=None, ig_range=None, join=True, after_op=None):
         """self.out.grad[lo:hi] must hold d loss / d out.
 
         wscale (fp32 device vector, one weight per sample of [lo,hi)) switches on the single-pass weighted mode of a
         network that supports it (single_pass_ok): the input-gradient chain runs on the plain gradients, every
         weight/bias gradient on the weighted copies (Val.grad_w; self.out.grad_w must hold the weighted d loss / d out),
-        and the network-input gradient is only produced for samples ig_range = (a, b)."""
+        and the network-input gradient is only produced for samples ig_range = (a, b).
+
+        join=False leaves the weight-gradient side stream (Runtime.wgrad_stream) un-joined when the call returns.
+        after_op: {op index: callable}, called once the backward launches of ops[index:] have all been issued (the
+        gradients of their parameters -- the flat range [param_offset(index), n) -- are then complete in stream order)."""
         for v in self.vals:
             v.gw = False
         self.out.gw = True
         self.wscale, self.ig_range = wscale, ig_range
         try:
-            for op in reversed(self.ops):
-                op.bwd(self.rt, lo, hi, wgrad, input_grad)
+            for i in range(len(self.ops) - 1, -1, -1):
+                self.ops[i].bwd(self.rt, lo, hi, wgrad, input_grad)
+                if after_op is not None and i in after_op:
+                    after_op[i]()
         finally:
             self.wscale, self.ig_range = None, None
-            self.rt.join_wgrad_stream()
+            if join:       # join=False: the caller joins (Runtime.join_wgrad_stream) before it touches this network's
+                self.rt.join_wgrad_stream()      # gradients or buffers again; weight gradients keep running meanwhile
 
     def single_pass_ok(self):
         """True if the weighted single-pass backward is implemented for this program: a scalar head, a first layer

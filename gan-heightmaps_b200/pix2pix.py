@@ -137,6 +137,7 @@ class Pix2Pix(object):
         self.train_keys = ['dcgan_gen', 'dcgan_disc', 'p2p_gen', 'p2p_recon', 'p2p_disc']
         self._stage = {}
         self._graphs = {}
+        self._pending, self._reduced = [], set()
         self._graphs_ok = rt.device.type == "cuda" and os.environ.get("HMGAN_CUDA_GRAPHS", "1") != "0"
         self.train_fn = lambda Z, X, Y: self._step_host(Z, X, Y, True)
         self.loss_fn = lambda Z, X, Y: self._step_host(Z, X, Y, False)
@@ -187,6 +188,27 @@ class Pix2Pix(object):
     # ------------------------------------------------------------------ #
     # the step (reference pix2pix.py:87-147)
     # ------------------------------------------------------------------ #
+    def _allreduce_async(self, flat):
+        """Sum all-reduce of (a slice of) a network's flat gradient over the data-parallel group, issued NOW behind
+        everything already launched -- including the weight gradients still running on the side stream -- and awaited
+        only before the update, so it overlaps the backward passes that follow (NCCL over NVLink)."""
+        if self.pg is None:
+            return
+        import torch.distributed as dist
+        rt = self.rt
+        side = rt._wgrad_stream if rt._wgrad_forked else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(rt.device))
+            with torch.cuda.stream(side):
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        else:
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self._pending.append(work)
+        base = flat._base if flat._base is not None else flat
+        for net in self._nets():
+            if net.gflat is base:
+                self._reduced.add(id(net))
+
     def _adv(self, net, h, dh, target, slot, gscale):
         """adv_loss(out, target).mean() of pix2pix.py:102-110 on a (half) batch of
         discriminator outputs; optionally its gradient."""
@@ -264,30 +286,48 @@ class Pix2Pix(object):
                 n.pack()
 
     def _step_eager(self, Zd, Xd, Yd, train=True, part=0):
-        """part 0: the whole step.  part 1: only what depends on Z alone (G's forward pass); part 2: everything else.
-        The host path captures the two parts as separate CUDA graphs so that the X/Y upload overlaps part 1."""
+        """part 0: the whole step.  part 1: only what depends on Z alone (G's forward pass); part 3: D(x), which depends
+        on X alone; part 2: everything else (given parts 1 and 3).  The host path captures the parts as separate CUDA
+        graphs so that the X/Y upload overlaps part 1 and D(x) runs beside the rest of it (_step_host_overlapped)."""
         rt = self.rt
         B = int(Xd.shape[0])
         S = self.in_shp
         ls = rt.loss_scale
+        ca = 1 if self.is_a_grayscale else 3
+        fork = part == 0 and self.have_dcgan and rt._fork_ok      # D(x) beside G(z) on the auxiliary stream
         if part in (0, 1):
             self.losses.zero_()
             if self.have_dcgan:
                 self.G.ensure(B)
                 self.D.ensure(2 * B, input_grads=(0,))
+                if fork:
+                    # D(x) needs only X: it runs beside G's forward pass, whose 4x4..64x64 layers fill a fraction of the
+                    # SMs.  (Without BatchNorm D treats every sample independently, so two half-batch passes equal one.)
+                    with rt.fork():
+                        self._load_nchw(Xd, self.D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
+                        self.D.forward(2 * B, 0, B)                         # D(x)            :94
                 rt.call("hm_cast", _ptr(Zd), _lib.F32, _ptr(self.G.inputs[0].buf), rt.cd, Zd.numel())
                 self.G.forward(B)                                           # G(z)            :92
             if part == 1:
                 return self.losses
+        if part == 3:
+            self._load_nchw(Xd, self.D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
+            self.D.forward(2 * B, 0, B)                                     # D(x)            :94
+            return self.losses
         upd = []
         if self.have_dcgan:
             G, D = self.G, self.D
             do = train and self.train_mode in ('both', 'dcgan')
-            ca = 1 if self.is_a_grayscale else 3
-            self._load_nchw(Xd, D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
             gz = G.out.buf[:B]
             self._copy(gz, D.inputs[0].buf[B:2 * B])
-            h = D.forward(2 * B)                                            # D(x), D(G(z))   :94-95
+            if fork or (part == 2 and rt._fork_ok):
+                if fork:
+                    rt.join()                                               # D(x) done (and D's packs, if it made them)
+                D.forward(2 * B, B, 2 * B)                                  # D(G(z))         :95
+            else:
+                self._load_nchw(Xd, D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
+                D.forward(2 * B)                                            # D(x), D(G(z))   :94-95
+            h = D.out.buf[:2 * B]
             dh = D.out.grad if do else None
             self._adv(D, h[:B], dh[:B] if do else None, 1., 1, ls)          # disc_loss_dcgan :108
             if do and self._single_pass:
@@ -303,11 +343,23 @@ class Pix2Pix(object):
                 rt.call("hm_adv_loss_pair", _ptr(h[B:]), _ptr(dh[B:2 * B]), _ptr(dhw[B:2 * B]), _ptr(ws[B:]),
                         _ptr(ws[2 * B:]), rt.cd, R, head["G"], _lib.ACT[head["out_act"]], 1 if self.lsgan else 0,
                         1 if head["relu_head"] else 0, ls, _ptr(self.losses[1:]), _ptr(self.losses[0:]))
-                D.backward(0, 2 * B, wgrad=True, input_grad=True, wscale=ws[:2 * B], ig_range=(B, 2 * B))
+                # D's weight gradients stay on the side stream (un-joined) while G's backward pass runs: nothing below
+                # touches D's buffers again before the join at the end of G.backward
+                D.backward(0, 2 * B, wgrad=True, input_grad=True, wscale=ws[:2 * B], ig_range=(B, 2 * B), join=False)
+                self._allreduce_async(D.gflat)                  # under G's backward pass
                 n_in = D.inputs[0].grad[B:2 * B].numel() // B
                 rt.call("hm_scale_rows", _ptr(D.inputs[0].grad[B:2 * B]), _ptr(ws[2 * B:]), _ptr(G.out.grad[:B]),
                         rt.cd, B, n_in)
-                G.backward(0, B, wgrad=True)
+                # G's flat gradient in two buckets: everything above the dense layer's block as soon as it is complete
+                # (the dense layer's 8.2M-element gradient, the head of the flat vector, is produced last)
+                hook = None
+                if self.pg is not None and len(G.ops) > 4:
+                    k = 3
+                    off = G.param_offset(k)
+                    if 0 < off < G.n_trainable:
+                        hook = {k: lambda: self._allreduce_async(G.gflat[off:])}
+                G.backward(0, B, wgrad=True, after_op=hook)
+                self._allreduce_async(G.gflat[:off] if hook else G.gflat)
                 upd += [G, D]
             else:
                 self._adv(D, h[B:], dh[B:2 * B] if do else None, 0., 1, ls)
@@ -324,7 +376,6 @@ class Pix2Pix(object):
             do = train and self.train_mode in ('both', 'p2p')
             P.ensure(B)
             Dp.ensure(2 * B, input_grads=(1,))
-            ca = 1 if self.is_a_grayscale else 3
             cb = 1 if self.is_b_grayscale else 3
             self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
             a_in, b_in = Dp.inputs
@@ -358,7 +409,11 @@ class Pix2Pix(object):
                 import torch.distributed as dist
                 world = dist.get_world_size(self.pg)
                 for net in upd:                                  # data-parallel: sum of per-rank mean gradients
-                    dist.all_reduce(net.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+                    if id(net) not in self._reduced:
+                        self._allreduce_async(net.gflat)
+                for work in self._pending:                       # the current stream waits for every reduction
+                    work.wait()
+                self._pending, self._reduced = [], set()
             for net in upd:
                 net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
                 net.pack()       # packed copies follow the master weights inside the step (and inside its CUDA graph)
@@ -396,6 +451,15 @@ class Pix2Pix(object):
             gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(gA):
                 self._step_eager(st["Z"], st["X"], st["Y"], train, part=1)
+            st["gC"] = None
+            if self.have_dcgan and self.rt._fork_ok:        # D(x) as its own graph, replayed on the upload stream
+                st["gC"] = torch.cuda.CUDAGraph()
+                self.rt.lane = "aux"
+                try:
+                    with torch.cuda.graph(st["gC"], pool=gA.pool()):
+                        self._step_eager(st["Z"], st["X"], st["Y"], train, part=3)
+                finally:
+                    self.rt.lane = "main"
             with torch.cuda.graph(gB, pool=gA.pool()):
                 self._step_eager(st["Z"], st["X"], st["Y"], train, part=2)
             st["launches"] = self.rt.launches - l0
@@ -409,6 +473,8 @@ class Pix2Pix(object):
         st["gA"].replay()
         with torch.cuda.stream(st["side"]):        # the previous step ended with a host synchronisation: X/Y are free
             st["X"].copy_(Xs, non_blocking=True)
+            if st["gC"] is not None:
+                st["gC"].replay()                   # D(x) as soon as X has landed, beside G's forward pass
             if Ys is not None:
                 st["Y"].copy_(Ys, non_blocking=True)
             st["ev"].record(st["side"])

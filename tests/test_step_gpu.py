@@ -15,15 +15,20 @@ PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 if PKG not in sys.path:
     sys.path.insert(0, PKG)
 
-from test_engine_cpu import TINY, build_pair, _check_grads, _check_params   # noqa: E402
+from test_engine_cpu import TINY, build_pair, _check_grads, _check_grads_l2, _check_params   # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
 
-def test_gate64_dcgan_step_parity():
-    """BASELINE.json configs[0]."""
+@pytest.mark.parametrize("precision", ["parity", "tc32"])
+def test_gate64_dcgan_step_parity(precision):
+    """BASELINE.json configs[0], in both float32-grade modes: 'parity' (SIMT fp32 kernels) and 'tc32' (the tcgen05
+    kernels of the benchmarked path on three-plane bf16 operand splits, 7 of the 11 convolutions at these widths)."""
     cfg = S.experiment_kwargs('gate64')
-    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda")
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision=precision)
+    if precision == "tc32":
+        paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
+        assert paths.count("tcgen05") >= 7, paths
     for it in range(3):
         Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=10 + it)
         lo = om.train_fn(Z, X, Y)
@@ -52,11 +57,17 @@ def test_joint_512_step_parity(bilinear):
     np.testing.assert_allclose(m.gen_fn_det(X[:1]), om.gen_fn_det(X[:1]), rtol=2e-3, atol=2e-4)
 
 
-def test_full_width_dcgan_forward_and_losses_parity():
+@pytest.mark.parametrize("precision", ["parity", "tc32"])
+def test_full_width_dcgan_forward_and_losses_parity(precision):
     """BASELINE configs[1] architecture (full widths, 512x512, z=1000) at batch 2: G(z) and the two DCGAN
-    losses against the oracle; range properties of the outputs."""
+    losses against the oracle at 1e-3; range properties of the outputs.  tc32: 15 of the 17 convolutions run on the
+    tcgen05 kernels (all but the one-channel ends)."""
     cfg = S.experiment_kwargs('test1_nobn_bilin_both')
-    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda")
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision=precision)
+    if precision == "tc32":
+        paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
+        assert paths.count("tcgen05") >= 15, paths
+    _set_head_bias(om, m, 0.6)
     Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=1)
     lo = om.loss_fn(Z, X, Y)
     lm = m.loss_fn(Z, X, Y)
@@ -64,6 +75,89 @@ def test_full_width_dcgan_forward_and_losses_parity():
     gz = m.z_fn_det(Z)
     assert gz.shape == (2, 1, 512, 512) and gz.min() > 0 and gz.max() < 1
     np.testing.assert_allclose(gz, om.z_fn_det(Z), rtol=1e-3, atol=1e-5)
+
+
+def _set_head_bias(om, m, value):
+    """At the Glorot initialisation the ReLU head of the full-width DCGAN discriminator is dead on these inputs (D(.) = 0,
+    both losses exactly 1, every gradient exactly 0): a head bias puts D(.) near `value`, where the step is informative."""
+    vals = m.D.get_all_param_values()
+    vals[-1][:] = value
+    m.D.set_all_param_values(vals)
+    with torch.no_grad():
+        om.params['D'][-1].fill_(value)
+
+
+# Gradient bounds of the full-width step tests.  The discriminator's max-pools and LeakyReLU kinks make the per-array
+# gradient error grow like the SQUARE ROOT of the forward perturbation: every unit whose two candidates (or whose sign)
+# are closer than the perturbation re-routes its whole gradient, the number of such units is proportional to the
+# perturbation, and the L2 error to the root of that number.  Measured on B200 against the oracle (tools/dbg_tc32.py,
+# profiles/r2_parity_sensitivity.txt; DCGAN 512x512 full width, relative L2 of the worst weight array of G / of D):
+#     SIMT float32 'parity' (forward agrees to ~1e-6)     batch 2:  5.0e-3 / 8.4e-4
+#     'tc32' on tcgen05   (forward agrees to ~1e-5)        batch 2:  2.9e-2 / 6.5e-3      batch 8: 2.3e-2 / 3.6e-3
+#     'fast' fp16 on tcgen05 (forward agrees to ~5e-4)     batch 2:  1.8e-1 / 4.6e-2      batch 8: 1.5e-1 / 2.1e-2
+# while every convolution kernel by itself agrees with the SIMT float32 kernel to 2.5e-5 (tests/test_tc_gpu.py) and a
+# wrong kernel moves these numbers to 0.7 - 1.0.  The bounds below are 2x the measured values.
+FULL_WIDTH_BOUNDS = {
+    #            losses per step (rtol)   G grads  D grads
+    "tc32": ((1e-3, 2e-3, 1e-2), 6e-2, 1e-2),
+    "fast": ((1e-3, 5e-3, 5e-2), 0.3, 5e-2),
+}
+
+
+@pytest.mark.parametrize("precision", ["tc32", "fast"])
+def test_full_width_dcgan_train_steps_track_oracle(precision):
+    """The benchmarked configuration (BASELINE configs[1]: DCGAN 512x512, z=1000, full widths) at batch 8, three train_fn
+    steps against the oracle on the path bench.py times -- 'fast' (fp16 tcgen05, CUDA graphs, single-pass discriminator
+    backward, side streams) -- and on the same kernels in float32-grade 'tc32' mode.  Losses per step, every
+    weight-gradient array of the first step (relative L2; biases in front of a BatchNorm have a zero true gradient and
+    are compared with the network's gradient norm) within the bounds justified above, and the direction of every weight
+    array's accumulated update after three RMSprop steps."""
+    cfg = S.experiment_kwargs('test1_nobn_bilin_both')
+    om, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision=precision, lr=1e-4)
+    _set_head_bias(om, m, 0.6)
+    loss_tol, g_tol, d_tol = FULL_WIDTH_BOUNDS[precision]
+    p0 = {k: [a.copy() for a in om.get_all_param_values(k)] for k in ('G', 'D')}
+    for it in range(3):
+        Z, X, Y = S.synthetic_batch(8, cfg['latent_dim'], 512, seed=10 + it)
+        lo = om.train_fn(Z, X, Y)
+        lm = m.train_fn(Z, X, Y)
+        assert np.all(np.isfinite(lm))
+        np.testing.assert_allclose(lm[:2], lo[:2], rtol=loss_tol[it], atol=1e-6)
+        if it == 0:
+            _check_grads_l2(om, m, ('G', 'D'), d_tol, scale=1.0 / m.rt.loss_scale, tol_by_net={'G': g_tol})
+    # updated parameters: RMSprop turns a gradient into a step of ~lr*sqrt(10) times its SIGN, so weights whose gradient
+    # is smaller than the gradient error may step the other way; the comparable quantity is the direction of the
+    # accumulated update of each weight array (cosine with the oracle's)
+    for k, net in (('G', m.G), ('D', m.D)):
+        for a, b, a0, q in zip(net.get_all_param_values(), om.get_all_param_values(k), p0[k], net.params):
+            if not (q.trainable and q.kind == "W"):
+                continue
+            ua, ub = (a - a0).ravel().astype(np.float64), (b - a0).ravel().astype(np.float64)
+            cos = float(ua @ ub / (np.linalg.norm(ua) * np.linalg.norm(ub) + 1e-30))
+            assert cos >= UPDATE_COS[precision], (k, a.shape, cos)
+
+
+UPDATE_COS = {"tc32": 0.98, "fast": 0.95}      # measured on B200: 0.996 and 0.987 (generator, worst array)
+
+
+def test_full_width_joint_step_parity_on_tensor_cores():
+    """BASELINE configs[2] architecture (all four networks at full width, 512x512, bilinear U-Net) at batch 2 in tc32
+    mode: 34 of the 40 convolutions on the tcgen05 kernels (forward, input gradient, weight gradient; stride-2,
+    concat + bilinear, phase-decomposed and row-box variants).  The five losses and P(x) against the oracle at 1e-3.
+    Weight gradients (relative L2): PatchGAN <= 5e-3 (measured 7e-4); U-Net <= 0.1 -- the step is ill-conditioned at
+    batch 2 (the 1x1 / 2x2 bottleneck BatchNorms see 2..8 values per channel): the SIMT float32 'parity' mode measures
+    3.4e-2 against the same oracle, tc32 2.3e-2 (profiles/r2_parity_sensitivity.txt)."""
+    cfg = S.experiment_kwargs('test1_nobn_bilin_both')
+    om, m = build_pair(cfg, 'both', device="cuda", precision="tc32")
+    paths = [op.path for net in (m.G, m.D, m.P, m.Dp) for op in net.ops if hasattr(op, "path")]
+    assert paths.count("tcgen05") >= 34, paths
+    _set_head_bias(om, m, 0.6)
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=2)
+    np.testing.assert_allclose(m.gen_fn_det(X[:1]), om.gen_fn_det(X[:1]), rtol=1e-3, atol=1e-4)
+    lo = om.train_fn(Z, X, Y)
+    lm = m.train_fn(Z, X, Y)
+    np.testing.assert_allclose(lm, lo, rtol=1e-3, atol=1e-6)
+    _check_grads_l2(om, m, ('Dp', 'P'), 5e-3, tol_by_net={'P': 0.1})
 
 
 def test_fast_mode_tracks_parity_mode():
@@ -163,8 +257,9 @@ def test_single_pass_discriminator_backward_equals_two_passes_at_full_width(monk
     """BASELINE configs[1] architecture (512x512, full width) at batch 2, fast mode: the weighted single backward pass
     through D (hm_adv_loss_pair: disc-loss weights on the weight gradients, gen-loss weights on dG(z)) against the
     reference's two separate passes (pix2pix.py:107-108,131-135) on the same weights and inputs.  Same kernels, same
-    fp16 storage; only the scalar per-sample factors move, so every gradient array agrees to 2e-2 in relative L2 norm
-    (fp16 rounding of differently-scaled intermediates) and the losses to 1e-5."""
+    fp16 storage; only the scalar per-sample factors move, so every gradient array agrees to 5e-2 in relative L2 norm
+    (fp16 rounding of differently-scaled intermediates; measured 1.5e-2 .. 2.6e-2 on the first layer's array depending on
+    whether the small layers split K) and the losses to 1e-5."""
     cfg = S.experiment_kwargs('test1_nobn_bilin_both')
     Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=3)
     res = {}
@@ -187,4 +282,4 @@ def test_single_pass_discriminator_backward_equals_two_passes_at_full_width(monk
             if k == "G" and res["0"][3][i].kind == "b" and i < len(res["0"][idx]) - 1:
                 continue                 # biases in front of a BatchNorm: the true gradient is zero, both are noise
             rel = float(np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
-            assert rel <= 2e-2, (k, i, a.shape, rel)
+            assert rel <= 5e-2, (k, i, a.shape, rel)

@@ -31,7 +31,7 @@ for name, prec in [(n, p) for n in (args or ["wide64", "gate64", "dcgan512", "jo
         cfg, mode, p2p, size = S.experiment_kwargs('test1_nobn_bilin_both'), 'dcgan', False, 512
     else:
         cfg, mode, p2p, size = S.experiment_kwargs('test1_nobn_bilin_both'), 'both', True, 512
-    om, m = build_pair(cfg, mode, with_p2p=p2p, device="cuda", precision=prec)
+    om, m = build_pair(cfg, mode, with_p2p=p2p, device="cuda", precision=prec, lr=float(kv.get("lr", 1e-3)))
     if head_bias is not None:
         vals = m.D.get_all_param_values()
         vals[-1][:] = head_bias
@@ -43,6 +43,7 @@ for name, prec in [(n, p) for n in (args or ["wide64", "gate64", "dcgan512", "jo
     paths = [op.path for _, n in nets for op in n.ops if hasattr(op, "path")]
     print("== %s precision=%s B=%d: %d of %d convolutions on tcgen05" % (name, prec, B, paths.count("tcgen05"), len(paths)),
           flush=True)
+    p_init = {k: [a.copy() for a in om.get_all_param_values(k)] for k, _ in nets}
     for it in range(steps):
         Z, X, Y = S.synthetic_batch(B, cfg['latent_dim'], size, seed=10 + it)
         lo, lm = om.train_fn(Z, X, Y), m.train_fn(Z, X, Y)
@@ -61,10 +62,13 @@ for name, prec in [(n, p) for n in (args or ["wide64", "gate64", "dcgan512", "jo
                     k, max(r[0] for r in w), float(np.median([r[0] for r in w])),
                     " ".join("%.1e" % r[0] for r in rels)), flush=True)
     for k, net in nets:
-        errs = []
-        for a, b in zip(net.get_all_param_values(), om.get_all_param_values(k)):
-            errs.append(float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)))
-        print("  params %-2s after %d steps: worst max-norm rel %.2e" % (k, steps, max(errs)))
+        cs = []
+        for a, b, a0, q in zip(net.get_all_param_values(), om.get_all_param_values(k), p_init[k], net.params):
+            if q.trainable and q.kind == "W":
+                ua, ub = (a - a0).ravel().astype(np.float64), (b - a0).ravel().astype(np.float64)
+                cs.append(float(ua @ ub / (np.linalg.norm(ua) * np.linalg.norm(ub) + 1e-30)))
+        print("  params %-2s after %d steps: cosine of the accumulated update per W array: min %.3f | %s" % (
+            k, steps, min(cs), " ".join("%.3f" % c for c in cs)))
     if p2p:
         Zx = X[:1]
         a, b = m.gen_fn_det(Zx), om.gen_fn_det(Zx)
