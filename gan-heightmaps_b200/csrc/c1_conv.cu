@@ -16,7 +16,11 @@
 // patch in shared memory (registers prefetch the next tile's patch), each builder thread then writes ITS row of the
 // [128][64] fp16 operand tile in the 128B-swizzled K-major layout tcgen05 reads (K = 36, zero-padded to 48), one
 // elected thread issues 3 tcgen05.mma (M=128, N, K=16) into a double-buffered TMEM accumulator, four epilogue warps
-// drain it.  Weights ([N][64] fp16, <= 32 KB) are loaded once per CTA by TMA.
+// drain it.  Weights ([N][64] fp16, <= 32 KB) are loaded once per CTA by TMA.  The epilogue stages its [128 px][64 ch]
+// output tile (and the argmax bytes) in shared memory, 128B- / 64B-swizzled, and ONE thread hands each tile to the TMA
+// unit (cp.async.bulk.tensor store, clipped at the image border): per-thread 16-byte stores of NHWC rows touch 32
+// different 128-byte lines per warp instruction, and at 24 KB of output per 384 cycles of MMA work the LSU transaction
+// rate, not HBM, was what bounded this kernel (round-2 profile: 1.9 TB/s, unchanged by a second epilogue warp group).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -31,6 +35,8 @@ constexpr int C1_STAGES = 3;
 constexpr int C1_A_BYTES = 128 * 128;  // one [128 rows][64 k] fp16 operand tile
 constexpr int C1_PATCH_WORDS = 784;    // >= max over (bw,bh) of (2bh+4)*(bw+2) 32-bit words (780 at bw=128 or bw=1)
 constexpr int C1_PRE = 7;              // patch words per builder thread
+constexpr int C1_Y_STAGE = 128 * 128;  // output staging: [128 px][64 ch] fp16, SWIZZLE_128B
+constexpr int C1_I_STAGE = 128 * 64;   // argmax staging:  [128 px][64 ch] uint8, SWIZZLE_64B
 
 struct C1Params {
   int B, H, W, Hq, Wq;
@@ -52,27 +58,30 @@ __device__ __forceinline__ float c1_act(float v, float slope) {
   return v;
 }
 
-// it0 / itstep: this warp group drains the tiles it0, it0 + itstep, ... of the CTA's tile sequence (0 / 1: all of them;
-// g / 2: group g of two alternates, i.e. owns TMEM accumulator g)
+// The four epilogue warps (128 threads, named barrier 2).  stage_s / stage_g: shared-window / generic address of the
+// output staging area: two [y tile | idx tile] buffers, alternating per tile.
 template <int ACT>
-__device__ __forceinline__ void c1_epilogue(const C1Params& p, uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
-                                            const float* bias_s, int warp, int lane, int it0 = 0, int itstep = 1) {
+__device__ __forceinline__ void c1_epilogue(const C1Params& p, const CUtensorMap* tmY, const CUtensorMap* tmI,
+                                            uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
+                                            const float* bias_s, uint32_t stage_s, uint8_t* stage_g, int warp, int lane) {
   const int q = warp & 3;
   const int row = q * 32 + lane;
-  const int iy = row / p.bw, ix = row - iy * p.bw;
   const int per_img = p.tiles_x * p.tiles_y;
   const int accstride = p.pool ? 256 : 64;
-  int it = it0;
-  for (int t = blockIdx.x + it0 * gridDim.x; t < p.n_tiles; t += itstep * gridDim.x, it += itstep) {
+  const bool issuer = q == 0 && lane == 0;
+  int it = 0;
+  for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
     const int acc = it & 1;
+    uint8_t* ybuf = stage_g + (it & 1) * (C1_Y_STAGE + C1_I_STAGE);
+    uint8_t* ibuf = ybuf + C1_Y_STAGE;
+    // the TMA store of tile it-2 has finished READING this staging buffer
+    if (issuer) bulk_wait_group_read<1>();
+    named_bar_sync(2, 128);
     mbar_wait(t_full0 + 8u * acc, (it >> 1) & 1);
     tc_fence_after();
     const int b = t / per_img, rem = t - b * per_img;
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-    const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
-    const bool valid = wy < p.Hq && wx < p.Wq;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * accstride;
-    const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
     if (p.pool) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -82,7 +91,6 @@ __device__ __forceinline__ void c1_epilogue(const C1Params& p, uint32_t tmem_bas
         tmem_ld16(taddr + 128 + c0, v2);
         tmem_ld16(taddr + 192 + c0, v3);
         tmem_ld_wait();
-        if (!valid) continue;
         uint32_t packed[8], kb[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
@@ -101,10 +109,12 @@ __device__ __forceinline__ void c1_epilogue(const C1Params& p, uint32_t tmem_bas
           __half2 h = __floats2half2_rn(r2[0], r2[1]);
           packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint4* d4 = reinterpret_cast<uint4*>(p.y + o + c0);
-        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-        *reinterpret_cast<uint4*>(p.idx + o + c0) = make_uint4(kb[0], kb[1], kb[2], kb[3]);
+        const int ch = c0 >> 3;                                // 16-byte chunk of the row's 128 bytes
+        *reinterpret_cast<uint4*>(ybuf + sw128_off(row, ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(ybuf + sw128_off(row, ch + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        // SWIZZLE_64B: 16-byte chunk index (address bits 4-5) XOR address bits 7-8 = (row >> 1) & 3 at a 64-byte pitch
+        *reinterpret_cast<uint4*>(ibuf + row * 64 + ((((c0 >> 4) ^ (row >> 1)) & 3) << 4)) =
+            make_uint4(kb[0], kb[1], kb[2], kb[3]);
       }
     } else {
 #pragma unroll 1
@@ -112,7 +122,6 @@ __device__ __forceinline__ void c1_epilogue(const C1Params& p, uint32_t tmem_bas
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        if (!valid) continue;
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -120,25 +129,37 @@ __device__ __forceinline__ void c1_epilogue(const C1Params& p, uint32_t tmem_bas
                                         c1_act<ACT>(__uint_as_float(v[j + 1]) + bias_s[c0 + j + 1], p.slope));
           packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint4* d4 = reinterpret_cast<uint4*>(p.y + o + c0);
 #pragma unroll
-        for (int j = 0; j < 4; j++) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        for (int j = 0; j < 4; j++)
+          *reinterpret_cast<uint4*>(ybuf + sw128_off(row, (c0 >> 3) + j)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       }
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(t_empty0 + 8u * acc);
+    if (lane == 0) mbar_arrive(t_empty0 + 8u * acc);              // the accumulator is drained
+    fence_proxy_async();                                          // staging writes -> visible to the TMA unit
+    named_bar_sync(2, 128);
+    if (issuer) {
+      const uint32_t ys = stage_s + (it & 1) * (C1_Y_STAGE + C1_I_STAGE);
+      tma_store_4d(tmY, ys, 0, tx * p.bw, ty * p.bh, b);
+      if (p.pool) tma_store_4d(tmI, ys + C1_Y_STAGE, 0, tx * p.bw, ty * p.bh, b);
+      bulk_commit_group();
+    }
   }
+  if (issuer) bulk_wait_group<0>();                               // every store has landed before the CTA exits
 }
 
 __global__ void __launch_bounds__(C1_THREADS, 1)
-    c1s2_conv_kernel(const __grid_constant__ CUtensorMap tmW, const C1Params p) {
+    c1s2_conv_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
+                     const __grid_constant__ CUtensorMap tmI, const C1Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t w_bytes = (uint32_t)p.N * 128u;
   const uint32_t a_off = w_bytes;
-  const uint32_t patch_off = a_off + C1_STAGES * C1_A_BYTES;
+  const uint32_t stage_off = a_off + C1_STAGES * C1_A_BYTES;             // 1024-aligned: two [y | idx] output buffers
+  const uint32_t patch_off = stage_off + 2 * (C1_Y_STAGE + C1_I_STAGE);
   const uint32_t ctrl_off = patch_off + 2 * C1_PATCH_WORDS * 4;
   const uint32_t ctrl = base + ctrl_off;
   const uint32_t w_full = ctrl;
@@ -166,6 +187,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1)
     }
     mbar_fence_init();
     prefetch_tensormap(&tmW);
+    prefetch_tensormap(&tmY);
+    prefetch_tensormap(&tmI);
   }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
   if (warp >= 1 && warp <= 4) {            // zero the operand stages once: chunk 5 and the tail of chunk 4 stay zero
@@ -253,10 +276,12 @@ __global__ void __launch_bounds__(C1_THREADS, 1)
     }
   } else {
     // ===================== epilogue (warps 5..8) =====================
+    const uint32_t ss = base + stage_off;
+    uint8_t* sg = gbase + stage_off;
     switch (p.act) {
-      case HM_ACT_LRELU: c1_epilogue<HM_ACT_LRELU>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane); break;
-      case HM_ACT_RELU: c1_epilogue<HM_ACT_RELU>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane); break;
-      default: c1_epilogue<HM_ACT_LINEAR>(p, tmem_base, t_full(0), t_empty(0), bias_s, warp, lane); break;
+      case HM_ACT_LRELU: c1_epilogue<HM_ACT_LRELU>(p, &tmY, &tmI, tmem_base, t_full(0), t_empty(0), bias_s, ss, sg, warp, lane); break;
+      case HM_ACT_RELU: c1_epilogue<HM_ACT_RELU>(p, &tmY, &tmI, tmem_base, t_full(0), t_empty(0), bias_s, ss, sg, warp, lane); break;
+      default: c1_epilogue<HM_ACT_LINEAR>(p, &tmY, &tmI, tmem_base, t_full(0), t_empty(0), bias_s, ss, sg, warp, lane); break;
     }
   }
   tc_fence_before();
@@ -327,8 +352,32 @@ extern "C" int hm_c1s2_conv(const void* x, const void* wk, const float* bias, vo
       return HM_ERR_CUDA;
     }
   }
+  // output tiles leave through TMA stores: y[B,Hq,Wq,64] fp16 (128-byte rows, SWIZZLE_128B) and idx (64-byte rows,
+  // SWIZZLE_64B), box {64 ch, bw, bh, 1}; the part of a tile beyond the image is clipped by the TMA unit
+  CUtensorMap tmY, tmI;
+  {
+    cuuint64_t dims[4] = {64, (cuuint64_t)p.Wq, (cuuint64_t)p.Hq, (cuuint64_t)B};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint64_t sy[3] = {128, (cuuint64_t)p.Wq * 128, (cuuint64_t)p.Hq * p.Wq * 128};
+    CUresult r = c1_encode_fn()(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, y, dims, sy, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && idx) {
+      cuuint64_t si[3] = {64, (cuuint64_t)p.Wq * 64, (cuuint64_t)p.Hq * p.Wq * 64};
+      r = c1_encode_fn()(&tmI, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, idx, dims, si, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      tmI = tmY;
+    }
+    if (r != CUDA_SUCCESS) {
+      set_error("hm_c1s2_conv: cuTensorMapEncodeTiled failed for the output (CUresult %d)", (int)r);
+      return HM_ERR_CUDA;
+    }
+  }
   // >= 120 KB so that only one CTA (which may own all 512 TMEM columns) is resident per SM
-  size_t smem = 1024 + (size_t)ncols * 128 + C1_STAGES * C1_A_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024;
+  size_t smem = 1024 + (size_t)ncols * 128 + C1_STAGES * C1_A_BYTES + 2 * (C1_Y_STAGE + C1_I_STAGE) +
+                2 * C1_PATCH_WORDS * 4 + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;
   static bool attr = false;
   if (!attr) {
@@ -340,7 +389,7 @@ extern "C" int hm_c1s2_conv(const void* x, const void* wk, const float* bias, vo
     attr = true;
   }
   int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  c1s2_conv_kernel<<<grid, C1_THREADS, smem, (cudaStream_t)stream>>>(tmW, p);
+  c1s2_conv_kernel<<<grid, C1_THREADS, smem, (cudaStream_t)stream>>>(tmW, tmY, tmI, p);
   HM_CHECK_LAUNCH("hm_c1s2_conv");
   return HM_OK;
 }
@@ -476,23 +525,29 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       const int t = blockIdx.x + it * gridDim.x;
       const int b = t / per_img, rem = t - b * per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int wy = ty * p.bh + iy, wx = tx * p.bw + ix;
-      const bool valid = wy < p.Hq && wx < p.Wq;
-      const size_t o = (((size_t)b * p.Hq + wy) * p.Wq + wx) * 64;
       const float isc = p.img_scale ? p.img_scale[b] : 1.f;
-      // issue every global load of this tile up front (24 gradient / activation / argmax loads + the patch words):
-      // one round trip per tile instead of three
+      // issue every global load of this tile up front (24 gradient / activation / argmax loads + the patch words): one
+      // round trip per tile instead of three.  The G' tiles are built chunk-wise -- (window r, 8-channel chunk cc) needs
+      // only g, p, idx at that position -- so the loads are laid out for coalescing, not per window: in pass k a warp
+      // covers 4 consecutive windows x 8 chunks = 512 contiguous bytes of g and of p (256 of idx), i.e. 4 + 4 + 2
+      // 128-byte lines per three instructions.  (One thread per window row touched 32 lines per instruction; the LSU
+      // transaction rate, not HBM, bounded the kernel: round-2 profile.)
+      const int sub = tb >> 3, cc = tb & 7;
       uint4 gv[8], pv[8];
       uint2 kv[8];
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
-        if (valid) {
-          gv[c] = *reinterpret_cast<const uint4*>(p.g + o + c * 8);
-          pv[c] = *reinterpret_cast<const uint4*>(p.pl + o + c * 8);
-          kv[c] = *reinterpret_cast<const uint2*>(p.idx + o + c * 8);
+      for (int k = 0; k < 8; k++) {
+        const int r = k * 16 + sub;
+        const int riy = r / p.bw, rix = r - riy * p.bw;
+        const int rwy = ty * p.bh + riy, rwx = tx * p.bw + rix;
+        if (rwy < p.Hq && rwx < p.Wq) {
+          const size_t ro = (((size_t)b * p.Hq + rwy) * p.Wq + rwx) * 64 + cc * 8;
+          gv[k] = *reinterpret_cast<const uint4*>(p.g + ro);
+          pv[k] = *reinterpret_cast<const uint4*>(p.pl + ro);
+          kv[k] = *reinterpret_cast<const uint2*>(p.idx + ro);
         } else {
-          gv[c] = pv[c] = make_uint4(0, 0, 0, 0);
-          kv[c] = make_uint2(0, 0);
+          gv[k] = pv[k] = make_uint4(0, 0, 0, 0);
+          kv[k] = make_uint2(0, 0);
         }
       }
       uint32_t pre[C1_PRE];
@@ -524,7 +579,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       const uint32_t f_pos = __half_as_ushort(__float2half_rn(isc)) * 0x00010001u;
       const uint32_t f_neg = __half_as_ushort(__float2half_rn(neg * isc)) * 0x00010001u;
 #pragma unroll
-      for (int c = 0; c < 8; c++) {
+      for (int c = 0; c < 8; c++) {         // pass c: window c*16 + sub, chunk cc
         const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
         uint32_t hv[4];                     // 8 halves
 #pragma unroll
@@ -541,7 +596,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           const uint32_t e0 = __vcmpeq4(kv[c].x, 0x01010101u * (uint32_t)d), e1 = __vcmpeq4(kv[c].y, 0x01010101u * (uint32_t)d);
           const uint32_t m0 = hv[0] & __byte_perm(e0, 0, 0x1100), m1 = hv[1] & __byte_perm(e0, 0, 0x3322);
           const uint32_t m2 = hv[2] & __byte_perm(e1, 0, 0x1100), m3 = hv[3] & __byte_perm(e1, 0, 0x3322);
-          *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(tb, c)) = make_uint4(m0, m1, m2, m3);
+          *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(c * 16 + sub, cc)) = make_uint4(m0, m1, m2, m3);
         }
       }
       if (p.want_dw) {

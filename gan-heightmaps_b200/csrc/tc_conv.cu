@@ -1051,23 +1051,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 }
 
 // ---- split-K variant for the small layers ------------------------------------------------------------------------
-// (opt-in: HMGAN_TC_SPLITK=1 and a caller workspace, hm_tc_conv_ws; written from the round-1 launch list, where the
-// 4x4..16x16 layers run 4..128 CTAs for 20-90 us each because one CTA walks all K = taps*Cin/64 stages of its tile;
-// NOT yet measured on B200.)
-// Work item = (M tile, N tile, K slice): the slice's partial accumulator is added to an fp32 workspace
-// ws[pixel][GEMM column] with red.global.add.v4.f32; tc_splitk_finish_kernel then applies bias / activation /
-// accumulate / depth-to-space exactly like epilogue_loop and leaves the workspace zeroed for the next launch.
+// (hm_tc_conv_ws with a caller workspace.  Written from the round-1 launch list, where the 4x4..16x16 layers ran
+// 4..128 CTAs for 20-90 us each because one CTA walks all K = taps*Cin/64 stages of its tile.  Measured on B200 in
+// round 2: DCGAN step -0.1 ms, joint step -0.5 ms.)
+// Work item = (M tile, N tile, K slice): the slice's partial accumulator is STORED to its own plane of an fp32
+// workspace ws[slice][pixel][GEMM column]; tc_splitk_finish_kernel sums the planes in slice order -- a fixed order, so
+// the result is deterministic (a first version reduced the slices with fp32 atomics: run-to-run differences of one
+// fp16 ulp in a few activations, which the max-pools downstream amplify to percents of a gradient) -- and applies bias /
+// activation / accumulate / depth-to-space exactly like epilogue_loop.  The workspace needs no initialisation.
 struct TcSplitParams {
   TcParams p;        // S = 1, n_super = n_mtiles
-  float* ws;         // [B*Ho*Wo][ws_cols] fp32, zero on entry
+  float* ws;         // [ksplit][B*Ho*Wo][ws_cols] fp32 scratch
   int ws_cols;       // n_ntiles * ntile
   int ksplit;        // K slices per tile (<= taps * Cin/64)
+  long long plane;   // elements per slice plane = B*Ho*Wo*ws_cols
 };
 
-__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)),
-               "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
-               : "memory");
+__device__ __forceinline__ void st_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(a, b, c, d);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -1184,7 +1185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5): partial sums -> fp32 workspace =====================
+    // ===================== epilogue (warps 2..5): partial sums -> this slice's plane of the workspace =============
     const int qd = warp & 3;                                  // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const int px_per_img = p.bw * p.bh;
@@ -1193,7 +1194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int iy = rem / p.bw, ix = rem - iy * p.bw;
     int it = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, it++) {
-      const int t = w / q.ksplit;
+      const int t = w / q.ksplit, sl = w - t * q.ksplit;
       const int mt = t / p.n_ntiles, nt = t - mt * p.n_ntiles;
       const int acc = it & 1;
       mbar_wait(tfull_bar(acc), (it >> 1) & 1);
@@ -1204,7 +1205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
       const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
       const size_t pix = (size_t)((size_t)n * p.Ho + oy) * p.Wo + ox;
-      float* dst = q.ws + pix * q.ws_cols + nt * p.ntile;
+      float* dst = q.ws + (size_t)sl * q.plane + pix * q.ws_cols + nt * p.ntile;
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * acc_cols;
       for (int c0 = 0; c0 < p.ntile; c0 += 32) {
         uint32_t v[32];
@@ -1215,10 +1216,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (!valid) continue;
         if (full32) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) red_add_v4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) st_v4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) red_add_v4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 16; j += 4) st_v4(dst + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
       tc_fence_before();
@@ -1234,8 +1235,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// ws[pixel][column] -> bias, (+ stored value), activation -> fp16 output (plain / two concat targets / depth-to-space),
-// 8 columns per thread; the workspace is zeroed behind the read.
+// sum over slices of ws[slice][pixel][column] -> bias, (+ stored value), activation -> fp16 output (plain / two concat
+// targets / depth-to-space), 8 columns per thread.
 __global__ void __launch_bounds__(256) tc_splitk_finish_kernel(const TcSplitParams q) {
   const TcParams& p = q.p;
   const int groups = q.ws_cols >> 3;
@@ -1246,11 +1247,13 @@ __global__ void __launch_bounds__(256) tc_splitk_finish_kernel(const TcSplitPara
        i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / groups;
     const int col = (int)(i - pix * groups) * 8;
-    float4* w4 = reinterpret_cast<float4*>(q.ws + pix * q.ws_cols + col);
-    const float4 lo = w4[0], hi = w4[1];
-    w4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    w4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int sl = 0; sl < q.ksplit; sl++) {                  // fixed summation order: deterministic
+      const float4* w4 = reinterpret_cast<const float4*>(q.ws + (size_t)sl * q.plane + pix * q.ws_cols + col);
+      const float4 lo = w4[0], hi = w4[1];
+      v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w;
+      v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+    }
     const int ox = (int)(pix % p.Wo);
     const int oy = (int)((pix / p.Wo) % p.Ho);
     const int n = (int)(pix / ((long long)p.Wo * p.Ho));
@@ -1412,8 +1415,8 @@ extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
 static bool splitk_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("HMGAN_TC_SPLITK");      // opt-in until measured on B200
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("HMGAN_TC_SPLITK");      // on unless HMGAN_TC_SPLITK=0
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
@@ -1428,18 +1431,23 @@ static int splitk_factor(long long tiles, int ksteps) {
   return k < 2 ? 1 : (int)k;
 }
 
-// Bytes of zeroed fp32 workspace hm_tc_conv_ws may use for this problem: 0 when the split-K variant would not be chosen
+// Bytes of fp32 scratch hm_tc_conv_ws may use for this problem: 0 when the split-K variant would not be chosen
 // (switched off, unsupported shape, or enough tiles to fill the machine).  An upper bound that depends on d alone.
 extern "C" long long hm_tc_conv_ws_bytes(const HmConvDesc* d) {
   if (!d || !splitk_enabled() || d->dtype != HM_F16 || !hm_tc_conv_supported(d)) return 0;
-  const bool phase = is_up2conv(d) || is_dgrad_s2(d) || is_deconv_d2s(d);
+  const bool dc2 = is_deconv_d2s(d), dg2 = is_dgrad_s2(d);
+  const bool phase = is_up2conv(d) || dg2 || dc2;
   const long long gh = phase ? d->H : d->Ho, gw = phase ? d->W : d->Wo;        // tile grid
-  if (gw >= TILE_M) return 0;                                                   // row-box kernels take those layers
+  const int kh = dc2 ? 1 : (dg2 ? 2 : (phase ? 3 : d->kh)), kw = kh == d->kh && !phase ? d->kw : kh;
+  if (gw >= TILE_M && kw > 1) return 0;                                         // row-box kernels take those layers
   const long long cols = ((phase ? 4LL * d->Cout : d->Cout) + 15) / 16 * 16;
   const long long npix = (long long)d->B * gh * gw;
-  const long long min_tiles = (npix + TILE_M - 1) / TILE_M * ((cols + 255) / 256);
-  if (min_tiles * 2 > num_sms()) return 0;
-  return npix * cols * 4;
+  const int ntile = pick_ntile((int)(phase ? 4 * d->Cout : d->Cout), phase ? 4 * d->Cout : d->split);
+  if (ntile <= 0) return 0;
+  const long long tiles = (npix + TILE_M - 1) / TILE_M * ((cols + ntile - 1) / ntile);
+  const int ksplit = splitk_factor(tiles, kh * kw * ((d->C1 + d->C2) / KCH));
+  if (ksplit <= 1) return 0;
+  return npix * ((cols + ntile - 1) / ntile * ntile) * 4 * ksplit;
 }
 
 static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
@@ -1451,8 +1459,8 @@ extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, c
   return tc_conv_impl(d, x1, x2, w_tc, bias, y, y2, nullptr, 0, stream);
 }
 
-// The same with a caller-provided workspace of ws_bytes >= hm_tc_conv_ws_bytes(d) ZEROED bytes (left zeroed on return,
-// so one buffer serves every call on a stream): lets small layers split K over otherwise idle SMs.
+// The same with a caller-provided scratch workspace of ws_bytes >= hm_tc_conv_ws_bytes(d) bytes (no initialisation
+// needed; one buffer serves every call on a stream): lets small layers split K over otherwise idle SMs.
 extern "C" int hm_tc_conv_ws(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
                              void* y, void* y2, void* ws, long long ws_bytes, void* stream) {
   HM_CHECK_ARG(!ws || ((((uintptr_t)ws) & 15) == 0 && ws_bytes >= 0), "hm_tc_conv_ws: workspace must be 16-byte aligned");
@@ -1652,7 +1660,8 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   if (ws && splitk_enabled() && !p.bf16) {
     const int ksteps = p.kh * p.kw * (p.Cin / KCH);
     const int ksplit = splitk_factor((long long)p.n_mtiles * p.n_ntiles, ksteps);
-    const size_t need = (size_t)d->B * p.Ho * p.Wo * (size_t)(p.n_ntiles * p.ntile) * 4;
+    const size_t plane = (size_t)d->B * p.Ho * p.Wo * (size_t)(p.n_ntiles * p.ntile);
+    const size_t need = plane * 4 * (size_t)(ksplit > 1 ? ksplit : 1);
     if (ksplit > 1 && ws_bytes >= need) {
       TcSplitParams q;
       q.p = p;
@@ -1665,6 +1674,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
       q.ws = (float*)ws;
       q.ws_cols = p.n_ntiles * p.ntile;
       q.ksplit = ksplit;
+      q.plane = (long long)plane;
       static bool sk_attr = false;
       if (!sk_attr) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

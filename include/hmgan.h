@@ -124,12 +124,12 @@ int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const voi
 int hm_tc_conv_supported(const HmConvDesc* d);
 int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
                void* y, void* y2, void* stream);
-/* hm_tc_conv with a caller-provided workspace: `ws` holds ws_bytes >= hm_tc_conv_ws_bytes(d) bytes that are ZERO on
- * entry and are left zero on return, so one buffer serves every call issued on a stream.  With it, layers whose
- * tiles fill less than half of the SMs split K over the idle ones (partial sums reduced in the fp32 workspace, then
- * one finishing pass applies bias / activation exactly as hm_tc_conv does).  Opt-in: hm_tc_conv_ws_bytes() answers 0
- * -- and hm_tc_conv_ws() behaves as hm_tc_conv() -- unless HMGAN_TC_SPLITK=1 (the variant has not been measured on
- * B200 yet).  ws may be null. */
+/* hm_tc_conv with a caller-provided scratch workspace of ws_bytes >= hm_tc_conv_ws_bytes(d) bytes (no initialisation
+ * needed, contents undefined afterwards; one buffer serves every call issued on a stream).  With it, layers whose
+ * tiles fill less than half of the SMs split K over the idle ones: every K slice stores its partial sums to its own
+ * plane of the workspace and one finishing pass adds the planes in a fixed order (deterministic) and applies bias /
+ * activation exactly as hm_tc_conv does.  hm_tc_conv_ws_bytes() answers 0 -- and hm_tc_conv_ws() behaves as
+ * hm_tc_conv() -- for shapes that do not profit or when HMGAN_TC_SPLITK=0.  ws may be null. */
 long long hm_tc_conv_ws_bytes(const HmConvDesc* d);
 int hm_tc_conv_ws(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
                   void* y, void* y2, void* ws, long long ws_bytes, void* stream);

@@ -283,3 +283,105 @@ def test_single_pass_discriminator_backward_equals_two_passes_at_full_width(monk
                 continue                 # biases in front of a BatchNorm: the true gradient is zero, both are noise
             rel = float(np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30))
             assert rel <= 5e-2, (k, i, a.shape, rel)
+
+
+def _sync_state(src, dst):
+    """dst <- src: master parameters, BatchNorm running statistics and optimiser state of every network."""
+    for a, b in zip(src._nets(), dst._nets()):
+        b.pflat.copy_(a.pflat)
+        b.sflat.copy_(a.sflat)
+        for k, v in a.opt_state.items():
+            if k not in b.opt_state:
+                b.opt_state[k] = v.clone()
+            else:
+                b.opt_state[k].copy_(v)
+        b._packed = False
+
+
+@pytest.mark.parametrize("case", ["gate64_fast", "gate64_parity", "tiny512_both_fast", "wide64_fast"])
+def test_multi_stream_schedule_changes_nothing(case, monkeypatch):
+    """The default schedule -- weight gradients on a side stream (engine.Runtime.wgrad_stream), D(x) beside G's forward
+    pass (Runtime.fork), D's weight gradients under G's backward pass -- against the single-stream schedule
+    (HMGAN_WGRAD_STREAM=0 HMGAN_FORK=0): same kernels, same inputs, only issued on several streams.
+    Two models run side by side over five steps (eager, eager, captured, replayed, replayed); BEFORE every step the
+    side-stream model receives the other one's complete state, so that every step starts from identical parameters and
+    what is compared is one step's losses and gradient vectors -- a GAN step with RMSprop amplifies the run-to-run
+    noise of atomically reduced gradients within a few steps.  A missing cross-stream dependency would show up as
+    an O(1) relative error of some gradient array; the bound is the atomics' rounding noise: 1e-5 of the array norm
+    in float32, 2e-3 in fp16 fast mode."""
+    import torch
+    wide = dict(in_shp=64, latent_dim=32, G=dict(nch=256, num_repeats=0, div=[2, 2, 4, 4]),
+                D=dict(nch=64, num_repeats=0, bn=False, nonlinearity='linear', div=[1, 1, 1, 1]))
+    cfg, mode, p2p, B, px, prec = {
+        "gate64_fast": (S.experiment_kwargs('gate64'), 'dcgan', False, 4, 64, "fast"),
+        "gate64_parity": (S.experiment_kwargs('gate64'), 'dcgan', False, 4, 64, "parity"),
+        "tiny512_both_fast": (S.experiment_kwargs('tiny512'), 'both', True, 2, 512, "fast"),
+        "wide64_fast": (wide, 'dcgan', False, 4, 64, "fast"),
+    }[case]
+    monkeypatch.setenv("HMGAN_WGRAD_STREAM", "0")
+    monkeypatch.setenv("HMGAN_FORK", "0")
+    _, m0 = build_pair(cfg, mode, with_p2p=p2p, device="cuda", precision=prec)
+    monkeypatch.setenv("HMGAN_WGRAD_STREAM", "1")
+    monkeypatch.setenv("HMGAN_FORK", "1")
+    _, m1 = build_pair(cfg, mode, with_p2p=p2p, device="cuda", precision=prec)
+    assert m1.rt.wgrad_stream() is not None and m0.rt.wgrad_stream() is None
+    tol = 1e-5 if prec == "parity" else 2e-3
+    for it in range(5):
+        _sync_state(m0, m1)
+        Z, X, Y = S.synthetic_batch(B, cfg['latent_dim'], px, seed=20 + it)
+        l0, l1 = m0.train_fn(Z, X, Y), m1.train_fn(Z, X, Y)
+        np.testing.assert_allclose(l1, l0, rtol=1e-5 if prec == "parity" else 1e-3, atol=1e-6)
+        for n0, n1 in zip(m0._nets(), m1._nets()):
+            for i, (a, b) in enumerate(zip(n0.get_grads(), n1.get_grads())):
+                na = float(np.linalg.norm(a.ravel()))
+                err = float(np.linalg.norm((a - b).ravel()))
+                gmax = max(float(np.linalg.norm(g.ravel())) for g in n0.get_grads())
+                assert err <= tol * na + 1e-6 * gmax, (case, it, n0.name, i, a.shape, err / (na + 1e-30))
+    torch.cuda.synchronize()
+
+
+def test_default_objective_adam_cross_entropy_l2():
+    """The constructor's default objective (reference pix2pix.py:58-59: Adam, binary cross-entropy) with the L2
+    reconstruction, on the joint topology at toy widths: two steps against the oracle at 1e-3.  Adam's step count lives
+    in device memory (hm_adam_dev), so the step is captured in a CUDA graph like the RMSprop one: steps 3-5 replay it."""
+    cfg = dict(TINY)
+    cfg['D'] = dict(TINY['D'], nonlinearity='sigmoid')
+    cfg['Dp'] = dict(TINY['Dp'], act='sigmoid')
+    om, m = build_pair(cfg, 'both', opt="adam", lr=2e-4, lsgan=False, reconstruction='l2', device="cuda")
+    assert m._graphs_ok
+    for it in range(5):
+        Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 512, seed=30 + it)
+        np.testing.assert_allclose(m.train_fn(Z, X, Y), om.train_fn(Z, X, Y), rtol=1e-3 if it < 2 else 5e-3, atol=1e-6)
+    assert any(st.get("gA") is not None or st.get("graph") is not None for st in m._graphs.values())
+    assert int(m.G.opt_state["t"].item()) == 5
+
+
+def test_replayed_graphs_see_updated_weights_and_survive_reallocation(monkeypatch):
+    """Captured CUDA graphs against the eager schedule (HMGAN_CUDA_GRAPHS=0) over the call sequence of Pix2Pix.train():
+    three train_fn calls (the third is captured), three loss_fn calls (captured too), a train_fn replay, then a loss_fn
+    replay -- which must see the weights of the LAST update (the packed compute-dtype copies are refreshed inside the
+    step, not by a host flag) -- then a z_fn call with a larger batch that reallocates G's buffers, after which the
+    train_fn graph must be re-captured instead of replaying into freed memory."""
+    cfg = S.experiment_kwargs('gate64')
+    res = {}
+    for graphs in ("1", "0"):
+        monkeypatch.setenv("HMGAN_CUDA_GRAPHS", graphs)
+        _, m = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast")
+        out = []
+        batches = [S.synthetic_batch(4, cfg['latent_dim'], 64, seed=40 + i) for i in range(10)]
+        for i in range(3):
+            out.append(m.train_fn(*batches[i]))
+        for i in range(3, 6):
+            out.append(m.loss_fn(*batches[i]))
+        out.append(m.train_fn(*batches[6]))
+        out.append(m.loss_fn(*batches[7]))
+        Zbig = np.random.RandomState(1).rand(16, cfg['latent_dim']).astype(np.float32)
+        gz = m.z_fn_det(Zbig)
+        out.append(m.train_fn(*batches[8]))
+        out.append(m.loss_fn(*batches[9]))
+        res[graphs] = (np.array(out)[:, :2], gz)
+        del m
+        torch.cuda.empty_cache()
+    # fp16 fast mode, atomically reduced weight gradients: the two schedules agree to run-to-run noise
+    np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(res["1"][1], res["0"][1], atol=5e-3)

@@ -18,6 +18,7 @@ from util import synthetic_batch   # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 wl = sys.argv[2] if len(sys.argv) > 2 else "dcgan"
 m = bench.build_model(wl, "cuda:0", "fast")
+bench.liven_head(m, 0.6)
 Z, X, Y = synthetic_batch(B, 1000, 512, seed=100)
 Zd, Xd, Yd = (torch.from_numpy(t).cuda() for t in (Z, X, Y))
 for _ in range(2):
