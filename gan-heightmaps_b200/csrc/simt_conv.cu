@@ -332,6 +332,25 @@ __device__ __forceinline__ void pack_elem(const float* __restrict__ w, T* __rest
         }
       }
     }
+  } else if (mode == 20) {
+    // input gradient of (nearest-2x -> 5x5 'same' conv) as ONE 6x6 stride-2 pad-2 convolution of dy on the low-res grid:
+    //   dx[q][ci] = sum_{u,v<6} sum_co dy[2q-2+(u,v)][co] * Wt[(u*6+v)][ci][co]
+    // with  Wt[(u*6+v)][ci][co] = sum_{r in R(u&1, 2-(u>>1)), s in R(v&1, 2-(v>>1))} W[co][ci][4-r][4-s]   (R as in mode 8:
+    // the adjoint of the four 3x3 phase filters; mode 14 is its Cout == 1 case).   (K-major tcgen05 pack, K = co)
+    int co = (int)(i % cout);
+    long long k = i / cout;
+    int ci = (int)(k % cin);
+    int tap = (int)(k / cin);
+    int uu = tap / 6, vv = tap % 6;
+    int py = uu & 1, px = vv & 1, dy_ = 2 - (uu >> 1), dx_ = 2 - (vv >> 1);
+    val = 0.f;
+    for (int r = 0; r < 5; r++) {
+      if (((py + r - 2 + 4) >> 1) - 2 + 1 != dy_) continue;
+      for (int q = 0; q < 5; q++) {
+        if (((px + q - 2 + 4) >> 1) - 2 + 1 != dx_) continue;
+        val += w[(((size_t)co * cin + ci) * 5 + (4 - r)) * 5 + (4 - q)];
+      }
+    }
   } else if (mode == 15) {
     // hm_c1s2_conv, pooled form: conv5x5 'same' (Cin == 1) evaluated at the four positions d = (dy,dx) of every 2x2
     // pooling window from the window's 6x6 patch:  Wk[d*cout+co][u*6+v] = W[co][0][4-(u-dy)][4-(v-dx)] where the
@@ -549,6 +568,7 @@ static long long pack_count(int mode, int cout, int cin, int kh, int kw) {
   if (mode == 17) n = 4LL * cout * cin;
   if (mode == 18) n = 64LL * cin;
   if (mode == 19) n = 64LL * cout;
+  if (mode == 20) n = 36LL * cout * cin;
   return n;
 }
 
@@ -575,7 +595,7 @@ extern "C" int hm_pack_conv_weight_multi(const HmPackJob* jobs_dev, int n_jobs, 
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 19),
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 20),
                "hm_pack_conv_weight: bad mode %d", mode);
   HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
   HM_CHECK_ARG((mode != 15 && mode != 16) || (cin == 1 && kh == 5 && kw == 5),
@@ -586,7 +606,7 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   HM_CHECK_ARG(mode != 19 || kh * kw * cin <= 64, "hm_pack_conv_weight: mode 19 needs kh*kw*Cin <= 64");
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
   HM_CHECK_ARG(mode != 11 || (cin == 1 && kh * kw <= 64), "hm_pack_conv_weight: mode 11 needs Cin == 1 and <= 64 taps");
-  HM_CHECK_ARG(mode != 8 || (kh == 5 && kw == 5), "hm_pack_conv_weight: mode 8 is defined for 5x5 filters");
+  HM_CHECK_ARG((mode != 8 && mode != 20) || (kh == 5 && kw == 5), "hm_pack_conv_weight: modes 8 and 20 are defined for 5x5 filters");
   const long long n = pack_count(mode, cout, cin, kh, kw);
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;

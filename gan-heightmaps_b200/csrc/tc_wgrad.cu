@@ -38,6 +38,8 @@ struct WgParams {
   float* dw;            // [units*64][pitch] fp32; this launch fills columns [n_off, n_off + Cout)
   int n_off, pitch;     // N tiling when the layer has more than 256 output channels
   int bf16;             // operands are bfloat16 (HM_BF16X3: batch-stacked hi/lo splits of fp32 tensors) instead of fp16
+  int cpb;              // > 0: phase form of (nearest-2x -> 5x5): the N columns are (phase, co) with cpb = Cout_real/64
+                        //      channel blocks per phase; dy is the HIGH-res gradient, read with TMA element strides of 2
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -191,8 +193,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = tn * p.bn;
         wg_wait(bempty(bs), bph ^ 1);
         wg_expect_tx(bfull(bs), b_bytes);
-        for (uint32_t j = 0; j < nblk; j++)
-          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), p.n_off + j * 64, ox0, oy0, n0);
+        for (uint32_t j = 0; j < nblk; j++) {
+          const int jb = p.n_off / 64 + (int)j;                // 64-column block of the GEMM's N axis
+          if (p.cpb > 0) {                                     // (phase, co): phase (py,px) = pixels (2y+py, 2x+px) of dy
+            const int ph = jb / p.cpb, cb = jb - ph * p.cpb;
+            wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), cb * 64, 2 * ox0 + (ph & 1), 2 * oy0 + (ph >> 1), n0);
+          } else {
+            wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), jb * 64, ox0, oy0, n0);
+          }
+        }
         if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         for (int mt = mt0; mt < mt1; mt++) {
           wg_wait(aempty(as), aph ^ 1);
@@ -374,8 +383,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const int n0 = pt / (p.tiles_x * p.tiles_y);
         wg_wait(bempty(bs), bph ^ 1);
         wg_expect_tx(bfull(bs), b_bytes);
-        for (uint32_t j = 0; j < nblk; j++)
-          wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), p.n_off + j * 64, ox0, oy0, n0);
+        for (uint32_t j = 0; j < nblk; j++) {
+          const int jb = p.n_off / 64 + (int)j;                // 64-column block of the GEMM's N axis
+          if (p.cpb > 0) {                                     // (phase, co): phase (py,px) = pixels (2y+py, 2x+px) of dy
+            const int ph = jb / p.cpb, cb = jb - ph * p.cpb;
+            wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), cb * 64, 2 * ox0 + (ph & 1), 2 * oy0 + (ph >> 1), n0);
+          } else {
+            wg_tma_4d(&tmDY, base + bs * b_bytes + j * BLK_BYTES, bfull(bs), jb * 64, ox0, oy0, n0);
+          }
+        }
         if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
         wg_wait(aempty(as), aph ^ 1);
         wg_expect_tx(afull(as), n_boxes * box_bytes);
@@ -511,8 +527,19 @@ static inline int wg_pow2_floor(int v) {
 
 using namespace hm;
 
+// weight gradient of (nearest-2x upsampling -> 5x5 'same' stride-1 convolution) in phase form: `d` is the layer's FORWARD
+// descriptor (up = HM_UP_NEAREST2, H x W the low-res source grid, Ho x Wo = 2H x 2W); the result is the gradient of
+// the four 3x3 phase filters, dw[(tap3, ci)][(phase, co)] (9*Cin rows, 4*Cout columns; hm_unpack_conv_wgrad mode 8
+// folds it onto the 5x5 filter): 36 taps on H x W pixels instead of 25 taps on the materialised 2H x 2W tensor
+static bool is_up2_wgrad(const HmConvDesc* d) {
+  return d->up == HM_UP_NEAREST2 && d->kh == 5 && d->kw == 5 && d->pad == 2 && d->stride == 1 && !d->transposed &&
+         d->C2 == 0 && d->Ho == 2 * d->H && d->Wo == 2 * d->W && d->oH == d->Ho && d->oW == d->Wo && d->os == 1 &&
+         !d->ou && !d->ov && d->C1 > 0 && d->C1 % 64 == 0 && d->Cout > 0 && d->Cout % 64 == 0;
+}
+
 extern "C" int hm_tc_wgrad_supported(const HmConvDesc* d) {
   if (!d) return 0;
+  if ((d->dtype == HM_F16 || d->dtype == HM_BF16X3) && is_up2_wgrad(d)) return 1;
   if ((d->dtype != HM_F16 && d->dtype != HM_BF16X3) || d->transposed || d->up || (d->stride != 1 && d->stride != 2)) return 0;
   if (d->os != 1 || d->ou || d->ov) return 0;
   if (d->C1 % 64 || d->C2 % 64 || d->C1 <= 0) return 0;
@@ -529,14 +556,15 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
 extern "C" int hm_tc_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw,
                            void* stream) {
   HM_CHECK_ARG(d && x1 && dy && dw, "hm_tc_wgrad: null argument");
-  if (hm_tc_wgrad_supported(d) && d->Cout > 256) {
-    for (int n_off = 0; n_off < d->Cout; n_off += 256) {
+  const int ncols = hm_tc_wgrad_supported(d) && is_up2_wgrad(d) ? 4 * d->Cout : d->Cout;       // GEMM N
+  if (hm_tc_wgrad_supported(d) && ncols > 256) {
+    for (int n_off = 0; n_off < ncols; n_off += 256) {
       int rc = tc_wgrad_tile(d, x1, x2, dy, dw, stream, n_off, 256);
       if (rc) return rc;
     }
     return HM_OK;
   }
-  return tc_wgrad_tile(d, x1, x2, dy, dw, stream, 0, d ? d->Cout : 0);
+  return tc_wgrad_tile(d, x1, x2, dy, dw, stream, 0, ncols);
 }
 
 static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, const void* dy, float* dw, void* stream,
@@ -555,20 +583,24 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
     set_error("hm_tc_wgrad: pointers must be 16-byte aligned");
     return HM_ERR_ALIGN;
   }
+  const bool up2 = is_up2_wgrad(d);
+  const int gH = up2 ? d->H : d->Ho, gW = up2 ? d->W : d->Wo;       // pixel grid of the reduction (low-res in phase form)
+  const int kh = up2 ? 3 : d->kh, kw = up2 ? 3 : d->kw, pad = up2 ? 1 : d->pad;
   WgParams p;
-  p.B = d->B; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.B = d->B; p.Ho = gH; p.Wo = gW;
   p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = ntile;
-  p.n_off = n_off; p.pitch = d->Cout;
+  p.n_off = n_off; p.pitch = up2 ? 4 * d->Cout : d->Cout;
   p.bf16 = d->dtype == HM_BF16X3 ? 1 : 0;
-  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.stride = d->stride;
-  p.bw = wg_pow2_floor(d->Wo < 128 ? d->Wo : 128);
-  p.bh = wg_pow2_floor(d->Ho < 128 / p.bw ? d->Ho : 128 / p.bw);
+  p.cpb = up2 ? d->Cout / 64 : 0;
+  p.kh = kh; p.kw = kw; p.pad = pad; p.stride = d->stride;
+  p.bw = wg_pow2_floor(gW < 128 ? gW : 128);
+  p.bh = wg_pow2_floor(gH < 128 / p.bw ? gH : 128 / p.bw);
   p.bn = 128 / (p.bw * p.bh);
-  p.tiles_x = (d->Wo + p.bw - 1) / p.bw;
-  p.tiles_y = (d->Ho + p.bh - 1) / p.bh;
+  p.tiles_x = (gW + p.bw - 1) / p.bw;
+  p.tiles_y = (gH + p.bh - 1) / p.bh;
   p.tiles_n = (d->B + p.bn - 1) / p.bn;
   p.n_ptiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.units = d->kh * d->kw * (p.Cin / 64);
+  p.units = kh * kw * (p.Cin / 64);
   p.n_mtiles = (p.units + 1) / 2;
   p.acc = 512 / p.Cout;
   p.n_mgroups = (p.n_mtiles + p.acc - 1) / p.acc;
@@ -595,7 +627,7 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
   int rc = wg_encode_act(&tmX, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn, p.stride);
   if (!rc && d->C2) rc = wg_encode_act(&tmX2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn, p.stride);
   if (!d->C2) tmX2 = tmX;
-  if (!rc) rc = wg_encode_act(&tmDY, dy, d->B, d->Ho, d->Wo, d->Cout, p.bw, p.bh, p.bn);
+  if (!rc) rc = wg_encode_act(&tmDY, dy, d->B, d->Ho, d->Wo, d->Cout, p.bw, p.bh, p.bn, up2 ? 2 : 1);
   if (rc) {
     set_error("hm_tc_wgrad: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
     return HM_ERR_CUDA;
@@ -606,10 +638,10 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
     const char* e = getenv("HMGAN_TC_ROWBOX");
     rb_enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (rb_enabled && d->stride == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 && d->kw > 1 && d->kw <= 9) {
+  if (rb_enabled && d->stride == 1 && p.bw == 128 && p.bh == 1 && p.bn == 1 && kw > 1 && kw <= 9) {
     WgRbParams q;
     q.w = p;
-    q.rb_bytes = (((128 + d->kw - 1) * 128) + 1023) / 1024 * 1024;
+    q.rb_bytes = (((128 + kw - 1) * 128) + 1023) / 1024 * 1024;
     const int cblocks = p.Cin / 64;
     // worst case over m-groups of (filter rows spanned) * cblocks
     int max_boxes = 0;
@@ -618,7 +650,7 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
       const int mt1 = (int)(((long long)(mg + 1) * p.n_mtiles) / p.n_mgroups);
       const int u_lo = 2 * mt0, u_hi = (2 * mt1 < p.units ? 2 * mt1 : p.units);
       if (u_hi <= u_lo) continue;
-      const int r0 = (u_lo / cblocks) / d->kw, r1 = ((u_hi - 1) / cblocks) / d->kw;
+      const int r0 = (u_lo / cblocks) / kw, r1 = ((u_hi - 1) / cblocks) / kw;
       const int nb = (r1 - r0 + 1) * cblocks;
       if (nb > max_boxes) max_boxes = nb;
     }
@@ -639,8 +671,8 @@ static int tc_wgrad_tile(const HmConvDesc* d, const void* x1, const void* x2, co
     if (a_sl >= 2) {
       q.w.a_slots = a_sl;
       CUtensorMap rX, rX2;
-      rc = wg_encode_act(&rX, x1, d->B, d->H, d->W, d->C1, 128 + d->kw - 1, 1, 1);
-      if (!rc && d->C2) rc = wg_encode_act(&rX2, x2, d->B, d->H, d->W, d->C2, 128 + d->kw - 1, 1, 1);
+      rc = wg_encode_act(&rX, x1, d->B, d->H, d->W, d->C1, 128 + kw - 1, 1, 1);
+      if (!rc && d->C2) rc = wg_encode_act(&rX2, x2, d->B, d->H, d->W, d->C2, 128 + kw - 1, 1, 1);
       if (!d->C2) rX2 = rX;
       if (rc) {
         set_error("hm_tc_wgrad: cuTensorMapEncodeTiled failed for the row box (CUresult %d)", rc);

@@ -344,12 +344,23 @@ class ConvOp(object):
         self.dg2_cat = False
         self.gcat = None
         self.dg2 = False      # input gradient of a 3x3 stride-2 conv as a 2x2-tap phase convolution of dy (pack mode 12)
+        self.dg6 = False      # input gradient of nearest-2x + 5x5 as a 6x6 stride-2 convolution of dy (pack mode 20)
+        self.wg8 = False      # weight gradient of nearest-2x + 5x5 as the gradient of its four 3x3 phase filters
         if rt.tc and kind == "conv" and self.stride in (1, 2):
             if self.up == _lib.UP_NEAREST2 and self.x2 is None and self.stride == 1:
                 # (thin outputs take the fp16-only hm_s2d_pad64 route for their weight gradient: fast mode only)
                 self.up2 = (not rt.split or self.Cout > 4) and rt.tc_supported(self._fwd_desc(rt, 1))
+            # ... and its input gradient as ONE 6x6 stride-2 convolution of dy that lands on the low-res source grid
+            # (pack mode 20): 36 taps on H x W pixels instead of 25 taps on 2H x 2W plus the adjoint of the upsampling
+            self.dg6 = (self.up2 and self.kh == 5 and os.environ.get("HMGAN_DG6", "1") != "0"
+                        and rt.tc_supported(self._dg6_desc(rt, 1, 0)))
             self.tc_fwd = self.up2 or rt.tc_supported(self._tc_fwd_desc(rt, 1))
             self.tc_wg = rt.tc_supported(self._tc_fwd_desc(rt, 1), wgrad=True)
+            # ... and its weight gradient in phase form: gradient of the four 3x3 phase filters on the low-res source
+            # against the strided phases of dy (hm_tc_wgrad with the forward descriptor, unpack mode 8): no
+            # materialised 2x copy of the source, 36 instead of 100 low-res taps
+            self.wg8 = (self.up2 and self.Cout % 64 == 0 and os.environ.get("HMGAN_WG8", "1") != "0"
+                        and rt.tc_supported(self._fwd_desc(rt, 1), wgrad=True))
             if self.stride == 1:
                 self.tc_dg = rt.tc_supported(self._tc_dgrad_desc(rt, 1, 0))
             elif not self.up:
@@ -401,7 +412,7 @@ class ConvOp(object):
             self.wp_f = rt.empty((n,))
             self.wp_d = rt.empty((n,)) if self.kind != "dense" else None
             self.dwp = rt.empty((n,), torch.float32)
-        if self.up and self.src.srcs[0].kind != "input" and not self.c1dg:
+        if self.up and self.src.srcs[0].kind != "input" and not self.c1dg and not self.dg6:
             self.gup = rt.empty((B, self.Hv, self.Wv, self.Cin))
         if self.dc2:
             self.dy64 = rt.empty((B, self.x1.shape[0], self.x1.shape[1], 64))
@@ -431,7 +442,9 @@ class ConvOp(object):
             self.gcat = rt.empty((B, self.Hv, self.Wv, self.Cin))
             if self.wt_d is None:
                 self.wt_d = rt.empty((tcm * 16 * self.Cin * self.Cout,), rt.tc_dtype)
-        if self.tc_dg and self.wt_d is None:
+        if self.dg6 and self.wt_d is None:
+            self.wt_d = rt.empty((tcm * 36 * self.Cin * self.Cout,), rt.tc_dtype)
+        elif self.tc_dg and self.wt_d is None:
             self.wt_d = rt.empty((tcm * (16 * self.Cin * self.Cout if self.dg2 else n),), rt.tc_dtype)
         self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient of the thin phase-decomposed layer
         if self.thin_up2_wg:
@@ -439,7 +452,9 @@ class ConvOp(object):
             self.dy64 = rt.empty((B, self.x1.shape[0], self.x1.shape[1], 64))
             if self.dwp is None or self.dwp.numel() < 9 * self.Cin * 64:
                 self.dwp = rt.empty((9 * self.Cin * 64,), torch.float32)
-        if self.up and ((self.tc_fwd and not self.up2) or (self.tc_wg and not self.thin_up2_wg)):
+        if self.wg8 and (self.dwp is None or self.dwp.numel() < 36 * self.Cin * self.Cout):
+            self.dwp = rt.empty((36 * self.Cin * self.Cout,), torch.float32)
+        if self.up and ((self.tc_fwd and not self.up2) or (self.tc_wg and not self.thin_up2_wg and not self.wg8)):
             # the tensor-core kernels read dense NHWC tiles through TMA: materialise the 2x resampling once
             self.x1u = rt.empty((B, self.Hv, self.Wv, self.C1))
             self.x2u = rt.empty((B, self.Hv, self.Wv, self.C2)) if self.x2 is not None else None
@@ -467,7 +482,9 @@ class ConvOp(object):
                            self.Cin, self.C1)
             if self.c1dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wk), 14, 1, self.Cin, 5, 5, 0, 0, rt.cd)
-            if self.dg2_cat:
+            if self.dg6:
+                rt.tc_pack(_ptr(w), _ptr(self.wt_d), 20, self.Cout, self.Cin, 5, 5, self.Cout)
+            elif self.dg2_cat:
                 rt.tc_pack(_ptr(w), _ptr(self.wt_d), 12, self.Cout, self.Cin, self.kh, self.kw, self.Cout)
             elif not self.tc_dg:
                 rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_d), 7 if self.fw_dg else 1, self.Cout, self.Cin,
@@ -566,6 +583,22 @@ class ConvOp(object):
         d.Ho, d.Wo, d.Cout = self.Hv, self.Wv, self.Cin
         d.oH, d.oW, d.os, d.ou, d.ov = self.Hv, self.Wv, 1, 0, 0
         d.split = self.C1
+        d.act, d.slope = 0, 0.0
+        d.accumulate = acc
+        return d
+
+    def _dg6_desc(self, rt, n, acc):
+        """Input gradient of (nearest-2x -> 5x5 'same' conv) as a forward 6x6 stride-2 pad-2 convolution of dy
+        [n, 2H, 2W, Cout] onto the low-res source grid [n, H, W, Cin] (weights: pack mode 20)."""
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W = n, self.out.shape[0], self.out.shape[1]
+        d.C1, d.C2, d.up = self.Cout, 0, 0
+        d.kh, d.kw, d.stride, d.pad = 6, 6, 2, 2
+        d.transposed = 0
+        d.Ho, d.Wo, d.Cout = self.x1.shape[0], self.x1.shape[1], self.Cin
+        d.oH, d.oW, d.os, d.ou, d.ov = d.Ho, d.Wo, 1, 0, 0
+        d.split = self.Cin
         d.act, d.slope = 0, 0.0
         d.accumulate = acc
         return d
@@ -728,6 +761,9 @@ class ConvOp(object):
             d.Ho, d.Wo, d.oH, d.oW, d.Cout, d.split = h, w, h, w, 64, 64
             rt.call("hm_tc_wgrad", C.byref(d), x1, None, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
             mode = 10
+        elif self.wg8:
+            rt.tc_wgrad(self._fwd_desc(rt, n), x1, None, _ptr(g), _ptr(self.dwp))
+            mode = 8
         elif self.tc_wg and (not self.up or self.x1u is not None):
             if self.up and not getattr(self, "_xu_valid", False):   # forward did not materialise the 2x copy
                 for (x, xu, c) in ((self.x1, self.x1u, self.C1), (self.x2, self.x2u, self.C2)):
@@ -779,6 +815,9 @@ class ConvOp(object):
             self.x1.gw = True
             rt.call("hm_c1s2_conv", _ptr(g), _ptr(self.wk), None, _ptr(self.x1.g(lo, hi)), None, n, self.Hv, self.Wv,
                     64, 0, 0.0)
+        elif self.dg6 and t1:
+            d = self._dg6_desc(rt, n, self.x1.take_acc())
+            rt.tc_conv(d, _ptr(g), None, _ptr(self.wt_d), None, _ptr(self.x1.g(lo, hi)), None)
         elif self.up:
             # gradient on the virtual (2x) grid, then the adjoint of the resampling
             if self.gup is None:

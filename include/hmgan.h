@@ -210,6 +210,10 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  *           pack and pad' = k-1-pad)
  *  mode 8: nearest-2x + 5x5 as four 3x3 phase filters, mode 11: one-channel input over the im2col tensor, modes 14/15/16: hm_c1s2_* operands, mode 19: thin-source convolution over hm_im2col_thin's tensor, modes 17/18: Deconv2DLayer 2x2 stride 2 on the tensor cores (all phases; its input gradient over hm_s2d_pad64), mode 12: input
  *          gradient of a 3x3 stride-2 convolution as a 2x2-tap phase convolution of dy (see csrc/simt_conv.cu)
+ *  mode 20: input gradient of (Upscale2DLayer(2) -> 5x5 'same' conv, dcgan.py:31-32 / :21-22) as ONE 6x6 stride-2 pad-2
+ *          convolution of dy landing directly on the low-res source grid -> Wt[(u*6+v)][ci][co] (K-major, K = co): the
+ *          adjoint of the four 3x3 phase filters of mode 8; 36 taps on H x W pixels instead of 25 taps on 2H x 2W
+ *          followed by hm_upsample2_bwd (mode 14 is its Cout == 1 case for hm_c1s2_conv)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)
  * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the

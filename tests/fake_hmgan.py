@@ -188,6 +188,16 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     for s_ in range(5):
                         if (py + r - 2) // 2 + 1 == dy_ and (px + s_ - 2) // 2 + 1 == dx_:
                             out[:, uu * 6 + vv] += Wc[:, r, s_]
+    elif mode == 20:
+        Wc = W.reshape(cout, cin, 5, 5)[:, :, ::-1, ::-1]                        # correlation taps Wc[co][ci][r][s]
+        out = np.zeros((36, cin, cout), np.float32)
+        for uu in range(6):
+            for vv in range(6):
+                py, px, dy_, dx_ = uu & 1, vv & 1, 2 - (uu >> 1), 2 - (vv >> 1)
+                for r in range(5):
+                    for s_ in range(5):
+                        if (py + r - 2) // 2 + 1 == dy_ and (px + s_ - 2) // 2 + 1 == dx_:
+                            out[uu * 6 + vv] += Wc[:, :, r, s_].T
     elif mode == 15:
         Wc = W.reshape(cout, 5, 5)[:, ::-1, ::-1]                                # Cin == 1: correlation taps Wc[co][r][s]
         out = np.zeros((4, cout, 64), np.float32)
@@ -640,6 +650,8 @@ def _tc_ok(d, wgrad):
     if d.dtype == BF16X3:            # bf16 hi/lo splits of fp32 tensors: same shape rules as fp16
         d = type(d).from_buffer_copy(d)
         d.dtype = F16
+    if wgrad and d.dtype == F16 and _is_up2_wgrad(d):
+        return True
     if not wgrad and d.dtype == F16 and _is_deconv_d2s(d):
         return d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0 and (d.Cout % 32 == 0 or d.Cout <= 4)
     if not wgrad and d.dtype == F16 and _is_dgrad_s2(d):
@@ -727,9 +739,26 @@ def hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream=None):
     return hm_conv_gather(dp, x1, x2, wk.ctypes.data, bias, y, y2)
 
 
+def _is_up2_wgrad(d):
+    return (d.up == 1 and d.kh == 5 and d.kw == 5 and d.pad == 2 and d.stride == 1 and not d.transposed and d.C2 == 0
+            and d.Ho == 2 * d.H and d.Wo == 2 * d.W and d.oH == d.Ho and d.oW == d.Wo and d.os == 1 and not d.ou
+            and not d.ov and d.C1 > 0 and d.C1 % 64 == 0 and d.Cout > 0 and d.Cout % 64 == 0)
+
+
 def hm_tc_wgrad(dp, x1, x2, dy, dw, stream=None):
     d = dp._obj if hasattr(dp, "_obj") else dp
     assert _tc_ok(d, True)
+    if _is_up2_wgrad(d):
+        # phase form: dw[(tap3, ci)][(phase, co)] += gradient of the four 3x3 phase filters (unpack mode 8)
+        if d.dtype == BF16X3:
+            d, _keep, (x1, _x2, dy) = _bf16x3_as_f32(d, ((x1, d.B * d.H * d.W * d.C1), (None, 0),
+                                                          (dy, d.B * d.Ho * d.Wo * d.Cout)))
+        Ci, Co = d.C1, d.Cout
+        tmp = np.zeros(36 * Ci * Co, np.float32)
+        hm_up2conv_wgrad_phases(d, x1, dy, tmp.ctypes.data)                     # [phase][(tap3, ci)][co]
+        out = _a(dw, 36 * Ci * Co, np.float32).reshape(9 * Ci, 4, Co)
+        out += tmp.reshape(4, 9 * Ci, Co).transpose(1, 0, 2)
+        return 0
     if d.dtype == BF16X3:
         nsrc = d.B * d.H * d.W
         dp, _keep, (x1, x2, dy) = _bf16x3_as_f32(d, ((x1, nsrc * d.C1), (x2, nsrc * d.C2),

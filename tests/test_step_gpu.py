@@ -307,8 +307,12 @@ def test_multi_stream_schedule_changes_nothing(case, monkeypatch):
     side-stream model receives the other one's complete state, so that every step starts from identical parameters and
     what is compared is one step's losses and gradient vectors -- a GAN step with RMSprop amplifies the run-to-run
     noise of atomically reduced gradients within a few steps.  A missing cross-stream dependency would show up as
-    an O(1) relative error of some gradient array; the bound is the atomics' rounding noise: 1e-5 of the array norm
-    in float32, 2e-3 in fp16 fast mode."""
+    an O(1) relative error of some gradient array.  Bounds: float32 'parity' mode (side stream only) 1e-5 of the array
+    norm, the atomics' rounding noise -- measured 0 to 1.4e-7, i.e. the two schedules are bit-identical up to the order
+    of atomic adds.  fp16 'fast' mode 5e-2: with the fork D runs as two half-batch launches, whose small layers pick a
+    different split-K factor than the full batch, i.e. another (deterministic) summation order; the few activations that
+    round to the neighbouring fp16 value re-route max-pool ties downstream (measured 1.4e-2 on the generator's arrays,
+    the same sensitivity tests/test_step_gpu.py documents for fp16 against float32)."""
     import torch
     wide = dict(in_shp=64, latent_dim=32, G=dict(nch=256, num_repeats=0, div=[2, 2, 4, 4]),
                 D=dict(nch=64, num_repeats=0, bn=False, nonlinearity='linear', div=[1, 1, 1, 1]))
@@ -325,12 +329,12 @@ def test_multi_stream_schedule_changes_nothing(case, monkeypatch):
     monkeypatch.setenv("HMGAN_FORK", "1")
     _, m1 = build_pair(cfg, mode, with_p2p=p2p, device="cuda", precision=prec)
     assert m1.rt.wgrad_stream() is not None and m0.rt.wgrad_stream() is None
-    tol = 1e-5 if prec == "parity" else 2e-3
+    tol = 1e-5 if prec == "parity" else 5e-2
     for it in range(5):
         _sync_state(m0, m1)
         Z, X, Y = S.synthetic_batch(B, cfg['latent_dim'], px, seed=20 + it)
         l0, l1 = m0.train_fn(Z, X, Y), m1.train_fn(Z, X, Y)
-        np.testing.assert_allclose(l1, l0, rtol=1e-5 if prec == "parity" else 1e-3, atol=1e-6)
+        np.testing.assert_allclose(l1, l0, rtol=1e-5 if prec == "parity" else 2e-3, atol=1e-6)
         for n0, n1 in zip(m0._nets(), m1._nets()):
             for i, (a, b) in enumerate(zip(n0.get_grads(), n1.get_grads())):
                 na = float(np.linalg.norm(a.ravel()))
@@ -384,4 +388,4 @@ def test_replayed_graphs_see_updated_weights_and_survive_reallocation(monkeypatc
         torch.cuda.empty_cache()
     # fp16 fast mode, atomically reduced weight gradients: the two schedules agree to run-to-run noise
     np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=5e-3, atol=1e-5)
-    np.testing.assert_allclose(res["1"][1], res["0"][1], atol=5e-3)
+    np.testing.assert_allclose(res["1"][1], res["0"][1], atol=3e-2)      # G(z) in (0,1) after five updates at lr 1e-3

@@ -97,3 +97,15 @@ def test_tc32_up2conv_matches_simt_fp32(case):
 def test_tc32_stride2_fwd_wgrad_dgrad_match_simt_fp32(case):
     rel, line = tc_probe.run_s2_case32(*case)
     assert rel <= TC32_TOL, line
+
+
+@pytest.mark.parametrize("tc32", [False, True], ids=["fp16", "tc32"])
+@pytest.mark.parametrize("case", tc_probe.UP2_BWD_CASES, ids=[c[0] for c in tc_probe.UP2_BWD_CASES])
+def test_tc_up2conv_backward_on_the_low_res_grid(case, tc32):
+    """Backward of nearest-2x + 5x5 (the generator's layers, reference architectures/dcgan.py:21-22,31-32) evaluated on the
+    LOW-res grid: input gradient as one 6x6 stride-2 convolution of dy (pack mode 20), weight gradient as the gradient of
+    the four 3x3 phase filters (unpack mode 8) -- 36 instead of 100 low-res taps each -- against the SIMT kernels through
+    the virtual upsampling: 3e-3 of the scale on fp16 data (the high-res fp16 input gradient is rounded once more before
+    hm_upsample2_bwd sums it), 5e-5 in tc32 mode."""
+    rel, line = tc_probe.run_up2_bwd_case(*case, tc32=tc32)
+    assert rel <= (TC32_TOL if tc32 else 3e-3), line

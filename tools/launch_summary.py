@@ -15,15 +15,13 @@ def main(path, min_ms=1.0):
     rows = [row for row in r if len(row) > vi]
     # a training step ends with the optimiser launches: keep only the last complete step when there are several
     marks = [i for i, row in enumerate(rows) if 'rmsprop' in row[ki] or 'adam_kernel' in row[ki]]
-    groups = []
-    for i in marks:
-        if groups and i == groups[-1][1] + 1:
-            groups[-1][1] = i
-        else:
-            groups.append([i, i])
-    if len(groups) >= 2:
-        rows = rows[groups[-2][1] + 1:groups[-1][1] + 1]
-        print('last full training step (%d of %d launches)' % (len(rows), len(marks) and groups[-1][1] + 1))
+    # the update of a step = its optimiser launches, each followed by that network's weight re-packs; the first
+    # optimiser launch of a step is the one that comes after a long stretch of other kernels
+    starts = [i for k, i in enumerate(marks) if k == 0 or i - marks[k - 1] > 60]
+    if len(starts) >= 2:
+        # one step period: from the first optimiser launch of the previous step up to that of the last step
+        rows = rows[starts[-2]:starts[-1]]
+        print('last full training step period (%d of %d launches)' % (len(rows), starts[-1]))
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot, big = 0.0, []
     for row in rows:

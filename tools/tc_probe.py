@@ -401,6 +401,64 @@ def run_s2_case32(name, B, H, W, C1, C2, Co):
     return worst, "\n".join(lines)
 
 
+UP2_BWD_CASES = [c for c in UP2_CASES if c[5] % 64 == 0]
+
+
+def run_up2_bwd_case(name, B, H, W, Ci, Co, act, tc32=False):
+    """Backward of nearest-2x + 5x5 'same': the input gradient as ONE 6x6 stride-2 convolution of dy (pack mode 20) and
+    the weight gradient in phase form (hm_tc_wgrad with the forward descriptor, unpack mode 8), against the SIMT kernels
+    through the virtual upsampling (high-res input gradient + hm_upsample2_bwd; gather weight gradient, unpack mode 0).
+    tc32: float32 tensors, tensor-core operands as three-plane bf16 splits."""
+    torch.manual_seed(abs(hash(name)) % 1000 + 17)
+    dt, tdt = (0, torch.float32) if tc32 else (1, torch.float16)
+    x = torch.randn(B, H, W, Ci, device="cuda").to(tdt)
+    dy = torch.randn(B, 2 * H, 2 * W, Co, device="cuda").to(tdt)
+    Wm = torch.randn(Co, Ci, 5, 5, device="cuda") / np.sqrt(25 * Ci)
+    fwd = desc(dtype=dt, B=B, H=H, W=W, C1=Ci, C2=0, up=1, kh=5, kw=5, stride=1, pad=2, transposed=0, Ho=2 * H, Wo=2 * W,
+               Cout=Co, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Co, act=0, slope=0.0, accumulate=0)
+    # ---- weight gradient
+    ref_p = torch.zeros(25 * Ci, Co, device="cuda")
+    _lib.call("hm_conv_wgrad", C.byref(fwd), x.data_ptr(), None, dy.data_ptr(), ref_p.data_ptr(), None)
+    ref_w = torch.empty(Co, Ci, 5, 5, device="cuda")
+    _lib.call("hm_unpack_conv_wgrad", ref_p.data_ptr(), ref_w.data_ptr(), 0, Co, Ci, 5, 5, None)
+    out_p = torch.zeros(9 * Ci, 4 * Co, device="cuda")
+    if tc32:
+        sx, sd = _split(x, 2), _split(dy, 3)
+        d2 = desc(**{f: getattr(fwd, f) for f, _ in fwd._fields_})
+        d2.dtype, d2.B = 2, 6 * B
+        _lib.call("hm_tc_wgrad", C.byref(d2), sx.data_ptr(), None, sd.data_ptr(), out_p.data_ptr(), None)
+    else:
+        _lib.call("hm_tc_wgrad", C.byref(fwd), x.data_ptr(), None, dy.data_ptr(), out_p.data_ptr(), None)
+    out_w = torch.empty(Co, Ci, 5, 5, device="cuda")
+    _lib.call("hm_unpack_conv_wgrad", out_p.data_ptr(), out_w.data_ptr(), 8, Co, Ci, 5, 5, None)
+    # ---- input gradient
+    wp1 = torch.empty(25 * Ci * Co, device="cuda", dtype=tdt)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wp1.data_ptr(), 1, Co, Ci, 5, 5, 0, 0, dt, None)
+    dg = desc(dtype=dt, B=B, H=2 * H, W=2 * W, C1=Co, C2=0, up=0, kh=5, kw=5, stride=1, pad=2, transposed=1, Ho=2 * H,
+              Wo=2 * W, Cout=Ci, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Ci, act=0, slope=0.0, accumulate=0)
+    gup = torch.zeros(B, 2 * H, 2 * W, Ci, device="cuda", dtype=tdt)
+    _lib.call("hm_conv_gather", C.byref(dg), dy.data_ptr(), None, wp1.data_ptr(), None, gup.data_ptr(), None, None)
+    ref_x = torch.zeros(B, H, W, Ci, device="cuda", dtype=tdt)
+    _lib.call("hm_upsample2_bwd", gup.data_ptr(), ref_x.data_ptr(), dt, B, H, W, Ci, 1, 0, None)
+    d6 = desc(dtype=dt, B=B, H=2 * H, W=2 * W, C1=Co, C2=0, up=0, kh=6, kw=6, stride=2, pad=2, transposed=0, Ho=H, Wo=W,
+              Cout=Ci, oH=H, oW=W, os=1, ou=0, ov=0, split=Ci, act=0, slope=0.0, accumulate=0)
+    out_x = torch.full((B, H, W, Ci), 7.0, device="cuda", dtype=tdt)
+    if tc32:
+        w20 = _pack32(Wm, 20, Co, Ci, 5, 5, Co)
+        sdy = _split(dy, 0)
+        d62 = desc(**{f: getattr(d6, f) for f, _ in d6._fields_})
+        d62.dtype, d62.C1 = 2, 6 * Co
+        _lib.call("hm_tc_conv", C.byref(d62), sdy.data_ptr(), None, w20.data_ptr(), None, out_x.data_ptr(), None, None)
+    else:
+        w20 = torch.empty(36 * Ci * Co, device="cuda", dtype=torch.float16)
+        _lib.call("hm_pack_conv_weight", Wm.data_ptr(), w20.data_ptr(), 20, Co, Ci, 5, 5, 0, 0, 1, None)
+        _tc_conv(C.byref(d6), dy.data_ptr(), None, w20.data_ptr(), None, out_x.data_ptr(), None, None)
+    torch.cuda.synchronize()
+    r1, l1 = _cmp32("up2 wgrad" + (" tc32" if tc32 else ""), name, out_w, ref_w)
+    r2, l2 = _cmp32("up2 dgrad" + (" tc32" if tc32 else ""), name, out_x.float(), ref_x.float())
+    return max(r1, r2), l1 + "\n" + l2
+
+
 DC2_CASES = [
     # name, B, H, W (input grid), C1, C2, Cout, act
     ("dc2_128_3_w256_tanh", 1, 256, 256, 64, 64, 3, 4),
@@ -701,6 +759,14 @@ if __name__ == "__main__":
                 print("c1bwd %-22s EXC %s" % (c[0], e), flush=True)
                 break
         perf_c1bwd()
+        sys.exit(0)
+    if sys.argv[1:] == ["up2bwd"]:
+        for c in UP2_BWD_CASES:
+            for tc32 in (False, True):
+                try:
+                    print(run_up2_bwd_case(*c, tc32=tc32)[1], flush=True)
+                except Exception as e:
+                    print("up2bwd %-24s EXC %s" % (c[0], e), flush=True)
         sys.exit(0)
     if sys.argv[1:] == ["tc32"]:
         for fn, cases in ((run_case32, CASES), (run_wgrad_case32, WGRAD_CASES), (run_up2_case32, UP2_CASES),
