@@ -209,6 +209,28 @@ class Pix2Pix(object):
             if net.gflat is base:
                 self._reduced.add(id(net))
 
+    def _update_on_side_stream(self, net, ls):
+        """Optimiser step + weight re-packs of `net` on the weight-gradient side stream, behind the network's last weight
+        gradient (and its all-reduce), while the current stream goes on with work that no longer reads this network's
+        weights or gradients.  Returns False (nothing done) when there is no side stream."""
+        rt = self.rt
+        side = rt._wgrad_stream if rt._wgrad_forked else None
+        if side is None:
+            return False
+        self._sync_lr()
+        world = 1
+        side.wait_stream(torch.cuda.current_stream(rt.device))     # gradients produced on the current stream
+        with torch.cuda.stream(side):
+            if self.pg is not None:
+                import torch.distributed as dist
+                world = dist.get_world_size(self.pg)
+                for work in self._pending:                     # this network's all-reduce(s): the side stream waits
+                    work.wait()
+                self._pending = []
+            net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
+            net.pack()
+        return True
+
     def _adv(self, net, h, dh, target, slot, gscale):
         """adv_loss(out, target).mean() of pix2pix.py:102-110 on a (half) batch of
         discriminator outputs; optionally its gradient."""
@@ -347,6 +369,7 @@ class Pix2Pix(object):
                 # touches D's buffers again before the join at the end of G.backward
                 D.backward(0, 2 * B, wgrad=True, input_grad=True, wscale=ws[:2 * B], ig_range=(B, 2 * B), join=False)
                 self._allreduce_async(D.gflat)                  # under G's backward pass
+                early = self._update_on_side_stream(D, ls)      # ... and so are D's update and weight re-packs
                 n_in = D.inputs[0].grad[B:2 * B].numel() // B
                 rt.call("hm_scale_rows", _ptr(D.inputs[0].grad[B:2 * B]), _ptr(ws[2 * B:]), _ptr(G.out.grad[:B]),
                         rt.cd, B, n_in)
@@ -360,7 +383,7 @@ class Pix2Pix(object):
                         hook = {k: lambda: self._allreduce_async(G.gflat[off:])}
                 G.backward(0, B, wgrad=True, after_op=hook)
                 self._allreduce_async(G.gflat[:off] if hook else G.gflat)
-                upd += [G, D]
+                upd += [G] if early else [G, D]
             else:
                 self._adv(D, h[B:], dh[B:2 * B] if do else None, 0., 1, ls)
                 if do:
