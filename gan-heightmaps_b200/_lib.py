@@ -62,6 +62,8 @@ _PROTOS = {
     "hm_bn_apply_act": ([_P, _P, _I, _LL, _I, _P, _P, _I, _F, _P], C.c_int),
     "hm_bn_bwd_reduce": ([_P, _P, _P, _I, _LL, _I, _P, _P, _I, _F, _P, _P], C.c_int),
     "hm_bn_bwd_apply": ([_P, _P, _P, _P, _I, _LL, _I, _P, _P, _P, _I, _F, _P, _P, _P, _P], C.c_int),
+    "hm_bn_bwd_reduce_a": ([_P, _P, _P, _I, _LL, _I, _P, _P, _P, _P, _I, _F, _P, _P], C.c_int),
+    "hm_bn_bwd_apply_a": ([_P, _P, _P, _P, _I, _LL, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P], C.c_int),
     "hm_act_bwd": ([_P, _P, _P, _I, _LL, _I, _F, _I, _P], C.c_int),
     "hm_col_sum": ([_P, _I, _LL, _I, _P, _P], C.c_int),
     "hm_maxpool2_fwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -727,6 +727,162 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------
+// BatchNorm backward WITHOUT reading the layer's input x: xhat is recovered from the OUTPUT a = act(gamma*xhat + beta),
+//     xhat = (act^-1(a) - beta) / gamma,        act^-1(a) = a >= 0 ? a : a / slope   (linear: a)
+// for invertible activations (linear, leaky rectify with slope > 0) and channels with |gamma| >= 2^-10; a thread whose 8
+// channels include a smaller gamma reads x for them as before.  One tensor less per pass: reduce 3 -> 2 reads,
+// apply 4 -> 3 accesses (fast mode only; the float32 modes keep the x-based form, which is the oracle's arithmetic).
+// ---------------------------------------------------------------------------
+struct BnInv8 {
+  float mu[8], is[8], ig[8], bt[8];
+  bool all_ok;
+  unsigned ok;
+};
+__device__ __forceinline__ void bn_inv8_load(BnInv8& k, const float* mean, const float* inv_std, const float* gamma,
+                                             const float* beta, int c0) {
+  k.ok = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float g = gamma[c0 + j];
+    k.mu[j] = mean[c0 + j];
+    k.is[j] = inv_std[c0 + j];
+    k.bt[j] = beta[c0 + j];
+    const bool ok = fabsf(g) >= 9.765625e-4f;
+    k.ig[j] = ok ? 1.f / g : 0.f;
+    k.ok |= ok ? (1u << j) : 0u;
+  }
+  k.all_ok = k.ok == 0xffu;
+}
+__device__ __forceinline__ float bn_xhat_from_a(const BnInv8& k, int j, float a, float x, float inv_slope) {
+  if ((k.ok >> j) & 1u) return ((a >= 0.f ? a : a * inv_slope) - k.bt[j]) * k.ig[j];
+  return (x - k.mu[j]) * k.is[j];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    bn_bwd_reduce_a_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x, long long M, int C,
+                           const float* __restrict__ mean, const float* __restrict__ inv_std,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, int act, float slope,
+                           double* red) {
+  __shared__ float sh0[256 * 8], sh1[256 * 8];
+  const int cg = C >> 3;
+  const int ct = cg < 256 ? cg : 256;
+  const int lanes = 256 / ct;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct;
+  const bool active = tr < lanes;
+  const long long step = (long long)gridDim.x * lanes;
+  const float inv_slope = act == HM_ACT_LRELU ? 1.f / slope : 1.f;
+  for (int g0 = 0; g0 < cg; g0 += ct) {
+    const int g = g0 + tc;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s0[j] = s1[j] = 0.f;
+    if (active && g < cg) {
+      BnInv8 k;
+      bn_inv8_load(k, mean, inv_std, gamma, beta, g * 8);
+      long long m = (long long)blockIdx.x * lanes + tr;
+      for (; m + step < M; m += 2 * step) {                 // two rows in flight: four independent 16-byte loads
+        const size_t o0 = (size_t)m * C + g * 8, o1 = (size_t)(m + step) * C + g * 8;
+        float g0v[8], a0v[8], x0v[8], g1v[8], a1v[8], x1v[8];
+        load8(da + o0, g0v);
+        load8(a + o0, a0v);
+        load8(da + o1, g1v);
+        load8(a + o1, a1v);
+        if (!k.all_ok) {
+          load8(x + o0, x0v);
+          load8(x + o1, x1v);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gg0 = g0v[j] * act_grad_from_out(a0v[j], act, slope);
+          const float gg1 = g1v[j] * act_grad_from_out(a1v[j], act, slope);
+          s0[j] += gg0 + gg1;
+          s1[j] += gg0 * bn_xhat_from_a(k, j, a0v[j], k.all_ok ? 0.f : x0v[j], inv_slope) +
+                   gg1 * bn_xhat_from_a(k, j, a1v[j], k.all_ok ? 0.f : x1v[j], inv_slope);
+        }
+      }
+      for (; m < M; m += step) {
+        const size_t o = (size_t)m * C + g * 8;
+        float gv[8], av[8], xv[8];
+        load8(da + o, gv);
+        load8(a + o, av);
+        if (!k.all_ok) load8(x + o, xv);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gg = gv[j] * act_grad_from_out(av[j], act, slope);
+          s0[j] += gg;
+          s1[j] += gg * bn_xhat_from_a(k, j, av[j], k.all_ok ? 0.f : xv[j], inv_slope);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sh0[threadIdx.x * 8 + j] = s0[j];
+      sh1[threadIdx.x * 8 + j] = s1[j];
+    }
+    __syncthreads();
+    if (tr == 0 && g < cg) {
+      for (int l = 1; l < lanes; l++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s0[j] += sh0[(l * ct + tc) * 8 + j];
+          s1[j] += sh1[(l * ct + tc) * 8 + j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        atomicAdd(red + g * 8 + j, (double)s0[j]);
+        atomicAdd(red + C + g * 8 + j, (double)s1[j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// requires (gridDim.x * blockDim.x) % (C/8) == 0, as bn_bwd_apply_v8h_kernel
+template <typename T>
+__global__ void __launch_bounds__(256)
+    bn_bwd_apply_a_kernel(const T* __restrict__ da, const T* __restrict__ a, const T* __restrict__ x, T* __restrict__ dx,
+                          long long M, int C, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, int act, float slope,
+                          const double* __restrict__ red, float* dgamma, float* dbeta) {
+  const int cg = C >> 3;
+  const long long n8 = M * cg;
+  const float invM = 1.f / (float)M;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n8) return;
+  const int c0 = (int)(i0 % cg) * 8;
+  const float inv_slope = act == HM_ACT_LRELU ? 1.f / slope : 1.f;
+  BnInv8 k;
+  bn_inv8_load(k, mean, inv_std, gamma, beta, c0);
+  float gi[8], r0m[8], r1m[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int c = c0 + j;
+    const float r0 = (float)red[c], r1 = (float)red[C + c];
+    gi[j] = gamma[c] * k.is[j];
+    r0m[j] = r0 * invM;
+    r1m[j] = r1 * invM;
+    if (i0 < cg) {
+      if (dgamma) dgamma[c] = r1;
+      if (dbeta) dbeta[c] = r0;
+    }
+  }
+  for (long long i = i0; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float gv[8], av[8], xv[8], o[8];
+    load8(da + i * 8, gv);
+    load8(a + i * 8, av);
+    if (!k.all_ok) load8(x + i * 8, xv);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float gg = gv[j] * act_grad_from_out(av[j], act, slope);
+      const float xh = bn_xhat_from_a(k, j, av[j], k.all_ok ? 0.f : xv[j], inv_slope);
+      o[j] = gi[j] * (gg - r0m[j] - xh * r1m[j]);
+    }
+    store8(dx + i * 8, o);
+  }
+}
+
 // same idea for the forward apply: scale/shift of a thread's 8 channels are loop invariants
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1324,6 +1480,44 @@ extern "C" int hm_bn_bwd_apply(const void* da, const void* a, const void* x, voi
                         (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, act, slope,
                         red, dgamma, dbeta)));
   HM_CHECK_LAUNCH("hm_bn_bwd_apply");
+  return HM_OK;
+}
+
+// xhat from the layer's OUTPUT where that is possible (see bn_bwd_reduce_a_kernel): same results up to rounding, one
+// tensor read less.  Falls back to hm_bn_bwd_reduce / hm_bn_bwd_apply for shapes or activations it does not cover.
+static inline bool bn_from_a_ok(int act, float slope, int C) {
+  return C % 8 == 0 && (act == HM_ACT_LINEAR || (act == HM_ACT_LRELU && slope > 1e-3f));
+}
+
+extern "C" int hm_bn_bwd_reduce_a(const void* da, const void* a, const void* x, int dtype, long long M, int C,
+                                  const float* mean, const float* inv_std, const float* gamma, const float* beta, int act,
+                                  float slope, double* red, void* stream) {
+  CHECK_DTYPE(dtype, "hm_bn_bwd_reduce_a");
+  HM_CHECK_ARG(da && a && x && mean && inv_std && gamma && beta && red && M > 0 && C > 0, "hm_bn_bwd_reduce_a: bad argument");
+  if (!bn_from_a_ok(act, slope, C) || !al16(da) || !al16(a) || !al16(x))
+    return hm_bn_bwd_reduce(da, a, x, dtype, M, C, mean, inv_std, act, slope, red, stream);
+  int cg = C / 8, l8 = 256 / (cg < 256 ? cg : 256);
+  unsigned g8 = ew_grid((M + l8 - 1) / l8, 1, 4);
+  DISPATCH_T(dtype, (bn_bwd_reduce_a_kernel<T><<<g8, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)da, (const T*)a, (const T*)x, M, C, mean, inv_std, gamma, beta, act, slope, red)));
+  HM_CHECK_LAUNCH("hm_bn_bwd_reduce_a");
+  return HM_OK;
+}
+
+extern "C" int hm_bn_bwd_apply_a(const void* da, const void* a, const void* x, void* dx, int dtype, long long M, int C,
+                                 const float* mean, const float* inv_std, const float* gamma, const float* beta, int act,
+                                 float slope, const double* red, float* dgamma, float* dbeta, void* stream) {
+  CHECK_DTYPE(dtype, "hm_bn_bwd_apply_a");
+  HM_CHECK_ARG(da && a && x && dx && mean && inv_std && gamma && beta && red && M > 0 && C > 0,
+               "hm_bn_bwd_apply_a: bad argument");
+  const long long n = M * C;
+  const unsigned ga = ew_grid(n / 8 > 0 ? n / 8 : 1);
+  if (!bn_from_a_ok(act, slope, C) || !al16(da) || !al16(a) || !al16(x) || !al16(dx) || ((long long)ga * 256) % (C / 8) != 0)
+    return hm_bn_bwd_apply(da, a, x, dx, dtype, M, C, mean, inv_std, gamma, act, slope, red, dgamma, dbeta, stream);
+  DISPATCH_T(dtype, (bn_bwd_apply_a_kernel<T><<<ga, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)da, (const T*)a, (const T*)x, (T*)dx, M, C, mean, inv_std, gamma, beta, act, slope, red,
+                        dgamma, dbeta)));
+  HM_CHECK_LAUNCH("hm_bn_bwd_apply_a");
   return HM_OK;
 }
 

@@ -905,16 +905,29 @@ class BNActOp(object):
         bm, bi = self.st[0], self.st[1]
         da, a, x = self.out.g(lo, hi), self.out.b(lo, hi), self.x.b(lo, hi)
         self.red.zero_()
-        rt.call("hm_bn_bwd_reduce", _ptr(da), _ptr(a), _ptr(x), rt.cd, M, self.Cn, _ptr(bm), _ptr(bi),
-                ACT[self.act.name], self.act.slope, _ptr(self.red))
+        # fast mode: xhat from the layer's output instead of reading x a third time (hm_bn_bwd_*_a, include/hmgan.h)
+        from_a = rt.precision == "fast" and os.environ.get("HMGAN_BN_FROM_A", "1") != "0"
+        gam, bet = _ptr(net.pview(self.gamma)), _ptr(net.pview(self.beta))
+        if from_a:
+            rt.call("hm_bn_bwd_reduce_a", _ptr(da), _ptr(a), _ptr(x), rt.cd, M, self.Cn, _ptr(bm), _ptr(bi), gam, bet,
+                    ACT[self.act.name], self.act.slope, _ptr(self.red))
+        else:
+            rt.call("hm_bn_bwd_reduce", _ptr(da), _ptr(a), _ptr(x), rt.cd, M, self.Cn, _ptr(bm), _ptr(bi),
+                    ACT[self.act.name], self.act.slope, _ptr(self.red))
         if rt.sync_bn_group is not None:
             # [sum g, sum g*xhat] averaged over ranks: dx then uses the global-batch means, and d gamma / d beta come
             # out as (global sum) / world -- what the later sum all-reduce + 1/world of the gradients expects
             rt.allreduce_mean(self.red)
         assert self.x.consumers == 1
         self.x.gw = True
+        if from_a:
+            rt.call("hm_bn_bwd_apply_a", _ptr(da), _ptr(a), _ptr(x), _ptr(self.x.g(lo, hi)), rt.cd, M, self.Cn,
+                    _ptr(bm), _ptr(bi), gam, bet, ACT[self.act.name], self.act.slope,
+                    _ptr(self.red), _ptr(net.gview(self.gamma)) if wgrad else None,
+                    _ptr(net.gview(self.beta)) if wgrad else None)
+            return
         rt.call("hm_bn_bwd_apply", _ptr(da), _ptr(a), _ptr(x), _ptr(self.x.g(lo, hi)), rt.cd, M, self.Cn,
-                _ptr(bm), _ptr(bi), _ptr(net.pview(self.gamma)), ACT[self.act.name], self.act.slope,
+                _ptr(bm), _ptr(bi), gam, ACT[self.act.name], self.act.slope,
                 _ptr(self.red), _ptr(net.gview(self.gamma)) if wgrad else None,
                 _ptr(net.gview(self.beta)) if wgrad else None)
 

@@ -258,6 +258,17 @@ int hm_bn_bwd_apply(const void* da, const void* a, const void* x, void* dx, int 
                     int C, const float* mean, const float* inv_std, const float* gamma, int act,
                     float slope, const double* red, float* dgamma, float* dbeta, void* stream);
 
+/* The same two passes without reading x where xhat can be recovered from the layer's OUTPUT a = act(gamma*xhat + beta):
+ * xhat = (act^-1(a) - beta)/gamma for linear / leaky-rectify (slope > 0) layers and channels with |gamma| >= 2^-10 (other
+ * channels, activations and shapes read x exactly as above).  One tensor less per pass; results agree with the x-based
+ * form to the rounding of a.  Used by the fp16 fast mode. */
+int hm_bn_bwd_reduce_a(const void* da, const void* a, const void* x, int dtype, long long M, int C, const float* mean,
+                       const float* inv_std, const float* gamma, const float* beta, int act, float slope, double* red,
+                       void* stream);
+int hm_bn_bwd_apply_a(const void* da, const void* a, const void* x, void* dx, int dtype, long long M, int C,
+                      const float* mean, const float* inv_std, const float* gamma, const float* beta, int act, float slope,
+                      const double* red, float* dgamma, float* dbeta, void* stream);
+
 /* ---- elementwise / pooling / resampling ----------------------------------- */
 /* dx = dy * act'(y)   (NonlinearityLayer backward expressed through the OUTPUT y) */
 int hm_act_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, int act, float slope,

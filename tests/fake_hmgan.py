@@ -365,6 +365,16 @@ def hm_bn_bwd_apply(da, a, x, dx, dtype, M, Cn, mean, inv_std, gamma, act, slope
     return 0
 
 
+def hm_bn_bwd_reduce_a(da, a, x, dtype, M, Cn, mean, inv_std, gamma, beta, act, slope, red, stream=None):
+    """Contract: the results of hm_bn_bwd_reduce up to the rounding of a (the emulation uses the x-based form)."""
+    return hm_bn_bwd_reduce(da, a, x, dtype, M, Cn, mean, inv_std, act, slope, red)
+
+
+def hm_bn_bwd_apply_a(da, a, x, dx, dtype, M, Cn, mean, inv_std, gamma, beta, act, slope, red, dgamma, dbeta,
+                      stream=None):
+    return hm_bn_bwd_apply(da, a, x, dx, dtype, M, Cn, mean, inv_std, gamma, act, slope, red, dgamma, dbeta)
+
+
 def hm_act_bwd(dy, y, dx, dtype, n, act, slope, accumulate, stream=None):
     g = _t(_a(dy, n, _NP[dtype]))
     yv = _t(_a(y, n, _NP[dtype]))

@@ -156,7 +156,9 @@ def test_batchnorm_chain(M, Cn, dtype):
     sums = bo.t(np.zeros(2 * Cn), torch.float64)
     bo.run("hm_bn_stats", lambda P: (P(x), dtype, M, Cn, P(sums)))
     bo.check(sums, 1e-5, "bn_stats")
-    gamma, beta = bo.t(r.rand(Cn) + 0.5), bo.t(r.randn(Cn))
+    gam = r.rand(Cn) + 0.5
+    gam[0] = 1e-5                                   # below the 2^-10 threshold of hm_bn_bwd_*_a: x-based fallback
+    gamma, beta = bo.t(gam), bo.t(r.randn(Cn))
     rm, ri = bo.t(r.randn(Cn)), bo.t(r.rand(Cn) + 0.5)
     outs = [bo.t(np.zeros(Cn)) for _ in range(4)]
     # use the CPU sums on both sides so the comparison below isolates each kernel
@@ -182,6 +184,17 @@ def test_batchnorm_chain(M, Cn, dtype):
     bo.check(dx, TOL[dtype], "bn_bwd_apply")
     bo.check(dg, 1e-6, "dgamma")
     bo.check(db, 1e-6, "dbeta")
+    # the same two passes with xhat recovered from the OUTPUT a instead of reading x (hm_bn_bwd_*_a; a channel with a
+    # tiny gamma takes the x-based fallback inside the kernel): equal up to the rounding of a
+    red2 = bo.t(np.zeros(2 * Cn), torch.float64)
+    dx2 = bo.t(np.zeros((M, Cn)), TD[dtype])
+    bo.run("hm_bn_bwd_reduce_a", lambda P: (P(da), P(a), P(x), dtype, M, Cn, P(outs[0]), P(outs[1]), P(gamma), P(beta),
+                                            1, 0.2, P(red2)))
+    bo.check(red2, 1e-4 if dtype == 0 else 5e-3, "bn_bwd_reduce_a")
+    bo.gpu[red2].copy_(bo.cpu[red2])
+    bo.run("hm_bn_bwd_apply_a", lambda P: (P(da), P(a), P(x), P(dx2), dtype, M, Cn, P(outs[0]), P(outs[1]), P(gamma),
+                                           P(beta), 1, 0.2, P(red2), P(dg), P(db)))
+    bo.check(dx2, 1e-4 if dtype == 0 else 5e-3, "bn_bwd_apply_a")
     # deterministic mode: scale/shift from the running statistics
     bo.run("hm_bn_finalize", lambda P: (None, M, Cn, P(gamma), P(beta), P(rm), P(ri), 1e-4, 0.1, 0, None, None,
                                         P(outs[2]), P(outs[3])))

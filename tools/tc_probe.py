@@ -730,7 +730,37 @@ def perf():
             print("perf %-26s %s %8.3f ms  %7.1f TFLOP/s" % (name, what, ms, flop / ms / 1e9), flush=True)
 
 
+def perf_up2():
+    """Forward of the generator's last layers in phase form (nearest-2x + 5x5 as four 3x3 convolutions on the low-res grid):
+    64 -> 1 @256^2 x32 (N = 4 real columns in one zero-padded 16-column tile) and 64 -> 64 @128^2 / @256^2 x32."""
+    for (name, B, H, W, Ci, Co, act) in (("Gout 64->1 @256^2(low) x32", 32, 256, 256, 64, 1, 3),
+                                         ("G7 64->64 @128^2(low) x32", 32, 128, 128, 64, 64, 0),
+                                         ("G6 64->64 @64^2(low) x32", 32, 64, 64, 64, 64, 0)):
+        x = torch.randn(B, H, W, Ci, device="cuda").half()
+        w8 = (torch.randn(36 * Ci * Co, device="cuda") * 0.02).half()
+        bias = torch.zeros(Co, device="cuda")
+        y = torch.empty(B, 2 * H, 2 * W, Co, device="cuda", dtype=torch.float16)
+        d = desc(dtype=1, B=B, H=H, W=W, C1=Ci, C2=0, up=1, kh=5, kw=5, stride=1, pad=2, transposed=0, Ho=2 * H, Wo=2 * W,
+                 Cout=Co, oH=2 * H, oW=2 * W, os=1, ou=0, ov=0, split=Co, act=act, slope=0.2, accumulate=0)
+        fn = lambda: _tc_conv(C.byref(d), x.data_ptr(), None, w8.data_ptr(), bias.data_ptr(), y.data_ptr(), None, None)  # noqa: E731
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        gb = (x.numel() + y.numel()) * 2 / 1e9
+        print("perf %-30s %8.3f ms  %7.1f GB/s  %7.1f TFLOP/s (36-tap)" % (
+            name, ms, gb / ms * 1e3, 2.0 * B * H * W * 36 * Ci * Co / ms / 1e9), flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["perf_up2"]:
+        perf_up2()
+        sys.exit(0)
     if sys.argv[1:] == ["perf"]:
         perf()
         sys.exit(0)
