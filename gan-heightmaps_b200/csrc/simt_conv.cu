@@ -332,6 +332,11 @@ __device__ __forceinline__ void pack_elem(const float* __restrict__ w, T* __rest
         }
       }
     }
+  } else if (mode == 21) {
+    // DenseLayer W (in, out) as a 1x1 tensor-core convolution: Wt[co][ci] = W[ci][co]   (K-major, K = ci)
+    int ci = (int)(i % cin);
+    int co = (int)(i / cin);
+    val = w[(size_t)ci * cout + co];
   } else if (mode == 20) {
     // input gradient of (nearest-2x -> 5x5 'same' conv) as ONE 6x6 stride-2 pad-2 convolution of dy on the low-res grid:
     //   dx[q][ci] = sum_{u,v<6} sum_co dy[2q-2+(u,v)][co] * Wt[(u*6+v)][ci][co]
@@ -595,7 +600,7 @@ extern "C" int hm_pack_conv_weight_multi(const HmPackJob* jobs_dev, int n_jobs, 
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 20),
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 21),
                "hm_pack_conv_weight: bad mode %d", mode);
   HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
   HM_CHECK_ARG((mode != 15 && mode != 16) || (cin == 1 && kh == 5 && kw == 5),

@@ -1405,7 +1405,10 @@ extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
     return d->oH == d->Ho && d->oW == d->Wo;
   }
   if (d->os != 1 || d->ou || d->ov || d->split <= 0 || d->split > d->Cout) return 0;
-  if (d->C1 % KCH || d->C2 % KCH || d->C1 <= 0) return 0;
+  // channels: multiples of 64 per source -- or ONE source whose channel count is any multiple of 8 (16-byte rows: a
+  // DenseLayer's input, dcgan.py:16, latent_dim = 1000): the last 64-channel K slice is then partly out of bounds in
+  // both tensor maps and zero-filled by the TMA unit
+  if (d->C1 <= 0 || d->C2 % KCH || (d->C1 % KCH && (d->C2 != 0 || d->C1 % 8 || d->dtype != HM_F16))) return 0;
   if (d->Cout < 1 || pick_ntile(d->Cout, d->split) == 0) return 0;
   if (d->Ho != d->H + 2 * d->pad - d->kh + 1 || d->Wo != d->W + 2 * d->pad - d->kw + 1) return 0;
   if (d->oH != d->Ho || d->oW != d->Wo) return 0;
@@ -1493,7 +1496,9 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   p.cph = d->Cout;
   p.stride = (!up2 && d->stride == 2) ? 2 : 1;
   p.B = d->B; p.Ho = up2 ? d->H : d->Ho; p.Wo = up2 ? d->W : d->Wo;       // tile grid (low-res when phase-decomposed)
-  p.Cin = d->C1 + d->C2; p.C1 = d->C1; p.Cout = up2 ? 4 * d->Cout : d->Cout;
+  const int cin_real = d->C1 + d->C2;
+  p.Cin = (cin_real + KCH - 1) / KCH * KCH;           // K slices of 64 channels; a ragged tail is TMA zero fill
+  p.C1 = d->C2 ? d->C1 : p.Cin; p.Cout = up2 ? 4 * d->Cout : d->Cout;
   p.kh = dc2 ? 1 : (dg2 ? 2 : (up2 ? 3 : d->kh)); p.kw = dc2 ? 1 : (dg2 ? 2 : (up2 ? 3 : d->kw));
   p.pad = (dg2 || dc2) ? 0 : (up2 ? 1 : d->pad);
   p.bw = pow2_floor(p.Wo < TILE_M ? p.Wo : TILE_M);
@@ -1537,7 +1542,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   int rc = encode_act(&tmA, x1, d->B, d->H, d->W, d->C1, p.bw, p.bh, p.bn, p.stride);
   if (!rc) rc = d->C2 ? encode_act(&tmA2, x2, d->B, d->H, d->W, d->C2, p.bw, p.bh, p.bn, p.stride) : 0;
   if (!d->C2) tmA2 = tmA;
-  if (!rc) rc = encode_wgt(&tmB, w_tc, p.kh * p.kw, p.Cout, p.Cin, p.ntile);
+  if (!rc) rc = encode_wgt(&tmB, w_tc, p.kh * p.kw, p.Cout, cin_real, p.ntile);
   if (rc) {
     set_error("hm_tc_conv: cuTensorMapEncodeTiled failed (CUresult %d)", rc);
     return HM_ERR_CUDA;
@@ -1582,7 +1587,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
         rc = encode_act(&rA, x1, d->B, d->H, d->W, d->C1, TILE_M + q.kw - 1, 1, 1);
         if (!rc) rc = d->C2 ? encode_act(&rA2, x2, d->B, d->H, d->W, d->C2, TILE_M + q.kw - 1, 1, 1) : 0;
         if (!d->C2) rA2 = rA;
-        if (!rc) rc = encode_wgt(&hB, w_tc, q.kh * q.kw, q.Cout, q.Cin, q.ntile / 2);
+        if (!rc) rc = encode_wgt(&hB, w_tc, q.kh * q.kw, q.Cout, cin_real, q.ntile / 2);
         if (rc) {
           set_error("hm_tc_conv: cuTensorMapEncodeTiled failed for the pair variant (CUresult %d)", rc);
           return HM_ERR_CUDA;

@@ -371,6 +371,12 @@ class ConvOp(object):
                     self.tc_dg = self.dg2 = ok
                 else:
                     self.dg2_cat = ok        # gradient of the whole (thin) concat on the tensor cores, then sliced
+        # DenseLayer (the generator's first layer, z[B,1000] -> 8192) as a 1x1 tensor-core convolution over [B,1,1,in]
+        # (pack mode 21; the SIMT gather spent 0.17 ms on 0.5 GFLOP there); its weight gradient stays on the SIMT kernel
+        self.dense_tc = False
+        if rt.precision == "fast" and kind == "dense" and self.x2 is None and self.Cin % 8 == 0:
+            self.dense_tc = rt.tc_supported(self._dense_desc(rt, 1))
+            self.tc_fwd = self.dense_tc
         # one-channel input (first discriminator layer): im2col to 64 "tap channels", then a 1x1 tensor-core GEMM
         self.col1 = (rt.precision == "fast" and kind == "conv" and self.Cin == 1 and self.x2 is None and not self.up
                      and self.stride == 1 and self.kh * self.kw <= 64 and 2 * self.pad == self.kh - 1
@@ -462,7 +468,9 @@ class ConvOp(object):
     def pack(self, rt):
         """master (Lasagne layout, fp32) -> packed [K][Cout] copies in the compute dtype."""
         w = self.net.pview(self.W)
-        if self.kind == "dense":
+        if self.kind == "dense" and self.dense_tc:
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 21, self.Cout, self.Cin, 1, 1, 0, 0, rt.cd)
+        elif self.kind == "dense":
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wp_f), 4, self.Cout, self.Cin, 1, 1, 0, 0, rt.cd)
         elif self.kind == "conv":
             if self.pool_fused is not None:
@@ -587,6 +595,19 @@ class ConvOp(object):
         d.accumulate = acc
         return d
 
+    def _dense_desc(self, rt, n):
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        d.B, d.H, d.W, d.C1, d.C2, d.up = n, 1, 1, self.Cin, 0, 0
+        d.kh = d.kw = 1
+        d.stride, d.pad, d.transposed = 1, 0, 0
+        d.Ho, d.Wo, d.Cout = 1, 1, self.Cout
+        d.oH, d.oW, d.os, d.ou, d.ov = 1, 1, 1, 0, 0
+        d.split = self.Cout
+        d.act, d.slope = ACT[self.act.name], self.act.slope
+        d.accumulate = 0
+        return d
+
     def _dg6_desc(self, rt, n, acc):
         """Input gradient of (nearest-2x -> 5x5 'same' conv) as a forward 6x6 stride-2 pad-2 convolution of dy
         [n, 2H, 2W, Cout] onto the low-res source grid [n, H, W, Cin] (weights: pack mode 20)."""
@@ -633,7 +654,9 @@ class ConvOp(object):
         x2 = _ptr(self.x2.b(lo, hi)) if self.x2 is not None else None
         bias = _ptr(self.net.pview(self.bias))
         y = _ptr(self.out.b(lo, hi)) if self.out.buf is not None else None
-        if self.dc2:
+        if self.dense_tc:
+            rt.call("hm_tc_conv", C.byref(self._dense_desc(rt, n)), x1, None, _ptr(self.wt_f), bias, y, None)
+        elif self.dc2:
             rt.call("hm_tc_conv", C.byref(self._dc2_desc(rt, n)), x1, x2, _ptr(self.wt_f), bias, y, None)
         elif self.kind == "deconv":
             per = self.Cin * self.Cout

@@ -214,6 +214,8 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  *          convolution of dy landing directly on the low-res source grid -> Wt[(u*6+v)][ci][co] (K-major, K = co): the
  *          adjoint of the four 3x3 phase filters of mode 8; 36 taps on H x W pixels instead of 25 taps on 2H x 2W
  *          followed by hm_upsample2_bwd (mode 14 is its Cout == 1 case for hm_c1s2_conv)
+ *  mode 21: DenseLayer W (in,out) -> Wt[co][ci] (K-major): the layer as a 1x1 tensor-core convolution over a [B,1,1,in]
+ *          tensor; `in` may be any multiple of 8 (hm_tc_conv zero-fills the last 64-channel slice, e.g. latent_dim 1000)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)
  * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the

@@ -188,6 +188,8 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
                     for s_ in range(5):
                         if (py + r - 2) // 2 + 1 == dy_ and (px + s_ - 2) // 2 + 1 == dx_:
                             out[:, uu * 6 + vv] += Wc[:, r, s_]
+    elif mode == 21:
+        out = W.reshape(cin, cout).T                                             # [co][ci]
     elif mode == 20:
         Wc = W.reshape(cout, cin, 5, 5)[:, :, ::-1, ::-1]                        # correlation taps Wc[co][ci][r][s]
         out = np.zeros((36, cin, cout), np.float32)
@@ -657,6 +659,7 @@ def _is_deconv_d2s(d):
 
 
 def _tc_ok(d, wgrad):
+    dtype0 = d.dtype
     if d.dtype == BF16X3:            # bf16 hi/lo splits of fp32 tensors: same shape rules as fp16
         d = type(d).from_buffer_copy(d)
         d.dtype = F16
@@ -679,7 +682,8 @@ def _tc_ok(d, wgrad):
     if not wgrad and d.dtype == F16 and _is_up2conv(d):
         return d.C1 % 64 == 0 and d.C1 > 0 and d.os == 1 and not d.ou and not d.ov and d.oH == d.Ho and d.oW == d.Wo
     ok = d.dtype == F16 and not d.transposed and not d.up and d.stride == 1 and d.os == 1 and not d.ou and not d.ov
-    ok = ok and d.C1 % 64 == 0 and d.C2 % 64 == 0 and d.C1 > 0
+    ragged = (not wgrad) and d.C2 == 0 and d.C1 % 8 == 0 and dtype0 == F16         # one source, TMA zero-fills the tail
+    ok = ok and d.C2 % 64 == 0 and d.C1 > 0 and (d.C1 % 64 == 0 or ragged)
     ok = ok and d.Ho == d.H + 2 * d.pad - d.kh + 1 and d.Wo == d.W + 2 * d.pad - d.kw + 1
     ok = ok and d.oH == d.Ho and d.oW == d.Wo
     if wgrad:

@@ -228,7 +228,9 @@ def test_fast_mode_lowering_uses_tensor_core_kernels_where_eligible(cpu_backend,
     # G's nearest-2x -> conv5x5(64->1), both through hm_c1s2_conv
     assert calls.get("hm_c1s2_conv", 0) >= 2 and m.D.ops[0].pool_fused is not None and m.G.ops[-1].c1dg, calls
     paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
-    assert "tcgen05" in paths and "simt" in paths
+    # every convolution of this model is on the tensor cores, the DenseLayer included (1x1 convolution, ragged K)
+    # (hm_conv_gather remains for the input gradient of the discriminator's one-channel head)
+    assert set(paths) == {"tcgen05"} and m.G.ops[0].dense_tc and calls.get("hm_conv_gather", 0) <= 1, (paths, calls)
 
 
 def test_fast_mode_stride2_layers_route_to_tensor_cores(cpu_backend, monkeypatch):
