@@ -373,18 +373,25 @@ def main():
 
 
 def _finish(world, ok=True):
-    """Tear the NCCL communicator down (the models and their captured graphs, which hold collectives of that
-    communicator, are gone by now); a replica mismatch fails the run."""
+    """Multi-rank runs leave WITHOUT tearing the NCCL communicator down: dist.destroy_process_group() hangs in this image
+    once CUDA graphs holding collectives of the communicator have been replayed (observed again in round 2 on 2 x B200
+    with the models and graphs deleted and the device synchronised first: the JSON line was out, the call never
+    returned, the launcher had to be killed).  Everything this process had to say is flushed; the exit status carries
+    the replica check.  HMGAN_BENCH_DESTROY_PG=1 tries the clean teardown."""
     sys.stdout.flush()
     sys.stderr.flush()
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.synchronize()
-        if os.environ.get("HMGAN_BENCH_HARD_EXIT", "0") == "1":
-            os._exit(0 if ok else 1)
-        dist.destroy_process_group()
     if not ok:
-        sys.exit("bench.py: data-parallel replicas diverged (parameter checksums differ across ranks)")
+        sys.stderr.write("bench.py: data-parallel replicas diverged (parameter checksums differ across ranks)\n")
+        sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        if os.environ.get("HMGAN_BENCH_DESTROY_PG", "0") == "1":
+            import torch.distributed as dist
+            dist.destroy_process_group()
+            sys.exit(0 if ok else 1)
+        os._exit(0 if ok else 1)
+    if not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,16 @@ def _setup(rank, world, port):
     return dist
 
 
+def _leave():
+    """Results are on disk: leave without tearing the NCCL communicator down.  destroy_process_group() hangs in this
+    image once CUDA graphs holding collectives of the communicator have been replayed (observed on 2 x B200 for both
+    bench.py and these workers: everything had completed, the call never returned)."""
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def _worker_parity(rank, world, port, out_dir):
     dist = _setup(rank, world, port)
     from oracle import step as S
@@ -58,9 +68,7 @@ def _worker_parity(rank, world, port, out_dir):
     if rank == 0:
         out.update({"opG%d" % i: v for i, v in enumerate(om.get_all_param_values('G'))})
     np.savez(os.path.join(out_dir, "parity%d.npz" % rank), **out)
-    del m
-    torch.cuda.synchronize()
-    dist.destroy_process_group()
+    _leave()
 
 
 def _worker_fast(rank, world, port, out_dir):
@@ -94,9 +102,7 @@ def _worker_fast(rank, world, port, out_dir):
     out["pD"] = m.D.pflat.detach().cpu().numpy()
     out["graphs"] = np.asarray([sum(1 for st in m._graphs.values() if st.get("gA") is not None or st.get("graph") is not None)])
     np.savez(os.path.join(out_dir, "fast%d.npz" % rank), **out)
-    del m, solo
-    torch.cuda.synchronize()
-    dist.destroy_process_group()
+    _leave()
 
 
 def test_two_ranks_over_nccl_equal_the_oracle_on_the_whole_batch(tmp_path):
