@@ -40,6 +40,7 @@ _PROTOS = {
     "hm_conv_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_conv": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_conv_ws": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _LL, _P], C.c_int),
+    "hm_tc_conv_pool": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "hm_tc_wgrad": ([C.POINTER(ConvDesc), _P, _P, _P, _P, _P], C.c_int),
     "hm_split_bf16x3": ([_P, _P, _LL, _I, _I, _I, _P], C.c_int),
     "hm_up2conv_wgrad_phases": ([C.POINTER(ConvDesc), _P, _P, _P, _P], C.c_int),
@@ -100,7 +101,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    for name in ("hm_tc_conv_supported", "hm_tc_wgrad_supported"):
+    for name in ("hm_tc_conv_supported", "hm_tc_wgrad_supported", "hm_tc_conv_pool_supported"):
         getattr(lib, name).argtypes = [C.POINTER(ConvDesc)]
         getattr(lib, name).restype = C.c_int
     lib.hm_tc_conv_ws_bytes.argtypes = [C.POINTER(ConvDesc)]
@@ -110,7 +111,8 @@ def load():
 
 
 def exported_symbols():
-    return sorted(list(_PROTOS) + ["hm_tc_conv_supported", "hm_tc_wgrad_supported", "hm_tc_conv_ws_bytes"])
+    return sorted(list(_PROTOS) + ["hm_tc_conv_supported", "hm_tc_wgrad_supported", "hm_tc_conv_ws_bytes",
+                                   "hm_tc_conv_pool_supported"])
 
 
 def pack_count(mode, cout, cin, kh, kw):

@@ -50,6 +50,9 @@ struct TcParams {
   int d2s;                 // 1: nearest-2x + 5x5 as four 3x3 phase convolutions: N = (phase, co), the epilogue scatters
                            //    phase (py,px) of low-res pixel (qy,qx) to output pixel (2qy+py, 2qx+px)
   int cph;                 // channels per phase (= real Cout) when d2s
+  int pool;                // row-box kernel, S == 2: 2x2 max-pool fused into the epilogue; the two sub-tiles of a super tile
+                           // are the image rows 2yp, 2yp+1 of one 128-pixel segment, y is the POOLED tensor
+  uint8_t* idx;            // [B, Ho/2, Wo/2, Cout] argmax bytes (pool)
   int bf16;                // operands are bfloat16 (HM_BF16X3: hi/lo splits of fp32 tensors) instead of fp16
   int out32;               // y / y2 are float tensors (HM_BF16X3): the fp32 accumulator is stored unrounded
 };
@@ -191,6 +194,21 @@ __device__ __forceinline__ void epi_pack32(const uint32_t* v, const float* bias3
   }
 }
 
+// M tile -> (x segment, image row block, image block).  Pooled layers enumerate their tiles so that the consecutive
+// tiles 2k, 2k+1 -- the two sub-tiles of a super tile (S == 2) -- are the rows 2yp and 2yp+1 of the same segment.
+__device__ __forceinline__ void mtile_coords(const TcParams& p, int mt, int& tx, int& ty, int& tn) {
+  if (p.pool) {
+    const int i = mt & 1, pt = mt >> 1, hy = p.tiles_y >> 1;
+    tx = pt % p.tiles_x;
+    ty = 2 * ((pt / p.tiles_x) % hy) + i;
+    tn = pt / (p.tiles_x * hy);
+  } else {
+    tx = mt % p.tiles_x;
+    ty = (mt / p.tiles_x) % p.tiles_y;
+    tn = mt / (p.tiles_x * p.tiles_y);
+  }
+}
+
 // HM_BF16X3 epilogue: up to 32 accumulator columns -> (+ stored value) + bias -> activation -> FLOAT stores (the fp32
 // accumulator is kept unrounded: the operands were bf16 hi/lo splits of fp32 tensors, see hm_split_bf16x3)
 template <int ACT>
@@ -251,11 +269,58 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
     tc_fence_after();
     const int col0 = nt * p.ntile;
     const float* bias_t = bias_s + col0;
+    if (!OUT32 && p.pool) {
+      // ---- conv + bias + activation + 2x2 max-pool: lane = pixel x of the rows 2yp (accumulator 0) and 2yp+1
+      // (accumulator 1); vertical max in registers, horizontal max with the neighbouring lane; the even lanes write the
+      // pooled pixel and its argmax (d = 2*dy + dx, first maximum wins, as hm_maxpool2_fwd).  The activation is
+      // monotonic (host check), so it commutes with the max.
+      int tx, ty, tn;
+      mtile_coords(p, mt0, tx, ty, tn);
+      const int ox = tx * p.bw + ix;
+      const bool wr = !(lane & 1) && tn < p.B && ox < p.Wo;
+      const uint32_t ta0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.S * p.ntile), ta1 = ta0 + p.ntile;
+      const size_t pp = ((size_t)tn * (p.Ho >> 1) + (ty >> 1)) * (size_t)(p.Wo >> 1) + (ox >> 1);
+      __half* yo = p.y + pp * p.Cout + col0;
+      uint8_t* io = p.idx + pp * p.Cout + col0;
+      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(ta0 + c0, v0);
+        tmem_ld32(ta1 + c0, v1);
+        tmem_ld_wait();
+        uint32_t packed[16], kb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) kb[j] = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float r2[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const float a = __uint_as_float(v0[j + e]), b = __uint_as_float(v1[j + e]);
+            float m = b > a ? b : a;
+            uint32_t k = b > a ? 2u : 0u;
+            const float pm = __shfl_xor_sync(0xffffffffu, m, 1);
+            const uint32_t pk = __shfl_xor_sync(0xffffffffu, k, 1) + 1u;          // the odd lane is dx = 1
+            if (pm > m || (pm == m && pk < k)) { m = pm; k = pk; }
+            r2[e] = act_t<ACT>(m + bias_t[c0 + j + e], p.slope);
+            kb[(j + e) >> 2] |= k << (8 * ((j + e) & 3));
+          }
+          __half2 h = __floats2half2_rn(r2[0], r2[1]);
+          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (wr) {
+          uint4* d4 = reinterpret_cast<uint4*>(yo + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          uint4* i4 = reinterpret_cast<uint4*>(io + c0);
+          i4[0] = make_uint4(kb[0], kb[1], kb[2], kb[3]);
+          i4[1] = make_uint4(kb[4], kb[5], kb[6], kb[7]);
+        }
+      }
+    } else
    for (int sub = 0; sub < nv; sub++) {
     const int mt = mt0 + sub;
-    const int tx = mt % p.tiles_x;
-    const int ty = (mt / p.tiles_x) % p.tiles_y;
-    const int tn = mt / (p.tiles_x * p.tiles_y);
+    int tx, ty, tn;
+    mtile_coords(p, mt, tx, ty, tn);
     const int n = tn * p.bn + in, oy = ty * p.bh + iy, ox = tx * p.bw + ix;
     const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.S * p.ntile) + sub * p.ntile;
@@ -432,13 +497,17 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tm
 constexpr uint32_t UMMA_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | (uint64_t)lo; }
 __device__ __forceinline__ uint32_t umma_lo_of(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+// Issue order: K slice outer, sub-tile inner -- consecutive MMAs then accumulate into DIFFERENT TMEM accumulators.  Back-to-
+// back MMAs into the same accumulator serialise on the accumulate dependency; for wide N tiles an MMA is longer than that
+// latency, for the thin layers (N = 16: 36 dependent MMAs of ~160 cycles per tile measured on the generator's last layer,
+// tensor pipe 5 % busy, independent of how the operands were loaded) it was the whole run time.
 template <int NS>
 __device__ __forceinline__ void mma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t a_sub, uint32_t b_lo, uint32_t ntile,
                                         uint32_t idesc, uint32_t acc_first) {
 #pragma unroll
-  for (int i = 0; i < NS; i++) {
+  for (int k = 0; k < KCH / 16; k++) {
 #pragma unroll
-    for (int k = 0; k < KCH / 16; k++)
+    for (int i = 0; i < NS; i++)
       tc_mma_f16(d_tmem + i * ntile, umma_desc_lo(a_lo + i * a_sub + 2 * k), umma_desc_lo(b_lo + 2 * k), idesc,
                  acc_first | (uint32_t)k);
   }
@@ -460,7 +529,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_slot = ctrl + 8u * (2 * p.stages + 4);
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
-  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);     // [n_ntiles * ntile] (<= 2048) floats
+  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);     // [n_ntiles * ntile] (<= 8192) floats
   {
     const int ncols = p.n_ntiles * p.ntile;
     const int creal = p.d2s ? p.cph : p.Cout;
@@ -739,9 +808,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll 1
             for (int i = 0; i < nv; i++) {
               const int mt = st * p.S + i;                         // bh == bn == 1: a tile is a row segment
-              const int ox = (mt % p.tiles_x) * p.bw - p.pad;
-              const int oy = (mt / p.tiles_x) % p.tiles_y - p.pad + r;
-              const int on = mt / (p.tiles_x * p.tiles_y);
+              int tx_, ty_, on;
+              mtile_coords(p, mt, tx_, ty_, on);
+              const int ox = tx_ * p.bw - p.pad;
+              const int oy = ty_ - p.pad + r;
               const uint32_t dst = base + as * a_slot_bytes + i * p.rb_bytes;
               if (c < p.C1)
                 tma_load_4d(&tmA, dst, afull(as), c, ox, oy, on);
@@ -1410,6 +1480,7 @@ extern "C" int hm_tc_conv_supported(const HmConvDesc* d) {
   // both tensor maps and zero-filled by the TMA unit
   if (d->C1 <= 0 || d->C2 % KCH || (d->C1 % KCH && (d->C2 != 0 || d->C1 % 8 || d->dtype != HM_F16))) return 0;
   if (d->Cout < 1 || pick_ntile(d->Cout, d->split) == 0) return 0;
+  if (d->Cout > 8192 || (d->Cout > 2048 && d->Wo >= TILE_M)) return 0;
   if (d->Ho != d->H + 2 * d->pad - d->kh + 1 || d->Wo != d->W + 2 * d->pad - d->kw + 1) return 0;
   if (d->oH != d->Ho || d->oW != d->Wo) return 0;
   return 1;
@@ -1448,13 +1519,13 @@ extern "C" long long hm_tc_conv_ws_bytes(const HmConvDesc* d) {
   const int ntile = pick_ntile((int)(phase ? 4 * d->Cout : d->Cout), phase ? 4 * d->Cout : d->split);
   if (ntile <= 0) return 0;
   const long long tiles = (npix + TILE_M - 1) / TILE_M * ((cols + ntile - 1) / ntile);
-  const int ksplit = splitk_factor(tiles, kh * kw * ((d->C1 + d->C2) / KCH));
+  const int ksplit = splitk_factor(tiles, kh * kw * ((d->C1 + d->C2 + KCH - 1) / KCH));
   if (ksplit <= 1) return 0;
   return npix * ((cols + ntile - 1) / ntile * ntile) * 4 * ksplit;
 }
 
 static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
-                        void* y, void* y2, void* ws, size_t ws_bytes, void* stream);
+                        void* y, void* y2, void* ws, size_t ws_bytes, void* stream, uint8_t* pool_idx = nullptr);
 
 // y[B,Ho,Wo,Cout] = act( corr(x1|x2, w_tc) + bias );  w_tc is the pack [kh*kw][Cout][C1+C2] (fp16, K-major).
 extern "C" int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
@@ -1470,8 +1541,42 @@ extern "C" int hm_tc_conv_ws(const HmConvDesc* d, const void* x1, const void* x2
   return tc_conv_impl(d, x1, x2, w_tc, bias, y, y2, ws, (size_t)ws_bytes, stream);
 }
 
+// largest N tile (multiple of 32, <= 128) of a pooled layer: two accumulator sets x S = 2 sub-tiles x ntile <= 512 columns
+static int pool_ntile(int Cout) {
+  for (int n = 128; n >= 32; n -= 32)
+    if (Cout % n == 0) return n;
+  return 0;
+}
+
+// conv + bias + activation + MaxPool2DLayer(2) in one pass (reference architectures/dcgan.py:42-47 for the layers whose
+// rows are at least 128 pixels wide): plain stride-1 convolution, fp16, one output tensor, even Ho and Wo, Wo >= 128,
+// Cout a multiple of 32, a monotonic activation.
+extern "C" int hm_tc_conv_pool_supported(const HmConvDesc* d) {
+  if (!d || d->dtype != HM_F16 || !hm_tc_conv_supported(d)) return 0;
+  if (is_up2conv(d) || is_dgrad_s2(d) || is_deconv_d2s(d) || d->transposed || d->up || d->stride != 1) return 0;
+  if (d->split != d->Cout || d->accumulate || d->Cout % 32 || pool_ntile(d->Cout) == 0) return 0;
+  if (d->Ho % 2 || d->Wo % 2 || d->Wo < TILE_M || d->kw < 2 || d->kw > 9) return 0;
+  if (d->act != HM_ACT_LINEAR && d->act != HM_ACT_LRELU && d->act != HM_ACT_RELU) return 0;
+  if (d->act == HM_ACT_LRELU && d->slope < 0.f) return 0;
+  return 1;
+}
+
+extern "C" int hm_tc_conv_pool(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+                               void* y_pooled, uint8_t* idx, void* stream) {
+  HM_CHECK_ARG(d && x1 && w_tc && y_pooled && idx, "hm_tc_conv_pool: null argument");
+  if (!hm_tc_conv_pool_supported(d)) {
+    set_error("hm_tc_conv_pool: shape not supported (plain stride-1 fp16 convolution, even Ho/Wo, Wo >= 128, Cout %% 32 == 0)");
+    return HM_ERR_UNSUPPORTED;
+  }
+  if (((uintptr_t)idx) & 15) {
+    set_error("hm_tc_conv_pool: idx must be 16-byte aligned");
+    return HM_ERR_ALIGN;
+  }
+  return tc_conv_impl(d, x1, x2, w_tc, bias, y_pooled, nullptr, nullptr, 0, stream, idx);
+}
+
 static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
-                        void* y, void* y2, void* ws, size_t ws_bytes, void* stream) {
+                        void* y, void* y2, void* ws, size_t ws_bytes, void* stream, uint8_t* pool_idx) {
   HM_CHECK_ARG(d && x1 && w_tc && (y || y2), "hm_tc_conv: null argument");
   if (!hm_tc_conv_supported(d)) {
     set_error("hm_tc_conv: shape not supported by the tcgen05 path (need fp16, stride 1, C%%64==0, Cout%%16==0)");
@@ -1508,12 +1613,19 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   p.tiles_y = (p.Ho + p.bh - 1) / p.bh;
   p.tiles_n = (d->B + p.bn - 1) / p.bn;
   p.n_mtiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  p.ntile = pick_ntile(p.Cout, up2 ? p.Cout : d->split);
+  p.pool = pool_idx ? 1 : 0;
+  p.idx = pool_idx;
+  p.ntile = p.pool ? pool_ntile(p.Cout) : pick_ntile(p.Cout, up2 ? p.Cout : d->split);
   p.n_ntiles = (p.Cout + p.ntile - 1) / p.ntile;
-  if (p.n_ntiles * p.ntile > 2048) {
-    set_error("hm_tc_conv: more than 2048 GEMM columns (%d) are not supported", p.n_ntiles * p.ntile);
+  // the kernels keep the bias of every GEMM column in shared memory: 2048 columns for the row-box / pair variants, up to
+  // 8192 (a DenseLayer's width) for the plain kernel, which only small spatial extents reach
+  const int ncols_pad = p.n_ntiles * p.ntile;
+  const bool wide = ncols_pad > 2048;
+  if (ncols_pad > 8192 || (wide && p.Wo >= TILE_M)) {
+    set_error("hm_tc_conv: %d GEMM columns are not supported (2048; 8192 for rows shorter than 128 pixels)", ncols_pad);
     return HM_ERR_UNSUPPORTED;
   }
+  const int bias_bytes = wide ? 4 * ncols_pad : 8192;
   p.vec_store = (p.Cout % 16 == 0 && d->split % 16 == 0) ? 1 : 0;
   int S = 256 / p.ntile;                                   // 2 (double buffer) * S * ntile <= 512 TMEM columns
   if (S < 1) S = 1;
@@ -1528,10 +1640,11 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
     if (S > smax) S = smax;
   }
   while (S > 1 && ((p.n_mtiles + S - 1) / S) * p.n_ntiles < num_sms()) S >>= 1;   // keep every SM busy on small layers
+  if (p.pool) S = 2;                                       // the two image rows of a pooling window
   p.S = S;
   p.n_super = (p.n_mtiles + S - 1) / S;
   const int stage_bytes = S * A_BYTES + p.ntile * 128;
-  int stages = (227 * 1024 - 10240) / stage_bytes;
+  int stages = (227 * 1024 - 2048 - bias_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.act = d->act; p.slope = d->slope; p.bias = bias; p.y = (__half*)y; p.y2 = (__half*)y2;
@@ -1561,7 +1674,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
     const char* e = getenv("HMGAN_TC_PAIR");
     pair_enabled = (e && e[0] == '1') ? 1 : 0;
   }
-  if (rb_enabled && pair_enabled && !p.bf16 && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9 &&
+  if (rb_enabled && pair_enabled && !p.bf16 && !p.pool && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9 &&
       p.ntile >= 64 && p.ntile % 32 == 0 && (num_sms() % 2) == 0) {
     TcParams q = p;
     int S2 = 256 / q.ntile;
@@ -1611,7 +1724,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
       }
     }
   }
-  if (rb_enabled && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
+  if ((rb_enabled || p.pool) && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
     p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;
     p.a_slots = (S * p.rb_bytes > 40 * 1024) ? 2 : 3;
     {
@@ -1662,6 +1775,10 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
       return HM_OK;
     }
   }
+  if (p.pool) {
+    set_error("hm_tc_conv_pool: the row-box kernel did not take this shape");
+    return HM_ERR_UNSUPPORTED;
+  }
   if (ws && splitk_enabled() && !p.bf16) {
     const int ksteps = p.kh * p.kw * (p.Cin / KCH);
     const int ksplit = splitk_factor((long long)p.n_mtiles * p.n_ntiles, ksteps);
@@ -1703,7 +1820,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
       return HM_OK;
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 1024 + 8192 /*control block + bias (<= 2048 columns)*/;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + 1024 + bias_bytes /*control block + bias*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -401,6 +401,7 @@ class ConvOp(object):
         # hm_c1s2_conv (in-kernel im2col of a one-channel image): (a) this layer + its 2x2 max-pool in one pass, set by
         # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
         self.pool_fused = None
+        self.pool_tc = None           # PoolOp whose 2x2 max-pool runs in this convolution's tensor-core epilogue
         self.db_done = False
         self.bias_grad_zero = False
         self.wk = None
@@ -678,6 +679,11 @@ class ConvOp(object):
                         self.kw, self.stride, self.pad, self.out.shape[0], self.out.shape[1])
             d = self._col1_desc(rt, n)
             rt.call("hm_tc_conv", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(self.wt_f), bias, y, None)
+        elif self.pool_tc is not None:
+            # conv + bias + activation + 2x2 max-pool in the tcgen05 epilogue: the un-pooled activation is never written
+            pool = self.pool_tc
+            rt.call("hm_tc_conv_pool", C.byref(self._tc_fwd_desc(rt, n)), x1, x2, _ptr(self.wt_f), bias,
+                    _ptr(pool.out.b(lo, hi)), _ptr(pool.idx[lo:hi]))
         elif self.up2:
             self._xu_valid = False
             d = self._fwd_desc(rt, n)
@@ -962,7 +968,8 @@ class PoolOp(object):
     def __init__(self, net, x, out, act):
         self.net, self.x, self.out, self.act = net, x, out, act
         self.idx = None
-        self.fused = False
+        self.fused = False        # forward AND backward inside the producing convolution (hm_c1s2_*)
+        self.fused_tc = False     # forward inside the producing convolution's epilogue (hm_tc_conv_pool)
         self.prod = None          # the ConvOp that wrote x (set by Net)
 
     def alloc(self, rt, B):
@@ -973,7 +980,7 @@ class PoolOp(object):
         pass
 
     def fwd(self, rt, lo, hi, det):
-        if self.fused:            # written by the producing convolution (hm_c1s2_conv)
+        if self.fused or self.fused_tc:            # written by the producing convolution
             return
         H, W, Cn = self.x.shape
         rt.call("hm_maxpool2_fwd", _ptr(self.x.b(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]),
@@ -1202,6 +1209,12 @@ class Net(object):
                     and x.shape[1] % 2 == 0):
                 cv.pool_fused, pop.fused = pop, True
                 x.fused_away = True          # the un-pooled activation and its gradient are never materialised
+            elif (cv is not None and self.rt.precision == "fast" and cv.kind == "conv" and cv.tc_fwd and not cv.up
+                  and not cv.col1 and not cv.colk and cv.stride == 1 and x.consumers == 1
+                  and os.environ.get("HMGAN_POOL_TC", "1") != "0"
+                  and bool(_lib.query("hm_tc_conv_pool_supported", C.byref(cv._tc_fwd_desc(self.rt, 1))))):
+                cv.pool_tc, pop.fused_tc = pop, True
+                x.no_buf = True              # only the GRADIENT of the un-pooled activation exists (hm_maxpool2_bwd writes it)
             return out
         if isinstance(layer, (L.Conv2DLayer, L.TransposedConv2DLayer, L.DenseLayer)):
             src = self._lower(layer.input_layer, None)
@@ -1268,7 +1281,7 @@ class Net(object):
                 if v.kind == "buf" and getattr(v, "fused_away", False):
                     continue
                 if v.kind == "buf":
-                    v.buf = rt.empty((B,) + v.shape)
+                    v.buf = None if getattr(v, "no_buf", False) else rt.empty((B,) + v.shape)
                     v.grad = rt.empty((B,) + v.shape)
                     if self.single_pass and any(isinstance(o, ConvOp) and o.out is v for o in self.ops):
                         v.grad_w = rt.empty((B,) + v.shape)

@@ -124,6 +124,13 @@ int hm_conv_wgrad(const HmConvDesc* d, const void* x1, const void* x2, const voi
 int hm_tc_conv_supported(const HmConvDesc* d);
 int hm_tc_conv(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
                void* y, void* y2, void* stream);
+/* Convolution + bias + activation + MaxPool2DLayer(2) in ONE pass (dcgan.py:42-47): y_pooled[B,Ho/2,Wo/2,Cout] and
+ * idx[B,Ho/2,Wo/2,Cout] (argmax 0..3, first maximum wins: the layout of hm_maxpool2_fwd); the un-pooled activation is
+ * never written.  Plain stride-1 fp16 convolutions with rows of at least 128 pixels, even Ho / Wo, Cout % 32 == 0 and a
+ * monotonic activation (hm_tc_conv_pool_supported); the maximum is taken over the fp32 values before rounding. */
+int hm_tc_conv_pool_supported(const HmConvDesc* d);
+int hm_tc_conv_pool(const HmConvDesc* d, const void* x1, const void* x2, const void* w_tc, const float* bias,
+                    void* y_pooled, uint8_t* idx, void* stream);
 /* hm_tc_conv with a caller-provided scratch workspace of ws_bytes >= hm_tc_conv_ws_bytes(d) bytes (no initialisation
  * needed, contents undefined afterwards; one buffer serves every call issued on a stream).  With it, layers whose
  * tiles fill less than half of the SMs split K over the idle ones: every K slice stores its partial sums to its own

@@ -694,6 +694,22 @@ def _tc_ok(d, wgrad):
     return ok and 0 < d.split <= d.Cout and bool(ntile)
 
 
+def _pool_ok(d):
+    ok = d.dtype == F16 and _tc_ok(d, False) and not d.transposed and not d.up and d.stride == 1
+    ok = ok and d.split == d.Cout and not d.accumulate and d.Cout % 32 == 0
+    ok = ok and d.Ho % 2 == 0 and d.Wo % 2 == 0 and d.Wo >= 128 and 2 <= d.kw <= 9 and d.act in (0, 1, 2)
+    return bool(ok)
+
+
+def hm_tc_conv_pool(dp, x1, x2, w_tc, bias, y_pooled, idx, stream=None):
+    """Contract: hm_tc_conv followed by hm_maxpool2_fwd, the un-pooled tensor never leaving the kernel."""
+    d = dp._obj if hasattr(dp, "_obj") else dp
+    assert _pool_ok(d)
+    full = np.zeros(d.B * d.Ho * d.Wo * d.Cout, np.float16)
+    hm_tc_conv(d, x1, x2, w_tc, bias, full.ctypes.data, None)
+    return hm_maxpool2_fwd(full.ctypes.data, y_pooled, idx, F16, d.B, d.Ho, d.Wo, d.Cout)
+
+
 def hm_tc_conv_ws(dp, x1, x2, w_tc, bias, y, y2, ws, ws_bytes, stream=None):
     """hm_tc_conv with a workspace the emulation has no use for (it must stay zero)."""
     return hm_tc_conv(dp, x1, x2, w_tc, bias, y, y2, stream)
@@ -898,6 +914,8 @@ def query(name, dp):
     d = dp._obj if hasattr(dp, "_obj") else dp
     if name == "hm_tc_conv_ws_bytes":
         return 0                       # the emulation never splits K
+    if name == "hm_tc_conv_pool_supported":
+        return int(_pool_ok(d))
     return int(_tc_ok(d, name == "hm_tc_wgrad_supported"))
 
 

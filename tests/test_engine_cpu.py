@@ -439,3 +439,41 @@ def test_num_repeats_adds_convolutions_per_level(cpu_backend):
     Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=6)
     np.testing.assert_allclose(m.train_fn(Z, X, Y)[:2], om.train_fn(Z, X, Y)[:2], rtol=1e-4, atol=1e-6)
     _check_grads(om, m, ('G', 'D'), 1e-3, {'G': 1e-2})
+
+
+def test_fast_mode_pool_in_the_conv_epilogue(cpu_backend):
+    """Conv2DLayer + LeakyReLU + MaxPool2DLayer(2) with rows of >= 128 pixels (the DCGAN discriminator's layers 2 and 3 at
+    512x512, reference architectures/dcgan.py:42-47) lower to hm_tc_conv_pool: the un-pooled activation has no buffer,
+    forward and every gradient agree with the float32 oracle ops (fp16 storage: 2e-2 relative L2)."""
+    import lasagne_compat as LC
+    import engine
+    from oracle import lasagne_ops as LO
+    r = np.random.RandomState(5)
+    inp = LC.InputLayer((None, 64, 4, 128))
+    c1 = LC.Conv2DLayer(inp, 64, 3, pad='same', nonlinearity=LC.LeakyRectify(0.2))
+    p1 = LC.MaxPool2DLayer(c1, 2)
+    c2 = LC.Conv2DLayer(p1, 64, 3, pad='same', nonlinearity=LC.linear)
+    rt = engine.Runtime("cpu", "fast", loss_scale=1.0)
+    net = engine.Net(rt, c2, name="pool", rng=r)
+    convs = [op for op in net.ops if isinstance(op, engine.ConvOp)]
+    pools = [op for op in net.ops if isinstance(op, engine.PoolOp)]
+    assert convs[0].pool_tc is pools[0] and pools[0].fused_tc and convs[1].pool_tc is None
+    x = r.randn(2, 64, 4, 128).astype(np.float32)
+    net.ensure(2, input_grads=(0,))
+    assert convs[0].out.buf is None and convs[0].out.grad is not None
+    net.inputs[0].buf.copy_(torch.from_numpy(x.transpose(0, 2, 3, 1)).half())
+    y = net.forward(2)
+    W1, b1, W2, b2 = [torch.tensor(v, requires_grad=True) for v in net.get_all_param_values()]
+    xt = torch.tensor(x, requires_grad=True)
+    ref = LO.conv2d(LO.max_pool(LO.leaky_rectify(LO.conv2d(xt, W1, b1, 1, "same"), 0.2)), W2, b2, 1, "same")
+
+    def rel(a, b):
+        return np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / (np.linalg.norm(np.asarray(b).ravel()) + 1e-30)
+    assert rel(y.float().numpy(), ref.detach().permute(0, 2, 3, 1).numpy()) <= 2e-2
+    gy = r.randn(*ref.shape).astype(np.float32)
+    ref.backward(torch.tensor(gy))
+    net.out.grad.copy_(torch.from_numpy(gy.transpose(0, 2, 3, 1)).half())
+    net.backward(0, 2, wgrad=True, input_grad=True)
+    for a, b in zip(net.get_grads(), (W1.grad, b1.grad, W2.grad, b2.grad)):
+        assert rel(a, b.numpy()) <= 2e-2, (a.shape, rel(a, b.numpy()))
+    assert rel(net.inputs[0].grad[:2].float().numpy(), xt.grad.permute(0, 2, 3, 1).numpy()) <= 2e-2

@@ -109,3 +109,12 @@ def test_tc_up2conv_backward_on_the_low_res_grid(case, tc32):
     hm_upsample2_bwd sums it), 1e-4 in tc32 mode (measured <= 5.5e-5: two float32 summation orders of up to 9216 terms)."""
     rel, line = tc_probe.run_up2_bwd_case(*case, tc32=tc32)
     assert rel <= (1e-4 if tc32 else 3e-3), line
+
+
+@pytest.mark.parametrize("case", tc_probe.POOL_CASES, ids=[c[0] for c in tc_probe.POOL_CASES])
+def test_tc_conv_with_fused_maxpool(case):
+    """hm_tc_conv_pool (the discriminator's conv + LeakyReLU + 2x2 max-pool, reference architectures/dcgan.py:42-47, in the
+    tensor-core epilogue) against hm_tc_conv + hm_maxpool2_fwd: identical pooled values, and an argmax whose un-pooled value
+    IS the pooled value (ragged widths, two-source, Cout = 64 .. 256 in 128-column tiles)."""
+    bad, line = tc_probe.run_pool_case(*case)
+    assert bad == 0.0, line

@@ -459,6 +459,55 @@ def run_up2_bwd_case(name, B, H, W, Ci, Co, act, tc32=False):
     return max(r1, r2), l1 + "\n" + l2
 
 
+POOL_CASES = [
+    # name, B, H, W, C1, C2, Cout, k, pad, act
+    ("pool_5x5_64_128_w256", 2, 8, 256, 64, 0, 128, 5, 2, 1),
+    ("pool_5x5_128_128_w128", 3, 6, 128, 128, 0, 128, 5, 2, 1),
+    ("pool_3x3_64_64_w384", 1, 4, 384, 64, 0, 64, 3, 1, 2),
+    ("pool_5x5_64_256_w128", 1, 4, 128, 64, 0, 256, 5, 2, 0),
+    ("pool_3x3_cat64+64_96_w130", 2, 2, 130, 64, 64, 96, 3, 1, 1),
+]
+
+
+def run_pool_case(name, B, H, W, C1, C2, Cout, k, pad, act):
+    """hm_tc_conv_pool (conv + bias + activation + 2x2 max-pool in the tensor-core epilogue) against hm_tc_conv followed by
+    hm_maxpool2_fwd on the same data.  The pooled VALUES must be identical (rounding to fp16 is monotonic, so the max of
+    the rounded values is the rounded max); the argmax may differ only where two candidates round to the same fp16 value
+    (the fused kernel compares the fp32 values), so it is checked by value: the un-pooled tensor at the reported position
+    equals the pooled value."""
+    torch.manual_seed(abs(hash(name)) % 1000 + 23)
+    Ct = C1 + C2
+    x1 = torch.randn(B, H, W, C1, device="cuda").half()
+    x2 = torch.randn(B, H, W, C2, device="cuda").half() if C2 else None
+    p2 = x2.data_ptr() if C2 else None
+    Wm = torch.randn(Cout, Ct, k, k, device="cuda") / np.sqrt(k * k * Ct)
+    bias = torch.randn(Cout, device="cuda")
+    wt = torch.empty(k * k * Ct * Cout, device="cuda", dtype=torch.float16)
+    _lib.call("hm_pack_conv_weight", Wm.data_ptr(), wt.data_ptr(), 5, Cout, Ct, k, k, 0, 0, 1, None)
+    d = desc(dtype=1, B=B, H=H, W=W, C1=C1, C2=C2, up=0, kh=k, kw=k, stride=1, pad=pad, transposed=0, Ho=H, Wo=W,
+             Cout=Cout, oH=H, oW=W, os=1, ou=0, ov=0, split=Cout, act=act, slope=0.2, accumulate=0)
+    assert _lib.query("hm_tc_conv_pool_supported", C.byref(d)) == 1, name
+    full = torch.zeros(B, H, W, Cout, device="cuda", dtype=torch.float16)
+    _lib.call("hm_tc_conv", C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), full.data_ptr(), None, None)
+    ref = torch.zeros(B, H // 2, W // 2, Cout, device="cuda", dtype=torch.float16)
+    ref_i = torch.zeros(B, H // 2, W // 2, Cout, device="cuda", dtype=torch.uint8)
+    _lib.call("hm_maxpool2_fwd", full.data_ptr(), ref.data_ptr(), ref_i.data_ptr(), 1, B, H, W, Cout, None)
+    out = torch.full((B, H // 2, W // 2, Cout), 7.0, device="cuda", dtype=torch.float16)
+    out_i = torch.full((B, H // 2, W // 2, Cout), 9, device="cuda", dtype=torch.uint8)
+    _lib.call("hm_tc_conv_pool", C.byref(d), x1.data_ptr(), p2, wt.data_ptr(), bias.data_ptr(), out.data_ptr(),
+              out_i.data_ptr(), None)
+    torch.cuda.synchronize()
+    dv = float((out.float() - ref.float()).abs().max())
+    win = full.view(B, H // 2, 2, W // 2, 2, Cout).permute(0, 1, 3, 5, 2, 4).reshape(B, H // 2, W // 2, Cout, 4)
+    ok_range = bool((out_i <= 3).all())
+    picked = torch.gather(win, 4, out_i.clamp(max=3).long().unsqueeze(-1)).squeeze(-1)
+    di = float((picked.float() - out.float()).abs().max())
+    same_idx = float((out_i == ref_i).float().mean())
+    bad = 0.0 if (dv == 0.0 and di == 0.0 and ok_range) else 1.0
+    return bad, "pool %-28s value diff %.3g  value-at-argmax diff %.3g  argmax in range %s  same argmax %.4f" % (
+        name, dv, di, ok_range, same_idx)
+
+
 DC2_CASES = [
     # name, B, H, W (input grid), C1, C2, Cout, act
     ("dc2_128_3_w256_tanh", 1, 256, 256, 64, 64, 3, 4),
@@ -789,6 +838,13 @@ if __name__ == "__main__":
                 print("c1bwd %-22s EXC %s" % (c[0], e), flush=True)
                 break
         perf_c1bwd()
+        sys.exit(0)
+    if sys.argv[1:] == ["pool"]:
+        for c in POOL_CASES:
+            try:
+                print(run_pool_case(*c)[1], flush=True)
+            except Exception as e:
+                print("pool %-28s EXC %s" % (c[0], e), flush=True)
         sys.exit(0)
     if sys.argv[1:] == ["up2bwd"]:
         for c in UP2_BWD_CASES:
