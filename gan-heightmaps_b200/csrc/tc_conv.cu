@@ -497,17 +497,15 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tm
 constexpr uint32_t UMMA_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)UMMA_DESC_HI << 32) | (uint64_t)lo; }
 __device__ __forceinline__ uint32_t umma_lo_of(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
-// Issue order: K slice outer, sub-tile inner -- consecutive MMAs then accumulate into DIFFERENT TMEM accumulators.  Back-to-
-// back MMAs into the same accumulator serialise on the accumulate dependency; for wide N tiles an MMA is longer than that
-// latency, for the thin layers (N = 16: 36 dependent MMAs of ~160 cycles per tile measured on the generator's last layer,
-// tensor pipe 5 % busy, independent of how the operands were loaded) it was the whole run time.
+// (Issue order: sub-tile outer, K slice inner.  Interleaving the sub-tiles' accumulators -- K slice outer -- changed nothing,
+// neither on the wide layers nor on the thin N = 16 one: measured in round 2.)
 template <int NS>
 __device__ __forceinline__ void mma_tap(uint32_t d_tmem, uint32_t a_lo, uint32_t a_sub, uint32_t b_lo, uint32_t ntile,
                                         uint32_t idesc, uint32_t acc_first) {
 #pragma unroll
-  for (int k = 0; k < KCH / 16; k++) {
+  for (int i = 0; i < NS; i++) {
 #pragma unroll
-    for (int i = 0; i < NS; i++)
+    for (int k = 0; k < KCH / 16; k++)
       tc_mma_f16(d_tmem + i * ntile, umma_desc_lo(a_lo + i * a_sub + 2 * k), umma_desc_lo(b_lo + 2 * k), idesc,
                  acc_first | (uint32_t)k);
   }

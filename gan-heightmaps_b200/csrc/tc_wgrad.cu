@@ -440,13 +440,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const uint32_t b_lo = (((base + bs * b_bytes) & 0x3FFFF) >> 4) | ((uint32_t)(BLK_BYTES >> 4) << 16);
         const uint32_t a_lo = ((a_base + as * a_bytes) & 0x3FFFF) >> 4;
         const uint32_t accum0 = pt > pt0 ? 1u : 0u;
-        // K slice outer, accumulator inner: consecutive MMAs go to different TMEM accumulators (see mma_tap in tc_conv.cu)
+        // (accumulator outer, K slice inner.  The other order -- consecutive MMAs into different accumulators -- measured
+        // 16-19 % SLOWER on the 256^2 / 128^2 layers, round 2.)
 #pragma unroll
-        for (int kk = 0; kk < 8; kk++) {                               // 16 pixels (two 8-row swizzle atoms) per MMA
+        for (int i = 0; i < 8; i++) {
+          if (i < nmt) {
+            const uint32_t d_tmem = tmem_base + i * p.Cout;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            if (i < nmt)
-              wg_mma(tmem_base + i * p.Cout, ((uint64_t)HI << 32) | (uint64_t)(a_lo + rel[i] + kk * 128),
+            for (int kk = 0; kk < 8; kk++)                             // 16 pixels (two 8-row swizzle atoms) per MMA
+              wg_mma(d_tmem, ((uint64_t)HI << 32) | (uint64_t)(a_lo + rel[i] + kk * 128),
                      ((uint64_t)HI << 32) | (uint64_t)(b_lo + kk * 128), idesc, accum0 | (uint32_t)kk);
           }
         }
