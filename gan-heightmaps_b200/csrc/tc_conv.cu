@@ -242,6 +242,34 @@ __device__ __forceinline__ void epi_store32_f32(float* dst, const uint32_t* v, c
   }
 }
 
+// depth-to-space store of a thin phase-decomposed layer: columns (phase, co), co < CPH <= 4; phase (py, px) of low-res
+// pixel (oy, ox) goes to output pixel (2oy+py, 2ox+px).  row0 = pixel index of (2oy, 2ox) in the [B, 2Ho, 2Wo] grid.
+template <int ACT, int CPH>
+__device__ __forceinline__ void d2s_thin_store(const TcParams& p, const uint32_t* v, const float* bias_t, size_t row0) {
+#pragma unroll
+  for (int py = 0; py < 2; py++) {
+    __half* dst = p.y + (row0 + (size_t)py * (2 * p.Wo)) * CPH;       // pixels (2oy+py, 2ox) and (2oy+py, 2ox+1): 2*CPH halves
+    float a[2 * CPH];
+#pragma unroll
+    for (int px = 0; px < 2; px++)
+#pragma unroll
+      for (int co = 0; co < CPH; co++) {
+        const int col = (py * 2 + px) * CPH + co;
+        a[px * CPH + co] = __uint_as_float(v[col]) + bias_t[col];
+        if (p.accumulate & 1) a[px * CPH + co] += __half2float(dst[px * CPH + co]);
+        a[px * CPH + co] = act_t<ACT>(a[px * CPH + co], p.slope);
+      }
+    if (CPH % 2 == 0 || CPH == 1) {            // 4-byte aligned pairs (2ox is even): half2 stores
+#pragma unroll
+      for (int e = 0; e < 2 * CPH; e += 2)
+        *reinterpret_cast<__half2*>(dst + e) = __floats2half2_rn(a[e], a[e + 1]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2 * CPH; e++) dst[e] = __float2half_rn(a[e]);
+    }
+  }
+}
+
 // The whole epilogue role: for every tile of this CTA wait for the accumulator, drain it, release it.
 // pair_rank < 0: single-CTA kernels (work items blockIdx.x, +gridDim.x, ...; tempty0 is a local barrier).
 // pair_rank = 0/1: CTA pair (cta_group::2): work items are shared by the pair, this CTA owns sub-tiles
@@ -382,6 +410,18 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
 #pragma unroll
           for (int j = 0; j < 4; j++)
             d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        } else if (p.cph <= 4 && gc == 0) {
+          // thin layers (1..4 channels per phase: the generator's last layer, the U-Net's output deconvolution): the
+          // 4*cph real columns with compile-time phase / channel indices.  (The generic loop below -- 32 predicated
+          // iterations with a runtime division each -- WAS the run time of the generator's last layer: 0.35 ms for a
+          // 268 MB read, tensor pipe 5 % busy, stall samples spread over its 32 reconvergence points; round-2 profile.)
+          const size_t row0 = ((size_t)n * 2 * p.Ho + 2 * oy) * (size_t)(2 * p.Wo) + 2 * ox;
+          switch (p.cph) {
+            case 1: d2s_thin_store<ACT, 1>(p, v, bias_t, row0); break;
+            case 2: d2s_thin_store<ACT, 2>(p, v, bias_t, row0); break;
+            case 3: d2s_thin_store<ACT, 3>(p, v, bias_t, row0); break;
+            default: d2s_thin_store<ACT, 4>(p, v, bias_t, row0); break;
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j++) {

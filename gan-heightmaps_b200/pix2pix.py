@@ -141,6 +141,8 @@ class Pix2Pix(object):
         self._graphs_ok = rt.device.type == "cuda" and os.environ.get("HMGAN_CUDA_GRAPHS", "1") != "0"
         self.train_fn = lambda Z, X, Y: self._step_host(Z, X, Y, True)
         self.loss_fn = lambda Z, X, Y: self._step_host(Z, X, Y, False)
+        self.train_fn_async = lambda Z, X, Y: self._step_host_async(Z, X, Y, True)      # device tensors, no host sync
+        self.loss_fn_async = lambda Z, X, Y: self._step_host_async(Z, X, Y, False)
         self.gen_fn = lambda X: self._gen_p2p(X, False)
         self.gen_fn_det = lambda X: self._gen_p2p(X, True)
         self.z_fn = lambda Z: self._gen_dcgan(Z, False)
@@ -492,9 +494,11 @@ class Pix2Pix(object):
         self._sync_lr()
         self._ensure_packed()
         main = torch.cuda.current_stream(dev)
+        if st.get("done") is not None:              # X / Y of the previous step are free once its second graph has finished
+            st["side"].wait_event(st["done"])       # (a no-op after a host synchronisation; needed by *_fn_async)
         st["Z"].copy_(Zs, non_blocking=True)
         st["gA"].replay()
-        with torch.cuda.stream(st["side"]):        # the previous step ended with a host synchronisation: X/Y are free
+        with torch.cuda.stream(st["side"]):
             st["X"].copy_(Xs, non_blocking=True)
             if st["gC"] is not None:
                 st["gC"].replay()                   # D(x) as soon as X has landed, beside G's forward pass
@@ -503,6 +507,9 @@ class Pix2Pix(object):
             st["ev"].record(st["side"])
         main.wait_event(st["ev"])
         st["gB"].replay()
+        if st.get("done") is None:
+            st["done"] = torch.cuda.Event()
+        st["done"].record(main)
         self.rt.launches += st["launches"]
         return self.losses
 
@@ -516,6 +523,20 @@ class Pix2Pix(object):
         Yd = self._to_dev("Y", Y) if self.have_p2p else None      # a DCGAN-only model never reads the texture batch
         losses = self.step_device(Zd, Xd, Yd, train).cpu().numpy()
         return [np.float32(v) for v in losses]
+
+    def _step_host_async(self, Z, X, Y, train):
+        """train_fn / loss_fn without the per-step host synchronisation: the step is enqueued and a DEVICE copy of the five
+        losses is returned (read it with .cpu() whenever convenient; the next call may be issued at once).  What the
+        reference's loop does after every batch -- np.mean over the epoch's losses (pix2pix.py:201-212) -- only needs
+        the values at the end of the epoch: Pix2Pix.train(loss_sync_every=N) uses this."""
+        if self._graphs_ok and os.environ.get("HMGAN_OVERLAP_H2D", "1") != "0":
+            out = self._step_host_overlapped(Z, X, Y, train)
+            if out is not None:
+                return out.clone()
+        Zd = self._to_dev("Z", Z)
+        Xd = self._to_dev("X", X)
+        Yd = self._to_dev("Y", Y) if self.have_p2p else None
+        return self.step_device(Zd, Xd, Yd, train).clone()
 
     def _gen_dcgan(self, Z, det):
         if not self.have_dcgan:
@@ -576,17 +597,37 @@ class Pix2Pix(object):
     # training loop (reference pix2pix.py:187-275)
     # ------------------------------------------------------------------ #
     def train(self, it_train, it_val, batch_size, num_epochs, out_dir, model_dir=None, save_every=10,
-              resume=False, quick_run=False):
+              resume=False, quick_run=False, loss_sync_every=None):
+        """loss_sync_every (not in the reference; default 1 or $HMGAN_LOSS_SYNC_EVERY): read the losses back every N steps
+        instead of after every step -- the epoch means are the same numbers, the host just stops waiting for each step."""
+        if loss_sync_every is None:
+            loss_sync_every = int(os.environ.get("HMGAN_LOSS_SYNC_EVERY", "1"))
+
         def _loop(fn, itr):
             rec = [[] for _ in range(len(self.train_keys))]
+            pend = []
+            fn_async = {self.train_fn: self.train_fn_async, self.loss_fn: self.loss_fn_async}.get(fn)
+
+            def flush():
+                if pend:
+                    for row in torch.stack(pend).cpu().numpy():
+                        for i in range(len(self.train_keys)):
+                            rec[i].append(np.float32(row[i]))
+                    del pend[:]
             for b in range(itr.N // batch_size):
                 X_batch, Y_batch = it_train.next()      # sic: the reference reads it_train here too (:204)
                 Z_batch = floatX(self.sampler(X_batch.shape[0], self.latent_dim))
-                results = fn(Z_batch, X_batch, Y_batch)
-                for i in range(len(results)):
-                    rec[i].append(results[i])
+                if loss_sync_every > 1 and fn_async is not None:
+                    pend.append(fn_async(Z_batch, X_batch, Y_batch))
+                    if len(pend) >= loss_sync_every:
+                        flush()
+                else:
+                    results = fn(Z_batch, X_batch, Y_batch)
+                    for i in range(len(results)):
+                        rec[i].append(results[i])
                 if quick_run:
                     break
+            flush()
             return tuple([np.mean(elem) for elem in rec])
         header = ["epoch"] + ["train_%s" % k for k in self.train_keys] + ["valid_%s" % k for k in self.train_keys]
         header += ["lr", "time", "mode"]

@@ -63,9 +63,14 @@ def iterate_hdf5(imgen=None, is_a_grayscale=True, is_b_grayscale=False, is_uint8
                     out.append(np.ascontiguousarray(a))
                 yield out[0], out[1]
 
+    # Raw-byte batches are exact only under augmenters that MOVE pixels (flips, order-0 rotation: the built-in ones, marked
+    # `pixel_moving`).  Any other `imgen` (e.g. a Keras ImageDataGenerator with interpolation, as the reference passes)
+    # works on the normalised floats exactly as in the reference: the host float path below.
+    raw = device_normalise and (imgen is None or getattr(imgen, "pixel_moving", False))
+
     def _iterate_hdf5(X_arr, y_arr, bs, rnd_state=np.random.RandomState(0)):
         assert X_arr.shape[0] == y_arr.shape[0]
-        if device_normalise:
+        if raw:
             if not is_uint8:
                 raise ValueError("device_normalise=True is for uint8 data (is_uint8=True)")
             for batch in _iterate_raw(X_arr, y_arr, bs, rnd_state):      # endless
@@ -116,6 +121,7 @@ class Hdf5Iterator(object):
 
 
 class FlipAugmenter(object):
+    pixel_moving = True          # exact on raw uint8 data (util.iterate_hdf5, device_normalise)
     """Keras-free stand-in for ImageDataGenerator(horizontal_flip=, vertical_flip=) (reference experiments.py:13):
     ``flow(x, None, batch_size=, seed=)`` yields x with every sample flipped or not by a RandomState(seed), so X and Y
     passed with the same seed get the same flips."""
@@ -136,6 +142,7 @@ class FlipAugmenter(object):
 
 
 class RotateFlipAugmenter(object):
+    pixel_moving = True          # order-0 resampling: exact on raw uint8 data (util.iterate_hdf5, device_normalise)
     """Keras-free restatement of what the reference builds for training (experiments.py:13):
     ``ImageDataGenerator(horizontal_flip=True, vertical_flip=True, rotation_range=360, fill_mode="reflect")`` used through
     ``flow(x, None, batch_size=bs, seed=seed).next()`` on an NCHW batch (util.py:38-40).

@@ -389,3 +389,20 @@ def test_replayed_graphs_see_updated_weights_and_survive_reallocation(monkeypatc
     # fp16 fast mode, atomically reduced weight gradients: the two schedules agree to run-to-run noise
     np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=5e-3, atol=1e-5)
     np.testing.assert_allclose(res["1"][1], res["0"][1], atol=3e-2)      # G(z) in (0,1) after five updates at lr 1e-3
+
+
+def test_async_loss_readback_equals_per_step_readback():
+    """train_fn_async / loss_fn_async (no host synchronisation per step; Pix2Pix.train(loss_sync_every=N)) against
+    train_fn / loss_fn from identical states: eager, captured and replayed steps, losses read back only at the end."""
+    cfg = S.experiment_kwargs('gate64')
+    _, m0 = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast", lr=1e-4)
+    _, m1 = build_pair(cfg, 'dcgan', with_p2p=False, device="cuda", precision="fast", lr=1e-4)
+    sync, pend = [], []
+    for it in range(6):
+        Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 64, seed=60 + it)
+        fn0, fn1 = (m0.train_fn, m1.train_fn_async) if it % 3 != 2 else (m0.loss_fn, m1.loss_fn_async)
+        sync.append(fn0(Z, X, Y))
+        pend.append(fn1(Z, X, Y))
+        assert isinstance(pend[-1], torch.Tensor) and pend[-1].is_cuda
+    got = torch.stack(pend).cpu().numpy()
+    np.testing.assert_allclose(got[:, :2], np.array(sync)[:, :2], rtol=2e-3, atol=1e-5)

@@ -117,3 +117,26 @@ def test_sampling_entry_points(cpu_backend, tmp_path):
     b = m.z_fn(Z)
     assert a.shape == b.shape == (2, 1, 512, 512)
     assert any(np.abs(x - y).max() > 0 for x, y in zip(stats, m.G.get_all_param_values()))
+
+
+def test_loss_sync_every_n_steps_gives_the_same_epoch_row(cpu_backend, tmp_path):
+    """Pix2Pix.train(loss_sync_every=N) (the loop only needs the epoch means) reads the losses back in
+    groups through train_fn_async / loss_fn_async: the results.txt row equals the per-step read-back's; a model without
+    the pix2pix stage (gen_fn_p2p=None) saves a checkpoint that loads again with the default mode."""
+    cfg = S.experiment_kwargs('gate64')
+    rows = []
+    for n in (1, 3):
+        _, m = build_pair(cfg, 'dcgan', with_p2p=False)
+        np.random.seed(3)
+        out_dir = str(tmp_path / ("out%d" % n))
+        m.train(util.SyntheticIterator(4, 1, 64, seed=0), util.SyntheticIterator(4, 1, 64, seed=50), batch_size=1,
+                num_epochs=1, out_dir=out_dir, model_dir=str(tmp_path / ("m%d" % n)), save_every=1, loss_sync_every=n)
+        rows.append([float(v) for v in open(os.path.join(out_dir, "results.txt")).read().strip().splitlines()[1]
+                     .split(",")[1:11]])
+    np.testing.assert_allclose(rows[1], rows[0], rtol=1e-6, atol=0)
+    m.load_model(str(tmp_path / "m3" / "1.model"))             # DCGAN-only model: the p2p lists of the file are empty
+    with pytest.raises(ValueError):
+        _, both = build_pair(S.experiment_kwargs('tiny512'), 'both')
+        m.save_model(str(tmp_path / "dc.model"))
+        both.save_model(str(tmp_path / "both.model"))
+        m.load_model(str(tmp_path / "both.model"))              # holds p2p parameters this model has no network for
