@@ -994,15 +994,18 @@ __global__ void __launch_bounds__(256)
       o2[j] = k == 2 ? gg : 0.f;
       o3[j] = k == 3 ? gg : 0.f;
     }
-    T* base = dx + (((size_t)b * H + 2 * py) * W + 2 * px) * C + g * 8;
-    store8(base, o0);
-    store8(base + C, o1);
-    store8(base + (size_t)W * C, o2);
-    store8(base + (size_t)W * C + C, o3);
+    const size_t off = (((size_t)b * H + 2 * py) * W + 2 * px) * C + g * 8;
+    if (dx) {                                   // (null: only the weighted copy / the bias gradient are wanted)
+      T* base = dx + off;
+      store8(base, o0);
+      store8(base + C, o1);
+      store8(base + (size_t)W * C, o2);
+      store8(base + (size_t)W * C + C, o3);
+    }
     if (dxs) {
 #pragma unroll
       for (int j = 0; j < 8; j++) { o0[j] *= sc; o1[j] *= sc; o2[j] *= sc; o3[j] *= sc; }
-      T* bs2 = dxs + (base - dx);
+      T* bs2 = dxs + off;
       store8(bs2, o0);
       store8(bs2 + C, o1);
       store8(bs2 + (size_t)W * C, o2);
@@ -1735,9 +1738,9 @@ extern "C" int hm_maxpool2_bwd_scaled(const void* dp, const void* p, const uint8
                                       const float* scale, int dtype, int B, int H, int W, int C, int act, float slope,
                                       float* db, void* stream) {
   CHECK_DTYPE(dtype, "hm_maxpool2_bwd_scaled");
-  HM_CHECK_ARG(dp && p && idx && dx && dxs && scale && B > 0 && H >= 2 && W >= 2 && C > 0,
+  HM_CHECK_ARG(dp && p && idx && dxs && scale && B > 0 && H >= 2 && W >= 2 && C > 0,
                "hm_maxpool2_bwd_scaled: bad argument");
-  if (!(C % 8 == 0 && 256 % (C / 8) == 0 && al16(dp) && al16(p) && al16(dx) && al16(dxs) && (((uintptr_t)idx) & 7) == 0)) {
+  if (!(C % 8 == 0 && 256 % (C / 8) == 0 && al16(dp) && al16(p) && (!dx || al16(dx)) && al16(dxs) && (((uintptr_t)idx) & 7) == 0)) {
     set_error("hm_maxpool2_bwd_scaled: needs C %% 8 == 0, 256 %% (C/8) == 0 and 16-byte aligned tensors (C = %d)", C);
     return HM_ERR_UNSUPPORTED;
   }

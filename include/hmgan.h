@@ -294,7 +294,8 @@ int hm_maxpool2_bwd(const void* dp, const void* p, const uint8_t* idx, void* dx,
                     int H, int W, int C, int act, float slope, float* db, void* stream);
 /* The same with a per-image weight: dx as above, dxs = scale[image] * dx (a second tensor of dx's shape) and
  * db += scale[image] * (sum of dx).  Used by the single-pass discriminator backward (hm_adv_loss_pair): the
- * input-gradient chain runs on dx, weight and bias gradients on dxs.  Needs C % 8 == 0 and 256 % (C/8) == 0. */
+ * input-gradient chain runs on dx, weight and bias gradients on dxs.  Needs C % 8 == 0 and 256 % (C/8) == 0.  dx may be
+ * NULL (only dxs and db are produced: the half of the work that belongs on the weight-gradient stream). */
 int hm_maxpool2_bwd_scaled(const void* dp, const void* p, const uint8_t* idx, void* dx, void* dxs, const float* scale,
                            int dtype, int B, int H, int W, int C, int act, float slope, float* db, void* stream);
 /* dst[r][:] = scale[r] * src[r][:]  (R rows of L elements). */

@@ -423,7 +423,8 @@ def hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, db=None, str
 
 
 def hm_maxpool2_bwd_scaled(dp, p, idx, dx, dxs, scale, dtype, B, H, W, Cn, act, slope, db=None, stream=None):
-    hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, None)
+    if dx:
+        hm_maxpool2_bwd(dp, p, idx, dx, dtype, B, H, W, Cn, act, slope, None)
     sc = _t(_a(scale, B, np.float32)).view(B, 1, 1, 1)
     Hp, Wp = H // 2, W // 2
     n = B * Hp * Wp * Cn
