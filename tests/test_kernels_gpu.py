@@ -147,6 +147,34 @@ def test_pack_unpack(mode, shape, dtype):
         bo.check(out, 0.0, "unpack mode %d" % mode)
 
 
+@pytest.mark.parametrize("mode,shape", [(5, (64, 96, 3, 3)), (6, (64, 96, 3, 3)), (5, (40, 33, 5, 5)), (6, (40, 33, 5, 5)),
+                                        (5, (128, 64, 1, 1)), (6, (96, 64, 2, 2)), (0, (64, 96, 3, 3)),
+                                        (0, (40, 33, 5, 5)), (20, (64, 64, 5, 5)), (21, (48, 40, 1, 1)),
+                                        (8, (32, 64, 5, 5)), (12, (64, 64, 3, 3))])
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_tensor_core_packs_tiled_and_generic(mode, shape, dtype):
+    """The K-major tensor-core packs (modes 5 / 6 and the un-pack mode 0 through the tiled shared-memory kernels when both
+    channel counts reach 32, ragged tiles included; the phase packs 8 / 12 / 20 and the dense pack 21 through the generic
+    one) against the emulation of their index maps: exact in float32, one rounding in fp16."""
+    r = np.random.RandomState(mode * 7 + shape[0])
+    cout, cin, kh, kw = shape
+    bo = Both()
+    wshape = (cin, cout) if mode == 21 else (cout, cin, kh, kw)
+    w = bo.t(r.randn(*wshape))
+    if mode == 0:
+        if dtype == 1:
+            pytest.skip("the un-pack is float32 only")
+        g = bo.t(r.randn(kh * kw * cin * cout))
+        out = bo.t(np.zeros(cout * cin * kh * kw))
+        bo.run("hm_unpack_conv_wgrad", lambda P: (P(g), P(out), 0, cout, cin, kh, kw))
+        bo.check(out, 0.0, "unpack mode 0 %r" % (shape,))
+        return
+    n = _lib.pack_count(mode, cout, cin, kh, kw)
+    wp = bo.t(np.zeros(n), TD[dtype])
+    bo.run("hm_pack_conv_weight", lambda P: (P(w), P(wp), mode, cout, cin, kh, kw, 0, 0, dtype))
+    bo.check(wp, 1e-3 if dtype else (1e-6 if mode in (8, 20) else 0.0), "pack mode %d %r" % (mode, shape))
+
+
 @pytest.mark.parametrize("dtype", [0, 1])
 @pytest.mark.parametrize("M,Cn", [(1000, 8), (4, 2048), (4099, 64), (300, 512), (77, 3)])
 def test_batchnorm_chain(M, Cn, dtype):

@@ -15,11 +15,12 @@ def main(path, min_ms=1.0):
     rows = [row for row in r if len(row) > vi]
     # a training step ends with the optimiser launches: keep only the last complete step when there are several
     marks = [i for i, row in enumerate(rows) if 'rmsprop' in row[ki] or 'adam_kernel' in row[ki]]
-    # the update of a step = its optimiser launches, each followed by that network's weight re-packs; the first
-    # optimiser launch of a step is the one that comes after a long stretch of other kernels
-    starts = [i for k, i in enumerate(marks) if k == 0 or i - marks[k - 1] > 60]
+    # a step starts with the cast of the latent batch into the generator's input buffer (one cast_kernel<float, __half>
+    # per step; the optimiser launches are spread over two streams and no longer mark a boundary)
+    starts = [i for i, row in enumerate(rows) if 'cast_kernel<float' in row[ki]]
+    if len(starts) < 2:
+        starts = [i for k, i in enumerate(marks) if k == 0 or i - marks[k - 1] > 60]
     if len(starts) >= 2:
-        # one step period: from the first optimiser launch of the previous step up to that of the last step
         rows = rows[starts[-2]:starts[-1]]
         print('last full training step period (%d of %d launches)' % (len(rows), starts[-1]))
     agg = collections.defaultdict(lambda: [0, 0.0])
