@@ -439,48 +439,55 @@ __global__ void pack_weight_multi_kernel(const HmPackJob* __restrict__ jobs) {
 //   MODE 0 (unpack, T = float): dw[co][ci][a][b] = dwp[((kh-1-a)*kw + (kw-1-b))*cin + ci][co]
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict__ w, T* __restrict__ wp, int cout, int cin,
-                                                        int taps) {
+                                                        int taps, int tco) {
   extern __shared__ float sm_pk[];
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
-  const int row = 32 * taps + 1;                               // +1: the transposing accesses below hit 32 banks
-  const int nci = min(32, cin - ci0), nco = min(32, cout - co0);
-  for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += blockDim.x) {
+  const int co0 = blockIdx.y * tco, ci0 = blockIdx.x * 32;
+  const int row = 32 * taps + 1;                               // +1: the transposing accesses below hit different banks
+  const int nci = min(32, cin - ci0), nco = min(tco, cout - co0);
+  for (int idx = threadIdx.x; idx < tco * 32 * taps; idx += blockDim.x) {
     const int c = idx / (32 * taps), rem = idx - c * (32 * taps);
     if (c < nco && rem < nci * taps) sm_pk[c * row + rem] = w[((size_t)(co0 + c) * cin + ci0) * taps + rem];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < taps * 32 * 32; idx += blockDim.x) {
-    const int t = idx >> 10, a = (idx >> 5) & 31, b = idx & 31;
-    if (MODE == 5) {                                           // a = co, b = ci (contiguous in the pack)
+  if (MODE == 5) {                                             // runs of 32 ci
+    for (int idx = threadIdx.x; idx < taps * tco * 32; idx += blockDim.x) {
+      const int b = idx & 31, a = (idx >> 5) % tco, t = (idx >> 5) / tco;
       if (a < nco && b < nci) stf(wp + ((size_t)t * cout + co0 + a) * cin + ci0 + b, sm_pk[a * row + b * taps + (taps - 1 - t)]);
-    } else {                                                   // a = ci, b = co (contiguous in the pack)
+    }
+  } else {                                                     // runs of tco co
+    for (int idx = threadIdx.x; idx < taps * 32 * tco; idx += blockDim.x) {
+      const int b = idx % tco, a = (idx / tco) & 31, t = idx / (tco * 32);
       if (a < nci && b < nco) stf(wp + ((size_t)t * cin + ci0 + a) * cout + co0 + b, sm_pk[b * row + a * taps + t]);
     }
   }
 }
 
 __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cout,
-                                                          int cin, int taps) {
+                                                          int cin, int taps, int tco) {
   extern __shared__ float sm_pk[];
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int co0 = blockIdx.y * tco, ci0 = blockIdx.x * 32;
   const int row = 32 * taps + 1;
-  const int nci = min(32, cin - ci0), nco = min(32, cout - co0);
-  for (int idx = threadIdx.x; idx < taps * 32 * 32; idx += blockDim.x) {
-    const int t = idx >> 10, a = (idx >> 5) & 31, b = idx & 31;          // a = ci, b = co (contiguous in dwp)
+  const int nci = min(32, cin - ci0), nco = min(tco, cout - co0);
+  for (int idx = threadIdx.x; idx < taps * 32 * tco; idx += blockDim.x) {
+    const int b = idx % tco, a = (idx / tco) & 31, t = idx / (tco * 32);          // a = ci, b = co (contiguous in dwp)
     if (a < nci && b < nco) sm_pk[b * row + a * taps + (taps - 1 - t)] = dwp[((size_t)t * cin + ci0 + a) * cout + co0 + b];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < tco * 32 * taps; idx += blockDim.x) {
     const int c = idx / (32 * taps), rem = idx - c * (32 * taps);
     if (c < nco && rem < nci * taps) dw[((size_t)(co0 + c) * cin + ci0) * taps + rem] = sm_pk[c * row + rem];
   }
 }
 
-// shared memory of one tile; 0 if the shape is not worth / not able to take the tiled path
-static size_t pack_tile_smem(int cout, int cin, int taps) {
+// co rows per tile: 32, halved while that leaves less than ~2 CTAs per SM (the small layers of the DCGAN); 0 = use the
+// generic kernel (tiny or odd shapes)
+static int pack_tile_tco(int cout, int cin, int taps) {
   if (cout < 32 || cin < 32 || taps < 1 || taps > 49) return 0;
-  return (size_t)32 * (32 * taps + 1) * sizeof(float);
+  int tco = 32;
+  while (tco > 4 && (long long)((cin + 31) / 32) * ((cout + tco - 1) / tco) < 2LL * num_sms()) tco >>= 1;
+  return tco;
 }
+static size_t pack_tile_smem(int tco, int taps) { return (size_t)tco * (32 * taps + 1) * sizeof(float); }
 
 template <typename K>
 static bool pack_tile_attr(K kernel, size_t smem) {
@@ -674,15 +681,16 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 5 || mode == 6) {
-    const size_t smem = pack_tile_smem(cout, cin, kh * kw);
-    const dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+    const int tco = pack_tile_tco(cout, cin, kh * kw);
+    const size_t smem = tco ? pack_tile_smem(tco, kh * kw) : 0;
+    const dim3 grid((cin + 31) / 32, tco ? (cout + tco - 1) / tco : 1);
     bool done = false;
 #define HM_PACK_TILE(T_, M_)                                                                                       \
     if (pack_tile_attr(pack_tile_kernel<T_, M_>, smem)) {                                                            \
-      pack_tile_kernel<T_, M_><<<grid, 256, smem, st>>>(w, (T_*)wp, cout, cin, kh * kw);                             \
+      pack_tile_kernel<T_, M_><<<grid, 256, smem, st>>>(w, (T_*)wp, cout, cin, kh * kw, tco);                        \
       done = true;                                                                                                   \
     }
-    if (smem && grid.y <= 65535) {
+    if (tco && grid.y <= 65535) {
       if (dst_dtype == HM_F32) {
         if (mode == 5) { HM_PACK_TILE(float, 5) } else { HM_PACK_TILE(float, 6) }
       } else {
@@ -711,10 +719,11 @@ extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int c
                "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;
   if (mode == 0) {
-    const size_t smem = pack_tile_smem(cout, cin, kh * kw);
-    if (smem && (cout + 31) / 32 <= 65535 && pack_tile_attr(unpack_tile_kernel, smem)) {
-      unpack_tile_kernel<<<dim3((cin + 31) / 32, (cout + 31) / 32), 256, smem, (cudaStream_t)stream>>>(dwp, dw, cout, cin,
-                                                                                                      kh * kw);
+    const int tco = pack_tile_tco(cout, cin, kh * kw);
+    const size_t smem = tco ? pack_tile_smem(tco, kh * kw) : 0;
+    if (tco && (cout + tco - 1) / tco <= 65535 && pack_tile_attr(unpack_tile_kernel, smem)) {
+      unpack_tile_kernel<<<dim3((cin + 31) / 32, (cout + tco - 1) / tco), 256, smem, (cudaStream_t)stream>>>(
+          dwp, dw, cout, cin, kh * kw, tco);
       HM_CHECK_LAUNCH("hm_unpack_conv_wgrad(tiled)");
       return HM_OK;
     }

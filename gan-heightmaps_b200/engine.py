@@ -64,47 +64,51 @@ class Runtime(object):
         self.sync_bn_group = None
         self._pack_jobs = None
         self._pack_tables = {}
-        self._wgrad_stream = None
-        self._wgrad_forked = False
+        # lanes: independent parts of the step run on their own streams (Runtime.fork): "main", "aux" (D(x) beside G's
+        # forward pass), "p2p" (the pix2pix half of a joint step beside the DCGAN half).  Per-lane state -- the
+        # weight-gradient side stream, scratch workspaces -- is keyed by the lane NAME, which is the same during the
+        # eager warm-up calls and under CUDA-graph capture.
+        self.lane = "main"
+        self._lane_streams = {}
+        self._wgrad_streams = {}
+        self._wgrad_forked = {}
         self._wgrad_side = (self.device.type == "cuda" and not self.split
                             and os.environ.get("HMGAN_WGRAD_STREAM", "1") != "0")
         self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "1") != "0"
         self._tc_ws = {}
-        # lanes: the step forks independent work onto an auxiliary stream (Runtime.fork); per-lane scratch is keyed by
-        # the lane NAME, which is the same during the eager warm-up calls and under CUDA-graph capture
-        self.lane = "main"
-        self._aux_stream = None
         self._fork_ok = (self.device.type == "cuda" and precision == "fast"
                          and os.environ.get("HMGAN_FORK", "1") != "0")
         _lib.load()
 
     class _Fork(object):
-        def __init__(self, rt):
-            self.rt = rt
+        def __init__(self, rt, lane):
+            self.rt, self.lane = rt, lane
 
         def __enter__(self):
             rt = self.rt
-            if rt._aux_stream is None:
-                rt._aux_stream = torch.cuda.Stream(rt.device)
-            rt._aux_stream.wait_stream(torch.cuda.current_stream(rt.device))      # everything issued so far is visible
-            self.ctx = torch.cuda.stream(rt._aux_stream)
+            st = rt._lane_streams.get(self.lane)
+            if st is None:
+                st = rt._lane_streams[self.lane] = torch.cuda.Stream(rt.device)
+            st.wait_stream(torch.cuda.current_stream(rt.device))      # everything issued so far is visible
+            self.ctx = torch.cuda.stream(st)
             self.ctx.__enter__()
-            rt.lane = "aux"
+            self.prev, rt.lane = rt.lane, self.lane
             return self
 
         def __exit__(self, *exc):
-            self.rt.lane = "main"
+            self.rt.lane = self.prev
             return self.ctx.__exit__(*exc)
 
-    def fork(self):
-        """`with rt.fork():` issues the enclosed launches on the auxiliary stream, ordered after everything already
-        issued on the current stream; join() makes the current stream wait for them.  Works eagerly and under CUDA-graph
-        capture (cross-stream edges of the captured graph).  Only independent work may go there."""
-        return Runtime._Fork(self)
+    def fork(self, lane="aux"):
+        """`with rt.fork(lane):` issues the enclosed launches on that lane's stream, ordered after everything already
+        issued on the current stream; join(lane) makes the current stream wait for them.  Works eagerly and under
+        CUDA-graph capture (cross-stream edges of the captured graph).  Only independent work may go there."""
+        return Runtime._Fork(self, lane)
 
-    def join(self):
-        if self._aux_stream is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self._aux_stream)
+    def join(self, lane="aux"):
+        st = self._lane_streams.get(lane)
+        if st is not None:
+            torch.cuda.current_stream(self.device).wait_stream(st)
 
     def allreduce_mean(self, t):
         """Average a small device tensor over the SyncBN group (sum, then 1/world: gloo has no AVG)."""
@@ -128,14 +132,22 @@ class Runtime(object):
         invisible to callers and is captured into the step's CUDA graph as ordinary cross-stream dependencies."""
         if not self._wgrad_side:
             return None
-        if self._wgrad_stream is None:
-            self._wgrad_stream = torch.cuda.Stream(self.device)
-        return self._wgrad_stream
+        st = self._wgrad_streams.get(self.lane)
+        if st is None:
+            st = self._wgrad_streams[self.lane] = torch.cuda.Stream(self.device)
+        return st
+
+    def mark_wgrad_forked(self):
+        self._wgrad_forked[self.lane] = True
+
+    def side_if_forked(self):
+        """This lane's weight-gradient stream if work is pending on it (un-joined), else None."""
+        return self._wgrad_streams.get(self.lane) if self._wgrad_forked.get(self.lane) else None
 
     def join_wgrad_stream(self):
-        if self._wgrad_forked:
-            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
-            self._wgrad_forked = False
+        if self._wgrad_forked.get(self.lane):
+            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_streams[self.lane])
+            self._wgrad_forked[self.lane] = False
 
     def call(self, name, *args):
         if self._pack_jobs is not None and name == "hm_pack_conv_weight":
@@ -732,7 +744,7 @@ class ConvOp(object):
                 side.wait_stream(torch.cuda.current_stream(rt.device))
                 with torch.cuda.stream(side):
                     dw_part()
-                rt._wgrad_forked = True
+                rt.mark_wgrad_forked()
             elif wgrad:
                 dw_part()
             if t1:
@@ -769,7 +781,7 @@ class ConvOp(object):
                     if pre is not None:
                         pre()
                     self._bwd_wgrad(rt, lo, hi, g, x1, x2)
-                rt._wgrad_forked = True
+                rt.mark_wgrad_forked()
         elif pre is not None:
             pre()
         self._bwd_dgrad(rt, lo, hi, g_plain, wgrad, input_grad)

@@ -198,7 +198,7 @@ class Pix2Pix(object):
             return
         import torch.distributed as dist
         rt = self.rt
-        side = rt._wgrad_stream if rt._wgrad_forked else None
+        side = rt.side_if_forked()
         if side is not None:
             side.wait_stream(torch.cuda.current_stream(rt.device))
             with torch.cuda.stream(side):
@@ -216,7 +216,7 @@ class Pix2Pix(object):
         gradient (and its all-reduce), while the current stream goes on with work that no longer reads this network's
         weights or gradients.  Returns False (nothing done) when there is no side stream."""
         rt = self.rt
-        side = rt._wgrad_stream if rt._wgrad_forked else None
+        side = rt.side_if_forked()
         if side is None:
             return False
         self._sync_lr()
@@ -339,6 +339,15 @@ class Pix2Pix(object):
             self.D.forward(2 * B, 0, B)                                     # D(x)            :94
             return self.losses
         upd = []
+        # a joint step: the pix2pix half is independent of the DCGAN half until the update -- it runs on its own lane
+        # (stream), so that its many HBM-bound passes (17 BatchNorm layers, resampling) overlap the DCGAN half's
+        # tensor-core kernels and vice versa; the halves meet again before the update
+        p2p_done, p2p_upd = False, []
+        if self.have_p2p and self.have_dcgan and rt._fork_ok and part in (0, 2) and \
+                os.environ.get("HMGAN_FORK_P2P", "1") != "0":
+            with rt.fork("p2p"):
+                p2p_upd = self._p2p_part(Xd, Yd, B, train)
+            p2p_done = True
         if self.have_dcgan:
             G, D = self.G, self.D
             do = train and self.train_mode in ('both', 'dcgan')
@@ -396,37 +405,11 @@ class Pix2Pix(object):
                     self._copy(D.inputs[0].grad[B:2 * B], G.out.grad[:B])
                     G.backward(0, B, wgrad=True)
                     upd += [G, D]
-        if self.have_p2p:
-            P, Dp = self.P, self.Dp
-            do = train and self.train_mode in ('both', 'p2p')
-            P.ensure(B)
-            Dp.ensure(2 * B, input_grads=(1,))
-            cb = 1 if self.is_b_grayscale else 3
-            self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
-            a_in, b_in = Dp.inputs
-            self._load_nchw(Xd, a_in.buf, B, ca, S, S, self.is_a_grayscale)
-            self._copy(a_in.buf[:B], a_in.buf[B:2 * B])
-            self._load_nchw(Yd, b_in.buf, B, cb, S, S, self.is_b_grayscale)
-            px = P.forward(B)                                               # P(X)            :99
-            self._copy(px, b_in.buf[B:2 * B])
-            h = Dp.forward(2 * B)                                           # Dp(X,Y), Dp(X,P(X)) :98,101
-            dh = Dp.out.grad if do else None
-            self._adv(Dp, h[:B], dh[:B] if do else None, 1., 4, ls)         # disc_loss_p2p   :121
-            self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 0., 4, ls)
-            if do:
-                Dp.backward(0, 2 * B, wgrad=True, input_grad=False)
-            self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 1., 2, ls)   # gen_loss_p2p :110
-            dpx = None
-            if do:
-                Dp.backward(B, 2 * B, wgrad=False, input_grad=True)
-                dpx = b_in.grad[B:2 * B]
-            # recon_loss :112-115 ; gradient weight alpha (gen_total_loss_p2p :117)
-            rt.call("hm_recon_loss", _ptr(px), _ptr(b_in.buf[:B]), _ptr(dpx), rt.cd, px.numel(),
-                    1 if self.reconstruction == 'l2' else 0, 1.0, ls * self.alpha, 1, _ptr(self.losses[3:]))
-            if do:
-                self._copy(dpx, P.out.grad[:B])
-                P.backward(0, B, wgrad=True)
-                upd += [P, Dp]
+        if self.have_p2p and not p2p_done:
+            upd += self._p2p_part(Xd, Yd, B, train)
+        elif p2p_done:
+            rt.join("p2p")
+            upd += p2p_upd
         if upd:
             self._sync_lr()
             world = 1
@@ -443,6 +426,46 @@ class Pix2Pix(object):
                 net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
                 net.pack()       # packed copies follow the master weights inside the step (and inside its CUDA graph)
         return self.losses
+
+    def _p2p_part(self, Xd, Yd, B, train):
+        """The pix2pix half of the step (pix2pix.py:98-101,110-121): P and Dp forward, the three losses, their backward
+        passes.  Returns the networks to update.  Independent of the DCGAN half until the update."""
+        rt = self.rt
+        S = self.in_shp
+        ls = rt.loss_scale
+        ca = 1 if self.is_a_grayscale else 3
+        upd = []
+        P, Dp = self.P, self.Dp
+        do = train and self.train_mode in ('both', 'p2p')
+        P.ensure(B)
+        Dp.ensure(2 * B, input_grads=(1,))
+        cb = 1 if self.is_b_grayscale else 3
+        self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
+        a_in, b_in = Dp.inputs
+        self._load_nchw(Xd, a_in.buf, B, ca, S, S, self.is_a_grayscale)
+        self._copy(a_in.buf[:B], a_in.buf[B:2 * B])
+        self._load_nchw(Yd, b_in.buf, B, cb, S, S, self.is_b_grayscale)
+        px = P.forward(B)                                               # P(X)            :99
+        self._copy(px, b_in.buf[B:2 * B])
+        h = Dp.forward(2 * B)                                           # Dp(X,Y), Dp(X,P(X)) :98,101
+        dh = Dp.out.grad if do else None
+        self._adv(Dp, h[:B], dh[:B] if do else None, 1., 4, ls)         # disc_loss_p2p   :121
+        self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 0., 4, ls)
+        if do:
+            Dp.backward(0, 2 * B, wgrad=True, input_grad=False)
+        self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 1., 2, ls)   # gen_loss_p2p :110
+        dpx = None
+        if do:
+            Dp.backward(B, 2 * B, wgrad=False, input_grad=True)
+            dpx = b_in.grad[B:2 * B]
+        # recon_loss :112-115 ; gradient weight alpha (gen_total_loss_p2p :117)
+        rt.call("hm_recon_loss", _ptr(px), _ptr(b_in.buf[:B]), _ptr(dpx), rt.cd, px.numel(),
+                1 if self.reconstruction == 'l2' else 0, 1.0, ls * self.alpha, 1, _ptr(self.losses[3:]))
+        if do:
+            self._copy(dpx, P.out.grad[:B])
+            P.backward(0, B, wgrad=True)
+            upd += [P, Dp]
+        return upd
 
     def _host_tensor(self, a):
         """float32 host tensor of a numpy array / tensor; raw uint8 image data stay uint8 (normalised on the device)."""
