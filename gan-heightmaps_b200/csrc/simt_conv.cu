@@ -5,6 +5,8 @@
 // Restates theano CorrMM / CorrMM_gradInputs / CorrMM_gradWeights as reached from
 // lasagne Conv2DLayer / Deconv2DLayer / DenseLayer (reference architectures/dcgan.py:16,
 // 22,32,42,50; architectures/p2p.py:20-24).
+#include <stdlib.h>
+
 #include "hm_common.cuh"
 
 namespace hm {
@@ -482,7 +484,12 @@ __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restric
 // co rows per tile: 32, halved while that leaves less than ~2 CTAs per SM (the small layers of the DCGAN); 0 = use the
 // generic kernel (tiny or odd shapes)
 static int pack_tile_tco(int cout, int cin, int taps) {
-  if (cout < 32 || cin < 32 || taps < 1 || taps > 49) return 0;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("HMGAN_PACK_TILED");               // diagnostic: 0 = always the generic kernels
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled || cout < 32 || cin < 32 || taps < 1 || taps > 49) return 0;
   int tco = 32;
   while (tco > 4 && (long long)((cin + 31) / 32) * ((cout + tco - 1) / tco) < 2LL * num_sms()) tco >>= 1;
   return tco;
