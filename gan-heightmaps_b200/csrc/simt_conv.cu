@@ -414,6 +414,10 @@ __device__ __forceinline__ void pack_elem(const float* __restrict__ w, T* __rest
   stf(wp + i, val);
 }
 
+// (A tiled shared-memory variant of the mode 5 / 6 packs and of the mode-0 un-pack was written and measured in round 2:
+// it coalesces the strided side of the permutation, but inside the captured step the ~50 packs are launch-bound and
+// partly hidden on the side stream -- 12.55 vs 12.67 ms DCGAN, 18.19 vs 18.26 ms joint, 11.20 vs 11.24 ms pix2pix, i.e. no
+// gain -- so it was removed again.)
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int mode, int cout,
                                    int cin, int kh, int kw, int u, int v, long long n) {
@@ -429,76 +433,6 @@ __global__ void pack_weight_multi_kernel(const HmPackJob* __restrict__ jobs) {
   const HmPackJob j = jobs[blockIdx.y];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += (long long)gridDim.x * blockDim.x)
     pack_elem<T>(j.w, (T*)j.wp, j.mode, j.cout, j.cin, j.kh, j.kw, j.u, j.v, i);
-}
-
-// ---- tiled (un)packs of the big tensor-core layouts ---------------------------------------------------------------------
-// The generic kernels above gather one element per thread; for the K-major packs that means reads (or writes) with a
-// stride of kh*kw floats (mode 5) or Cin*kh*kw floats (mode 6): 8x sector over-fetch, 1.1 ms per pix2pix step for its
-// 54 M parameters (round-2 profile).  Here a CTA moves a [32 co][32 ci][taps] block through shared memory: the master
-// layout W[co][ci][tap] is read in runs of 32*taps contiguous floats, the packs are written in runs of 32 elements.
-//   MODE 5: wp[(r*kw+s)][co][ci] = W[co][ci][kh-1-r][kw-1-s]      (tap index reversed)
-//   MODE 6: wp[(r*kw+s)][ci][co] = W[co][ci][r][s]
-//   MODE 0 (unpack, T = float): dw[co][ci][a][b] = dwp[((kh-1-a)*kw + (kw-1-b))*cin + ci][co]
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict__ w, T* __restrict__ wp, int cout, int cin,
-                                                        int taps, int tco) {
-  extern __shared__ float sm_pk[];
-  const int co0 = blockIdx.y * tco, ci0 = blockIdx.x * 32;
-  const int row = 32 * taps + 1;                               // +1: the transposing accesses below hit different banks
-  const int nci = min(32, cin - ci0), nco = min(tco, cout - co0);
-  for (int idx = threadIdx.x; idx < tco * 32 * taps; idx += blockDim.x) {
-    const int c = idx / (32 * taps), rem = idx - c * (32 * taps);
-    if (c < nco && rem < nci * taps) sm_pk[c * row + rem] = w[((size_t)(co0 + c) * cin + ci0) * taps + rem];
-  }
-  __syncthreads();
-  if (MODE == 5) {                                             // runs of 32 ci
-    for (int idx = threadIdx.x; idx < taps * tco * 32; idx += blockDim.x) {
-      const int b = idx & 31, a = (idx >> 5) % tco, t = (idx >> 5) / tco;
-      if (a < nco && b < nci) stf(wp + ((size_t)t * cout + co0 + a) * cin + ci0 + b, sm_pk[a * row + b * taps + (taps - 1 - t)]);
-    }
-  } else {                                                     // runs of tco co
-    for (int idx = threadIdx.x; idx < taps * 32 * tco; idx += blockDim.x) {
-      const int b = idx % tco, a = (idx / tco) & 31, t = idx / (tco * 32);
-      if (a < nci && b < nco) stf(wp + ((size_t)t * cin + ci0 + a) * cout + co0 + b, sm_pk[b * row + a * taps + t]);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cout,
-                                                          int cin, int taps, int tco) {
-  extern __shared__ float sm_pk[];
-  const int co0 = blockIdx.y * tco, ci0 = blockIdx.x * 32;
-  const int row = 32 * taps + 1;
-  const int nci = min(32, cin - ci0), nco = min(tco, cout - co0);
-  for (int idx = threadIdx.x; idx < taps * 32 * tco; idx += blockDim.x) {
-    const int b = idx % tco, a = (idx / tco) & 31, t = idx / (tco * 32);          // a = ci, b = co (contiguous in dwp)
-    if (a < nci && b < nco) sm_pk[b * row + a * taps + (taps - 1 - t)] = dwp[((size_t)t * cin + ci0 + a) * cout + co0 + b];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < tco * 32 * taps; idx += blockDim.x) {
-    const int c = idx / (32 * taps), rem = idx - c * (32 * taps);
-    if (c < nco && rem < nci * taps) dw[((size_t)(co0 + c) * cin + ci0) * taps + rem] = sm_pk[c * row + rem];
-  }
-}
-
-// co rows per tile: 32, halved while that leaves less than ~2 CTAs per SM (the small layers of the DCGAN); 0 = use the
-// generic kernel (tiny or odd shapes)
-static int pack_tile_tco(int cout, int cin, int taps) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("HMGAN_PACK_TILED");               // diagnostic: 0 = always the generic kernels
-    enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled || cout < 32 || cin < 32 || taps < 1 || taps > 49) return 0;
-  int tco = 32;
-  while (tco > 4 && (long long)((cin + 31) / 32) * ((cout + tco - 1) / tco) < 2LL * num_sms()) tco >>= 1;
-  return tco;
-}
-static size_t pack_tile_smem(int tco, int taps) { return (size_t)tco * (32 * taps + 1) * sizeof(float); }
-
-template <typename K>
-static bool pack_tile_attr(K kernel, size_t smem) {
-  return smem <= 48 * 1024 || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024) == cudaSuccess;
 }
 
 // packed fp32 gradient -> master layout gradient
@@ -687,29 +621,6 @@ extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout,
   const long long n = pack_count(mode, cout, cin, kh, kw);
   unsigned blocks = (unsigned)((n + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == 5 || mode == 6) {
-    const int tco = pack_tile_tco(cout, cin, kh * kw);
-    const size_t smem = tco ? pack_tile_smem(tco, kh * kw) : 0;
-    const dim3 grid((cin + 31) / 32, tco ? (cout + tco - 1) / tco : 1);
-    bool done = false;
-#define HM_PACK_TILE(T_, M_)                                                                                       \
-    if (pack_tile_attr(pack_tile_kernel<T_, M_>, smem)) {                                                            \
-      pack_tile_kernel<T_, M_><<<grid, 256, smem, st>>>(w, (T_*)wp, cout, cin, kh * kw, tco);                        \
-      done = true;                                                                                                   \
-    }
-    if (tco && grid.y <= 65535) {
-      if (dst_dtype == HM_F32) {
-        if (mode == 5) { HM_PACK_TILE(float, 5) } else { HM_PACK_TILE(float, 6) }
-      } else {
-        if (mode == 5) { HM_PACK_TILE(__half, 5) } else { HM_PACK_TILE(__half, 6) }
-      }
-    }
-#undef HM_PACK_TILE
-    if (done) {
-      HM_CHECK_LAUNCH("hm_pack_conv_weight(tiled)");
-      return HM_OK;
-    }
-  }
   if (dst_dtype == HM_F32)
     pack_weight_kernel<float><<<blocks, 256, 0, st>>>(w, (float*)wp, mode, cout, cin, kh, kw, u, v, n);
   else
@@ -725,16 +636,6 @@ extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int c
                    (mode == 17 && kh == 2 && kw == 2 && 4 * cout <= 64),
                "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;
-  if (mode == 0) {
-    const int tco = pack_tile_tco(cout, cin, kh * kw);
-    const size_t smem = tco ? pack_tile_smem(tco, kh * kw) : 0;
-    if (tco && (cout + tco - 1) / tco <= 65535 && pack_tile_attr(unpack_tile_kernel, smem)) {
-      unpack_tile_kernel<<<dim3((cin + 31) / 32, (cout + tco - 1) / tco), 256, smem, (cudaStream_t)stream>>>(
-          dwp, dw, cout, cin, kh * kw, tco);
-      HM_CHECK_LAUNCH("hm_unpack_conv_wgrad(tiled)");
-      return HM_OK;
-    }
-  }
   unpack_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dwp, dw, mode, cout,
                                                                                      cin, kh, kw, n);
   HM_CHECK_LAUNCH("hm_unpack_conv_wgrad");

@@ -75,6 +75,8 @@ class Runtime(object):
         self._wgrad_side = (self.device.type == "cuda" and not self.split
                             and os.environ.get("HMGAN_WGRAD_STREAM", "1") != "0")
         self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "1") != "0"
+        # the weighted max-pool gradient copies and D1's weight gradient on the weight-gradient stream (A/B knob)
+        self.side_extra = os.environ.get("HMGAN_SIDE_EXTRA", "1") != "0"
         self._tc_ws = {}
         self._fork_ok = (self.device.type == "cuda" and precision == "fast"
                          and os.environ.get("HMGAN_FORK", "1") != "0")
@@ -728,7 +730,7 @@ class ConvOp(object):
         ws = _ptr(net.wscale) if net.wscale is not None else None
         ia, ib = net.ig_range if (net.ig_range is not None and t1) else (lo, hi)
         same = (ia, ib) == (lo, hi) and ws is None
-        side = rt.wgrad_stream() if wgrad else None
+        side = rt.wgrad_stream() if (wgrad and rt.side_extra) else None
 
         def dw_part():          # weight / bias gradient: reads g, pooled, idx, x; on the weight-gradient stream if there is one
             self.dwk.zero_()
@@ -1031,7 +1033,7 @@ class PoolOp(object):
         if self.net.wscale is not None:
             args = (_ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]))
             tail = (rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope)
-            if wgrad and self.prod is not None and rt.wgrad_stream() is not None:
+            if wgrad and self.prod is not None and rt.side_extra and rt.wgrad_stream() is not None:
                 # the input-gradient chain needs only the plain dX: it stays here; the per-sample-weighted copy and the
                 # bias gradient are operands of the producing convolution's WEIGHT gradient and are produced on its stream
                 rt.call("hm_maxpool2_bwd", *args, _ptr(self.x.g(lo, hi)), *tail, None)

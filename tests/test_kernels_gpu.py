@@ -152,10 +152,9 @@ def test_pack_unpack(mode, shape, dtype):
                                         (0, (40, 33, 5, 5)), (20, (64, 64, 5, 5)), (21, (48, 40, 1, 1)),
                                         (8, (32, 64, 5, 5)), (12, (64, 64, 3, 3))])
 @pytest.mark.parametrize("dtype", [0, 1])
-def test_tensor_core_packs_tiled_and_generic(mode, shape, dtype):
-    """The K-major tensor-core packs (modes 5 / 6 and the un-pack mode 0 through the tiled shared-memory kernels when both
-    channel counts reach 32, ragged tiles included; the phase packs 8 / 12 / 20 and the dense pack 21 through the generic
-    one) against the emulation of their index maps: exact in float32, one rounding in fp16."""
+def test_tensor_core_packs(mode, shape, dtype):
+    """The K-major tensor-core packs (modes 5 / 6, the phase packs 8 / 12 / 20, the dense pack 21) and the un-pack mode 0
+    at layer-sized shapes against the emulation of their index maps: exact in float32, one rounding in fp16."""
     r = np.random.RandomState(mode * 7 + shape[0])
     cout, cin, kh, kw = shape
     bo = Both()
