@@ -76,7 +76,12 @@ class Runtime(object):
                             and os.environ.get("HMGAN_WGRAD_STREAM", "1") != "0")
         self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "1") != "0"
         # the weighted max-pool gradient copies and D1's weight gradient on the weight-gradient stream (A/B knob)
-        self.side_extra = os.environ.get("HMGAN_SIDE_EXTRA", "1") != "0"
+        # two more pieces of the discriminator's backward pass that COULD run on the weight-gradient stream.  Measured on
+        # one box (profiles/r2_variants_ab.txt, visit r2q): both on = 12.23 / 12.28 ms, both off = 12.06 / 12.08 ms per
+        # DCGAN step, joint step unchanged -- the deferred copy re-reads the pooled gradient and argmax, and the side
+        # stream is already the longer one while D's backward runs.  Off by default.
+        self.side_d1dw = os.environ.get("HMGAN_SIDE_D1DW", "0") != "0"      # D layer 1's weight gradient (hm_c1s2_bwd)
+        self.side_poolcopy = os.environ.get("HMGAN_SIDE_POOLCOPY", "0") != "0"   # the per-sample-weighted max-pool copy
         self._tc_ws = {}
         self._fork_ok = (self.device.type == "cuda" and precision == "fast"
                          and os.environ.get("HMGAN_FORK", "1") != "0")
@@ -730,7 +735,7 @@ class ConvOp(object):
         ws = _ptr(net.wscale) if net.wscale is not None else None
         ia, ib = net.ig_range if (net.ig_range is not None and t1) else (lo, hi)
         same = (ia, ib) == (lo, hi) and ws is None
-        side = rt.wgrad_stream() if (wgrad and rt.side_extra) else None
+        side = rt.wgrad_stream() if (wgrad and rt.side_d1dw) else None
 
         def dw_part():          # weight / bias gradient: reads g, pooled, idx, x; on the weight-gradient stream if there is one
             self.dwk.zero_()
@@ -1033,7 +1038,7 @@ class PoolOp(object):
         if self.net.wscale is not None:
             args = (_ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]))
             tail = (rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope)
-            if wgrad and self.prod is not None and rt.side_extra and rt.wgrad_stream() is not None:
+            if wgrad and self.prod is not None and rt.side_poolcopy and rt.wgrad_stream() is not None:
                 # the input-gradient chain needs only the plain dX: it stays here; the per-sample-weighted copy and the
                 # bias gradient are operands of the producing convolution's WEIGHT gradient and are produced on its stream
                 rt.call("hm_maxpool2_bwd", *args, _ptr(self.x.g(lo, hi)), *tail, None)

@@ -311,8 +311,9 @@ class Pix2Pix(object):
 
     def _step_eager(self, Zd, Xd, Yd, train=True, part=0):
         """part 0: the whole step.  part 1: only what depends on Z alone (G's forward pass); part 3: D(x), which depends
-        on X alone; part 2: everything else (given parts 1 and 3).  The host path captures the parts as separate CUDA
-        graphs so that the X/Y upload overlaps part 1 and D(x) runs beside the rest of it (_step_host_overlapped)."""
+        on X alone; part 4 (a pix2pix-only model): P(X), which depends on X alone; part 2: everything else (given the
+        other parts).  The host path captures the parts as separate CUDA graphs so that the X/Y upload overlaps part 1,
+        D(x) runs beside the rest of it and the texture batch Y lands under P's forward pass (_step_host_overlapped)."""
         rt = self.rt
         B = int(Xd.shape[0])
         S = self.in_shp
@@ -338,6 +339,10 @@ class Pix2Pix(object):
             self._load_nchw(Xd, self.D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
             self.D.forward(2 * B, 0, B)                                     # D(x)            :94
             return self.losses
+        if part == 4:
+            self._p2p_part(Xd, Yd, B, train, phase=1)                       # P(X)            :99
+            return self.losses
+        p2p_phase = 2 if (part == 2 and not self.have_dcgan) else 0         # P(X) came from part 4
         upd = []
         # a joint step: the pix2pix half is independent of the DCGAN half until the update -- it runs on its own lane
         # (stream), so that its many HBM-bound passes (17 BatchNorm layers, resampling) overlap the DCGAN half's
@@ -406,7 +411,7 @@ class Pix2Pix(object):
                     G.backward(0, B, wgrad=True)
                     upd += [G, D]
         if self.have_p2p and not p2p_done:
-            upd += self._p2p_part(Xd, Yd, B, train)
+            upd += self._p2p_part(Xd, Yd, B, train, phase=p2p_phase)
         elif p2p_done:
             rt.join("p2p")
             upd += p2p_upd
@@ -427,9 +432,10 @@ class Pix2Pix(object):
                 net.pack()       # packed copies follow the master weights inside the step (and inside its CUDA graph)
         return self.losses
 
-    def _p2p_part(self, Xd, Yd, B, train):
+    def _p2p_part(self, Xd, Yd, B, train, phase=0):
         """The pix2pix half of the step (pix2pix.py:98-101,110-121): P and Dp forward, the three losses, their backward
-        passes.  Returns the networks to update.  Independent of the DCGAN half until the update."""
+        passes.  Returns the networks to update.  Independent of the DCGAN half until the update.  phase 1 = only P's
+        forward pass (all that can run before Y has arrived), phase 2 = the rest, phase 0 = both."""
         rt = self.rt
         S = self.in_shp
         ls = rt.loss_scale
@@ -440,12 +446,17 @@ class Pix2Pix(object):
         P.ensure(B)
         Dp.ensure(2 * B, input_grads=(1,))
         cb = 1 if self.is_b_grayscale else 3
-        self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
+        if phase in (0, 1):
+            self._load_nchw(Xd, P.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
+            px = P.forward(B)                                           # P(X)            :99
+            if phase == 1:
+                return upd
+        else:
+            px = P.out.buf[:B]
         a_in, b_in = Dp.inputs
         self._load_nchw(Xd, a_in.buf, B, ca, S, S, self.is_a_grayscale)
         self._copy(a_in.buf[:B], a_in.buf[B:2 * B])
         self._load_nchw(Yd, b_in.buf, B, cb, S, S, self.is_b_grayscale)
-        px = P.forward(B)                                               # P(X)            :99
         self._copy(px, b_in.buf[B:2 * B])
         h = Dp.forward(2 * B)                                           # Dp(X,Y), Dp(X,P(X)) :98,101
         dh = Dp.out.grad if do else None
@@ -477,9 +488,10 @@ class Pix2Pix(object):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
     def _step_host_overlapped(self, Z, X, Y, train):
-        """train_fn / loss_fn from HOST inputs with the step captured as TWO graphs: part 1 (G's forward pass, needs only
-        Z) starts at once while X (and Y) are still being uploaded on a side stream; part 2 waits for them.  Returns None
-        until the graphs exist (two eager calls size every buffer first)."""
+        """train_fn / loss_fn from HOST inputs with the step captured as several graphs: part 1 (G's forward pass, needs
+        only Z) starts at once while X and then Y are uploaded on a copy stream; D(x) (or, without a DCGAN, P(X)) starts
+        as soon as X has landed; part 2 waits for Y and for those.  Returns None until the graphs exist (two eager calls
+        size every buffer first)."""
         Zs, Xs = self._host_tensor(Z), self._host_tensor(X)
         Ys = self._host_tensor(Y) if self.have_p2p else None
         key = ("host", tuple(Zs.shape), tuple(Xs.shape), Xs.dtype, tuple(Ys.shape) if Ys is not None else None,
@@ -499,8 +511,8 @@ class Pix2Pix(object):
             gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(gA):
                 self._step_eager(st["Z"], st["X"], st["Y"], train, part=1)
-            st["gC"] = None
-            if self.have_dcgan and self.rt._fork_ok:        # D(x) as its own graph, replayed on the upload stream
+            st["gC"] = st["gP"] = None
+            if self.have_dcgan and self.rt._fork_ok:        # D(x) as its own graph, replayed beside G's forward pass
                 st["gC"] = torch.cuda.CUDAGraph()
                 self.rt.lane = "aux"
                 try:
@@ -508,12 +520,17 @@ class Pix2Pix(object):
                         self._step_eager(st["Z"], st["X"], st["Y"], train, part=3)
                 finally:
                     self.rt.lane = "main"
+            elif self.have_p2p and not self.have_dcgan:     # P(X) as its own graph: Y is uploaded under it
+                st["gP"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st["gP"], pool=gA.pool()):
+                    self._step_eager(st["Z"], st["X"], st["Y"], train, part=4)
             with torch.cuda.graph(gB, pool=gA.pool()):
                 self._step_eager(st["Z"], st["X"], st["Y"], train, part=2)
             st["launches"] = self.rt.launches - l0
             st["gA"], st["gB"] = gA, gB
             st["gen"] = self._generations()
-            st["side"], st["ev"] = torch.cuda.Stream(dev), torch.cuda.Event()
+            st["side"], st["aux"] = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            st["evX"], st["evY"], st["evC"] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self._sync_lr()
         self._ensure_packed()
         main = torch.cuda.current_stream(dev)
@@ -521,14 +538,23 @@ class Pix2Pix(object):
             st["side"].wait_event(st["done"])       # (a no-op after a host synchronisation; needed by *_fn_async)
         st["Z"].copy_(Zs, non_blocking=True)
         st["gA"].replay()
-        with torch.cuda.stream(st["side"]):
+        with torch.cuda.stream(st["side"]):         # the copy stream: X, then Y right behind it
             st["X"].copy_(Xs, non_blocking=True)
-            if st["gC"] is not None:
-                st["gC"].replay()                   # D(x) as soon as X has landed, beside G's forward pass
+            st["evX"].record(st["side"])
             if Ys is not None:
                 st["Y"].copy_(Ys, non_blocking=True)
-            st["ev"].record(st["side"])
-        main.wait_event(st["ev"])
+            st["evY"].record(st["side"])
+        if st["gC"] is not None:
+            with torch.cuda.stream(st["aux"]):      # D(x) as soon as X has landed, beside G's forward pass and Y's upload
+                st["aux"].wait_event(st["evX"])
+                st["gC"].replay()
+                st["evC"].record(st["aux"])
+        if st["gP"] is not None:
+            main.wait_event(st["evX"])
+            st["gP"].replay()                       # P(X) while Y is still on its way
+        main.wait_event(st["evY"])
+        if st["gC"] is not None:
+            main.wait_event(st["evC"])
         st["gB"].replay()
         if st.get("done") is None:
             st["done"] = torch.cuda.Event()
