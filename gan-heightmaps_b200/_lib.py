@@ -54,6 +54,7 @@ _PROTOS = {
     "hm_adv_loss_pair": ([_P, _P, _P, _P, _P, _I, _LL, _I, _I, _I, _I, _F, _P, _P, _P], C.c_int),
     "hm_c1s2_bwd_fold": ([_P, _P, _P, _I, _P], C.c_int),
     "hm_c1s2_col2im": ([_P, _P, _I, _I, _I, _P], C.c_int),
+    "hm_c1s2_wgrad": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
     "hm_pack_conv_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "hm_pack_conv_weight_multi": ([_P, _I, _LL, _I, _P], C.c_int),
     "hm_pack_conv_weight_count": ([_I, _I, _I, _I, _I], C.c_longlong),

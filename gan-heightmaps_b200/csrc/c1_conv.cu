@@ -425,6 +425,7 @@ struct CbParams {
   float* dwk;           // [256][64] fp32, atomically accumulated
   __half* u;            // [B,Hq,Wq,64]
   const float* img_scale;   // [B] or null: g is multiplied by img_scale[image] (per-sample weighting of dW, db)
+  int plain;            // hm_c1s2_wgrad: g IS the 64-row operand (no activation derivative, no argmax routing, d = 0 only)
 };
 
 __global__ void __launch_bounds__(CB_THREADS, 1)
@@ -487,8 +488,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         mbar_wait(full(s), n & 1);
         tc_fence_after();
         if (p.want_dw) {
-#pragma unroll
-          for (int h = 0; h < 2; h++)
+          const int nh = p.plain ? 1 : 2;                  // plain: rows 0..63 = the operand, rows 64..127 stay zero
+#pragma unroll 1
+          for (int h = 0; h < nh; h++)
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)                 // 16 windows (two 8-row swizzle atoms) per MMA
               tc_mma_f16(tmem_base + h * 64, desc_mn_sw128(g_addr + h * 2 * C1_A_BYTES + kk * 2048, C1_A_BYTES),
@@ -543,8 +545,13 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         if (rwy < p.Hq && rwx < p.Wq) {
           const size_t ro = (((size_t)b * p.Hq + rwy) * p.Wq + rwx) * 64 + cc * 8;
           gv[k] = *reinterpret_cast<const uint4*>(p.g + ro);
-          pv[k] = *reinterpret_cast<const uint4*>(p.pl + ro);
-          kv[k] = *reinterpret_cast<const uint2*>(p.idx + ro);
+          if (!p.plain) {
+            pv[k] = *reinterpret_cast<const uint4*>(p.pl + ro);
+            kv[k] = *reinterpret_cast<const uint2*>(p.idx + ro);
+          } else {
+            pv[k] = make_uint4(0, 0, 0, 0);
+            kv[k] = make_uint2(0, 0);
+          }
         } else {
           gv[k] = pv[k] = make_uint4(0, 0, 0, 0);
           kv[k] = make_uint2(0, 0);
@@ -578,6 +585,11 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       const __half2 zero2 = __float2half2_rn(0.f);
       const uint32_t f_pos = __half_as_ushort(__float2half_rn(isc)) * 0x00010001u;
       const uint32_t f_neg = __half_as_ushort(__float2half_rn(neg * isc)) * 0x00010001u;
+      if (p.plain) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(stg + sw128_off(c * 16 + sub, cc)) = gv[c];
+      }
+      if (!p.plain) {
 #pragma unroll
       for (int c = 0; c < 8; c++) {         // pass c: window c*16 + sub, chunk cc
         const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
@@ -598,6 +610,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           const uint32_t m2 = hv[2] & __byte_perm(e1, 0, 0x1100), m3 = hv[3] & __byte_perm(e1, 0, 0x3322);
           *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(c * 16 + sub, cc)) = make_uint4(m0, m1, m2, m3);
         }
+      }
       }
       if (p.want_dw) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
@@ -659,11 +672,12 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         }
       }
     }
-    if (p.want_dw && my_tiles > 0) {
+    if (p.want_dw && my_tiles > 0 && !(p.plain && q >= 2)) {      // plain: rows 0..63 of the first accumulator only
       mbar_wait(dw_full, 0);
       tc_fence_after();
+      const int nh = p.plain ? 1 : 2;
 #pragma unroll 1
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < nh; h++) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 64;
         uint32_t v[32], v2[16];
         tmem_ld32(taddr, v);
@@ -741,6 +755,47 @@ __global__ void c1s2_col2im_kernel(const __half* __restrict__ u, __half* __restr
 
 }  // namespace hm
 
+// geometry, the (optional) weight tensor map and the launch shared by hm_c1s2_bwd and hm_c1s2_wgrad
+static int c1s2_bwd_launch(hm::CbParams& p, int B, int H, int W, const void* wk2, void* stream, const char* who) {
+  using namespace hm;
+  p.B = B; p.H = H; p.W = W; p.Hq = H / 2; p.Wq = W / 2;
+  int bw = 1;
+  while (bw * 2 <= p.Wq && bw < 128) bw *= 2;
+  p.bw = bw; p.bh = 128 / bw;
+  p.tiles_x = (p.Wq + p.bw - 1) / p.bw;
+  p.tiles_y = (p.Hq + p.bh - 1) / p.bh;
+  p.n_tiles = B * p.tiles_x * p.tiles_y;
+  CUtensorMap tmW;
+  {
+    cuuint64_t dims[2] = {64, 256};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t es[2] = {1, 1};
+    void* wp = const_cast<void*>(wk2 ? wk2 : (const void*)p.g);     // unused (never dereferenced) without the input gradient
+    CUresult r = c1_encode_fn()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wp, dims, strides, box, es,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d)", who, (int)r);
+      return HM_ERR_CUDA;
+    }
+  }
+  const size_t smem = 1024 + 256 * 128 + 2 * CB_STAGE_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(c1s2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("%s: cannot raise dynamic shared memory: %s", who, cudaGetErrorString(e));
+      return HM_ERR_CUDA;
+    }
+    attr = true;
+  }
+  int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+  c1s2_bwd_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(tmW, p);
+  HM_CHECK_LAUNCH(who);
+  return HM_OK;
+}
+
 // Backward of hm_c1s2_conv's pooled form from the gradient g of the pooled tensor (see the kernel comment).
 //   dwk != NULL: dwk[256][64] fp32 += weight-gradient partials (caller zeroes; fold with hm_c1s2_bwd_fold);
 //   u   != NULL: u[B,H/2,W/2,64] = patch-space input gradient (needs wk2 = pack mode 16; fold with hm_c1s2_col2im);
@@ -762,45 +817,34 @@ extern "C" int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, con
     return HM_ERR_CUDA;
   }
   CbParams p;
-  p.B = B; p.H = H; p.W = W; p.Hq = H / 2; p.Wq = W / 2;
-  int bw = 1;
-  while (bw * 2 <= p.Wq && bw < 128) bw *= 2;
-  p.bw = bw; p.bh = 128 / bw;
-  p.tiles_x = (p.Wq + p.bw - 1) / p.bw;
-  p.tiles_y = (p.Hq + p.bh - 1) / p.bh;
-  p.n_tiles = B * p.tiles_x * p.tiles_y;
   p.act = act; p.slope = slope; p.want_dw = dwk ? 1 : 0; p.want_u = u ? 1 : 0;
   p.x = (const __half*)x; p.g = (const __half*)g; p.pl = (const __half*)pooled; p.idx = idx; p.dwk = dwk; p.u = (__half*)u;
   p.img_scale = img_scale;
-  CUtensorMap tmW;
-  {
-    cuuint64_t dims[2] = {64, 256};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 256};
-    cuuint32_t es[2] = {1, 1};
-    void* wp = const_cast<void*>(wk2 ? wk2 : g);         // unused (never dereferenced) without the input gradient
-    CUresult r = c1_encode_fn()(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wp, dims, strides, box, es,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("hm_c1s2_bwd: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-      return HM_ERR_CUDA;
-    }
+  p.plain = 0;
+  return c1s2_bwd_launch(p, B, H, W, wk2, stream, "hm_c1s2_bwd");
+}
+
+// Weight gradient of (nearest-2x -> conv5x5 'same', 64 -> 1 channel) from the one-channel dy: the same kernel with the
+// roles swapped -- the 6x6 stride-2 patches are gathered from dy, the 64-row operand is the low-res source itself:
+//   dwk[ci][u*6+v] += sum_q x[q][ci] * dy[2q-2+(u,v)]      (the gradient of pack mode 14's Wk; unpack mode 14 folds it
+// onto the 5x5 filter).  x is read once (128 B per source pixel) and nothing else is materialised.
+extern "C" int hm_c1s2_wgrad(const void* dy, const void* x, float* dwk, int B, int H, int W, void* stream) {
+  HM_CHECK_ARG(dy && x && dwk && B > 0 && H > 0 && W > 0, "hm_c1s2_wgrad: bad argument");
+  HM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "hm_c1s2_wgrad: dy must have even height and width (%dx%d)", H, W);
+  if ((((uintptr_t)dy) & 3) || (((uintptr_t)x) & 15)) {
+    set_error("hm_c1s2_wgrad: dy must be 4-byte, x 16-byte aligned");
+    return HM_ERR_ALIGN;
   }
-  const size_t smem = 1024 + 256 * 128 + 2 * CB_STAGE_BYTES + 2 * C1_PATCH_WORDS * 4 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(c1s2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_error("hm_c1s2_bwd: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-      return HM_ERR_CUDA;
-    }
-    attr = true;
+  if (!c1_encode_fn()) {
+    set_error("hm_c1s2_wgrad: cuTensorMapEncodeTiled is not available from this driver");
+    return HM_ERR_CUDA;
   }
-  int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-  c1s2_bwd_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(tmW, p);
-  HM_CHECK_LAUNCH("hm_c1s2_bwd");
-  return HM_OK;
+  CbParams p;
+  p.act = HM_ACT_LINEAR; p.slope = 0.f; p.want_dw = 1; p.want_u = 0;
+  p.x = (const __half*)dy; p.g = (const __half*)x; p.pl = nullptr; p.idx = nullptr; p.dwk = dwk; p.u = nullptr;
+  p.img_scale = nullptr;
+  p.plain = 1;
+  return c1s2_bwd_launch(p, B, H, W, nullptr, stream, "hm_c1s2_wgrad");
 }
 
 extern "C" int hm_c1s2_bwd_fold(const float* dwk, float* dw, float* db, int cout, void* stream) {

@@ -480,6 +480,22 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
                            : dwp[(size_t)(tap * cin + ci) * 64 + ph * cout + co];
       }
     dw[i] = acc;
+  } else if (mode == 14) {
+    // adjoint of pack mode 14 (Cout == 1): master W[0][ci][a][b] from dwp[ci][64] = the gradient of Wk[ci][u*6+v]
+    // (hm_c1s2_wgrad); tap (r,s) = (4-a, 4-b) enters the 6x6 entry of either phase once
+    int b = (int)(i % 5);
+    long long t = i / 5;
+    int a = (int)(t % 5);
+    int ci = (int)(t / 5);
+    int r = 4 - a, s = 4 - b;
+    float acc = 0.f;
+    for (int py = 0; py < 2; py++)
+      for (int px = 0; px < 2; px++) {
+        int dy_ = ((py + r - 2 + 4) >> 1) - 2 + 1, dx_ = ((px + s - 2 + 4) >> 1) - 2 + 1;   // 0..2
+        int uu = 2 * (2 - dy_) + py, vv = 2 * (2 - dx_) + px;
+        acc += dwp[(size_t)ci * 64 + uu * 6 + vv];
+      }
+    dw[i] = acc;
   } else if (mode == 17) {
     // master deconv W[ci][co][a][b] (2x2, stride 2) from dwp[ci][64], column (u*2+v)*cout + co, (u,v) = (1-a, 1-b):
     // the tensor-core weight gradient of x against hm_s2d_pad64(dy)
@@ -633,6 +649,7 @@ extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int c
                                     int kw, void* stream) {
   HM_CHECK_ARG(dwp && dw, "hm_unpack_conv_wgrad: null pointer");
   HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9 || mode == 10) && kh == 5 && kw == 5) ||
+                   (mode == 14 && kh == 5 && kw == 5 && cout == 1) ||
                    (mode == 17 && kh == 2 && kw == 2 && 4 * cout <= 64),
                "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;

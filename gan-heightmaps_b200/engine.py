@@ -474,7 +474,13 @@ class ConvOp(object):
         elif self.tc_dg and self.wt_d is None:
             self.wt_d = rt.empty((tcm * (16 * self.Cin * self.Cout if self.dg2 else n),), rt.tc_dtype)
         self.thin_up2_wg = self.up2 and self.Cout <= 4           # weight gradient of the thin phase-decomposed layer
-        if self.thin_up2_wg:
+        # ... which for the generator's last layer (64 -> 1) is the c1s2 gather with the roles swapped: 6x6 stride-2
+        # patches of the one-channel dy against the low-res source rows, nothing materialised (hm_c1s2_wgrad)
+        self.c1wg = self.thin_up2_wg and self.c1dg and os.environ.get("HMGAN_C1WG", "1") != "0"
+        if self.c1wg:
+            if self.dwp is None or self.dwp.numel() < 64 * 64:
+                self.dwp = rt.empty((64 * 64,), torch.float32)
+        elif self.thin_up2_wg:
             # tensor cores: s2d(dy) zero-padded to 64 channels against the low-res source (3x3 taps)
             self.dy64 = rt.empty((B, self.x1.shape[0], self.x1.shape[1], 64))
             if self.dwp is None or self.dwp.numel() < 9 * self.Cin * 64:
@@ -816,6 +822,9 @@ class ConvOp(object):
             d = self._col1_desc(rt, n)
             rt.call("hm_tc_wgrad", C.byref(d), _ptr(self.xc[lo:hi]), None, _ptr(g), _ptr(self.dwp))
             mode = 0              # rows [0, kh*kw*Cin) of the [64][Cout] result are the packed gradient
+        elif self.c1wg:
+            rt.call("hm_c1s2_wgrad", _ptr(g), x1, _ptr(self.dwp), n, self.Hv, self.Wv)
+            mode = 14
         elif self.thin_up2_wg:
             # dW of (nearest-2x -> 5x5 -> few channels): per output phase a 3x3 weight gradient on the low-res
             # source against the phase's strided slice of dy, folded back onto the 5x5 filter (unpack mode 9)

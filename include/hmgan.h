@@ -203,6 +203,12 @@ int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, const uint8_t*
                 void* u, const float* img_scale /* [B] or NULL: g of image b times img_scale[b] */, int B, int H, int W,
                 int act, float slope, void* stream);
 int hm_c1s2_bwd_fold(const float* dwk, float* dw, float* db, int cout, void* stream);
+/* Weight gradient of the generator's last layer (nearest-2x -> conv5x5 'same', 64 -> 1 channel; dcgan.py:31-32) from the
+ * one-channel dy[B,H,W] and the low-res source x[B,H/2,W/2,64]: the kernel of hm_c1s2_bwd with the roles swapped (6x6
+ * stride-2 patches of dy against the source rows), dwk[ci][u*6+v] (fp32 [64][64], caller zeroes) +=
+ * sum_q x[q][ci] * dy[2q-2+(u,v)] = the gradient of pack mode 14's operand; hm_unpack_conv_wgrad(mode 14) folds it onto
+ * the 5x5 filter.  x is read once; no regrouped copy of dy is materialised. */
+int hm_c1s2_wgrad(const void* dy, const void* x, float* dwk, int B, int H, int W, void* stream);
 int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
 
 /* Weight (un)packing between Lasagne master layout and the packed [K][Cout] layout.
@@ -227,7 +233,7 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  *          -> Wp[(r*kw+s)*Cout+co][ci] = W[co][ci][r][s]   (used when dy has <= 4 channels: thin-input kernel)
  * `dst_dtype` is the HmDType of the packed copy.  hm_unpack_conv_wgrad applies the
  * inverse index map of mode 0 / 2(all taps) / 4 to a packed fp32 gradient and
- * (over)writes the master-layout gradient. */
+ * (over)writes the master-layout gradient; modes 8 / 9 / 10 / 14 / 17 apply the ADJOINT of that pack (they sum). */
 int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                         int u, int v, int dst_dtype, void* stream);
 /* All packs of a network in one launch.  jobs_dev: n_jobs HmPackJob records in DEVICE memory (same fields as the

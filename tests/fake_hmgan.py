@@ -270,6 +270,19 @@ def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
                         gc[r, s_] += g3[(py + r - 2) // 2 + 1, (px + s_ - 2) // 2 + 1, :, py * 2 + px, :]
         dst[:] = np.ascontiguousarray(gc.transpose(3, 2, 0, 1)[:, :, ::-1, ::-1]).reshape(-1)
         return 0
+    if mode == 14:
+        assert cout == 1 and kh == 5 and kw == 5
+        g6 = _a(dwp, cin * 64, np.float32).reshape(cin, 64)
+        gc = np.zeros((cin, 5, 5), np.float32)                                   # correlation taps [ci][r][s]
+        for py in range(2):
+            for px in range(2):
+                for r in range(5):
+                    for s_ in range(5):
+                        uu = 2 * (2 - ((py + r - 2) // 2 + 1)) + py
+                        vv = 2 * (2 - ((px + s_ - 2) // 2 + 1)) + px
+                        gc[:, r, s_] += g6[:, uu * 6 + vv]
+        dst[:] = np.ascontiguousarray(gc[:, ::-1, ::-1]).reshape(-1)
+        return 0
     if mode == 17:
         g4 = _a(dwp, cin * 64, np.float32).reshape(cin, 64)[:, :4 * cout].reshape(cin, 2, 2, cout)   # [ci][u][v][co]
         dst[:] = np.ascontiguousarray(g4.transpose(0, 3, 1, 2)[:, :, ::-1, ::-1]).reshape(-1)
@@ -861,6 +874,19 @@ def hm_c1s2_bwd(x, g, pooled, idx, wk2, dwk, u, img_scale, B, H, W, act, slope, 
         w2 = _t(_a(wk2, 256 * 64, np.float16)).reshape(4, 64, 64)             # [d][k][co]
         U = torch.einsum("wdc,dkc->wk", G4.reshape(-1, 4, 64), w2)
         _a(u, n, np.float16)[:] = U.numpy().reshape(-1).astype(np.float16)
+    return 0
+
+
+def hm_c1s2_wgrad(dy, x, dwk, B, H, W, stream=None):
+    """dwk[ci][u*6+v] += sum_q x[q][ci] * dy[2q-2+(u,v)]  (column 36 collects sum_q x[q][ci], as the kernel's does)."""
+    Hq, Wq = H // 2, W // 2
+    a = _t(_a(dy, B * H * W, np.float16)).reshape(B, 1, H, W)
+    cols = F.unfold(a, (6, 6), padding=2, stride=2).permute(0, 2, 1).reshape(B * Hq * Wq, 36)
+    A = torch.zeros(B * Hq * Wq, 64)
+    A[:, :36] = cols
+    A[:, 36] = 1.0
+    xs = _t(_a(x, B * Hq * Wq * 64, np.float16)).reshape(B * Hq * Wq, 64)
+    _a(dwk, 64 * 64, np.float32)[:] += (xs.double().t() @ A.double()).float().numpy().reshape(-1)
     return 0
 
 

@@ -227,10 +227,37 @@ def test_fast_mode_lowering_uses_tensor_core_kernels_where_eligible(cpu_backend,
     # the one-channel ends: D's conv5x5(1->64)+LeakyReLU+max-pool in one pass (real+fake batch), and the input gradient of
     # G's nearest-2x -> conv5x5(64->1), both through hm_c1s2_conv
     assert calls.get("hm_c1s2_conv", 0) >= 2 and m.D.ops[0].pool_fused is not None and m.G.ops[-1].c1dg, calls
+    assert calls.get("hm_c1s2_wgrad", 0) == 1 and m.G.ops[-1].c1wg, calls      # ... and that layer's weight gradient
     paths = [op.path for op in m.G.ops + m.D.ops if hasattr(op, "path")]
     # every convolution of this model is on the tensor cores, the DenseLayer included (1x1 convolution, ragged K)
     # (hm_conv_gather remains for the input gradient of the discriminator's one-channel head)
     assert set(paths) == {"tcgen05"} and m.G.ops[0].dense_tc and calls.get("hm_conv_gather", 0) <= 1, (paths, calls)
+
+
+def test_generator_output_layer_weight_gradient_routes_agree(cpu_backend, monkeypatch):
+    """The weight gradient of G's last layer (nearest-2x -> conv5x5, 64 -> 1): hm_c1s2_wgrad + unpack mode 14 (6x6 stride-2
+    patches of dy against the low-res source) against the route it replaced (hm_s2d_pad64 + 3x3 phase weight gradient +
+    unpack mode 10), from identical states: the same dy and source, so the same gradient up to float32 summation order."""
+    cfg = dict(in_shp=64, latent_dim=32,
+               G=dict(nch=256, num_repeats=0, div=[2, 2, 4, 4]),
+               D=dict(nch=64, num_repeats=0, bn=False, nonlinearity='linear', div=[1, 1, 1, 1]))
+    Z, X, Y = S.synthetic_batch(2, cfg['latent_dim'], 64, seed=1)
+    grads = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("HMGAN_C1WG", knob)
+        om, m = build_pair(cfg, 'dcgan', with_p2p=False, precision="fast")
+        vals = m.D.get_all_param_values()
+        vals[-1][:] = 0.6                     # a live ReLU head: non-zero gradients
+        m.D.set_all_param_values(vals)
+        m.train_fn(Z, X, Y)
+        assert m.G.ops[-1].c1wg == (knob == "1")
+        tr = [q for q in m.G.params if q.trainable]
+        iw = max(i for i, q in enumerate(tr) if q.kind == "W")
+        assert tuple(tr[iw].shape) == (1, 64, 5, 5)
+        grads[knob] = m.G.get_grads()[iw]
+    a, b = grads["1"].ravel().astype(np.float64), grads["0"].ravel().astype(np.float64)
+    assert np.linalg.norm(b) > 0
+    assert np.linalg.norm(a - b) <= 1e-5 * np.linalg.norm(b), np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
 def test_fast_mode_stride2_layers_route_to_tensor_cores(cpu_backend, monkeypatch):

@@ -58,6 +58,16 @@ def test_c1s2_bwd_pooled_first_layer_gradients(case):
     assert rel <= 3e-3, line
 
 
+@pytest.mark.parametrize("case", tc_probe.C1B_CASES, ids=[c[0].replace("c1bwd", "c1wg") for c in tc_probe.C1B_CASES])
+def test_c1s2_wgrad_generator_output_layer(case):
+    """hm_c1s2_wgrad + hm_unpack_conv_wgrad(mode 14): the weight gradient of the generator's last layer (nearest-2x ->
+    conv5x5, 64 -> 1; reference architectures/dcgan.py:31-32) as 6x6 stride-2 patches of the one-channel dy against the
+    low-res source rows, against torch autograd in float32 on the same fp16 data: 1e-3 of the gradient's scale (fp16
+    operands are exact, fp32 accumulation over B*H*W/4 terms in tile order)."""
+    rel, line = tc_probe.run_c1wg_case(*case)
+    assert rel <= 1e-3, line
+
+
 @pytest.mark.parametrize("case", tc_probe.DC2_CASES, ids=[c[0] for c in tc_probe.DC2_CASES])
 def test_tc_deconv_2x2_stride2_all_phases(case):
     """Deconv2DLayer 2x2 stride 2 (pix2pix U-Net output layer, reference architectures/p2p.py:272) as one tensor-core

@@ -619,6 +619,29 @@ def run_c1_case(name, B, H, W, pooled):
     return err, "%-26s max_err/scale %.3g" % (name, err)
 
 
+def run_c1wg_case(name, B, H, W):
+    """hm_c1s2_wgrad + hm_unpack_conv_wgrad(mode 14): weight gradient of nearest-2x -> conv5x5(64 -> 1) (the generator's
+    output layer) from dy[B,H,W] and the low-res source x[B,H/2,W/2,64], against torch autograd in float32 on the same
+    fp16-rounded data.  Returns (max error / scale, line)."""
+    import torch.nn.functional as F
+    torch.manual_seed(abs(hash(name)) % 1000)
+    dy = torch.randn(B, H, W, device="cuda").half()
+    x = torch.randn(B, H // 2, W // 2, 64, device="cuda").half()
+    dwk = torch.zeros(64 * 64, device="cuda")
+    dw = torch.full((1, 64, 5, 5), 7.0, device="cuda")
+    _lib.call("hm_c1s2_wgrad", dy.data_ptr(), x.data_ptr(), dwk.data_ptr(), B, H, W, None)
+    _lib.call("hm_unpack_conv_wgrad", dwk.data_ptr(), dw.data_ptr(), 14, 1, 64, 5, 5, None)
+    torch.cuda.synchronize()
+    Wm = torch.zeros(1, 64, 5, 5, device="cuda", requires_grad=True)
+    xu = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    out = F.conv2d(xu, Wm.flip(2, 3), padding=2)                  # Lasagne's Conv2DLayer convolves (flipped filter)
+    out.backward(dy.float()[:, None])
+    ref = Wm.grad
+    scale = float(ref.abs().max())
+    err = float((dw - ref).abs().max()) / scale
+    return err, "%-26s max_err/scale %.3g" % (name, err)
+
+
 C1B_CASES = [
     # name, B, H, W
     ("c1bwd_64", 2, 64, 64),
