@@ -230,6 +230,9 @@ def measure(workload, B, steps, warmup, precision, local, rank, world, pg, sampl
     launches = m.rt.launches - l0
     clk = clocks.stop() if clocks else None
     losses = m.losses.cpu().numpy()
+    # share of the 2B discriminator outputs of the last timed step that are on the live side of the ReLU head: training on
+    # random data can kill the head again (D(.) -> 0), and a step that multiplies zeros is flattered
+    alive = float((m.D.out.buf[:2 * B].float() > 0).float().mean().item()) if m.D is not None else None
     # end to end through the public API: pinned host inputs, losses read back every step
     for _ in range(3):                    # the host path captures its own graphs on its third call
         m.train_fn(Zp, Xp, Yp)
@@ -253,7 +256,7 @@ def measure(workload, B, steps, warmup, precision, local, rank, world, pg, sampl
                     # only the tensors a model reads are copied (a DCGAN-only model never reads Y, a pix2pix-only one Z)
                     "h2d_bytes_per_step": int((Z.nbytes if with_z else 0) + X.nbytes + (Y.nbytes if with_y else 0)),
                     "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / steps},
-               gpu_launches=int(launches), clocks=clk, losses=[float(v) for v in losses],
+               gpu_launches=int(launches), clocks=clk, losses=[float(v) for v in losses], head_alive_frac=alive,
                step_achieved_tflops=step_tflops, step_frac_of_burst=step_tflops / pk["burst"],
                step_frac_of_sustained=step_tflops / pk["sustained"], replicas_identical=identical)
     return res, m
@@ -317,7 +320,31 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
+    def alive_frac(r):               # the least alive replica decides (every rank must take the same branch)
+        v = r["head_alive_frac"]
+        if v is None:
+            return 1.0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([v], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            v = float(t.item())
+        return v
+
     res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias)
+    remeasured = None
+    first = alive_frac(res)
+    if a.head_bias and first < 0.5:
+        # the discriminator's ReLU head died while training on random data: most gradients of that run were zeros and its
+        # time is that of an idle-data step.  Measure once more from a fresh model; the line reports the second run.
+        remeasured = {"why": "discriminator head died during the first run (share of live outputs %.2f)" % first,
+                      "first_run_ms_per_step": res["ms_per_step"]}
+        del m
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias)
+        alive_frac(res)
     out = None
     if rank == 0:
         pk = peaks()
@@ -342,7 +369,9 @@ def main():
                              "step_achieved": res["step_achieved_tflops"],
                              "step_frac_of_burst": res["step_frac_of_burst"],
                              "step_frac_of_sustained": res["step_frac_of_sustained"]},
-                   losses=res["losses"])
+                   losses=res["losses"], head_alive_frac=res["head_alive_frac"])
+        if remeasured:
+            out["remeasured"] = remeasured
         if world > 1:
             out["replicas_identical"] = res["replicas_identical"]
     del m
