@@ -122,7 +122,7 @@ def pack_count(mode, cout, cin, kh, kw):
     if mode == 2:
         return cin * cout
     return {8: 36 * cout * cin, 11: 64 * cout, 12: 16 * cout * cin, 14: 64 * cin, 15: 256 * cout, 16: 256 * cout,
-            17: 4 * cout * cin, 18: 64 * cin, 19: 64 * cout, 20: 36 * cout * cin}.get(mode, cout * cin * kh * kw)
+            17: 4 * cout * cin, 18: 64 * cin, 19: 64 * cout, 20: 36 * cout * cin, 22: 4 * cout * cin}.get(mode, cout * cin * kh * kw)
 
 
 def pack_job_table(jobs):

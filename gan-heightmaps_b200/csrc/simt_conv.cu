@@ -408,6 +408,13 @@ __device__ __forceinline__ void pack_elem(const float* __restrict__ w, T* __rest
       int ph = k / cout, co = k - ph * cout;
       val = w[(((size_t)ci * cout + co) * 2 + (1 - (ph >> 1))) * 2 + (1 - (ph & 1))];
     }
+  } else if (mode == 22) {
+    // mode 18 without the padding: Wt[ci][(u*2+v)*cout + co] = W[ci][co][1-u][1-v]   (K-major, K = 4*cout): the input
+    // gradient of a 2x2 deconvolution of a 1x1 input as a 1x1 convolution over dy viewed as [B,1,1,(u,v,co)]
+    int k = (int)(i % (4 * cout));
+    int ci = (int)(i / (4 * cout));
+    int ph = k / cout, co = k - ph * cout;
+    val = w[(((size_t)ci * cout + co) * 2 + (1 - (ph >> 1))) * 2 + (1 - (ph & 1))];
   } else {
     val = w[i];
   }
@@ -497,15 +504,16 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
       }
     dw[i] = acc;
   } else if (mode == 17) {
-    // master deconv W[ci][co][a][b] (2x2, stride 2) from dwp[ci][64], column (u*2+v)*cout + co, (u,v) = (1-a, 1-b):
-    // the tensor-core weight gradient of x against hm_s2d_pad64(dy)
+    // master deconv W[ci][co][a][b] (2x2) from dwp[ci][ld], column (u*2+v)*cout + co, (u,v) = (1-a, 1-b): the tensor-core
+    // weight gradient of x against hm_s2d_pad64(dy) (ld = 64) or, for the wide 1x1-input form, against dy (ld = 4*cout)
     int b = (int)(i % 2);
     long long t = i / 2;
     int a = (int)(t % 2);
     t /= 2;
     int co = (int)(t % cout);
     int ci = (int)(t / cout);
-    dw[i] = dwp[(size_t)ci * 64 + ((1 - a) * 2 + (1 - b)) * cout + co];
+    const int ld = 4 * cout <= 64 ? 64 : 4 * cout;
+    dw[i] = dwp[(size_t)ci * ld + ((1 - a) * 2 + (1 - b)) * cout + co];
   } else {
     dw[i] = dwp[i];
   }
@@ -592,7 +600,7 @@ static long long pack_count(int mode, int cout, int cin, int kh, int kw) {
   if (mode == 12) n = 16LL * cout * cin;
   if (mode == 14) n = 64LL * cin;
   if (mode == 15 || mode == 16) n = 256LL * cout;
-  if (mode == 17) n = 4LL * cout * cin;
+  if (mode == 17 || mode == 22) n = 4LL * cout * cin;
   if (mode == 18) n = 64LL * cin;
   if (mode == 19) n = 64LL * cout;
   if (mode == 20) n = 36LL * cout * cin;
@@ -622,13 +630,14 @@ extern "C" int hm_pack_conv_weight_multi(const HmPackJob* jobs_dev, int n_jobs, 
 extern "C" int hm_pack_conv_weight(const float* w, void* wp, int mode, int cout, int cin, int kh, int kw,
                                    int u, int v, int dst_dtype, void* stream) {
   HM_CHECK_ARG(w && wp, "hm_pack_conv_weight: null pointer");
-  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 21),
+  HM_CHECK_ARG((mode >= 0 && mode <= 8) || mode == 11 || mode == 12 || (mode >= 14 && mode <= 22),
                "hm_pack_conv_weight: bad mode %d", mode);
   HM_CHECK_ARG(mode != 14 || (cout == 1 && kh == 5 && kw == 5), "hm_pack_conv_weight: mode 14 needs Cout == 1 and a 5x5 filter");
   HM_CHECK_ARG((mode != 15 && mode != 16) || (cin == 1 && kh == 5 && kw == 5),
                "hm_pack_conv_weight: modes 15/16 need Cin == 1 and a 5x5 filter");
   HM_CHECK_ARG(mode != 16 || cout == 64, "hm_pack_conv_weight: mode 16 needs Cout == 64");
-  HM_CHECK_ARG((mode != 17 && mode != 18) || (kh == 2 && kw == 2), "hm_pack_conv_weight: modes 17/18 are defined for 2x2 filters");
+  HM_CHECK_ARG((mode != 17 && mode != 18 && mode != 22) || (kh == 2 && kw == 2),
+               "hm_pack_conv_weight: modes 17/18/22 are defined for 2x2 filters");
   HM_CHECK_ARG(mode != 18 || 4 * cout <= 64, "hm_pack_conv_weight: mode 18 needs 4*Cout <= 64");
   HM_CHECK_ARG(mode != 19 || kh * kw * cin <= 64, "hm_pack_conv_weight: mode 19 needs kh*kw*Cin <= 64");
   HM_CHECK_ARG(mode != 12 || (kh == 3 && kw == 3), "hm_pack_conv_weight: mode 12 is defined for 3x3 filters");
@@ -650,7 +659,7 @@ extern "C" int hm_unpack_conv_wgrad(const float* dwp, float* dw, int mode, int c
   HM_CHECK_ARG(dwp && dw, "hm_unpack_conv_wgrad: null pointer");
   HM_CHECK_ARG(mode == 0 || mode == 2 || mode == 4 || ((mode == 8 || mode == 9 || mode == 10) && kh == 5 && kw == 5) ||
                    (mode == 14 && kh == 5 && kw == 5 && cout == 1) ||
-                   (mode == 17 && kh == 2 && kw == 2 && 4 * cout <= 64),
+                   (mode == 17 && kh == 2 && kw == 2),
                "hm_unpack_conv_wgrad: bad mode %d", mode);
   long long n = (long long)cout * cin * kh * kw;
   unpack_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dwp, dw, mode, cout,

@@ -416,6 +416,16 @@ class ConvOp(object):
                 and not self.up and 4 * self.Cout <= 64 and self.C1 % 64 == 0 and self.C2 % 64 == 0):
             self.dc2 = bool(_lib.query("hm_tc_conv_supported", C.byref(self._dc2_desc(rt, 1))))
             self.tc_fwd = self.dc2
+        # Deconv2DLayer 2x2 on a 1x1 input (the U-Net's bottleneck, p2p.py:197-198): every output position sees the one input
+        # pixel, so the layer IS a dense layer in -> (u, v, co) and runs as 1x1 tensor-core GEMMs (forward with pack mode
+        # 17 and a bias tiled over the four positions, input gradient with pack mode 22, weight gradient + unpack mode 17)
+        self.dc1 = False
+        if (rt.precision == "fast" and kind == "deconv" and not self.dc2 and self.kh == 2 and self.kw == 2
+                and self.Hv == 1 and self.Wv == 1 and self.x2 is None and self.C1 % 64 == 0
+                and (4 * self.Cout) % 256 == 0 and os.environ.get("HMGAN_DC1", "1") != "0"):
+            self.dc1 = (rt.tc_supported(self._dc1_desc(rt, 1, True)) and rt.tc_supported(self._dc1_desc(rt, 1, False))
+                        and rt.tc_supported(self._dc1_desc(rt, 1, True), wgrad=True))
+            self.tc_fwd = self.dc1
         self.path = "tcgen05" if self.tc_fwd else "simt"
         # hm_c1s2_conv (in-kernel im2col of a one-channel image): (a) this layer + its 2x2 max-pool in one pass, set by
         # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
@@ -447,6 +457,10 @@ class ConvOp(object):
                 self.wt_f = rt.empty((4 * self.Cout * self.Cin,))
                 self.wt_d = rt.empty((64 * self.Cin,))
                 self.dwp = rt.empty((64 * self.Cin,), torch.float32)
+        if self.dc1 and self.wt_f is None:
+            self.wt_f = rt.empty((4 * self.Cout * self.Cin,))
+            self.wt_d = rt.empty((4 * self.Cout * self.Cin,))
+            self.bias4 = rt.empty((4, self.Cout), torch.float32)
         if self.c1dg and self.wk is None:
             self.wk = rt.empty((64 * 64,))
         if self.pool_fused is not None:
@@ -530,6 +544,10 @@ class ConvOp(object):
         elif self.dc2:
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 17, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
             rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 18, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
+        elif self.dc1:
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_f), 17, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
+            rt.call("hm_pack_conv_weight", _ptr(w), _ptr(self.wt_d), 22, self.Cout, self.Cin, 2, 2, 0, 0, rt.cd)
+            self.bias4.copy_(self.net.pview(self.bias).view(1, self.Cout).expand(4, self.Cout))
         else:
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -635,6 +653,22 @@ class ConvOp(object):
         d.accumulate = 0
         return d
 
+    def _dc1_desc(self, rt, n, fwd):
+        """The 2x2 deconvolution of a 1x1 input as a 1x1 convolution over [n,1,1,C]: forward Cin -> (u,v,co) columns, input
+        gradient (u,v,co) -> Cin."""
+        d = _lib.ConvDesc()
+        d.dtype = rt.cd
+        cin, cout = (self.Cin, 4 * self.Cout) if fwd else (4 * self.Cout, self.Cin)
+        d.B, d.H, d.W, d.C1, d.C2, d.up = n, 1, 1, cin, 0, 0
+        d.kh = d.kw = 1
+        d.stride, d.pad, d.transposed = 1, 0, 0
+        d.Ho, d.Wo, d.Cout = 1, 1, cout
+        d.oH, d.oW, d.os, d.ou, d.ov = 1, 1, 1, 0, 0
+        d.split = cout
+        d.act, d.slope = (ACT[self.act.name], self.act.slope) if fwd else (0, 0.0)
+        d.accumulate = 0
+        return d
+
     def _dg6_desc(self, rt, n, acc):
         """Input gradient of (nearest-2x -> 5x5 'same' conv) as a forward 6x6 stride-2 pad-2 convolution of dy
         [n, 2H, 2W, Cout] onto the low-res source grid [n, H, W, Cin] (weights: pack mode 20)."""
@@ -685,6 +719,9 @@ class ConvOp(object):
             rt.call("hm_tc_conv", C.byref(self._dense_desc(rt, n)), x1, None, _ptr(self.wt_f), bias, y, None)
         elif self.dc2:
             rt.call("hm_tc_conv", C.byref(self._dc2_desc(rt, n)), x1, x2, _ptr(self.wt_f), bias, y, None)
+        elif self.dc1:
+            rt.call("hm_tc_conv", C.byref(self._dc1_desc(rt, n, True)), x1, None, _ptr(self.wt_f), _ptr(self.bias4), y,
+                    None)
         elif self.kind == "deconv":
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -810,6 +847,11 @@ class ConvOp(object):
             d = self._dc2_1x1_desc(rt, n, self.C1, self.C2, 64)
             rt.call("hm_tc_wgrad", C.byref(d), x1, x2, _ptr(self.dy64[lo:hi]), _ptr(self.dwp))
             mode = 17
+        elif self.dc1:
+            d = self._dc1_desc(rt, n, True)
+            d.act = 0
+            rt.call("hm_tc_wgrad", C.byref(d), x1, None, _ptr(g), _ptr(self.dwp))      # dwp[ci][(u,v,co)]
+            mode = 17
         elif self.kind == "deconv":
             per = self.Cin * self.Cout
             for u in range(self.kh):
@@ -884,6 +926,10 @@ class ConvOp(object):
             d = self._dc2_1x1_desc(rt, n, 64, 0, self.Cin, split=self.C1, acc=acc)
             rt.call("hm_tc_conv", C.byref(d), _ptr(self.dy64[lo:hi]), None, _ptr(self.wt_d), None,
                     _ptr(self.x1.g(lo, hi)) if t1 else None, _ptr(self.x2.g(lo, hi)) if t2 else None)
+        elif self.dc1:
+            d = self._dc1_desc(rt, n, False)
+            d.accumulate = self.x1.take_acc()
+            rt.call("hm_tc_conv", C.byref(d), _ptr(g), None, _ptr(self.wt_d), None, _ptr(self.x1.g(lo, hi)), None)
         elif self.c1dg and t1 and not self.x1.gw:
             # dy[B,2H,2W,1] -> dx[B,H,W,64] in one pass (four 3x3 phase filters as a 6x6 stride-2 gather of dy)
             self.x1.gw = True

@@ -227,6 +227,11 @@ int hm_c1s2_col2im(const void* u, void* dx, int B, int H, int W, void* stream);
  *          convolution of dy landing directly on the low-res source grid -> Wt[(u*6+v)][ci][co] (K-major, K = co): the
  *          adjoint of the four 3x3 phase filters of mode 8; 36 taps on H x W pixels instead of 25 taps on 2H x 2W
  *          followed by hm_upsample2_bwd (mode 14 is its Cout == 1 case for hm_c1s2_conv)
+ *  mode 22: Deconv2DLayer W (Cin,Cout,2,2) -> Wt[ci][(u*2+v)*Cout+co] = W[ci][co][1-u][1-v] (K-major, K = 4*Cout): mode
+ *          18 without the padding.  A 2x2 deconvolution of a 1x1 input (the U-Net bottleneck, p2p.py:197-198) is a dense
+ *          layer Cin -> (u,v,co): forward = 1x1 hm_tc_conv with pack mode 17 (bias tiled over the four positions), input
+ *          gradient = 1x1 hm_tc_conv over dy[B,1,1,4*Cout] with this pack, weight gradient = 1x1 hm_tc_wgrad, whose
+ *          [ci][4*Cout] result hm_unpack_conv_wgrad(mode 17) takes with leading dimension 4*Cout (64 when 4*Cout <= 64)
  *  mode 21: DenseLayer W (in,out) -> Wt[co][ci] (K-major): the layer as a 1x1 tensor-core convolution over a [B,1,1,in]
  *          tensor; `in` may be any multiple of 8 (hm_tc_conv zero-fills the last 64-channel slice, e.g. latent_dim 1000)
  *  mode 7: Conv2DLayer W, the same input-gradient-as-forward form in the gather layout

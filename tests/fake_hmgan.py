@@ -229,6 +229,9 @@ def hm_pack_conv_weight(w, wp, mode, cout, cin, kh, kw, u, v, dst_dtype, stream=
         Wd = W.reshape(cin, cout, 2, 2)[:, :, ::-1, ::-1]
         out = np.zeros((cin, 64), np.float32)
         out[:, :4 * cout] = Wd.transpose(0, 2, 3, 1).reshape(cin, 4 * cout)        # [ci][(u,v,co)]
+    elif mode == 22:
+        Wd = W.reshape(cin, cout, 2, 2)[:, :, ::-1, ::-1]
+        out = Wd.transpose(0, 2, 3, 1).reshape(cin, 4 * cout)                      # [ci][(u,v,co)], unpadded mode 18
     elif mode == 7:
         out = W.reshape(cout, cin, kh, kw).transpose(2, 3, 0, 1)   # [r][s][co][ci]
     elif mode == 6:
@@ -284,7 +287,8 @@ def hm_unpack_conv_wgrad(dwp, dw, mode, cout, cin, kh, kw, stream=None):
         dst[:] = np.ascontiguousarray(gc[:, ::-1, ::-1]).reshape(-1)
         return 0
     if mode == 17:
-        g4 = _a(dwp, cin * 64, np.float32).reshape(cin, 64)[:, :4 * cout].reshape(cin, 2, 2, cout)   # [ci][u][v][co]
+        ld = 64 if 4 * cout <= 64 else 4 * cout
+        g4 = _a(dwp, cin * ld, np.float32).reshape(cin, ld)[:, :4 * cout].reshape(cin, 2, 2, cout)   # [ci][u][v][co]
         dst[:] = np.ascontiguousarray(g4.transpose(0, 3, 1, 2)[:, :, ::-1, ::-1]).reshape(-1)
         return 0
     if mode == 0:

@@ -66,7 +66,7 @@ def test_bad_arguments_are_reported_not_fatal(lib):
 def test_pack_element_counts_agree_between_python_and_the_library(lib):
     """_lib.pack_count (used to fill the HmPackJob table of hm_pack_conv_weight_multi) == hm_pack_conv_weight_count."""
     lib.hm_pack_conv_weight_count.restype = C.c_longlong
-    for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 14, 15, 16, 17, 18, 19):
+    for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 14, 15, 16, 17, 18, 19, 20, 21, 22):
         for (cout, cin, kh, kw) in ((64, 1, 5, 5), (128, 64, 5, 5), (3, 128, 2, 2), (64, 4, 3, 3), (1, 64, 5, 5)):
             assert _lib.pack_count(mode, cout, cin, kh, kw) == lib.hm_pack_conv_weight_count(mode, cout, cin, kh, kw), \
                 (mode, cout, cin, kh, kw)

@@ -296,6 +296,51 @@ def test_fast_mode_stride2_layers_route_to_tensor_cores(cpu_backend, monkeypatch
         assert np.linalg.norm((a - b).ravel()) <= 2e-2 * np.linalg.norm(b.ravel())
 
 
+def test_fast_mode_unet_bottleneck_deconv_is_a_dense_tensor_core_gemm(cpu_backend, monkeypatch):
+    """The U-Net's bottleneck (reference architectures/p2p.py:193-198): conv 2x2 'valid' (2x2 -> 1x1), LeakyReLU, then
+    Deconv2DLayer 2x2 stride 1 (1x1 -> 2x2).  In fast mode the deconvolution of the single input pixel runs as 1x1
+    tensor-core GEMMs -- forward with pack mode 17 and the bias tiled over the four output positions, input gradient with
+    pack mode 22, weight gradient + unpack mode 17 (leading dimension 4*Cout) -- instead of four SIMT gathers per pass.
+    Forward and every gradient against the float32 oracle ops (2e-2 in relative L2), and the route against the SIMT one."""
+    import lasagne_compat as LC
+    import engine
+    from oracle import lasagne_ops as LO
+    res = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("HMGAN_DC1", knob)
+        r = np.random.RandomState(5)
+        inp = LC.InputLayer((None, 64, 2, 2))
+        c9 = LC.NonlinearityLayer(LC.Conv2DLayer(inp, 128, 2, stride=1, pad='valid', nonlinearity=LC.linear), LC.leaky_rectify)
+        d1 = LC.TransposedConv2DLayer(c9, 64, 2, stride=1, nonlinearity=LC.linear)
+        rt = engine.Runtime("cpu", "fast", loss_scale=1.0)
+        net = engine.Net(rt, d1, name="neck", rng=r)
+        convs = [op for op in net.ops if isinstance(op, engine.ConvOp)]
+        assert convs[-1].kind == "deconv" and convs[-1].dc1 == (knob == "1") and convs[-1].path == ("tcgen05" if knob == "1" else "simt")
+        x = r.randn(3, 64, 2, 2).astype(np.float32)
+        net.ensure(3)
+        net.inputs[0].buf.copy_(torch.from_numpy(x.transpose(0, 2, 3, 1)).half())
+        vals = net.get_all_param_values()
+        vals[3][:] = r.randn(*vals[3].shape).astype(np.float32) * 0.1            # a non-zero bias (tiled over the positions)
+        net.set_all_param_values(vals)
+        y = net.forward(3)
+        W1, b1, W2, b2 = [torch.tensor(v, requires_grad=True) for v in net.get_all_param_values()]
+        xt = torch.tensor(x)
+        ref = LO.deconv2d(LO.leaky_rectify(LO.conv2d(xt, W1, b1, 1, "valid"), 0.01), W2, b2, 1)
+        assert tuple(ref.shape) == (3, 64, 2, 2)
+        np.testing.assert_allclose(y.float().numpy(), ref.detach().permute(0, 2, 3, 1).numpy(), rtol=2e-2, atol=2e-2)
+        gy = r.randn(*ref.shape).astype(np.float32)
+        ref.backward(torch.tensor(gy))
+        net.out.grad.copy_(torch.from_numpy(gy.transpose(0, 2, 3, 1)).half())
+        net.backward(0, 3, wgrad=True)
+        g = net.get_grads()
+        for a, b in zip(g, (W1.grad, b1.grad, W2.grad, b2.grad)):
+            e = np.linalg.norm((a - b.numpy()).ravel()) / (np.linalg.norm(b.numpy().ravel()) + 1e-30)
+            assert e <= 2e-2, (a.shape, e)
+        res[knob] = [y.float().numpy().copy()] + [a.copy() for a in g]
+    for a, b in zip(res["1"], res["0"]):
+        assert np.linalg.norm((a - b).ravel()) <= 2e-3 * np.linalg.norm(b.ravel())
+
+
 def test_fast_mode_unet_ends_route_to_tensor_cores(cpu_backend):
     """The pix2pix ends in fast mode: a thin-source 3x3 stride-2 convolution over a ConcatLayer of a 1- and a 3-channel
     image (PatchGAN layer 1, reference architectures/p2p.py:279-285) runs as hm_im2col_thin + 1x1 tensor-core GEMMs, and

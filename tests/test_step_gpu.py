@@ -431,3 +431,50 @@ def test_host_path_graphs_equal_the_eager_schedule(mode, monkeypatch):
         del m
         torch.cuda.empty_cache()
     np.testing.assert_allclose(res["1"], res["0"], rtol=5e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_unet_bottleneck_deconv_on_tensor_cores_equals_the_simt_route(monkeypatch):
+    """The U-Net bottleneck at its real width (reference architectures/p2p.py:193-198: conv 2x2 'valid' 512 -> 512 on a
+    2x2 map, LeakyReLU, Deconv2DLayer 2x2 stride 1 512 -> 512 on the 1x1 map), batch 16, fast mode: the deconvolution as
+    1x1 tcgen05 GEMMs with N = (u, v, co) = 2048 columns (pack modes 17 / 22, unpack mode 17 with leading dimension 2048)
+    against the four-SIMT-gathers route (HMGAN_DC1=0) on the same fp16 data: output, input gradient (through the conv's
+    weight gradient) and both layers' gradients within 3e-3 in relative L2; and against the float32 oracle ops (2e-2)."""
+    import lasagne_compat as LC
+    import engine
+    from oracle import lasagne_ops as LO
+    res = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("HMGAN_DC1", knob)
+        r = np.random.RandomState(5)
+        inp = LC.InputLayer((None, 512, 2, 2))
+        c9 = LC.NonlinearityLayer(LC.Conv2DLayer(inp, 512, 2, stride=1, pad='valid', nonlinearity=LC.linear), LC.leaky_rectify)
+        d1 = LC.TransposedConv2DLayer(c9, 512, 2, stride=1, nonlinearity=LC.linear)
+        rt = engine.Runtime("cuda", "fast", loss_scale=1.0)
+        net = engine.Net(rt, d1, name="neck", rng=r)
+        convs = [op for op in net.ops if isinstance(op, engine.ConvOp)]
+        assert convs[-1].dc1 == (knob == "1")
+        x = r.randn(16, 512, 2, 2).astype(np.float32)
+        net.ensure(16)
+        net.inputs[0].buf.copy_(torch.from_numpy(x.transpose(0, 2, 3, 1)).half())
+        vals = net.get_all_param_values()
+        vals[3][:] = r.randn(*vals[3].shape).astype(np.float32) * 0.1
+        net.set_all_param_values(vals)
+        y = net.forward(16)
+        gy = r.randn(16, 512, 2, 2).astype(np.float32)
+        net.out.grad.copy_(torch.from_numpy(gy.transpose(0, 2, 3, 1)).half())
+        net.backward(0, 16, wgrad=True)
+        torch.cuda.synchronize()
+        res[knob] = [y.float().cpu().numpy().copy()] + [a.copy() for a in net.get_grads()]
+        if knob == "1":
+            W1, b1, W2, b2 = [torch.tensor(v, requires_grad=True) for v in net.get_all_param_values()]
+            ref = LO.deconv2d(LO.leaky_rectify(LO.conv2d(torch.tensor(x), W1, b1, 1, "valid"), 0.01), W2, b2, 1)
+            ref.backward(torch.tensor(gy))
+            refs = [ref.detach().permute(0, 2, 3, 1).numpy()] + [t.grad.numpy() for t in (W1, b1, W2, b2)]
+            for a, b in zip(res[knob], refs):
+                e = np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30)
+                assert e <= 2e-2, (a.shape, e)
+        del net
+    for a, b in zip(res["1"], res["0"]):
+        e = np.linalg.norm((a - b).ravel()) / (np.linalg.norm(b.ravel()) + 1e-30)
+        assert e <= 3e-3, (a.shape, e)
