@@ -113,7 +113,7 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
-def build_model(workload, device, precision, pg=None, verbose=False):
+def build_model(workload, device, precision, pg=None, verbose=False, lr=1e-4):
     from architectures import p2p, dcgan
     from lasagne_compat import linear, tanh, rmsprop, shared, floatX
     from pix2pix import Pix2Pix
@@ -127,7 +127,7 @@ def build_model(workload, device, precision, pg=None, verbose=False):
         gen_params_p2p={'nf': 64, 'act': tanh, 'num_repeats': 0, 'bilinear_upsample': True},
         disc_params_p2p={'nf': 64, 'bn': False, 'num_repeats': 0, 'act': linear, 'mul_factor': [1, 2, 4, 8]},
         in_shp=512, latent_dim=1000, is_a_grayscale=True, is_b_grayscale=False, lsgan=True, opt=rmsprop,
-        opt_args={'learning_rate': shared(floatX(1e-4))}, train_mode=workload, verbose=verbose,
+        opt_args={'learning_rate': shared(floatX(lr))}, train_mode=workload, verbose=verbose,
         device=device, precision=precision, seed=2, process_group=pg)
 
 
@@ -189,11 +189,11 @@ def cpu_baseline(workload, sample_b, steps=1, warmup=1):
     return sample_b / dt, dt
 
 
-def measure(workload, B, steps, warmup, precision, local, rank, world, pg, sample_clocks, head_bias=0.6):
+def measure(workload, B, steps, warmup, precision, local, rank, world, pg, sample_clocks, head_bias=0.6, lr=1e-4):
     """Build the model of `workload`, run W warm-up + K timed steps device-resident and again end to end from pinned
     host memory.  Returns (result dict, model)."""
     import torch.distributed as dist
-    m = build_model(workload, "cuda:%d" % local, precision, pg)
+    m = build_model(workload, "cuda:%d" % local, precision, pg, lr=lr)
     liven_head(m, head_bias)
     from util import synthetic_batch
     Z, X, Y = synthetic_batch(B, 1000, 512, seed=100 + rank)
@@ -274,6 +274,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] / configs[4] lines")
     ap.add_argument("--cpu-sample", type=int, default=4)
+    ap.add_argument("--lr", type=float, default=1e-8,
+                    help="RMSprop learning rate of the timed steps.  The default keeps the model at its initialisation: at the "
+                         "experiment's 1e-4 the DCGAN discriminator's ReLU head dies within ~20 steps on random data (D(.) = 0, "
+                         "all-zero gradients) and the step is then timed on zeros.  The optimiser kernels do the same work.")
     ap.add_argument("--head-bias", type=float, default=0.6,
                     help="bias of the DCGAN discriminator's head (0 = leave the Glorot init: dead head, all-zero gradients)")
     a = ap.parse_args()
@@ -286,7 +290,8 @@ def main():
               "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
               "precision": a.precision,
               "init": "Glorot-uniform (seed 2); DCGAN discriminator head bias %g so that its ReLU head is alive and the "
-                      "step moves dense gradients" % a.head_bias if a.head_bias else "Glorot-uniform (seed 2)"}
+                      "step moves dense gradients" % a.head_bias if a.head_bias else "Glorot-uniform (seed 2)",
+              "lr": a.lr}
     base = {"metric": "512px heightmap+texture images/sec/GPU at 1/2/4/8 B200; tensor-pipe %",
             "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": config}
@@ -331,7 +336,7 @@ def main():
             v = float(t.item())
         return v
 
-    res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias)
+    res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias, a.lr)
     remeasured = None
     first = alive_frac(res)
     if a.head_bias and first < 0.5:
@@ -343,7 +348,7 @@ def main():
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias)
+        res, m = measure(a.workload, B, a.steps, a.warmup, a.precision, local, rank, world, pg, True, a.head_bias, a.lr)
         alive_frac(res)
     out = None
     if rank == 0:
@@ -382,7 +387,7 @@ def main():
     if not a.no_secondary and a.workload == "dcgan" and not a.batch:
         sec = {}
         for wl in ("both", "p2p"):
-            r2, m2 = measure(wl, BATCH[wl], min(a.steps, 20), a.warmup, a.precision, local, rank, world, pg, False, a.head_bias)
+            r2, m2 = measure(wl, BATCH[wl], min(a.steps, 20), a.warmup, a.precision, local, rank, world, pg, False, a.head_bias, a.lr)
             del m2
             torch.cuda.empty_cache()
             ok = ok and r2["replicas_identical"]
