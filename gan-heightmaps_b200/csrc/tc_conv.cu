@@ -270,15 +270,11 @@ __device__ __forceinline__ void d2s_thin_store(const TcParams& p, const uint32_t
   }
 }
 
-// The whole epilogue role: for every tile of this CTA wait for the accumulator, drain it, release it.
-// pair_rank < 0: single-CTA kernels (work items blockIdx.x, +gridDim.x, ...; tempty0 is a local barrier).
-// pair_rank = 0/1: CTA pair (cta_group::2): work items are shared by the pair, this CTA owns sub-tiles
-// [ (2*st + rank)*S, +S ) of super tile st, and releases the accumulator on the LEADER's barrier (tempty0 is then a
-// shared::cluster address).
+// The whole epilogue role: for every tile of this CTA (work items blockIdx.x, +gridDim.x, ...) wait for the accumulator,
+// drain it, release it.
 template <int ACT, bool OUT32 = false>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                              const float* bias_s, int warp, int lane, int total_tiles,
-                                              int pair_rank = -1) {
+                                              const float* bias_s, int warp, int lane, int total_tiles) {
   const int q = warp & 3;                                   // TMEM lane quarter this warp may access
   const int row = q * 32 + lane;
   const int px_per_img = p.bw * p.bh;
@@ -286,11 +282,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   const int rem = row - in * px_per_img;
   const int iy = rem / p.bw, ix = rem - iy * p.bw;
   int it = 0;
-  const int t0 = pair_rank < 0 ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
-  const int tstep = pair_rank < 0 ? (int)gridDim.x : (int)(gridDim.x >> 1);
-  for (int t = t0; t < total_tiles; t += tstep, it++) {
+  for (int t = (int)blockIdx.x; t < total_tiles; t += (int)gridDim.x, it++) {
     const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
-    const int mt0 = pair_rank < 0 ? st * p.S : (2 * st + pair_rank) * p.S;
+    const int mt0 = st * p.S;
     const int nv = max(0, min(p.S, p.n_mtiles - mt0));
     const int acc = it & 1;
     mbar_wait(tfull0 + 8u * acc, (it >> 1) & 1);
@@ -498,20 +492,14 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
    }
     tc_fence_before();
     __syncwarp();
-    if (elect_one()) {
-      if (pair_rank < 0)
-        mbar_arrive(tempty0 + 8u * acc);
-      else
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty0 + 8u * acc) : "memory");
-    }
+    if (elect_one()) mbar_arrive(tempty0 + 8u * acc);
   }
 }
 
 // activation / output-type dispatch of the epilogue role
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
-                                                  const float* bias_s, int warp, int lane, int total_tiles,
-                                                  int pair_rank = -1) {
-#define HM_EPI(A_, O_) epilogue_loop<A_, O_>(p, tmem_base, tfull0, tempty0, bias_s, warp, lane, total_tiles, pair_rank)
+                                                  const float* bias_s, int warp, int lane, int total_tiles) {
+#define HM_EPI(A_, O_) epilogue_loop<A_, O_>(p, tmem_base, tfull0, tempty0, bias_s, warp, lane, total_tiles)
   if (p.out32) {
     switch (p.act) {
       case HM_ACT_LRELU: HM_EPI(HM_ACT_LRELU, true); break;
@@ -945,218 +933,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// CTA-pair variant of the row-box kernel (tcgen05 cta_group::2, cluster of two CTAs on two SMs).
-// The SS-mode MMA is bound by shared-memory operand bandwidth (~64 B/clk/SM measured): an
-// M=128,N,K=16 MMA reads 4096 + 32 N bytes per N/2 cycles.  With cta_group::2 one instruction computes M = 256 rows
-// (128 per CTA, each from its own shared memory and into its own TMEM) and every CTA supplies only HALF of the N
-// weight rows, so the per-SM operand traffic drops to 4096 + 16 N bytes per N/2 cycles and the weight ring to half.
-//   * both CTAs run a TMA producer for their own pixels and their half of each weight slice; every load signals the
-//     LEADER's (rank 0) full barriers (cp.async.bulk.tensor ... cta_group::2 with the leader's barrier address);
-//   * only the leader issues tcgen05.mma.cta_group::2; tcgen05.commit ... multicast::cluster frees the stages in
-//     both CTAs and publishes the accumulators to both epilogues;
-//   * the epilogue warps of both CTAs release the accumulator on the leader's barrier (count 8).
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* tm, uint32_t dst, uint32_t leader_bar, int c0, int c1,
-                                                 int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* tm, uint32_t dst, uint32_t leader_bar, int c0, int c1,
-                                                 int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` (same offset) in both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// kind::f16 instruction descriptor for the pair: M = 256 (128 rows per CTA), N = n
-__host__ __device__ constexpr uint32_t umma_idesc_f16_pair(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-    tc_conv_rb2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_slot_bytes = p.S * p.rb_bytes;
-  const uint32_t b_slot_bytes = (p.ntile / 2) * 128;                 // this CTA's half of a weight slice
-  const uint32_t b_base = base + p.a_slots * a_slot_bytes;
-  const uint32_t ctrl = b_base + p.b_slots * b_slot_bytes;
-  auto afull = [&](int s) { return ctrl + 8u * s; };
-  auto aempty = [&](int s) { return ctrl + 8u * (p.a_slots + s); };
-  auto bfull = [&](int s) { return ctrl + 8u * (2 * p.a_slots + s); };
-  auto bempty = [&](int s) { return ctrl + 8u * (2 * p.a_slots + p.b_slots + s); };
-  auto tfull_bar = [&](int a) { return ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + a); };
-  auto tempty_bar = [&](int a) { return ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + 2 + a); };
-  const uint32_t tmem_slot = ctrl + 8u * (2 * p.a_slots + 2 * p.b_slots + 4);
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_p = (volatile uint32_t*)(gen_base + (tmem_slot - base));
-  float* bias_s = (float*)(gen_base + (ctrl - base) + 1024);
-  {
-    const int ncols = p.n_ntiles * p.ntile;
-    const int creal = p.d2s ? p.cph : p.Cout;
-    for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
-      const int c = p.d2s ? i % p.cph : i;
-      bias_s[i] = (p.bias && c < creal && (!p.d2s || i < 4 * p.cph)) ? p.bias[c] : 0.f;
-    }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int acc_cols = p.S * p.ntile;
-  const int tmem_cols = 2 * acc_cols <= 128 ? 128 : (2 * acc_cols <= 256 ? 256 : 512);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_slots; s++) {
-      mbar_init(afull(s), 1);
-      mbar_init(aempty(s), 1);
-    }
-    for (int s = 0; s < p.b_slots; s++) {
-      mbar_init(bfull(s), 1);
-      mbar_init(bempty(s), 1);
-    }
-    for (int a = 0; a < 2; a++) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);                        // four epilogue warps in each CTA of the pair
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                                     // both CTAs' barriers exist before any remote signal
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_p;
-  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-  const int total_tiles = p.n_super * p.n_ntiles;        // n_super counts super tiles of 2*S M tiles here
-  const int cchunks = p.Cin / KCH;
-  const uint32_t box_bytes = (uint32_t)(TILE_M + p.kw - 1) * 128u;
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (elect_one()) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int t = pair; t < total_tiles; t += n_pairs) {
-        const int st = t / p.n_ntiles, nt = t - st * p.n_ntiles;
-        const int mt0 = (2 * st + (int)rank) * p.S;
-        for (int r = 0; r < p.kh; r++) {
-          for (int cc = 0; cc < cchunks; cc++) {
-            const int c = cc * KCH;
-            mbar_wait(aempty(as), aph ^ 1);
-            const uint32_t lead_afull = mapa_shared(afull(as), 0);
-            if (rank == 0) mbar_expect_tx(afull(as), 2u * p.S * box_bytes);
-            // (tiles past the end of the list load out-of-bounds boxes: zero fill, same byte count)
-#pragma unroll 1
-            for (int i = 0; i < p.S; i++) {
-              const int mt = mt0 + i;
-              const int ox = (mt % p.tiles_x) * p.bw - p.pad;
-              const int oy = (mt / p.tiles_x) % p.tiles_y - p.pad + r;
-              const int on = mt / (p.tiles_x * p.tiles_y);
-              const uint32_t dst = base + as * a_slot_bytes + i * p.rb_bytes;
-              if (c < p.C1)
-                tma_load_4d_pair(&tmA, dst, lead_afull, c, ox, oy, on);
-              else
-                tma_load_4d_pair(&tmA2, dst, lead_afull, c - p.C1, ox, oy, on);
-            }
-            if (++as == p.a_slots) { as = 0; aph ^= 1; }
-            for (int s = 0; s < p.kw; s++) {
-              mbar_wait(bempty(bs), bph ^ 1);
-              if (rank == 0) mbar_expect_tx(bfull(bs), 2u * b_slot_bytes);
-              tma_load_3d_pair(&tmB, b_base + bs * b_slot_bytes, mapa_shared(bfull(bs), 0), c,
-                               nt * p.ntile + (int)rank * (p.ntile / 2), r * p.kw + s);
-              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && elect_one()) {
-      const uint32_t idesc = umma_idesc_f16_pair(p.ntile);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int it = 0;
-      for (int t = pair; t < total_tiles; t += n_pairs, it++) {
-        const int acc = it & 1;
-        mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_cols;
-        bool first = true;
-        for (int r = 0; r < p.kh; r++) {
-          for (int cc = 0; cc < cchunks; cc++) {
-            mbar_wait(afull(as), aph);
-            tc_fence_after();
-            const uint32_t a_addr = base + as * a_slot_bytes;
-            for (int s = 0; s < p.kw; s++) {
-              mbar_wait(bfull(bs), bph);
-              tc_fence_after();
-              const uint64_t bd = umma_desc_k_sw128(b_base + bs * b_slot_bytes);
-              for (int i = 0; i < p.S; i++) {
-                const uint64_t ad = umma_desc_k_sw128(a_addr + i * p.rb_bytes + s * 128);
-#pragma unroll
-                for (int k = 0; k < KCH / 16; k++)
-                  tc_mma_f16_pair(d_tmem + i * p.ntile, ad + 2 * k, bd + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-              }
-              first = false;
-              tc_commit_pair(bempty(bs));
-              if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
-            }
-            tc_commit_pair(aempty(as));
-            if (++as == p.a_slots) { as = 0; aph ^= 1; }
-          }
-        }
-        tc_commit_pair(tfull_bar(acc));
-      }
-    }
-  } else {
-    const uint32_t lead_tempty = mapa_shared(tempty_bar(0), 0);
-    epilogue_dispatch(p, tmem_base, tfull_bar(0), lead_tempty, bias_s, warp, lane, total_tiles, (int)rank);
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                                     // nobody's TMEM / barriers are in use by the peer any more
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-  }
-}
+// (A CTA-pair variant of the row-box kernel -- tcgen05 cta_group::2, M = 256 over a cluster of two CTAs, each supplying
+// half of the weight rows -- was written and validated in round 1 and measured 3-8 % SLOWER than this kernel on every
+// layer, N = 64 included (profiles/r1_tc_pair_experiment.txt); it was removed in round 2.)
 
 // ---- split-K variant for the small layers ------------------------------------------------------------------------
 // (hm_tc_conv_ws with a caller workspace.  Written from the round-1 launch list, where the 4x4..16x16 layers ran
@@ -1655,7 +1434,7 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   p.idx = pool_idx;
   p.ntile = p.pool ? pool_ntile(p.Cout) : pick_ntile(p.Cout, up2 ? p.Cout : d->split);
   p.n_ntiles = (p.Cout + p.ntile - 1) / p.ntile;
-  // the kernels keep the bias of every GEMM column in shared memory: 2048 columns for the row-box / pair variants, up to
+  // the kernels keep the bias of every GEMM column in shared memory: 2048 columns for the row-box variant, up to
   // 8192 (a DenseLayer's width) for the plain kernel, which only small spatial extents reach
   const int ncols_pad = p.n_ntiles * p.ntile;
   const bool wide = ncols_pad > 2048;
@@ -1703,64 +1482,6 @@ static int tc_conv_impl(const HmConvDesc* d, const void* x1, const void* x2, con
   if (rb_enabled < 0) {
     const char* e = getenv("HMGAN_TC_ROWBOX");
     rb_enabled = (e && e[0] == '0') ? 0 : 1;
-  }
-  // CTA-pair (cta_group::2) row-box variant: N tiles of 64..256 columns, enough tiles for 74 pairs
-  static int pair_enabled = -1;
-  if (pair_enabled < 0) {
-    // validated (tools/tc_probe.py, tests) but measured 3-8 % SLOWER than the single-CTA kernel on these layers
-    // (profiles/r1_tc_pair_experiment.txt), so it is opt-in
-    const char* e = getenv("HMGAN_TC_PAIR");
-    pair_enabled = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (rb_enabled && pair_enabled && !p.bf16 && !p.pool && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9 &&
-      p.ntile >= 64 && p.ntile % 32 == 0 && (num_sms() % 2) == 0) {
-    TcParams q = p;
-    int S2 = 256 / q.ntile;
-    if (S2 < 1) S2 = 1;
-    if (S2 > 4) S2 = 4;
-    {
-      const char* e = getenv("HMGAN_TC_SMAX");
-      if (e && atoi(e) >= 1 && S2 > atoi(e)) S2 = atoi(e);
-    }
-    const int n_pairs = num_sms() / 2;
-    while (S2 > 1 && ((q.n_mtiles + 2 * S2 - 1) / (2 * S2)) * q.n_ntiles < n_pairs) S2 >>= 1;
-    if (((q.n_mtiles + 2 * S2 - 1) / (2 * S2)) * q.n_ntiles >= n_pairs) {
-      q.S = S2;
-      q.n_super = (q.n_mtiles + 2 * S2 - 1) / (2 * S2);
-      q.rb_bytes = (((TILE_M + q.kw - 1) * 128) + 1023) / 1024 * 1024;
-      q.a_slots = (S2 * q.rb_bytes > 40 * 1024) ? 2 : 3;
-      const int b_slot = (q.ntile / 2) * 128;
-      int b_slots = (227 * 1024 - 10240 - q.a_slots * S2 * q.rb_bytes) / b_slot;
-      if (b_slots > 12) b_slots = 12;
-      if (b_slots >= 2) {
-        q.b_slots = b_slots;
-        CUtensorMap rA, rA2, hB;
-        rc = encode_act(&rA, x1, d->B, d->H, d->W, d->C1, TILE_M + q.kw - 1, 1, 1);
-        if (!rc) rc = d->C2 ? encode_act(&rA2, x2, d->B, d->H, d->W, d->C2, TILE_M + q.kw - 1, 1, 1) : 0;
-        if (!d->C2) rA2 = rA;
-        if (!rc) rc = encode_wgt(&hB, w_tc, q.kh * q.kw, q.Cout, cin_real, q.ntile / 2);
-        if (rc) {
-          set_error("hm_tc_conv: cuTensorMapEncodeTiled failed for the pair variant (CUresult %d)", rc);
-          return HM_ERR_CUDA;
-        }
-        const size_t smem_p = (size_t)q.a_slots * S2 * q.rb_bytes + (size_t)q.b_slots * b_slot + 1024 + 1024 + 8192;
-        static bool pair_attr = false;
-        if (!pair_attr) {
-          cudaError_t e = cudaFuncSetAttribute(tc_conv_rb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-          if (e != cudaSuccess) {
-            set_error("hm_tc_conv: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
-            return HM_ERR_CUDA;
-          }
-          pair_attr = true;
-        }
-        int grid_p = q.n_super * q.n_ntiles * 2;
-        if (grid_p > num_sms()) grid_p = num_sms();
-        // at least 120 KB of dynamic shared memory keeps one CTA (which may own all 512 TMEM columns) per SM
-        tc_conv_rb2_kernel<<<grid_p, TC_THREADS, smem_p < 120 * 1024 ? 120 * 1024 : smem_p, (cudaStream_t)stream>>>(rA, rA2, hB, q);
-        HM_CHECK_LAUNCH("hm_tc_conv(row box, CTA pair)");
-        return HM_OK;
-      }
-    }
   }
   if ((rb_enabled || p.pool) && p.stride == 1 && p.bw == TILE_M && p.bh == 1 && p.bn == 1 && p.kw > 1 && p.kw <= 9) {
     p.rb_bytes = (((TILE_M + p.kw - 1) * 128) + 1023) / 1024 * 1024;
