@@ -150,7 +150,8 @@ def test_pack_unpack(mode, shape, dtype):
 @pytest.mark.parametrize("mode,shape", [(5, (64, 96, 3, 3)), (6, (64, 96, 3, 3)), (5, (40, 33, 5, 5)), (6, (40, 33, 5, 5)),
                                         (5, (128, 64, 1, 1)), (6, (96, 64, 2, 2)), (0, (64, 96, 3, 3)),
                                         (0, (40, 33, 5, 5)), (20, (64, 64, 5, 5)), (21, (48, 40, 1, 1)),
-                                        (8, (32, 64, 5, 5)), (12, (64, 64, 3, 3))])
+                                        (8, (32, 64, 5, 5)), (12, (64, 64, 3, 3)), (22, (64, 128, 2, 2)),
+                                        (17, (64, 128, 2, 2))])
 @pytest.mark.parametrize("dtype", [0, 1])
 def test_tensor_core_packs(mode, shape, dtype):
     """The K-major tensor-core packs (modes 5 / 6, the phase packs 8 / 12 / 20, the dense pack 21) and the un-pack mode 0
@@ -172,6 +173,31 @@ def test_tensor_core_packs(mode, shape, dtype):
     wp = bo.t(np.zeros(n), TD[dtype])
     bo.run("hm_pack_conv_weight", lambda P: (P(w), P(wp), mode, cout, cin, kh, kw, 0, 0, dtype))
     bo.check(wp, 1e-3 if dtype else (1e-6 if mode in (8, 20) else 0.0), "pack mode %d %r" % (mode, shape))
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_all_packs_of_a_network_in_one_launch(dtype):
+    """hm_pack_conv_weight_multi (an HmPackJob table in device memory, one launch) against one hm_pack_conv_weight call
+    per job on the GPU: bit-identical packed copies for a mix of modes and sizes (the job table's element counts come from
+    _lib.pack_count)."""
+    r = np.random.RandomState(3)
+    specs = [(5, 128, 64, 5, 5), (6, 128, 64, 5, 5), (15, 64, 1, 5, 5), (8, 64, 64, 5, 5), (22, 64, 128, 2, 2),
+             (17, 64, 128, 2, 2), (21, 96, 40, 1, 1)]
+    ws, one, multi, jobs = [], [], [], []
+    for (mode, cout, cin, kh, kw) in specs:
+        w = torch.from_numpy(r.randn(cout * cin * kh * kw).astype(np.float32)).cuda()
+        n = _lib.pack_count(mode, cout, cin, kh, kw)
+        a = torch.zeros(n, dtype=TD[dtype], device="cuda")
+        b = torch.full((n,), 7.0, dtype=TD[dtype], device="cuda")
+        _lib.call("hm_pack_conv_weight", w.data_ptr(), a.data_ptr(), mode, cout, cin, kh, kw, 0, 0, dtype, None)
+        jobs.append((w.data_ptr(), b.data_ptr(), mode, cout, cin, kh, kw, 0, 0, dtype))
+        ws.append(w), one.append(a), multi.append(b)
+    raw, max_n = _lib.pack_job_table(jobs)
+    tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    _lib.call("hm_pack_conv_weight_multi", tab.data_ptr(), len(jobs), max_n, dtype, None)
+    torch.cuda.synchronize()
+    for spec, a, b in zip(specs, one, multi):
+        assert torch.equal(a, b), spec
 
 
 @pytest.mark.parametrize("dtype", [0, 1])
