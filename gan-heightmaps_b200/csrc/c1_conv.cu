@@ -108,6 +108,10 @@ __device__ __forceinline__ void c1_epilogue(const C1Params& p, const CUtensorMap
           }
           __half2 h = __floats2half2_rn(r2[0], r2[1]);
           packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          // bit 2 of the argmax byte: the STORED fp16 value is on the slope-1 side of the activation (>= 0; > 0 for ReLU),
+          // so that the backward pass does not have to read the pooled tensor for act'
+          const uint32_t pm = ACT == HM_ACT_RELU ? __hgt2_mask(h, __float2half2_rn(0.f)) : __hge2_mask(h, __float2half2_rn(0.f));
+          kb[j >> 2] |= ((pm & 0x4u) << (8 * (j & 3))) | ((pm & 0x40000u) >> 16 << (8 * ((j + 1) & 3)));
         }
         const int ch = c0 >> 3;                                // 16-byte chunk of the row's 128 bytes
         *reinterpret_cast<uint4*>(ybuf + sw128_off(row, ch)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           const size_t ro = (((size_t)b * p.Hq + rwy) * p.Wq + rwx) * 64 + cc * 8;
           gv[k] = *reinterpret_cast<const uint4*>(p.g + ro);
           if (!p.plain) {
-            pv[k] = *reinterpret_cast<const uint4*>(p.pl + ro);
+            pv[k] = p.pl ? *reinterpret_cast<const uint4*>(p.pl + ro) : make_uint4(0, 0, 0, 0);
             kv[k] = *reinterpret_cast<const uint2*>(p.idx + ro);
           } else {
             pv[k] = make_uint4(0, 0, 0, 0);
@@ -593,11 +597,17 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
 #pragma unroll
       for (int c = 0; c < 8; c++) {         // pass c: window c*16 + sub, chunk cc
         const uint32_t gw[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w}, pw4[4] = {pv[c].x, pv[c].y, pv[c].z, pv[c].w};
+        // without the pooled tensor: bit 2 of the argmax bytes (written by hm_c1s2_conv) says which side of the
+        // activation the stored value is on; bytes spread to 0xffff half lanes like the position compare below
+        const uint32_t s0 = __vcmpeq4(kv[c].x & 0x04040404u, 0x04040404u), s1 = __vcmpeq4(kv[c].y & 0x04040404u, 0x04040404u);
+        const uint32_t sm[4] = {__byte_perm(s0, 0, 0x1100), __byte_perm(s0, 0, 0x3322), __byte_perm(s1, 0, 0x1100),
+                                __byte_perm(s1, 0, 0x3322)};
         uint32_t hv[4];                     // 8 halves
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const __half2 p2 = *reinterpret_cast<const __half2*>(&pw4[j]);
-          const uint32_t pm = p.act == HM_ACT_RELU ? __hgt2_mask(p2, zero2) : __hge2_mask(p2, zero2);   // 0xffff per lane
+          const uint32_t pm = !p.pl ? sm[j]
+                                    : (p.act == HM_ACT_RELU ? __hgt2_mask(p2, zero2) : __hge2_mask(p2, zero2));   // 0xffff per lane
           const uint32_t fb = (f_pos & pm) | (f_neg & ~pm);
           const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&fb));
           hv[j] = *reinterpret_cast<const uint32_t*>(&h);
@@ -605,7 +615,8 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         // per window position d: keep the channels whose argmax byte equals d (byte compare, bytes spread to halves)
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-          const uint32_t e0 = __vcmpeq4(kv[c].x, 0x01010101u * (uint32_t)d), e1 = __vcmpeq4(kv[c].y, 0x01010101u * (uint32_t)d);
+          const uint32_t e0 = __vcmpeq4(kv[c].x & 0x03030303u, 0x01010101u * (uint32_t)d),
+                         e1 = __vcmpeq4(kv[c].y & 0x03030303u, 0x01010101u * (uint32_t)d);
           const uint32_t m0 = hv[0] & __byte_perm(e0, 0, 0x1100), m1 = hv[1] & __byte_perm(e0, 0, 0x3322);
           const uint32_t m2 = hv[2] & __byte_perm(e1, 0, 0x1100), m3 = hv[3] & __byte_perm(e1, 0, 0x3322);
           *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(c * 16 + sub, cc)) = make_uint4(m0, m1, m2, m3);
@@ -803,7 +814,7 @@ static int c1s2_bwd_launch(hm::CbParams& p, int B, int H, int W, const void* wk2
 extern "C" int hm_c1s2_bwd(const void* x, const void* g, const void* pooled, const uint8_t* idx, const void* wk2,
                            float* dwk, void* u, const float* img_scale, int B, int H, int W, int act, float slope,
                            void* stream) {
-  HM_CHECK_ARG(g && pooled && idx && B > 0 && H > 0 && W > 0 && (dwk || u), "hm_c1s2_bwd: bad argument");
+  HM_CHECK_ARG(g && idx && B > 0 && H > 0 && W > 0 && (dwk || u), "hm_c1s2_bwd: bad argument");
   HM_CHECK_ARG(!dwk || x, "hm_c1s2_bwd: the weight gradient needs the source image");
   HM_CHECK_ARG(!u || wk2, "hm_c1s2_bwd: the input gradient needs the weights (pack mode 16)");
   HM_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "hm_c1s2_bwd: the image must have even height and width (%dx%d)", H, W);

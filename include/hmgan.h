@@ -188,12 +188,14 @@ int hm_up2conv_wgrad_phases(const HmConvDesc* d, const void* x, const void* dy, 
  *                 nearest-2x -> conv5x5(64 -> 1), dcgan.py:31-32, straight from dy[B,H,W] to dx[B,H/2,W/2,64]); idx NULL;
  *   ncols == 256: wk = [(d,co)][64] (mode 15: the discriminator's first layer conv5x5(1 -> 64) + activation + 2x2
  *                 max-pool, dcgan.py:42-47, in one pass): y = act(max_d + bias[co]), idx[B,H/2,W/2,64] = argmax d
- *                 (d = 2*dy+dx, first maximum), the layout hm_maxpool2_fwd writes.
+ *                 (d = 2*dy+dx, first maximum) in bits 0-1, the layout hm_maxpool2_fwd writes, plus bit 2 = the stored y
+ *                 is on the slope-1 side of the activation (y >= 0; y > 0 for ReLU) for hm_c1s2_bwd.
  * act: HM_ACT_LINEAR, HM_ACT_LRELU or HM_ACT_RELU (monotonic, so it commutes with the max). */
 int hm_c1s2_conv(const void* x, const void* wk, const float* bias, void* y, uint8_t* idx, int B, int H, int W,
                  int ncols, int act, float slope, void* stream);
 /* Backward of the pooled form from g = d loss / d (pooled output) [B,H/2,W/2,64]; `pooled`, `idx` as written by the
- * forward pass.  With G'[w][(d,co)] = g[w][co] * act'(pooled[w][co]) * [idx[w][co] == d]:
+ * forward pass; `pooled` may be NULL, act' is then taken from bit 2 of idx (one tensor less to read: what the engine
+ * does).  With G'[w][(d,co)] = g[w][co] * act'(pooled[w][co]) * [idx[w][co] == d]:
  *   dwk != NULL: dwk[(d,co)][k] (fp32 [256][64], caller zeroes) += sum_w G'[w][(d,co)] * A[w][k], A[w][36] = 1;
  *                hm_c1s2_bwd_fold turns it into dW[co][0][5][5] (Lasagne layout) and db[co];
  *   u   != NULL: u[B,H/2,W/2,64], u[w][k] = sum_(d,co) G'[w][(d,co)] * wk2[d*64+k][co] (wk2 = pack mode 16);

@@ -851,21 +851,29 @@ def hm_c1s2_conv(x, wk, bias, y, idx, B, H, W, ncols, act, slope, stream=None):
     if ncols == 256:
         o4 = out.reshape(B, Hq, Wq, 4, 64)
         m, k = o4.max(dim=3)
-        _a(idx, B * Hq * Wq * 64, np.uint8)[:] = k.numpy().reshape(-1).astype(np.uint8)
         out = m
     res = _act(out + bv, act, slope)
-    _a(y, B * Hq * Wq * 64, np.float16)[:] = res.numpy().reshape(-1).astype(np.float16)
+    r16 = res.numpy().reshape(-1).astype(np.float16)
+    _a(y, B * Hq * Wq * 64, np.float16)[:] = r16
+    if ncols == 256:       # bits 0-1: argmax position; bit 2: the stored value is on the slope-1 side of the activation
+        side = (r16 > 0) if act == 2 else (r16 >= 0)
+        _a(idx, B * Hq * Wq * 64, np.uint8)[:] = k.numpy().reshape(-1).astype(np.uint8) | (side.astype(np.uint8) << 2)
     return 0
 
 
 def hm_c1s2_bwd(x, g, pooled, idx, wk2, dwk, u, img_scale, B, H, W, act, slope, stream=None):
     Hq, Wq = H // 2, W // 2
     n = B * Hq * Wq * 64
-    gg = _t(_a(g, n, np.float16)) * _act_grad_from_out(_t(_a(pooled, n, np.float16)), act, slope)
+    if pooled:
+        gg = _t(_a(g, n, np.float16)) * _act_grad_from_out(_t(_a(pooled, n, np.float16)), act, slope)
+    else:                  # act' from bit 2 of the argmax bytes
+        side = torch.from_numpy(((_a(idx, n, np.uint8) >> 2) & 1).astype(np.float32))
+        neg = slope if act == 1 else (0.0 if act == 2 else 1.0)
+        gg = _t(_a(g, n, np.float16)) * (side + (1 - side) * neg)
     if img_scale:
         gg = (gg.reshape(B, -1) * _t(_a(img_scale, B, np.float32)).view(B, 1)).reshape(-1)
     gg = gg.half().float().reshape(B * Hq * Wq, 64)                            # the kernel rounds g*act' to fp16
-    k = torch.from_numpy(_a(idx, n, np.uint8).astype(np.int64)).reshape(B * Hq * Wq, 64)
+    k = torch.from_numpy((_a(idx, n, np.uint8) & 3).astype(np.int64)).reshape(B * Hq * Wq, 64)
     G4 = torch.stack([gg * (k == d) for d in range(4)], 1).reshape(B * Hq * Wq, 256)   # [(w)][(d,co)]
     if dwk:
         a = _t(_a(x, B * H * W, np.float16)).reshape(B, 1, H, W)

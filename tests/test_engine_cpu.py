@@ -34,9 +34,9 @@ def _nl(name):
 
 
 def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with_p2p=True, seed=2, device="cpu",
-               lsgan=True, reconstruction='l1'):
+               lsgan=True, reconstruction='l1', with_dcgan=True):
     """The same seeded weights in the oracle and in the product model."""
-    which = ('G', 'D', 'P', 'Dp') if with_p2p else ('G', 'D')
+    which = (('G', 'D') if with_dcgan else ()) + (('P', 'Dp') if with_p2p else ())
     nets = S.build_nets(cfg, seed=seed, which=which)
     om = S.OracleModel(nets, alpha=100., opt=opt, lr=lr, train_mode=train_mode, lsgan=lsgan,
                        reconstruction=reconstruction)
@@ -45,6 +45,8 @@ def build_pair(cfg, train_mode, precision="parity", opt="rmsprop", lr=1e-3, with
     kw = dict(gen_fn_dcgan=dcgan.default_generator, disc_fn_dcgan=dcgan.default_discriminator,
               gen_params_dcgan=cfg['G'], disc_params_dcgan=dp,
               gen_fn_p2p=None, disc_fn_p2p=None, gen_params_p2p={}, disc_params_p2p={})
+    if not with_dcgan:
+        kw.update(gen_fn_dcgan=None, disc_fn_dcgan=None)
     if with_p2p:
         pp, dpp = dict(cfg['P']), dict(cfg['Dp'])
         pp['act'] = _nl(pp['act'])

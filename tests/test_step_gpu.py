@@ -413,17 +413,19 @@ def test_async_loss_readback_equals_per_step_readback():
 def test_host_path_graphs_equal_the_eager_schedule(mode, monkeypatch):
     """The host path (train_fn from numpy batches) replays the step as several CUDA graphs around the X / Y upload:
     G's forward pass at once, D(x) -- or P(X) for a pix2pix-only model -- once X has landed, the rest once Y has.
-    Against the eager schedule (HMGAN_CUDA_GRAPHS=0) in float32, two models side by side over six training steps (the
-    last four replayed) and a loss_fn call; BEFORE every call the graph model receives the eager one's complete state,
-    so that each call starts from identical parameters (left to themselves two correct schedules drift apart by up to
-    5e-3 within six steps: atomically reduced weight gradients, amplified by the max-pool / RMSprop sensitivity).
-    Losses within 1e-5, every gradient array within 1e-5 of its norm; a mis-ordered upload or graph shows up at O(1)."""
+    Against the eager schedule (HMGAN_CUDA_GRAPHS=0) in fast mode (the fork of D(x) exists there), two models side by side
+    over six training steps (the last four replayed) and a loss_fn call; BEFORE every call the graph model receives the
+    eager one's complete state, so that each call starts from identical parameters (left to themselves two correct
+    schedules drift apart by up to 5e-3 within six steps: atomically reduced weight gradients, amplified by the
+    max-pool / RMSprop sensitivity).  Both sides launch the same kernels on the same data: losses within 1e-4, every
+    gradient array within 1e-3 of its norm (order of the atomic adds); a mis-ordered upload or graph shows up at O(1)."""
     cfg = dict(TINY)
+    kw = dict(device="cuda", lr=1e-4, precision="fast", with_dcgan=(mode == "both"))
     monkeypatch.setenv("HMGAN_CUDA_GRAPHS", "0")
-    _, m0 = build_pair(cfg, mode, device="cuda", lr=1e-4)
+    _, m0 = build_pair(cfg, mode, **kw)
     monkeypatch.setenv("HMGAN_CUDA_GRAPHS", "1")
-    _, m1 = build_pair(cfg, mode, device="cuda", lr=1e-4)
-    assert m1._graphs_ok and not m0._graphs_ok
+    _, m1 = build_pair(cfg, mode, **kw)
+    assert m1._graphs_ok and not m0._graphs_ok and m1.have_dcgan == (mode == "both")
     for it in range(7):
         _sync_state(m0, m1)
         Z, X, Y = S.synthetic_batch(1, cfg['latent_dim'], 512, seed=70 + it)
@@ -431,17 +433,16 @@ def test_host_path_graphs_equal_the_eager_schedule(mode, monkeypatch):
             l0, l1 = m0.train_fn(Z, X, Y), m1.train_fn(Z, X, Y)
         else:
             l0, l1 = m0.loss_fn(Z, X, Y), m1.loss_fn(Z, X, Y)
-        np.testing.assert_allclose(l1, l0, rtol=1e-5, atol=1e-6, err_msg="call %d" % it)
+        np.testing.assert_allclose(l1, l0, rtol=1e-4, atol=1e-6, err_msg="call %d" % it)
         if it < 6:
             for n0, n1 in zip(m0._nets(), m1._nets()):
                 gmax = max(float(np.linalg.norm(g.ravel())) for g in n0.get_grads())
                 for i, (a_, b_) in enumerate(zip(n0.get_grads(), n1.get_grads())):
                     err = float(np.linalg.norm((a_ - b_).ravel()))
-                    assert err <= 1e-5 * float(np.linalg.norm(a_.ravel())) + 1e-6 * gmax, (mode, it, n0.name, i, a_.shape, err)
-    if m1.have_dcgan:
-        assert any(k[0] == "host" and v.get("gC") is not None for k, v in m1._graphs.items())
-    else:
-        assert any(k[0] == "host" and v.get("gP") is not None for k, v in m1._graphs.items())
+                    assert err <= 1e-3 * float(np.linalg.norm(a_.ravel())) + 1e-5 * gmax, (mode, it, n0.name, i, a_.shape, err)
+    # the graphs this test is about exist: D(x) on its own stream for the joint model, P(X) for the pix2pix-only one
+    slot = "gC" if mode == "both" else "gP"
+    assert any(k[0] == "host" and v.get(slot) is not None for k, v in m1._graphs.items() if isinstance(k, tuple))
     torch.cuda.synchronize()
 
 

@@ -595,8 +595,10 @@ def run_c1_case(name, B, H, W, pooled):
         scale = float(ref.abs().max())
         err = float((a - ref).abs().max()) / scale
         # the argmax must point at an element that attains the pooled value (ties / fp16-near-ties may differ)
-        k = idx.long()
-        assert int(k.max()) <= 3, "argmax byte out of range (untouched output?)"
+        assert int(idx.max()) <= 7, "argmax byte out of range (untouched output?)"
+        # bit 2 of the byte: the stored value is on the slope-1 side of the activation (hm_c1s2_bwd takes act' from it)
+        assert bool(((idx >> 2) == (y.float() >= 0).to(torch.uint8)).all()), "act' bit of the argmax byte"
+        k = (idx & 3).long()
         fw = full.permute(0, 2, 3, 1).reshape(B, H // 2, 2, W // 2, 2, 64).permute(0, 1, 3, 5, 2, 4).reshape(B, H // 2, W // 2, 64, 4)
         picked = torch.gather(fw, 4, k[..., None])[..., 0]
         ierr = float((picked - ref).abs().max()) / scale
@@ -685,13 +687,18 @@ def run_c1bwd_case(name, B, H, W):
     u2 = torch.zeros_like(u)
     _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(),
               dwk2.data_ptr(), u2.data_ptr(), None, B, H, W, 1, 0.2, None)
+    # what the engine does: no pooled tensor, act' from bit 2 of the argmax bytes -- the same patch-space gradient, bit for bit
+    u3 = torch.zeros_like(u)
+    _lib.call("hm_c1s2_bwd", None, g.data_ptr(), None, idx.data_ptr(), wk2.data_ptr(), None, u3.data_ptr(),
+              None, B, H, W, 1, 0.2, None)
     torch.cuda.synchronize()
+    assert torch.equal(u3[..., :36], u[..., :36]), "hm_c1s2_bwd without the pooled tensor differs from the run with it"
     # reference in float32 with the kernel's own routing (argmax bytes) and activation derivative (sign of the pooled
     # value): full-resolution gradient, then the convolution's adjoints as GEMMs over unfolded patches
     gp = g.float() * torch.where(pooled.float() >= 0, 1.0, 0.2)
     gp = gp.half().float()
     dyf = torch.zeros(B, Hq, 2, Wq, 2, 64, device="cuda")
-    k = idx.long()
+    k = (idx & 3).long()
     for d in range(4):
         dyf[:, :, d >> 1, :, d & 1, :] = gp * (k == d)
     dyf = dyf.reshape(B, H * W, 64)                                               # [B, L, co]
@@ -725,6 +732,9 @@ def perf_c1bwd():
     dx = torch.empty(B, H, W, device="cuda", dtype=torch.float16)
     runs = (("D1 bwd weight gradient x64", lambda: _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), None, dwk.data_ptr(), None, None, 64, H, W, 1, 0.2, None), 64 * 65536 * (128 + 128 + 64) / 1e9),
             ("D1 bwd input gradient x32 (patch space)", lambda: _lib.call("hm_c1s2_bwd", None, g.data_ptr(), pooled.data_ptr(), idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(), None, 32, H, W, 1, 0.2, None), 32 * 65536 * (128 + 128 + 64 + 80) / 1e9),
+            ("D1 bwd weight gradient x64, act' from idx", lambda: _lib.call("hm_c1s2_bwd", x.data_ptr(), g.data_ptr(), None, idx.data_ptr(), None, dwk.data_ptr(), None, None, 64, H, W, 1, 0.2, None), 64 * 65536 * (128 + 64) / 1e9),
+            ("D1 bwd input gradient x32, act' from idx", lambda: _lib.call("hm_c1s2_bwd", None, g.data_ptr(), None, idx.data_ptr(), wk2.data_ptr(), None, u.data_ptr(), None, 32, H, W, 1, 0.2, None), 32 * 65536 * (128 + 64 + 80) / 1e9),
+            ("G-out weight gradient x32 (hm_c1s2_wgrad)", lambda: _lib.call("hm_c1s2_wgrad", x.data_ptr(), g.data_ptr(), dwk.data_ptr(), 32, H, W, None), 32 * 65536 * (128 + 8) / 1e9),
             ("D1 bwd col2im x32", lambda: _lib.call("hm_c1s2_col2im", u.data_ptr(), dx.data_ptr(), 32, H, W, None), 32 * 65536 * (72 + 8) / 1e9))
     for nm, fn, gb in runs:
         fn()
