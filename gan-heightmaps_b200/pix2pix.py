@@ -677,7 +677,15 @@ class Pix2Pix(object):
                 if quick_run:
                     break
             flush()
-            return tuple([np.mean(elem) for elem in rec])
+            means = tuple([np.mean(elem) for elem in rec])
+            if self.rt.precision == "fast" and not np.all(np.isfinite(means)):
+                # the reference (float32) would carry on; here a non-finite loss is almost always an fp16 overflow of the
+                # statically scaled gradients (e.g. a degenerate BatchNorm batch) and must not pass unnoticed
+                import warnings
+                warnings.warn("non-finite losses in precision='fast' (fp16 storage, static loss scale %g): the fp16 "
+                              "gradients overflowed; rerun with precision='tc32' / 'parity' or a smaller loss_scale"
+                              % self.rt.loss_scale, RuntimeWarning)
+            return means
         header = ["epoch"] + ["train_%s" % k for k in self.train_keys] + ["valid_%s" % k for k in self.train_keys]
         header += ["lr", "time", "mode"]
         if not os.path.exists(out_dir):
