@@ -527,66 +527,58 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
     uint32_t* pb = patch + grp * C1_PATCH_WORDS;
     uint8_t* stg = gbase + st_off + grp * CB_STAGE_BYTES;
     const float neg = p.act == HM_ACT_LRELU ? p.slope : (p.act == HM_ACT_RELU ? 0.f : 1.f);
-    // Global loads of a tile (24 gradient / activation / argmax loads + the patch words per thread).  The G' tiles are
-    // built chunk-wise -- (window r, 8-channel chunk cc) needs only g, p, idx at that position -- so the loads are laid
-    // out for coalescing, not per window: in pass k a warp covers 4 consecutive windows x 8 chunks = 512 contiguous
-    // bytes of g and of p (256 of idx), i.e. 4 + 4 + 2 128-byte lines per three instructions.  (One thread per window
-    // row touched 32 lines per instruction; the LSU transaction rate, not HBM, bounded the kernel: round-2 profile.)
-    // The loads of the group's NEXT tile are issued pass by pass into the registers the current tile's pass has just
-    // consumed, so a whole tile is in flight per group while it builds (the builders were latency-bound: one tile in
-    // flight per SM on average) at no cost in registers.
-    const int sub = tb >> 3, cc = tb & 7;
-    uint4 gv[8], pv[8];
-    uint2 kv[8];
-    uint32_t pre[C1_PRE];
-    int b = 0, ty = 0, tx = 0;
-    auto coords = [&](int it_) {
-      const int t = blockIdx.x + it_ * gridDim.x;
-      b = t / per_img;
-      const int rem = t - b * per_img;
-      ty = rem / p.tiles_x;
-      tx = rem - ty * p.tiles_x;
-    };
-    auto load_pass = [&](int k) {          // pass k of tile (b, ty, tx): window k*16 + sub, chunk cc
-      const int r = k * 16 + sub;
-      const int riy = r / p.bw, rix = r - riy * p.bw;
-      const int rwy = ty * p.bh + riy, rwx = tx * p.bw + rix;
-      gv[k] = pv[k] = make_uint4(0, 0, 0, 0);
-      kv[k] = make_uint2(0, 0);
-      if (rwy < p.Hq && rwx < p.Wq) {
-        const size_t ro = (((size_t)b * p.Hq + rwy) * p.Wq + rwx) * 64 + cc * 8;
-        gv[k] = *reinterpret_cast<const uint4*>(p.g + ro);
-        if (!p.plain) {
-          if (p.pl) pv[k] = *reinterpret_cast<const uint4*>(p.pl + ro);
-          kv[k] = *reinterpret_cast<const uint2*>(p.idx + ro);
-        }
-      }
-    };
-    auto load_patch = [&]() {
-      const int Y0 = 2 * ty * p.bh - 2, X0 = 2 * tx * p.bw - 2;
-      const __half* img = p.x + (size_t)b * p.H * p.W;
-#pragma unroll
-      for (int j = 0; j < C1_PRE; j++) {
-        const int i = tb + 128 * j;
-        uint32_t v = 0;
-        if (i < n_words) {
-          const int pr = i / PWW, pw = i - pr * PWW;
-          const int Y = Y0 + pr, X = X0 + 2 * pw;
-          if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
-        }
-        pre[j] = v;
-      }
-    };
-    if (grp < my_tiles) {
-      coords(grp);
-#pragma unroll
-      for (int k = 0; k < 8; k++) load_pass(k);
-      if (p.want_dw) load_patch();
-    }
     for (int it = grp; it < my_tiles; it += 2) {
-      const float isc = p.img_scale ? p.img_scale[b] : 1.f;       // (b still names the current tile here)
-      const bool has_next = it + 2 < my_tiles;
-      if (has_next) coords(it + 2);                                // from here on (b, ty, tx) name the NEXT tile
+      const int t = blockIdx.x + it * gridDim.x;
+      const int b = t / per_img, rem = t - b * per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const float isc = p.img_scale ? p.img_scale[b] : 1.f;
+      // issue every global load of this tile up front (24 gradient / activation / argmax loads + the patch words): one
+      // round trip per tile instead of three.  The G' tiles are built chunk-wise -- (window r, 8-channel chunk cc) needs
+      // only g, p, idx at that position -- so the loads are laid out for coalescing, not per window: in pass k a warp
+      // covers 4 consecutive windows x 8 chunks = 512 contiguous bytes of g and of p (256 of idx), i.e. 4 + 4 + 2
+      // 128-byte lines per three instructions.  (One thread per window row touched 32 lines per instruction; the LSU
+      // transaction rate, not HBM, bounded the kernel: round-2 profile.)  Tried and reverted: issuing the NEXT tile's loads
+      // pass by pass into the registers each pass of the build has just consumed (a tile in flight per group while it
+      // builds) made all three uses 30-45 % slower (0.479 -> 0.644 ms): the 24 loads must go out back to back.
+      const int sub = tb >> 3, cc = tb & 7;
+      uint4 gv[8], pv[8];
+      uint2 kv[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int r = k * 16 + sub;
+        const int riy = r / p.bw, rix = r - riy * p.bw;
+        const int rwy = ty * p.bh + riy, rwx = tx * p.bw + rix;
+        if (rwy < p.Hq && rwx < p.Wq) {
+          const size_t ro = (((size_t)b * p.Hq + rwy) * p.Wq + rwx) * 64 + cc * 8;
+          gv[k] = *reinterpret_cast<const uint4*>(p.g + ro);
+          if (!p.plain) {
+            pv[k] = p.pl ? *reinterpret_cast<const uint4*>(p.pl + ro) : make_uint4(0, 0, 0, 0);
+            kv[k] = *reinterpret_cast<const uint2*>(p.idx + ro);
+          } else {
+            pv[k] = make_uint4(0, 0, 0, 0);
+            kv[k] = make_uint2(0, 0);
+          }
+        } else {
+          gv[k] = pv[k] = make_uint4(0, 0, 0, 0);
+          kv[k] = make_uint2(0, 0);
+        }
+      }
+      uint32_t pre[C1_PRE];
+      if (p.want_dw) {
+        const int Y0 = 2 * ty * p.bh - 2, X0 = 2 * tx * p.bw - 2;
+        const __half* img = p.x + (size_t)b * p.H * p.W;
+#pragma unroll
+        for (int j = 0; j < C1_PRE; j++) {
+          const int i = tb + 128 * j;
+          uint32_t v = 0;
+          if (i < n_words) {
+            const int pr = i / PWW, pw = i - pr * PWW;
+            const int Y = Y0 + pr, X = X0 + 2 * pw;
+            if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) v = *reinterpret_cast<const uint32_t*>(img + (size_t)Y * p.W + X);
+          }
+          pre[j] = v;
+        }
+      }
       mbar_wait(empty(grp), ((it >> 1) & 1) ^ 1);
       if (p.want_dw) {
 #pragma unroll
@@ -594,7 +586,6 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           const int i = tb + 128 * j;
           if (i < n_words) pb[i] = pre[j];
         }
-        if (has_next) load_patch();
       }
       // g' = g * act'(p) * isc in half2 arithmetic: the factor is one of two constants selected by the sign of p
       const __half2 zero2 = __float2half2_rn(0.f);
@@ -602,10 +593,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       const uint32_t f_neg = __half_as_ushort(__float2half_rn(neg * isc)) * 0x00010001u;
       if (p.plain) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-          *reinterpret_cast<uint4*>(stg + sw128_off(c * 16 + sub, cc)) = gv[c];
-          if (has_next) load_pass(c);
-        }
+        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(stg + sw128_off(c * 16 + sub, cc)) = gv[c];
       }
       if (!p.plain) {
 #pragma unroll
@@ -627,11 +615,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           hv[j] = *reinterpret_cast<const uint32_t*>(&h);
         }
         // per window position d: keep the channels whose argmax byte equals d (byte compare, bytes spread to halves)
-        const uint32_t k0 = kv[c].x & 0x03030303u, k1 = kv[c].y & 0x03030303u;
-        if (has_next) load_pass(c);         // this pass's registers are free: refill them with the next tile's pass c
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-          const uint32_t e0 = __vcmpeq4(k0, 0x01010101u * (uint32_t)d), e1 = __vcmpeq4(k1, 0x01010101u * (uint32_t)d);
+          const uint32_t e0 = __vcmpeq4(kv[c].x & 0x03030303u, 0x01010101u * (uint32_t)d),
+                         e1 = __vcmpeq4(kv[c].y & 0x03030303u, 0x01010101u * (uint32_t)d);
           const uint32_t m0 = hv[0] & __byte_perm(e0, 0, 0x1100), m1 = hv[1] & __byte_perm(e0, 0, 0x3322);
           const uint32_t m2 = hv[2] & __byte_perm(e1, 0, 0x1100), m3 = hv[3] & __byte_perm(e1, 0, 0x3322);
           *reinterpret_cast<uint4*>(stg + d * C1_A_BYTES + sw128_off(c * 16 + sub, cc)) = make_uint4(m0, m1, m2, m3);

@@ -206,6 +206,7 @@ class Pix2Pix(object):
         else:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         self._pending.append(work)
+        self.allreduce_calls = getattr(self, "allreduce_calls", 0) + 1       # diagnostic: buckets issued so far
         base = flat._base if flat._base is not None else flat
         for net in self._nets():
             if net.gflat is base:
@@ -464,6 +465,7 @@ class Pix2Pix(object):
         self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 0., 4, ls)
         if do:
             Dp.backward(0, 2 * B, wgrad=True, input_grad=False)
+            self._allreduce_async(Dp.gflat)                             # data-parallel: under the rest of this half
         self._adv(Dp, h[B:2 * B], dh[B:2 * B] if do else None, 1., 2, ls)   # gen_loss_p2p :110
         dpx = None
         if do:
@@ -474,7 +476,16 @@ class Pix2Pix(object):
                 1 if self.reconstruction == 'l2' else 0, 1.0, ls * self.alpha, 1, _ptr(self.losses[3:]))
         if do:
             self._copy(dpx, P.out.grad[:B])
-            P.backward(0, B, wgrad=True)
+            # data-parallel: the U-Net's flat gradient (92 MB) in two buckets -- the decoder half (the tail of the flat
+            # vector, produced first) goes out while the encoder's backward pass runs
+            hook, off = None, 0
+            if self.pg is not None and len(P.ops) > 8:
+                k = min(range(1, len(P.ops)), key=lambda i: abs(P.param_offset(i) - P.n_trainable // 2))
+                off = P.param_offset(k)
+                if 0 < off < P.n_trainable:
+                    hook = {k: lambda: self._allreduce_async(P.gflat[off:])}
+            P.backward(0, B, wgrad=True, after_op=hook)
+            self._allreduce_async(P.gflat[:off] if hook else P.gflat)
             upd += [P, Dp]
         return upd
 

@@ -143,3 +143,76 @@ def test_sync_batchnorm_makes_two_ranks_equal_one_rank_on_the_whole_batch(tmp_pa
     for i in range(nS):          # parameters after the update, BatchNorm running mean / inv_std included
         np.testing.assert_array_equal(r0["sG%d" % i], r1["sG%d" % i])
         np.testing.assert_allclose(r0["sG%d" % i], r0["osG%d" % i], rtol=2e-3, atol=2e-4, err_msg="G value %d" % i)
+
+
+def _worker_p2p(rank, world, port, out_dir):
+    for p in (ROOT, PKG, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_hmgan
+    import _lib
+    _lib.call, _lib.query, _lib.load = fake_hmgan.call, fake_hmgan.query, (lambda: None)
+    from oracle import step as S
+    import test_engine_cpu as T
+    cfg = dict(T.TINY)
+    _, m = T.build_pair(cfg, 'p2p', with_dcgan=False)
+    m.pg = dist.group.WORLD
+    Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 512, seed=12)
+    sl = slice(2 * rank, 2 * rank + 2)
+    losses = m.train_fn(Z[sl], X[sl], Y[sl])
+    out = {"losses": np.asarray(losses), "buckets": np.asarray(m.allreduce_calls)}
+    out.update({"gP%d" % i: v for i, v in enumerate(m.P.get_grads())})               # all-reduced SUMS
+    out.update({"gDp%d" % i: v for i, v in enumerate(m.Dp.get_grads())})
+    out.update({"P%d" % i: v for i, v in enumerate(m.P.get_all_param_values())})
+    out.update({"Dp%d" % i: v for i, v in enumerate(m.Dp.get_all_param_values())})
+    np.savez(os.path.join(out_dir, "p2p%d.npz" % rank), **out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_pix2pix_step_reduces_every_gradient_exactly_once(tmp_path):
+    """The pix2pix networks' gradients are all-reduced in buckets issued during the backward pass (the PatchGAN's after
+    its weight-gradient pass, the U-Net's decoder half while the encoder's backward pass runs, the rest at the end).
+    After the step every gradient array on both ranks must be the SUM of the two shards' local gradients (computed here
+    by two single-process models) -- a bucket that was skipped would hold one shard's gradient, one reduced twice four
+    shards' worth -- and the trainable parameters of the replicas must be bit-identical."""
+    world, port = 2, 33500 + os.getpid() % 2000
+    mp.spawn(_worker_p2p, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(str(tmp_path / "p2p0.npz"))
+    r1 = np.load(str(tmp_path / "p2p1.npz"))
+    for k in r0.files:
+        if k.startswith("g"):
+            np.testing.assert_array_equal(r0[k], r1[k], err_msg=k)
+    assert int(r0["buckets"]) == 3 and int(r1["buckets"]) == 3       # PatchGAN, U-Net decoder half, U-Net rest
+    sys.path.insert(0, PKG)
+    import fake_hmgan
+    import _lib
+    import test_engine_cpu as T
+    from oracle import step as S
+    saved = (_lib.call, _lib.query, _lib.load)
+    _lib.call, _lib.query, _lib.load = fake_hmgan.call, fake_hmgan.query, (lambda: None)
+    try:
+        cfg = dict(T.TINY)
+        Z, X, Y = S.synthetic_batch(4, cfg['latent_dim'], 512, seed=12)
+        local = []
+        for rank in range(2):
+            _, m = T.build_pair(cfg, 'p2p', with_dcgan=False)
+            trainable = {"P": [q.trainable for q in m.P.params], "Dp": [q.trainable for q in m.Dp.params]}
+            sl = slice(2 * rank, 2 * rank + 2)
+            m.train_fn(Z[sl], X[sl], Y[sl])
+            local.append({"P": m.P.get_grads(), "Dp": m.Dp.get_grads()})
+        for net in ("P", "Dp"):
+            assert len(local[0][net]) > 4
+            for i, (g0, g1) in enumerate(zip(local[0][net], local[1][net])):
+                want = g0 + g1
+                scale = max(float(np.abs(want).max()), 1e-12)
+                np.testing.assert_allclose(r0["g%s%d" % (net, i)], want, rtol=1e-5, atol=1e-6 * scale,
+                                           err_msg="%s gradient %d" % (net, i))
+            # replicas: identical trainable parameters (BatchNorm running statistics are per-rank by design)
+            for i, tr in enumerate(trainable[net]):
+                if tr:
+                    np.testing.assert_array_equal(r0["%s%d" % (net, i)], r1["%s%d" % (net, i)], err_msg="%s param %d" % (net, i))
+    finally:
+        _lib.call, _lib.query, _lib.load = saved
