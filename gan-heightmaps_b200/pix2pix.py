@@ -139,11 +139,6 @@ class Pix2Pix(object):
         self._graphs = {}
         self._pending, self._reduced = [], set()
         self._graphs_ok = rt.device.type == "cuda" and os.environ.get("HMGAN_CUDA_GRAPHS", "1") != "0"
-        # G's packed weight copies are refreshed at the START of a step, beside D(x), instead of at its end where nothing
-        # else is left to run (its update is the last thing of a step); G._packed stays False between steps so that any
-        # other user of G (gen_fn, z_fn) re-packs first
-        self._defer_gpack = (gen_fn_dcgan is not None and rt._fork_ok
-                             and os.environ.get("HMGAN_DEFER_GPACK", "1") != "0")
         self.train_fn = lambda Z, X, Y: self._step_host(Z, X, Y, True)
         self.loss_fn = lambda Z, X, Y: self._step_host(Z, X, Y, False)
         self.train_fn_async = lambda Z, X, Y: self._step_host_async(Z, X, Y, True)      # device tensors, no host sync
@@ -288,15 +283,8 @@ class Pix2Pix(object):
         self._sync_lr()
         self._ensure_packed()
         st["graph"].replay()
-        self._after_replay(train)
         self.rt.launches += st["launches"]
         return self.losses
-
-    def _after_replay(self, train):
-        """Host flags a replayed step cannot set: with the deferred generator pack, G's packed copies are stale after a
-        training step (its master weights moved last) and fresh after a loss-only step."""
-        if self._defer_gpack:
-            self.G._packed = not train
 
     def _nets(self):
         return [n for n in (self.G, self.D, self.P, self.Dp) if n is not None]
@@ -319,8 +307,6 @@ class Pix2Pix(object):
         """Refresh the packed weight copies of any network whose master parameters changed outside a step
         (set_all_param_values, load_model) or whose buffers were reallocated; eager launches, never captured."""
         for n in self._nets():
-            if n is self.G and self._defer_gpack:
-                continue                       # every step packs G itself, first thing
             if not n._packed and n.B > 0:
                 n.pack()
 
@@ -347,8 +333,6 @@ class Pix2Pix(object):
                         self._load_nchw(Xd, self.D.inputs[0].buf, B, ca, S, S, self.is_a_grayscale)
                         self.D.forward(2 * B, 0, B)                         # D(x)            :94
                 rt.call("hm_cast", _ptr(Zd), _lib.F32, _ptr(self.G.inputs[0].buf), rt.cd, Zd.numel())
-                if self._defer_gpack:
-                    self.G.pack()                                           # from the last update's master weights
                 self.G.forward(B)                                           # G(z)            :92
             if part == 1:
                 return self.losses
@@ -446,8 +430,9 @@ class Pix2Pix(object):
                 self._pending, self._reduced = [], set()
             for net in upd:
                 net.apply_update(self.opt, self._lr_dev, 1.0 / (ls * world), self.opt_hyper)
-                if not (self._defer_gpack and net is self.G):
-                    net.pack()   # packed copies follow the master weights inside the step (and inside its CUDA graph)
+                net.pack()       # packed copies follow the master weights inside the step (and inside its CUDA graph)
+                # (tried: G's packs at the START of the next step, beside D(x), instead of here where nothing else is left
+                # to run -- 12.17 / 12.20 vs 12.16 / 12.25 ms on one box: no gain, removed)
         return self.losses
 
     def _p2p_part(self, Xd, Yd, B, train, phase=0):
@@ -587,7 +572,6 @@ class Pix2Pix(object):
         if st.get("done") is None:
             st["done"] = torch.cuda.Event()
         st["done"].record(main)
-        self._after_replay(train)
         self.rt.launches += st["launches"]
         return self.losses
 
