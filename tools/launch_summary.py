@@ -1,12 +1,12 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time per kernel family and the
-slowest individual launches (of the last complete training step when the capture holds several).  usage: python tools/launch_summary.py gpurun_out/launches.csv [min_ms]"""
+slowest individual launches (of the last complete training step when the capture holds several).  usage: python tools/launch_summary.py gpurun_out/launches.csv [min_ms] [top]"""
 import collections
 import csv
 import re
 import sys
 
 
-def main(path, min_ms=1.0):
+def main(path, min_ms=1.0, top=20):
     with open(path) as f:
         lines = [l for l in f if not l.startswith('==')]
     r = csv.reader(lines)
@@ -35,7 +35,7 @@ def main(path, min_ms=1.0):
         if v >= min_ms:
             big.append((v, row[gi], name))
     print('total %.2f ms over %d launches' % (tot, sum(n for n, _ in agg.values())))
-    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:20]:
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         print('%8.2f ms %5.1f%% n=%4d  %s' % (t, 100 * t / tot, n, k))
     print('launches >= %.1f ms:' % min_ms)
     for b in big:
@@ -43,4 +43,4 @@ def main(path, min_ms=1.0):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 1.0)
+    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 1.0, int(sys.argv[3]) if len(sys.argv) > 3 else 20)
