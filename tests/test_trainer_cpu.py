@@ -140,3 +140,25 @@ def test_loss_sync_every_n_steps_gives_the_same_epoch_row(cpu_backend, tmp_path)
         m.save_model(str(tmp_path / "dc.model"))
         both.save_model(str(tmp_path / "both.model"))
         m.load_model(str(tmp_path / "both.model"))              # holds p2p parameters this model has no network for
+
+
+def test_train_warns_about_non_finite_losses_in_fast_mode(cpu_backend, tmp_path):
+    """fp16 storage with a static loss scale: gradients that overflow turn the parameters (and then the losses) into
+    inf / NaN, where the float32 reference would carry on.  Pix2Pix.train() must say so instead of writing rows of nan
+    silently; the float32 modes keep the reference's behaviour (no warning)."""
+    import warnings
+    cfg = S.experiment_kwargs('tiny512')
+    for precision, expect in (("fast", True), ("parity", False)):
+        _, m = build_pair(cfg, 'both', precision=precision)
+        nan_row = [np.float32("nan")] * 5
+        m.train_fn = lambda Z, X, Y: nan_row
+        m.loss_fn = lambda Z, X, Y: nan_row
+        it_train = util.SyntheticIterator(2, 1, 512, seed=0)
+        it_val = util.SyntheticIterator(2, 1, 512, seed=100)
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter("always")
+            m.train(it_train, it_val, batch_size=1, num_epochs=1, out_dir=str(tmp_path / precision), quick_run=True)
+        hits = [w for w in caught if issubclass(w.category, RuntimeWarning) and "non-finite losses" in str(w.message)]
+        assert bool(hits) == expect, (precision, [str(w.message) for w in caught])
+        if expect:
+            assert "tc32" in str(hits[0].message)
