@@ -76,12 +76,10 @@ class Runtime(object):
                             and os.environ.get("HMGAN_WGRAD_STREAM", "1") != "0")
         self._splitk = self.device.type == "cuda" and os.environ.get("HMGAN_TC_SPLITK", "1") != "0"
         # the weighted max-pool gradient copies and D1's weight gradient on the weight-gradient stream (A/B knob)
-        # two more pieces of the discriminator's backward pass that COULD run on the weight-gradient stream.  Measured on
-        # one box (profiles/r2_variants_ab.txt, visit r2q): both on = 12.23 / 12.28 ms, both off = 12.06 / 12.08 ms per
-        # DCGAN step, joint step unchanged -- the deferred copy re-reads the pooled gradient and argmax, and the side
-        # stream is already the longer one while D's backward runs.  Off by default.
-        self.side_d1dw = os.environ.get("HMGAN_SIDE_D1DW", "0") != "0"      # D layer 1's weight gradient (hm_c1s2_bwd)
-        self.side_poolcopy = os.environ.get("HMGAN_SIDE_POOLCOPY", "0") != "0"   # the per-sample-weighted max-pool copy
+        # (Measured and left out, profiles/r2_variants_ab.txt visits r2q / r2r: running the per-sample-weighted max-pool copy
+        # and D layer 1's weight gradient on the weight-gradient stream as well -- 12.23 / 12.28 ms against 12.06 / 12.08 ms
+        # per DCGAN step: the deferred copy re-reads the pooled gradient and argmax, and that stream is already the longer
+        # one while D's backward pass runs.)
         self._tc_ws = {}
         self._fork_ok = (self.device.type == "cuda" and precision == "fast"
                          and os.environ.get("HMGAN_FORK", "1") != "0")
@@ -431,7 +429,6 @@ class ConvOp(object):
         # Net when a PoolOp consumes the output (pool_fused); (b) the input gradient of nearest-2x -> 5x5 -> one channel
         self.pool_fused = None
         self.pool_tc = None           # PoolOp whose 2x2 max-pool runs in this convolution's tensor-core epilogue
-        self._pre_wgrad = None        # work the consuming PoolOp deferred to the weight-gradient stream (weighted dY)
         self.db_done = False
         self.bias_grad_zero = False
         self.wk = None
@@ -781,24 +778,18 @@ class ConvOp(object):
         ws = _ptr(net.wscale) if net.wscale is not None else None
         ia, ib = net.ig_range if (net.ig_range is not None and t1) else (lo, hi)
         same = (ia, ib) == (lo, hi) and ws is None
-        side = rt.wgrad_stream() if (wgrad and rt.side_d1dw) else None
 
-        def dw_part():          # weight / bias gradient: reads g, pooled, idx, x; on the weight-gradient stream if there is one
+        def dw_part():          # weight / bias gradient: reads g, the argmax bytes and x
             self.dwk.zero_()
             rt.call("hm_c1s2_bwd", x1, g, pl, idx, None, _ptr(self.dwk), None, ws, n, self.Hv, self.Wv, act, slope)
             rt.call("hm_c1s2_bwd_fold", _ptr(self.dwk), _ptr(net.gview(self.W)), _ptr(net.gview(self.bias)), self.Cout)
-        if wgrad and t1 and same and side is None:         # one launch produces both
+        if wgrad and t1 and same:                          # one launch produces both
             self.dwk.zero_()
             rt.call("hm_c1s2_bwd", x1, g, pl, idx, _ptr(self.wk2), _ptr(self.dwk), _ptr(self.ubuf[lo:hi]), None, n,
                     self.Hv, self.Wv, act, slope)
             rt.call("hm_c1s2_bwd_fold", _ptr(self.dwk), _ptr(net.gview(self.W)), _ptr(net.gview(self.bias)), self.Cout)
         else:
-            if wgrad and side is not None:
-                side.wait_stream(torch.cuda.current_stream(rt.device))
-                with torch.cuda.stream(side):
-                    dw_part()
-                rt.mark_wgrad_forked()
-            elif wgrad:
+            if wgrad:
                 dw_part()
             if t1:
                 rt.call("hm_c1s2_bwd", None, _ptr(pool.out.g(ia, ib)), None if signbits else _ptr(pool.out.b(ia, ib)),
@@ -822,22 +813,15 @@ class ConvOp(object):
         g_plain = g
         if wgrad and self.net.wscale is not None:
             g = self.out.grad_w[lo:hi]        # weight and bias gradients see the per-sample-weighted gradient
-        pre, self._pre_wgrad = self._pre_wgrad, None
         if wgrad:
             side = None if self.dc2 else rt.wgrad_stream()     # (dc2: the input gradient reads the wgrad block's s2d copy)
             if side is None:
-                if pre is not None:
-                    pre()
                 self._bwd_wgrad(rt, lo, hi, g, x1, x2)
             else:
                 side.wait_stream(torch.cuda.current_stream(rt.device))      # dY (and its activation backward) is ready
                 with torch.cuda.stream(side):
-                    if pre is not None:
-                        pre()
                     self._bwd_wgrad(rt, lo, hi, g, x1, x2)
                 rt.mark_wgrad_forked()
-        elif pre is not None:
-            pre()
         self._bwd_dgrad(rt, lo, hi, g_plain, wgrad, input_grad)
 
     def _bwd_wgrad(self, rt, lo, hi, g, x1, x2):
@@ -1097,18 +1081,6 @@ class PoolOp(object):
         if self.net.wscale is not None:
             args = (_ptr(self.out.g(lo, hi)), _ptr(self.out.b(lo, hi)), _ptr(self.idx[lo:hi]))
             tail = (rt.cd, hi - lo, H, W, Cn, ACT[self.act.name], self.act.slope)
-            if wgrad and self.prod is not None and rt.side_poolcopy and rt.wgrad_stream() is not None:
-                # the input-gradient chain needs only the plain dX: it stays here; the per-sample-weighted copy and the
-                # bias gradient are operands of the producing convolution's WEIGHT gradient and are produced on its stream
-                rt.call("hm_maxpool2_bwd", *args, _ptr(self.x.g(lo, hi)), *tail, None)
-                dxs, ws = _ptr(self.x.grad_w[lo:hi]), _ptr(self.net.wscale)
-
-                def deferred(args=args, tail=tail, dxs=dxs, ws=ws, db=db, dbt=dbt if db is not None else None):
-                    if dbt is not None:
-                        dbt.zero_()
-                    rt.call("hm_maxpool2_bwd_scaled", *args, None, dxs, ws, *tail, db)
-                self.prod._pre_wgrad = deferred
-                return
             rt.call("hm_maxpool2_bwd_scaled", *args, _ptr(self.x.g(lo, hi)), _ptr(self.x.grad_w[lo:hi]),
                     _ptr(self.net.wscale), *tail, db)
             return
