@@ -172,13 +172,13 @@ def time_dominant_kernel(m, reps=5):
     return name, bf, ms, getattr(op, "path", "simt")
 
 
-def cpu_baseline(workload, sample_b, steps=1, warmup=1):
+def cpu_baseline(workload, sample_b, steps=1, warmup=1, lr=1e-4):
     """The oracle's train step (torch-CPU float32, all host threads) on `sample_b` images of the workload."""
     from oracle import step as S
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = S.experiment_kwargs('test1_nobn_bilin_both')
     which = {"both": ('G', 'D', 'P', 'Dp'), "dcgan": ('G', 'D'), "p2p": ('P', 'Dp')}[workload]
-    om = S.OracleModel(S.build_nets(cfg, seed=2, which=which), opt='rmsprop', lr=1e-4, train_mode=workload, lsgan=True)
+    om = S.OracleModel(S.build_nets(cfg, seed=2, which=which), opt='rmsprop', lr=lr, train_mode=workload, lsgan=True)
     Z, X, Y = S.synthetic_batch(sample_b, cfg['latent_dim'], 512, seed=0)
     for _ in range(warmup):
         om.train_fn(Z, X, Y)
@@ -304,7 +304,7 @@ def main():
         if rank != 0:
             return
         k, w = max(1, min(a.steps, 4)), min(a.warmup, 1)
-        v, dt = cpu_baseline(a.workload, a.cpu_sample, steps=k, warmup=w)
+        v, dt = cpu_baseline(a.workload, a.cpu_sample, steps=k, warmup=w, lr=a.lr)
         cores = os.cpu_count() or 1
         sample = ("%d timed + %d warm-up full train steps (fwd+bwd+update) on %d images of the same 512x512 workload; "
                   "the GPU arm's step has %d images" % (k, w, a.cpu_sample, B))
@@ -398,7 +398,7 @@ def main():
             out["secondary"] = sec
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
-            v, dt = cpu_baseline(a.workload, a.cpu_sample)
+            v, dt = cpu_baseline(a.workload, a.cpu_sample, lr=a.lr)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                                    "sample": "%d images of the same workload, 1 warm-up + 1 timed full step "
                                              "(%.1f s/step)" % (a.cpu_sample, dt)}
