@@ -247,7 +247,7 @@ class Pix2Pix(object):
         """One train_fn / loss_fn evaluation on float32 NCHW DEVICE tensors (Yd may be None for a model without the
         pix2pix stage); the five losses stay on the device in self.losses (no host synchronisation).
 
-        On a CUDA device the ~1000 kernel launches of a step are captured once into a CUDA graph per
+        On a CUDA device the 200-650 kernel launches of a step are captured once into a CUDA graph per
         (batch size, train flag) -- after two eager warm-up calls that size every buffer -- and replayed
         afterwards, so the host cost of a step is one graph launch (all buffers are static, tensor maps and
         descriptors are kernel arguments, the learning rate is read from device memory).  Set
